@@ -1,0 +1,217 @@
+// apply.cu -- fused per-pixel pass of the reduction chain (K3) and small elementwise helpers
+//
+// reduce_apply_kernel: one pass raw -> reduced
+//   v = f32(raw) * gain[chan]                 gain_corr      blackbox.py:7460
+//   v = f32(f64(v) - vos_fit[chan][row])      os_corr        blackbox.py:6553 / 6556
+//   v = f32(f64(v) - oscan[chan][col])        os_corr        blackbox.py:6844
+//   crop to the data sections                 os_corr        blackbox.py:6847
+//   v = v - mbias                             master bias    blackbox.py:1679
+//   non-finite -> 0, 'bad' if unmasked        mask_init      blackbox.py:4408-4414
+//   sat = f64(v) >= satlevel[chan]            mask_init      blackbox.py:4494, 4538
+//   v = v / mflat                             master flat    blackbox.py:1825
+// Every step is a separately rounded IEEE operation (library built with -fmad=false), so the
+// result is bit-identical to numpy's given identical fit vectors.
+//
+// HBM-bound: per output pixel 2 B (u16 raw) + 4 (mbias) + 4 (mflat) + 1 (bpm) read, 4 + 1
+// written.  Each thread owns 4 consecutive pixels: 8-byte raw load, 16-byte f32 loads/stores,
+// 4-byte mask load/store; fit vectors come from L1/L2.
+#include "bbx_common.cuh"
+
+struct ApplyArgs {
+    const double *vos_fit;     // [16][dy] or null
+    const double *oscan;       // [16][xsize_chan] or null
+    const float *mbias;        // [red] or null
+    const float *mflat;        // [red] or null
+    const uint8_t *bpm;        // [red] or null
+    const double *satlevel;    // [16] device, or null
+    float *out_img;            // [red]
+    uint8_t *out_mask;         // [red] or null
+    int bit_bad, bit_sat;
+};
+
+template <typename T> struct RawVec4;
+template <> struct RawVec4<uint16_t> {
+    static __device__ __forceinline__ void load(const uint16_t *p, float v[4]) {
+        const uint2 u = ld_stream_u2(p);
+        v[0] = (float)(u.x & 0xffffu); v[1] = (float)(u.x >> 16);
+        v[2] = (float)(u.y & 0xffffu); v[3] = (float)(u.y >> 16);
+    }
+};
+template <> struct RawVec4<float> {
+    static __device__ __forceinline__ void load(const float *p, float v[4]) {
+        const uint4 u = ld_stream_u4(p);
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y);
+        v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void apply_px(float &v, uint8_t &m, bool have_mask, float gn, double fitv,
+                                         double osc, bool has_bias, float mb, bool has_flat, float mf,
+                                         bool has_sat, double satl, int bit_bad, int bit_sat)
+{
+    v = v * gn;
+    v = sub_f64(v, fitv);
+    v = sub_f64(v, osc);
+    if (has_bias) v = v - mb;
+    if (have_mask) {
+        if (!isfinite(v)) { v = 0.f; if (m == 0) m |= (uint8_t)bit_bad; }
+        if (has_sat && (double)v >= satl) m |= (uint8_t)(bit_sat | BBX_TMP_SAT);
+    }
+    if (has_flat) v = v / mf;
+}
+
+// VEC = 4: xsize_chan % 4 == 0 and all row starts suitably aligned; VEC = 1: generic
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+reduce_apply_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a)
+{
+    const int RW = g.nx * g.xsize_chan;                 // reduced width
+    const int RH = g.ny * g.ysize_chan;
+    const int groups_per_row = RW / VEC;
+    const long long total = (long long)RH * groups_per_row;
+    const bool have_mask = a.out_mask != nullptr;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
+         gi += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(gi / groups_per_row);
+        const int x = (int)(gi - (long long)y * groups_per_row) * VEC;
+        const int r = y / g.ysize_chan, ly = y - r * g.ysize_chan;
+        const int c = x / g.xsize_chan, lx = x - c * g.xsize_chan;
+        const int ch = r * g.nx + c;
+        const int rr = (r == 0 ? g.data_y0_bot : g.data_y0_top) + ly;
+        const size_t ro = (size_t)rr * g.W + (size_t)c * g.dx + lx;
+        const size_t oo = (size_t)y * RW + x;
+        const float gn = gain.v[ch];
+        const double fitv = a.vos_fit ? a.vos_fit[(size_t)ch * g.dy + (rr - r * g.dy)] : 0.0;
+        const double satl = a.satlevel ? a.satlevel[ch] : 0.0;
+        float v[VEC], mb[VEC], mf[VEC];
+        uint8_t m[VEC];
+        if (VEC == 4) {
+            RawVec4<T>::load(raw + ro, v);
+            if (a.mbias) { const uint4 u = ld_stream_u4(a.mbias + oo); mb[0] = __uint_as_float(u.x); mb[1] = __uint_as_float(u.y); mb[2] = __uint_as_float(u.z); mb[3] = __uint_as_float(u.w); }
+            if (a.mflat) { const uint4 u = ld_stream_u4(a.mflat + oo); mf[0] = __uint_as_float(u.x); mf[1] = __uint_as_float(u.y); mf[2] = __uint_as_float(u.z); mf[3] = __uint_as_float(u.w); }
+            uint32_t mm = 0;
+            if (a.bpm) mm = *reinterpret_cast<const uint32_t *>(a.bpm + oo);
+#pragma unroll
+            for (int k = 0; k < 4; k++) m[k] = (uint8_t)(mm >> (8 * k));
+        } else {
+            v[0] = raw_to_f32<T>(raw[ro]);
+            if (a.mbias) mb[0] = a.mbias[oo];
+            if (a.mflat) mf[0] = a.mflat[oo];
+            m[0] = a.bpm ? a.bpm[oo] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            const double osc = a.oscan ? a.oscan[(size_t)ch * g.xsize_chan + lx + k] : 0.0;
+            apply_px<T>(v[k], m[k], have_mask, gn, fitv, osc, a.mbias != nullptr, mb[k], a.mflat != nullptr, mf[k],
+                        a.satlevel != nullptr, satl, a.bit_bad, a.bit_sat);
+        }
+        if (VEC == 4) {
+            st_stream_u4(a.out_img + oo, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+            if (have_mask) st_stream_u32(a.out_mask + oo, (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24));
+        } else {
+            a.out_img[oo] = v[0];
+            if (have_mask) a.out_mask[oo] = m[0];
+        }
+    }
+}
+
+__global__ void satlevels_kernel(ChanF64 sat_e, const double *__restrict__ biasm, double *__restrict__ out)
+{
+    const int i = threadIdx.x;
+    if (i < BBX_NCHAN) out[i] = sat_e.v[i] - biasm[i];
+}
+
+__global__ void __launch_bounds__(256) gain_corr_kernel(float *__restrict__ raw, bbx_geom g, ChanF32 gain)
+{
+    const long long total = (long long)g.H * g.W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / g.W), x = (int)(i - (long long)y * g.W);
+        const int ch = (y / g.dy) * g.nx + x / g.dx;
+        raw[i] = raw[i] * gain.v[ch];
+    }
+}
+
+__global__ void __launch_bounds__(256) binary_inplace_kernel(float *__restrict__ a, const float *__restrict__ b, size_t n, int op)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        a[i] = (op == 0) ? a[i] - b[i] : a[i] / b[i];
+}
+
+__global__ void __launch_bounds__(256) mask_or_kernel(uint8_t *__restrict__ mask, const uint8_t *__restrict__ flag, size_t n, int bit)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (flag[i]) mask[i] |= (uint8_t)bit;
+}
+
+static inline bool aligned_to(const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
+
+extern "C" int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                                const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
+                                const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
+                                float *out_img, uint8_t *out_mask, void *stream)
+{
+    BBX_REQUIRE(g && raw && out_img, "bbx_reduce_apply: null raw / geometry / output");
+    BBX_REQUIRE(g->ny == 2 && g->nx * g->ny == BBX_NCHAN, "bbx_reduce_apply: expected 2 x 8 channels");
+    BBX_REQUIRE(out_mask == nullptr || bits != nullptr, "bbx_reduce_apply: mask output needs the mask bit values");
+    BBX_REQUIRE((const void *)out_img != raw, "bbx_reduce_apply: output must not alias the raw frame");
+    ChanF32 gn;
+    for (int i = 0; i < BBX_NCHAN; i++) gn.v[i] = gain_h ? gain_h[i] : 1.0f;
+    ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits ? bits->bad : 0, bits ? bits->saturated : 0};
+    const size_t esz = raw_type == BBX_RAW_U16 ? 2 : 4;
+    const long long RW = (long long)g->nx * g->xsize_chan, RH = (long long)g->ny * g->ysize_chan;
+    const bool vec4 = (g->xsize_chan % 4 == 0) && (g->dx % 4 == 0) && (g->W % 4 == 0) &&
+                      aligned_to(raw, 4 * esz) && aligned_to(mbias, 16) && aligned_to(mflat, 16) &&
+                      aligned_to(out_img, 16) && aligned_to(bpm, 4) && aligned_to(out_mask, 4);
+    const long long groups = RH * RW / (vec4 ? 4 : 1);
+    const int blocks = (int)((groups + 255) / 256 < (long long)BBX_SM_COUNT * 16 ? (groups + 255) / 256 : BBX_SM_COUNT * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (raw_type == BBX_RAW_U16) {
+        if (vec4) reduce_apply_kernel<uint16_t, 4><<<blocks, 256, 0, s>>>((const uint16_t *)raw, *g, gn, a);
+        else reduce_apply_kernel<uint16_t, 1><<<blocks, 256, 0, s>>>((const uint16_t *)raw, *g, gn, a);
+    } else {
+        if (vec4) reduce_apply_kernel<float, 4><<<blocks, 256, 0, s>>>((const float *)raw, *g, gn, a);
+        else reduce_apply_kernel<float, 1><<<blocks, 256, 0, s>>>((const float *)raw, *g, gn, a);
+    }
+    BBX_CHECK_LAUNCH("bbx_reduce_apply");
+    return 0;
+}
+
+extern "C" int bbx_satlevels(const double *sat_e_h, const double *biasm, double *out_satlevel, void *stream)
+{
+    BBX_REQUIRE(sat_e_h && biasm && out_satlevel, "bbx_satlevels: null argument");
+    ChanF64 se;
+    for (int i = 0; i < BBX_NCHAN; i++) se.v[i] = sat_e_h[i];
+    satlevels_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(se, biasm, out_satlevel);
+    BBX_CHECK_LAUNCH("bbx_satlevels");
+    return 0;
+}
+
+extern "C" int bbx_gain_corr(float *raw, const bbx_geom *g, const float *gain_h, void *stream)
+{
+    BBX_REQUIRE(raw && g && gain_h, "bbx_gain_corr: null argument");
+    ChanF32 gn;
+    for (int i = 0; i < BBX_NCHAN; i++) gn.v[i] = gain_h[i];
+    gain_corr_kernel<<<BBX_SM_COUNT * 16, 256, 0, (cudaStream_t)stream>>>(raw, *g, gn);
+    BBX_CHECK_LAUNCH("bbx_gain_corr");
+    return 0;
+}
+
+extern "C" int bbx_binary_inplace(float *a, const float *b, size_t n, int op, void *stream)
+{
+    BBX_REQUIRE(a && b, "bbx_binary_inplace: null argument");
+    BBX_REQUIRE(op == 0 || op == 1, "bbx_binary_inplace: op %d (0 = subtract, 1 = divide)", op);
+    if (n == 0) return 0;
+    binary_inplace_kernel<<<BBX_SM_COUNT * 16, 256, 0, (cudaStream_t)stream>>>(a, b, n, op);
+    BBX_CHECK_LAUNCH("bbx_binary_inplace");
+    return 0;
+}
+
+extern "C" int bbx_mask_or(uint8_t *mask, const uint8_t *flag, size_t n, int bit, void *stream)
+{
+    BBX_REQUIRE(mask && flag, "bbx_mask_or: null argument");
+    if (n == 0) return 0;
+    mask_or_kernel<<<BBX_SM_COUNT * 16, 256, 0, (cudaStream_t)stream>>>(mask, flag, n, bit);
+    BBX_CHECK_LAUNCH("bbx_mask_or");
+    return 0;
+}

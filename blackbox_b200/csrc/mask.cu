@@ -1,0 +1,486 @@
+// mask.cu -- mask_init morphology (reference: blackbox.py:4473-4566, fill_sat_holes 4584-4596),
+// connected-component counts (ndimage.label, blackbox.py:4354, 4544) and mask_header counts.
+//
+// All integer / byte work, HBM-bound.  "Computed saturation" (mask_sat of the reference, i.e.
+// data >= satlevel, as opposed to a 'saturated' bit that a bad-pixel mask might carry) travels
+// in the spare bit BBX_TMP_SAT (0x80) of the mask; bbx_fill_sat_holes clears it at the end.
+#include <cooperative_groups.h>
+#include "bbx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+
+// --------------------------------------------------------------------------------------------
+// crosstalk-victim bit: a pixel is flagged if the pixel at the same tile position (y mirrored
+// between the CCD halves) is saturated in any OTHER channel.  One thread owns the 16 mirrored
+// words (4 pixels each) of one tile position, so every byte is read and written exactly once.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+xtalk_victim_kernel(uint8_t *__restrict__ mask, int W, int ysc, int xsc, uint32_t bit_xtalk)
+{
+    const int words = xsc / 4;
+    const long long total = (long long)ysc * words;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ly = (int)(t / words), lx = (int)(t - (long long)ly * words) * 4;
+        uint32_t w[16], tot = 0;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+            const size_t off = (size_t)row * W + (size_t)(c & 7) * xsc + lx;
+            w[c] = *reinterpret_cast<const uint32_t *>(mask + off);
+            tot += (w[c] >> 7) & 0x01010101u;           // per-byte count of saturated sources
+        }
+        if (tot == 0) continue;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const uint32_t others = tot - ((w[c] >> 7) & 0x01010101u);
+            uint32_t nz = others | (others >> 1) | (others >> 2) | (others >> 3) | (others >> 4);
+            nz &= 0x01010101u;
+            if (nz) {
+                const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+                const size_t off = (size_t)row * W + (size_t)(c & 7) * xsc + lx;
+                *reinterpret_cast<uint32_t *>(mask + off) = w[c] | (nz * bit_xtalk);
+            }
+        }
+    }
+}
+
+// generic (any xsize_chan): one thread per tile position and pixel
+__global__ void __launch_bounds__(256)
+xtalk_victim_scalar_kernel(uint8_t *__restrict__ mask, int W, int ysc, int xsc, uint32_t bit_xtalk)
+{
+    const long long total = (long long)ysc * xsc;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ly = (int)(t / xsc), lx = (int)(t - (long long)ly * xsc);
+        uint8_t w[16];
+        int tot = 0;
+        for (int c = 0; c < 16; c++) {
+            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+            w[c] = mask[(size_t)row * W + (size_t)(c & 7) * xsc + lx];
+            tot += (w[c] >> 7) & 1;
+        }
+        if (tot == 0) continue;
+        for (int c = 0; c < 16; c++)
+            if (tot - ((w[c] >> 7) & 1) > 0) {
+                const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+                mask[(size_t)row * W + (size_t)(c & 7) * xsc + lx] = w[c] | (uint8_t)bit_xtalk;
+            }
+    }
+}
+
+// saturated-connected: 8-neighbour of a saturated pixel, not itself saturated (zero border)
+__global__ void __launch_bounds__(256)
+satcon_kernel(uint8_t *__restrict__ mask, int H, int W, uint32_t bit_satcon)
+{
+    const long long total = (long long)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+        const uint8_t m = mask[p];
+        if (m & BBX_TMP_SAT) continue;
+        bool near = false;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                near |= (mask[(size_t)yy * W + xx] & BBX_TMP_SAT) != 0;
+            }
+        }
+        if (near) mask[p] = m | (uint8_t)bit_satcon;
+    }
+}
+
+extern "C" int bbx_mask_sat_neighbours(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                       const bbx_maskbits *bits, void *stream)
+{
+    BBX_REQUIRE(mask && bits, "bbx_mask_sat_neighbours: null argument");
+    BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_mask_sat_neighbours: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
+    BBX_REQUIRE(((bits->bad | bits->cosmic | bits->saturated | bits->satcon | bits->sattrail | bits->edge | bits->crosstalk) & 0x80) == 0,
+                "bbx_mask_sat_neighbours: mask value 128 is reserved for internal use");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = BBX_SM_COUNT * 8;
+    if (xsize_chan % 4 == 0 && ((uintptr_t)mask % 4) == 0)
+        xtalk_victim_kernel<<<blocks, 256, 0, s>>>(mask, W, ysize_chan, xsize_chan, (uint32_t)bits->crosstalk);
+    else
+        xtalk_victim_scalar_kernel<<<blocks, 256, 0, s>>>(mask, W, ysize_chan, xsize_chan, (uint32_t)bits->crosstalk);
+    BBX_CHECK_LAUNCH("xtalk_victim_kernel");
+    satcon_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, H, W, (uint32_t)bits->satcon);
+    BBX_CHECK_LAUNCH("satcon_kernel");
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// fill_sat_holes
+//   m      = saturated | saturated-connected bits
+//   closed = erode3(dilate3(m)), outside the image counts as 0 in both steps
+//   filled = closed plus every background region not 8-connected to the image border
+//   mask[filled & mask == 0] = saturated-connected
+// State image S (work): 0 = closed foreground, 1 = background, 2 = background known to reach
+// the border.  Background pixels with a free straight line to the border in +-x or +-y are
+// resolved implicitly from the per-row / per-column foreground extents; only the remaining
+// "enclosed in all four directions" pixels are propagated (tile-local fixed point inside a
+// persistent cooperative kernel, grid-wide rounds until nothing changes).
+// --------------------------------------------------------------------------------------------
+struct HoleWork {
+    uint8_t *S;          // [H*W]
+    int *rowmin, *rowmax, *colmin, *colmax;
+    int *tiles;          // active tile list
+    int *tile_flag;      // per tile: already on the list
+    int *counters;       // [0] number of active tiles, [1] changed flag, [2] any foreground
+    int max_tiles;
+};
+#define HOLE_TILE 64
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static HoleWork carve_hole_work(void *work, int H, int W)
+{
+    HoleWork hw;
+    uint8_t *p = (uint8_t *)work;
+    hw.S = p; p += align_up((size_t)H * W, 256);
+    hw.rowmin = (int *)p; p += align_up(sizeof(int) * H, 256);
+    hw.rowmax = (int *)p; p += align_up(sizeof(int) * H, 256);
+    hw.colmin = (int *)p; p += align_up(sizeof(int) * W, 256);
+    hw.colmax = (int *)p; p += align_up(sizeof(int) * W, 256);
+    hw.max_tiles = ceil_div(H, HOLE_TILE) * ceil_div(W, HOLE_TILE);
+    hw.tiles = (int *)p; p += align_up(sizeof(int) * hw.max_tiles, 256);
+    hw.tile_flag = (int *)p; p += align_up(sizeof(int) * hw.max_tiles, 256);
+    hw.counters = (int *)p;
+    return hw;
+}
+
+extern "C" size_t bbx_fill_holes_work_bytes(int H, int W)
+{
+    const size_t tiles = (size_t)ceil_div(H, HOLE_TILE) * ceil_div(W, HOLE_TILE);
+    return align_up((size_t)H * W, 256) + 2 * align_up(sizeof(int) * H, 256) + 2 * align_up(sizeof(int) * W, 256) +
+           2 * align_up(sizeof(int) * tiles, 256) + 256;
+}
+
+__global__ void hole_init_kernel(HoleWork hw, int H, int W)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < H) { hw.rowmin[i] = W; hw.rowmax[i] = -1; }
+    if (i < W) { hw.colmin[i] = H; hw.colmax[i] = -1; }
+    if (i < 4) hw.counters[i] = 0;
+}
+
+// closing + state image + foreground extents.  32x32 outputs per block, halo 2.
+__global__ void __launch_bounds__(1024)
+hole_close_kernel(const uint8_t *__restrict__ mask, HoleWork hw, int H, int W, uint32_t mbits)
+{
+    __shared__ uint8_t m[36][36];
+    __shared__ uint8_t d[34][34];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int i = ty * 32 + tx; i < 36 * 36; i += 1024) {
+        const int yy = i / 36, xx = i - yy * 36;
+        const int gy = y0 + yy - 2, gx = x0 + xx - 2;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (mask[(size_t)gy * W + gx] & mbits) != 0;
+        m[yy][xx] = v;
+    }
+    __syncthreads();
+    for (int i = ty * 32 + tx; i < 34 * 34; i += 1024) {
+        const int yy = i / 34, xx = i - yy * 34;            // dilated value at (y0+yy-1, x0+xx-1)
+        const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) v |= m[yy + a][xx + b];
+        }
+        d[yy][xx] = v;      // positions outside the image stay 0: erosion fails next to the border
+    }
+    __syncthreads();
+    const int gy = y0 + ty, gx = x0 + tx;
+    if (gy < H && gx < W) {
+        uint8_t e = 1;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) e &= d[ty + a][tx + b];
+        hw.S[(size_t)gy * W + gx] = e ? 0 : 1;
+        if (e) {
+            atomicMin(&hw.rowmin[gy], gx); atomicMax(&hw.rowmax[gy], gx);
+            atomicMin(&hw.colmin[gx], gy); atomicMax(&hw.colmax[gx], gy);
+            hw.counters[2] = 1;
+        }
+    }
+}
+
+__device__ __forceinline__ bool hole_free_line(const HoleWork &hw, int y, int x)
+{
+    return x < hw.rowmin[y] || x > hw.rowmax[y] || y < hw.colmin[x] || y > hw.colmax[x];
+}
+
+// one block per image row: scan only the span between the first and last foreground pixel and
+// register tiles that hold unresolved background
+__global__ void __launch_bounds__(256)
+hole_candidates_kernel(HoleWork hw, int H, int W, int *__restrict__ tile_flag)
+{
+    const int y = blockIdx.x;
+    const int a = hw.rowmin[y], b = hw.rowmax[y];
+    if (a > b) return;
+    const int tiles_x = (W + HOLE_TILE - 1) / HOLE_TILE;
+    for (int x = a + threadIdx.x; x <= b; x += blockDim.x) {
+        if (hw.S[(size_t)y * W + x] == 1 && !hole_free_line(hw, y, x)) {
+            const int t = (y / HOLE_TILE) * tiles_x + x / HOLE_TILE;
+            if (atomicExch(&tile_flag[t], 1) == 0) {
+                const int slot = atomicAdd(&hw.counters[0], 1);
+                hw.tiles[slot] = t;
+            }
+        }
+    }
+}
+
+// persistent cooperative kernel: propagate "reaches the border" through unresolved background
+__global__ void __launch_bounds__(256)
+hole_propagate_kernel(HoleWork hw, int H, int W, int max_rounds, int32_t *unconverged)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint8_t t[HOLE_TILE + 2][HOLE_TILE + 2];
+    __shared__ int s_changed, s_any;
+    const int ntiles = hw.counters[0];
+    const int tiles_x = (W + HOLE_TILE - 1) / HOLE_TILE;
+    int round = 0;
+    if (ntiles == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) *unconverged = 0; return; }
+    for (;;) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) hw.counters[1] = 0;
+        grid.sync();
+        for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+            const int tile = hw.tiles[ti];
+            const int y0 = (tile / tiles_x) * HOLE_TILE, x0 = (tile % tiles_x) * HOLE_TILE;
+            // load tile + 1-pixel halo: 0 fg, 1 unknown, 2 outside (explicit or implicit)
+            for (int i = threadIdx.x; i < (HOLE_TILE + 2) * (HOLE_TILE + 2); i += blockDim.x) {
+                const int yy = i / (HOLE_TILE + 2), xx = i - yy * (HOLE_TILE + 2);
+                const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+                uint8_t v = 2;                                  // outside the image = border value 1
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    v = hw.S[(size_t)gy * W + gx];
+                    if (v == 1 && hole_free_line(hw, gy, gx)) v = 2;
+                }
+                t[yy][xx] = v;
+            }
+            if (threadIdx.x == 0) s_any = 0;
+            __syncthreads();
+            for (;;) {
+                if (threadIdx.x == 0) s_changed = 0;
+                __syncthreads();
+                for (int i = threadIdx.x; i < HOLE_TILE * HOLE_TILE; i += blockDim.x) {
+                    const int yy = i / HOLE_TILE + 1, xx = i % HOLE_TILE + 1;
+                    if (t[yy][xx] != 1) continue;
+                    const bool reach = t[yy - 1][xx - 1] == 2 || t[yy - 1][xx] == 2 || t[yy - 1][xx + 1] == 2 ||
+                                       t[yy][xx - 1] == 2 || t[yy][xx + 1] == 2 ||
+                                       t[yy + 1][xx - 1] == 2 || t[yy + 1][xx] == 2 || t[yy + 1][xx + 1] == 2;
+                    if (reach) { t[yy][xx] = 2; s_changed = 1; }
+                }
+                __syncthreads();
+                const int ch = s_changed;
+                __syncthreads();
+                if (!ch) break;
+                if (threadIdx.x == 0) s_any = 1;
+            }
+            __syncthreads();
+            if (s_any) {
+                for (int i = threadIdx.x; i < HOLE_TILE * HOLE_TILE; i += blockDim.x) {
+                    const int yy = i / HOLE_TILE, xx = i % HOLE_TILE;
+                    const int gy = y0 + yy, gx = x0 + xx;
+                    if (gy < H && gx < W && t[yy + 1][xx + 1] == 2) hw.S[(size_t)gy * W + gx] = 2;
+                }
+                if (threadIdx.x == 0) hw.counters[1] = 1;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        round++;
+        const int changed = hw.counters[1];
+        if (!changed || round >= max_rounds) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) *unconverged = changed ? 1 : 0;
+            break;
+        }
+        grid.sync();            // everybody has read the flag before it is reset
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hole_commit_kernel(uint8_t *__restrict__ mask, HoleWork hw, int H, int W, uint32_t bit_satcon,
+                   const int32_t *__restrict__ unconverged)
+{
+    if (*unconverged) return;         // bbx_fill_holes_more has to finish the propagation first
+    const long long total = (long long)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        uint8_t m = mask[p];
+        const uint8_t m0 = m;
+        m &= (uint8_t)~BBX_TMP_SAT;
+        if (m == 0) {
+            const uint8_t s = hw.S[p];
+            bool filled = (s == 0);
+            if (s == 1) {
+                const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+                filled = !hole_free_line(hw, y, x);
+            }
+            if (filled) m = (uint8_t)bit_satcon;
+        }
+        if (m != m0) mask[p] = m;
+    }
+}
+
+static int launch_propagate(HoleWork hw, int H, int W, int rounds, int32_t *unconverged, cudaStream_t s)
+{
+    int per_sm = 0;
+    BBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hole_propagate_kernel, 256, 0));
+    BBX_REQUIRE(per_sm > 0, "hole_propagate_kernel cannot be made resident");
+    int dev = 0, sms = 0;
+    BBX_CUDA(cudaGetDevice(&dev));
+    BBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * (per_sm > 2 ? 2 : per_sm);
+    void *args[] = {&hw, &H, &W, &rounds, &unconverged};
+    BBX_CUDA(cudaLaunchCooperativeKernel((const void *)hole_propagate_kernel, dim3(blocks), dim3(256), args, 0, s));
+    return 0;
+}
+
+extern "C" int bbx_fill_sat_holes(uint8_t *mask, int H, int W, const bbx_maskbits *bits, void *work,
+                                  int rounds, int32_t *unconverged, void *stream)
+{
+    BBX_REQUIRE(mask && bits && work && unconverged, "bbx_fill_sat_holes: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    HoleWork hw = carve_hole_work(work, H, W);
+    const int n = H > W ? H : W;
+    hole_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(hw, H, W);
+    BBX_CHECK_LAUNCH("hole_init_kernel");
+    const uint32_t mbits = (uint32_t)(bits->saturated | bits->satcon);
+    hole_close_kernel<<<dim3(ceil_div(W, 32), ceil_div(H, 32)), dim3(32, 32), 0, s>>>(mask, hw, H, W, mbits);
+    BBX_CHECK_LAUNCH("hole_close_kernel");
+    BBX_CUDA(cudaMemsetAsync(hw.tile_flag, 0, sizeof(int) * hw.max_tiles, s));
+    hole_candidates_kernel<<<H, 256, 0, s>>>(hw, H, W, hw.tile_flag);
+    BBX_CHECK_LAUNCH("hole_candidates_kernel");
+    if (launch_propagate(hw, H, W, rounds, unconverged, s)) return -2;
+    hole_commit_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, hw, H, W, (uint32_t)bits->satcon, unconverged);
+    BBX_CHECK_LAUNCH("hole_commit_kernel");
+    return 0;
+}
+
+extern "C" int bbx_fill_holes_more(uint8_t *mask, int H, int W, const bbx_maskbits *bits, void *work,
+                                   int rounds, int32_t *unconverged, void *stream)
+{
+    BBX_REQUIRE(mask && bits && work && unconverged, "bbx_fill_holes_more: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    HoleWork hw = carve_hole_work(work, H, W);
+    if (launch_propagate(hw, H, W, rounds, unconverged, s)) return -2;
+    hole_commit_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, hw, H, W, (uint32_t)bits->satcon, unconverged);
+    BBX_CHECK_LAUNCH("hole_commit_kernel");
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// 8-connected component count (union-find with atomicMin, label = linear pixel index)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int *L, int i)
+{
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int *L, int a, int b)
+{
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(256)
+ccl_init_kernel(const uint8_t *__restrict__ mask, uint32_t bit, long long total, int *__restrict__ L)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x)
+        if (mask[p] & bit) L[p] = (int)p;
+}
+
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const uint8_t *__restrict__ mask, uint32_t bit, int H, int W, int *__restrict__ L)
+{
+    const long long total = (long long)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        if (!(mask[p] & bit)) continue;
+        const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+        if (x > 0 && (mask[p - 1] & bit)) uf_union(L, (int)p, (int)p - 1);
+        if (y > 0) {
+            const long long q = p - W;
+            if (mask[q] & bit) uf_union(L, (int)p, (int)q);
+            if (x > 0 && (mask[q - 1] & bit)) uf_union(L, (int)p, (int)q - 1);
+            if (x + 1 < W && (mask[q + 1] & bit)) uf_union(L, (int)p, (int)q + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_count_kernel(const uint8_t *__restrict__ mask, uint32_t bit, long long total, const int *__restrict__ L,
+                 int32_t *__restrict__ out)
+{
+    int c = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x)
+        if ((mask[p] & bit) && L[p] == (int)p) c++;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+extern "C" int bbx_count_objects(const uint8_t *mask, int bit, int H, int W, int32_t *labels,
+                                 int32_t *out_count, void *stream)
+{
+    BBX_REQUIRE(mask && labels && out_count, "bbx_count_objects: null argument");
+    BBX_REQUIRE((long long)H * W < 2147483647LL, "bbx_count_objects: image too large for 32-bit labels");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (long long)H * W;
+    BBX_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), s));
+    ccl_init_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, (uint32_t)bit, total, labels);
+    BBX_CHECK_LAUNCH("ccl_init_kernel");
+    ccl_merge_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, (uint32_t)bit, H, W, labels);
+    BBX_CHECK_LAUNCH("ccl_merge_kernel");
+    ccl_count_kernel<<<BBX_SM_COUNT * 16, 256, 0, s>>>(mask, (uint32_t)bit, total, labels, out_count);
+    BBX_CHECK_LAUNCH("ccl_count_kernel");
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// per-bit pixel counts
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_counts_kernel(const uint8_t *__restrict__ mask, size_t n, unsigned long long *__restrict__ out)
+{
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = mask[p];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] += (m >> k) & 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int v = warp_sum(c[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&out[k], (unsigned long long)v);
+    }
+}
+
+extern "C" int bbx_mask_counts(const uint8_t *mask, size_t n, unsigned long long *out_counts, void *stream)
+{
+    BBX_REQUIRE(mask && out_counts, "bbx_mask_counts: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    BBX_CUDA(cudaMemsetAsync(out_counts, 0, 8 * sizeof(unsigned long long), s));
+    if (n == 0) return 0;
+    mask_counts_kernel<<<BBX_SM_COUNT * 8, 256, 0, s>>>(mask, n, out_counts);
+    BBX_CHECK_LAUNCH("mask_counts_kernel");
+    return 0;
+}

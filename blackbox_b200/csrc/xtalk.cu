@@ -1,0 +1,90 @@
+// xtalk.cu -- 16x16-channel crosstalk correction (reference: xtalk_corr, blackbox.py:7138-7258)
+//
+//   S_s      = data_s * ((data_s > 0) & !bad & !cosmic)                    float32
+//   corr_v   = sum_{s same CCD half} c[s][v] S_s(y, x)  +  sum_{s other half} c[s][v] S_s(H-1-y, x)
+//              (two 8-term float64 dot products, added; np.matmul of f32 x f64 -> f64)
+//   data_v   = f32( f64(data_v) - corr_v * !edge )
+// All sources are the UNCORRECTED pixels (the reference builds the correction cube first).
+//
+// One thread owns a tile position (ly, lx..lx+1) in all 16 channels: the 8 bottom channels at
+// row ly and the 8 top channels at the mirrored row.  Those 32 pixels are exactly each other's
+// sources, so every pixel of the frame is read once and written once (HBM-bound: 4+1 B read,
+// 4 B written per pixel; 16 float64 FMAs per pixel).
+#include "bbx_common.cuh"
+
+struct XtalkCoef { double c[16][16]; };   // [source][victim], kernel parameter (constant bank)
+
+template <int PX>
+__global__ void __launch_bounds__(256)
+xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int xsc, XtalkCoef k,
+             uint32_t bits_src_bad, uint32_t bit_edge)
+{
+    const int groups = xsc / PX;
+    const long long total = (long long)ysc * groups;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ly = (int)(t / groups), lx = (int)(t - (long long)ly * groups) * PX;
+        float v[16][PX];
+        float S[16][PX];
+        uint32_t vic_ok = 0;                               // bit (c*PX + p)
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+            const size_t off = (size_t)row * W + (size_t)(c & 7) * xsc + lx;
+            if (PX == 2) {
+                const float2 f = *reinterpret_cast<const float2 *>(img + off);
+                v[c][0] = f.x; v[c][PX - 1] = f.y;
+            } else {
+                v[c][0] = img[off];
+            }
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                const uint32_t m = mask ? mask[off + p] : 0u;
+                const bool src_ok = (v[c][p] > 0.0f) && !(m & bits_src_bad);
+                S[c][p] = v[c][p] * (src_ok ? 1.0f : 0.0f);
+                if (!(m & bit_edge)) vic_ok |= 1u << (c * PX + p);
+            }
+        }
+#pragma unroll
+        for (int vch = 0; vch < 16; vch++) {
+            float outv[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                // same-half sources first (quadrant q=0 / q=3), then the mirrored half
+                const int same0 = (vch < 8) ? 0 : 8, other0 = 8 - same0;
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) a = fma((double)S[same0 + s][p], k.c[same0 + s][vch], a);
+#pragma unroll
+                for (int s = 0; s < 8; s++) b = fma((double)S[other0 + s][p], k.c[other0 + s][vch], b);
+                double corr = 0.0 + a;
+                corr = corr + b;
+                corr = corr * (((vic_ok >> (vch * PX + p)) & 1u) ? 1.0 : 0.0);
+                outv[p] = (float)((double)v[vch][p] - corr);
+            }
+            const int row = (vch < 8) ? ly : (ysc + (ysc - 1 - ly));
+            const size_t off = (size_t)row * W + (size_t)(vch & 7) * xsc + lx;
+            if (PX == 2) *reinterpret_cast<float2 *>(img + off) = make_float2(outv[0], outv[PX - 1]);
+            else img[off] = outv[0];
+        }
+    }
+}
+
+extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                         const double *coeffs_h, const bbx_maskbits *bits, void *stream)
+{
+    BBX_REQUIRE(img && coeffs_h && bits, "bbx_xtalk: null argument");
+    BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_xtalk: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
+    XtalkCoef k;
+    for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[s][v] = coeffs_h[s * 16 + v];
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
+    const bool px2 = (xsize_chan % 2 == 0) && (W % 2 == 0) && ((uintptr_t)img % 8) == 0;
+    const long long total = (long long)ysize_chan * (xsize_chan / (px2 ? 2 : 1));
+    long long want = (total + 255) / 256;
+    const int blocks = (int)(want < BBX_SM_COUNT * 8 ? want : BBX_SM_COUNT * 8);
+    if (px2) xtalk_kernel<2><<<blocks, 256, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+    else xtalk_kernel<1><<<blocks, 256, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+    BBX_CHECK_LAUNCH("xtalk_kernel");
+    return 0;
+}

@@ -1,0 +1,616 @@
+"""Drop-in replacements for blackbox.py's reduction steps, running on a B200.
+
+Same names, argument meaning and error behaviour (Python exceptions) as the reference:
+
+    gain_corr(data, header, tel=None)                               blackbox.py:7442
+    os_corr(data, header, imgtype, xbin=1, ybin=1, data_limit=2000, tel=None)   :6407
+    mask_init(data, header, filt, imgtype)                          blackbox.py:4375
+    cosmics_corr(data, header, data_mask, header_mask)              blackbox.py:4259
+    xtalk_corr(data, crosstalk_file, data_mask=None)                blackbox.py:7138
+    detect_cosmics(indat, inmask=None, sigclip=..., ...)            astroscrappy 1.0.8
+    master_combine(frames, imgtype, ...)      arithmetic core of master_prep, :4908-4984
+
+``data`` may be a numpy array (copied to the GPU, results copied back / mutated in place
+exactly where the reference mutates) or a CUDA ``torch.Tensor`` (nothing leaves HBM).
+``header`` is any mapping; astropy ``Header`` objects get ``(value, comment)`` tuples.
+The module-global ``tel`` mirrors the reference's global of that name (blackbox.py:141).
+
+All arithmetic happens in libbbx.so (hand-written sm_100a kernels, include/bbx.h); there is
+no CPU fallback.  The only host numerics are FITPACK's smoothing spline (hostfit.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, hostfit, set_bb
+from ._lib import BbxMaskBits, call, query
+from .geometry import Geometry, define_sections
+from .set_bb import get_par
+
+tel = None          # module-global telescope name, as in the reference (blackbox.py:141)
+
+_bpm_registry = {}  # filter -> bad-pixel mask (numpy or CUDA tensor); see set_bad_pixel_mask
+
+
+# -------------------------------------------------------------------------------------------
+# plumbing
+# -------------------------------------------------------------------------------------------
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.BbxUnavailable('no CUDA device: blackbox_b200 has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _to_dev(a, dtype=None):
+    """numpy / tensor -> contiguous CUDA tensor (no copy if already there)."""
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        t = a if a.is_cuda else a.to(_device())
+    else:
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint16:
+            t = torch.from_numpy(a.view(np.int16)).to(_device()).view(torch.uint16)
+        else:
+            t = torch.from_numpy(a).to(_device())
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _harr(values, ctype):
+    return (ctype * len(values))(*values)
+
+
+def _set(header, key, value, comment=None):
+    if header is None:
+        return
+    if comment is not None and hasattr(header, 'comments'):
+        header[key] = (value, comment)
+    else:
+        header[key] = value
+
+
+def _raw_type(t):
+    if t.dtype == torch.uint16 or t.dtype == torch.int16:
+        return 0
+    if t.dtype == torch.float32:
+        return 1
+    raise TypeError('raw frame must be uint16 or float32, got {}'.format(t.dtype))
+
+
+def _bits(tel_):
+    return BbxMaskBits.from_dict(get_par(set_bb.mask_value, tel_))
+
+
+def _tel_kind(tel_):
+    return 0 if str(tel_)[0:2] == 'ML' else 1
+
+
+# -------------------------------------------------------------------------------------------
+# gain
+# -------------------------------------------------------------------------------------------
+def gain_corr(data, header, tel=None):
+    """In place ``data[chan] *= gain[chan]``; header GAIN1..16 (blackbox.py:7442-7465)."""
+    gain = get_par(set_bb.gain, tel)
+    is_np = isinstance(data, np.ndarray)
+    t = _to_dev(data)
+    if t.dtype != torch.float32:
+        raise TypeError('gain_corr expects a float32 frame (as read_hdulist(dtype="float32"))')
+    geom = Geometry.from_raw_shape(tuple(t.shape), tel=tel) if _has_overscan(t.shape, tel) \
+        else _reduced_geometry(tuple(t.shape), tel)
+    g = geom.as_struct()
+    call('bbx_gain_corr', _ptr(t), C.byref(g), _harr([float(x) for x in gain], C.c_float), _stream())
+    if is_np:
+        data[...] = t.cpu().numpy()
+    for i in range(geom.nchans):
+        _set(header, 'GAIN{}'.format(i + 1), gain[i],
+             '[e-/ADU] gain applied to channel {}'.format(i + 1))
+
+
+def _has_overscan(shape, tel_, xbin=1, ybin=1):
+    ysc = get_par(set_bb.ysize_chan, tel_) // ybin
+    xsc = get_par(set_bb.xsize_chan, tel_) // xbin
+    return shape[0] > set_bb.ny * ysc and shape[1] > set_bb.nx * xsc
+
+
+def _reduced_geometry(shape, tel_):
+    """Geometry of a frame without overscans (tile == data section)."""
+    ny, nx = get_par(set_bb.ny, tel_), get_par(set_bb.nx, tel_)
+    H, W = shape
+    if H % ny or W % nx:
+        raise ValueError('frame {} is not divisible into {} x {} channels'.format(shape, ny, nx))
+    dy, dx = H // ny, W // nx
+    return Geometry(H, W, ny, nx, dy, dx, dy, dx, 0, 0, 0, (0, dy), (0, dy))
+
+
+# -------------------------------------------------------------------------------------------
+# overscan
+# -------------------------------------------------------------------------------------------
+class OverscanState:
+    """Device-resident intermediates of the overscan correction of one frame."""
+
+    def __init__(self, geom, device):
+        n, dy, nc = geom.nchans, geom.dy, geom.xsize_chan
+        f64, f32, i32, u8 = torch.float64, torch.float32, torch.int32, torch.uint8
+        z = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        self.geom = geom
+        self.mean_vos = z((n, dy), f64)
+        self.vos_fit = z((n, dy), f64)
+        self.vos_coef = z((n, 8), f64)
+        self.biasm = z((n,), f64)
+        self.vfit_ok = z((n,), i32)
+        self.satcnt = z((n, 2, nc), i32)
+        self.dlevel = z((n,), f64)
+        self.hos_mean = z((n, nc), f32)
+        self.hos_std = z((n, nc), f32)
+        self.hos_n = z((n, nc), i32)
+        self.satcol = z((n, nc), u8)
+        self.std_vos = z((n,), f64)
+        self.oscan = z((n, nc), f64)
+        self.need_spline = z((n, nc), u8)
+        self.fit_status = z((n,), i32)
+        self.satlevel = z((n,), f64)
+
+
+def overscan_enqueue(raw_t, geom, tel_, gain=None, data_limit=2000, state=None):
+    """Enqueue every overscan statistics / fit kernel for one raw frame on the current
+    stream (no synchronisation).  ``gain``: list of 16 gains to apply on the fly (raw counts)
+    or None if ``raw_t`` is already gain-corrected.  Returns the OverscanState."""
+    st = state if state is not None else OverscanState(geom, raw_t.device)
+    g = geom.as_struct()
+    rt = _raw_type(raw_t)
+    gain_h = _harr([float(x) for x in gain], C.c_float) if gain is not None else None
+    s = _stream()
+    kind = _tel_kind(tel_)
+    call('bbx_vos_rowstats', _ptr(raw_t), rt, C.byref(g), gain_h, 3.0, 5, _ptr(st.mean_vos), s)
+    call('bbx_vos_fit', _ptr(st.mean_vos), C.byref(g), int(get_par(set_bb.voscan_poldeg, tel_)), 5.0,
+         _ptr(st.vos_fit), _ptr(st.vos_coef), _ptr(st.biasm), _ptr(st.vfit_ok), s)
+    sat_e = (np.array(get_par(set_bb.satlevel, tel_), dtype=np.float64) *
+             np.array(get_par(set_bb.gain, tel_), dtype=np.float64))
+    sat_e_h = _harr([float(x) for x in sat_e], C.c_double)
+    if kind == 1:
+        lim = get_par(set_bb.hos_sat_ypix_lim, tel_)
+        call('bbx_hos_satcount', _ptr(raw_t), rt, C.byref(g), gain_h, _ptr(st.vos_fit), sat_e_h,
+             int(lim[0]), int(lim[1]), _ptr(st.satcnt), s)
+    call('bbx_hos_stats', _ptr(raw_t), rt, C.byref(g), gain_h, _ptr(st.vos_fit), kind,
+         float(data_limit), _ptr(st.satcnt), _ptr(st.dlevel), _ptr(st.hos_mean), _ptr(st.hos_std),
+         _ptr(st.hos_n), _ptr(st.satcol), s)
+    call('bbx_vos_std', _ptr(raw_t), rt, C.byref(g), gain_h, _ptr(st.vos_fit), _ptr(st.dlevel),
+         _ptr(st.std_vos), s)
+    split_chan = 8 if tel_ == 'BG2' else -1
+    call('bbx_hos_fit', _ptr(st.hos_mean), _ptr(st.hos_std), _ptr(st.hos_n), _ptr(st.satcol),
+         C.byref(g), kind, split_chan, 654, _ptr(st.oscan), _ptr(st.need_spline),
+         _ptr(st.fit_status), s)
+    call('bbx_satlevels', sat_e_h, _ptr(st.biasm), _ptr(st.satlevel), s)
+    return st
+
+
+def overscan_resolve_spline(st, strict):
+    """Host step: evaluate FITPACK's smoothing spline for the columns that need it (all
+    channels if ``strict``) and patch ``st.oscan``.  Synchronises the current stream.
+    Raises RuntimeError if a polynomial fit had too few points (the reference raises from
+    np.polyfit in that case)."""
+    status = st.fit_status.cpu().numpy()
+    if status.any():
+        raise RuntimeError('horizontal-overscan polynomial fit failed for channel(s) {} '
+                           '(too few valid columns)'.format(
+                               [int(i) + 1 for i in np.nonzero(status)[0]]))
+    need = st.need_spline.cpu().numpy().astype(bool)
+    chans = range(st.geom.nchans) if strict else np.nonzero(need.any(axis=1))[0]
+    if len(chans) == 0:
+        return 0
+    mean = st.hos_mean.cpu().numpy()
+    std = st.hos_std.cpu().numpy()
+    n = st.hos_n.cpu().numpy()
+    patched = 0
+    for i in chans:
+        spl = hostfit.hos_spline(mean[i], std[i], n[i])
+        cols = np.nonzero(need[i])[0]
+        if len(cols):
+            vals = torch.from_numpy(np.ascontiguousarray(spl[cols])).to(st.oscan.device)
+            st.oscan[i, torch.from_numpy(cols).to(st.oscan.device)] = vals
+            patched += len(cols)
+    return patched
+
+
+def apply_enqueue(raw_t, geom, tel_, st=None, gain=None, mbias=None, mflat=None, bpm=None,
+                  want_mask=False, out_img=None, out_mask=None):
+    """Enqueue the fused per-pixel pass (include/bbx.h: bbx_reduce_apply)."""
+    g = geom.as_struct()
+    RH, RW = geom.red_shape
+    if out_img is None:
+        out_img = torch.empty((RH, RW), dtype=torch.float32, device=raw_t.device)
+    if want_mask and out_mask is None:
+        out_mask = torch.empty((RH, RW), dtype=torch.uint8, device=raw_t.device)
+    bits = _bits(tel_)
+    gain_h = _harr([float(x) for x in gain], C.c_float) if gain is not None else None
+    call('bbx_reduce_apply', _ptr(raw_t), _raw_type(raw_t), C.byref(g), gain_h,
+         _ptr(st.vos_fit) if st is not None else None, _ptr(st.oscan) if st is not None else None,
+         _ptr(mbias), _ptr(mflat), _ptr(bpm),
+         _ptr(st.satlevel) if (st is not None and want_mask) else None,
+         C.byref(bits), _ptr(out_img), _ptr(out_mask) if want_mask else None, _stream())
+    return out_img, out_mask
+
+
+def os_corr(data, header, imgtype, xbin=1, ybin=1, data_limit=2000, tel=None, strict=True,
+            return_state=False):
+    """Overscan correction; returns the cropped float32 frame and fills the header keywords
+    BIAS{i}A{n}, VFITOK{i}, BIASM{i}, RDN{i}, BIASMEAN, RDNOISE (blackbox.py:6407-6879).
+
+    ``data``: float32 raw frame, already gain-corrected (as after gain_corr), or a uint16 raw
+    frame (the gain is then applied on the fly).  Unlike the reference the input array is
+    left untouched (the reference subtracts the overscan from it as a side effect that no
+    caller uses).
+    """
+    is_np = isinstance(data, np.ndarray)
+    raw_t = _to_dev(data)
+    geom = Geometry.from_raw_shape(tuple(raw_t.shape), xbin=xbin, ybin=ybin, tel=tel)
+    gain = get_par(set_bb.gain, tel) if _raw_type(raw_t) == 0 else None
+    st = overscan_enqueue(raw_t, geom, tel, gain=gain, data_limit=data_limit)
+    overscan_resolve_spline(st, strict)
+    out, _ = apply_enqueue(raw_t, geom, tel, st=st, gain=gain)
+    fill_os_header(header, st)
+    if return_state:
+        return (out.cpu().numpy() if is_np else out), st
+    return out.cpu().numpy() if is_np else out
+
+
+def fill_os_header(header, st):
+    """Header keywords of os_corr from the device state (synchronises)."""
+    coef = st.vos_coef.cpu().numpy()
+    ok = st.vfit_ok.cpu().numpy()
+    biasm = st.biasm.cpu().numpy()
+    rdn = st.std_vos.cpu().numpy()
+    deg = int(set_bb.voscan_poldeg)
+    n = st.geom.nchans
+    for i in range(n):
+        for nc in range(deg + 1):
+            v = float(coef[i, nc])
+            _set(header, 'BIAS{}A{}'.format(i + 1, nc), v if np.isfinite(v) else 'None',
+                 '[e-] channel {} vert. overscan A{} polyfit coeff'.format(i + 1, nc))
+        _set(header, 'VFITOK{}'.format(i + 1), bool(ok[i]),
+             'channel {} vert. overscan polyfit finite?'.format(i + 1))
+    for i in range(n):
+        _set(header, 'BIASM{}'.format(i + 1), float(biasm[i]),
+             '[e-] channel {} mean vertical overscan'.format(i + 1))
+    for i in range(n):
+        _set(header, 'RDN{}'.format(i + 1), float(rdn[i]),
+             '[e-] channel {} sigma (STD) vertical overscan'.format(i + 1))
+    _set(header, 'BIASMEAN', float(np.nanmean(biasm)), '[e-] average all channel means vert. overscan')
+    _set(header, 'RDNOISE', float(np.nanmean(rdn)), '[e-] average all channel sigmas vert. overscan')
+
+
+# -------------------------------------------------------------------------------------------
+# bias / flat (blackbox.py:1679, 1825)
+# -------------------------------------------------------------------------------------------
+def subtract_mbias(data, data_mbias):
+    """In place ``data -= data_mbias`` (float32)."""
+    return _binary_inplace(data, data_mbias, 0)
+
+
+def divide_mflat(data, data_mflat):
+    """In place ``data /= data_mflat`` (float32 IEEE division)."""
+    return _binary_inplace(data, data_mflat, 1)
+
+
+def _binary_inplace(a, b, op):
+    is_np = isinstance(a, np.ndarray)
+    ta, tb = _to_dev(a, torch.float32), _to_dev(b, torch.float32)
+    if ta.shape != tb.shape:
+        raise ValueError('shape mismatch {} vs {}'.format(tuple(ta.shape), tuple(tb.shape)))
+    call('bbx_binary_inplace', _ptr(ta), _ptr(tb), ta.numel(), op, _stream())
+    if is_np:
+        a[...] = ta.cpu().numpy()
+        return a
+    return ta
+
+
+# -------------------------------------------------------------------------------------------
+# mask
+# -------------------------------------------------------------------------------------------
+def set_bad_pixel_mask(filt, bpm):
+    """Register the bad-pixel mask of filter ``filt`` (the reference reads
+    set_bb.bad_pixel_mask with 'bpm' -> 'bpm_<filt>' from disk, blackbox.py:4386-4398)."""
+    if bpm is None:
+        _bpm_registry.pop(filt, None)
+    else:
+        _bpm_registry[filt] = bpm
+
+
+class MaskWork:
+    """Scratch buffers of the mask morphology for one frame shape (reusable)."""
+
+    def __init__(self, H, W, device):
+        self.H, self.W = H, W
+        self.holes = torch.empty(query('bbx_fill_holes_work_bytes', H, W), dtype=torch.uint8, device=device)
+        self.labels = torch.empty(H * W, dtype=torch.int32, device=device)
+        self.unconverged = torch.zeros(1, dtype=torch.int32, device=device)
+        self.nobj = torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=64):
+    """Enqueue crosstalk-victim / saturated-connected / NOBJ-SAT / fill_sat_holes on a mask
+    that carries the saturation marker written by bbx_reduce_apply."""
+    H, W = mask_t.shape
+    bits = _bits(tel_)
+    s = _stream()
+    call('bbx_mask_sat_neighbours', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), s)
+    if count_objects:
+        call('bbx_count_objects', _ptr(mask_t), 0x80, H, W, _ptr(work.labels), _ptr(work.nobj), s)
+    call('bbx_fill_sat_holes', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), rounds,
+         _ptr(work.unconverged), s)
+
+
+def mask_morph_finish(mask_t, tel_, work, rounds=1024):
+    """Synchronise; continue the hole filling if it had not converged.  Returns NOBJ-SAT."""
+    H, W = mask_t.shape
+    bits = _bits(tel_)
+    while int(work.unconverged.item()) != 0:
+        call('bbx_fill_holes_more', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), rounds,
+             _ptr(work.unconverged), _stream())
+    return int(work.nobj.item())
+
+
+def mask_init(data, header, filt, imgtype, bpm=None):
+    """Initial mask from the bad-pixel mask, non-finite pixels, per-channel saturation,
+    crosstalk victims, saturated-connected pixels and filled holes
+    (blackbox.py:4375-4579, 4584-4596).  Returns (uint8 mask, header_mask dict); ``data``
+    has its non-finite pixels zeroed in place.  Uses the module-global ``tel``."""
+    is_np = isinstance(data, np.ndarray)
+    t = _to_dev(data, torch.float32)
+    H, W = t.shape
+    if bpm is None:
+        bpm = _bpm_registry.get(filt)
+    bpm_t = _to_dev(bpm, torch.uint8)
+    if bpm_t is not None and tuple(bpm_t.shape) != (H, W):
+        raise ValueError('bad pixel mask shape {} does not match data {}'.format(tuple(bpm_t.shape), (H, W)))
+    header_mask = {}
+    if imgtype != 'object':
+        mask_t = bpm_t.clone() if bpm_t is not None else torch.zeros((H, W), dtype=torch.uint8, device=t.device)
+        return (mask_t.cpu().numpy() if is_np else mask_t), header_mask
+    nchans = set_bb.ny * set_bb.nx
+    biaslevel = np.array([header['BIASM{}'.format(i + 1)] for i in range(nchans)], dtype=np.float64)
+    satlevel_chans = (np.array(get_par(set_bb.satlevel, tel)) * np.array(get_par(set_bb.gain, tel))
+                      - biaslevel)
+    sat_mean = float(np.mean(satlevel_chans))
+    _set(header_mask, 'SATURATE', sat_mean, '[e-] mean saturation threshold')
+    _set(header, 'SATURATE', sat_mean, '[e-] mean saturation threshold')
+    for i in range(nchans):
+        key, descr = 'SATLEV{}'.format(i + 1), '[e-] channel {} saturation threshold'.format(i + 1)
+        _set(header, key, round(float(satlevel_chans[i]), 1), descr)
+        _set(header_mask, key, round(float(satlevel_chans[i]), 1), descr)
+    # seed: bpm | non-finite -> bad | saturated (+ marker) through the fused per-pixel kernel
+    geom = _reduced_geometry((H, W), tel)
+    satlevel_t = torch.from_numpy(satlevel_chans).to(t.device)
+    out_img = torch.empty_like(t)
+    mask_t = _apply_seed(t, geom, satlevel_t, bpm_t, out_img)
+    work = MaskWork(H, W, t.device)
+    mask_morph_enqueue(mask_t, tel, work)
+    nobj = mask_morph_finish(mask_t, tel, work)
+    _set(header_mask, 'NOBJ-SAT', nobj, 'number of saturated objects')
+    _set(header, 'NOBJ-SAT', nobj, 'number of saturated objects')
+    if is_np:
+        data[...] = out_img.cpu().numpy()
+        return mask_t.cpu().numpy(), header_mask
+    t.copy_(out_img)
+    return mask_t, header_mask
+
+
+def _apply_seed(t, geom, satlevel_t, bpm_t, out_img):
+    g = geom.as_struct()
+    out_mask = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
+    bits = _bits(tel)
+    call('bbx_reduce_apply', _ptr(t), 1, C.byref(g), None, None, None, None, None, _ptr(bpm_t),
+         _ptr(satlevel_t), C.byref(bits), _ptr(out_img), _ptr(out_mask), _stream())
+    return out_mask
+
+
+def mask_header(data_mask, header_mask):
+    """Per-type pixel counts M-*NUM etc. (blackbox.py:4601-4620)."""
+    t = _to_dev(data_mask, torch.uint8)
+    counts = torch.zeros(8, dtype=torch.int64, device=t.device)
+    call('bbx_mask_counts', _ptr(t), t.numel(), _ptr(counts), _stream())
+    counts = counts.cpu().numpy()
+    text = {'bad': 'BP', 'edge': 'EP', 'saturated': 'SP', 'saturated-connected': 'SCP',
+            'satellite trail': 'STP', 'cosmic ray': 'CRP'}
+    mv = get_par(set_bb.mask_value, tel)
+    for mask_type, short in text.items():
+        value = mv[mask_type]
+        _set(header_mask, 'M-{}'.format(short), True, '{} pixels included in mask?'.format(mask_type))
+        _set(header_mask, 'M-{}VAL'.format(short), value, 'value added to mask for {} pixels'.format(mask_type))
+        _set(header_mask, 'M-{}NUM'.format(short), int(counts[int(value).bit_length() - 1]),
+             'number of {} pixels'.format(mask_type))
+
+
+# -------------------------------------------------------------------------------------------
+# cosmic rays
+# -------------------------------------------------------------------------------------------
+class LacosmicWork:
+    def __init__(self, H, W, niter, device):
+        self.buf = torch.empty(query('bbx_lacosmic_work_bytes', H, W), dtype=torch.uint8, device=device)
+        self.info = torch.zeros(2 + max(niter, 1), dtype=torch.int64, device=device)
+
+
+def lacosmic_enqueue(img_t, inmask_t, crmask_t, sigclip, sigfrac, objlim, readnoise, niter,
+                     work, readnoise_dev=None):
+    H, W = img_t.shape
+    call('bbx_lacosmic', _ptr(img_t), _ptr(inmask_t), _ptr(crmask_t), H, W,
+         float(np.float32(sigclip)), float(np.float32(sigfrac)), float(np.float32(objlim)),
+         float(np.float32(readnoise)), _ptr(readnoise_dev), int(niter), _ptr(work.buf),
+         _ptr(work.info), _stream())
+
+
+def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gain=1.0,
+                   readnoise=6.5, satlevel=65536.0, pssl=0.0, niter=4, sepmed=True,
+                   cleantype='meanmask', fsmode='median', psfmodel='gauss', psffwhm=2.5,
+                   psfsize=7, psfk=None, psfbeta=4.765, verbose=False, info=None):
+    """astroscrappy.detect_cosmics (1.0.8 signature) -> (crmask bool, cleanarr float32).
+
+    Implemented path: sepmed=False, cleantype='medmask', fsmode='median', pssl=0,
+    satlevel=inf -- the one blackbox.py:4323-4332 uses; anything else raises
+    NotImplementedError rather than silently computing something different."""
+    if sepmed or cleantype != 'medmask' or fsmode != 'median' or pssl != 0.0:
+        raise NotImplementedError('detect_cosmics: only sepmed=False, cleantype="medmask", '
+                                  'fsmode="median", pssl=0 are implemented')
+    if np.isfinite(satlevel):
+        raise NotImplementedError('detect_cosmics: finite satlevel is not implemented '
+                                  '(the reference passes satlevel=inf, blackbox.py:4272)')
+    is_np = isinstance(indat, np.ndarray)
+    clean = _to_dev(indat, torch.float32).clone()
+    if gain != 1.0:
+        clean *= float(np.float32(gain))
+    H, W = clean.shape
+    inmask_t = None
+    if inmask is not None:
+        inmask_t = _to_dev(inmask)
+        inmask_t = (inmask_t != 0).to(torch.uint8) if inmask_t.dtype != torch.uint8 else inmask_t
+    crmask = torch.empty((H, W), dtype=torch.uint8, device=clean.device)
+    work = LacosmicWork(H, W, niter, clean.device)
+    lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work)
+    if gain != 1.0:
+        clean /= float(np.float32(gain))
+    if info is not None:
+        inf = work.info.cpu().numpy()
+        info.update(iterations=int(inf[0]), ncr_per_iter=inf[2:2 + int(inf[0])].copy())
+    crb = crmask.to(torch.bool)
+    if is_np:
+        return crb.cpu().numpy(), clean.cpu().numpy()
+    return crb, clean
+
+
+def cosmics_corr(data, header, data_mask, header_mask):
+    """LACosmic detection + cleaning, cosmic-ray bit into the mask, NCOSMICS into both
+    headers (blackbox.py:4259-4370).  Uses the module-global ``tel``."""
+    is_np = isinstance(data, np.ndarray)
+    d = _to_dev(data, torch.float32)
+    m = _to_dev(data_mask, torch.uint8)
+    mask_cr, clean = detect_cosmics(
+        d, inmask=(m != 0), sigclip=get_par(set_bb.sigclip, tel),
+        sigfrac=get_par(set_bb.sigfrac, tel), objlim=get_par(set_bb.objlim, tel),
+        niter=get_par(set_bb.niter, tel), readnoise=header['RDNOISE'], gain=1.0,
+        satlevel=np.inf, cleantype='medmask', sepmed=get_par(set_bb.sepmed, tel))
+    cr8 = mask_cr.to(torch.uint8)
+    bit = get_par(set_bb.mask_value, tel)['cosmic ray']
+    call('bbx_mask_or', _ptr(m), _ptr(cr8), m.numel(), int(bit), _stream())
+    H, W = cr8.shape
+    labels = torch.empty(H * W, dtype=torch.int32, device=d.device)
+    nobj = torch.zeros(1, dtype=torch.int32, device=d.device)
+    call('bbx_count_objects', _ptr(cr8), 1, H, W, _ptr(labels), _ptr(nobj), _stream())
+    ncosmics_persec = int(nobj.item()) / float(header['EXPTIME'])
+    _set(header, 'NCOSMICS', ncosmics_persec, '[/s] number of cosmic rays identified')
+    _set(header_mask, 'NCOSMICS', ncosmics_persec, '[/s] number of cosmic rays identified')
+    if is_np:
+        if isinstance(data_mask, np.ndarray):
+            data_mask[...] = m.cpu().numpy()
+            return clean.cpu().numpy(), data_mask
+        return clean.cpu().numpy(), m.cpu().numpy()
+    if isinstance(data_mask, torch.Tensor) and data_mask.data_ptr() != m.data_ptr():
+        data_mask.copy_(m)
+        m = data_mask
+    return clean, m
+
+
+# -------------------------------------------------------------------------------------------
+# crosstalk
+# -------------------------------------------------------------------------------------------
+def read_crosstalk_file(crosstalk_file, nchans=16):
+    """ASCII table with columns victim / source / correction (1-based channel numbers, column
+    names on the first line; blackbox.py:7157-7161) -> float64 [source, victim] matrix."""
+    coeffs = np.zeros((nchans, nchans))
+    with open(crosstalk_file) as fh:
+        rows = [ln.split() for ln in fh if ln.strip() and not ln.lstrip().startswith('#')]
+    names = ['victim', 'source', 'correction']
+    try:
+        float(rows[0][0])
+    except ValueError:
+        names = [n.lower() for n in rows[0]]
+        rows = rows[1:]
+    iv, isrc, ic = names.index('victim'), names.index('source'), names.index('correction')
+    for r in rows:
+        coeffs[int(float(r[isrc])) - 1, int(float(r[iv])) - 1] = float(r[ic])
+    return coeffs
+
+
+def xtalk_enqueue(img_t, mask_t, coeffs, tel_):
+    H, W = img_t.shape
+    bits = _bits(tel_)
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    call('bbx_xtalk', _ptr(img_t), _ptr(mask_t), H, W, H // 2, W // 8,
+         c.ctypes.data_as(C.c_void_p), C.byref(bits), _stream())
+
+
+def xtalk_corr(data, crosstalk_file, data_mask=None):
+    """In-place crosstalk correction (blackbox.py:7138-7258).  ``crosstalk_file`` is the path
+    of the coefficient table or an already parsed [source, victim] matrix.  ``data_mask`` is
+    left unchanged.  Uses the module-global ``tel``."""
+    coeffs = crosstalk_file if isinstance(crosstalk_file, np.ndarray) else read_crosstalk_file(crosstalk_file)
+    is_np = isinstance(data, np.ndarray)
+    t = _to_dev(data, torch.float32)
+    m = None
+    if data_mask is not None:
+        m = _to_dev(data_mask)
+        if m.dtype != torch.uint8:
+            m = m.to(torch.uint8)
+    if t.shape[0] % 2 or t.shape[1] % 8:
+        raise ValueError('xtalk_corr: frame {} is not 2 x 8 channels'.format(tuple(t.shape)))
+    xtalk_enqueue(t, m, coeffs, tel)
+    if is_np:
+        data[...] = t.cpu().numpy()
+
+
+# -------------------------------------------------------------------------------------------
+# master frames
+# -------------------------------------------------------------------------------------------
+def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=None):
+    """Arithmetic core of master_prep (blackbox.py:4908-4984, 5063-5073): per-pixel median of
+    the stack; flats are first divided by their normalisation median (``medsec[i]`` = the
+    header's MEDSEC, else the median over set_bb.flat_norm_sec) and get edge / non-positive
+    pixels set to 1 afterwards.  ``frames``: sequence of float32 arrays / CUDA tensors of one
+    shape (or a 3-D array).  Returns (master, scales)."""
+    is_np = isinstance(frames[0], np.ndarray)
+    ts = [_to_dev(f, torch.float32) for f in frames]
+    n = len(ts)
+    if n < 1 or n > 64:
+        raise ValueError('master_combine: {} frames (supported: 1..64)'.format(n))
+    shape = tuple(ts[0].shape)
+    scales = [0.0] * n
+    if imgtype == 'flat':
+        sec = get_par(set_bb.flat_norm_sec, tel)
+        for i, t in enumerate(ts):
+            if medsec is not None and medsec[i] is not None:
+                med = float(medsec[i])
+            else:
+                med = float(exact_median(t[sec]))
+            scales[i] = med
+    bpm_t = _to_dev(bpm, torch.uint8) if (imgtype == 'flat' and bpm is not None) else None
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=ts[0].device)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    call('bbx_stack_median', ptrs, _harr([float(np.float32(s)) for s in scales], C.c_float), n,
+         out.numel(), 1 if (imgtype == 'flat' and bpm_t is not None) else 0, _ptr(bpm_t),
+         int(get_par(set_bb.mask_value, tel)['edge']), _ptr(out), _stream())
+    return (out.cpu().numpy() if is_np else out), scales
+
+
+def exact_median(t):
+    """np.median of a float32 CUDA tensor: mean of the two middle values for even counts
+    (float32), via two exact rank selections."""
+    flat = t.contiguous().view(-1)
+    n = flat.numel()
+    if n == 0:
+        return float('nan')
+    srt = torch.sort(flat).values
+    if n % 2:
+        return srt[n // 2].item()
+    a, b = srt[n // 2 - 1], srt[n // 2]
+    return ((a + b) / 2).item()

@@ -1,0 +1,233 @@
+/*
+ * bbx.h -- C ABI of libbbx.so: B200 (sm_100a) kernels for BlackBOX's per-frame CCD reduction
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer unless the name ends in _h (host);
+ *   - images are row-major, C-contiguous; "raw" = frame with overscans (bbx_geom.H x W),
+ *     "red" = reduced frame (ny*ysize_chan x nx*xsize_chan);
+ *   - stream is a cudaStream_t passed as void*; calls enqueue work and return, they never
+ *     synchronise the device unless documented;
+ *   - return value 0 = ok, < 0 = error; bbx_last_error() describes the last failure of the
+ *     calling thread.  Nothing here calls exit() or resets the device -- the Python shim
+ *     raises RuntimeError so blackbox_reduce's per-step try/except keeps working
+ *     (reference: blackbox.py:1476-1488, 1531-1594, 1750-1761, 1866-1878, 1897-1912);
+ *   - no hidden device allocation: scratch space is passed in by the caller.
+ *
+ * Each entry point cites the reference code it replaces (file:line into the reference repo).
+ */
+#ifndef BBX_H
+#define BBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBX_NCHAN 16
+#define BBX_MAX_POLY_DEG 7
+
+/* raw pixel types accepted by the kernels that read a raw frame */
+#define BBX_RAW_U16 0
+#define BBX_RAW_F32 1
+
+/* telescope families: decides the horizontal-overscan masking rule (blackbox.py:6586-6643) */
+#define BBX_TEL_ML 0
+#define BBX_TEL_BG 1
+
+/* Integer description of the channel layout; filled from define_sections
+ * (blackbox.py:6334-6402) by blackbox_b200/geometry.py. */
+typedef struct {
+    int H, W;                     /* raw frame shape                                         */
+    int ny, nx;                   /* channels in y (2) and x (8)                             */
+    int dy, dx;                   /* channel tile incl. overscans                            */
+    int ysize_chan, xsize_chan;   /* data section of one channel                             */
+    int vos_x0, vos_w;            /* vertical-overscan strip: first column (tile-relative), width */
+    int hos_rows;                 /* rows of the (cut) horizontal-overscan strip             */
+    int data_y0_bot, data_y0_top; /* first raw row of the data section, bottom / top half    */
+    int hos_y0_bot, hos_y0_top;   /* first raw row of the horizontal-overscan strip          */
+} bbx_geom;
+
+/* Internal marker bit of the uint8 mask: "this pixel was found saturated by the data >= level
+ * test" (mask_sat of the reference, blackbox.py:4469-4498), as opposed to a 'saturated' bit a
+ * bad-pixel mask may already carry.  Set by bbx_reduce_apply, consumed by
+ * bbx_mask_sat_neighbours / bbx_count_objects, cleared by bbx_fill_sat_holes.  No mask value
+ * may use it. */
+#define BBX_TMP_SAT 0x80
+
+/* mask bit values (set_zogy.mask_value; reference uses them at blackbox.py:4413-4596, 7171-7184) */
+typedef struct {
+    int bad, cosmic, saturated, satcon, sattrail, edge, crosstalk;
+} bbx_maskbits;
+
+const char *bbx_last_error(void);
+int bbx_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Overscan statistics and fits -- os_corr, blackbox.py:6407-6879
+ * ------------------------------------------------------------------------------------- */
+
+/* Row-wise sigma-clipped mean (sigma 3, <= maxiters, centre = mean, zeros masked) of the 16
+ * vertical-overscan strips of a raw frame after the gain multiply.
+ * Replaces blackbox.py:6480-6490 (+ gain_corr 7460 when raw is u16).
+ * out_mean: float64 [16][dy], NaN for a fully masked row. */
+int bbx_vos_rowstats(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                     double sigma, int maxiters, double *out_mean, void *stream);
+
+/* Per channel: 5-sigma clip of the row means, drop the rows overlapping the horizontal
+ * overscan, least-squares polynomial of degree `deg` (<= 7) in the row index, evaluate on all
+ * dy rows.  Replaces blackbox.py:6497-6556 (np.polyfit / np.polyval).
+ * out_fit  float64 [16][dy]   value subtracted from every row of the channel tile
+ * out_coef float64 [16][8]    ascending monomial coefficients (BIAS{i}A{n})
+ * out_biasm float64 [16]      BIASM{i}
+ * out_ok   int32 [16]         VFITOK{i} (0: fit not finite -> out_fit = nanmedian of the means)
+ * smem budget: 3*dy doubles per block. */
+int bbx_vos_fit(const double *mean_vos, const bbx_geom *g, int deg, double nsigma,
+                double *out_fit, double *out_coef, double *out_biasm, int32_t *out_ok,
+                void *stream);
+
+/* BlackGEM: per channel and data column, count pixels >= 0.9*sat_e in the lim1 / lim2 data
+ * rows nearest the horizontal overscan (values after gain and vertical-overscan subtraction).
+ * Replaces blackbox.py:6624-6640.  out_cnt: int32 [16][2][xsize_chan], zeroed by the call. */
+int bbx_hos_satcount(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                     const double *vos_fit, const double *sat_e_h, int lim1, int lim2,
+                     int32_t *out_cnt, void *stream);
+
+/* Horizontal-overscan strip of every channel: level offset dlevel (clipped mean of the last
+ * 300 data columns), masking (ML: > data_limit with single-column un-masking and 5x5 growth;
+ * BG: saturated columns from out_cnt), column-wise 2.5-sigma clipped mean / std(ddof 1) /
+ * count.  Replaces blackbox.py:6565-6568, 6583-6662.
+ * out_dlevel f64[16]; out_mean,out_std f32[16][xsize_chan]; out_n i32[16][xsize_chan];
+ * out_satcol u8[16][xsize_chan] (BG; zeros for ML). */
+int bbx_hos_stats(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                  const double *vos_fit, int tel_kind, float data_limit,
+                  const int32_t *satcnt, double *out_dlevel, float *out_mean, float *out_std,
+                  int32_t *out_n, uint8_t *out_satcol, void *stream);
+
+/* Sigma-clipped std (sigma 3, <= 5 iterations, zeros masked) of each vertical-overscan strip
+ * after the vertical-overscan fit and dlevel were subtracted: RDN{i}.
+ * Replaces blackbox.py:6572-6573.  out_std f64[16]. */
+int bbx_vos_std(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                const double *vos_fit, const double *dlevel, double *out_std, void *stream);
+
+/* Per channel: turn the column statistics into the overscan vector to subtract: errors,
+ * 5-sigma pre-clean, 3x [polynomial fit of degree `deg` on columns >= 120, reject > 3 err],
+ * BG2 channel 9 split fit, plain column mean where valid for the first 150 columns.
+ * Replaces blackbox.py:6666-6678, 6727-6814 except the smoothing spline, which is only
+ * needed for columns flagged in out_need_spline (host evaluates scipy's UnivariateSpline for
+ * those; blackbox.py:6698-6723, 6795).
+ * out_oscan f64[16][xsize_chan]; out_need_spline u8[16][xsize_chan]; out_status i32[16]
+ * (0 ok, 1 = too few points for the fit). */
+int bbx_hos_fit(const float *hos_mean, const float *hos_std, const int32_t *hos_n,
+                const uint8_t *satcol, const bbx_geom *g, int tel_kind, int split_chan,
+                int split_col, double *out_oscan, uint8_t *out_need_spline,
+                int32_t *out_status, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused per-pixel pass -- gain_corr 7460, os_corr 6553/6556/6844-6847, master bias 1679,
+ * mask_init 4408-4414 + 4494-4498 + 4538, master flat 1825
+ *   v = f32(raw)*gain; v -= vos_fit[row]; v -= oscan[col]; crop; v -= mbias;
+ *   non-finite -> 0 and 'bad' (if unmasked); saturated = v >= satlevel[chan] (float64
+ *   compare) -> 'saturated'; v /= mflat.
+ * Null mbias / mflat / bpm / out_mask / satlevel skip the corresponding step.
+ * out_img f32 [red]; out_mask u8 [red]. */
+int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                     const double *vos_fit, const double *oscan, const float *mbias,
+                     const float *mflat, const uint8_t *bpm, const double *satlevel,
+                     const bbx_maskbits *bits, float *out_img, uint8_t *out_mask,
+                     void *stream);
+
+/* satlevel[i] = sat_e_h[i] - biasm[i] on the device (blackbox.py:4448-4454) */
+int bbx_satlevels(const double *sat_e_h, const double *biasm, double *out_satlevel,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Mask morphology -- mask_init blackbox.py:4473-4566, fill_sat_holes 4584-4596
+ * ------------------------------------------------------------------------------------- */
+
+/* crosstalk-victim bit from saturated pixels of the other 15 channels (y-mirrored across CCD
+ * halves), then saturated-connected = 3x3 dilation of saturated minus saturated.
+ * mask: u8 [red] in place. */
+int bbx_mask_sat_neighbours(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                            const bbx_maskbits *bits, void *stream);
+
+/* fill_sat_holes: closing (3x3, border 0) of saturated|saturated-connected, fill holes
+ * (8-connected background), new pixels with mask==0 get 'saturated-connected'.
+ * work: >= bbx_fill_holes_work_bytes(H, W) bytes.  `rounds` propagation rounds are enqueued;
+ * *unconverged (device int32) is non-zero afterwards if more rounds are needed (call
+ * bbx_fill_holes_more). */
+size_t bbx_fill_holes_work_bytes(int H, int W);
+int bbx_fill_sat_holes(uint8_t *mask, int H, int W, const bbx_maskbits *bits, void *work,
+                       int rounds, int32_t *unconverged, void *stream);
+int bbx_fill_holes_more(uint8_t *mask, int H, int W, const bbx_maskbits *bits, void *work,
+                        int rounds, int32_t *unconverged, void *stream);
+
+/* number of 8-connected components of (mask & bit) != 0  (ndimage.label; blackbox.py:4354,
+ * 4544).  labels: int32 [H*W] scratch; out_count device int32. */
+int bbx_count_objects(const uint8_t *mask, int bit, int H, int W, int32_t *labels,
+                      int32_t *out_count, void *stream);
+
+/* per-bit pixel counts (mask_header, blackbox.py:4601-4620): out_counts int64 [8], bit k */
+int bbx_mask_counts(const uint8_t *mask, size_t n, unsigned long long *out_counts,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Crosstalk -- xtalk_corr blackbox.py:7138-7258
+ * coeffs_h: float64 [16][16] indexed [source][victim].  img in place.
+ * ------------------------------------------------------------------------------------- */
+int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+              const double *coeffs_h, const bbx_maskbits *bits, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Master frames -- master_prep core blackbox.py:4908-4984 (+5063-5073)
+ * frames_h: host array of N device pointers to float32 [npix]; scale_h: float32 [N] divisors
+ * (0 = leave frame i unscaled; blackbox.py:4941).  np.median semantics: even N -> (a+b)/2 in
+ * float32; any NaN -> NaN.  flat_fix != 0: pixels <= 0 or with bpm == edge become 1.
+ * ------------------------------------------------------------------------------------- */
+int bbx_stack_median(const float *const *frames_h, const float *scale_h, int N, size_t npix,
+                     int flat_fix, const uint8_t *bpm, int edge_value, float *out,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LACosmic -- astroscrappy.detect_cosmics 1.0.8 (sepmed=False, fsmode='median',
+ * cleantype='medmask', gain=1, pssl=0, satlevel=inf), call site blackbox.py:4323-4332
+ * img    f32 [H][W]  in: image, out: cleaned image
+ * inmask u8  [H][W]  non-zero = excluded
+ * crmask u8  [H][W]  out: 0/1
+ * work   >= bbx_lacosmic_work_bytes(H, W) bytes
+ * out_info int64 [2 + niter] device: [0] iterations run, [1] reserved, [2+k] new CR pixels in
+ * iteration k.  The iteration loop runs on the device without host synchronisation;
+ * iterations after one that found nothing are skipped (as the reference's `break`).
+ * ------------------------------------------------------------------------------------- */
+size_t bbx_lacosmic_work_bytes(int H, int W);
+int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                 float sigclip, float sigfrac, float objlim, float readnoise,
+                 const double *readnoise_dev, int niter, void *work, long long *out_info,
+                 void *stream);
+
+/* lower median a[(n-1)/2] of the pixels with inmask == 0 (astroscrappy's background level)
+ * work >= bbx_select_work_bytes(); out device float32 */
+size_t bbx_select_work_bytes(void);
+int bbx_masked_lower_median(const float *img, const uint8_t *inmask, size_t n, void *work,
+                            float *out, void *stream);
+
+/* single LACosmic building blocks, exported for kernel-level parity tests */
+int bbx_medfilt(const float *in, float *out, int H, int W, int ksize, void *stream);
+int bbx_laplace_plus(const float *in, float *out, int H, int W, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * small elementwise helpers for the drop-in functions used one step at a time
+ * ------------------------------------------------------------------------------------- */
+/* gain_corr on a float32 raw frame in place (blackbox.py:7459-7460) */
+int bbx_gain_corr(float *raw, const bbx_geom *g, const float *gain_h, void *stream);
+/* a -= b (op 0) / a /= b (op 1), float32 (blackbox.py:1679, 1825) */
+int bbx_binary_inplace(float *a, const float *b, size_t n, int op, void *stream);
+/* mask[crmask != 0] |= bit  (blackbox.py:4349) */
+int bbx_mask_or(uint8_t *mask, const uint8_t *flag, size_t n, int bit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBX_H */

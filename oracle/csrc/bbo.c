@@ -1,0 +1,481 @@
+/*
+ * bbo.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the third-party numerics the reference's reduction hot path calls
+ * and that are absent from /root/reference:
+ *
+ *   - astropy.stats.sigma_clip / sigma_clipped_stats "fast" path
+ *     (call sites: blackbox.py:6482, 6489, 6500, 6565, 6572, 6652, 6734)
+ *   - astroscrappy 1.0.8 detect_cosmics, the sepmed=False / fsmode='median' /
+ *     cleantype='medmask' path (only call site: blackbox.py:4323-4332)
+ *
+ * Neither library can be imported in the build container (no astropy, no astroscrappy, no
+ * network), and the reference ships no tests or golden vectors:  PARITY UNPINNED for these
+ * two pieces.  The algorithms are restated from their published sources / the LACosmic paper
+ * (van Dokkum 2001); every rounding step is made explicit so the CUDA kernels can be checked
+ * bit-for-bit against this file.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  Build: oracle/build.py (gcc -O2 -fopenmp -ffp-contract=off).
+ *
+ * All float32 arithmetic below is written one IEEE operation per statement; the file must be
+ * compiled with -ffp-contract=off so that no FMA is formed.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define BBO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * selection helpers
+ * ---------------------------------------------------------------------------------------- */
+
+/* k-th smallest (0-based) of a[0..n); a is permuted (Wirth/Hoare selection). */
+static double kth_smallest_d(double *a, long n, long k)
+{
+    long l = 0, m = n - 1;
+    while (l < m) {
+        double x = a[k];
+        long i = l, j = m;
+        do {
+            while (a[i] < x) i++;
+            while (x < a[j]) j--;
+            if (i <= j) { double t = a[i]; a[i] = a[j]; a[j] = t; i++; j--; }
+        } while (i <= j);
+        if (j < k) l = i;
+        if (k < i) m = j;
+    }
+    return a[k];
+}
+
+static float kth_smallest_f(float *a, long n, long k)
+{
+    long l = 0, m = n - 1;
+    while (l < m) {
+        float x = a[k];
+        long i = l, j = m;
+        do {
+            while (a[i] < x) i++;
+            while (x < a[j]) j--;
+            if (i <= j) { float t = a[i]; a[i] = a[j]; a[j] = t; i++; j--; }
+        } while (i <= j);
+        if (j < k) l = i;
+        if (k < i) m = j;
+    }
+    return a[k];
+}
+
+/* median as astropy's C helper defines it: mean of the two middle values for even n */
+static double median_avg_d(double *a, long n)
+{
+    if (n & 1) return kth_smallest_d(a, n, n / 2);
+    return 0.5 * (kth_smallest_d(a, n, n / 2) + kth_smallest_d(a, n, n / 2 - 1));
+}
+
+/* LOWER median a[(n-1)/2]: astroscrappy's quick-select median (medutils PyMedian) */
+BBO_API float bbo_lower_median_f(const float *a, long n)
+{
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    float r;
+    if (n <= 0) { free(tmp); return 0.0f; }
+    memcpy(tmp, a, sizeof(float) * (size_t)n);
+    r = kth_smallest_f(tmp, n, (n - 1) / 2);
+    free(tmp);
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * astropy sigma clipping (fast C path): bounds of every slice
+ *
+ * v      [nslices][len] float64 values (caller converts float32 -> float64, as the gufunc does)
+ * valid  [nslices][len] 1 = take part (not masked, finite)
+ * Per slice: survivors are packed into a buffer; loop: mean and population std (about the
+ * mean, even when the centre is the median) in float64, sequential sums; bounds =
+ * centre -/+ sigma*std; keep lo <= x <= hi; stop when nothing was rejected or after
+ * `maxiters` bound computations (maxiters < 0 = unlimited).  Empty slice -> NaN bounds.
+ * ---------------------------------------------------------------------------------------- */
+BBO_API void bbo_clip_bounds(const double *v, const uint8_t *valid, long nslices, long len,
+                             int use_median, int maxiters, double sig_lo, double sig_hi,
+                             double *lo_out, double *hi_out)
+{
+#pragma omp parallel
+    {
+        double *buf = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+        double *scratch = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+#pragma omp for schedule(static)
+        for (long s = 0; s < nslices; s++) {
+            const double *x = v + s * len;
+            const uint8_t *ok = valid + s * len;
+            long count = 0;
+            double lo = NAN, hi = NAN;
+            for (long i = 0; i < len; i++)
+                if (ok[i]) buf[count++] = x[i];
+            if (count > 0) {
+                int iteration = 0;
+                for (;;) {
+                    double mean = 0.0, std = 0.0, cen;
+                    long kept = 0;
+                    for (long i = 0; i < count; i++) mean += buf[i];
+                    mean /= (double)count;
+                    for (long i = 0; i < count; i++) {
+                        double d = mean - buf[i];
+                        std += d * d;
+                    }
+                    std = sqrt(std / (double)count);
+                    if (use_median) {
+                        memcpy(scratch, buf, sizeof(double) * (size_t)count);
+                        cen = median_avg_d(scratch, count);
+                    } else {
+                        cen = mean;
+                    }
+                    lo = cen - sig_lo * std;
+                    hi = cen + sig_hi * std;
+                    for (long i = 0; i < count; i++)
+                        if (buf[i] >= lo && buf[i] <= hi) buf[kept++] = buf[i];
+                    if (kept == count) break;
+                    count = kept;
+                    iteration++;
+                    if (maxiters >= 0 && iteration >= maxiters) break;
+                    if (count == 0) break;
+                }
+            }
+            lo_out[s] = lo;
+            hi_out[s] = hi;
+        }
+        free(buf);
+        free(scratch);
+    }
+}
+
+/* nan-statistics of the survivors of every slice, float64, sequential sums (bottleneck
+ * nanmean / nanmedian / nanstd semantics): keep = valid & lo <= x <= hi. */
+BBO_API void bbo_clipped_moments(const double *v, const uint8_t *valid, long nslices, long len,
+                                 const double *lo, const double *hi, int ddof,
+                                 double *mean_out, double *median_out, double *std_out,
+                                 long *count_out)
+{
+#pragma omp parallel
+    {
+        double *buf = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+#pragma omp for schedule(static)
+        for (long s = 0; s < nslices; s++) {
+            const double *x = v + s * len;
+            const uint8_t *ok = valid + s * len;
+            long n = 0;
+            double sum = 0.0, ss = 0.0, mean;
+            for (long i = 0; i < len; i++)
+                if (ok[i] && !(x[i] < lo[s]) && !(x[i] > hi[s])) { buf[n++] = x[i]; }
+            if (count_out) count_out[s] = n;
+            if (n == 0) {
+                mean_out[s] = NAN; std_out[s] = NAN;
+                if (median_out) median_out[s] = NAN;
+                continue;
+            }
+            for (long i = 0; i < n; i++) sum += buf[i];
+            mean = sum / (double)n;
+            for (long i = 0; i < n; i++) { double d = buf[i] - mean; ss += d * d; }
+            mean_out[s] = mean;
+            std_out[s] = (n - ddof > 0) ? sqrt(ss / (double)(n - ddof)) : NAN;
+            if (median_out) median_out[s] = median_avg_d(buf, n);
+        }
+        free(buf);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * astroscrappy 1.0.8 image utilities (float32, row-major [H][W])
+ * ---------------------------------------------------------------------------------------- */
+
+#define CSWAP(a, b) do { if ((a) > (b)) { float _t = (a); (a) = (b); (b) = _t; } } while (0)
+
+static inline float med9(float *p)
+{
+    CSWAP(p[1], p[2]); CSWAP(p[4], p[5]); CSWAP(p[7], p[8]);
+    CSWAP(p[0], p[1]); CSWAP(p[3], p[4]); CSWAP(p[6], p[7]);
+    CSWAP(p[1], p[2]); CSWAP(p[4], p[5]); CSWAP(p[7], p[8]);
+    CSWAP(p[0], p[3]); CSWAP(p[5], p[8]); CSWAP(p[4], p[7]);
+    CSWAP(p[3], p[6]); CSWAP(p[1], p[4]); CSWAP(p[2], p[5]);
+    CSWAP(p[4], p[7]); CSWAP(p[4], p[2]); CSWAP(p[6], p[4]);
+    CSWAP(p[4], p[2]);
+    return p[4];
+}
+
+/* K x K median filter; the K/2-wide frame of the output is a copy of the input. */
+static void medfilt(const float *in, float *out, int H, int W, int K)
+{
+    const int r = K / 2, n = K * K;
+    if (H < K || W < K) { memcpy(out, in, sizeof(float) * (size_t)H * W); return; }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        float win[49];
+        const size_t row = (size_t)y * W;
+        if (y < r || y >= H - r) {
+            memcpy(out + row, in + row, sizeof(float) * (size_t)W);
+            continue;
+        }
+        for (int x = 0; x < r; x++) { out[row + x] = in[row + x]; out[row + W - 1 - x] = in[row + W - 1 - x]; }
+        for (int x = r; x < W - r; x++) {
+            int c = 0;
+            for (int dy = -r; dy <= r; dy++) {
+                const float *src = in + (size_t)(y + dy) * W + (x - r);
+                for (int dx = 0; dx < K; dx++) win[c++] = src[dx];
+            }
+            out[row + x] = (K == 3) ? med9(win) : kth_smallest_f(win, n, n / 2);
+        }
+    }
+}
+
+BBO_API void bbo_medfilt3(const float *in, float *out, int H, int W) { medfilt(in, out, H, W, 3); }
+BBO_API void bbo_medfilt5(const float *in, float *out, int H, int W) { medfilt(in, out, H, W, 5); }
+BBO_API void bbo_medfilt7(const float *in, float *out, int H, int W) { medfilt(in, out, H, W, 7); }
+
+/* out[2H][2W]: every pixel replicated into a 2x2 block */
+BBO_API void bbo_subsample(const float *in, float *out, int H, int W)
+{
+    const size_t W2 = (size_t)2 * W;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            float v = in[(size_t)y * W + x];
+            size_t o = (size_t)(2 * y) * W2 + 2 * x;
+            out[o] = v; out[o + 1] = v; out[o + W2] = v; out[o + W2 + 1] = v;
+        }
+}
+
+/* Laplacian kernel [[0,-1,0],[-1,4,-1],[0,-1,0]], neighbours outside the image omitted.
+ * One float32 rounding per step, order: 4*c, -right, -left, -next row, -previous row. */
+BBO_API void bbo_laplace(const float *in, float *out, int H, int W)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            size_t i = (size_t)y * W + x;
+            float p = 4.0f * in[i];
+            if (x + 1 < W) p = p - in[i + 1];
+            if (x > 0) p = p - in[i - 1];
+            if (y + 1 < H) p = p - in[i + W];
+            if (y > 0) p = p - in[i - W];
+            out[i] = p;
+        }
+}
+
+/* in[2H][2W] -> out[H][W]: mean of each 2x2 block, summed (y,x),(y,x+1),(y+1,x),(y+1,x+1) */
+BBO_API void bbo_rebin(const float *in, float *out, int H, int W)
+{
+    const size_t W2 = (size_t)2 * W;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            size_t o = (size_t)(2 * y) * W2 + 2 * x;
+            float p = in[o];
+            p = p + in[o + 1];
+            p = p + in[o + W2];
+            p = p + in[o + W2 + 1];
+            out[(size_t)y * W + x] = p / 4.0f;
+        }
+}
+
+/* 3x3 binary dilation, interior only; the 1-pixel frame copies the input */
+BBO_API void bbo_dilate3(const uint8_t *in, uint8_t *out, int H, int W)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            size_t i = (size_t)y * W + x;
+            if (y == 0 || y == H - 1 || x == 0 || x == W - 1) { out[i] = in[i]; continue; }
+            out[i] = in[i] || in[i + 1] || in[i - 1] || in[i + W] || in[i - W] ||
+                     in[i + W + 1] || in[i + W - 1] || in[i - W + 1] || in[i - W - 1];
+        }
+}
+
+/* 5x5-minus-corners binary dilation repeated `niter` times, zero padded */
+BBO_API void bbo_dilate5(const uint8_t *in, uint8_t *out, int H, int W, int niter)
+{
+    uint8_t *a = (uint8_t *)malloc((size_t)H * W), *b = (uint8_t *)malloc((size_t)H * W);
+    memcpy(a, in, (size_t)H * W);
+    for (int it = 0; it < niter; it++) {
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                uint8_t p = 0;
+                for (int dy = -2; dy <= 2 && !p; dy++)
+                    for (int dx = -2; dx <= 2; dx++) {
+                        int yy = y + dy, xx = x + dx;
+                        if ((dy == -2 || dy == 2) && (dx == -2 || dx == 2)) continue;
+                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                        if (a[(size_t)yy * W + xx]) { p = 1; break; }
+                    }
+                b[(size_t)y * W + x] = p;
+            }
+        { uint8_t *t = a; a = b; b = t; }
+    }
+    memcpy(out, a, (size_t)H * W);
+    free(a); free(b);
+}
+
+/* medmask cleaning: each crmask pixel of the interior [2,H-2) x [2,W-2) becomes the LOWER
+ * median of the 5x5 neighbours that are neither in crmask nor in mask, else `background`.
+ * Only crmask pixels are written and only non-crmask pixels are read: order-free. */
+BBO_API void bbo_clean_medmask(float *clean, const uint8_t *crmask, const uint8_t *mask,
+                               int H, int W, float background)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 2; y < H - 2; y++) {
+        float win[25];
+        for (int x = 2; x < W - 2; x++) {
+            size_t i = (size_t)y * W + x;
+            int n = 0;
+            if (!crmask[i]) continue;
+            for (int dy = -2; dy <= 2; dy++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    size_t j = (size_t)(y + dy) * W + (x + dx);
+                    if (!crmask[j] && !mask[j]) win[n++] = clean[j];
+                }
+            clean[i] = n ? kth_smallest_f(win, n, (n - 1) / 2) : background;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * detect_cosmics driver.  clean: in = image, out = cleaned image (float32, in place);
+ * mask: input mask (non-zero = excluded; updated only if satlevel is finite);
+ * crmask: output.  Optional dump buffers (may be NULL) receive first-iteration intermediates
+ * so individual kernels can be checked.  Returns the number of iterations executed.
+ * ---------------------------------------------------------------------------------------- */
+BBO_API int bbo_detect_cosmics(float *clean, uint8_t *mask, uint8_t *crmask, int H, int W,
+                               float sigclip, float sigfrac, float objlim, float readnoise,
+                               float satlevel, int niter, long *ncr_per_iter,
+                               float *dump_sp, float *dump_f, float *dump_noise,
+                               float *background_out)
+{
+    const size_t N = (size_t)H * W;
+    float *sub = (float *)malloc(sizeof(float) * 4 * N);
+    float *conv = (float *)malloc(sizeof(float) * 4 * N);
+    float *s = (float *)malloc(sizeof(float) * N);
+    float *noise = (float *)malloc(sizeof(float) * N);
+    float *t1 = (float *)malloc(sizeof(float) * N);
+    float *t2 = (float *)malloc(sizeof(float) * N);
+    uint8_t *cr = (uint8_t *)malloc(N), *cr2 = (uint8_t *)malloc(N);
+    const float sigcliplow = sigfrac * sigclip;
+    const float rn2 = readnoise * readnoise;
+    float background;
+    int it;
+
+    /* update_mask: saturated stars (no-op for satlevel = +inf unless the image holds +inf) */
+    if (isfinite(satlevel)) {
+        const float lim = satlevel / 10.0f;
+        medfilt(clean, t1, H, W, 5);
+        for (size_t i = 0; i < N; i++) cr[i] = (clean[i] >= satlevel) && (t1[i] > lim);
+        bbo_dilate5(cr, cr2, H, W, 2);
+        for (size_t i = 0; i < N; i++) mask[i] = mask[i] || cr2[i];
+    }
+
+    /* default background for CR pixels without usable neighbours: lower median of unmasked */
+    {
+        size_t ngood = 0;
+        for (size_t i = 0; i < N; i++) if (!mask[i]) t1[ngood++] = clean[i];
+        background = ngood ? kth_smallest_f(t1, (long)ngood, (long)((ngood - 1) / 2)) : 0.0f;
+        if (background_out) *background_out = background;
+    }
+
+    memset(crmask, 0, N);
+    for (it = 0; it < niter; it++) {
+        long ncr = 0;
+        /* L+ : Laplacian of the 2x subsampled image, negative part clipped, rebinned */
+        bbo_subsample(clean, sub, H, W);
+        bbo_laplace(sub, conv, 2 * H, 2 * W);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < 4 * N; i++) if (conv[i] < 0.0f) conv[i] = 0.0f;
+        bbo_rebin(conv, s, H, W);
+        /* noise model and Laplacian S/N */
+        medfilt(clean, t1, H, W, 5);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < N; i++) {
+            float m5 = t1[i];
+            float nz, d;
+            if (m5 < 0.00001f) m5 = 0.00001f;
+            nz = m5 + rn2;
+            nz = sqrtf(nz);
+            noise[i] = nz;
+            d = 2.0f * nz;
+            s[i] = s[i] / d;
+        }
+        /* s' = s - med5(s) */
+        medfilt(s, t1, H, W, 5);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < N; i++) s[i] = s[i] - t1[i];
+        /* fine structure f = (med3 - med7(med3)) / noise, floored at 0.01 */
+        medfilt(clean, t1, H, W, 3);
+        medfilt(t1, t2, H, W, 7);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < N; i++) {
+            float f = t1[i] - t2[i];
+            f = f / noise[i];
+            if (f < 0.01f) f = 0.01f;
+            t1[i] = f;
+        }
+        if (it == 0) {
+            if (dump_sp) memcpy(dump_sp, s, sizeof(float) * N);
+            if (dump_f) memcpy(dump_f, t1, sizeof(float) * N);
+            if (dump_noise) memcpy(dump_noise, noise, sizeof(float) * N);
+        }
+        /* candidates, then two growth steps with relaxed thresholds */
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < N; i++) {
+            float ratio = s[i] / t1[i];
+            cr[i] = (s[i] > sigclip) && !mask[i] && (ratio > objlim);
+        }
+        bbo_dilate3(cr, cr2, H, W);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < N; i++) cr[i] = cr2[i] && !mask[i] && (s[i] > sigclip);
+        bbo_dilate3(cr, cr2, H, W);
+#pragma omp parallel for schedule(static) reduction(+ : ncr)
+        for (size_t i = 0; i < N; i++) {
+            uint8_t c = cr2[i] && !mask[i] && (s[i] > sigcliplow);
+            ncr += c;
+            crmask[i] = crmask[i] || c;
+        }
+        if (ncr_per_iter) ncr_per_iter[it] = ncr;
+        if (ncr == 0) { it++; break; }
+        bbo_clean_medmask(clean, crmask, mask, H, W, background);
+    }
+    free(sub); free(conv); free(s); free(noise); free(t1); free(t2); free(cr); free(cr2);
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * stack median along axis 0 (np.median semantics for finite float32 input; used only to
+ * time the CPU baseline without numpy's 8.9 GB copy -- the parity oracle is np.median itself)
+ * frames: nframes pointers to [npix] float32, scale[i] divides frame i first (0 = no scaling)
+ * ---------------------------------------------------------------------------------------- */
+BBO_API void bbo_stack_median(const float *const *frames, const float *scale, int nframes,
+                              long npix, float *out)
+{
+#pragma omp parallel
+    {
+        float *buf = (float *)malloc(sizeof(float) * (size_t)nframes);
+#pragma omp for schedule(static)
+        for (long p = 0; p < npix; p++) {
+            for (int k = 0; k < nframes; k++) {
+                float v = frames[k][p];
+                if (scale && scale[k] != 0.0f) v = v / scale[k];
+                buf[k] = v;
+            }
+            if (nframes & 1) {
+                out[p] = kth_smallest_f(buf, nframes, nframes / 2);
+            } else {
+                float hi = kth_smallest_f(buf, nframes, nframes / 2);
+                float lo = buf[0];
+                for (int k = 1; k < nframes / 2; k++) if (buf[k] > lo) lo = buf[k];
+                /* after selection buf[0..n/2) <= hi: the lower middle is their maximum */
+                {
+                    float sum = lo + hi;
+                    out[p] = sum / 2.0f;
+                }
+            }
+        }
+        free(buf);
+    }
+}

@@ -1,0 +1,285 @@
+"""GPU parity of the single reduction steps against the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng_img(rng, shape, level=300.0):
+    return (level + 20 * rng.standard_normal(shape)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('k', [3, 5, 7])
+def test_medfilt_bit_exact(k):
+    import torch
+    from blackbox_b200 import _lib, reduce as bbr
+    from oracle import clib
+    rng = np.random.default_rng(k)
+    img = _rng_img(rng, (97, 203))
+    img[10:14, 50:60] = 5000.0
+    img[rng.random(img.shape) < 0.02] = 0.0          # ties
+    ref = {3: clib.medfilt3, 5: clib.medfilt5, 7: clib.medfilt7}[k](img)
+    t = torch.from_numpy(img).cuda()
+    out = torch.empty_like(t)
+    _lib.call('bbx_medfilt', bbr._ptr(t), bbr._ptr(out), img.shape[0], img.shape[1], k, bbr._stream())
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_medfilt_tiny_images():
+    import torch
+    from blackbox_b200 import _lib, reduce as bbr
+    from oracle import clib
+    rng = np.random.default_rng(0)
+    for shape in [(1, 1), (2, 9), (5, 5), (6, 4), (7, 7), (8, 33)]:
+        img = _rng_img(rng, shape)
+        t = torch.from_numpy(img).cuda()
+        for k, ref in ((3, clib.medfilt3), (5, clib.medfilt5), (7, clib.medfilt7)):
+            out = torch.empty_like(t)
+            _lib.call('bbx_medfilt', bbr._ptr(t), bbr._ptr(out), shape[0], shape[1], k, bbr._stream())
+            assert np.array_equal(out.cpu().numpy(), ref(img)), (shape, k)
+
+
+def test_laplace_plus_bit_exact():
+    import torch
+    from blackbox_b200 import _lib, reduce as bbr
+    from oracle import clib, lacosmic
+    rng = np.random.default_rng(3)
+    for shape in [(1, 1), (1, 7), (9, 1), (64, 131)]:
+        img = _rng_img(rng, shape)
+        ref_c = clib.rebin(np.maximum(clib.laplace(clib.subsample(img)), 0))
+        assert np.array_equal(ref_c, lacosmic.laplace_plus(img))
+        t = torch.from_numpy(img).cuda()
+        out = torch.empty_like(t)
+        _lib.call('bbx_laplace_plus', bbr._ptr(t), bbr._ptr(out), shape[0], shape[1], bbr._stream())
+        assert np.array_equal(out.cpu().numpy(), ref_c), shape
+
+
+def test_masked_lower_median():
+    import torch
+    from blackbox_b200 import _lib, reduce as bbr
+    from oracle import clib
+    rng = np.random.default_rng(4)
+    for n, frac in [(1, 0.0), (2, 0.0), (1001, 0.3), (250000, 0.1), (64, 1.0)]:
+        img = _rng_img(rng, (n,))
+        img[::7] = -img[::7]
+        mask = (rng.random(n) < frac).astype(np.uint8)
+        t, m = torch.from_numpy(img).cuda(), torch.from_numpy(mask).cuda()
+        work = torch.empty(_lib.query('bbx_select_work_bytes'), dtype=torch.uint8, device='cuda')
+        out = torch.zeros(1, dtype=torch.float32, device='cuda')
+        _lib.call('bbx_masked_lower_median', bbr._ptr(t), bbr._ptr(m), n, bbr._ptr(work), bbr._ptr(out), bbr._stream())
+        good = img[mask == 0]
+        want = clib.lower_median(good) if good.size else np.float32(0)
+        assert out.item() == want, (n, frac)
+
+
+# ------------------------------------------------------------------------------------------
+def _lacosmic_case(seed, shape=(160, 232), ncr=60, masked_frac=0.01):
+    rng = np.random.default_rng(seed)
+    img = (300 + np.sqrt(300) * rng.standard_normal(shape)).astype(np.float32)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    for _ in range(25):                                     # stars
+        y0, x0, f = rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(2e3, 2e5)
+        img += (f / (2 * np.pi * 1.5 ** 2) * np.exp(-((yy - y0) ** 2 + (xx - x0) ** 2) / (2 * 1.5 ** 2))).astype(np.float32)
+    for _ in range(ncr):                                    # cosmic rays, also on the borders
+        y, x = rng.integers(0, shape[0]), rng.integers(0, shape[1])
+        for t in range(rng.integers(1, 8)):
+            yy_, xx_ = min(y + t // 2, shape[0] - 1), min(x + t, shape[1] - 1)
+            img[yy_, xx_] += rng.uniform(500, 30000)
+    mask = rng.random(shape) < masked_frac
+    mask[40:60, 100:104] = True
+    return img, mask
+
+
+@pytest.mark.parametrize('seed,niter', [(1, 4), (2, 3), (3, 1)])
+def test_detect_cosmics_bit_exact(seed, niter):
+    from blackbox_b200 import reduce as bbr
+    from oracle import lacosmic
+    img, mask = _lacosmic_case(seed)
+    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=niter, readnoise=8.5, gain=1.0,
+              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    info_o, info_g = {}, {}
+    cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=mask, info=info_o, **kw)
+    cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g, **kw)
+    assert cr_o.sum() > 50
+    assert np.array_equal(cr_g, cr_o)
+    assert np.array_equal(clean_g.view(np.uint32), clean_o.view(np.uint32))
+    assert info_g['iterations'] == info_o['iterations']
+    assert np.array_equal(info_g['ncr_per_iter'], info_o['ncr_per_iter'])
+
+
+def test_detect_cosmics_no_mask_and_early_stop():
+    from blackbox_b200 import reduce as bbr
+    from oracle import lacosmic
+    rng = np.random.default_rng(9)
+    img = (100 + rng.standard_normal((64, 80))).astype(np.float32)     # nothing to find
+    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=4, readnoise=5.0, gain=1.0,
+              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    info_o, info_g = {}, {}
+    cr_o, clean_o = lacosmic.detect_cosmics(img, info=info_o, **kw)
+    cr_g, clean_g = bbr.detect_cosmics(img, info=info_g, **kw)
+    assert not cr_o.any() and not cr_g.any()
+    assert info_g['iterations'] == info_o['iterations'] == 1
+    assert np.array_equal(clean_g, clean_o)
+
+
+def test_detect_cosmics_unsupported_modes_raise():
+    from blackbox_b200 import reduce as bbr
+    img = np.zeros((16, 16), np.float32)
+    with pytest.raises(NotImplementedError):
+        bbr.detect_cosmics(img)                                    # astroscrappy defaults
+    with pytest.raises(NotImplementedError):
+        bbr.detect_cosmics(img, sepmed=False, cleantype='medmask', satlevel=5e4)
+
+
+# ------------------------------------------------------------------------------------------
+def _mask_case(seed, shape=(2 * 96, 8 * 132)):
+    rng = np.random.default_rng(seed)
+    data = _rng_img(rng, shape)
+    sat = 2.5e5
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    # rings (holes), a diagonal-gap ring (leaks), blobs, a bleed column, border contact
+    for (cy, cx, r0, r1) in [(30, 100, 5, 8), (140, 700, 9, 11), (60, 400, 3, 4)]:
+        rr = np.hypot(yy - cy, xx - cx)
+        data[(rr >= r0) & (rr <= r1)] = sat
+    data[100:108, 300] = sat; data[100, 300:308] = sat; data[108, 300:309] = sat; data[100:108, 308] = sat
+    data[101, 309] = sat
+    data[20:25, 900:905] = sat
+    data[0:3, 50:53] = sat                      # touches the image border
+    data[shape[0] - 1, 200:203] = sat
+    data[10:90, 555] = sat                      # bleed trail
+    data[50, 10] = np.nan
+    data[51, 11] = np.inf
+    # two blobs separated by a one-pixel gap: closing joins them
+    data[160:164, 100:104] = sat; data[160:164, 105:109] = sat
+    bpm = np.zeros(shape, np.uint8)
+    bpm[rng.random(shape) < 0.002] = 1
+    bpm[:4, :] = 32; bpm[-4:, :] = 32; bpm[:, :4] = 32; bpm[:, -4:] = 32
+    return data, bpm
+
+
+@pytest.mark.parametrize('tel', ['ML1', 'BG3'])
+def test_mask_init_bit_exact(tel, small_bb):
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from oracle import reduce as R
+    small_bb(96, 132)
+    data, bpm = _mask_case(5)
+    hdr = {'BIASM{}'.format(i + 1): 6500.0 + i for i in range(16)}
+    hdr_o, hdr_g = dict(hdr), dict(hdr)
+    d_o = data.copy()
+    mask_o, hm_o = R.mask_init(d_o, hdr_o, bpm, 'object', tel=tel)
+    bbr.tel = tel
+    d_g = data.copy()
+    mask_g, hm_g = bbr.mask_init(d_g, hdr_g, 'q', 'object', bpm=bpm)
+    assert np.array_equal(mask_g, mask_o), np.argwhere(mask_g != mask_o)[:10]
+    assert np.array_equal(d_g, d_o)
+    assert hdr_g['NOBJ-SAT'] == hdr_o['NOBJ-SAT'] > 5
+    assert hm_g['SATURATE'] == hm_o['SATURATE']
+    for i in range(16):
+        assert hdr_g['SATLEV{}'.format(i + 1)] == hdr_o['SATLEV{}'.format(i + 1)]
+    # torch in, torch out, nothing else changes
+    d_t = torch.from_numpy(data.copy()).cuda()
+    mask_t, _ = bbr.mask_init(d_t, dict(hdr), 'q', 'object', bpm=torch.from_numpy(bpm).cuda())
+    assert np.array_equal(mask_t.cpu().numpy(), mask_o)
+    assert np.array_equal(d_t.cpu().numpy(), d_o)
+
+
+def test_mask_init_no_saturation_and_no_bpm(small_bb):
+    from blackbox_b200 import reduce as bbr
+    from oracle import reduce as R
+    small_bb(96, 132)
+    rng = np.random.default_rng(1)
+    data = _rng_img(rng, (192, 1056))
+    hdr = {'BIASM{}'.format(i + 1): 6500.0 for i in range(16)}
+    bbr.tel = 'ML1'
+    mask_o, _ = R.mask_init(data.copy(), dict(hdr), None, 'object', tel='ML1')
+    mask_g, _ = bbr.mask_init(data.copy(), dict(hdr), 'q', 'object')
+    assert not mask_o.any() and np.array_equal(mask_g, mask_o)
+
+
+def test_mask_header_counts(small_bb):
+    from blackbox_b200 import reduce as bbr
+    rng = np.random.default_rng(2)
+    mask = rng.integers(0, 128, (50, 77)).astype(np.uint8)
+    hm = {}
+    bbr.tel = 'ML1'
+    bbr.mask_header(mask, hm)
+    for name, short in [('bad', 'BP'), ('edge', 'EP'), ('saturated', 'SP'), ('saturated-connected', 'SCP'),
+                        ('satellite trail', 'STP'), ('cosmic ray', 'CRP')]:
+        from blackbox_b200 import set_bb
+        v = set_bb.mask_value[name]
+        assert hm['M-{}NUM'.format(short)] == int(np.sum(mask & v == v))
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('with_mask', [True, False])
+def test_xtalk_parity(with_mask, small_bb, tmp_path):
+    from blackbox_b200 import reduce as bbr, synth
+    from oracle import reduce as R
+    small_bb(64, 132)
+    rng = np.random.default_rng(6)
+    shape = (128, 1056)
+    data = _rng_img(rng, shape, level=50.0)
+    data[rng.random(shape) < 0.01] += 60000.0
+    mask = None
+    if with_mask:
+        mask = rng.choice(np.array([0, 0, 0, 1, 2, 32, 64, 33], np.uint8), size=shape)
+    v, s, c, coeffs = synth.make_xtalk(11, amp=3e-4)
+    path = tmp_path / 'xtalk.txt'
+    synth.write_xtalk_file(str(path), v, s, c)
+    assert np.array_equal(bbr.read_crosstalk_file(str(path)), coeffs)
+    d_o = data.copy()
+    R.xtalk_corr(d_o, coeffs, None if mask is None else mask.copy(), tel='ML1')
+    bbr.tel = 'ML1'
+    d_g = data.copy()
+    m_g = None if mask is None else mask.copy()
+    bbr.xtalk_corr(d_g, str(path), m_g)
+    if mask is not None:
+        assert np.array_equal(m_g, mask)
+    assert np.mean(d_g == d_o) > 0.9999
+    np.testing.assert_allclose(d_g, d_o, rtol=1e-6, atol=0)
+    assert np.abs(d_o - data).max() > 1.0          # the correction did something
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 3, 15, 20, 33, 50, 64])
+def test_stack_median_bit_exact(n):
+    from blackbox_b200 import reduce as bbr
+    rng = np.random.default_rng(n)
+    frames = [_rng_img(rng, (33, 129)) for _ in range(n)]
+    frames[0][3, 5] = -1e30
+    if n > 2:
+        frames[1][7, 7] = np.nan
+        frames[2][8, 8] = np.inf
+    want = np.median(np.stack(frames), axis=0)
+    got, _ = bbr.master_combine(frames, 'bias')
+    assert got.dtype == np.float32
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_master_flat_combine(small_bb):
+    from blackbox_b200 import reduce as bbr, set_bb
+    from oracle import reduce as R
+    small_bb(96, 132)
+    set_bb_sec = dict(set_bb.flat_norm_sec)
+    set_bb.flat_norm_sec['ML1'] = (slice(20, 90), slice(100, 500))
+    try:
+        rng = np.random.default_rng(8)
+        shape = (192, 1056)
+        frames = [(_rng_img(rng, shape, level=20000.0 * rng.uniform(0.8, 1.2))) for _ in range(15)]
+        frames[3][100, 100] = -5.0
+        for f in frames:
+            f[50, 60] = -1.0                        # non-positive median -> 1
+        bpm = np.zeros(shape, np.uint8)
+        bpm[:5, :] = 32
+        bpm[40, 40] = 33                            # not == edge: untouched
+        medsec = [None] * 15
+        medsec[4] = 19876.5
+        want, sc_o = R.master_median(frames, 'flat', medsec=medsec, bpm=bpm, tel='ML1')
+        got, sc_g = bbr.master_combine(frames, 'flat', medsec=medsec, bpm=bpm, tel='ML1')
+        assert np.array_equal(np.float32(sc_g), np.float32(sc_o))
+        assert np.array_equal(got, want)
+        assert got[50, 60] == 1.0 and (got[:5] == 1.0).all()
+    finally:
+        set_bb.flat_norm_sec.update(set_bb_sec)
