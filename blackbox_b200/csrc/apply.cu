@@ -215,3 +215,30 @@ extern "C" int bbx_mask_or(uint8_t *mask, const uint8_t *flag, size_t n, int bit
     BBX_CHECK_LAUNCH("bbx_mask_or");
     return 0;
 }
+
+// BIASMEAN / RDNOISE = np.nanmean over the 16 channel values, summed in numpy's pairwise order
+// for 16 float64 (8 accumulators a[j] + a[j+8], then a balanced tree); blackbox.py:6865-6868
+__global__ void header_means_kernel(const double *__restrict__ biasm, const double *__restrict__ std_vos,
+                                    double *__restrict__ out)
+{
+    if (threadIdx.x >= 2) return;
+    const double *a = threadIdx.x == 0 ? biasm : std_vos;
+    double r[8];
+    int cnt = 0;
+    for (int j = 0; j < 8; j++) {
+        const double x = a[j], y = a[j + 8];
+        const bool nx = (x != x), ny = (y != y);
+        cnt += !nx + !ny;
+        r[j] = (nx ? 0.0 : x) + (ny ? 0.0 : y);
+    }
+    const double s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    out[threadIdx.x] = cnt ? s / (double)cnt : NAN;
+}
+
+extern "C" int bbx_header_means(const double *biasm, const double *std_vos, double *out, void *stream)
+{
+    BBX_REQUIRE(biasm && std_vos && out, "bbx_header_means: null argument");
+    header_means_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(biasm, std_vos, out);
+    BBX_CHECK_LAUNCH("bbx_header_means");
+    return 0;
+}

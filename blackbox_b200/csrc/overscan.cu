@@ -735,12 +735,8 @@ extern "C" int bbx_vos_fit(const double *mean_vos, const bbx_geom *g, int deg, d
     if (check_geom(g, "bbx_vos_fit")) return -1;
     BBX_REQUIRE(deg >= 0 && deg <= BBX_MAX_POLY_DEG, "bbx_vos_fit: degree %d not in 0..%d", deg, BBX_MAX_POLY_DEG);
     const size_t smem = (size_t)g->dy * (4 * sizeof(double) + 1) + 16;
-    BBX_REQUIRE(smem <= 227 * 1024, "bbx_vos_fit: %d rows need %zu bytes of shared memory", g->dy, smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-        BBX_CUDA(cudaFuncSetAttribute(vos_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    BBX_REQUIRE(smem <= 225 * 1024, "bbx_vos_fit: %d rows need %zu bytes of shared memory", g->dy, smem);
+    BBX_CUDA(cudaFuncSetAttribute(vos_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vos_fit_kernel<<<BBX_NCHAN, 256, smem, (cudaStream_t)stream>>>(mean_vos, *g, deg, nsigma, out_fit, out_coef, out_biasm, out_ok);
     BBX_CHECK_LAUNCH("bbx_vos_fit");
     return 0;
@@ -778,17 +774,15 @@ extern "C" int bbx_hos_stats(const void *raw, int raw_type, const bbx_geom *g, c
     BBX_REQUIRE(tel_kind == BBX_TEL_ML || satcnt != nullptr, "bbx_hos_stats: BlackGEM masking needs the saturated-column counts");
     const size_t cells = (size_t)g->hos_rows * g->xsize_chan;
     const size_t smem = cells * (sizeof(float) + 2) + g->xsize_chan + 16;
-    BBX_REQUIRE(smem <= 227 * 1024, "bbx_hos_stats: strip of %d x %d needs %zu bytes of shared memory", g->hos_rows, g->xsize_chan, smem);
+    BBX_REQUIRE(smem <= 225 * 1024, "bbx_hos_stats: strip of %d x %d needs %zu bytes of shared memory", g->hos_rows, g->xsize_chan, smem);
     ChanF32 gn; fill_chan_f32(gn, gain_h);
     cudaStream_t s = (cudaStream_t)stream;
     if (raw_type == BBX_RAW_U16) {
-        static bool done = false;
-        if (!done) { BBX_CUDA(cudaFuncSetAttribute(hos_stats_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        BBX_CUDA(cudaFuncSetAttribute(hos_stats_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hos_stats_kernel<uint16_t><<<BBX_NCHAN, 256, smem, s>>>((const uint16_t *)raw, *g, gn, vos_fit, tel_kind, data_limit, satcnt,
                                                               out_dlevel, out_mean, out_std, out_n, out_satcol);
     } else {
-        static bool done = false;
-        if (!done) { BBX_CUDA(cudaFuncSetAttribute(hos_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+        BBX_CUDA(cudaFuncSetAttribute(hos_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hos_stats_kernel<float><<<BBX_NCHAN, 256, smem, s>>>((const float *)raw, *g, gn, vos_fit, tel_kind, data_limit, satcnt,
                                                            out_dlevel, out_mean, out_std, out_n, out_satcol);
     }
@@ -817,9 +811,8 @@ extern "C" int bbx_hos_fit(const float *hos_mean, const float *hos_std, const in
 {
     if (check_geom(g, "bbx_hos_fit")) return -1;
     const size_t smem = (size_t)g->xsize_chan * (6 * sizeof(double) + 3) + 16;
-    BBX_REQUIRE(smem <= 227 * 1024, "bbx_hos_fit: %d columns need %zu bytes of shared memory", g->xsize_chan, smem);
-    static bool done = false;
-    if (!done) { BBX_CUDA(cudaFuncSetAttribute(hos_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); done = true; }
+    BBX_REQUIRE(smem <= 225 * 1024, "bbx_hos_fit: %d columns need %zu bytes of shared memory", g->xsize_chan, smem);
+    BBX_CUDA(cudaFuncSetAttribute(hos_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hos_fit_kernel<<<BBX_NCHAN, 256, smem, (cudaStream_t)stream>>>(hos_mean, hos_std, hos_n, satcol, *g, tel_kind, split_chan, split_col,
                                                                   out_oscan, out_need_spline, out_status);
     BBX_CHECK_LAUNCH("bbx_hos_fit");

@@ -143,6 +143,11 @@ int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const flo
 int bbx_satlevels(const double *sat_e_h, const double *biasm, double *out_satlevel,
                   void *stream);
 
+/* out[0] = BIASMEAN = nanmean(biasm[16]), out[1] = RDNOISE = nanmean(std_vos[16]), summed in
+ * numpy's order (blackbox.py:6865-6868); device scalars so LACosmic can start without a host
+ * round trip. */
+int bbx_header_means(const double *biasm, const double *std_vos, double *out, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Mask morphology -- mask_init blackbox.py:4473-4566, fill_sat_holes 4584-4596
  * ------------------------------------------------------------------------------------- */

@@ -1,0 +1,77 @@
+"""GPU parity of the whole chain (FramePipeline) against oracle.reduce_frame."""
+import numpy as np
+import pytest
+
+from conftest import float_class_ok
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(tel, seed, ysc):
+    from blackbox_b200 import synth
+    raw, truth = synth.make_raw(tel, seed, nstars=400, ncosmics=150)
+    shape = (2 * ysc, 10560)
+    mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
+    _, _, _, coeffs = synth.make_xtalk(seed + 2)
+    return raw, mbias, mflat, bpm, coeffs
+
+
+@pytest.mark.parametrize('tel,niter', [('ML1', 3), ('BG3', 4), ('BG2', 1)])
+def test_full_chain_parity(tel, niter, small_bb):
+    from blackbox_b200.pipeline import FramePipeline
+    from blackbox_b200 import set_bb
+    from oracle import reduce as R
+    ysc = 160
+    small_bb(ysc)
+    raw, mbias, mflat, bpm, coeffs = _inputs(tel, 4001, ysc)
+    raw[40:48, 2000:2008] = 65535                     # a saturated blob with neighbours
+    data_o, mask_o, hdr_o, hm_o = R.reduce_frame(raw, tel, mbias, mflat, bpm, coeffs,
+                                                 exptime=60.0, niter=niter)
+    pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
+                         niter=niter, exptime=60.0)
+    res = pipe.reduce(raw)
+    img, mask = res.img.cpu().numpy(), res.mask.cpu().numpy()
+    mv = set_bb.mask_value
+    # masks: bit-exact except documented threshold ties (<= 1e-5 of the pixels)
+    mism = np.mean(mask != mask_o)
+    assert mism <= 1e-5, 'mask mismatch fraction {}'.format(mism)
+    for name in ('saturated', 'saturated-connected', 'crosstalk', 'bad', 'edge'):
+        assert np.array_equal(mask & mv[name], mask_o & mv[name]), name
+    assert (mask & 0x80).sum() == 0
+    # float output
+    same_cr = (mask & mv['cosmic ray']) == (mask_o & mv['cosmic ray'])
+    ok = float_class_ok(img, data_o, scale=hdr_o['BIASMEAN'])
+    assert ok[same_cr].all(), np.abs(img - data_o)[same_cr].max()
+    assert np.mean(img == data_o) > 0.999
+    for key in ('BIASMEAN', 'RDNOISE', 'SATURATE'):
+        assert res.header[key] == pytest.approx(hdr_o[key], rel=1e-9)
+    assert res.header['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
+    if mism == 0:
+        assert res.header['NCOSMICS'] == pytest.approx(hdr_o['NCOSMICS'])
+    # a second frame through the same pipeline object (buffers are reused)
+    raw2, *_ = _inputs(tel, 4002, ysc)
+    data_o2, mask_o2, _, _ = R.reduce_frame(raw2, tel, mbias, mflat, bpm, coeffs, niter=niter)
+    res2 = pipe.reduce(raw2)
+    assert np.mean(res2.mask.cpu().numpy() != mask_o2) <= 1e-5
+    assert np.mean(res2.img.cpu().numpy() == data_o2) > 0.999
+
+
+def test_chain_spline_redo(small_bb):
+    """Columns < 150 with saturated pixels above them (BlackGEM) need the host spline: the
+    pipeline detects that on the device and redoes the frame through the strict path."""
+    from blackbox_b200.pipeline import FramePipeline
+    from oracle import reduce as R
+    tel, ysc = 'BG3', 160
+    small_bb(ysc)
+    raw, mbias, mflat, bpm, coeffs = _inputs(tel, 4100, ysc)
+    raw[100:160, 1500 * 2 + 20:1500 * 2 + 24] = 65535       # channel 3, columns 20..23, next to hos
+    diag = {}
+    data_o, mask_o, hdr_o, _ = R.reduce_frame(raw, tel, mbias, mflat, bpm, coeffs, niter=2, diag=diag)
+    assert diag['chans'][2]['spline_needed'].sum() >= 4
+    pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=2)
+    res = pipe.reduce(raw)
+    assert res.redo
+    assert np.mean(res.mask.cpu().numpy() != mask_o) <= 1e-5
+    img = res.img.cpu().numpy()
+    assert float_class_ok(img, data_o, scale=hdr_o['BIASMEAN']).mean() > 0.99999
+    assert np.mean(img == data_o) > 0.999
