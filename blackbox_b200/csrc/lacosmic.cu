@@ -326,43 +326,85 @@ extern "C" size_t bbx_lacosmic_work_bytes(int H, int W)
     return 3 * lac_align(n * sizeof(float)) + lac_align(n) + lac_align(sizeof(SelState)) + 256;
 }
 
-extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
-                            float sigclip, float sigfrac, float objlim, float readnoise,
-                            const double *readnoise_dev, int niter, void *work, long long *out_info,
-                            void *stream)
-{
-    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic: null argument");
-    BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic: bad shape %d x %d or niter %d", H, W, niter);
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)H * W;
-    uint8_t *p = (uint8_t *)work;
-    float *s = (float *)p; p += lac_align(n * sizeof(float));
-    float *noise = (float *)p; p += lac_align(n * sizeof(float));
-    float *f3 = (float *)p; p += lac_align(n * sizeof(float));
-    uint8_t *flags = p; p += lac_align(n);
-    SelState *sel = (SelState *)p; p += lac_align(sizeof(SelState));
-    float *background = (float *)p;
+struct LacWork {
+    float *s, *noise, *f3;
+    uint8_t *flags;
+    SelState *sel;
+    float *background;
+};
 
+static LacWork carve_lac_work(void *work, size_t n)
+{
+    LacWork w;
+    uint8_t *p = (uint8_t *)work;
+    w.s = (float *)p; p += lac_align(n * sizeof(float));
+    w.noise = (float *)p; p += lac_align(n * sizeof(float));
+    w.f3 = (float *)p; p += lac_align(n * sizeof(float));
+    w.flags = p; p += lac_align(n);
+    w.sel = (SelState *)p; p += lac_align(sizeof(SelState));
+    w.background = (float *)p;
+    return w;
+}
+
+static LacParams make_params(float sigclip, float sigfrac, float objlim, float readnoise, const double *readnoise_dev)
+{
     LacParams prm;
     prm.sigclip = sigclip;
     prm.sigcliplow = sigfrac * sigclip;      // float32 product, as the reference's C float
     prm.objlim = objlim;
     prm.readnoise = readnoise;
     prm.readnoise_dev = readnoise_dev;
+    return prm;
+}
 
+static int lac_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
+                         int it, const LacWork &w, long long *info, cudaStream_t st)
+{
+    const dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
+    lac_stage1_kernel<<<grid, 256, 0, st>>>(img, w.s, w.noise, w.f3, H, W, prm, info);
+    lac_stage2_kernel<<<grid, 256, 0, st>>>(w.s, w.noise, w.f3, inmask, w.flags, H, W, prm, info, nullptr, nullptr);
+    lac_grow_kernel<<<grid, 256, 0, st>>>(w.flags, crmask, H, W, it, info);
+    lac_control_kernel<<<1, 1, 0, st>>>(info, it);
+    lac_clean_kernel<<<grid, 256, 0, st>>>(img, crmask, inmask, H, W, w.background, info);
+    BBX_CHECK_LAUNCH("lac_iteration");
+    return 0;
+}
+
+extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                                  int niter, void *work, long long *out_info, void *stream)
+{
+    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
+    BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)H * W;
+    const LacWork w = carve_lac_work(work, n);
     BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
     lac_init_kernel<<<1, 32, 0, st>>>(out_info, INFO_NCR + niter);
-    if (bbx_masked_lower_median(img, inmask, n, sel, background, stream)) return -2;
+    BBX_CHECK_LAUNCH("lac_init_kernel");
+    return bbx_masked_lower_median(img, inmask, n, w.sel, w.background, stream) ? -2 : 0;
+}
 
-    const dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
-    for (int it = 0; it < niter; it++) {
-        lac_stage1_kernel<<<grid, 256, 0, st>>>(img, s, noise, f3, H, W, prm, out_info);
-        lac_stage2_kernel<<<grid, 256, 0, st>>>(s, noise, f3, inmask, flags, H, W, prm, out_info, nullptr, nullptr);
-        lac_grow_kernel<<<grid, 256, 0, st>>>(flags, crmask, H, W, it, out_info);
-        lac_control_kernel<<<1, 1, 0, st>>>(out_info, it);
-        lac_clean_kernel<<<grid, 256, 0, st>>>(img, crmask, inmask, H, W, background, out_info);
-    }
-    BBX_CHECK_LAUNCH("bbx_lacosmic");
+extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                                      float sigclip, float sigfrac, float objlim, float readnoise,
+                                      const double *readnoise_dev, int iter, void *work, long long *out_info,
+                                      void *stream)
+{
+    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_iteration: null argument");
+    const LacWork w = carve_lac_work(work, (size_t)H * W);
+    return lac_iteration(img, inmask, crmask, H, W, make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev),
+                         iter, w, out_info, (cudaStream_t)stream);
+}
+
+extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                            float sigclip, float sigfrac, float objlim, float readnoise,
+                            const double *readnoise_dev, int niter, void *work, long long *out_info,
+                            void *stream)
+{
+    if (bbx_lacosmic_begin(img, inmask, crmask, H, W, niter, work, out_info, stream)) return -2;
+    const LacWork w = carve_lac_work(work, (size_t)H * W);
+    const LacParams prm = make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
+    for (int it = 0; it < niter; it++)
+        if (lac_iteration(img, inmask, crmask, H, W, prm, it, w, out_info, (cudaStream_t)stream)) return -2;
     return 0;
 }
 

@@ -2,16 +2,17 @@
 
 ``FramePipeline.enqueue(raw)`` puts the whole chain of blackbox_reduce's array steps
 (blackbox.py:1479-1902: gain -> overscan -> master bias -> mask_init -> master flat ->
-LACosmic -> crosstalk) on the current CUDA stream without any host synchronisation and without
-allocating: every scratch buffer is created once per pipeline.  ``finish()`` synchronises,
-checks the device-side status words (rarely needed smoothing spline, failed fits, hole filling
-that needs more rounds) and returns the header values.
+LACosmic -> crosstalk) on the current CUDA stream.  Nothing is allocated per frame: every
+scratch buffer is created once per pipeline.  There is exactly one short host round trip per
+frame, right after the overscan statistics (< 1 ms of GPU work): the host reads the 16
+"spline needed" flags and, for the channels that have saturated-star columns among the first
+150 horizontal-overscan columns, evaluates FITPACK's smoothing spline (hostfit.py).
+``finish()`` synchronises, checks the remaining device status word (hole filling that needs
+more rounds) and returns the header values.
 
 Frames are independent, so a night batch shards one frame per GPU (``shard_frames``); nothing
 is exchanged between ranks.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 
@@ -25,10 +26,11 @@ from .set_bb import get_par
 class FrameResult:
     """Outputs and header values of one reduced frame."""
 
-    def __init__(self, img, mask, header, header_mask, redo=False):
+    def __init__(self, img, mask, header, header_mask, spline_columns=0, redo=False):
         self.img, self.mask = img, mask
         self.header, self.header_mask = header, header_mask
-        self.redo = redo            # True if the frame had to take the strict (host spline) path
+        self.spline_columns = spline_columns   # overscan columns taken from the host spline
+        self.redo = redo                       # hole filling needed extra rounds -> chain redone
 
 
 class FramePipeline:
@@ -54,25 +56,39 @@ class FramePipeline:
         self.crmask = torch.empty((RH, RW), dtype=torch.uint8, device=dev)
         self.means = torch.zeros(2, dtype=torch.float64, device=dev)      # BIASMEAN, RDNOISE
         self.ncosmic = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flags_host = torch.zeros(2 * self.geom.nchans, dtype=torch.uint8).pin_memory()
         self._raw = None
         self._out = None
+        self._spline_cols = 0
 
     # ---------------------------------------------------------------------------------------
-    def enqueue(self, raw_t, out_img=None, out_mask=None):
-        """Enqueue the full chain for one raw frame (uint16 or float32 CUDA tensor)."""
-        tel, geom, st = self.tel, self.geom, self.st
+    def _gain_for(self, raw_t):
+        return self.gain if R._raw_type(raw_t) == 0 else None
+
+    def _overscan(self, raw_t):
+        """Overscan statistics + fits on the device, then the one host round trip."""
+        st = self.st
+        R.overscan_enqueue(raw_t, self.geom, self.tel, gain=self._gain_for(raw_t), state=st)
+        flags = torch.cat([st.need_spline.any(dim=1).to(torch.uint8),
+                           (st.fit_status != 0).to(torch.uint8)])
+        self._flags_host.copy_(flags, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        f = self._flags_host.numpy()
+        n = self.geom.nchans
+        self._spline_cols = 0
+        if f[n:].any() or f[:n].any():
+            self._spline_cols = R.overscan_resolve_spline(st, strict=False)
+        call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
+
+    def _rest(self, raw_t, out_img, out_mask, wait_holes=False):
+        tel, geom = self.tel, self.geom
         RH, RW = geom.red_shape
         s = R._stream()
-        if out_img is None:
-            out_img = torch.empty((RH, RW), dtype=torch.float32, device=self.device)
-        if out_mask is None:
-            out_mask = torch.empty((RH, RW), dtype=torch.uint8, device=self.device)
-        gain = self.gain if R._raw_type(raw_t) == 0 else None
-        R.overscan_enqueue(raw_t, geom, tel, gain=gain, state=st)
-        call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), s)
-        R.apply_enqueue(raw_t, geom, tel, st=st, gain=gain, mbias=self.mbias, mflat=self.mflat,
-                        bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask)
+        R.apply_enqueue(raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias,
+                        mflat=self.mflat, bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask)
         R.mask_morph_enqueue(out_mask, tel, self.mwork, count_objects=self.count_objects)
+        if wait_holes:
+            R.mask_morph_finish(out_mask, tel, self.mwork)
         if self.niter > 0:
             R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
                                get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
@@ -84,21 +100,38 @@ class FramePipeline:
                      R._ptr(self.ncosmic), s)
         if self.coeffs is not None:
             R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
+
+    def enqueue(self, raw_t, out_img=None, out_mask=None):
+        """Run the overscan stage and enqueue the rest of the chain for one raw frame (uint16
+        or float32 CUDA tensor).  Returns the output tensors (valid after ``finish``)."""
+        RH, RW = self.geom.red_shape
+        if out_img is None:
+            out_img = torch.empty((RH, RW), dtype=torch.float32, device=self.device)
+        if out_mask is None:
+            out_mask = torch.empty((RH, RW), dtype=torch.uint8, device=self.device)
+        self._overscan(raw_t)
+        self._rest(raw_t, out_img, out_mask)
         self._raw, self._out = raw_t, (out_img, out_mask)
         return out_img, out_mask
+
+    def enqueue_status(self, host_slot):
+        """Enqueue a copy of the hole-filling status word into the pinned int32[1] tensor
+        ``host_slot`` (valid after the stream is synchronised): non-zero means the frame has to
+        be finished with ``finish()`` before its outputs are used."""
+        host_slot.copy_(self.mwork.unconverged, non_blocking=True)
 
     # ---------------------------------------------------------------------------------------
     def finish(self, fill_header=True):
         """Synchronise, verify the device status of the last enqueued frame and return its
-        FrameResult.  Frames that needed the smoothing spline (or more hole-filling rounds)
-        are redone through the strict path so the result is always the reference's."""
+        FrameResult."""
         st = self.st
         out_img, out_mask = self._out
         redo = False
-        need = bool(st.need_spline.any().item())
-        if need or bool(st.fit_status.any().item()) or int(self.mwork.unconverged.item()) != 0:
+        if int(self.mwork.unconverged.item()) != 0:
+            # the mask LACosmic saw was not final: redo everything after the overscan stage
             redo = True
-            self._redo_strict()
+            self._rest(self._raw, out_img, out_mask, wait_holes=True)
+            torch.cuda.current_stream().synchronize()
         header, header_mask = {}, {}
         if fill_header:
             R.fill_os_header(header, st)
@@ -113,35 +146,7 @@ class FramePipeline:
                 header['NCOSMICS'] = header_mask['NCOSMICS'] = nc
                 info = self.lwork.info.cpu().numpy()
                 header['LAC-NIT'] = int(info[0])
-        return FrameResult(out_img, out_mask, header, header_mask, redo)
-
-    def _redo_strict(self):
-        """Slow path: host spline, then the remaining chain again."""
-        tel, geom, st = self.tel, self.geom, self.st
-        raw_t = self._raw
-        out_img, out_mask = self._out
-        gain = self.gain if R._raw_type(raw_t) == 0 else None
-        R.overscan_enqueue(raw_t, geom, tel, gain=gain, state=st)
-        R.overscan_resolve_spline(st, strict=False)
-        s = R._stream()
-        call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), s)
-        R.apply_enqueue(raw_t, geom, tel, st=st, gain=gain, mbias=self.mbias, mflat=self.mflat,
-                        bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask)
-        R.mask_morph_enqueue(out_mask, tel, self.mwork, count_objects=self.count_objects)
-        R.mask_morph_finish(out_mask, tel, self.mwork)
-        RH, RW = geom.red_shape
-        if self.niter > 0:
-            R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
-                               get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
-                               self.niter, self.lwork, readnoise_dev=self.means[1:])
-            bit = int(get_par(set_bb.mask_value, tel)['cosmic ray'])
-            call('bbx_mask_or', R._ptr(out_mask), R._ptr(self.crmask), out_mask.numel(), bit, s)
-            if self.count_objects:
-                call('bbx_count_objects', R._ptr(self.crmask), 1, RH, RW, R._ptr(self.mwork.labels),
-                     R._ptr(self.ncosmic), s)
-        if self.coeffs is not None:
-            R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
-        torch.cuda.current_stream().synchronize()
+        return FrameResult(out_img, out_mask, header, header_mask, self._spline_cols, redo)
 
     # ---------------------------------------------------------------------------------------
     def reduce(self, raw):

@@ -212,6 +212,16 @@ int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int 
                  const double *readnoise_dev, int niter, void *work, long long *out_info,
                  void *stream);
 
+/* The same in two parts, so one iteration can be enqueued (and timed) on its own:
+ * _begin zeroes crmask / out_info and computes the background level, _iteration enqueues the
+ * kernels of iteration `iter` (a no-op on the device once an earlier iteration found nothing). */
+int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                       int niter, void *work, long long *out_info, void *stream);
+int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                           float sigclip, float sigfrac, float objlim, float readnoise,
+                           const double *readnoise_dev, int iter, void *work, long long *out_info,
+                           void *stream);
+
 /* lower median a[(n-1)/2] of the pixels with inmask == 0 (astroscrappy's background level)
  * work >= bbx_select_work_bytes(); out device float32 */
 size_t bbx_select_work_bytes(void);
