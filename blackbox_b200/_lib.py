@@ -55,9 +55,9 @@ _SIGNATURES = {
     'bbx_xtalk': [P, P, I, I, I, I, P, BITS, P],
     'bbx_stack_median': [P, P, I, SZ, I, P, I, P, P],
     'bbx_lacosmic_work_bytes': [I, I],
-    'bbx_lacosmic': [P, P, P, I, I, F, F, F, F, P, I, P, P, P],
-    'bbx_lacosmic_begin': [P, P, P, I, I, I, P, P, P],
-    'bbx_lacosmic_iteration': [P, P, P, I, I, F, F, F, F, P, I, P, P, P],
+    'bbx_lacosmic': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],
+    'bbx_lacosmic_begin': [P, P, P, I, I, I, I, P, P, P],
+    'bbx_lacosmic_iteration': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],
     'bbx_select_work_bytes': [],
     'bbx_masked_lower_median': [P, P, SZ, P, P, P],
     'bbx_medfilt': [P, P, I, I, I, P],

@@ -19,53 +19,7 @@
 // The iteration loop is enqueued up front; a device-side flag turns the kernels of later
 // iterations into no-ops once an iteration finds nothing (the reference's `break`), so no
 // host synchronisation is needed.
-#include "bbx_common.cuh"
-#include "median_networks.cuh"
-
-// out_info layout (int64): [0] iterations run, [1] active flag, [2+k] new CR pixels of iteration k
-#define INFO_ITERS 0
-#define INFO_ACTIVE 1
-#define INFO_NCR 2
-
-// --------------------------------------------------------------------------------------------
-// building blocks
-// --------------------------------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ float median_at(const float *__restrict__ in, int H, int W, int y, int x)
-{
-    constexpr int R = K / 2;
-    if (y < R || y >= H - R || x < R || x >= W - R) return in[(size_t)y * W + x];
-    float v[K * K];
-#pragma unroll
-    for (int dy = 0; dy < K; dy++)
-#pragma unroll
-        for (int dx = 0; dx < K; dx++) v[dy * K + dx] = in[(size_t)(y + dy - R) * W + (x + dx - R)];
-    if constexpr (K == 3) return bbx_med9(v);
-    else if constexpr (K == 5) return bbx_med25(v);
-    else return bbx_med49(v);
-}
-
-// L+ of pixel (y,x): the four Laplacian values of its 2x2 sub-pixels, clipped at 0, averaged
-__device__ __forceinline__ float laplace_plus_at(const float *__restrict__ in, int H, int W, int y, int x)
-{
-    const size_t i = (size_t)y * W + x;
-    const float c = in[i];
-    const bool hl = x > 0, hr = x + 1 < W, hu = y > 0, hd = y + 1 < H;   // u = previous row
-    const float l = hl ? in[i - 1] : 0.f, r = hr ? in[i + 1] : 0.f;
-    const float u = hu ? in[i - W] : 0.f, d = hd ? in[i + W] : 0.f;
-    const float c4 = 4.0f * c;
-    // order of subtraction: right, left, next row, previous row (missing neighbours skipped)
-    float s00 = c4 - c; if (hl) s00 = s00 - l; s00 = s00 - c; if (hu) s00 = s00 - u;
-    float s01 = c4; if (hr) s01 = s01 - r; s01 = s01 - c; s01 = s01 - c; if (hu) s01 = s01 - u;
-    float s10 = c4 - c; if (hl) s10 = s10 - l; if (hd) s10 = s10 - d; s10 = s10 - c;
-    float s11 = c4; if (hr) s11 = s11 - r; s11 = s11 - c; if (hd) s11 = s11 - d; s11 = s11 - c;
-    s00 = s00 < 0.f ? 0.f : s00; s01 = s01 < 0.f ? 0.f : s01;
-    s10 = s10 < 0.f ? 0.f : s10; s11 = s11 < 0.f ? 0.f : s11;
-    float p = s00 + s01;
-    p = p + s10;
-    p = p + s11;
-    return p / 4.0f;
-}
+#include "lacosmic_common.cuh"
 
 template <int K>
 __global__ void __launch_bounds__(256)
@@ -87,18 +41,6 @@ laplace_plus_kernel(const float *__restrict__ in, float *__restrict__ out, int H
 // --------------------------------------------------------------------------------------------
 // iteration kernels
 // --------------------------------------------------------------------------------------------
-struct LacParams {
-    float sigclip, sigcliplow, objlim;
-    float readnoise;                 // used when readnoise_dev == nullptr
-    const double *readnoise_dev;     // device scalar (e.g. RDNOISE computed on the GPU), or null
-};
-
-__device__ __forceinline__ float lac_rn2(const LacParams &p)
-{
-    const float rn = p.readnoise_dev ? (float)(*p.readnoise_dev) : p.readnoise;
-    return rn * rn;
-}
-
 __global__ void __launch_bounds__(256)
 lac_stage1_kernel(const float *__restrict__ clean, float *__restrict__ s, float *__restrict__ noise,
                   float *__restrict__ f3, int H, int W, LacParams prm, const long long *__restrict__ info)
@@ -230,24 +172,6 @@ lac_clean_kernel(float *clean, const uint8_t *__restrict__ crmask, const uint8_t
 // exact rank selection over the unmasked pixels (radix select on order-preserving keys,
 // 11 + 11 + 10 bits): astroscrappy's background level = lower median a[(n-1)/2]
 // --------------------------------------------------------------------------------------------
-#define SEL_BINS 2048
-struct SelState {
-    unsigned long long k;       // rank still to find inside the current prefix
-    unsigned int prefix;        // key bits fixed so far
-    unsigned int pad;
-    unsigned int hist[3][SEL_BINS];
-};
-
-__device__ __forceinline__ unsigned int f32_key(float f)
-{
-    const unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_f32(unsigned int k)
-{
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 template <int PASS>
 __global__ void __launch_bounds__(512)
 select_hist_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SelState *st)
@@ -320,7 +244,7 @@ extern "C" int bbx_masked_lower_median(const float *img, const uint8_t *inmask, 
 // --------------------------------------------------------------------------------------------
 static size_t lac_align(size_t v) { return (v + 255) / 256 * 256; }
 
-extern "C" size_t bbx_lacosmic_work_bytes(int H, int W)
+size_t lac_dense_work_bytes(int H, int W)
 {
     const size_t n = (size_t)H * W;
     return 3 * lac_align(n * sizeof(float)) + lac_align(n) + lac_align(sizeof(SelState)) + 256;
@@ -346,7 +270,7 @@ static LacWork carve_lac_work(void *work, size_t n)
     return w;
 }
 
-static LacParams make_params(float sigclip, float sigfrac, float objlim, float readnoise, const double *readnoise_dev)
+LacParams lac_make_params(float sigclip, float sigfrac, float objlim, float readnoise, const double *readnoise_dev)
 {
     LacParams prm;
     prm.sigclip = sigclip;
@@ -357,55 +281,29 @@ static LacParams make_params(float sigclip, float sigfrac, float objlim, float r
     return prm;
 }
 
-static int lac_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
-                         int it, const LacWork &w, long long *info, cudaStream_t st)
+int lac_dense_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
+                        int it, void *work, long long *info, cudaStream_t st)
 {
+    const LacWork w = carve_lac_work(work, (size_t)H * W);
     const dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
     lac_stage1_kernel<<<grid, 256, 0, st>>>(img, w.s, w.noise, w.f3, H, W, prm, info);
     lac_stage2_kernel<<<grid, 256, 0, st>>>(w.s, w.noise, w.f3, inmask, w.flags, H, W, prm, info, nullptr, nullptr);
     lac_grow_kernel<<<grid, 256, 0, st>>>(w.flags, crmask, H, W, it, info);
     lac_control_kernel<<<1, 1, 0, st>>>(info, it);
     lac_clean_kernel<<<grid, 256, 0, st>>>(img, crmask, inmask, H, W, w.background, info);
-    BBX_CHECK_LAUNCH("lac_iteration");
+    BBX_CHECK_LAUNCH("lac_dense_iteration");
     return 0;
 }
 
-extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
-                                  int niter, void *work, long long *out_info, void *stream)
+int lac_dense_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, int niter, void *work,
+                    long long *info, cudaStream_t st)
 {
-    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
-    BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)H * W;
     const LacWork w = carve_lac_work(work, n);
     BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
-    lac_init_kernel<<<1, 32, 0, st>>>(out_info, INFO_NCR + niter);
+    lac_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter);
     BBX_CHECK_LAUNCH("lac_init_kernel");
-    return bbx_masked_lower_median(img, inmask, n, w.sel, w.background, stream) ? -2 : 0;
-}
-
-extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
-                                      float sigclip, float sigfrac, float objlim, float readnoise,
-                                      const double *readnoise_dev, int iter, void *work, long long *out_info,
-                                      void *stream)
-{
-    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_iteration: null argument");
-    const LacWork w = carve_lac_work(work, (size_t)H * W);
-    return lac_iteration(img, inmask, crmask, H, W, make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev),
-                         iter, w, out_info, (cudaStream_t)stream);
-}
-
-extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
-                            float sigclip, float sigfrac, float objlim, float readnoise,
-                            const double *readnoise_dev, int niter, void *work, long long *out_info,
-                            void *stream)
-{
-    if (bbx_lacosmic_begin(img, inmask, crmask, H, W, niter, work, out_info, stream)) return -2;
-    const LacWork w = carve_lac_work(work, (size_t)H * W);
-    const LacParams prm = make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
-    for (int it = 0; it < niter; it++)
-        if (lac_iteration(img, inmask, crmask, H, W, prm, it, w, out_info, (cudaStream_t)stream)) return -2;
-    return 0;
+    return bbx_masked_lower_median(img, inmask, n, w.sel, w.background, (void *)st) ? -2 : 0;
 }
 
 extern "C" int bbx_medfilt(const float *in, float *out, int H, int W, int ksize, void *stream)

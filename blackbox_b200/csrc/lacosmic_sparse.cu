@@ -1,0 +1,642 @@
+// lacosmic_sparse.cu -- LACosmic with lazy evaluation: bit-identical results to the dense
+// implementation (lacosmic.cu) at a tiny fraction of the arithmetic.
+//
+// Observation (all inequalities hold exactly in float32 because +, /, sqrt and the median are
+// monotone under round-to-nearest):
+//   * s  = L+ / (2 noise) >= 0 everywhere, hence med5(s) >= 0 and  s' = s - med5(s) <= s;
+//   * noise = sqrt(max(med5(img), 1e-5) + rn^2) >= noise_min = sqrt(1e-5 + rn^2), hence
+//     s <= s_ub = L+ / (2 noise_min);
+//   * a pixel can only become a cosmic-ray pixel if it lies within 2 pixels of a candidate
+//     c0 = (s' > sigclip) & good & (s'/f > objlim), and c0 needs s' > sigclip.
+// So one dense, HBM-bound pass computes only the 5-point Laplacian L+ and keeps the pixels with
+// s_ub > sigclip (a few 1e-4 of a typical frame).  Everything else -- the 5x5 / 3x3 / 7x7
+// medians, the fine-structure image, the two growth steps and the cleaning -- is evaluated
+// only where its value can influence the result, from short device-side work lists:
+//
+//   scan   (dense)   L+ -> list A  = { s_ub > sigclip }
+//   cand1  (list A)  good, med5(img), s > sigclip            -> list B
+//   cand2  (list B)  warp per pixel: s on 5x5, s' ; f on 7x7 -> c0 flag, list C0
+//   grow1  (C0 x 9)  warp per neighbour: s' > sigclip & good -> c1 flag, list C1
+//   grow2  (C1 x 9)  warp per neighbour: s' > sigcliplow & good -> c2: count, crmask, CR list
+//   clean  (CR list) lower median of the unflagged 5x5 neighbours
+//
+// The reference's background level (lower median of all unmasked pixels of the input image,
+// used for CR pixels without any usable neighbour) is found without extra dense passes: a
+// strided sample of <= 2^18 pixels brackets the median rank (+-5 sigma of the sampling error),
+// the first iteration's scan counts the pixels below the bracket and collects those inside it,
+// and a radix select over that short list returns the exact order statistic.  If the bracket
+// misses (or a work list overflows) a status bit is raised and the caller repeats the frame
+// with the dense implementation (LAC_STATUS_NEED_BG / LAC_STATUS_OVERFLOW).
+#include "lacosmic_common.cuh"
+
+#define FLAG_C0 1u
+#define FLAG_C1 2u
+#define FLAG_C2 4u
+
+struct SparseCounters {
+    unsigned int nA, nB, nC0, nC1, nCR;
+    unsigned int pad[3];
+};
+
+#define BG_SAMPLES 262144u
+
+struct BgState {
+    float a, b;                          // bracket of the median, from the sample
+    unsigned int n_list;                 // values collected inside [a, b]
+    unsigned int pad;
+    unsigned long long n_valid, n_below; // unmasked pixels; unmasked pixels < a
+};
+
+struct SparseWork {
+    uint8_t *flags;              // [N] per pixel: (iteration stamp << 4) | FLAG_*
+    unsigned int *listA, *listB, *listC0, *listC1, *listCR;
+    unsigned int capA, capB, capC, capCR, capBG;
+    SparseCounters *cnt;
+    BgState *bg;
+    float *sample;               // [BG_SAMPLES]
+    float *bglist;               // [capBG]
+    SelState *sel;
+    float *background;
+};
+
+static size_t sp_align(size_t v) { return (v + 255) / 256 * 256; }
+
+static void sparse_caps(size_t n, unsigned int &capA, unsigned int &capB, unsigned int &capC, unsigned int &capCR)
+{
+    // generous: a typical 10560^2 frame has ~1e4..1e5 entries in A and ~1e4 cosmic-ray pixels
+    capA = (unsigned int)(n / 8 + 1024);
+    capB = (unsigned int)(n / 32 + 1024);
+    capC = (unsigned int)(n / 32 + 1024);
+    capCR = (unsigned int)(n / 16 + 1024);
+}
+static unsigned int sparse_cap_bg(size_t n) { return (unsigned int)(n / 16 + 4096); }
+
+size_t lac_sparse_work_bytes(int H, int W)
+{
+    const size_t n = (size_t)H * W;
+    unsigned int a, b, c, cr;
+    sparse_caps(n, a, b, c, cr);
+    return sp_align(n) + sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + sp_align(4ull * cr) +
+           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(BgState)) + sp_align(4ull * BG_SAMPLES) +
+           sp_align(4ull * sparse_cap_bg(n)) + sp_align(sizeof(SelState)) + 512;
+}
+
+static SparseWork carve_sparse(void *work, size_t n)
+{
+    SparseWork w;
+    sparse_caps(n, w.capA, w.capB, w.capC, w.capCR);
+    uint8_t *p = (uint8_t *)work;
+    w.flags = p; p += sp_align(n);
+    w.listA = (unsigned int *)p; p += sp_align(4ull * w.capA);
+    w.listB = (unsigned int *)p; p += sp_align(4ull * w.capB);
+    w.listC0 = (unsigned int *)p; p += sp_align(4ull * w.capC);
+    w.listC1 = (unsigned int *)p; p += sp_align(4ull * w.capC);
+    w.listCR = (unsigned int *)p; p += sp_align(4ull * w.capCR);
+    w.cnt = (SparseCounters *)p; p += sp_align(sizeof(SparseCounters));
+    w.bg = (BgState *)p; p += sp_align(sizeof(BgState));
+    w.sample = (float *)p; p += sp_align(4ull * BG_SAMPLES);
+    w.capBG = sparse_cap_bg(n);
+    w.bglist = (float *)p; p += sp_align(4ull * w.capBG);
+    w.sel = (SelState *)p; p += sp_align(sizeof(SelState));
+    w.background = (float *)p;
+    return w;
+}
+
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void list_push(unsigned int *list, unsigned int *count, unsigned int cap,
+                                          unsigned int value, long long *info)
+{
+    const unsigned int slot = atomicAdd(count, 1u);
+    if (slot < cap) list[slot] = value;
+    else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_OVERFLOW);
+}
+
+// set `bit` in the flag byte of pixel p for iteration stamp `stamp`; returns true if the bit
+// was not set before (for this stamp).  32-bit CAS on the word that holds the byte.
+__device__ __forceinline__ bool flag_set(uint8_t *flags, size_t p, unsigned int stamp, unsigned int bit)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(flags + (p & ~(size_t)3));
+    const unsigned int shift = (unsigned int)(p & 3) * 8;
+    unsigned int old = *word;
+    for (;;) {
+        const unsigned int b = (old >> shift) & 0xffu;
+        const unsigned int cur = ((b >> 4) == stamp) ? (b & 0xfu) : 0u;
+        if (cur & bit) return false;
+        const unsigned int nb = (stamp << 4) | cur | bit;
+        const unsigned int nw = (old & ~(0xffu << shift)) | (nb << shift);
+        const unsigned int seen = atomicCAS(word, old, nw);
+        if (seen == old) return true;
+        old = seen;
+    }
+}
+
+__device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsigned int cap)
+{
+    const unsigned int n = *count;
+    return n < cap ? n : cap;
+}
+
+// --------------------------------------------------------------------------------------------
+// dense scan: 4 pixels per thread, 128-bit loads of the three rows
+// --------------------------------------------------------------------------------------------
+// COLLECT (first iteration only): also count the unmasked pixels and those below the median
+// bracket, and gather the values inside the bracket (block-aggregated appends).
+template <bool COLLECT>
+__global__ void __launch_bounds__(256)
+sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
+               SparseWork w, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    __shared__ float s_buf[COLLECT ? 1024 : 1];
+    __shared__ unsigned int s_cnt, s_base;
+    __shared__ unsigned long long s_red[33];
+    unsigned int n_valid = 0, n_below = 0;
+    float bra = 0.f, brb = 0.f;
+    if (COLLECT) {
+        bra = w.bg->a; brb = w.bg->b;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    }
+    // smallest possible noise: med5 floored at 1e-5
+    float nmin = 0.00001f + lac_rn2(prm);
+    nmin = sqrtf(nmin);
+    const float den_min = 2.0f * nmin;
+    const int groups = (W + 3) / 4;
+    const long long total = (long long)H * groups;
+    const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+      const long long t = base + threadIdx.x;
+      if (t < total) {
+        const int y = (int)(t / groups), x0 = (int)(t - (long long)y * groups) * 4;
+        if (COLLECT) {
+            for (int k = 0; k < 4 && x0 + k < W; k++) {
+                const size_t i = (size_t)y * W + x0 + k;
+                if (inmask && inmask[i]) continue;
+                const float v = img[i];
+                n_valid++;
+                if (v < bra) n_below++;
+                else if (v <= brb) s_buf[atomicAdd(&s_cnt, 1u)] = v;
+            }
+        }
+        if (vec_ok && y > 0 && y + 1 < H && x0 > 0 && x0 + 4 < W) {
+            const size_t i = (size_t)y * W + x0;
+            const float4 c = *reinterpret_cast<const float4 *>(img + i);
+            const float4 u = *reinterpret_cast<const float4 *>(img + i - W);
+            const float4 d = *reinterpret_cast<const float4 *>(img + i + W);
+            const float lft = img[i - 1], rgt = img[i + 4];
+            const float cc[6] = {lft, c.x, c.y, c.z, c.w, rgt};
+            const float uu[4] = {u.x, u.y, u.z, u.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                s00 = s00 < 0.f ? 0.f : s00; s01 = s01 < 0.f ? 0.f : s01;
+                s10 = s10 < 0.f ? 0.f : s10; s11 = s11 < 0.f ? 0.f : s11;
+                float p = s00 + s01; p = p + s10; p = p + s11;
+                const float lp = p / 4.0f;
+                const float sub = lp / den_min;
+                if (sub > prm.sigclip) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+            }
+        } else {
+            for (int k = 0; k < 4 && x0 + k < W; k++) {
+                const float lp = laplace_plus_at(img, H, W, y, x0 + k);
+                const float sub = lp / den_min;
+                if (sub > prm.sigclip) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)((size_t)y * W + x0 + k), info);
+            }
+        }
+      }
+      if (COLLECT) {
+          __syncthreads();
+          const unsigned int c = s_cnt;
+          if (c) {
+              if (threadIdx.x == 0) s_base = atomicAdd(&w.bg->n_list, c);
+              __syncthreads();
+              const unsigned int b0 = s_base;
+              for (unsigned int j = threadIdx.x; j < c; j += blockDim.x)
+                  if (b0 + j < w.capBG) w.bglist[b0 + j] = s_buf[j];
+              __syncthreads();
+              if (threadIdx.x == 0) s_cnt = 0;
+          }
+          __syncthreads();
+      }
+    }
+    if (COLLECT) {
+        const unsigned long long tv = block_sum((unsigned long long)n_valid, s_red);
+        const unsigned long long tb = block_sum((unsigned long long)n_below, s_red);
+        if (threadIdx.x == 0) {
+            if (tv) atomicAdd(&w.bg->n_valid, tv);
+            if (tb) atomicAdd(&w.bg->n_below, tb);
+        }
+    }
+}
+
+// ---- background level ----------------------------------------------------------------------
+// rank-th smallest (0-based) of vals[0..n) by one block, 3-pass radix select
+__device__ float block_radix_select(const float *vals, unsigned int n, unsigned int rank, unsigned int *hist,
+                                    unsigned int *s_state)
+{
+    unsigned int prefix = 0, k = rank;
+    for (int pass = 0; pass < 3; pass++) {
+        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned int key = f32_key(vals[i]);
+            if (pass == 0) atomicAdd(&hist[key >> 21], 1u);
+            else if (pass == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&hist[(key >> 10) & 0x7ffu], 1u); }
+            else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&hist[key & 0x3ffu], 1u); }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nb = pass == 2 ? 1024 : SEL_BINS;
+            unsigned int acc = 0;
+            int b = 0;
+            for (; b < nb - 1; b++) {
+                if (acc + hist[b] > k) break;
+                acc += hist[b];
+            }
+            s_state[0] = k - acc;
+            s_state[1] = pass == 0 ? ((unsigned int)b << 21) : pass == 1 ? (prefix | ((unsigned int)b << 10)) : (prefix | (unsigned int)b);
+        }
+        __syncthreads();
+        k = s_state[0];
+        prefix = s_state[1];
+        __syncthreads();
+    }
+    return key_f32(prefix);
+}
+
+__global__ void __launch_bounds__(1024)
+sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
+{
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ unsigned int s_state[2];
+    __shared__ unsigned int s_ns;
+    if (threadIdx.x == 0) s_ns = 0;
+    __syncthreads();
+    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
+    for (size_t j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) {
+        const size_t i = j * stride;
+        if (i >= n) break;
+        if (inmask && inmask[i]) continue;
+        w.sample[atomicAdd(&s_ns, 1u)] = img[i];
+    }
+    __syncthreads();
+    const unsigned int ns = s_ns;
+    float a = -INFINITY, b = INFINITY;
+    if (ns > 0) {
+        const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
+        if (mid > d) a = block_radix_select(w.sample, ns, mid - d, hist, s_state);
+        if (mid + d < ns - 1) b = block_radix_select(w.sample, ns, mid + d, hist, s_state);
+    }
+    if (threadIdx.x == 0) {
+        w.bg->a = a; w.bg->b = b;
+        w.bg->n_list = 0; w.bg->n_valid = 0; w.bg->n_below = 0;
+    }
+}
+
+// after the first scan: rank of the median inside the collected list (or failure)
+__global__ void sp_bg_rank_kernel(SparseWork w, long long *info)
+{
+    if (threadIdx.x != 0) return;
+    SelState *st = w.sel;
+    for (int i = 0; i < 3 * SEL_BINS; i++) (&st->hist[0][0])[i] = 0;
+    st->prefix = 0;
+    const unsigned long long nv = w.bg->n_valid, nb = w.bg->n_below;
+    const unsigned int nl = w.bg->n_list;
+    if (nv == 0) { *w.background = 0.0f; st->k = ~0ull; return; }
+    const unsigned long long k = (nv - 1) / 2;
+    if (nl > w.capBG || k < nb || k >= nb + nl) {
+        atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
+        *w.background = 0.0f;
+        st->k = ~0ull;
+        return;
+    }
+    st->k = k - nb;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(512)
+sp_lsel_hist_kernel(SparseWork w)
+{
+    SelState *st = w.sel;
+    if (st->k == ~0ull) return;
+    __shared__ unsigned int h[SEL_BINS];
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const unsigned int n = w.bg->n_list, prefix = st->prefix;
+    for (unsigned int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const unsigned int key = f32_key(w.bglist[p]);
+        if (PASS == 0) atomicAdd(&h[key >> 21], 1u);
+        else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&h[(key >> 10) & 0x7ffu], 1u); }
+        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&h[key & 0x3ffu], 1u); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&st->hist[PASS][i], h[i]);
+}
+
+template <int PASS>
+__global__ void sp_lsel_scan_kernel(SparseWork w)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SelState *st = w.sel;
+    unsigned long long k = st->k;
+    if (k == ~0ull) return;
+    const int nb = (PASS == 2) ? 1024 : SEL_BINS;
+    unsigned long long acc = 0;
+    int b = 0;
+    for (; b < nb - 1; b++) {
+        const unsigned long long c = st->hist[PASS][b];
+        if (acc + c > k) break;
+        acc += c;
+    }
+    st->k = k - acc;
+    if (PASS == 0) st->prefix = (unsigned int)b << 21;
+    else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
+    else { st->prefix |= (unsigned int)b; *w.background = key_f32(st->prefix); }
+}
+
+// list A -> list B: unmasked pixels whose true Laplacian S/N exceeds sigclip
+__global__ void __launch_bounds__(128)
+sp_cand1_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
+                SparseWork w, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int n = list_len(&w.cnt->nA, w.capA);
+    const float rn2 = lac_rn2(prm);
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int p = w.listA[k];
+        if (inmask && inmask[p]) continue;
+        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
+        // s' = s - med5(s) is 0 in the 2-pixel frame (the median filter copies its input there)
+        if (y < 2 || y >= H - 2 || x < 2 || x >= W - 2) continue;
+        float nz;
+        const float s = lac_s_at(img, H, W, y, x, rn2, nz);
+        if (s > prm.sigclip) list_push(w.listB, &w.cnt->nB, w.capB, p, info);
+    }
+}
+
+// s' of pixel (y,x) by one warp: lanes 0..24 evaluate s on the 5x5 neighbourhood.
+// Returns s' in every lane; s_c / noise_c = s and noise of the centre pixel.
+__device__ __forceinline__ float warp_sprime(const float *__restrict__ img, int H, int W, int y, int x, float rn2,
+                                             int lane, float &s_c, float &noise_c)
+{
+    float sv = 0.f, nz = 0.f;
+    if (lane < 25) {
+        const int qy = y + lane / 5 - 2, qx = x + lane % 5 - 2;
+        if (qy >= 0 && qy < H && qx >= 0 && qx < W) sv = lac_s_at(img, H, W, qy, qx, rn2, nz);
+    }
+    s_c = __shfl_sync(0xffffffffu, sv, 12);
+    noise_c = __shfl_sync(0xffffffffu, nz, 12);
+    if (y < 2 || y >= H - 2 || x < 2 || x >= W - 2) return s_c - s_c;      // frame: med5 copies its input
+    float v[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) v[k] = __shfl_sync(0xffffffffu, sv, k);
+    const float med = bbx_med25(v);
+    return s_c - med;
+}
+
+// fine-structure value f of pixel (y,x) by one warp (med3 on 7x7, then their median)
+__device__ __forceinline__ float warp_fine(const float *__restrict__ img, int H, int W, int y, int x, float noise_c,
+                                           int lane)
+{
+    float a = 0.f, b = 0.f;
+    {
+        const int k0 = lane, k1 = lane + 32;
+        const int qy0 = y + k0 / 7 - 3, qx0 = x + k0 % 7 - 3;
+        if (qy0 >= 0 && qy0 < H && qx0 >= 0 && qx0 < W) a = median_at<3>(img, H, W, qy0, qx0);
+        if (k1 < 49) {
+            const int qy1 = y + k1 / 7 - 3, qx1 = x + k1 % 7 - 3;
+            if (qy1 >= 0 && qy1 < H && qx1 >= 0 && qx1 < W) b = median_at<3>(img, H, W, qy1, qx1);
+        }
+    }
+    const float f3c = __shfl_sync(0xffffffffu, a, 24);           // centre = index 3*7+3
+    float m7;
+    if (y < 3 || y >= H - 3 || x < 3 || x >= W - 3) {
+        m7 = f3c;                                                 // frame: med7 copies its input
+    } else {
+        float v[49];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = __shfl_sync(0xffffffffu, a, k);
+#pragma unroll
+        for (int k = 32; k < 49; k++) v[k] = __shfl_sync(0xffffffffu, b, k - 32);
+        m7 = bbx_med49(v);
+    }
+    float f = f3c - m7;
+    f = f / noise_c;
+    if (f < 0.01f) f = 0.01f;
+    return f;
+}
+
+// list B -> c0: warp per pixel
+__global__ void __launch_bounds__(128)
+sp_cand2_kernel(const float *__restrict__ img, int H, int W, LacParams prm, SparseWork w, unsigned int stamp,
+                long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int n = list_len(&w.cnt->nB, w.capB);
+    const int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float rn2 = lac_rn2(prm);
+    for (unsigned int k = warp; k < n; k += nwarps) {
+        const unsigned int p = w.listB[k];
+        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
+        float s_c, nz_c;
+        const float sp = warp_sprime(img, H, W, y, x, rn2, lane, s_c, nz_c);
+        if (!(sp > prm.sigclip)) continue;                        // warp-uniform
+        const float f = warp_fine(img, H, W, y, x, nz_c, lane);
+        const float ratio = sp / f;
+        if (ratio > prm.objlim && lane == 0) {
+            if (flag_set(w.flags, p, stamp, FLAG_C0)) list_push(w.listC0, &w.cnt->nC0, w.capC, p, info);
+        }
+    }
+}
+
+// one growth step: for every listed pixel r and each of its 9 neighbours q (dilate3 copies its
+// input in the 1-pixel frame, so a frame pixel q only counts for q == r), test
+// good(q) & s'(q) > thr; warp per (r, q)
+template <int STEP>
+__global__ void __launch_bounds__(128)
+sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, uint8_t *__restrict__ crmask,
+               int H, int W, LacParams prm, SparseWork w, unsigned int stamp, int iter, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int *src = STEP == 1 ? w.listC0 : w.listC1;
+    const unsigned int n = STEP == 1 ? list_len(&w.cnt->nC0, w.capC) : list_len(&w.cnt->nC1, w.capC);
+    const float thr = STEP == 1 ? prm.sigclip : prm.sigcliplow;
+    // the centre pixel passed s' > sigclip already; that implies the step threshold if it is lower
+    const bool centre_implied = STEP == 1 || prm.sigcliplow <= prm.sigclip;
+    const int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float rn2 = lac_rn2(prm);
+    const unsigned long long total = (unsigned long long)n * 9ull;
+    for (unsigned long long t = warp; t < total; t += nwarps) {
+        const unsigned int r = src[t / 9];
+        const int k = (int)(t % 9);
+        const int ry = (int)(r / (unsigned int)W), rx = (int)(r - (unsigned int)ry * (unsigned int)W);
+        const int qy = ry + k / 3 - 1, qx = rx + k % 3 - 1;
+        if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+        const bool centre = (k == 4);
+        if (!centre && (qy == 0 || qy == H - 1 || qx == 0 || qx == W - 1)) continue;
+        const size_t q = (size_t)qy * W + qx;
+        if (inmask && inmask[q]) continue;
+        bool pass = centre && centre_implied;
+        if (!pass) {
+            float s_c, nz_c;
+            const float sp = warp_sprime(img, H, W, qy, qx, rn2, lane, s_c, nz_c);
+            pass = sp > thr;
+        }
+        if (!pass || lane != 0) continue;
+        if (STEP == 1) {
+            if (flag_set(w.flags, q, stamp, FLAG_C1)) list_push(w.listC1, &w.cnt->nC1, w.capC, (unsigned int)q, info);
+        } else {
+            if (flag_set(w.flags, q, stamp, FLAG_C2)) {
+                atomicAdd((unsigned long long *)&info[INFO_NCR + iter], 1ull);
+                if (crmask[q] == 0) {
+                    crmask[q] = 1;
+                    list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
+                }
+            }
+        }
+    }
+}
+
+__global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) info[i] = (i == INFO_ACTIVE) ? 1 : 0;
+    if (threadIdx.x == 0) { cnt->nA = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0; }
+}
+
+// after grow2: stop flag for the iterations that follow, reset of the per-iteration lists
+__global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt)
+{
+    if (!info[INFO_ACTIVE]) return;
+    info[INFO_ITERS] = iter + 1;
+    if (info[INFO_NCR + iter] == 0) info[INFO_ACTIVE] = 0;
+    cnt->nA = cnt->nB = cnt->nC0 = cnt->nC1 = 0;
+}
+
+// medmask cleaning of every pixel flagged so far (cumulative CR list)
+__global__ void __launch_bounds__(128)
+sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *__restrict__ inmask, int H, int W,
+                SparseWork w, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int n = list_len(&w.cnt->nCR, w.capCR);
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int p = w.listCR[k];
+        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
+        if (x < 2 || x >= W - 2 || y < 2 || y >= H - 2) continue;
+        float v[25];
+        int m = 0;
+        for (int dy = -2; dy <= 2; dy++)
+            for (int dx = -2; dx <= 2; dx++) {
+                const size_t j = (size_t)(y + dy) * W + (x + dx);
+                const bool bad = crmask[j] || (inmask && inmask[j]);
+                if (!bad) v[m++] = img[j];
+            }
+        if (m == 0) {                      // no usable neighbour: the global background level
+            img[p] = *w.background;
+            continue;
+        }
+        for (int a = 1; a < m; a++) {
+            const float key = v[a];
+            int b = a - 1;
+            while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; b--; }
+            v[b + 1] = key;
+        }
+        img[p] = v[(m - 1) / 2];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, int niter,
+                        void *work, long long *info, cudaStream_t st)
+{
+    const size_t n = (size_t)H * W;
+    const SparseWork w = carve_sparse(work, n);
+    BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
+    BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));
+    sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt);
+    sp_bg_sample_kernel<<<1, 1024, 0, st>>>(img, inmask, n, w);
+    BBX_CHECK_LAUNCH("sparse_begin");
+    return 0;
+}
+
+static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
+                            int it, void *work, long long *info, cudaStream_t st)
+{
+    const size_t n = (size_t)H * W;
+    const SparseWork w = carve_sparse(work, n);
+    const unsigned int stamp = (unsigned int)(it % 15) + 1;
+    const long long groups = (long long)H * ((W + 3) / 4);
+    const long long want = (groups + 255) / 256;
+    const int scan_blocks = (int)(want < (long long)BBX_SM_COUNT * 32 ? want : (long long)BBX_SM_COUNT * 32);
+    const int list_blocks = BBX_SM_COUNT * 8;
+    if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
+    if (it == 0) {
+        sp_scan_kernel<true><<<scan_blocks, 256, 0, st>>>(img, inmask, H, W, prm, w, info);
+        sp_bg_rank_kernel<<<1, 32, 0, st>>>(w, info);
+        sp_lsel_hist_kernel<0><<<BBX_SM_COUNT, 512, 0, st>>>(w);
+        sp_lsel_scan_kernel<0><<<1, 32, 0, st>>>(w);
+        sp_lsel_hist_kernel<1><<<BBX_SM_COUNT, 512, 0, st>>>(w);
+        sp_lsel_scan_kernel<1><<<1, 32, 0, st>>>(w);
+        sp_lsel_hist_kernel<2><<<BBX_SM_COUNT, 512, 0, st>>>(w);
+        sp_lsel_scan_kernel<2><<<1, 32, 0, st>>>(w);
+    } else {
+        sp_scan_kernel<false><<<scan_blocks, 256, 0, st>>>(img, inmask, H, W, prm, w, info);
+    }
+    sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, info);
+    sp_cand2_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
+    sp_grow_kernel<1><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_grow_kernel<2><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
+    sp_clean_kernel<<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    BBX_CHECK_LAUNCH("sparse_iteration");
+    return 0;
+}
+
+extern "C" size_t bbx_lacosmic_work_bytes(int H, int W)
+{
+    const size_t a = lac_dense_work_bytes(H, W), b = lac_sparse_work_bytes(H, W);
+    return a > b ? a : b;
+}
+
+extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                                  int niter, int mode, void *work, long long *out_info, void *stream)
+{
+    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
+    BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
+    BBX_REQUIRE(mode == 0 || mode == 1, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense)", mode);
+    BBX_REQUIRE((long long)H * W < 4294967295LL, "bbx_lacosmic_begin: image too large for 32-bit pixel indices");
+    if (mode == 1) return lac_dense_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
+    return sparse_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
+}
+
+extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                                      float sigclip, float sigfrac, float objlim, float readnoise,
+                                      const double *readnoise_dev, int iter, int mode, void *work,
+                                      long long *out_info, void *stream)
+{
+    BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_iteration: null argument");
+    const LacParams prm = lac_make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
+    if (mode == 1) return lac_dense_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
+    return sparse_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
+}
+
+extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
+                            float sigclip, float sigfrac, float objlim, float readnoise,
+                            const double *readnoise_dev, int niter, int mode, void *work, long long *out_info,
+                            void *stream)
+{
+    if (bbx_lacosmic_begin(img, inmask, crmask, H, W, niter, mode, work, out_info, stream)) return -2;
+    for (int it = 0; it < niter; it++)
+        if (bbx_lacosmic_iteration(img, inmask, crmask, H, W, sigclip, sigfrac, objlim, readnoise, readnoise_dev,
+                                   it, mode, work, out_info, stream)) return -2;
+    return 0;
+}

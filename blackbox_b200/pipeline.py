@@ -80,7 +80,7 @@ class FramePipeline:
             self._spline_cols = R.overscan_resolve_spline(st, strict=False)
         call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
 
-    def _rest(self, raw_t, out_img, out_mask, wait_holes=False):
+    def _rest(self, raw_t, out_img, out_mask, wait_holes=False, lac_mode=R.LAC_LAZY):
         tel, geom = self.tel, self.geom
         RH, RW = geom.red_shape
         s = R._stream()
@@ -92,7 +92,7 @@ class FramePipeline:
         if self.niter > 0:
             R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
                                get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
-                               self.niter, self.lwork, readnoise_dev=self.means[1:])
+                               self.niter, self.lwork, readnoise_dev=self.means[1:], mode=lac_mode)
             bit = int(get_par(set_bb.mask_value, tel)['cosmic ray'])
             call('bbx_mask_or', R._ptr(out_mask), R._ptr(self.crmask), out_mask.numel(), bit, s)
             if self.count_objects:
@@ -115,10 +115,14 @@ class FramePipeline:
         return out_img, out_mask
 
     def enqueue_status(self, host_slot):
-        """Enqueue a copy of the hole-filling status word into the pinned int32[1] tensor
-        ``host_slot`` (valid after the stream is synchronised): non-zero means the frame has to
-        be finished with ``finish()`` before its outputs are used."""
-        host_slot.copy_(self.mwork.unconverged, non_blocking=True)
+        """Enqueue a copy of the frame's status (hole filling unconverged | lazy LACosmic
+        incomplete) into the pinned int32[1] tensor ``host_slot`` (valid after the stream is
+        synchronised): non-zero means the frame has to be finished with ``finish()`` before its
+        outputs are used."""
+        stat = self.mwork.unconverged
+        if self.niter > 0:
+            stat = stat | self.lwork.info[2:3].to(torch.int32)
+        host_slot.copy_(stat, non_blocking=True)
 
     # ---------------------------------------------------------------------------------------
     def finish(self, fill_header=True):
@@ -127,11 +131,18 @@ class FramePipeline:
         st = self.st
         out_img, out_mask = self._out
         redo = False
-        if int(self.mwork.unconverged.item()) != 0:
-            # the mask LACosmic saw was not final: redo everything after the overscan stage
+        unconverged = int(self.mwork.unconverged.item()) != 0
+        lac_status = int(self.lwork.info[2].item()) if self.niter > 0 else 0
+        if unconverged or lac_status != 0:
+            # hole filling needed more rounds (the mask LACosmic saw was not final) or the lazy
+            # LACosmic needs its dense twin: redo everything after the overscan stage
             redo = True
-            self._rest(self._raw, out_img, out_mask, wait_holes=True)
+            self._rest(self._raw, out_img, out_mask, wait_holes=True,
+                       lac_mode=R.LAC_DENSE if lac_status != 0 else R.LAC_LAZY)
             torch.cuda.current_stream().synchronize()
+            if self.niter > 0 and int(self.lwork.info[2].item()) != 0:
+                self._rest(self._raw, out_img, out_mask, wait_holes=True, lac_mode=R.LAC_DENSE)
+                torch.cuda.current_stream().synchronize()
         header, header_mask = {}, {}
         if fill_header:
             R.fill_os_header(header, st)

@@ -438,23 +438,33 @@ def mask_header(data_mask, header_mask):
 class LacosmicWork:
     def __init__(self, H, W, niter, device):
         self.buf = torch.empty(query('bbx_lacosmic_work_bytes', H, W), dtype=torch.uint8, device=device)
-        self.info = torch.zeros(2 + max(niter, 1), dtype=torch.int64, device=device)
+        self.info = torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
+
+
+LAC_LAZY, LAC_DENSE = 0, 1
 
 
 def lacosmic_enqueue(img_t, inmask_t, crmask_t, sigclip, sigfrac, objlim, readnoise, niter,
-                     work, readnoise_dev=None):
+                     work, readnoise_dev=None, mode=LAC_LAZY):
+    """Enqueue detect_cosmics' iterations (include/bbx.h: bbx_lacosmic).  In lazy mode the
+    caller must check ``work.info[2]`` afterwards and repeat densely if it is non-zero."""
     H, W = img_t.shape
+    if sigclip < 0 or sigfrac < 0:
+        mode = LAC_DENSE
     call('bbx_lacosmic', _ptr(img_t), _ptr(inmask_t), _ptr(crmask_t), H, W,
          float(np.float32(sigclip)), float(np.float32(sigfrac)), float(np.float32(objlim)),
-         float(np.float32(readnoise)), _ptr(readnoise_dev), int(niter), _ptr(work.buf),
+         float(np.float32(readnoise)), _ptr(readnoise_dev), int(niter), int(mode), _ptr(work.buf),
          _ptr(work.info), _stream())
 
 
 def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gain=1.0,
                    readnoise=6.5, satlevel=65536.0, pssl=0.0, niter=4, sepmed=True,
                    cleantype='meanmask', fsmode='median', psfmodel='gauss', psffwhm=2.5,
-                   psfsize=7, psfk=None, psfbeta=4.765, verbose=False, info=None):
+                   psfsize=7, psfk=None, psfbeta=4.765, verbose=False, info=None, mode=None):
     """astroscrappy.detect_cosmics (1.0.8 signature) -> (crmask bool, cleanarr float32).
+
+    ``mode``: None = lazy evaluation with an automatic dense repeat when needed (same
+    result either way), LAC_LAZY / LAC_DENSE to force one implementation (tests).
 
     Implemented path: sepmed=False, cleantype='medmask', fsmode='median', pssl=0,
     satlevel=inf -- the one blackbox.py:4323-4332 uses; anything else raises
@@ -466,7 +476,8 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
         raise NotImplementedError('detect_cosmics: finite satlevel is not implemented '
                                   '(the reference passes satlevel=inf, blackbox.py:4272)')
     is_np = isinstance(indat, np.ndarray)
-    clean = _to_dev(indat, torch.float32).clone()
+    src = _to_dev(indat, torch.float32)
+    clean = src.clone()
     if gain != 1.0:
         clean *= float(np.float32(gain))
     H, W = clean.shape
@@ -476,12 +487,24 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
         inmask_t = (inmask_t != 0).to(torch.uint8) if inmask_t.dtype != torch.uint8 else inmask_t
     crmask = torch.empty((H, W), dtype=torch.uint8, device=clean.device)
     work = LacosmicWork(H, W, niter, clean.device)
-    lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work)
+    first = LAC_LAZY if mode is None else mode
+    lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work, mode=first)
+    inf = work.info.cpu().numpy()
+    status = int(inf[2])
+    if status != 0:
+        if mode is not None:
+            raise RuntimeError('detect_cosmics: lazy evaluation incomplete (status {})'.format(status))
+        clean.copy_(src)
+        if gain != 1.0:
+            clean *= float(np.float32(gain))
+        lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work,
+                         mode=LAC_DENSE)
+        inf = work.info.cpu().numpy()
     if gain != 1.0:
         clean /= float(np.float32(gain))
     if info is not None:
-        inf = work.info.cpu().numpy()
-        info.update(iterations=int(inf[0]), ncr_per_iter=inf[2:2 + int(inf[0])].copy())
+        info.update(iterations=int(inf[0]), ncr_per_iter=inf[4:4 + int(inf[0])].copy(),
+                    lazy_status=status)
     crb = crmask.to(torch.bool)
     if is_np:
         return crb.cpu().numpy(), clean.cpu().numpy()

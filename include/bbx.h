@@ -199,28 +199,38 @@ int bbx_stack_median(const float *const *frames_h, const float *scale_h, int N, 
  * LACosmic -- astroscrappy.detect_cosmics 1.0.8 (sepmed=False, fsmode='median',
  * cleantype='medmask', gain=1, pssl=0, satlevel=inf), call site blackbox.py:4323-4332
  * img    f32 [H][W]  in: image, out: cleaned image
- * inmask u8  [H][W]  non-zero = excluded
+ * inmask u8  [H][W]  non-zero = excluded (may be null)
  * crmask u8  [H][W]  out: 0/1
  * work   >= bbx_lacosmic_work_bytes(H, W) bytes
- * out_info int64 [2 + niter] device: [0] iterations run, [1] reserved, [2+k] new CR pixels in
- * iteration k.  The iteration loop runs on the device without host synchronisation;
- * iterations after one that found nothing are skipped (as the reference's `break`).
+ * readnoise_dev: optional device scalar (float64) used instead of `readnoise`
+ * mode   0 = lazy: one dense Laplacian pass per iteration, medians only where they can matter
+ *            (bit-identical to mode 1; requires sigclip >= 0 and sigfrac >= 0)
+ *        1 = dense: every intermediate image is materialised
+ * out_info int64 [4 + niter] device: [0] iterations run, [1] internal, [2] status bits
+ * (BBX_LAC_OVERFLOW: a work list overflowed, BBX_LAC_NEED_BG: a cosmic-ray pixel without
+ * usable neighbours needs the global background level -- in both cases the lazy result is
+ * incomplete and the call must be repeated with mode 1), [4+k] new CR pixels of iteration k.
+ * The iteration loop runs on the device without host synchronisation; iterations after one
+ * that found nothing are skipped (as the reference's `break`).
  * ------------------------------------------------------------------------------------- */
+#define BBX_LAC_OVERFLOW 1
+#define BBX_LAC_NEED_BG 2
 size_t bbx_lacosmic_work_bytes(int H, int W);
 int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
                  float sigclip, float sigfrac, float objlim, float readnoise,
-                 const double *readnoise_dev, int niter, void *work, long long *out_info,
-                 void *stream);
+                 const double *readnoise_dev, int niter, int mode, void *work,
+                 long long *out_info, void *stream);
 
 /* The same in two parts, so one iteration can be enqueued (and timed) on its own:
- * _begin zeroes crmask / out_info and computes the background level, _iteration enqueues the
- * kernels of iteration `iter` (a no-op on the device once an earlier iteration found nothing). */
+ * _begin zeroes crmask / out_info (mode 1: also computes the background level), _iteration
+ * enqueues the kernels of iteration `iter` (a no-op on the device once an earlier iteration
+ * found nothing). */
 int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
-                       int niter, void *work, long long *out_info, void *stream);
+                       int niter, int mode, void *work, long long *out_info, void *stream);
 int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
                            float sigclip, float sigfrac, float objlim, float readnoise,
-                           const double *readnoise_dev, int iter, void *work, long long *out_info,
-                           void *stream);
+                           const double *readnoise_dev, int iter, int mode, void *work,
+                           long long *out_info, void *stream);
 
 /* lower median a[(n-1)/2] of the pixels with inmask == 0 (astroscrappy's background level)
  * work >= bbx_select_work_bytes(); out device float32 */

@@ -91,21 +91,47 @@ def _lacosmic_case(seed, shape=(160, 232), ncr=60, masked_frac=0.01):
     return img, mask
 
 
-@pytest.mark.parametrize('seed,niter', [(1, 4), (2, 3), (3, 1)])
-def test_detect_cosmics_bit_exact(seed, niter):
+@pytest.mark.parametrize('mode', ['lazy', 'dense'])
+@pytest.mark.parametrize('seed,niter,sigclip', [(1, 4, 15), (2, 3, 20), (3, 1, 4.5), (4, 4, 6)])
+def test_detect_cosmics_bit_exact(seed, niter, sigclip, mode):
     from blackbox_b200 import reduce as bbr
     from oracle import lacosmic
     img, mask = _lacosmic_case(seed)
-    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=niter, readnoise=8.5, gain=1.0,
-              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    kw = dict(sigclip=sigclip, sigfrac=0.01 if seed != 4 else 0.3, objlim=3, niter=niter, readnoise=8.5,
+              gain=1.0, satlevel=np.inf, cleantype='medmask', sepmed=False)
     info_o, info_g = {}, {}
     cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=mask, info=info_o, **kw)
-    cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g, **kw)
+    cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g,
+                                       mode=bbr.LAC_LAZY if mode == 'lazy' else bbr.LAC_DENSE, **kw)
     assert cr_o.sum() > 50
     assert np.array_equal(cr_g, cr_o)
     assert np.array_equal(clean_g.view(np.uint32), clean_o.view(np.uint32))
     assert info_g['iterations'] == info_o['iterations']
     assert np.array_equal(info_g['ncr_per_iter'], info_o['ncr_per_iter'])
+
+
+def test_detect_cosmics_background_level():
+    """A fat cosmic-ray blob leaves interior pixels without usable neighbours: they get the
+    global background level (lower median of all unmasked input pixels), which the lazy path
+    finds from a sampled bracket + exact selection."""
+    from blackbox_b200 import reduce as bbr
+    from oracle import lacosmic
+    rng = np.random.default_rng(21)
+    img = (300 + 17 * rng.standard_normal((96, 120))).astype(np.float32)
+    img[40:49, 50:59] += rng.uniform(20000, 60000, (9, 9)).astype(np.float32)
+    img[10, 10] += 9000.0
+    mask = np.zeros(img.shape, bool)
+    mask[:, :7] = True
+    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=4, readnoise=8.5, gain=1.0,
+              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    for m in (None, mask):
+        info_o, info_g = {}, {}
+        cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=m, info=info_o, **kw)
+        assert (clean_o == info_o['background']).any()         # the case is exercised
+        for mode in (bbr.LAC_LAZY, bbr.LAC_DENSE):
+            cr_g, clean_g = bbr.detect_cosmics(img, inmask=m, info=info_g, mode=mode, **kw)
+            assert np.array_equal(cr_g, cr_o) and np.array_equal(clean_g, clean_o)
+            assert info_g['lazy_status'] == 0
 
 
 def test_detect_cosmics_no_mask_and_early_stop():
