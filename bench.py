@@ -141,7 +141,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -225,9 +225,10 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.6)          # nvidia-smi needs a moment before its first sample
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     redo = 0

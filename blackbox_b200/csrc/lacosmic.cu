@@ -193,27 +193,22 @@ select_hist_kernel(const float *__restrict__ img, const uint8_t *__restrict__ in
 }
 
 template <int PASS>
-__global__ void select_scan_kernel(SelState *st, float *out)
+__global__ void __launch_bounds__(256) select_scan_kernel(SelState *st, float *out)
 {
-    // single thread: 2048 bins, negligible
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long k = st->k;
     if (PASS == 0) {
-        unsigned long long total = 0;
-        for (int i = 0; i < SEL_BINS; i++) total += st->hist[0][i];
-        if (total == 0) { *out = 0.0f; st->k = ~0ull; return; }
+        __shared__ unsigned long long s_tot[33];
+        unsigned long long mine = 0;
+        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) mine += st->hist[0][i];
+        const unsigned long long total = block_sum(mine, s_tot);
+        if (total == 0) { if (threadIdx.x == 0) { *out = 0.0f; st->k = ~0ull; } return; }
         k = (total - 1) / 2;
     }
     if (k == ~0ull) return;
-    const int nb = (PASS == 2) ? 1024 : SEL_BINS;
-    unsigned long long acc = 0;
-    int b = 0;
-    for (; b < nb; b++) {
-        const unsigned long long c = st->hist[PASS][b];
-        if (acc + c > k) break;
-        acc += c;
-    }
-    st->k = k - acc;
+    unsigned long long below;
+    const int b = select_find_bin(st->hist[PASS], (PASS == 2) ? 1024 : SEL_BINS, k, below);
+    if (threadIdx.x != 0) return;
+    st->k = k - below;
     if (PASS == 0) st->prefix = (unsigned int)b << 21;
     else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
     else { st->prefix |= (unsigned int)b; *out = key_f32(st->prefix); }
@@ -230,11 +225,11 @@ extern "C" int bbx_masked_lower_median(const float *img, const uint8_t *inmask, 
     BBX_CUDA(cudaMemsetAsync(st, 0, sizeof(SelState), s));
     const int blocks = BBX_SM_COUNT * 4;
     select_hist_kernel<0><<<blocks, 512, 0, s>>>(img, inmask, n, st);
-    select_scan_kernel<0><<<1, 32, 0, s>>>(st, out);
+    select_scan_kernel<0><<<1, 256, 0, s>>>(st, out);
     select_hist_kernel<1><<<blocks, 512, 0, s>>>(img, inmask, n, st);
-    select_scan_kernel<1><<<1, 32, 0, s>>>(st, out);
+    select_scan_kernel<1><<<1, 256, 0, s>>>(st, out);
     select_hist_kernel<2><<<blocks, 512, 0, s>>>(img, inmask, n, st);
-    select_scan_kernel<2><<<1, 32, 0, s>>>(st, out);
+    select_scan_kernel<2><<<1, 256, 0, s>>>(st, out);
     BBX_CHECK_LAUNCH("bbx_masked_lower_median");
     return 0;
 }

@@ -100,6 +100,44 @@ __device__ __forceinline__ float key_f32(unsigned int k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Block-wide search (256 threads): first bin b of hist[0..nb) with cumulative count > k.
+// Returns b (clamped to nb-1) and the count below it in `below`; identical in all threads.
+__device__ __forceinline__ int select_find_bin(const unsigned int *hist, int nb, unsigned long long k,
+                                               unsigned long long &below)
+{
+    __shared__ unsigned int s_h[SEL_BINS];
+    __shared__ unsigned long long s_part[256];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_below;
+    const int per = SEL_BINS / 256;
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) s_h[i] = i < nb ? hist[i] : 0u;
+    if (threadIdx.x == 0) { s_bin = nb - 1; s_below = 0; }
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (int i = 0; i < per; i++) mine += s_h[threadIdx.x * per + i];
+    s_part[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0, total = 0;
+        for (int t = 0; t < 256; t++) total += s_part[t];
+        if (k >= total) {                       // rank beyond the data: last bin
+            unsigned long long a2 = 0;
+            for (int i = 0; i < nb - 1; i++) a2 += s_h[i];
+            s_below = a2;
+        } else {
+            int t = 0;
+            for (; t < 256; t++) { if (acc + s_part[t] > k) break; acc += s_part[t]; }
+            int b = t * per;
+            for (; b < nb - 1; b++) { if (acc + s_h[b] > k) break; acc += s_h[b]; }
+            s_bin = b;
+            s_below = acc;
+        }
+    }
+    __syncthreads();
+    below = s_below;
+    return s_bin;
+}
+
 // dense implementation (lacosmic.cu)
 struct LacWork;
 size_t lac_dense_work_bytes(int H, int W);

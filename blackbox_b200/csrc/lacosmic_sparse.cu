@@ -38,7 +38,7 @@ struct SparseCounters {
     unsigned int pad[3];
 };
 
-#define BG_SAMPLES 262144u
+#define BG_SAMPLES 16384u
 
 struct BgState {
     float a, b;                          // bracket of the median, from the sample
@@ -53,7 +53,6 @@ struct SparseWork {
     unsigned int capA, capB, capC, capCR, capBG;
     SparseCounters *cnt;
     BgState *bg;
-    float *sample;               // [BG_SAMPLES]
     float *bglist;               // [capBG]
     SelState *sel;
     float *background;
@@ -77,7 +76,7 @@ size_t lac_sparse_work_bytes(int H, int W)
     unsigned int a, b, c, cr;
     sparse_caps(n, a, b, c, cr);
     return sp_align(n) + sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + sp_align(4ull * cr) +
-           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(BgState)) + sp_align(4ull * BG_SAMPLES) +
+           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(BgState)) +
            sp_align(4ull * sparse_cap_bg(n)) + sp_align(sizeof(SelState)) + 512;
 }
 
@@ -94,7 +93,6 @@ static SparseWork carve_sparse(void *work, size_t n)
     w.listCR = (unsigned int *)p; p += sp_align(4ull * w.capCR);
     w.cnt = (SparseCounters *)p; p += sp_align(sizeof(SparseCounters));
     w.bg = (BgState *)p; p += sp_align(sizeof(BgState));
-    w.sample = (float *)p; p += sp_align(4ull * BG_SAMPLES);
     w.capBG = sparse_cap_bg(n);
     w.bglist = (float *)p; p += sp_align(4ull * w.capBG);
     w.sel = (SelState *)p; p += sp_align(sizeof(SelState));
@@ -140,14 +138,19 @@ __device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsi
 // dense scan: 4 pixels per thread, 128-bit loads of the three rows
 // --------------------------------------------------------------------------------------------
 // COLLECT (first iteration only): also count the unmasked pixels and those below the median
-// bracket, and gather the values inside the bracket (block-aggregated appends).
+// bracket, and gather the values inside the bracket (one block-aggregated append per block).
+// Grid: x = 512-pixel segments of a row, y = row; 128 threads x 4 pixels.
+// The list-A test `L+ / den_min > sigclip` is replaced by the division-free superset
+// `L+ > thr_lo`, thr_lo = sigclip * den_min * (1 - 2^-20): pixels it lets through in excess are
+// rejected by the exact tests of the candidate kernels.
+#define SCAN_THREADS 128
 template <bool COLLECT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SCAN_THREADS)
 sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
                SparseWork w, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
-    __shared__ float s_buf[COLLECT ? 1024 : 1];
+    __shared__ float s_buf[COLLECT ? 4 * SCAN_THREADS : 1];
     __shared__ unsigned int s_cnt, s_base;
     __shared__ unsigned long long s_red[33];
     unsigned int n_valid = 0, n_below = 0;
@@ -161,25 +164,26 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     float nmin = 0.00001f + lac_rn2(prm);
     nmin = sqrtf(nmin);
     const float den_min = 2.0f * nmin;
-    const int groups = (W + 3) / 4;
-    const long long total = (long long)H * groups;
+    const float thr_lo = (float)((double)prm.sigclip * (double)den_min * (1.0 - 9.5367431640625e-07));
     const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
-      const long long t = base + threadIdx.x;
-      if (t < total) {
-        const int y = (int)(t / groups), x0 = (int)(t - (long long)y * groups) * 4;
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    if (x0 < W) {
+        const size_t i = (size_t)y * W + x0;
         if (COLLECT) {
+            const bool mvec = inmask && vec_ok && x0 + 4 <= W && (((uintptr_t)inmask & 3) == 0);
+            unsigned int mm = 0;
+            if (mvec) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
             for (int k = 0; k < 4 && x0 + k < W; k++) {
-                const size_t i = (size_t)y * W + x0 + k;
-                if (inmask && inmask[i]) continue;
-                const float v = img[i];
+                const bool masked = inmask ? (mvec ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
+                if (masked) continue;
+                const float v = img[i + k];
                 n_valid++;
                 if (v < bra) n_below++;
                 else if (v <= brb) s_buf[atomicAdd(&s_cnt, 1u)] = v;
             }
         }
         if (vec_ok && y > 0 && y + 1 < H && x0 > 0 && x0 + 4 < W) {
-            const size_t i = (size_t)y * W + x0;
             const float4 c = *reinterpret_cast<const float4 *>(img + i);
             const float4 u = *reinterpret_cast<const float4 *>(img + i - W);
             const float4 d = *reinterpret_cast<const float4 *>(img + i + W);
@@ -193,37 +197,28 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
                 float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
                 float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
                 float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                s00 = s00 < 0.f ? 0.f : s00; s01 = s01 < 0.f ? 0.f : s01;
-                s10 = s10 < 0.f ? 0.f : s10; s11 = s11 < 0.f ? 0.f : s11;
+                s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
                 float p = s00 + s01; p = p + s10; p = p + s11;
-                const float lp = p / 4.0f;
-                const float sub = lp / den_min;
-                if (sub > prm.sigclip) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                const float lp = p * 0.25f;
+                if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
             }
         } else {
             for (int k = 0; k < 4 && x0 + k < W; k++) {
                 const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                const float sub = lp / den_min;
-                if (sub > prm.sigclip) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)((size_t)y * W + x0 + k), info);
+                if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
             }
         }
-      }
-      if (COLLECT) {
-          __syncthreads();
-          const unsigned int c = s_cnt;
-          if (c) {
-              if (threadIdx.x == 0) s_base = atomicAdd(&w.bg->n_list, c);
-              __syncthreads();
-              const unsigned int b0 = s_base;
-              for (unsigned int j = threadIdx.x; j < c; j += blockDim.x)
-                  if (b0 + j < w.capBG) w.bglist[b0 + j] = s_buf[j];
-              __syncthreads();
-              if (threadIdx.x == 0) s_cnt = 0;
-          }
-          __syncthreads();
-      }
     }
     if (COLLECT) {
+        __syncthreads();
+        const unsigned int c = s_cnt;
+        if (c) {
+            if (threadIdx.x == 0) s_base = atomicAdd(&w.bg->n_list, c);
+            __syncthreads();
+            const unsigned int b0 = s_base;
+            for (unsigned int j = threadIdx.x; j < c; j += blockDim.x)
+                if (b0 + j < w.capBG) w.bglist[b0 + j] = s_buf[j];
+        }
         const unsigned long long tv = block_sum((unsigned long long)n_valid, s_red);
         const unsigned long long tb = block_sum((unsigned long long)n_below, s_red);
         if (threadIdx.x == 0) {
@@ -234,64 +229,47 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
 }
 
 // ---- background level ----------------------------------------------------------------------
-// rank-th smallest (0-based) of vals[0..n) by one block, 3-pass radix select
-__device__ float block_radix_select(const float *vals, unsigned int n, unsigned int rank, unsigned int *hist,
-                                    unsigned int *s_state)
-{
-    unsigned int prefix = 0, k = rank;
-    for (int pass = 0; pass < 3; pass++) {
-        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned int key = f32_key(vals[i]);
-            if (pass == 0) atomicAdd(&hist[key >> 21], 1u);
-            else if (pass == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&hist[(key >> 10) & 0x7ffu], 1u); }
-            else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&hist[key & 0x3ffu], 1u); }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nb = pass == 2 ? 1024 : SEL_BINS;
-            unsigned int acc = 0;
-            int b = 0;
-            for (; b < nb - 1; b++) {
-                if (acc + hist[b] > k) break;
-                acc += hist[b];
-            }
-            s_state[0] = k - acc;
-            s_state[1] = pass == 0 ? ((unsigned int)b << 21) : pass == 1 ? (prefix | ((unsigned int)b << 10)) : (prefix | (unsigned int)b);
-        }
-        __syncthreads();
-        k = s_state[0];
-        prefix = s_state[1];
-        __syncthreads();
-    }
-    return key_f32(prefix);
-}
-
+// One block: gather a strided sample of the unmasked pixels into shared memory, bitonic-sort it
+// and bracket the median rank by +-(2.5 sqrt(ns) + 8) sample ranks (5 sigma of the binomial
+// sampling error of the median's rank).
 __global__ void __launch_bounds__(1024)
 sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
 {
-    __shared__ unsigned int hist[SEL_BINS];
-    __shared__ unsigned int s_state[2];
+    extern __shared__ float smp[];                    // BG_SAMPLES floats
     __shared__ unsigned int s_ns;
     if (threadIdx.x == 0) s_ns = 0;
+    for (unsigned int j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) smp[j] = INFINITY;
     __syncthreads();
     const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
     for (size_t j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) {
         const size_t i = j * stride;
         if (i >= n) break;
         if (inmask && inmask[i]) continue;
-        w.sample[atomicAdd(&s_ns, 1u)] = img[i];
+        const float v = img[i];
+        if (v != v) continue;                         // NaN would break the sort order
+        smp[atomicAdd(&s_ns, 1u)] = v;
     }
     __syncthreads();
     const unsigned int ns = s_ns;
-    float a = -INFINITY, b = INFINITY;
-    if (ns > 0) {
-        const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
-        if (mid > d) a = block_radix_select(w.sample, ns, mid - d, hist, s_state);
-        if (mid + d < ns - 1) b = block_radix_select(w.sample, ns, mid + d, hist, s_state);
-    }
+    for (unsigned int k = 2; k <= BG_SAMPLES; k <<= 1)
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int i = threadIdx.x; i < BG_SAMPLES; i += blockDim.x) {
+                const unsigned int l = i ^ j;
+                if (l > i) {
+                    const float x = smp[i], y = smp[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { smp[i] = y; smp[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
     if (threadIdx.x == 0) {
+        float a = -INFINITY, b = INFINITY;
+        if (ns > 0) {
+            const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
+            if (mid > d) a = smp[mid - d];
+            if (mid + d < ns - 1) b = smp[mid + d];
+        }
         w.bg->a = a; w.bg->b = b;
         w.bg->n_list = 0; w.bg->n_valid = 0; w.bg->n_below = 0;
     }
@@ -300,9 +278,9 @@ sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ i
 // after the first scan: rank of the median inside the collected list (or failure)
 __global__ void sp_bg_rank_kernel(SparseWork w, long long *info)
 {
-    if (threadIdx.x != 0) return;
     SelState *st = w.sel;
-    for (int i = 0; i < 3 * SEL_BINS; i++) (&st->hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 3 * SEL_BINS; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+    if (threadIdx.x != 0) return;
     st->prefix = 0;
     const unsigned long long nv = w.bg->n_valid, nb = w.bg->n_below;
     const unsigned int nl = w.bg->n_list;
@@ -339,21 +317,15 @@ sp_lsel_hist_kernel(SparseWork w)
 }
 
 template <int PASS>
-__global__ void sp_lsel_scan_kernel(SparseWork w)
+__global__ void __launch_bounds__(256) sp_lsel_scan_kernel(SparseWork w)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     SelState *st = w.sel;
-    unsigned long long k = st->k;
+    const unsigned long long k = st->k;
     if (k == ~0ull) return;
-    const int nb = (PASS == 2) ? 1024 : SEL_BINS;
-    unsigned long long acc = 0;
-    int b = 0;
-    for (; b < nb - 1; b++) {
-        const unsigned long long c = st->hist[PASS][b];
-        if (acc + c > k) break;
-        acc += c;
-    }
-    st->k = k - acc;
+    unsigned long long below;
+    const int b = select_find_bin(st->hist[PASS], (PASS == 2) ? 1024 : SEL_BINS, k, below);
+    if (threadIdx.x != 0) return;
+    st->k = k - below;
     if (PASS == 0) st->prefix = (unsigned int)b << 21;
     else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
     else { st->prefix |= (unsigned int)b; *w.background = key_f32(st->prefix); }
@@ -563,7 +535,8 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
     BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
     BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));
     sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt);
-    sp_bg_sample_kernel<<<1, 1024, 0, st>>>(img, inmask, n, w);
+    BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * BG_SAMPLES)));
+    sp_bg_sample_kernel<<<1, 1024, 4 * BG_SAMPLES, st>>>(img, inmask, n, w);
     BBX_CHECK_LAUNCH("sparse_begin");
     return 0;
 }
@@ -574,22 +547,21 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     const size_t n = (size_t)H * W;
     const SparseWork w = carve_sparse(work, n);
     const unsigned int stamp = (unsigned int)(it % 15) + 1;
-    const long long groups = (long long)H * ((W + 3) / 4);
-    const long long want = (groups + 255) / 256;
-    const int scan_blocks = (int)(want < (long long)BBX_SM_COUNT * 32 ? want : (long long)BBX_SM_COUNT * 32);
+    BBX_REQUIRE(H <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
+    const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), H);
     const int list_blocks = BBX_SM_COUNT * 8;
     if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {
-        sp_scan_kernel<true><<<scan_blocks, 256, 0, st>>>(img, inmask, H, W, prm, w, info);
-        sp_bg_rank_kernel<<<1, 32, 0, st>>>(w, info);
+        sp_scan_kernel<true><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
+        sp_bg_rank_kernel<<<1, 256, 0, st>>>(w, info);
         sp_lsel_hist_kernel<0><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<0><<<1, 32, 0, st>>>(w);
+        sp_lsel_scan_kernel<0><<<1, 256, 0, st>>>(w);
         sp_lsel_hist_kernel<1><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<1><<<1, 32, 0, st>>>(w);
+        sp_lsel_scan_kernel<1><<<1, 256, 0, st>>>(w);
         sp_lsel_hist_kernel<2><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<2><<<1, 32, 0, st>>>(w);
+        sp_lsel_scan_kernel<2><<<1, 256, 0, st>>>(w);
     } else {
-        sp_scan_kernel<false><<<scan_blocks, 256, 0, st>>>(img, inmask, H, W, prm, w, info);
+        sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
     }
     sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, info);
     sp_cand2_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);

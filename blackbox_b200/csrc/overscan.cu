@@ -495,23 +495,16 @@ hos_stats_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 // distributed shared memory and combined in rank order (deterministic)
 // ============================================================================================
 #define VSTD_CLUSTER 8
-#define VSTD_THREADS 512
+#define VSTD_THREADS 1024
+#define VSTD_MAXV 8          // strip width <= 256, as in K1
 
-struct VstdPartial { double a; long long n; };
+struct VstdPartial { double s, q; long long n; };
 
-template <typename T>
-__device__ __forceinline__ bool vstd_value(const T *raw, const bbx_geom &g, int ch, int r, int c,
-                                           float gn, const double *fitrow, double dlevel,
-                                           int hos_t0, int idx, double &x)
-{
-    const int trow = idx / g.vos_w, j = idx - trow * g.vos_w;
-    float v = raw_to_f32<T>(raw[(size_t)(r * g.dy + trow) * g.W + (size_t)c * g.dx + g.vos_x0 + j]) * gn;
-    v = sub_f64(v, fitrow[trow]);
-    if (trow >= hos_t0 && trow < hos_t0 + g.hos_rows) v = sub_f64(v, dlevel);
-    x = (double)v;
-    return vos_valid(v);
-}
-
+// Each warp walks rows rank*rows_per_cta + warp, +nwarps, ...; a lane holds the <= 8 strip
+// values of its row in registers, so one pass issues all loads of a row at once.  Every clip
+// iteration is ONE pass accumulating (count, sum, sum of squares) inside the current interval;
+// the population variance follows as q/n - mean^2 (the values are overscan residuals of a few
+// e-, so there is no cancellation to speak of).
 template <typename T>
 __global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS)
 vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
@@ -521,92 +514,85 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     cg::cluster_group cluster = cg::this_cluster();
     const int ch = blockIdx.y, r = ch / g.nx, c = ch - r * g.nx;
     const int rank = (int)cluster.block_rank();
-    const int total = g.dy * g.vos_w;
-    const int per = (total + VSTD_CLUSTER - 1) / VSTD_CLUSTER;
-    const int i0 = rank * per, i1 = min(i0 + per, total);
+    const int rows_per = (g.dy + VSTD_CLUSTER - 1) / VSTD_CLUSTER;
+    const int row0 = rank * rows_per, row1 = min(row0 + rows_per, g.dy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const float gn = gain.v[ch];
     const double *fitrow = vos_fit + (size_t)ch * g.dy;
     const double dlevel = dlevel_arr[ch];
     const int hos_t0 = ((r == 0) ? g.hos_y0_bot : g.hos_y0_top) - r * g.dy;
+    const T *base = raw + (size_t)(r * g.dy) * g.W + (size_t)c * g.dx + g.vos_x0;
 
     __shared__ double scr_d[33];
     __shared__ long long scr_l[33];
     __shared__ VstdPartial part[2];     // double-buffered slot read by the other CTAs
-
     int phase = 0;
-    // cluster-wide (sum, count): every CTA publishes its partial, all read all in rank order
-    auto cluster_reduce = [&](double a, long long n, double &A, long long &N) {
-        a = block_sum(a, scr_d);
+
+    // one pass over this CTA's rows: moments of the valid values inside [lo, hi]
+    auto pass = [&](double lo, double hi, bool closed_nan_ok, double &S, double &Q, long long &N) {
+        double s = 0.0, q = 0.0;
+        long long n = 0;
+        for (int trow = row0 + warp; trow < row1; trow += nwarps) {
+            const T *p = base + (size_t)trow * g.W;
+            const double fv = fitrow[trow];
+            const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
+            float v[VSTD_MAXV];
+#pragma unroll
+            for (int k = 0; k < VSTD_MAXV; k++) {
+                const int j = lane + 32 * k;
+                v[k] = (j < g.vos_w) ? raw_to_f32<T>(p[j]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < VSTD_MAXV; k++) {
+                const int j = lane + 32 * k;
+                if (j >= g.vos_w) continue;
+                float x = v[k] * gn;
+                x = sub_f64(x, fv);
+                if (in_hos) x = sub_f64(x, dlevel);
+                if (!vos_valid(x)) continue;
+                const double xd = (double)x;
+                const bool in = closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi);
+                if (in) { n++; s += xd; q += xd * xd; }
+            }
+        }
+        s = block_sum(s, scr_d);
+        q = block_sum(q, scr_d);
         n = block_sum(n, scr_l);
-        if (threadIdx.x == 0) { part[phase].a = a; part[phase].n = n; }
+        if (threadIdx.x == 0) { part[phase].s = s; part[phase].q = q; part[phase].n = n; }
         cluster.sync();
-        A = 0.0; N = 0;
-        for (int k = 0; k < VSTD_CLUSTER; k++) {
-            const VstdPartial *p = cluster.map_shared_rank(part, k);
-            A += p[phase].a;
-            N += p[phase].n;
+        S = 0.0; Q = 0.0; N = 0;
+        for (int k = 0; k < VSTD_CLUSTER; k++) {           // fixed order: deterministic
+            const VstdPartial *pp = cluster.map_shared_rank(part, k);
+            S += pp[phase].s; Q += pp[phase].q; N += pp[phase].n;
         }
         phase ^= 1;      // the next publish uses the other slot, so no second sync is needed
     };
 
     double LO = -INFINITY, HI = INFINITY, flo = NAN, fhi = NAN;
-    double s = 0.0;
-    long long n = 0;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        double x;
-        if (vstd_value<T>(raw, g, ch, r, c, gn, fitrow, dlevel, hos_t0, i, x)) { n++; s += x; }
-    }
-    double sum; long long cnt;
-    cluster_reduce(s, n, sum, cnt);
-    for (int it = 0; it < 5 && cnt > 0; it++) {
-        const double mean = sum / (double)cnt;
-        double ss = 0.0;
-        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-            double x;
-            if (vstd_value<T>(raw, g, ch, r, c, gn, fitrow, dlevel, hos_t0, i, x) && x >= LO && x <= HI) {
-                const double d = mean - x; ss += d * d;
-            }
-        }
-        double SS; long long dummy;
-        cluster_reduce(ss, 0, SS, dummy);
-        const double sd = sqrt(SS / (double)cnt);
+    double S, Q;
+    long long N;
+    pass(LO, HI, false, S, Q, N);
+    for (int it = 0; it < 5 && N > 0; it++) {
+        const double mean = S / (double)N;
+        const double var = fmax(Q / (double)N - mean * mean, 0.0);
+        const double sd = sqrt(var);
         flo = mean - 3.0 * sd;
         fhi = mean + 3.0 * sd;
         LO = fmax(LO, flo);
         HI = fmin(HI, fhi);
-        s = 0.0; n = 0;
-        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-            double x;
-            if (vstd_value<T>(raw, g, ch, r, c, gn, fitrow, dlevel, hos_t0, i, x) && x >= LO && x <= HI) { n++; s += x; }
-        }
-        double nsum; long long ncnt;
-        cluster_reduce(s, n, nsum, ncnt);
-        const bool done = (ncnt == cnt);
-        cnt = ncnt;
-        sum = nsum;
+        double S2, Q2;
+        long long N2;
+        pass(LO, HI, false, S2, Q2, N2);
+        const bool done = (N2 == N);
+        S = S2; Q = Q2; N = N2;
         if (done) break;
     }
-    // final: population std of everything inside the final bounds
-    s = 0.0; n = 0;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        double x;
-        if (vstd_value<T>(raw, g, ch, r, c, gn, fitrow, dlevel, hos_t0, i, x) && !(x < flo) && !(x > fhi)) { n++; s += x; }
-    }
-    double fs; long long fc;
-    cluster_reduce(s, n, fs, fc);
+    // final: population std of everything inside the final bounds (not the intersection)
+    pass(flo, fhi, true, S, Q, N);
     double result = NAN;
-    if (fc > 0) {
-        const double mean = fs / (double)fc;
-        double ss = 0.0;
-        for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-            double x;
-            if (vstd_value<T>(raw, g, ch, r, c, gn, fitrow, dlevel, hos_t0, i, x) && !(x < flo) && !(x > fhi)) {
-                const double d = x - mean; ss += d * d;
-            }
-        }
-        double SS; long long dummy;
-        cluster_reduce(ss, 0, SS, dummy);
-        result = sqrt(SS / (double)fc);
+    if (N > 0) {
+        const double mean = S / (double)N;
+        result = sqrt(fmax(Q / (double)N - mean * mean, 0.0));
     }
     if (rank == 0 && threadIdx.x == 0) out_std[ch] = result;
     cluster.sync();     // keep every CTA's shared memory alive until all remote reads are done
@@ -794,6 +780,7 @@ extern "C" int bbx_vos_std(const void *raw, int raw_type, const bbx_geom *g, con
                            const double *vos_fit, const double *dlevel, double *out_std, void *stream)
 {
     if (check_geom(g, "bbx_vos_std")) return -1;
+    BBX_REQUIRE(g->vos_w > 0 && g->vos_w <= 32 * VSTD_MAXV, "bbx_vos_std: strip width %d not in 1..%d", g->vos_w, 32 * VSTD_MAXV);
     ChanF32 gn; fill_chan_f32(gn, gain_h);
     dim3 grid(VSTD_CLUSTER, BBX_NCHAN);
     cudaStream_t s = (cudaStream_t)stream;
