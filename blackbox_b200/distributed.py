@@ -1,0 +1,90 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, ``torch.distributed``.
+
+* Science frames are independent (the reference already runs one OS process per frame,
+  blackbox.py:378): frame k goes to rank k mod world_size, nothing is exchanged
+  (``pipeline.shard_frames``).
+* The master-frame combine (master_prep core, blackbox.py:4908-4984) is a per-pixel median, so
+  it shards by ROW STRIPES of the stacked frames: rank g holds rows
+  [g*ceil(H/G), (g+1)*ceil(H/G)) of every one of the N frames, combines its stripe with the
+  stack-median kernel, and a single all-gather (NCCL on GPUs) assembles the master on every
+  rank.  That all-gather is the only collective of the whole build.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import set_bb
+from .set_bb import get_par
+
+
+def stripe_rows(H, world_size):
+    """Rows per stripe (the last stripe may be shorter or empty)."""
+    return (H + world_size - 1) // world_size
+
+
+def stripe_bounds(H, rank, world_size):
+    """[r0, r1) of the rows rank ``rank`` owns."""
+    n = stripe_rows(H, world_size)
+    r0 = min(rank * n, H)
+    return r0, min(r0 + n, H)
+
+
+def _default_combine(stripes, scales, flat_fix, bpm_stripe, tel):
+    from . import reduce as R
+    out, _ = R.master_combine(stripes, 'flat' if flat_fix else 'bias',
+                              medsec=scales if flat_fix else None, bpm=bpm_stripe, tel=tel)
+    return out
+
+
+def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stripe=None, tel=None,
+                           group=None, combine=None):
+    """Row-stripe sharded master combine.
+
+    stripes     this rank's row stripe of each of the N frames: float32 [r1-r0, W] tensors
+                (CUDA for the product path)
+    shape       (H, W) of the full frame
+    medsec      flats: the N normalisation medians (header MEDSEC, blackbox.py:4927-4941);
+                required here because a frame's normalisation section spans several stripes
+    bpm_stripe  flats: this rank's rows of the bad-pixel mask (edge pixels -> 1)
+    combine     test hook: callable(stripes, scales, flat_fix, bpm_stripe, tel) -> stripe master
+
+    Returns the full (H, W) master on every rank.
+    """
+    H, W = shape
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    r0, r1 = stripe_bounds(H, rank, world)
+    nrows = stripe_rows(H, world)
+    if len(stripes) == 0:
+        raise ValueError('no frames to combine')
+    for s in stripes:
+        if tuple(s.shape) != (r1 - r0, W):
+            raise ValueError('rank {}: stripe shape {} != {}'.format(rank, tuple(s.shape), (r1 - r0, W)))
+    flat = imgtype == 'flat'
+    if flat and medsec is None:
+        raise ValueError('sharded flat combine needs the MEDSEC normalisation medians')
+    fn = combine if combine is not None else _default_combine
+    dev = stripes[0].device
+    if r1 > r0:
+        mine = fn(stripes, medsec, flat, bpm_stripe, tel)
+        if not isinstance(mine, torch.Tensor):
+            mine = torch.from_numpy(np.ascontiguousarray(mine))
+        mine = mine.to(dev)
+    else:
+        mine = torch.empty((0, W), dtype=torch.float32, device=dev)
+    if world == 1:
+        return mine
+    # equal-sized contributions for the single all-gather: pad the last stripe
+    padded = torch.zeros((nrows, W), dtype=torch.float32, device=dev)
+    padded[:r1 - r0] = mine
+    full = torch.empty((world * nrows, W), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(full, padded, group=group)
+    return full[:H]
+
+
+def flat_scale_from_region(frames_full, tel=None):
+    """np.median over set_bb.flat_norm_sec of whole frames held on one rank (used when MEDSEC
+    is not in the header; blackbox.py:4931-4932)."""
+    from . import reduce as R
+    sec = get_par(set_bb.flat_norm_sec, tel)
+    return [float(R.exact_median(R._to_dev(f, torch.float32)[sec])) for f in frames_full]
