@@ -288,10 +288,10 @@ def run_gpu(args, rank, world, local_rank):
 
 def pipe_launches(tel, niter):
     """Kernels of libbbx.so launched per frame by FramePipeline.enqueue (memsets not counted):
-    overscan 8 (+1 BlackGEM saturated-column count), header means 1, fused apply 1, mask
-    neighbours 2, object count 3, hole filling 5, LACosmic 1 + 7 per iteration, cosmic bit
-    1, cosmic object count 3, crosstalk 1."""
-    return 8 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 2 + 3 + 5 + 1 + 7 * niter + 1 + 3 + 1
+    overscan 8 (+1 BlackGEM saturated-column count), header means 1, fused apply 1, sparse mask
+    morphology 11, LACosmic 2 + 7 in the first iteration + 7 per iteration, cosmic bit 1, cosmic
+    object count 3, crosstalk 1."""
+    return 8 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 7 + 7 * niter + 1 + 3 + 1
 
 
 def peak_hbm():
@@ -317,7 +317,8 @@ def measure_lacosmic_iteration(pipe, raws, out_img, out_mask, reps=3):
         R.overscan_enqueue(raws[k], pipe.geom, pipe.tel, gain=pipe.gain, state=pipe.st)
         call('bbx_header_means', R._ptr(pipe.st.biasm), R._ptr(pipe.st.std_vos), R._ptr(pipe.means), R._stream())
         R.apply_enqueue(raws[k], pipe.geom, pipe.tel, st=pipe.st, gain=pipe.gain, mbias=pipe.mbias,
-                        mflat=pipe.mflat, bpm=pipe.bpm, want_mask=True, out_img=out_img, out_mask=out_mask)
+                        mflat=pipe.mflat, bpm=pipe.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
+                        mwork=pipe.mwork)
         R.mask_morph_enqueue(out_mask, pipe.tel, pipe.mwork)
         call('bbx_lacosmic_begin', R._ptr(out_img), R._ptr(out_mask), R._ptr(pipe.crmask), H, W, NITER, 0,
              R._ptr(pipe.lwork.buf), R._ptr(pipe.lwork.info), R._stream())

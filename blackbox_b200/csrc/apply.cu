@@ -27,6 +27,10 @@ struct ApplyArgs {
     float *out_img;            // [red]
     uint8_t *out_mask;         // [red] or null
     int bit_bad, bit_sat;
+    unsigned int *seeds;       // optional list of pixels that seed the mask morphology
+    unsigned int *seed_count;  // [0] entries appended (may exceed seed_cap: overflow)
+    unsigned int seed_cap;
+    unsigned int seed_bits;    // saturated | saturated-connected bit values
 };
 
 template <typename T> struct RawVec4;
@@ -106,6 +110,18 @@ reduce_apply_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyAr
             apply_px<T>(v[k], m[k], have_mask, gn, fitv, osc, a.mbias != nullptr, mb[k], a.mflat != nullptr, mf[k],
                         a.satlevel != nullptr, satl, a.bit_bad, a.bit_sat);
         }
+        if (a.seeds && have_mask) {
+            // pixels found saturated (type 0) and pixels whose bad-pixel mask already carries a
+            // saturated / saturated-connected bit (type 1, bit 31) seed the sparse morphology
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const bool sat = (m[k] & BBX_TMP_SAT) != 0;
+                if (sat || (m[k] & a.seed_bits)) {
+                    const unsigned int slot = atomicAdd(a.seed_count, 1u);
+                    if (slot < a.seed_cap) a.seeds[slot] = (unsigned int)(oo + k) | (sat ? 0u : 0x80000000u);
+                }
+            }
+        }
         if (VEC == 4) {
             st_stream_u4(a.out_img + oo, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
             if (have_mask) st_stream_u32(a.out_mask + oo, (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24));
@@ -149,7 +165,8 @@ static inline bool aligned_to(const void *p, size_t a) { return p == nullptr || 
 extern "C" int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
                                 const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
                                 const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
-                                float *out_img, uint8_t *out_mask, void *stream)
+                                float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
+                                unsigned int seed_cap, void *stream)
 {
     BBX_REQUIRE(g && raw && out_img, "bbx_reduce_apply: null raw / geometry / output");
     BBX_REQUIRE(g->ny == 2 && g->nx * g->ny == BBX_NCHAN, "bbx_reduce_apply: expected 2 x 8 channels");
@@ -157,7 +174,13 @@ extern "C" int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g
     BBX_REQUIRE((const void *)out_img != raw, "bbx_reduce_apply: output must not alias the raw frame");
     ChanF32 gn;
     for (int i = 0; i < BBX_NCHAN; i++) gn.v[i] = gain_h ? gain_h[i] : 1.0f;
-    ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits ? bits->bad : 0, bits ? bits->saturated : 0};
+    BBX_REQUIRE((seeds == nullptr) == (seed_count == nullptr), "bbx_reduce_apply: seeds and seed_count go together");
+    BBX_REQUIRE((long long)g->ny * g->ysize_chan * g->nx * g->xsize_chan < 2147483647LL || seeds == nullptr,
+                "bbx_reduce_apply: frame too large for 31-bit seed indices");
+    ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits ? bits->bad : 0,
+                   bits ? bits->saturated : 0, seeds, seed_count, seed_cap,
+                   bits ? (unsigned int)(bits->saturated | bits->satcon) : 0u};
+    if (seeds) BBX_CUDA(cudaMemsetAsync(seed_count, 0, sizeof(unsigned int), (cudaStream_t)stream));
     const size_t esz = raw_type == BBX_RAW_U16 ? 2 : 4;
     const long long RW = (long long)g->nx * g->xsize_chan, RH = (long long)g->ny * g->ysize_chan;
     const bool vec4 = (g->xsize_chan % 4 == 0) && (g->dx % 4 == 0) && (g->W % 4 == 0) &&

@@ -484,3 +484,254 @@ extern "C" int bbx_mask_counts(const uint8_t *mask, size_t n, unsigned long long
     BBX_CHECK_LAUNCH("mask_counts_kernel");
     return 0;
 }
+
+// ============================================================================================
+// Sparse mask morphology: the same results as the dense kernels above, driven by the list of
+// saturated pixels ("seeds") that bbx_reduce_apply appends while it writes the mask.  Saturated
+// pixels are a few 1e-5 of a frame, so apart from one memset of the state image nothing here
+// touches more than small neighbourhoods of the seeds.
+// ============================================================================================
+#define SEED_BPM 0x80000000u
+
+__device__ __forceinline__ void byte_or(uint8_t *base, size_t p, unsigned int bits)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(base + (p & ~(size_t)3));
+    atomicOr(word, bits << ((unsigned int)(p & 3) * 8));
+}
+__device__ __forceinline__ void byte_and(uint8_t *base, size_t p, unsigned int bits)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(base + (p & ~(size_t)3));
+    const unsigned int sh = (unsigned int)(p & 3) * 8;
+    atomicAnd(word, (bits << sh) | ~(0xffu << sh));
+}
+
+__device__ __forceinline__ unsigned int seed_len(const unsigned int *count, unsigned int cap, int32_t *status)
+{
+    const unsigned int n = *count;
+    if (n > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, 1); return cap; }
+    return n;
+}
+
+// crosstalk victims (15 mirrored positions) and saturated-connected neighbours of every
+// saturated pixel; also resets the object counter and the status word
+__global__ void __launch_bounds__(128)
+ms_neigh_kernel(uint8_t *mask, int H, int W, int ysc, int xsc, unsigned int bit_xtalk, unsigned int bit_satcon,
+                const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
+                int32_t *status)
+{
+    const unsigned int n = seed_len(count, cap, status);
+    // 24 work items per seed: 15 victims + 8 neighbours (+1 idle)
+    const unsigned long long total = (unsigned long long)n * 24ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[t / 24];
+        if (sd & SEED_BPM) continue;
+        const int k = (int)(t % 24);
+        const int y = (int)(sd / (unsigned int)W), x = (int)(sd - (unsigned int)y * (unsigned int)W);
+        if (k < 16) {
+            // victim channel k (skip the source channel itself)
+            const int r = y / ysc, c = x / xsc, ly = y - r * ysc, lx = x - c * xsc;
+            const int src = r * 8 + c;
+            if (k == src) continue;
+            const int vr = k / 8, vc = k % 8;
+            const int vy = (vr == r) ? ly : (ysc - 1 - ly);
+            byte_or(mask, (size_t)(vr * ysc + vy) * W + (size_t)vc * xsc + lx, bit_xtalk);
+        } else {
+            const int j = k - 16;                     // 8 neighbours, skipping the centre
+            const int o = j < 4 ? j : j + 1;
+            const int qy = y + o / 3 - 1, qx = x + o % 3 - 1;
+            if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+            const size_t q = (size_t)qy * W + qx;
+            if (!(mask[q] & BBX_TMP_SAT)) byte_or(mask, q, bit_satcon);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ms_ccl_init_kernel(const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
+                   int *__restrict__ L, int32_t *out_nobj)
+{
+    const unsigned int n = min(*count, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_nobj = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[k];
+        if (!(sd & SEED_BPM)) L[sd] = (int)sd;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ms_ccl_merge_kernel(const uint8_t *__restrict__ mask, int H, int W, const unsigned int *__restrict__ seeds,
+                    const unsigned int *__restrict__ count, unsigned int cap, int *__restrict__ L)
+{
+    if (*count > cap) return;                   // incomplete list: labels of neighbours may be missing
+    const unsigned int n = *count;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[k];
+        if (sd & SEED_BPM) continue;
+        const int p = (int)sd;
+        const int y = p / W, x = p - y * W;
+        if (x > 0 && (mask[p - 1] & BBX_TMP_SAT)) uf_union(L, p, p - 1);
+        if (y > 0) {
+            const int q = p - W;
+            if (mask[q] & BBX_TMP_SAT) uf_union(L, p, q);
+            if (x > 0 && (mask[q - 1] & BBX_TMP_SAT)) uf_union(L, p, q - 1);
+            if (x + 1 < W && (mask[q + 1] & BBX_TMP_SAT)) uf_union(L, p, q + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ms_ccl_count_kernel(const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
+                    const int *__restrict__ L, int32_t *out_nobj)
+{
+    const unsigned int n = min(*count, cap);
+    int c = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[k];
+        if (!(sd & SEED_BPM) && L[sd] == (int)sd) c++;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out_nobj, c);
+}
+
+// closing evaluated only within 2 pixels of a seed: closed(q) = AND over N3(q) of
+// [OR over N3(r) of m], everything outside the image = 0
+__device__ __forceinline__ bool closed_at(const uint8_t *__restrict__ mask, int H, int W, int qy, int qx, unsigned int mbits)
+{
+    if (qy < 1 || qy >= H - 1 || qx < 1 || qx >= W - 1) return false;     // erosion fails at the frame
+    // m on the 5x5 around q, as 5 row bit-fields
+    unsigned int rows[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        const int yy = qy + a - 2;
+        unsigned int bitsr = 0;
+        if (yy >= 0 && yy < H) {
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const int xx = qx + b - 2;
+                if (xx >= 0 && xx < W && (mask[(size_t)yy * W + xx] & mbits)) bitsr |= 1u << b;
+            }
+        }
+        rows[a] = bitsr;
+    }
+    // dilated value at (qy + a - 1, qx + b - 1), a,b in 0..2: any m in rows a..a+2, cols b..b+2
+    bool all = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const unsigned int v = rows[a] | rows[a + 1] | rows[a + 2];
+#pragma unroll
+        for (int b = 0; b < 3; b++) all = all && ((v >> b) & 7u) != 0;
+    }
+    return all;
+}
+
+__global__ void __launch_bounds__(128)
+ms_close_kernel(const uint8_t *__restrict__ mask, HoleWork hw, int H, int W, unsigned int mbits,
+                const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap)
+{
+    const unsigned int n = min(*count, cap);
+    const unsigned long long total = (unsigned long long)n * 25ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[t / 25] & ~SEED_BPM;
+        const int k = (int)(t % 25);
+        const int y = (int)(sd / (unsigned int)W), x = (int)(sd - (unsigned int)y * (unsigned int)W);
+        const int qy = y + k / 5 - 2, qx = x + k % 5 - 2;
+        if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+        if (!closed_at(mask, H, W, qy, qx, mbits)) continue;
+        hw.S[(size_t)qy * W + qx] = 0;
+        atomicMin(&hw.rowmin[qy], qx); atomicMax(&hw.rowmax[qy], qx);
+        atomicMin(&hw.colmin[qx], qy); atomicMax(&hw.colmax[qx], qy);
+    }
+}
+
+// commit: closed pixels around the seeds, enclosed background in the candidate tiles, and the
+// removal of the internal saturation marker
+__global__ void __launch_bounds__(128)
+ms_commit_seeds_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bit_satcon,
+                       const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
+                       const int32_t *__restrict__ unconverged, int32_t *status)
+{
+    if (*unconverged) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 2); return; }
+    const unsigned int n = min(*count, cap);
+    const unsigned long long total = (unsigned long long)n * 25ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[t / 25] & ~SEED_BPM;
+        const int k = (int)(t % 25);
+        const int y = (int)(sd / (unsigned int)W), x = (int)(sd - (unsigned int)y * (unsigned int)W);
+        const int qy = y + k / 5 - 2, qx = x + k % 5 - 2;
+        if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+        const size_t q = (size_t)qy * W + qx;
+        if (hw.S[q] == 0 && (mask[q] & 0x7fu) == 0) byte_or(mask, q, bit_satcon);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ms_commit_tiles_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bit_satcon,
+                       const int32_t *__restrict__ unconverged)
+{
+    if (*unconverged) return;
+    const int ntiles = hw.counters[0];
+    const int tiles_x = (W + HOLE_TILE - 1) / HOLE_TILE;
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const int tile = hw.tiles[ti];
+        const int y0 = (tile / tiles_x) * HOLE_TILE, x0 = (tile % tiles_x) * HOLE_TILE;
+        for (int i = threadIdx.x; i < HOLE_TILE * HOLE_TILE; i += blockDim.x) {
+            const int gy = y0 + i / HOLE_TILE, gx = x0 + i % HOLE_TILE;
+            if (gy >= H || gx >= W) continue;
+            const size_t q = (size_t)gy * W + gx;
+            if (hw.S[q] == 1 && !hole_free_line(hw, gy, gx) && (mask[q] & 0x7fu) == 0) byte_or(mask, q, bit_satcon);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ms_clear_marker_kernel(uint8_t *mask, const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count,
+                       unsigned int cap, const int32_t *__restrict__ unconverged)
+{
+    if (*unconverged) return;
+    const unsigned int n = min(*count, cap);
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[k];
+        if (!(sd & SEED_BPM)) byte_and(mask, sd, 0x7fu);
+    }
+}
+
+extern "C" int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                     const bbx_maskbits *bits, const unsigned int *seeds, const unsigned int *seed_count,
+                                     unsigned int seed_cap, void *work, int32_t *labels, int32_t *out_nobj, int rounds,
+                                     int32_t *status, void *stream)
+{
+    BBX_REQUIRE(mask && bits && seeds && seed_count && work && labels && out_nobj && status, "bbx_mask_morph_sparse: null argument");
+    BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_mask_morph_sparse: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
+    BBX_REQUIRE(((uintptr_t)mask & 3) == 0, "bbx_mask_morph_sparse: mask must be 4-byte aligned");
+    BBX_REQUIRE(((bits->bad | bits->cosmic | bits->saturated | bits->satcon | bits->sattrail | bits->edge | bits->crosstalk) & 0x80) == 0,
+                "bbx_mask_morph_sparse: mask value 128 is reserved for internal use");
+    cudaStream_t s = (cudaStream_t)stream;
+    HoleWork hw = carve_hole_work(work, H, W);
+    const int lb = BBX_SM_COUNT * 4;
+    const unsigned int mbits = (unsigned int)(bits->saturated | bits->satcon);
+    BBX_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    ms_neigh_kernel<<<lb, 128, 0, s>>>(mask, H, W, ysize_chan, xsize_chan, (unsigned int)bits->crosstalk,
+                                       (unsigned int)bits->satcon, seeds, seed_count, seed_cap, status);
+    ms_ccl_init_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
+    ms_ccl_merge_kernel<<<lb, 128, 0, s>>>(mask, H, W, seeds, seed_count, seed_cap, labels);
+    ms_ccl_count_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
+    // hole filling: state image = background everywhere, closed foreground near the seeds
+    BBX_CUDA(cudaMemsetAsync(hw.S, 1, (size_t)H * W, s));
+    const int n = H > W ? H : W;
+    hole_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(hw, H, W);
+    ms_close_kernel<<<lb, 128, 0, s>>>(mask, hw, H, W, mbits, seeds, seed_count, seed_cap);
+    BBX_CUDA(cudaMemsetAsync(hw.tile_flag, 0, sizeof(int) * hw.max_tiles, s));
+    hole_candidates_kernel<<<H, 256, 0, s>>>(hw, H, W, hw.tile_flag);
+    BBX_CHECK_LAUNCH("bbx_mask_morph_sparse");
+    int32_t *unconverged = status + 1;           // status[1]: scratch word of the propagation
+    if (launch_propagate(hw, H, W, rounds, unconverged, s)) return -2;
+    ms_commit_seeds_kernel<<<lb, 128, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, seeds, seed_count, seed_cap,
+                                              unconverged, status);
+    ms_commit_tiles_kernel<<<BBX_SM_COUNT * 2, 256, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, unconverged);
+    ms_clear_marker_kernel<<<lb, 128, 0, s>>>(mask, seeds, seed_count, seed_cap, unconverged);
+    BBX_CHECK_LAUNCH("bbx_mask_morph_sparse");
+    return 0;
+}

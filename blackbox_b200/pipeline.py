@@ -80,15 +80,17 @@ class FramePipeline:
             self._spline_cols = R.overscan_resolve_spline(st, strict=False)
         call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
 
-    def _rest(self, raw_t, out_img, out_mask, wait_holes=False, lac_mode=R.LAC_LAZY):
+    def _rest(self, raw_t, out_img, out_mask, dense_morph=False, lac_mode=R.LAC_LAZY):
         tel, geom = self.tel, self.geom
         RH, RW = geom.red_shape
         s = R._stream()
         R.apply_enqueue(raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias,
-                        mflat=self.mflat, bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask)
-        R.mask_morph_enqueue(out_mask, tel, self.mwork, count_objects=self.count_objects)
-        if wait_holes:
-            R.mask_morph_finish(out_mask, tel, self.mwork)
+                        mflat=self.mflat, bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
+                        mwork=None if dense_morph else self.mwork)
+        R.mask_morph_enqueue(out_mask, tel, self.mwork, count_objects=self.count_objects,
+                             sparse=not dense_morph)
+        if dense_morph:
+            R.mask_morph_finish(out_mask, tel, self.mwork, sparse=False)
         if self.niter > 0:
             R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
                                get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
@@ -119,7 +121,7 @@ class FramePipeline:
         incomplete) into the pinned int32[1] tensor ``host_slot`` (valid after the stream is
         synchronised): non-zero means the frame has to be finished with ``finish()`` before its
         outputs are used."""
-        stat = self.mwork.unconverged
+        stat = self.mwork.status[0:1]
         if self.niter > 0:
             stat = stat | self.lwork.info[2:3].to(torch.int32)
         host_slot.copy_(stat, non_blocking=True)
@@ -131,17 +133,18 @@ class FramePipeline:
         st = self.st
         out_img, out_mask = self._out
         redo = False
-        unconverged = int(self.mwork.unconverged.item()) != 0
+        morph_bad = int(self.mwork.status[0].item()) != 0
         lac_status = int(self.lwork.info[2].item()) if self.niter > 0 else 0
-        if unconverged or lac_status != 0:
-            # hole filling needed more rounds (the mask LACosmic saw was not final) or the lazy
-            # LACosmic needs its dense twin: redo everything after the overscan stage
+        if morph_bad or lac_status != 0:
+            # the sparse mask morphology overflowed / did not converge (the mask LACosmic saw was
+            # not final) or the lazy LACosmic needs its dense twin: redo everything after the
+            # overscan stage with the dense kernels concerned
             redo = True
-            self._rest(self._raw, out_img, out_mask, wait_holes=True,
+            self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad,
                        lac_mode=R.LAC_DENSE if lac_status != 0 else R.LAC_LAZY)
             torch.cuda.current_stream().synchronize()
             if self.niter > 0 and int(self.lwork.info[2].item()) != 0:
-                self._rest(self._raw, out_img, out_mask, wait_holes=True, lac_mode=R.LAC_DENSE)
+                self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad, lac_mode=R.LAC_DENSE)
                 torch.cuda.current_stream().synchronize()
         header, header_mask = {}, {}
         if fill_header:

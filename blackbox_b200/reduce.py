@@ -32,6 +32,8 @@ tel = None          # module-global telescope name, as in the reference (blackbo
 
 _bpm_registry = {}  # filter -> bad-pixel mask (numpy or CUDA tensor); see set_bad_pixel_mask
 
+MASK_MORPH_SPARSE = True   # mask_init: seed-list driven morphology (False: dense passes; same result)
+
 
 # -------------------------------------------------------------------------------------------
 # plumbing
@@ -224,8 +226,10 @@ def overscan_resolve_spline(st, strict):
 
 
 def apply_enqueue(raw_t, geom, tel_, st=None, gain=None, mbias=None, mflat=None, bpm=None,
-                  want_mask=False, out_img=None, out_mask=None):
-    """Enqueue the fused per-pixel pass (include/bbx.h: bbx_reduce_apply)."""
+                  want_mask=False, out_img=None, out_mask=None, mwork=None):
+    """Enqueue the fused per-pixel pass (include/bbx.h: bbx_reduce_apply).  With ``mwork`` (a
+    MaskWork) the saturated pixels are also appended to its seed list for the sparse mask
+    morphology."""
     g = geom.as_struct()
     RH, RW = geom.red_shape
     if out_img is None:
@@ -238,7 +242,10 @@ def apply_enqueue(raw_t, geom, tel_, st=None, gain=None, mbias=None, mflat=None,
          _ptr(st.vos_fit) if st is not None else None, _ptr(st.oscan) if st is not None else None,
          _ptr(mbias), _ptr(mflat), _ptr(bpm),
          _ptr(st.satlevel) if (st is not None and want_mask) else None,
-         C.byref(bits), _ptr(out_img), _ptr(out_mask) if want_mask else None, _stream())
+         C.byref(bits), _ptr(out_img), _ptr(out_mask) if want_mask else None,
+         _ptr(mwork.seeds) if (mwork is not None and want_mask) else None,
+         _ptr(mwork.seed_count) if (mwork is not None and want_mask) else None,
+         int(mwork.seed_cap) if mwork is not None else 0, _stream())
     return out_img, out_mask
 
 
@@ -336,29 +343,44 @@ class MaskWork:
         self.labels = torch.empty(H * W, dtype=torch.int32, device=device)
         self.unconverged = torch.zeros(1, dtype=torch.int32, device=device)
         self.nobj = torch.zeros(1, dtype=torch.int32, device=device)
+        self.seed_cap = H * W // 8 + 1024
+        self.seeds = torch.empty(self.seed_cap, dtype=torch.int32, device=device)
+        self.seed_count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(2, dtype=torch.int32, device=device)
 
 
-def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=64):
+def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=4096, sparse=True):
     """Enqueue crosstalk-victim / saturated-connected / NOBJ-SAT / fill_sat_holes on a mask
-    that carries the saturation marker written by bbx_reduce_apply."""
+    that carries the saturation marker written by bbx_reduce_apply.  ``sparse``: driven by the
+    seed list in ``work`` (filled by apply_enqueue(..., mwork=work)); otherwise dense passes."""
     H, W = mask_t.shape
     bits = _bits(tel_)
     s = _stream()
+    if sparse:
+        call('bbx_mask_morph_sparse', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), _ptr(work.seeds),
+             _ptr(work.seed_count), int(work.seed_cap), _ptr(work.holes), _ptr(work.labels), _ptr(work.nobj),
+             int(rounds), _ptr(work.status), s)
+        return
+    work.status.zero_()
     call('bbx_mask_sat_neighbours', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), s)
     if count_objects:
         call('bbx_count_objects', _ptr(mask_t), 0x80, H, W, _ptr(work.labels), _ptr(work.nobj), s)
-    call('bbx_fill_sat_holes', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), rounds,
+    call('bbx_fill_sat_holes', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), min(rounds, 64),
          _ptr(work.unconverged), s)
 
 
-def mask_morph_finish(mask_t, tel_, work, rounds=1024):
-    """Synchronise; continue the hole filling if it had not converged.  Returns NOBJ-SAT."""
+def mask_morph_finish(mask_t, tel_, work, rounds=1024, sparse=True):
+    """Synchronise.  Sparse: returns (NOBJ-SAT, ok); ok False means the mask is not final and
+    the dense path has to be run on a fresh seed mask.  Dense: continues the hole filling until
+    it has converged."""
     H, W = mask_t.shape
+    if sparse:
+        return int(work.nobj.item()), int(work.status[0].item()) == 0
     bits = _bits(tel_)
     while int(work.unconverged.item()) != 0:
         call('bbx_fill_holes_more', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), rounds,
              _ptr(work.unconverged), _stream())
-    return int(work.nobj.item())
+    return int(work.nobj.item()), True
 
 
 def mask_init(data, header, filt, imgtype, bpm=None):
@@ -393,10 +415,16 @@ def mask_init(data, header, filt, imgtype, bpm=None):
     geom = _reduced_geometry((H, W), tel)
     satlevel_t = torch.from_numpy(satlevel_chans).to(t.device)
     out_img = torch.empty_like(t)
-    mask_t = _apply_seed(t, geom, satlevel_t, bpm_t, out_img)
     work = MaskWork(H, W, t.device)
-    mask_morph_enqueue(mask_t, tel, work)
-    nobj = mask_morph_finish(mask_t, tel, work)
+    ok = False
+    if MASK_MORPH_SPARSE:
+        mask_t = _apply_seed(t, geom, satlevel_t, bpm_t, out_img, work)
+        mask_morph_enqueue(mask_t, tel, work, sparse=True)
+        nobj, ok = mask_morph_finish(mask_t, tel, work, sparse=True)
+    if not ok:                      # seed list overflow / unconverged holes: dense passes
+        mask_t = _apply_seed(t, geom, satlevel_t, bpm_t, out_img, None)
+        mask_morph_enqueue(mask_t, tel, work, sparse=False)
+        nobj, _ = mask_morph_finish(mask_t, tel, work, sparse=False)
     _set(header_mask, 'NOBJ-SAT', nobj, 'number of saturated objects')
     _set(header, 'NOBJ-SAT', nobj, 'number of saturated objects')
     if is_np:
@@ -406,12 +434,15 @@ def mask_init(data, header, filt, imgtype, bpm=None):
     return mask_t, header_mask
 
 
-def _apply_seed(t, geom, satlevel_t, bpm_t, out_img):
+def _apply_seed(t, geom, satlevel_t, bpm_t, out_img, work):
     g = geom.as_struct()
     out_mask = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
     bits = _bits(tel)
     call('bbx_reduce_apply', _ptr(t), 1, C.byref(g), None, None, None, None, None, _ptr(bpm_t),
-         _ptr(satlevel_t), C.byref(bits), _ptr(out_img), _ptr(out_mask), _stream())
+         _ptr(satlevel_t), C.byref(bits), _ptr(out_img), _ptr(out_mask),
+         _ptr(work.seeds) if work is not None else None,
+         _ptr(work.seed_count) if work is not None else None,
+         int(work.seed_cap) if work is not None else 0, _stream())
     return out_mask
 
 

@@ -132,11 +132,17 @@ int bbx_hos_fit(const float *hos_mean, const float *hos_std, const int32_t *hos_
  *   non-finite -> 0 and 'bad' (if unmasked); saturated = v >= satlevel[chan] (float64
  *   compare) -> 'saturated'; v /= mflat.
  * Null mbias / mflat / bpm / out_mask / satlevel skip the corresponding step.
- * out_img f32 [red]; out_mask u8 [red]. */
+ * out_img f32 [red]; out_mask u8 [red].
+ * seeds / seed_count (optional, device): the pixels found saturated are appended to seeds
+ * (index into the reduced frame; bit 31 marks a pixel whose bad-pixel mask already carries a
+ * saturated / saturated-connected bit); seed_count[0] is reset by the call and may end up
+ * larger than seed_cap (overflow: the list is then incomplete).  Input of
+ * bbx_mask_morph_sparse. */
 int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
                      const double *vos_fit, const double *oscan, const float *mbias,
                      const float *mflat, const uint8_t *bpm, const double *satlevel,
                      const bbx_maskbits *bits, float *out_img, uint8_t *out_mask,
+                     unsigned int *seeds, unsigned int *seed_count, unsigned int seed_cap,
                      void *stream);
 
 /* satlevel[i] = sat_e_h[i] - biasm[i] on the device (blackbox.py:4448-4454) */
@@ -168,6 +174,20 @@ int bbx_fill_sat_holes(uint8_t *mask, int H, int W, const bbx_maskbits *bits, vo
                        int rounds, int32_t *unconverged, void *stream);
 int bbx_fill_holes_more(uint8_t *mask, int H, int W, const bbx_maskbits *bits, void *work,
                         int rounds, int32_t *unconverged, void *stream);
+
+/* The whole of mask_init's morphology driven by the seed list of bbx_reduce_apply instead of
+ * dense passes over the mask: crosstalk-victim and saturated-connected bits, NOBJ-SAT (8-
+ * connected components of the saturated pixels), fill_sat_holes, clearing of BBX_TMP_SAT.
+ * Bit-identical to bbx_mask_sat_neighbours + bbx_count_objects + bbx_fill_sat_holes.
+ * work >= bbx_fill_holes_work_bytes(H, W); labels int32 [H*W] scratch (touched sparsely);
+ * out_nobj device int32; status device int32[2]: status[0] bit 0 = seed list overflow, bit 1 =
+ * hole propagation did not converge in `rounds` -- in both cases the mask is NOT final and the
+ * dense entry points have to be run on a fresh mask; status[1] is scratch. */
+int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                          const bbx_maskbits *bits, const unsigned int *seeds,
+                          const unsigned int *seed_count, unsigned int seed_cap, void *work,
+                          int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
+                          void *stream);
 
 /* number of 8-connected components of (mask & bit) != 0  (ndimage.label; blackbox.py:4354,
  * 4544).  labels: int32 [H*W] scratch; out_count device int32. */

@@ -184,13 +184,18 @@ def _mask_case(seed, shape=(2 * 96, 8 * 132)):
     return data, bpm
 
 
+@pytest.mark.parametrize('sparse', [True, False])
 @pytest.mark.parametrize('tel', ['ML1', 'BG3'])
-def test_mask_init_bit_exact(tel, small_bb):
+def test_mask_init_bit_exact(tel, sparse, small_bb, monkeypatch):
     import torch
     from blackbox_b200 import reduce as bbr
     from oracle import reduce as R
+    monkeypatch.setattr(bbr, 'MASK_MORPH_SPARSE', sparse)
     small_bb(96, 132)
     data, bpm = _mask_case(5)
+    bpm[120:123, 500] = 4            # a bad-pixel mask that already carries saturated bits
+    bpm[130, 510:512] = 8            # ... and saturated-connected ones: part of the closing
+    bpm[130, 513] = 8                # one-pixel gap at column 512: closed, filled if unmasked
     hdr = {'BIASM{}'.format(i + 1): 6500.0 + i for i in range(16)}
     hdr_o, hdr_g = dict(hdr), dict(hdr)
     d_o = data.copy()
