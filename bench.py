@@ -289,9 +289,9 @@ def run_gpu(args, rank, world, local_rank):
 def pipe_launches(tel, niter):
     """Kernels of libbbx.so launched per frame by FramePipeline.enqueue (memsets not counted):
     overscan 8 (+1 BlackGEM saturated-column count), header means 1, fused apply 1, sparse mask
-    morphology 11, LACosmic 2 + 7 in the first iteration + 7 per iteration, cosmic bit 1, cosmic
-    object count 3, crosstalk 1."""
-    return 8 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 7 + 7 * niter + 1 + 3 + 1
+    morphology 11, LACosmic 2 + 7 in the first iteration + 7 per iteration, cosmic bit + object count 3,
+    crosstalk 1."""
+    return 8 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 7 + 7 * niter + 3 + 1
 
 
 def peak_hbm():

@@ -59,6 +59,7 @@ _SIGNATURES = {
     'bbx_lacosmic': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],
     'bbx_lacosmic_begin': [P, P, P, I, I, I, I, P, P, P],
     'bbx_lacosmic_iteration': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],
+    'bbx_lacosmic_finish': [P, P, I, I, I, I, P, P, P, P],
     'bbx_select_work_bytes': [],
     'bbx_masked_lower_median': [P, P, SZ, P, P, P],
     'bbx_medfilt': [P, P, I, I, I, P],

@@ -612,3 +612,90 @@ extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, 
                                    it, mode, work, out_info, stream)) return -2;
     return 0;
 }
+
+// --------------------------------------------------------------------------------------------
+// after the iterations: cosmic-ray bit into the frame mask and NCOSMICS (8-connected components
+// of crmask; ndimage.label, blackbox.py:4349-4355) from the CR list instead of dense passes
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sp_uf_find(const int *L, int i)
+{
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+__device__ __forceinline__ void sp_uf_union(int *L, int a, int b)
+{
+    bool done;
+    do {
+        a = sp_uf_find(L, a);
+        b = sp_uf_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(128)
+sp_finish_mark_kernel(uint8_t *mask, unsigned int bit, SparseWork w, int *__restrict__ L, int32_t *out_n)
+{
+    const unsigned int n = list_len(&w.cnt->nCR, w.capCR);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int p = w.listCR[k];
+        if (mask) {
+            unsigned int *word = reinterpret_cast<unsigned int *>(mask + (p & ~3u));
+            atomicOr(word, bit << ((p & 3u) * 8));
+        }
+        L[p] = (int)p;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sp_finish_merge_kernel(const uint8_t *__restrict__ crmask, int H, int W, SparseWork w, int *__restrict__ L)
+{
+    if (w.cnt->nCR > w.capCR) return;
+    const unsigned int n = w.cnt->nCR;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int p = (int)w.listCR[k];
+        const int y = p / W, x = p - y * W;
+        if (x > 0 && crmask[p - 1]) sp_uf_union(L, p, p - 1);
+        if (y > 0) {
+            const int q = p - W;
+            if (crmask[q]) sp_uf_union(L, p, q);
+            if (x > 0 && crmask[q - 1]) sp_uf_union(L, p, q - 1);
+            if (x + 1 < W && crmask[q + 1]) sp_uf_union(L, p, q + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sp_finish_count_kernel(SparseWork w, const int *__restrict__ L, int32_t *out_n)
+{
+    const unsigned int n = list_len(&w.cnt->nCR, w.capCR);
+    int c = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int p = w.listCR[k];
+        if (L[p] == (int)p) c++;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out_n, c);
+}
+
+extern "C" int bbx_lacosmic_finish(const uint8_t *crmask, uint8_t *mask, int cosmic_bit, int H, int W, int mode,
+                                   void *work, int32_t *labels, int32_t *out_ncosmics, void *stream)
+{
+    BBX_REQUIRE(crmask && work && labels && out_ncosmics, "bbx_lacosmic_finish: null argument");
+    BBX_REQUIRE(mask == nullptr || ((uintptr_t)mask & 3) == 0, "bbx_lacosmic_finish: mask must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) {
+        if (mask && bbx_mask_or(mask, crmask, (size_t)H * W, cosmic_bit, stream)) return -2;
+        return bbx_count_objects(crmask, 0xff, H, W, labels, out_ncosmics, stream);
+    }
+    const SparseWork w = carve_sparse(work, (size_t)H * W);
+    const int lb = BBX_SM_COUNT * 4;
+    sp_finish_mark_kernel<<<lb, 128, 0, st>>>(mask, (unsigned int)cosmic_bit, w, labels, out_ncosmics);
+    sp_finish_merge_kernel<<<lb, 128, 0, st>>>(crmask, H, W, w, labels);
+    sp_finish_count_kernel<<<lb, 128, 0, st>>>(w, labels, out_ncosmics);
+    BBX_CHECK_LAUNCH("bbx_lacosmic_finish");
+    return 0;
+}

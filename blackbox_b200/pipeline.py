@@ -96,10 +96,8 @@ class FramePipeline:
                                get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
                                self.niter, self.lwork, readnoise_dev=self.means[1:], mode=lac_mode)
             bit = int(get_par(set_bb.mask_value, tel)['cosmic ray'])
-            call('bbx_mask_or', R._ptr(out_mask), R._ptr(self.crmask), out_mask.numel(), bit, s)
-            if self.count_objects:
-                call('bbx_count_objects', R._ptr(self.crmask), 1, RH, RW, R._ptr(self.mwork.labels),
-                     R._ptr(self.ncosmic), s)
+            call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW, int(lac_mode),
+                 R._ptr(self.lwork.buf), R._ptr(self.mwork.labels), R._ptr(self.ncosmic), s)
         if self.coeffs is not None:
             R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
 

@@ -508,31 +508,12 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
                                   '(the reference passes satlevel=inf, blackbox.py:4272)')
     is_np = isinstance(indat, np.ndarray)
     src = _to_dev(indat, torch.float32)
-    clean = src.clone()
-    if gain != 1.0:
-        clean *= float(np.float32(gain))
-    H, W = clean.shape
     inmask_t = None
     if inmask is not None:
         inmask_t = _to_dev(inmask)
         inmask_t = (inmask_t != 0).to(torch.uint8) if inmask_t.dtype != torch.uint8 else inmask_t
-    crmask = torch.empty((H, W), dtype=torch.uint8, device=clean.device)
-    work = LacosmicWork(H, W, niter, clean.device)
-    first = LAC_LAZY if mode is None else mode
-    lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work, mode=first)
-    inf = work.info.cpu().numpy()
-    status = int(inf[2])
-    if status != 0:
-        if mode is not None:
-            raise RuntimeError('detect_cosmics: lazy evaluation incomplete (status {})'.format(status))
-        clean.copy_(src)
-        if gain != 1.0:
-            clean *= float(np.float32(gain))
-        lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work,
-                         mode=LAC_DENSE)
-        inf = work.info.cpu().numpy()
-    if gain != 1.0:
-        clean /= float(np.float32(gain))
+    clean, crmask, work, used_mode, inf, status = _detect_cosmics_dev(
+        src, inmask_t, sigclip, sigfrac, objlim, gain, readnoise, niter, mode)
     if info is not None:
         info.update(iterations=int(inf[0]), ncr_per_iter=inf[4:4 + int(inf[0])].copy(),
                     lazy_status=status)
@@ -542,24 +523,56 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
     return crb, clean
 
 
+def _detect_cosmics_dev(src, inmask_t, sigclip, sigfrac, objlim, gain, readnoise, niter, mode):
+    """Device part of detect_cosmics: lazy evaluation first, dense repeat if its status word
+    asks for it (or if ``mode`` forces one).  Returns (clean, crmask u8, work, mode used,
+    info array, lazy status)."""
+    H, W = src.shape
+    work = LacosmicWork(H, W, niter, src.device)
+    crmask = torch.empty((H, W), dtype=torch.uint8, device=src.device)
+
+    def run(m):
+        clean = src.clone()
+        if gain != 1.0:
+            clean *= float(np.float32(gain))
+        lacosmic_enqueue(clean, inmask_t, crmask, sigclip, sigfrac, objlim, readnoise, niter, work, mode=m)
+        return clean, work.info.cpu().numpy()
+
+    first = LAC_LAZY if mode is None else mode
+    if sigclip < 0 or sigfrac < 0:
+        first = LAC_DENSE
+    clean, inf = run(first)
+    status = int(inf[2])
+    used = first
+    if status != 0:
+        if mode is not None:
+            raise RuntimeError('detect_cosmics: lazy evaluation incomplete (status {})'.format(status))
+        clean, inf = run(LAC_DENSE)
+        used = LAC_DENSE
+    if gain != 1.0:
+        clean /= float(np.float32(gain))
+    return clean, crmask, work, used, inf, status
+
+
 def cosmics_corr(data, header, data_mask, header_mask):
     """LACosmic detection + cleaning, cosmic-ray bit into the mask, NCOSMICS into both
     headers (blackbox.py:4259-4370).  Uses the module-global ``tel``."""
+    if get_par(set_bb.sepmed, tel):
+        raise NotImplementedError('cosmics_corr: sepmed=True is not implemented')
     is_np = isinstance(data, np.ndarray)
     d = _to_dev(data, torch.float32)
     m = _to_dev(data_mask, torch.uint8)
-    mask_cr, clean = detect_cosmics(
-        d, inmask=(m != 0), sigclip=get_par(set_bb.sigclip, tel),
-        sigfrac=get_par(set_bb.sigfrac, tel), objlim=get_par(set_bb.objlim, tel),
-        niter=get_par(set_bb.niter, tel), readnoise=header['RDNOISE'], gain=1.0,
-        satlevel=np.inf, cleantype='medmask', sepmed=get_par(set_bb.sepmed, tel))
-    cr8 = mask_cr.to(torch.uint8)
+    if isinstance(data_mask, torch.Tensor) and m.data_ptr() != data_mask.data_ptr():
+        m = m.clone()
+    clean, cr8, work, used, _, _ = _detect_cosmics_dev(
+        d, m, get_par(set_bb.sigclip, tel), get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel),
+        1.0, header['RDNOISE'], get_par(set_bb.niter, tel), None)
     bit = get_par(set_bb.mask_value, tel)['cosmic ray']
-    call('bbx_mask_or', _ptr(m), _ptr(cr8), m.numel(), int(bit), _stream())
     H, W = cr8.shape
     labels = torch.empty(H * W, dtype=torch.int32, device=d.device)
     nobj = torch.zeros(1, dtype=torch.int32, device=d.device)
-    call('bbx_count_objects', _ptr(cr8), 1, H, W, _ptr(labels), _ptr(nobj), _stream())
+    call('bbx_lacosmic_finish', _ptr(cr8), _ptr(m), int(bit), H, W, int(used), _ptr(work.buf),
+         _ptr(labels), _ptr(nobj), _stream())
     ncosmics_persec = int(nobj.item()) / float(header['EXPTIME'])
     _set(header, 'NCOSMICS', ncosmics_persec, '[/s] number of cosmic rays identified')
     _set(header_mask, 'NCOSMICS', ncosmics_persec, '[/s] number of cosmic rays identified')

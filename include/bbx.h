@@ -252,6 +252,14 @@ int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, i
                            const double *readnoise_dev, int iter, int mode, void *work,
                            long long *out_info, void *stream);
 
+/* After bbx_lacosmic (same mode, same work buffer): mask[crmask != 0] |= cosmic_bit
+ * (blackbox.py:4349; mask may be null) and out_ncosmics = number of 8-connected cosmic-ray
+ * objects (ndimage.label, blackbox.py:4354-4355).  mode 0 walks the cosmic-ray pixel list of
+ * the lazy path; mode 1 does dense passes.  labels: int32 [H*W] scratch. */
+int bbx_lacosmic_finish(const uint8_t *crmask, uint8_t *mask, int cosmic_bit, int H, int W,
+                        int mode, void *work, int32_t *labels, int32_t *out_ncosmics,
+                        void *stream);
+
 /* lower median a[(n-1)/2] of the pixels with inmask == 0 (astroscrappy's background level)
  * work >= bbx_select_work_bytes(); out device float32 */
 size_t bbx_select_work_bytes(void);

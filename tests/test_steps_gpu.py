@@ -314,3 +314,30 @@ def test_master_flat_combine(small_bb):
         assert got[50, 60] == 1.0 and (got[:5] == 1.0).all()
     finally:
         set_bb.flat_norm_sec.update(set_bb_sec)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('as_tensor', [False, True])
+def test_cosmics_corr_parity(as_tensor, small_bb):
+    import torch
+    from blackbox_b200 import reduce as bbr, set_bb
+    from oracle import reduce as R
+    small_bb(80, 116)
+    img, mask = _lacosmic_case(11, shape=(160, 928))
+    data_mask = np.where(mask, 1, 0).astype(np.uint8)
+    data_mask[:3, :] |= 32
+    hdr_o = {'RDNOISE': 8.5, 'EXPTIME': 30.0}
+    hdr_g = dict(hdr_o)
+    hm_o, hm_g = {}, {}
+    d_o, m_o = R.cosmics_corr(img.copy(), hdr_o, data_mask.copy(), hm_o, tel='ML1')
+    bbr.tel = 'ML1'
+    if as_tensor:
+        d_in, m_in = torch.from_numpy(img.copy()).cuda(), torch.from_numpy(data_mask.copy()).cuda()
+        d_g, m_g = bbr.cosmics_corr(d_in, hdr_g, m_in, hm_g)
+        assert m_g.data_ptr() == m_in.data_ptr()
+        d_g, m_g = d_g.cpu().numpy(), m_g.cpu().numpy()
+    else:
+        d_g, m_g = bbr.cosmics_corr(img.copy(), hdr_g, data_mask.copy(), hm_g)
+    assert (m_o & set_bb.mask_value['cosmic ray']).sum() > 0
+    assert np.array_equal(m_g, m_o) and np.array_equal(d_g, d_o)
+    assert hdr_g['NCOSMICS'] == hdr_o['NCOSMICS'] == hm_g['NCOSMICS'] > 0
