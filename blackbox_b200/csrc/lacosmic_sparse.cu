@@ -139,18 +139,21 @@ __device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsi
 // --------------------------------------------------------------------------------------------
 // COLLECT (first iteration only): also count the unmasked pixels and those below the median
 // bracket, and gather the values inside the bracket (one block-aggregated append per block).
-// Grid: x = 512-pixel segments of a row, y = row; 128 threads x 4 pixels.
+// A block owns a 512-pixel wide, SCAN_ROWS tall strip: 128 threads x 4 pixels walk down the
+// rows keeping the previous / current / next row in registers, so every pixel is loaded once
+// per strip (plus one halo row at either end).
 // The list-A test `L+ / den_min > sigclip` is replaced by the division-free superset
 // `L+ > thr_lo`, thr_lo = sigclip * den_min * (1 - 2^-20): pixels it lets through in excess are
 // rejected by the exact tests of the candidate kernels.
 #define SCAN_THREADS 128
+#define SCAN_ROWS 16
 template <bool COLLECT>
 __global__ void __launch_bounds__(SCAN_THREADS)
 sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
                SparseWork w, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
-    __shared__ float s_buf[COLLECT ? 4 * SCAN_THREADS : 1];
+    __shared__ float s_buf[COLLECT ? 4 * SCAN_THREADS * SCAN_ROWS : 1];
     __shared__ unsigned int s_cnt, s_base;
     __shared__ unsigned long long s_red[33];
     unsigned int n_valid = 0, n_below = 0;
@@ -166,47 +169,59 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     const float den_min = 2.0f * nmin;
     const float thr_lo = (float)((double)prm.sigclip * (double)den_min * (1.0 - 9.5367431640625e-07));
     const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    const int y = blockIdx.y;
+    const bool mvec_ok = inmask && (W % 4 == 0) && (((uintptr_t)inmask & 3) == 0);
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    const int ya = blockIdx.y * SCAN_ROWS, yb = min(ya + SCAN_ROWS, H);
     if (x0 < W) {
-        const size_t i = (size_t)y * W + x0;
-        if (COLLECT) {
-            const bool mvec = inmask && vec_ok && x0 + 4 <= W && (((uintptr_t)inmask & 3) == 0);
-            unsigned int mm = 0;
-            if (mvec) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
-            for (int k = 0; k < 4 && x0 + k < W; k++) {
-                const bool masked = inmask ? (mvec ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
-                if (masked) continue;
-                const float v = img[i + k];
-                n_valid++;
-                if (v < bra) n_below++;
-                else if (v <= brb) s_buf[atomicAdd(&s_cnt, 1u)] = v;
-            }
+        const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
+        if (fast_x) {
+            if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
+            cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
         }
-        if (vec_ok && y > 0 && y + 1 < H && x0 > 0 && x0 + 4 < W) {
-            const float4 c = *reinterpret_cast<const float4 *>(img + i);
-            const float4 u = *reinterpret_cast<const float4 *>(img + i - W);
-            const float4 d = *reinterpret_cast<const float4 *>(img + i + W);
-            const float lft = img[i - 1], rgt = img[i + 4];
-            const float cc[6] = {lft, c.x, c.y, c.z, c.w, rgt};
-            const float uu[4] = {u.x, u.y, u.z, u.w}, dd[4] = {d.x, d.y, d.z, d.w};
+        for (int y = ya; y < yb; y++) {
+            const size_t i = (size_t)y * W + x0;
+            if (fast_x && y + 1 < H) dn = *reinterpret_cast<const float4 *>(img + i + W);
+            if (COLLECT) {
+                unsigned int mm = 0;
+                const bool mv = mvec_ok && x0 + 4 <= W;
+                if (mv) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
+                const float cv4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
-                float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
-                float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
-                float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
-                float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
-                float p = s00 + s01; p = p + s10; p = p + s11;
-                const float lp = p * 0.25f;
-                if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                for (int k = 0; k < 4; k++) {
+                    if (x0 + k >= W) break;
+                    const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
+                    if (masked) continue;
+                    const float v = fast_x ? cv4[k] : img[i + k];
+                    n_valid++;
+                    if (v < bra) n_below++;
+                    else if (v <= brb) s_buf[atomicAdd(&s_cnt, 1u)] = v;
+                }
             }
-        } else {
-            for (int k = 0; k < 4 && x0 + k < W; k++) {
-                const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+            if (fast_x && y > 0 && y + 1 < H) {
+                const float lft = img[i - 1], rgt = img[i + 4];
+                const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
+                const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                    float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                    float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                    float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                    float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                    s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                    float p = s00 + s01; p = p + s10; p = p + s11;
+                    const float lp = p * 0.25f;
+                    if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                }
+            } else {
+                for (int k = 0; k < 4 && x0 + k < W; k++) {
+                    const float lp = laplace_plus_at(img, H, W, y, x0 + k);
+                    if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                }
             }
+            up = cur;
+            cur = dn;
         }
     }
     if (COLLECT) {
@@ -547,8 +562,8 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     const size_t n = (size_t)H * W;
     const SparseWork w = carve_sparse(work, n);
     const unsigned int stamp = (unsigned int)(it % 15) + 1;
-    BBX_REQUIRE(H <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
-    const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), H);
+    BBX_REQUIRE(ceil_div(H, SCAN_ROWS) <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
+    const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
     const int list_blocks = BBX_SM_COUNT * 8;
     if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {

@@ -10,12 +10,16 @@
 // row ly and the 8 top channels at the mirrored row.  Those 32 pixels are exactly each other's
 // sources, so every pixel of the frame is read once and written once (HBM-bound: 4+1 B read,
 // 4 B written per pixel; 16 float64 FMAs per pixel).
+#include <stdlib.h>
 #include "bbx_common.cuh"
 
 struct XtalkCoef { double c[16][16]; };   // [source][victim], kernel parameter (constant bank)
 
+// PX = 4 (float4 + 32-bit mask words), 2 or 1 pixels per thread and channel.  Only the pixel
+// values and two 64-bit flag words are kept in registers; the masked source value
+// S = v * (ok ? 1 : 0) is formed on the fly.
 template <int PX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int xsc, XtalkCoef k,
              uint32_t bits_src_bad, uint32_t bit_edge)
 {
@@ -25,47 +29,63 @@ xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int x
          t += (long long)gridDim.x * blockDim.x) {
         const int ly = (int)(t / groups), lx = (int)(t - (long long)ly * groups) * PX;
         float v[16][PX];
-        float S[16][PX];
-        uint32_t vic_ok = 0;                               // bit (c*PX + p)
+        unsigned long long src_ok = 0, vic_ok = 0;           // bit (c * PX + p)
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
             const size_t off = (size_t)row * W + (size_t)(c & 7) * xsc + lx;
-            if (PX == 2) {
+            uint32_t mm = 0;
+            if (PX == 4) {
+                const float4 f = *reinterpret_cast<const float4 *>(img + off);
+                v[c][0] = f.x; v[c][PX > 1 ? 1 : 0] = f.y; v[c][PX > 2 ? 2 : 0] = f.z; v[c][PX > 3 ? 3 : 0] = f.w;
+                if (mask) mm = *reinterpret_cast<const uint32_t *>(mask + off);
+            } else if (PX == 2) {
                 const float2 f = *reinterpret_cast<const float2 *>(img + off);
-                v[c][0] = f.x; v[c][PX - 1] = f.y;
+                v[c][0] = f.x; v[c][PX > 1 ? 1 : 0] = f.y;
+                if (mask) mm = *reinterpret_cast<const uint16_t *>(mask + off);
             } else {
                 v[c][0] = img[off];
+                if (mask) mm = mask[off];
             }
 #pragma unroll
             for (int p = 0; p < PX; p++) {
-                const uint32_t m = mask ? mask[off + p] : 0u;
-                const bool src_ok = (v[c][p] > 0.0f) && !(m & bits_src_bad);
-                S[c][p] = v[c][p] * (src_ok ? 1.0f : 0.0f);
-                if (!(m & bit_edge)) vic_ok |= 1u << (c * PX + p);
+                const uint32_t m = (mm >> (8 * p)) & 0xffu;
+                if ((v[c][p] > 0.0f) && !(m & bits_src_bad)) src_ok |= 1ull << (c * PX + p);
+                if (!(m & bit_edge)) vic_ok |= 1ull << (c * PX + p);
+            }
+        }
+        // pixel by pixel: the 16 masked sources as float64, then the 16 victims; the outputs
+        // overwrite v[.][p] once its sources have been captured (keeps the register count low)
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            double S[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const float sf = v[c][p] * (((src_ok >> (c * PX + p)) & 1ull) ? 1.0f : 0.0f);
+                S[c] = (double)sf;
+            }
+#pragma unroll
+            for (int vch = 0; vch < 16; vch++) {
+                const int same0 = (vch < 8) ? 0 : 8, other0 = 8 - same0;
+                // same-half sources first (quadrant q=0 / q=3), then the mirrored half
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[same0 + s][vch], a);
+#pragma unroll
+                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[other0 + s][vch], b);
+                double corr = 0.0 + a;
+                corr = corr + b;
+                corr = corr * (((vic_ok >> (vch * PX + p)) & 1ull) ? 1.0 : 0.0);
+                v[vch][p] = (float)((double)v[vch][p] - corr);
             }
         }
 #pragma unroll
         for (int vch = 0; vch < 16; vch++) {
-            float outv[PX];
-#pragma unroll
-            for (int p = 0; p < PX; p++) {
-                // same-half sources first (quadrant q=0 / q=3), then the mirrored half
-                const int same0 = (vch < 8) ? 0 : 8, other0 = 8 - same0;
-                double a = 0.0, b = 0.0;
-#pragma unroll
-                for (int s = 0; s < 8; s++) a = fma((double)S[same0 + s][p], k.c[same0 + s][vch], a);
-#pragma unroll
-                for (int s = 0; s < 8; s++) b = fma((double)S[other0 + s][p], k.c[other0 + s][vch], b);
-                double corr = 0.0 + a;
-                corr = corr + b;
-                corr = corr * (((vic_ok >> (vch * PX + p)) & 1u) ? 1.0 : 0.0);
-                outv[p] = (float)((double)v[vch][p] - corr);
-            }
             const int row = (vch < 8) ? ly : (ysc + (ysc - 1 - ly));
             const size_t off = (size_t)row * W + (size_t)(vch & 7) * xsc + lx;
-            if (PX == 2) *reinterpret_cast<float2 *>(img + off) = make_float2(outv[0], outv[PX - 1]);
-            else img[off] = outv[0];
+            if (PX == 4) *reinterpret_cast<float4 *>(img + off) = make_float4(v[vch][0], v[vch][PX > 1 ? 1 : 0], v[vch][PX > 2 ? 2 : 0], v[vch][PX > 3 ? 3 : 0]);
+            else if (PX == 2) *reinterpret_cast<float2 *>(img + off) = make_float2(v[vch][0], v[vch][PX > 1 ? 1 : 0]);
+            else img[off] = v[vch][0];
         }
     }
 }
@@ -79,12 +99,18 @@ extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysiz
     for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[s][v] = coeffs_h[s * 16 + v];
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
-    const bool px2 = (xsize_chan % 2 == 0) && (W % 2 == 0) && ((uintptr_t)img % 8) == 0;
-    const long long total = (long long)ysize_chan * (xsize_chan / (px2 ? 2 : 1));
-    long long want = (total + 255) / 256;
-    const int blocks = (int)(want < BBX_SM_COUNT * 8 ? want : BBX_SM_COUNT * 8);
-    if (px2) xtalk_kernel<2><<<blocks, 256, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
-    else xtalk_kernel<1><<<blocks, 256, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+    const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
+    const bool px2 = (xsize_chan % 2 == 0) && ((uintptr_t)img % 8) == 0 && ((uintptr_t)mask % 2) == 0;
+    // measured on B200 (10560^2, tools/xt_bench.py): 2 px/thread 0.395 ms, 4 px/thread 0.435 ms
+    // (255 registers), 1 px/thread 0.76 ms
+    int px = px2 ? 2 : 1;
+    if (const char *e = getenv("BBX_XTALK_PX")) { const int want_px = atoi(e); if (want_px == 4 && px4) px = 4; if (want_px == 1) px = 1; }
+    const long long total = (long long)ysize_chan * (xsize_chan / px);
+    long long want = (total + 127) / 128;
+    const int blocks = (int)(want < BBX_SM_COUNT * 16 ? want : BBX_SM_COUNT * 16);
+    if (px == 4) xtalk_kernel<4><<<blocks, 128, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+    else if (px == 2) xtalk_kernel<2><<<blocks, 128, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+    else xtalk_kernel<1><<<blocks, 128, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
     BBX_CHECK_LAUNCH("xtalk_kernel");
     return 0;
 }
