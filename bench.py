@@ -122,7 +122,7 @@ def workload_config(args):
                         .format(TEL, args.batch, NITER),
             'frames_per_gpu_per_step': args.batch, 'lacosmic_niter': NITER,
             'l2': 'inputs larger than L2 (254 MB raw + 1 GB masters per frame vs 126 MB L2)',
-            'parallelism': 'frame k -> GPU k mod N, no collective'}
+            'parallelism': 'frame k -> GPU k mod N, no collective; 2 frames in flight per GPU on 2 streams'}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -178,7 +178,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from blackbox_b200 import reduce as R, set_bb, synth
-    from blackbox_b200.pipeline import FramePipeline
+    from blackbox_b200.pipeline import BatchReducer, FramePipeline
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -201,10 +201,12 @@ def run_gpu(args, rank, world, local_rank):
             base = base + torch.randint(-3, 4, base.shape, device=dev, generator=gen, dtype=torch.int32)
         raws.append(base.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
     del base
-    pipe = FramePipeline(TEL, raws[0].shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
+    batch = BatchReducer(TEL, raws[0].shape, depth=2, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
                          niter=NITER)
-    out_img = torch.empty(red_shape, dtype=torch.float32, device=dev)
-    out_mask = torch.empty(red_shape, dtype=torch.uint8, device=dev)
+    pipe = batch.pipes[0]
+    out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+    out_img, out_mask = out_imgs[0], out_masks[0]
 
     def barrier():
         if world > 1:
@@ -215,9 +217,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def step():
         redo = 0
-        for k in range(B):
-            pipe.enqueue(raws[k], out_img, out_mask)
-            res = pipe.finish(fill_header=False)
+        for res in batch.run(raws, out_imgs, out_masks):
             redo += res.redo
             spline_cols[0] += res.spline_columns
         return redo

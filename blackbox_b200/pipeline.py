@@ -172,3 +172,38 @@ def shard_frames(nframes, rank, world_size):
     """Indices of the frames rank ``rank`` reduces: frame k -> GPU k mod world_size
     (frames are independent: the reference runs one process per frame, blackbox.py:378)."""
     return list(range(rank, nframes, world_size))
+
+
+class BatchReducer:
+    """Reduce a batch of raw frames with ``depth`` FramePipelines ping-ponging on their own CUDA
+    streams: while the host waits for the overscan flags of one frame (the single round trip of
+    the chain) and enqueues its remaining kernels, the GPU is busy with the other frame, so the
+    device never idles on the host.  Results are identical to running the frames one by one."""
+
+    def __init__(self, tel, raw_shape, depth=2, **pipeline_kwargs):
+        self.depth = int(depth)
+        self.pipes = [FramePipeline(tel, raw_shape, **pipeline_kwargs) for _ in range(self.depth)]
+        self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
+
+    def run(self, raws, out_imgs, out_masks, fill_header=False):
+        """raws: CUDA tensors; out_imgs / out_masks: at least ``depth`` output tensors, frame k
+        is written to index k % len(out_imgs).  Returns the FrameResults in order (a frame's
+        output buffers are only valid until they are reused)."""
+        n, d = len(raws), self.depth
+        nout = len(out_imgs)
+        if nout < d or len(out_masks) != nout:
+            raise ValueError('need at least depth={} output buffers'.format(d))
+        results = [None] * n
+        caller = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(caller)
+        for k in range(n + d):
+            j = k % d
+            with torch.cuda.stream(self.streams[j]):
+                if k >= d:
+                    results[k - d] = self.pipes[j].finish(fill_header=fill_header)
+                if k < n:
+                    self.pipes[j].enqueue(raws[k], out_imgs[k % nout], out_masks[k % nout])
+        for s in self.streams:
+            caller.wait_stream(s)
+        return results

@@ -75,3 +75,30 @@ def test_chain_spline_redo(small_bb):
     img = res.img.cpu().numpy()
     assert float_class_ok(img, data_o, scale=hdr_o['BIASMEAN']).mean() > 0.99999
     assert np.mean(img == data_o) > 0.999
+
+
+def test_batch_reducer_equals_single_pipeline(small_bb):
+    """Two frames in flight on two streams give the bits of the one-by-one pipeline."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from blackbox_b200.pipeline import BatchReducer, FramePipeline
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw0, mbias, mflat, bpm, coeffs = _inputs(tel, 4200, ysc)
+    raws = [raw0] + [_inputs(tel, 4200 + i, ysc)[0] for i in (1, 2, 3, 4)]
+    kw = dict(mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=2)
+    single = FramePipeline(tel, raw0.shape, **kw)
+    want = []
+    for r in raws:
+        res = single.reduce(r)
+        want.append((res.img.cpu().numpy().copy(), res.mask.cpu().numpy().copy(), res.header['NCOSMICS']))
+    batch = BatchReducer(tel, raw0.shape, depth=2, **kw)
+    raws_t = [bbr._to_dev(r) for r in raws]
+    imgs = [torch.empty((2 * ysc, 10560), dtype=torch.float32, device='cuda') for _ in raws]
+    masks = [torch.empty((2 * ysc, 10560), dtype=torch.uint8, device='cuda') for _ in raws]
+    results = batch.run(raws_t, imgs, masks, fill_header=True)
+    torch.cuda.synchronize()
+    for k, (img, mask, nc) in enumerate(want):
+        assert np.array_equal(imgs[k].cpu().numpy(), img, equal_nan=True), k
+        assert np.array_equal(masks[k].cpu().numpy(), mask), k
+        assert results[k].header['NCOSMICS'] == nc
