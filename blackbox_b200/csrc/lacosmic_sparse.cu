@@ -172,52 +172,68 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     const bool mvec_ok = inmask && (W % 4 == 0) && (((uintptr_t)inmask & 3) == 0);
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const int ya = blockIdx.y * SCAN_ROWS, yb = min(ya + SCAN_ROWS, H);
-    if (x0 < W) {
-        const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
+    const bool in_x = x0 < W;
+    const int lane = threadIdx.x & 31;
+    {
+        const bool fast_x = in_x && vec_ok && x0 > 0 && x0 + 4 < W;
         float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
         if (fast_x) {
             if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
             cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
         }
-        for (int y = ya; y < yb; y++) {
+        for (int y = ya; y < yb; y++) {                       // uniform trip count in the block
             const size_t i = (size_t)y * W + x0;
             if (fast_x && y + 1 < H) dn = *reinterpret_cast<const float4 *>(img + i + W);
             if (COLLECT) {
                 unsigned int mm = 0;
-                const bool mv = mvec_ok && x0 + 4 <= W;
+                const bool mv = in_x && mvec_ok && x0 + 4 <= W;
                 if (mv) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
                 const float cv4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    if (x0 + k >= W) break;
-                    const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
-                    if (masked) continue;
-                    const float v = fast_x ? cv4[k] : img[i + k];
-                    n_valid++;
-                    if (v < bra) n_below++;
-                    else if (v <= brb) s_buf[atomicAdd(&s_cnt, 1u)] = v;
+                    bool take = false;
+                    float v = 0.f;
+                    if (in_x && x0 + k < W) {
+                        const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
+                        if (!masked) {
+                            v = fast_x ? cv4[k] : img[i + k];
+                            n_valid++;
+                            if (v < bra) n_below++;
+                            else take = v <= brb;
+                        }
+                    }
+                    // warp-aggregated append to the block's staging buffer
+                    const unsigned int ballot = __ballot_sync(0xffffffffu, take);
+                    if (ballot) {
+                        unsigned int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_cnt, (unsigned int)__popc(ballot));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (take) s_buf[base + __popc(ballot & ((1u << lane) - 1u))] = v;
+                    }
                 }
             }
-            if (fast_x && y > 0 && y + 1 < H) {
-                const float lft = img[i - 1], rgt = img[i + 4];
-                const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
-                const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
+            if (in_x) {
+                if (fast_x && y > 0 && y + 1 < H) {
+                    const float lft = img[i - 1], rgt = img[i + 4];
+                    const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
+                    const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
-                    float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
-                    float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
-                    float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
-                    float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                    s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
-                    float p = s00 + s01; p = p + s10; p = p + s11;
-                    const float lp = p * 0.25f;
-                    if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
-                }
-            } else {
-                for (int k = 0; k < 4 && x0 + k < W; k++) {
-                    const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                    if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                    for (int k = 0; k < 4; k++) {
+                        const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                        float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                        float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                        float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                        float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                        s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                        float p = s00 + s01; p = p + s10; p = p + s11;
+                        const float lp = p * 0.25f;
+                        if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                    }
+                } else {
+                    for (int k = 0; k < 4 && x0 + k < W; k++) {
+                        const float lp = laplace_plus_at(img, H, W, y, x0 + k);
+                        if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
+                    }
                 }
             }
             up = cur;
@@ -319,12 +335,21 @@ sp_lsel_hist_kernel(SparseWork w)
     __shared__ unsigned int h[SEL_BINS];
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const unsigned int n = w.bg->n_list, prefix = st->prefix;
-    for (unsigned int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const unsigned int key = f32_key(w.bglist[p]);
-        if (PASS == 0) atomicAdd(&h[key >> 21], 1u);
-        else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&h[(key >> 10) & 0x7ffu], 1u); }
-        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&h[key & 0x3ffu], 1u); }
+    const unsigned int n = min(w.bg->n_list, w.capBG), prefix = st->prefix;
+    const unsigned int nround = (n + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+    for (unsigned int it = 0; it < nround; it++) {            // uniform trip count: full-warp match
+        const unsigned int p = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        int bin = -1;
+        if (p < n) {
+            const unsigned int key = f32_key(w.bglist[p]);
+            if (PASS == 0) bin = (int)(key >> 21);
+            else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) bin = (int)((key >> 10) & 0x7ffu); }
+            else { if ((key >> 10) == (prefix >> 10)) bin = (int)(key & 0x3ffu); }
+        }
+        // the collected values sit in a narrow interval, so a warp usually hits one or two
+        // bins: one shared-memory atomic per distinct bin and warp
+        const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (threadIdx.x & 31) == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned int)__popc(peers));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
