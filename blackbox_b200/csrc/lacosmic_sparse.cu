@@ -20,40 +20,40 @@
 //   grow2  (C1 x 9)  warp per neighbour: s' > sigcliplow & good -> c2: count, crmask, CR list
 //   clean  (CR list) lower median of the unflagged 5x5 neighbours
 //
-// The reference's background level (lower median of all unmasked pixels of the input image,
-// used for CR pixels without any usable neighbour) is found without extra dense passes: a
-// strided sample of <= 2^18 pixels brackets the median rank (+-5 sigma of the sampling error),
-// the first iteration's scan counts the pixels below the bracket and collects those inside it,
-// and a radix select over that short list returns the exact order statistic.  If the bracket
-// misses (or a work list overflows) a status bit is raised and the caller repeats the frame
-// with the dense implementation (LAC_STATUS_NEED_BG / LAC_STATUS_OVERFLOW).
+// Iterations after the first do not rescan the image: L+ of a pixel changes only if the pixel or
+// one of its 4 neighbours was rewritten by the cleaning step, so the next list A is a subset of
+// (previous list A) u (cross neighbourhood of the cosmic-ray list) -- re-evaluated sparsely.
+//
+// The reference's background level (lower median of all unmasked pixels of the INPUT image,
+// used for CR pixels without any usable neighbour) is only computed when such a pixel turns up
+// (rare): the cleaning kernel raises a flag, and a cooperative kernel that is a no-op otherwise
+// puts the original values of the cosmic-ray pixels back (they are saved when a pixel enters the
+// CR list), runs an exact radix select over the unmasked pixels, restores the cleaned values
+// and patches the pixels concerned -- all on the device, no host round trip.  If a work list
+// overflows a status bit is raised and the caller repeats the frame with the dense
+// implementation (LAC_STATUS_OVERFLOW).
+#include <cooperative_groups.h>
 #include "lacosmic_common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define FLAG_C0 1u
 #define FLAG_C1 2u
 #define FLAG_C2 4u
+#define FLAG_A 8u
 
 struct SparseCounters {
-    unsigned int nA, nB, nC0, nC1, nCR;
-    unsigned int pad[3];
-};
-
-#define BG_SAMPLES 16384u
-
-struct BgState {
-    float a, b;                          // bracket of the median, from the sample
-    unsigned int n_list;                 // values collected inside [a, b]
-    unsigned int pad;
-    unsigned long long n_valid, n_below; // unmasked pixels; unmasked pixels < a
+    unsigned int nA[2];                  // list A of the current / previous iteration (ping-pong)
+    unsigned int nB, nC0, nC1, nCR;
+    unsigned int bg_need, bg_valid;      // background level: asked for by the cleaning / computed
 };
 
 struct SparseWork {
     uint8_t *flags;              // [N] per pixel: (iteration stamp << 4) | FLAG_*
-    unsigned int *listA, *listB, *listC0, *listC1, *listCR;
-    unsigned int capA, capB, capC, capCR, capBG;
+    unsigned int *listA[2], *listB, *listC0, *listC1, *listCR;
+    float *origCR;               // [capCR] input-image value of every CR-list pixel
+    unsigned int capA, capB, capC, capCR;
     SparseCounters *cnt;
-    BgState *bg;
-    float *bglist;               // [capBG]
     SelState *sel;
     float *background;
 };
@@ -68,16 +68,14 @@ static void sparse_caps(size_t n, unsigned int &capA, unsigned int &capB, unsign
     capC = (unsigned int)(n / 32 + 1024);
     capCR = (unsigned int)(n / 16 + 1024);
 }
-static unsigned int sparse_cap_bg(size_t n) { return (unsigned int)(n / 16 + 4096); }
 
 size_t lac_sparse_work_bytes(int H, int W)
 {
     const size_t n = (size_t)H * W;
     unsigned int a, b, c, cr;
     sparse_caps(n, a, b, c, cr);
-    return sp_align(n) + sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + sp_align(4ull * cr) +
-           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(BgState)) +
-           sp_align(4ull * sparse_cap_bg(n)) + sp_align(sizeof(SelState)) + 512;
+    return sp_align(n) + 2 * sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + 2 * sp_align(4ull * cr) +
+           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(SelState)) + 512;
 }
 
 static SparseWork carve_sparse(void *work, size_t n)
@@ -86,27 +84,28 @@ static SparseWork carve_sparse(void *work, size_t n)
     sparse_caps(n, w.capA, w.capB, w.capC, w.capCR);
     uint8_t *p = (uint8_t *)work;
     w.flags = p; p += sp_align(n);
-    w.listA = (unsigned int *)p; p += sp_align(4ull * w.capA);
+    w.listA[0] = (unsigned int *)p; p += sp_align(4ull * w.capA);
+    w.listA[1] = (unsigned int *)p; p += sp_align(4ull * w.capA);
     w.listB = (unsigned int *)p; p += sp_align(4ull * w.capB);
     w.listC0 = (unsigned int *)p; p += sp_align(4ull * w.capC);
     w.listC1 = (unsigned int *)p; p += sp_align(4ull * w.capC);
     w.listCR = (unsigned int *)p; p += sp_align(4ull * w.capCR);
+    w.origCR = (float *)p; p += sp_align(4ull * w.capCR);
     w.cnt = (SparseCounters *)p; p += sp_align(sizeof(SparseCounters));
-    w.bg = (BgState *)p; p += sp_align(sizeof(BgState));
-    w.capBG = sparse_cap_bg(n);
-    w.bglist = (float *)p; p += sp_align(4ull * w.capBG);
     w.sel = (SelState *)p; p += sp_align(sizeof(SelState));
     w.background = (float *)p;
     return w;
 }
 
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void list_push(unsigned int *list, unsigned int *count, unsigned int cap,
-                                          unsigned int value, long long *info)
+// appends `value`; returns the slot (>= cap: the list overflowed and the entry was dropped)
+__device__ __forceinline__ unsigned int list_push(unsigned int *list, unsigned int *count, unsigned int cap,
+                                                  unsigned int value, long long *info)
 {
     const unsigned int slot = atomicAdd(count, 1u);
     if (slot < cap) list[slot] = value;
     else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_OVERFLOW);
+    return slot;
 }
 
 // set `bit` in the flag byte of pixel p for iteration stamp `stamp`; returns true if the bit
@@ -134,253 +133,114 @@ __device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsi
     return n < cap ? n : cap;
 }
 
-// --------------------------------------------------------------------------------------------
-// dense scan: 4 pixels per thread, 128-bit loads of the three rows
-// --------------------------------------------------------------------------------------------
-// COLLECT (first iteration only): also count the unmasked pixels and those below the median
-// bracket, and gather the values inside the bracket (one block-aggregated append per block).
-// A block owns a 512-pixel wide, SCAN_ROWS tall strip: 128 threads x 4 pixels walk down the
-// rows keeping the previous / current / next row in registers, so every pixel is loaded once
-// per strip (plus one halo row at either end).
-// The list-A test `L+ / den_min > sigclip` is replaced by the division-free superset
-// `L+ > thr_lo`, thr_lo = sigclip * den_min * (1 - 2^-20): pixels it lets through in excess are
-// rejected by the exact tests of the candidate kernels.
-#define SCAN_THREADS 128
-#define SCAN_ROWS 16
-template <bool COLLECT>
-__global__ void __launch_bounds__(SCAN_THREADS)
-sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
-               SparseWork w, long long *info)
+// list-A threshold: `L+ / den_min > sigclip` (den_min = 2 sqrt(1e-5 + rn^2), the smallest
+// possible 2*noise) is replaced by the division-free superset `L+ > thr_lo`,
+// thr_lo = sigclip * den_min * (1 - 2^-20): pixels it lets through in excess are rejected by
+// the exact tests of the candidate kernels.
+__device__ __forceinline__ float lac_thr_lo(const LacParams &prm)
 {
-    if (!info[INFO_ACTIVE]) return;
-    __shared__ float s_buf[COLLECT ? 4 * SCAN_THREADS * SCAN_ROWS : 1];
-    __shared__ unsigned int s_cnt, s_base;
-    __shared__ unsigned long long s_red[33];
-    unsigned int n_valid = 0, n_below = 0;
-    float bra = 0.f, brb = 0.f;
-    if (COLLECT) {
-        bra = w.bg->a; brb = w.bg->b;
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-    }
-    // smallest possible noise: med5 floored at 1e-5
     float nmin = 0.00001f + lac_rn2(prm);
     nmin = sqrtf(nmin);
     const float den_min = 2.0f * nmin;
-    const float thr_lo = (float)((double)prm.sigclip * (double)den_min * (1.0 - 9.5367431640625e-07));
+    return (float)((double)prm.sigclip * (double)den_min * (1.0 - 9.5367431640625e-07));
+}
+
+// --------------------------------------------------------------------------------------------
+// dense scan (first iteration): 4 pixels per thread, 128-bit loads of the three rows
+// --------------------------------------------------------------------------------------------
+// A block owns a 512-pixel wide, SCAN_ROWS tall strip: 128 threads x 4 pixels walk down the
+// rows keeping the previous / current / next row in registers, so every pixel is loaded once
+// per strip (plus one halo row at either end).
+#define SCAN_THREADS 128
+#define SCAN_ROWS 16
+__global__ void __launch_bounds__(SCAN_THREADS)
+sp_scan_kernel(const float *__restrict__ img, int H, int W, LacParams prm, SparseWork w, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const float thr_lo = lac_thr_lo(prm);
     const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    const bool mvec_ok = inmask && (W % 4 == 0) && (((uintptr_t)inmask & 3) == 0);
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const int ya = blockIdx.y * SCAN_ROWS, yb = min(ya + SCAN_ROWS, H);
-    const bool in_x = x0 < W;
-    const int lane = threadIdx.x & 31;
-    {
-        const bool fast_x = in_x && vec_ok && x0 > 0 && x0 + 4 < W;
-        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
-        if (fast_x) {
-            if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
-            cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
-        }
-        for (int y = ya; y < yb; y++) {                       // uniform trip count in the block
-            const size_t i = (size_t)y * W + x0;
-            if (fast_x && y + 1 < H) dn = *reinterpret_cast<const float4 *>(img + i + W);
-            if (COLLECT) {
-                unsigned int mm = 0;
-                const bool mv = in_x && mvec_ok && x0 + 4 <= W;
-                if (mv) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
-                const float cv4[4] = {cur.x, cur.y, cur.z, cur.w};
+    if (x0 >= W) return;
+    const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
+    float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
+    if (fast_x) {
+        if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
+        cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
+    }
+    for (int y = ya; y < yb; y++) {
+        const size_t i = (size_t)y * W + x0;
+        if (fast_x && y + 1 < H) dn = *reinterpret_cast<const float4 *>(img + i + W);
+        if (fast_x && y > 0 && y + 1 < H) {
+            const float lft = img[i - 1], rgt = img[i + 4];
+            const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
+            const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    bool take = false;
-                    float v = 0.f;
-                    if (in_x && x0 + k < W) {
-                        const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
-                        if (!masked) {
-                            v = fast_x ? cv4[k] : img[i + k];
-                            n_valid++;
-                            if (v < bra) n_below++;
-                            else take = v <= brb;
-                        }
-                    }
-                    // warp-aggregated append to the block's staging buffer
-                    const unsigned int ballot = __ballot_sync(0xffffffffu, take);
-                    if (ballot) {
-                        unsigned int base = 0;
-                        if (lane == 0) base = atomicAdd(&s_cnt, (unsigned int)__popc(ballot));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (take) s_buf[base + __popc(ballot & ((1u << lane) - 1u))] = v;
-                    }
-                }
+            for (int k = 0; k < 4; k++) {
+                const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                float p = s00 + s01; p = p + s10; p = p + s11;
+                const float lp = p * 0.25f;
+                if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
             }
-            if (in_x) {
-                if (fast_x && y > 0 && y + 1 < H) {
-                    const float lft = img[i - 1], rgt = img[i + 4];
-                    const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
-                    const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
-                        float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
-                        float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
-                        float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
-                        float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                        s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
-                        float p = s00 + s01; p = p + s10; p = p + s11;
-                        const float lp = p * 0.25f;
-                        if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
-                    }
-                } else {
-                    for (int k = 0; k < 4 && x0 + k < W; k++) {
-                        const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                        if (lp > thr_lo) list_push(w.listA, &w.cnt->nA, w.capA, (unsigned int)(i + k), info);
-                    }
-                }
+        } else {
+            for (int k = 0; k < 4 && x0 + k < W; k++) {
+                const float lp = laplace_plus_at(img, H, W, y, x0 + k);
+                if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
             }
-            up = cur;
-            cur = dn;
         }
-    }
-    if (COLLECT) {
-        __syncthreads();
-        const unsigned int c = s_cnt;
-        if (c) {
-            if (threadIdx.x == 0) s_base = atomicAdd(&w.bg->n_list, c);
-            __syncthreads();
-            const unsigned int b0 = s_base;
-            for (unsigned int j = threadIdx.x; j < c; j += blockDim.x)
-                if (b0 + j < w.capBG) w.bglist[b0 + j] = s_buf[j];
-        }
-        const unsigned long long tv = block_sum((unsigned long long)n_valid, s_red);
-        const unsigned long long tb = block_sum((unsigned long long)n_below, s_red);
-        if (threadIdx.x == 0) {
-            if (tv) atomicAdd(&w.bg->n_valid, tv);
-            if (tb) atomicAdd(&w.bg->n_below, tb);
-        }
+        up = cur;
+        cur = dn;
     }
 }
 
-// ---- background level ----------------------------------------------------------------------
-// One block: gather a strided sample of the unmasked pixels into shared memory, bitonic-sort it
-// and bracket the median rank by +-(2.5 sqrt(ns) + 8) sample ranks (5 sigma of the binomial
-// sampling error of the median's rank).
-__global__ void __launch_bounds__(1024)
-sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
+// iterations >= 1: list A from the previous list A and the cross neighbourhood of every pixel
+// the cleaning step has rewritten (the cumulative CR list); FLAG_A removes duplicates
+__global__ void __launch_bounds__(128)
+sp_rescan_kernel(const float *__restrict__ img, int H, int W, LacParams prm, SparseWork w, int it, unsigned int stamp,
+                 long long *info)
 {
-    extern __shared__ float smp[];                    // BG_SAMPLES floats
-    __shared__ unsigned int s_ns;
-    if (threadIdx.x == 0) s_ns = 0;
-    for (unsigned int j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) smp[j] = INFINITY;
-    __syncthreads();
-    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
-    for (size_t j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) {
-        const size_t i = j * stride;
-        if (i >= n) break;
-        if (inmask && inmask[i]) continue;
-        const float v = img[i];
-        if (v != v) continue;                         // NaN would break the sort order
-        smp[atomicAdd(&s_ns, 1u)] = v;
-    }
-    __syncthreads();
-    const unsigned int ns = s_ns;
-    for (unsigned int k = 2; k <= BG_SAMPLES; k <<= 1)
-        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned int i = threadIdx.x; i < BG_SAMPLES; i += blockDim.x) {
-                const unsigned int l = i ^ j;
-                if (l > i) {
-                    const float x = smp[i], y = smp[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { smp[i] = y; smp[l] = x; }
-                }
-            }
-            __syncthreads();
+    if (!info[INFO_ACTIVE]) return;
+    const int cur = it & 1, prev = cur ^ 1;
+    const unsigned int nprev = list_len(&w.cnt->nA[prev], w.capA), ncr = list_len(&w.cnt->nCR, w.capCR);
+    const float thr_lo = lac_thr_lo(prm);
+    const unsigned long long total = (unsigned long long)nprev + 5ull * ncr;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        int y, x;
+        if (t < nprev) {
+            const unsigned int q = w.listA[prev][t];
+            y = (int)(q / (unsigned int)W); x = (int)(q - (unsigned int)y * (unsigned int)W);
+        } else {
+            const unsigned long long u = t - nprev;
+            const unsigned int p = w.listCR[u / 5];
+            const int k = (int)(u % 5);
+            y = (int)(p / (unsigned int)W); x = (int)(p - (unsigned int)y * (unsigned int)W);
+            if (k == 1) x--; else if (k == 2) x++; else if (k == 3) y--; else if (k == 4) y++;
+            if (x < 0 || x >= W || y < 0 || y >= H) continue;
         }
-    if (threadIdx.x == 0) {
-        float a = -INFINITY, b = INFINITY;
-        if (ns > 0) {
-            const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
-            if (mid > d) a = smp[mid - d];
-            if (mid + d < ns - 1) b = smp[mid + d];
-        }
-        w.bg->a = a; w.bg->b = b;
-        w.bg->n_list = 0; w.bg->n_valid = 0; w.bg->n_below = 0;
+        const float lp = laplace_plus_at(img, H, W, y, x);
+        if (!(lp > thr_lo)) continue;
+        const size_t q = (size_t)y * W + x;
+        if (flag_set(w.flags, q, stamp, FLAG_A)) list_push(w.listA[cur], &w.cnt->nA[cur], w.capA, (unsigned int)q, info);
     }
-}
-
-// after the first scan: rank of the median inside the collected list (or failure)
-__global__ void sp_bg_rank_kernel(SparseWork w, long long *info)
-{
-    SelState *st = w.sel;
-    for (int i = threadIdx.x; i < 3 * SEL_BINS; i += blockDim.x) (&st->hist[0][0])[i] = 0;
-    if (threadIdx.x != 0) return;
-    st->prefix = 0;
-    const unsigned long long nv = w.bg->n_valid, nb = w.bg->n_below;
-    const unsigned int nl = w.bg->n_list;
-    if (nv == 0) { *w.background = 0.0f; st->k = ~0ull; return; }
-    const unsigned long long k = (nv - 1) / 2;
-    if (nl > w.capBG || k < nb || k >= nb + nl) {
-        atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
-        *w.background = 0.0f;
-        st->k = ~0ull;
-        return;
-    }
-    st->k = k - nb;
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(512)
-sp_lsel_hist_kernel(SparseWork w)
-{
-    SelState *st = w.sel;
-    if (st->k == ~0ull) return;
-    __shared__ unsigned int h[SEL_BINS];
-    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    const unsigned int n = min(w.bg->n_list, w.capBG), prefix = st->prefix;
-    const unsigned int nround = (n + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
-    for (unsigned int it = 0; it < nround; it++) {            // uniform trip count: full-warp match
-        const unsigned int p = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        int bin = -1;
-        if (p < n) {
-            const unsigned int key = f32_key(w.bglist[p]);
-            if (PASS == 0) bin = (int)(key >> 21);
-            else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) bin = (int)((key >> 10) & 0x7ffu); }
-            else { if ((key >> 10) == (prefix >> 10)) bin = (int)(key & 0x3ffu); }
-        }
-        // the collected values sit in a narrow interval, so a warp usually hits one or two
-        // bins: one shared-memory atomic per distinct bin and warp
-        const unsigned int peers = __match_any_sync(0xffffffffu, bin);
-        if (bin >= 0 && (threadIdx.x & 31) == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned int)__popc(peers));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
-        if (h[i]) atomicAdd(&st->hist[PASS][i], h[i]);
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(256) sp_lsel_scan_kernel(SparseWork w)
-{
-    SelState *st = w.sel;
-    const unsigned long long k = st->k;
-    if (k == ~0ull) return;
-    unsigned long long below;
-    const int b = select_find_bin(st->hist[PASS], (PASS == 2) ? 1024 : SEL_BINS, k, below);
-    if (threadIdx.x != 0) return;
-    st->k = k - below;
-    if (PASS == 0) st->prefix = (unsigned int)b << 21;
-    else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
-    else { st->prefix |= (unsigned int)b; *w.background = key_f32(st->prefix); }
 }
 
 // list A -> list B: unmasked pixels whose true Laplacian S/N exceeds sigclip
 __global__ void __launch_bounds__(128)
 sp_cand1_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
-                SparseWork w, long long *info)
+                SparseWork w, int it, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
-    const unsigned int n = list_len(&w.cnt->nA, w.capA);
+    const unsigned int n = list_len(&w.cnt->nA[it & 1], w.capA);
+    const unsigned int *__restrict__ listA = w.listA[it & 1];
     const float rn2 = lac_rn2(prm);
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const unsigned int p = w.listA[k];
+        const unsigned int p = listA[k];
         if (inmask && inmask[p]) continue;
         const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
         // s' = s - med5(s) is 0 in the 2-pixel frame (the median filter copies its input there)
@@ -509,7 +369,10 @@ sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
                 atomicAdd((unsigned long long *)&info[INFO_NCR + iter], 1ull);
                 if (crmask[q] == 0) {
                     crmask[q] = 1;
-                    list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
+                    // a pixel that was never flagged has never been cleaned: img[q] is still the
+                    // input value (needed if the background level has to be computed later)
+                    const unsigned int slot = list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
+                    if (slot < w.capCR) w.origCR[slot] = img[q];
                 }
             }
         }
@@ -519,7 +382,10 @@ sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
 __global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt)
 {
     for (int i = threadIdx.x; i < n; i += blockDim.x) info[i] = (i == INFO_ACTIVE) ? 1 : 0;
-    if (threadIdx.x == 0) { cnt->nA = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0; }
+    if (threadIdx.x == 0) {
+        cnt->nA[0] = cnt->nA[1] = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0;
+        cnt->bg_need = cnt->bg_valid = 0;
+    }
 }
 
 // after grow2: stop flag for the iterations that follow, reset of the per-iteration lists
@@ -528,7 +394,8 @@ __global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt
     if (!info[INFO_ACTIVE]) return;
     info[INFO_ITERS] = iter + 1;
     if (info[INFO_NCR + iter] == 0) info[INFO_ACTIVE] = 0;
-    cnt->nA = cnt->nB = cnt->nC0 = cnt->nC1 = 0;
+    cnt->nA[(iter + 1) & 1] = 0;           // destination of the next iteration's rescan
+    cnt->nB = cnt->nC0 = cnt->nC1 = 0;
 }
 
 // medmask cleaning of every pixel flagged so far (cumulative CR list)
@@ -551,7 +418,8 @@ sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *_
                 if (!bad) v[m++] = img[j];
             }
         if (m == 0) {                      // no usable neighbour: the global background level
-            img[p] = *w.background;
+            if (w.cnt->bg_valid) img[p] = *w.background;
+            else w.cnt->bg_need = 1;       // sp_bg_resolve_kernel computes it and patches this pixel
             continue;
         }
         for (int a = 1; a < m; a++) {
@@ -565,6 +433,108 @@ sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *_
 }
 
 // --------------------------------------------------------------------------------------------
+// background level on demand (cooperative launch; returns at once unless the cleaning step met
+// a CR pixel without usable neighbours and the level is not known yet)
+// --------------------------------------------------------------------------------------------
+template <int PASS>
+__device__ __forceinline__ void sp_select_hist(const float *__restrict__ img, const uint8_t *__restrict__ inmask,
+                                               size_t n, SelState *st, unsigned int *h)
+{
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const unsigned int prefix = st->prefix;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        if (inmask && inmask[p]) continue;
+        const unsigned int key = f32_key(img[p]);
+        if (PASS == 0) atomicAdd(&h[key >> 21], 1u);
+        else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&h[(key >> 10) & 0x7ffu], 1u); }
+        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&h[key & 0x3ffu], 1u); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&st->hist[PASS][i], h[i]);
+}
+
+// one block, 256 threads: same decisions as select_scan_kernel of the dense path (lacosmic.cu)
+template <int PASS>
+__device__ __forceinline__ void sp_select_scan(SelState *st, float *out, unsigned long long *scr)
+{
+    unsigned long long k = st->k;
+    if (PASS == 0) {
+        unsigned long long mine = 0;
+        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) mine += st->hist[0][i];
+        const unsigned long long total = block_sum(mine, scr);
+        if (total == 0) { if (threadIdx.x == 0) { *out = 0.0f; st->k = ~0ull; } return; }
+        k = (total - 1) / 2;
+    }
+    if (k == ~0ull) return;
+    unsigned long long below;
+    const int b = select_find_bin(st->hist[PASS], (PASS == 2) ? 1024 : SEL_BINS, k, below);
+    if (threadIdx.x != 0) return;
+    st->k = k - below;
+    if (PASS == 0) st->prefix = (unsigned int)b << 21;
+    else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
+    else { st->prefix |= (unsigned int)b; *out = key_f32(st->prefix); }
+}
+
+__global__ void __launch_bounds__(256)
+sp_bg_resolve_kernel(float *img, const uint8_t *__restrict__ inmask, const uint8_t *__restrict__ crmask, int H, int W,
+                     SparseWork w, long long *info)
+{
+    // every block reads the same three words; nobody changes them before the first grid.sync
+    if (!info[INFO_ACTIVE] || !w.cnt->bg_need || w.cnt->bg_valid) return;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned int h[SEL_BINS];
+    __shared__ unsigned long long scr[33];
+    const size_t n = (size_t)H * W;
+    const unsigned int ncr = list_len(&w.cnt->nCR, w.capCR);
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    SelState *st = w.sel;
+    // input values back into the image (the cleaned ones are parked in origCR)
+    for (unsigned int k = gtid; k < ncr; k += gsz) {
+        const unsigned int p = w.listCR[k];
+        const float t = img[p];
+        img[p] = w.origCR[k];
+        w.origCR[k] = t;
+    }
+    for (unsigned int i = gtid; i < 3 * SEL_BINS; i += gsz) (&st->hist[0][0])[i] = 0;
+    if (gtid == 0) { st->k = 0; st->prefix = 0; }
+    grid.sync();
+    sp_select_hist<0>(img, inmask, n, st, h);
+    grid.sync();
+    if (blockIdx.x == 0) sp_select_scan<0>(st, w.background, scr);
+    grid.sync();
+    if (st->k != ~0ull) sp_select_hist<1>(img, inmask, n, st, h);
+    grid.sync();
+    if (blockIdx.x == 0) sp_select_scan<1>(st, w.background, scr);
+    grid.sync();
+    if (st->k != ~0ull) sp_select_hist<2>(img, inmask, n, st, h);
+    grid.sync();
+    if (blockIdx.x == 0) sp_select_scan<2>(st, w.background, scr);
+    grid.sync();
+    // cleaned values back; pixels without usable neighbours (skipped by sp_clean_kernel) get the level
+    const float bgv = *w.background;
+    for (unsigned int k = gtid; k < ncr; k += gsz) {
+        const unsigned int p = w.listCR[k];
+        const float t = img[p];
+        float v = w.origCR[k];
+        w.origCR[k] = t;
+        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
+        if (!(x < 2 || x >= W - 2 || y < 2 || y >= H - 2)) {
+            int m = 0;
+            for (int dy = -2; dy <= 2; dy++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    const size_t j = (size_t)(y + dy) * W + (x + dx);
+                    m += !(crmask[j] || (inmask && inmask[j]));
+                }
+            if (m == 0) v = bgv;
+        }
+        img[p] = v;
+    }
+    if (gtid == 0) w.cnt->bg_valid = 1;
+}
+
+// --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
 static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, int niter,
@@ -575,8 +545,6 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
     BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
     BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));
     sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt);
-    BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * BG_SAMPLES)));
-    sp_bg_sample_kernel<<<1, 1024, 4 * BG_SAMPLES, st>>>(img, inmask, n, w);
     BBX_CHECK_LAUNCH("sparse_begin");
     return 0;
 }
@@ -585,30 +553,32 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
                             int it, void *work, long long *info, cudaStream_t st)
 {
     const size_t n = (size_t)H * W;
-    const SparseWork w = carve_sparse(work, n);
-    const unsigned int stamp = (unsigned int)(it % 15) + 1;
+    SparseWork w = carve_sparse(work, n);
+    unsigned int stamp = (unsigned int)(it % 15) + 1;
     BBX_REQUIRE(ceil_div(H, SCAN_ROWS) <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
     const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
     const int list_blocks = BBX_SM_COUNT * 8;
     if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
-    if (it == 0) {
-        sp_scan_kernel<true><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
-        sp_bg_rank_kernel<<<1, 256, 0, st>>>(w, info);
-        sp_lsel_hist_kernel<0><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<0><<<1, 256, 0, st>>>(w);
-        sp_lsel_hist_kernel<1><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<1><<<1, 256, 0, st>>>(w);
-        sp_lsel_hist_kernel<2><<<BBX_SM_COUNT, 512, 0, st>>>(w);
-        sp_lsel_scan_kernel<2><<<1, 256, 0, st>>>(w);
-    } else {
-        sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
-    }
-    sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, info);
+    if (it == 0) sp_scan_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(img, H, W, prm, w, info);
+    else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);
+    sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, it, info);
     sp_cand2_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
     sp_grow_kernel<1><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_grow_kernel<2><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
     sp_clean_kernel<<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    {
+        static int coop_blocks = 0;
+        if (coop_blocks == 0) {
+            int per_sm = 0;
+            BBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_bg_resolve_kernel, 256, 0));
+            BBX_REQUIRE(per_sm > 0, "lazy LACosmic: background kernel does not fit an SM");
+            coop_blocks = BBX_SM_COUNT * (per_sm < 4 ? per_sm : 4);
+        }
+        const uint8_t *cr_c = crmask;
+        void *args[] = {(void *)&img, (void *)&inmask, (void *)&cr_c, (void *)&H, (void *)&W, (void *)&w, (void *)&info};
+        BBX_CUDA(cudaLaunchCooperativeKernel((const void *)sp_bg_resolve_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
+    }
     BBX_CHECK_LAUNCH("sparse_iteration");
     return 0;
 }

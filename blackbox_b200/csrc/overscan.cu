@@ -355,6 +355,70 @@ hos_satcount_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     if (c2) atomicAdd(&out_cnt[((size_t)ch * 2 + 1) * g.xsize_chan + x], c2);
 }
 
+// uint16 raw frames: for one row the test  f64(f32(f64(f32(n) * gain) - fit[row])) >= thr  is
+// monotone in the raw count n (gain > 0), so it is a comparison of n with a per-row integer
+// threshold.  A block finds the thresholds of its SATC_ROWS rows by bisection (one thread per
+// row, exactly the arithmetic above), then counts with 4 columns per thread: 8-byte loads and
+// two packed 16-bit counters per 32-bit register.
+#define SATC_ROWS 64
+#define SATC_THREADS 128
+__global__ void __launch_bounds__(SATC_THREADS)
+hos_satcount_u16_kernel(const uint16_t *__restrict__ raw, bbx_geom g, ChanF32 gain,
+                        const double *__restrict__ vos_fit, ChanF64 sat_e, int lim1, int lim2,
+                        int32_t *__restrict__ out_cnt)
+{
+    __shared__ unsigned int s_thr[SATC_ROWS];
+    const int ch = blockIdx.z, r = ch / g.nx, c = ch - r * g.nx;
+    const int d0 = blockIdx.y * SATC_ROWS, d1 = min(d0 + SATC_ROWS, min(lim2, g.ysize_chan));
+    const double thr = 0.9 * sat_e.v[ch];
+    const float gn = gain.v[ch];
+    if ((int)threadIdx.x < d1 - d0) {
+        const int d = d0 + threadIdx.x;
+        const int ly = (r == 0) ? (g.ysize_chan - 1 - d) : d;
+        const int rr = (r == 0 ? g.data_y0_bot : g.data_y0_top) + ly;
+        const double fv = vos_fit[(size_t)ch * g.dy + (rr - r * g.dy)];
+        // smallest n in [0, 65536] whose value reaches thr (65536: none; NaN fit: none)
+        unsigned int lo = 0, hi = 65536;
+        while (lo < hi) {
+            const unsigned int mid = (lo + hi) >> 1;
+            float v = (float)mid * gn;
+            v = sub_f64(v, fv);
+            if ((double)v >= thr) hi = mid; else lo = mid + 1;
+        }
+        s_thr[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int x = (blockIdx.x * SATC_THREADS + threadIdx.x) * 4;
+    if (x >= g.xsize_chan) return;
+    unsigned int a1x = 0, a1y = 0, a2x = 0, a2y = 0;          // packed counters: columns (0,1) and (2,3)
+    const uint16_t *col = raw + (size_t)c * g.dx + x;
+#pragma unroll 8
+    for (int d = d0; d < d1; d++) {
+        const int ly = (r == 0) ? (g.ysize_chan - 1 - d) : d;
+        const int rr = (r == 0 ? g.data_y0_bot : g.data_y0_top) + ly;
+        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(col + (size_t)rr * g.W));
+        const unsigned int t = s_thr[d - d0];
+        unsigned int hx, hy;
+        if (t > 65535u) { hx = 0; hy = 0; }
+        else {
+            const unsigned int t2 = t | (t << 16);
+            hx = __vcmpgeu2(u.x, t2) & 0x00010001u;
+            hy = __vcmpgeu2(u.y, t2) & 0x00010001u;
+        }
+        a2x += hx; a2y += hy;
+        if (d < lim1) { a1x += hx; a1y += hy; }
+    }
+    int32_t *o1 = out_cnt + ((size_t)ch * 2 + 0) * g.xsize_chan + x, *o2 = out_cnt + ((size_t)ch * 2 + 1) * g.xsize_chan + x;
+    if (a1x & 0xffffu) atomicAdd(o1 + 0, (int)(a1x & 0xffffu));
+    if (a1x >> 16) atomicAdd(o1 + 1, (int)(a1x >> 16));
+    if (a1y & 0xffffu) atomicAdd(o1 + 2, (int)(a1y & 0xffffu));
+    if (a1y >> 16) atomicAdd(o1 + 3, (int)(a1y >> 16));
+    if (a2x & 0xffffu) atomicAdd(o2 + 0, (int)(a2x & 0xffffu));
+    if (a2x >> 16) atomicAdd(o2 + 1, (int)(a2x >> 16));
+    if (a2y & 0xffffu) atomicAdd(o2 + 2, (int)(a2y & 0xffffu));
+    if (a2y >> 16) atomicAdd(o2 + 3, (int)(a2y >> 16));
+}
+
 // ============================================================================================
 // K2a: horizontal-overscan strip statistics
 // ============================================================================================
@@ -497,20 +561,71 @@ hos_stats_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 #define VSTD_CLUSTER 8
 #define VSTD_THREADS 1024
 #define VSTD_MAXV 8          // strip width <= 256, as in K1
+#define VSTD_LIST_PER_WARP 320
+#define VSTD_CORE_SIGMA 2.25
 
-struct VstdPartial { double s, q; long long n; };
+struct VstdPartial { double s, q, cs, cq; long long n, cn; int ovf, pad; };
+
+// The strip values are x = f32(f64(f32(raw) * gain) - fit[row]) [then - dlevel in the rows of the
+// horizontal overscan], used as float64.  The float32 <-> float64 conversions run on the
+// quarter-rate XU pipe and dominated the first version of this kernel (ncu: XU 74 %), so the
+// exact conversions are done with integer operations instead: widening a float32 is a shift of
+// the exponent/mantissa field, and f64 -> f32 -> f64 is a round-to-nearest-even of the low 29
+// mantissa bits.  Values outside the normal float32 range take the conversion instructions.
+__device__ __forceinline__ double widen_f32(float a)
+{
+    const unsigned int u = __float_as_uint(a);
+    const unsigned int e = (u >> 23) & 0xffu;
+    if (e == 0u || e == 255u) {
+        if ((u << 1) == 0u) return __hiloint2double((int)u, 0);      // signed zero
+        return (double)a;                                              // denormal, inf, nan
+    }
+    const unsigned int hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
+// == (double)(float)d
+__device__ __forceinline__ double round_to_f32(double d)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    const unsigned int e = (unsigned int)(b >> 52) & 0x7ffu;
+    if (e < 897u || e >= 1150u) return (double)(float)d;   // zero, below float32's normal range, overflow, inf, nan
+    const unsigned long long r = b + 0x0fffffffull + ((b >> 29) & 1ull);
+    return __longlong_as_double((long long)(r & ~0x1fffffffull));
+}
+template <typename T> __device__ __forceinline__ float raw_to_f32_alu(T v);
+template <> __device__ __forceinline__ float raw_to_f32_alu<uint16_t>(uint16_t v)
+{
+    return __uint_as_float(0x4b000000u | (unsigned int)v) - 8388608.0f;        // exact for v < 2^23
+}
+template <> __device__ __forceinline__ float raw_to_f32_alu<float>(float v) { return v; }
+
+template <typename T>
+__device__ __forceinline__ bool vstd_value(T rawv, float gn, double fv, bool in_hos, double dlevel, double &xd)
+{
+    const float a = raw_to_f32_alu<T>(rawv) * gn;
+    double d = round_to_f32(widen_f32(a) - fv);
+    if (in_hos) d = round_to_f32(d - dlevel);
+    xd = d;
+    return isfinite(d) && !(fabs(d) <= (double)MASKED_ZERO_TOL);
+}
 
 // Each warp walks rows rank*rows_per_cta + warp, +nwarps, ...; a lane holds the <= 8 strip
 // values of its row in registers, so one pass issues all loads of a row at once.  Every clip
-// iteration is ONE pass accumulating (count, sum, sum of squares) inside the current interval;
-// the population variance follows as q/n - mean^2 (the values are overscan residuals of a few
-// e-, so there is no cancellation to speak of).
+// iteration needs (count, sum, sum of squares) inside the current interval; the population
+// variance follows as q/n - mean^2 (the values are overscan residuals of a few e-, so there is
+// no cancellation to speak of).
+// Only the first two evaluations walk the strip: the second one also parks every value outside
+// the core band mean0 +- 2.25 sd0 (a few per cent) in a per-warp shared-memory list, in a
+// deterministic order, and accumulates the moments of the band.  As long as the later clip
+// bounds contain the band (they are 3 sigma bounds, so they do unless sd0 was inflated by more
+// than a third) an evaluation is "band moments + the listed values inside the bounds".
 template <typename T>
 __global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS)
 vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
                const double *__restrict__ vos_fit, const double *__restrict__ dlevel_arr,
                double *__restrict__ out_std)
 {
+    extern __shared__ double s_list[];                       // [warps][VSTD_LIST_PER_WARP]
     cg::cluster_group cluster = cg::this_cluster();
     const int ch = blockIdx.y, r = ch / g.nx, c = ch - r * g.nx;
     const int rank = (int)cluster.block_rank();
@@ -522,77 +637,138 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     const double dlevel = dlevel_arr[ch];
     const int hos_t0 = ((r == 0) ? g.hos_y0_bot : g.hos_y0_top) - r * g.dy;
     const T *base = raw + (size_t)(r * g.dy) * g.W + (size_t)c * g.dx + g.vos_x0;
+    double *mylist = s_list + (size_t)warp * VSTD_LIST_PER_WARP;
+    int nlist = 0;                                           // entries in this warp's list (warp-uniform)
 
     __shared__ double scr_d[33];
     __shared__ long long scr_l[33];
+    __shared__ int scr_i[33];
     __shared__ VstdPartial part[2];     // double-buffered slot read by the other CTAs
     int phase = 0;
 
-    // one pass over this CTA's rows: moments of the valid values inside [lo, hi]
-    auto pass = [&](double lo, double hi, bool closed_nan_ok, double &S, double &Q, long long &N) {
-        double s = 0.0, q = 0.0;
-        long long n = 0;
+    struct Mom { double S, Q; long long N; };
+    double CS = 0.0, CQ = 0.0;          // band moments of the whole channel
+    long long CN = 0;
+    bool use_list = false;
+    double clo = 0.0, chi = 0.0;
+
+    // publish this CTA's partial sums, combine those of the cluster in rank order
+    auto exchange = [&](double s, double q, long long n, double cs, double cq, long long cn, int ovf,
+                        Mom &m, bool with_core) {
+        s = block_sum(s, scr_d);
+        q = block_sum(q, scr_d);
+        n = block_sum(n, scr_l);
+        if (with_core) {
+            cs = block_sum(cs, scr_d);
+            cq = block_sum(cq, scr_d);
+            cn = block_sum(cn, scr_l);
+            ovf = block_sum(ovf, scr_i);
+        }
+        if (threadIdx.x == 0) {
+            VstdPartial &o = part[phase];
+            o.s = s; o.q = q; o.n = n; o.cs = cs; o.cq = cq; o.cn = cn; o.ovf = ovf;
+        }
+        cluster.sync();
+        m.S = 0.0; m.Q = 0.0; m.N = 0;
+        double tcs = 0.0, tcq = 0.0;
+        long long tcn = 0;
+        int tovf = 0;
+        for (int k = 0; k < VSTD_CLUSTER; k++) {           // fixed order: deterministic
+            const VstdPartial *pp = cluster.map_shared_rank(part, k);
+            m.S += pp[phase].s; m.Q += pp[phase].q; m.N += pp[phase].n;
+            if (with_core) { tcs += pp[phase].cs; tcq += pp[phase].cq; tcn += pp[phase].cn; tovf += pp[phase].ovf; }
+        }
+        if (with_core) { CS = tcs; CQ = tcq; CN = tcn; use_list = (tovf == 0); }
+        phase ^= 1;      // the next publish uses the other slot, so no second sync is needed
+    };
+
+    // one pass over this CTA's rows: moments of the valid values inside [lo, hi]; with BUILD
+    // also the band moments and the list of the values outside the band
+    auto strip_pass = [&](double lo, double hi, bool closed_nan_ok, bool build, Mom &m) {
+        double s = 0.0, q = 0.0, cs = 0.0, cq = 0.0;
+        long long n = 0, cn = 0;
+        int ovf = 0;
         for (int trow = row0 + warp; trow < row1; trow += nwarps) {
             const T *p = base + (size_t)trow * g.W;
             const double fv = fitrow[trow];
             const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
-            float v[VSTD_MAXV];
+            T v[VSTD_MAXV];
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
                 const int j = lane + 32 * k;
-                v[k] = (j < g.vos_w) ? raw_to_f32<T>(p[j]) : 0.f;
+                v[k] = (j < g.vos_w) ? p[j] : (T)0;
             }
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
                 const int j = lane + 32 * k;
-                if (j >= g.vos_w) continue;
-                float x = v[k] * gn;
-                x = sub_f64(x, fv);
-                if (in_hos) x = sub_f64(x, dlevel);
-                if (!vos_valid(x)) continue;
-                const double xd = (double)x;
-                const bool in = closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi);
+                if (32 * k >= g.vos_w) break;                 // warp-uniform
+                double xd = 0.0;
+                const bool valid = (j < g.vos_w) && vstd_value<T>(v[k], gn, fv, in_hos, dlevel, xd);
+                const bool in = valid && (closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi));
                 if (in) { n++; s += xd; q += xd * xd; }
+                if (build) {
+                    const bool core = valid && xd >= clo && xd <= chi;
+                    if (core) { cn++; cs += xd; cq += xd * xd; }
+                    const bool tail = valid && !core;
+                    const unsigned int ballot = __ballot_sync(0xffffffffu, tail);
+                    if (ballot) {
+                        const int pos = nlist + __popc(ballot & ((1u << lane) - 1u));
+                        if (tail) { if (pos < VSTD_LIST_PER_WARP) mylist[pos] = xd; else ovf = 1; }
+                        nlist += __popc(ballot);
+                    }
+                }
             }
         }
-        s = block_sum(s, scr_d);
-        q = block_sum(q, scr_d);
-        n = block_sum(n, scr_l);
-        if (threadIdx.x == 0) { part[phase].s = s; part[phase].q = q; part[phase].n = n; }
-        cluster.sync();
-        S = 0.0; Q = 0.0; N = 0;
-        for (int k = 0; k < VSTD_CLUSTER; k++) {           // fixed order: deterministic
-            const VstdPartial *pp = cluster.map_shared_rank(part, k);
-            S += pp[phase].s; Q += pp[phase].q; N += pp[phase].n;
+        exchange(s, q, n, cs, cq, cn, ovf, m, build);
+    };
+
+    // band moments + the listed values inside [lo, hi]
+    auto list_pass = [&](double lo, double hi, bool closed_nan_ok, Mom &m) {
+        double s = 0.0, q = 0.0;
+        long long n = 0;
+        for (int j = lane; j < nlist; j += 32) {
+            const double xd = mylist[j];
+            const bool in = closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi);
+            if (in) { n++; s += xd; q += xd * xd; }
         }
-        phase ^= 1;      // the next publish uses the other slot, so no second sync is needed
+        exchange(s, q, n, 0.0, 0.0, 0, 0, m, false);
+        m.S += CS; m.Q += CQ; m.N += CN;
+    };
+
+    auto eval = [&](double lo, double hi, bool closed_nan_ok, Mom &m) {
+        if (use_list && lo <= clo && hi >= chi) list_pass(lo, hi, closed_nan_ok, m);
+        else strip_pass(lo, hi, closed_nan_ok, false, m);
     };
 
     double LO = -INFINITY, HI = INFINITY, flo = NAN, fhi = NAN;
-    double S, Q;
-    long long N;
-    pass(LO, HI, false, S, Q, N);
-    for (int it = 0; it < 5 && N > 0; it++) {
-        const double mean = S / (double)N;
-        const double var = fmax(Q / (double)N - mean * mean, 0.0);
+    Mom m;
+    strip_pass(LO, HI, false, false, m);
+    for (int it = 0; it < 5 && m.N > 0; it++) {
+        const double mean = m.S / (double)m.N;
+        const double var = fmax(m.Q / (double)m.N - mean * mean, 0.0);
         const double sd = sqrt(var);
         flo = mean - 3.0 * sd;
         fhi = mean + 3.0 * sd;
         LO = fmax(LO, flo);
         HI = fmin(HI, fhi);
-        double S2, Q2;
-        long long N2;
-        pass(LO, HI, false, S2, Q2, N2);
-        const bool done = (N2 == N);
-        S = S2; Q = Q2; N = N2;
+        Mom m2;
+        if (it == 0) {
+            clo = mean - VSTD_CORE_SIGMA * sd;
+            chi = mean + VSTD_CORE_SIGMA * sd;
+            strip_pass(LO, HI, false, true, m2);
+        } else {
+            eval(LO, HI, false, m2);
+        }
+        const bool done = (m2.N == m.N);
+        m = m2;
         if (done) break;
     }
     // final: population std of everything inside the final bounds (not the intersection)
-    pass(flo, fhi, true, S, Q, N);
+    eval(flo, fhi, true, m);
     double result = NAN;
-    if (N > 0) {
-        const double mean = S / (double)N;
-        result = sqrt(fmax(Q / (double)N - mean * mean, 0.0));
+    if (m.N > 0) {
+        const double mean = m.S / (double)m.N;
+        result = sqrt(fmax(m.Q / (double)m.N - mean * mean, 0.0));
     }
     if (rank == 0 && threadIdx.x == 0) out_std[ch] = result;
     cluster.sync();     // keep every CTA's shared memory alive until all remote reads are done
@@ -740,6 +916,15 @@ extern "C" int bbx_hos_satcount(const void *raw, int raw_type, const bbx_geom *g
     cudaStream_t s = (cudaStream_t)stream;
     BBX_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * BBX_NCHAN * 2 * (size_t)g->xsize_chan, s));
     if (lim2 == 0) return 0;
+    bool gain_pos = true;
+    for (int i = 0; i < BBX_NCHAN; i++) gain_pos = gain_pos && (gn.v[i] > 0.0f) && (gn.v[i] < INFINITY);
+    if (raw_type == BBX_RAW_U16 && gain_pos && g->xsize_chan % 4 == 0 && g->dx % 4 == 0 && g->W % 4 == 0 &&
+        ((uintptr_t)raw & 7) == 0) {
+        dim3 grid4(ceil_div(g->xsize_chan / 4, SATC_THREADS), ceil_div(lim2, SATC_ROWS), BBX_NCHAN);
+        hos_satcount_u16_kernel<<<grid4, SATC_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, vos_fit, se, lim1, lim2, out_cnt);
+        BBX_CHECK_LAUNCH("bbx_hos_satcount");
+        return 0;
+    }
     const int rows_per_block = 64;
     dim3 grid(ceil_div(g->xsize_chan, 256), ceil_div(lim2, rows_per_block), BBX_NCHAN);
     if (raw_type == BBX_RAW_U16)
@@ -784,10 +969,14 @@ extern "C" int bbx_vos_std(const void *raw, int raw_type, const bbx_geom *g, con
     ChanF32 gn; fill_chan_f32(gn, gain_h);
     dim3 grid(VSTD_CLUSTER, BBX_NCHAN);
     cudaStream_t s = (cudaStream_t)stream;
-    if (raw_type == BBX_RAW_U16)
-        vos_std_kernel<uint16_t><<<grid, VSTD_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, vos_fit, dlevel, out_std);
-    else
-        vos_std_kernel<float><<<grid, VSTD_THREADS, 0, s>>>((const float *)raw, *g, gn, vos_fit, dlevel, out_std);
+    const size_t smem = sizeof(double) * (VSTD_THREADS / 32) * VSTD_LIST_PER_WARP;
+    if (raw_type == BBX_RAW_U16) {
+        BBX_CUDA(cudaFuncSetAttribute(vos_std_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vos_std_kernel<uint16_t><<<grid, VSTD_THREADS, smem, s>>>((const uint16_t *)raw, *g, gn, vos_fit, dlevel, out_std);
+    } else {
+        BBX_CUDA(cudaFuncSetAttribute(vos_std_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vos_std_kernel<float><<<grid, VSTD_THREADS, smem, s>>>((const float *)raw, *g, gn, vos_fit, dlevel, out_std);
+    }
     BBX_CHECK_LAUNCH("bbx_vos_std");
     return 0;
 }

@@ -6,10 +6,16 @@
 //   data_v   = f32( f64(data_v) - corr_v * !edge )
 // All sources are the UNCORRECTED pixels (the reference builds the correction cube first).
 //
-// One thread owns a tile position (ly, lx..lx+1) in all 16 channels: the 8 bottom channels at
-// row ly and the 8 top channels at the mirrored row.  Those 32 pixels are exactly each other's
-// sources, so every pixel of the frame is read once and written once (HBM-bound: 4+1 B read,
-// 4 B written per pixel; 16 float64 FMAs per pixel).
+// A tile position (ly, lx) in all 16 channels -- the 8 bottom channels at row ly and the 8 top
+// channels at the mirrored row -- is exactly a set of mutual sources, so every pixel of the
+// frame is read once and written once (4+1 B read, 4 B written per pixel; 16 float64 FMAs per
+// pixel: the FP64 pipe needs ~130 us per 10560^2 frame, HBM ~155 us).
+//
+// xtalk_tile_kernel: a CTA stages 128 tile positions x 16 channels in shared memory with
+// 128-bit coalesced loads, each thread then corrects one position in all 16 channels out of
+// shared memory (16 + 4 live doubles: ~64 registers, 6+ CTAs per SM hide the loads of the other
+// CTAs behind the FP64 work), and the tile goes back with 128-bit stores.
+// xtalk_kernel<PX>: generic fallback (any width / alignment), registers only.
 #include <stdlib.h>
 #include "bbx_common.cuh"
 
@@ -90,6 +96,87 @@ xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int x
     }
 }
 
+#define XT_TILE 128          // tile positions per CTA pass (= threads per CTA)
+
+__global__ void __launch_bounds__(XT_TILE)
+xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int xsc, XtalkCoef k,
+                  uint32_t bits_src_bad, uint32_t bit_edge)
+{
+    __shared__ __align__(16) float tile[16][XT_TILE];
+    __shared__ __align__(16) uint8_t mt[16][XT_TILE];
+    const int gpr = xsc / 4;                                   // float4 groups per channel row
+    const long long ngroups = (long long)ysc * gpr;
+    const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
+    const int g4 = threadIdx.x & 31, c0 = threadIdx.x >> 5;    // load role: group in tile, first channel
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // ---- stage: thread (c0, g4) moves group g4 of channels c0, c0+4, c0+8, c0+12
+        const long long G = t * (XT_TILE / 4) + g4;
+        const bool live = G < ngroups;
+        const int ly = live ? (int)(G / gpr) : 0, lx = live ? (int)(G - (long long)ly * gpr) * 4 : 0;
+        size_t off[4];
+        float4 f[4];
+        uint32_t mm[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = c0 + 4 * i;
+            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+            off[i] = (size_t)row * W + (size_t)(c & 7) * xsc + lx;
+            f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mm[i] = 0;
+            if (live) {
+                f[i] = *reinterpret_cast<const float4 *>(img + off[i]);
+                if (mask) mm[i] = *reinterpret_cast<const uint32_t *>(mask + off[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = c0 + 4 * i;
+            *reinterpret_cast<float4 *>(&tile[c][g4 * 4]) = f[i];
+            *reinterpret_cast<uint32_t *>(&mt[c][g4 * 4]) = mm[i];
+        }
+        __syncthreads();
+        // ---- correct: thread p owns tile position p in all 16 channels
+        {
+            const int p = threadIdx.x;
+            double S[16];
+            uint32_t vic_ok = 0;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const float v = tile[c][p];
+                const uint32_t m = mt[c][p];
+                const bool ok = (v > 0.0f) && !(m & bits_src_bad);
+                const float sf = v * (ok ? 1.0f : 0.0f);
+                S[c] = (double)sf;
+                if (!(m & bit_edge)) vic_ok |= 1u << c;
+            }
+#pragma unroll
+            for (int vch = 0; vch < 16; vch++) {
+                const int same0 = (vch < 8) ? 0 : 8, other0 = 8 - same0;
+                // same-half sources first (quadrant q=0 / q=3), then the mirrored half
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[same0 + s][vch], a);
+#pragma unroll
+                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[other0 + s][vch], b);
+                double corr = 0.0 + a;
+                corr = corr + b;
+                corr = corr * (((vic_ok >> vch) & 1u) ? 1.0 : 0.0);
+                tile[vch][p] = (float)((double)tile[vch][p] - corr);
+            }
+        }
+        __syncthreads();
+        // ---- write back
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int c = c0 + 4 * i;
+                *reinterpret_cast<float4 *>(img + off[i]) = *reinterpret_cast<const float4 *>(&tile[c][g4 * 4]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                          const double *coeffs_h, const bbx_maskbits *bits, void *stream)
 {
@@ -100,6 +187,14 @@ extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysiz
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
     const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
+    if (px4 && getenv("BBX_XTALK_PX") == nullptr) {
+        const long long ngroups = (long long)ysize_chan * (xsize_chan / 4);
+        const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
+        const int blocks = (int)(ntiles < (long long)BBX_SM_COUNT * 32 ? ntiles : (long long)BBX_SM_COUNT * 32);
+        xtalk_tile_kernel<<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        BBX_CHECK_LAUNCH("xtalk_tile_kernel");
+        return 0;
+    }
     const bool px2 = (xsize_chan % 2 == 0) && ((uintptr_t)img % 8) == 0 && ((uintptr_t)mask % 2) == 0;
     // measured on B200 (10560^2, tools/xt_bench.py): 2 px/thread 0.395 ms, 4 px/thread 0.435 ms
     // (255 registers), 1 px/thread 0.76 ms
