@@ -25,17 +25,18 @@
 // (previous list A) u (cross neighbourhood of the cosmic-ray list) -- re-evaluated sparsely.
 //
 // The reference's background level (lower median of all unmasked pixels of the INPUT image,
-// used for CR pixels without any usable neighbour) is only computed when such a pixel turns up
-// (rare): the cleaning kernel raises a flag, and a cooperative kernel that is a no-op otherwise
-// puts the original values of the cosmic-ray pixels back (they are saved when a pixel enters the
-// CR list), runs an exact radix select over the unmasked pixels, restores the cleaned values
-// and patches the pixels concerned -- all on the device, no host round trip.  If a work list
-// overflows a status bit is raised and the caller repeats the frame with the dense
-// implementation (LAC_STATUS_OVERFLOW).
-#include <cooperative_groups.h>
+// used for CR pixels without any usable neighbour -- the interior of a fat cosmic-ray blob, which
+// sigfrac = 0.01 makes common) costs no extra pass: a strided sample of 4096 pixels brackets the
+// median rank (+-5 sigma of the sampling error); the dense scan, which touches every pixel
+// anyway, counts the unmasked pixels below the bracket and histograms those inside it with ONE
+// BIN PER FLOAT32 KEY (the bracket is a few e- wide: ~1e5 distinct keys, a 4 MB table of global
+// atomics with next to no contention); the median is the key whose cumulative count reaches the
+// wanted rank.  Exact, no list of values, no selection passes.  If the bracket misses (or is
+// wider than the table) and the level is then actually needed, LAC_STATUS_NEED_BG is raised and
+// the caller repeats the call with mode 2, which runs the radix select of the dense path (three
+// passes over image + mask) up front.  If a work list overflows, LAC_STATUS_OVERFLOW is raised
+// and the caller repeats the call with the dense implementation.
 #include "lacosmic_common.cuh"
-
-namespace cg = cooperative_groups;
 
 #define FLAG_C0 1u
 #define FLAG_C1 2u
@@ -45,13 +46,22 @@ namespace cg = cooperative_groups;
 struct SparseCounters {
     unsigned int nA[2];                  // list A of the current / previous iteration (ping-pong)
     unsigned int nB, nC0, nC1, nCR;
-    unsigned int bg_need, bg_valid;      // background level: asked for by the cleaning / computed
+    unsigned int bg_valid, pad;          // background level known (mode 2)
+};
+
+#define BG_SAMPLES 4096u
+#define BG_BINS (1u << 20)
+
+struct BgState {
+    unsigned int key_a, width;           // bracket: keys key_a .. key_a + width - 1 (width 0: no bracket)
+    unsigned long long n_valid, n_below; // unmasked pixels; unmasked pixels with key < key_a
 };
 
 struct SparseWork {
     uint8_t *flags;              // [N] per pixel: (iteration stamp << 4) | FLAG_*
+    BgState *bg;
+    unsigned int *bghist;        // [BG_BINS] pixels per float32 key inside the bracket
     unsigned int *listA[2], *listB, *listC0, *listC1, *listCR;
-    float *origCR;               // [capCR] input-image value of every CR-list pixel
     unsigned int capA, capB, capC, capCR;
     SparseCounters *cnt;
     SelState *sel;
@@ -74,8 +84,9 @@ size_t lac_sparse_work_bytes(int H, int W)
     const size_t n = (size_t)H * W;
     unsigned int a, b, c, cr;
     sparse_caps(n, a, b, c, cr);
-    return sp_align(n) + 2 * sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + 2 * sp_align(4ull * cr) +
-           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(SelState)) + 512;
+    return sp_align(n) + 2 * sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + sp_align(4ull * cr) +
+           sp_align(sizeof(SparseCounters)) + sp_align(sizeof(SelState)) + sp_align(sizeof(BgState)) +
+           sp_align(4ull * BG_BINS) + 512;
 }
 
 static SparseWork carve_sparse(void *work, size_t n)
@@ -90,9 +101,10 @@ static SparseWork carve_sparse(void *work, size_t n)
     w.listC0 = (unsigned int *)p; p += sp_align(4ull * w.capC);
     w.listC1 = (unsigned int *)p; p += sp_align(4ull * w.capC);
     w.listCR = (unsigned int *)p; p += sp_align(4ull * w.capCR);
-    w.origCR = (float *)p; p += sp_align(4ull * w.capCR);
     w.cnt = (SparseCounters *)p; p += sp_align(sizeof(SparseCounters));
     w.sel = (SelState *)p; p += sp_align(sizeof(SelState));
+    w.bg = (BgState *)p; p += sp_align(sizeof(BgState));
+    w.bghist = (unsigned int *)p; p += sp_align(4ull * BG_BINS);
     w.background = (float *)p;
     return w;
 }
@@ -151,50 +163,211 @@ __device__ __forceinline__ float lac_thr_lo(const LacParams &prm)
 // A block owns a 512-pixel wide, SCAN_ROWS tall strip: 128 threads x 4 pixels walk down the
 // rows keeping the previous / current / next row in registers, so every pixel is loaded once
 // per strip (plus one halo row at either end).
+//
+// The kernel is instruction-issue bound (ncu: 90 % issue slots for the plain 25-operation
+// Laplacian), so almost every pixel is dismissed by a cheaper, rigorous bound first.  With
+// m1 = min(l, r), m2 = min(u, d) the largest of the four sub-pixel Laplacians is, in exact
+// arithmetic, t = 2c - m1 - m2; the float32 evaluation exceeds it by at most 4 roundings of
+// intermediates <= 8 mag (mag = largest magnitude involved), i.e. < 2^-18 mag, and the final
+// average of the clipped values by a factor < 1 + 2^-22.  t is evaluated with round-up
+// operations, so  t_ru <= thr_lo (1 - 2^-21) - 2^-18 mag  implies L+ <= thr_lo.  NaNs fail the
+// comparison and take the full evaluation.
+//
+// COLLECT (mode 0): also the statistics for the background level, see the file header.
 #define SCAN_THREADS 128
 #define SCAN_ROWS 16
+template <bool COLLECT>
 __global__ void __launch_bounds__(SCAN_THREADS)
-sp_scan_kernel(const float *__restrict__ img, int H, int W, LacParams prm, SparseWork w, long long *info)
+sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
+               SparseWork w, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
+    __shared__ unsigned long long s_red[33];
     const float thr_lo = lac_thr_lo(prm);
+    const float thr_s = __fmul_rd(thr_lo, thr_lo >= 0.f ? 0.99999952316284f : 1.00000047683716f);   // thr_lo (1 -+ 2^-21)
     const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    const bool mvec_ok = inmask && (W % 4 == 0) && (((uintptr_t)inmask & 3) == 0);
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const int ya = blockIdx.y * SCAN_ROWS, yb = min(ya + SCAN_ROWS, H);
-    if (x0 >= W) return;
-    const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
-    float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
-    if (fast_x) {
-        if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
-        cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
-    }
-    for (int y = ya; y < yb; y++) {
-        const size_t i = (size_t)y * W + x0;
-        if (fast_x && y + 1 < H) dn = *reinterpret_cast<const float4 *>(img + i + W);
-        if (fast_x && y > 0 && y + 1 < H) {
-            const float lft = img[i - 1], rgt = img[i + 4];
-            const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
-            const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
-                float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
-                float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
-                float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
-                float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
-                float p = s00 + s01; p = p + s10; p = p + s11;
-                const float lp = p * 0.25f;
-                if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+    unsigned int n_valid = 0, n_below = 0;
+    unsigned int key_a = 0, width = 0;
+    if (COLLECT) { key_a = w.bg->key_a; width = w.bg->width; }
+    if (x0 < W) {
+        const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
+        float mag_up = 0.f, mag_cur = 0.f, mag_dn = 0.f;       // largest |value| of the 4 own pixels of a row
+        if (fast_x) {
+            if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
+            cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
+            mag_up = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(up.z), fabsf(up.w)));
+            mag_cur = fmaxf(fmaxf(fabsf(cur.x), fabsf(cur.y)), fmaxf(fabsf(cur.z), fabsf(cur.w)));
+        }
+        for (int y = ya; y < yb; y++) {
+            const size_t i = (size_t)y * W + x0;
+            if (fast_x && y + 1 < H) {
+                dn = *reinterpret_cast<const float4 *>(img + i + W);
+                mag_dn = fmaxf(fmaxf(fabsf(dn.x), fabsf(dn.y)), fmaxf(fabsf(dn.z), fabsf(dn.w)));
             }
-        } else {
-            for (int k = 0; k < 4 && x0 + k < W; k++) {
-                const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+            if (COLLECT) {
+                unsigned int mm = 0;
+                const bool mv = mvec_ok && x0 + 4 <= W;
+                if (mv) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
+                const float cv4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (x0 + k >= W) break;
+                    const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
+                    if (masked) continue;
+                    const unsigned int key = f32_key(fast_x ? cv4[k] : img[i + k]);
+                    n_valid++;
+                    const unsigned int d = key - key_a;
+                    if (key < key_a) n_below++;
+                    else if (d < width) atomicAdd(&w.bghist[d], 1u);
+                }
+            }
+            if (fast_x && y > 0 && y + 1 < H) {
+                const float lft = img[i - 1], rgt = img[i + 4];
+                const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
+                const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
+                float mag = fmaxf(fmaxf(mag_up, mag_dn), fmaxf(mag_cur, fmaxf(fabsf(lft), fabsf(rgt))));
+                const float thr_row = __fmaf_rd(mag, -3.814697265625e-06f, thr_s);          // - 2^-18 mag
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float cv = cc[k + 1], l = cc[k], r = cc[k + 2];
+                    float t = __fsub_ru(cv, fminf(l, r));
+                    t = __fadd_ru(t, cv);
+                    t = __fsub_ru(t, fminf(uu[k], dd[k]));
+                    if (t <= thr_row) continue;
+                    const float c4 = 4.0f * cv;
+                    float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                    float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                    float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                    float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                    s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                    float p = s00 + s01; p = p + s10; p = p + s11;
+                    const float lp = p * 0.25f;
+                    if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+                }
+            } else {
+                for (int k = 0; k < 4 && x0 + k < W; k++) {
+                    const float lp = laplace_plus_at(img, H, W, y, x0 + k);
+                    if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+                }
+            }
+            up = cur; cur = dn;
+            mag_up = mag_cur; mag_cur = mag_dn;
+        }
+    }
+    if (COLLECT) {
+        const unsigned long long tv = block_sum((unsigned long long)n_valid, s_red);
+        const unsigned long long tb = block_sum((unsigned long long)n_below, s_red);
+        if (threadIdx.x == 0) {
+            if (tv) atomicAdd(&w.bg->n_valid, tv);
+            if (tb) atomicAdd(&w.bg->n_below, tb);
+        }
+    }
+}
+
+// ---- background level ----------------------------------------------------------------------
+// One block: gather a strided sample of the unmasked pixels into shared memory, bitonic-sort it
+// and bracket the median rank by +-(2.5 sqrt(ns) + 8) sample ranks (5 sigma of the binomial
+// sampling error of the median's rank).
+__global__ void __launch_bounds__(1024)
+sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
+{
+    __shared__ unsigned int smp[BG_SAMPLES];            // float32 keys
+    __shared__ unsigned int s_ns;
+    if (threadIdx.x == 0) s_ns = 0;
+    for (unsigned int j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) smp[j] = 0xffffffffu;
+    __syncthreads();
+    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
+    for (size_t j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) {
+        const size_t i = j * stride;
+        if (i >= n) break;
+        if (inmask && inmask[i]) continue;
+        const float v = img[i];
+        if (v != v) continue;                           // NaNs are left to the full-frame statistics
+        smp[atomicAdd(&s_ns, 1u)] = f32_key(v);
+    }
+    __syncthreads();
+    const unsigned int ns = s_ns;
+    for (unsigned int k = 2; k <= BG_SAMPLES; k <<= 1)
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int i = threadIdx.x; i < BG_SAMPLES; i += blockDim.x) {
+                const unsigned int l = i ^ j;
+                if (l > i) {
+                    const unsigned int x = smp[i], y = smp[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { smp[i] = y; smp[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        unsigned int key_a = 0, width = 0;
+        if (ns > 0) {
+            const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
+            if (mid > d && mid + d < ns - 1) {
+                const unsigned int ka = smp[mid - d], kb = smp[mid + d];
+                if (kb - ka < BG_BINS) { key_a = ka; width = kb - ka + 1u; }
             }
         }
-        up = cur;
-        cur = dn;
+        w.bg->key_a = key_a; w.bg->width = width;
+        w.bg->n_valid = 0; w.bg->n_below = 0;
+    }
+}
+
+// after the scan: the key whose cumulative count reaches the median rank
+__global__ void __launch_bounds__(1024)
+sp_bg_rank_kernel(SparseWork w)
+{
+    __shared__ unsigned long long s_tot[32];
+    __shared__ unsigned long long s_k;
+    __shared__ int s_warp;
+    const unsigned int width = w.bg->width;
+    const unsigned long long nv = w.bg->n_valid, nb = w.bg->n_below;
+    if (width == 0 || nv == 0) return;                         // bg_valid stays 0
+    const unsigned long long want = (nv - 1) / 2;               // lower median
+    if (want < nb) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int chunk = (width + 31) / 32;               // bins per warp
+    const unsigned int b0 = warp * chunk, b1 = min(b0 + chunk, width);
+    unsigned long long mine = 0;
+    for (unsigned int b = b0 + lane; b < b1; b += 32) mine += w.bghist[b];
+    mine = warp_sum(mine);
+    if (lane == 0) s_tot[warp] = mine;
+    if (threadIdx.x == 0) s_warp = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long k = want - nb, acc = 0;
+        for (int q = 0; q < 32; q++) {
+            if (acc + s_tot[q] > k) { s_warp = q; s_k = k - acc; break; }
+            acc += s_tot[q];
+        }
+    }
+    __syncthreads();
+    if (warp != s_warp) return;                                 // rank outside the bracket: bg_valid stays 0
+    unsigned long long k = s_k;
+    for (unsigned int base = b0; base < b1; base += 32) {
+        const unsigned int b = base + lane;
+        const unsigned long long c = b < b1 ? w.bghist[b] : 0ull;
+        // inclusive prefix over the lanes
+        unsigned long long pre = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const unsigned int hit = __ballot_sync(0xffffffffu, pre > k);
+        if (hit) {
+            const int first = __ffs(hit) - 1;
+            if (lane == first) {
+                *w.background = key_f32(w.bg->key_a + b);
+                w.cnt->bg_valid = 1;
+            }
+            return;
+        }
+        k -= __shfl_sync(0xffffffffu, pre, 31);
     }
 }
 
@@ -369,22 +542,19 @@ sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
                 atomicAdd((unsigned long long *)&info[INFO_NCR + iter], 1ull);
                 if (crmask[q] == 0) {
                     crmask[q] = 1;
-                    // a pixel that was never flagged has never been cleaned: img[q] is still the
-                    // input value (needed if the background level has to be computed later)
-                    const unsigned int slot = list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
-                    if (slot < w.capCR) w.origCR[slot] = img[q];
+                    list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
                 }
             }
         }
     }
 }
 
-__global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt)
+__global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt, unsigned int bg_valid)
 {
     for (int i = threadIdx.x; i < n; i += blockDim.x) info[i] = (i == INFO_ACTIVE) ? 1 : 0;
     if (threadIdx.x == 0) {
         cnt->nA[0] = cnt->nA[1] = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0;
-        cnt->bg_need = cnt->bg_valid = 0;
+        cnt->bg_valid = bg_valid; cnt->pad = 0;
     }
 }
 
@@ -419,7 +589,7 @@ sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *_
             }
         if (m == 0) {                      // no usable neighbour: the global background level
             if (w.cnt->bg_valid) img[p] = *w.background;
-            else w.cnt->bg_need = 1;       // sp_bg_resolve_kernel computes it and patches this pixel
+            else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
             continue;
         }
         for (int a = 1; a < m; a++) {
@@ -433,124 +603,28 @@ sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *_
 }
 
 // --------------------------------------------------------------------------------------------
-// background level on demand (cooperative launch; returns at once unless the cleaning step met
-// a CR pixel without usable neighbours and the level is not known yet)
-// --------------------------------------------------------------------------------------------
-template <int PASS>
-__device__ __forceinline__ void sp_select_hist(const float *__restrict__ img, const uint8_t *__restrict__ inmask,
-                                               size_t n, SelState *st, unsigned int *h)
-{
-    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    const unsigned int prefix = st->prefix;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
-        if (inmask && inmask[p]) continue;
-        const unsigned int key = f32_key(img[p]);
-        if (PASS == 0) atomicAdd(&h[key >> 21], 1u);
-        else if (PASS == 1) { if ((key >> 21) == (prefix >> 21)) atomicAdd(&h[(key >> 10) & 0x7ffu], 1u); }
-        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&h[key & 0x3ffu], 1u); }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
-        if (h[i]) atomicAdd(&st->hist[PASS][i], h[i]);
-}
-
-// one block, 256 threads: same decisions as select_scan_kernel of the dense path (lacosmic.cu)
-template <int PASS>
-__device__ __forceinline__ void sp_select_scan(SelState *st, float *out, unsigned long long *scr)
-{
-    unsigned long long k = st->k;
-    if (PASS == 0) {
-        unsigned long long mine = 0;
-        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) mine += st->hist[0][i];
-        const unsigned long long total = block_sum(mine, scr);
-        if (total == 0) { if (threadIdx.x == 0) { *out = 0.0f; st->k = ~0ull; } return; }
-        k = (total - 1) / 2;
-    }
-    if (k == ~0ull) return;
-    unsigned long long below;
-    const int b = select_find_bin(st->hist[PASS], (PASS == 2) ? 1024 : SEL_BINS, k, below);
-    if (threadIdx.x != 0) return;
-    st->k = k - below;
-    if (PASS == 0) st->prefix = (unsigned int)b << 21;
-    else if (PASS == 1) st->prefix |= (unsigned int)b << 10;
-    else { st->prefix |= (unsigned int)b; *out = key_f32(st->prefix); }
-}
-
-__global__ void __launch_bounds__(256)
-sp_bg_resolve_kernel(float *img, const uint8_t *__restrict__ inmask, const uint8_t *__restrict__ crmask, int H, int W,
-                     SparseWork w, long long *info)
-{
-    // every block reads the same three words; nobody changes them before the first grid.sync
-    if (!info[INFO_ACTIVE] || !w.cnt->bg_need || w.cnt->bg_valid) return;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned int h[SEL_BINS];
-    __shared__ unsigned long long scr[33];
-    const size_t n = (size_t)H * W;
-    const unsigned int ncr = list_len(&w.cnt->nCR, w.capCR);
-    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    SelState *st = w.sel;
-    // input values back into the image (the cleaned ones are parked in origCR)
-    for (unsigned int k = gtid; k < ncr; k += gsz) {
-        const unsigned int p = w.listCR[k];
-        const float t = img[p];
-        img[p] = w.origCR[k];
-        w.origCR[k] = t;
-    }
-    for (unsigned int i = gtid; i < 3 * SEL_BINS; i += gsz) (&st->hist[0][0])[i] = 0;
-    if (gtid == 0) { st->k = 0; st->prefix = 0; }
-    grid.sync();
-    sp_select_hist<0>(img, inmask, n, st, h);
-    grid.sync();
-    if (blockIdx.x == 0) sp_select_scan<0>(st, w.background, scr);
-    grid.sync();
-    if (st->k != ~0ull) sp_select_hist<1>(img, inmask, n, st, h);
-    grid.sync();
-    if (blockIdx.x == 0) sp_select_scan<1>(st, w.background, scr);
-    grid.sync();
-    if (st->k != ~0ull) sp_select_hist<2>(img, inmask, n, st, h);
-    grid.sync();
-    if (blockIdx.x == 0) sp_select_scan<2>(st, w.background, scr);
-    grid.sync();
-    // cleaned values back; pixels without usable neighbours (skipped by sp_clean_kernel) get the level
-    const float bgv = *w.background;
-    for (unsigned int k = gtid; k < ncr; k += gsz) {
-        const unsigned int p = w.listCR[k];
-        const float t = img[p];
-        float v = w.origCR[k];
-        w.origCR[k] = t;
-        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
-        if (!(x < 2 || x >= W - 2 || y < 2 || y >= H - 2)) {
-            int m = 0;
-            for (int dy = -2; dy <= 2; dy++)
-                for (int dx = -2; dx <= 2; dx++) {
-                    const size_t j = (size_t)(y + dy) * W + (x + dx);
-                    m += !(crmask[j] || (inmask && inmask[j]));
-                }
-            if (m == 0) v = bgv;
-        }
-        img[p] = v;
-    }
-    if (gtid == 0) w.cnt->bg_valid = 1;
-}
-
-// --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
 static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, int niter,
-                        void *work, long long *info, cudaStream_t st)
+                        bool with_background, void *work, long long *info, cudaStream_t st)
 {
     const size_t n = (size_t)H * W;
     const SparseWork w = carve_sparse(work, n);
     BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
     BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));
-    sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt);
+    if (with_background) {
+        if (bbx_masked_lower_median(img, inmask, n, w.sel, w.background, st)) return -2;
+    } else {
+        BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
+        sp_bg_sample_kernel<<<1, 1024, 0, st>>>(img, inmask, n, w);
+    }
+    sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt, with_background ? 1u : 0u);
     BBX_CHECK_LAUNCH("sparse_begin");
     return 0;
 }
 
 static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
-                            int it, void *work, long long *info, cudaStream_t st)
+                            int it, bool with_background, void *work, long long *info, cudaStream_t st)
 {
     const size_t n = (size_t)H * W;
     SparseWork w = carve_sparse(work, n);
@@ -559,26 +633,20 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
     const int list_blocks = BBX_SM_COUNT * 8;
     if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
-    if (it == 0) sp_scan_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(img, H, W, prm, w, info);
-    else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);
+    if (it == 0) {
+        if (with_background) {
+            sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
+        } else {
+            sp_scan_kernel<true><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
+            sp_bg_rank_kernel<<<1, 1024, 0, st>>>(w);
+        }
+    } else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);
     sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, it, info);
     sp_cand2_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
     sp_grow_kernel<1><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_grow_kernel<2><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
     sp_clean_kernel<<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
-    {
-        static int coop_blocks = 0;
-        if (coop_blocks == 0) {
-            int per_sm = 0;
-            BBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_bg_resolve_kernel, 256, 0));
-            BBX_REQUIRE(per_sm > 0, "lazy LACosmic: background kernel does not fit an SM");
-            coop_blocks = BBX_SM_COUNT * (per_sm < 4 ? per_sm : 4);
-        }
-        const uint8_t *cr_c = crmask;
-        void *args[] = {(void *)&img, (void *)&inmask, (void *)&cr_c, (void *)&H, (void *)&W, (void *)&w, (void *)&info};
-        BBX_CUDA(cudaLaunchCooperativeKernel((const void *)sp_bg_resolve_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
-    }
     BBX_CHECK_LAUNCH("sparse_iteration");
     return 0;
 }
@@ -594,10 +662,10 @@ extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8
 {
     BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
     BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
-    BBX_REQUIRE(mode == 0 || mode == 1, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense)", mode);
+    BBX_REQUIRE(mode >= 0 && mode <= 2, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense, 2 = lazy with background level)", mode);
     BBX_REQUIRE((long long)H * W < 4294967295LL, "bbx_lacosmic_begin: image too large for 32-bit pixel indices");
     if (mode == 1) return lac_dense_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
-    return sparse_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
+    return sparse_begin(img, inmask, crmask, H, W, niter, mode == 2, work, out_info, (cudaStream_t)stream);
 }
 
 extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
@@ -608,7 +676,7 @@ extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t
     BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_iteration: null argument");
     const LacParams prm = lac_make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
     if (mode == 1) return lac_dense_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
-    return sparse_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
+    return sparse_iteration(img, inmask, crmask, H, W, prm, iter, mode == 2, work, out_info, (cudaStream_t)stream);
 }
 
 extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,

@@ -135,11 +135,11 @@ class FramePipeline:
         lac_status = int(self.lwork.info[2].item()) if self.niter > 0 else 0
         if morph_bad or lac_status != 0:
             # the sparse mask morphology overflowed / did not converge (the mask LACosmic saw was
-            # not final) or the lazy LACosmic needs its dense twin: redo everything after the
-            # overscan stage with the dense kernels concerned
+            # not final) or the lazy LACosmic needs the background level / its dense twin: redo
+            # everything after the overscan stage with the kernels concerned
             redo = True
             self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad,
-                       lac_mode=R.LAC_DENSE if lac_status != 0 else R.LAC_LAZY)
+                       lac_mode=R.lac_retry_mode(lac_status) if lac_status != 0 else R.LAC_LAZY)
             torch.cuda.current_stream().synchronize()
             if self.niter > 0 and int(self.lwork.info[2].item()) != 0:
                 self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad, lac_mode=R.LAC_DENSE)

@@ -472,7 +472,13 @@ class LacosmicWork:
         self.info = torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
 
 
-LAC_LAZY, LAC_DENSE = 0, 1
+LAC_LAZY, LAC_DENSE, LAC_LAZY_BG = 0, 1, 2
+LAC_STATUS_OVERFLOW, LAC_STATUS_NEED_BG = 1, 2
+
+
+def lac_retry_mode(status):
+    """Mode to repeat a lazy LACosmic call with, given its non-zero status word."""
+    return LAC_DENSE if (status & LAC_STATUS_OVERFLOW) else LAC_LAZY_BG
 
 
 def lacosmic_enqueue(img_t, inmask_t, crmask_t, sigclip, sigfrac, objlim, readnoise, niter,
@@ -494,8 +500,9 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
                    psfsize=7, psfk=None, psfbeta=4.765, verbose=False, info=None, mode=None):
     """astroscrappy.detect_cosmics (1.0.8 signature) -> (crmask bool, cleanarr float32).
 
-    ``mode``: None = lazy evaluation with an automatic dense repeat when needed (same
-    result either way), LAC_LAZY / LAC_DENSE to force one implementation (tests).
+    ``mode``: None = lazy evaluation with an automatic repeat when its status word asks for it
+    (with the background level, or densely: same result either way), LAC_LAZY / LAC_DENSE /
+    LAC_LAZY_BG to force one implementation (tests).
 
     Implemented path: sepmed=False, cleantype='medmask', fsmode='median', pssl=0,
     satlevel=inf -- the one blackbox.py:4323-4332 uses; anything else raises
@@ -547,8 +554,11 @@ def _detect_cosmics_dev(src, inmask_t, sigclip, sigfrac, objlim, gain, readnoise
     if status != 0:
         if mode is not None:
             raise RuntimeError('detect_cosmics: lazy evaluation incomplete (status {})'.format(status))
-        clean, inf = run(LAC_DENSE)
-        used = LAC_DENSE
+        used = lac_retry_mode(status)
+        clean, inf = run(used)
+        if int(inf[2]) != 0:                 # the lists overflowed on the repeat as well
+            used = LAC_DENSE
+            clean, inf = run(used)
     if gain != 1.0:
         clean /= float(np.float32(gain))
     return clean, crmask, work, used, inf, status

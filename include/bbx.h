@@ -223,13 +223,17 @@ int bbx_stack_median(const float *const *frames_h, const float *scale_h, int N, 
  * crmask u8  [H][W]  out: 0/1
  * work   >= bbx_lacosmic_work_bytes(H, W) bytes
  * readnoise_dev: optional device scalar (float64) used instead of `readnoise`
- * mode   0 = lazy: one dense Laplacian pass per iteration, medians only where they can matter
+ * mode   0 = lazy: one dense Laplacian pass, then everything (medians, fine structure, growth,
+ *            cleaning, the Laplacian of later iterations) only where it can matter
  *            (bit-identical to mode 1; requires sigclip >= 0 and sigfrac >= 0)
  *        1 = dense: every intermediate image is materialised
+ *        2 = lazy, with the global background level (lower median of the unmasked input
+ *            pixels) computed up front by three extra passes over image + mask
  * out_info int64 [4 + niter] device: [0] iterations run, [1] internal, [2] status bits
- * (BBX_LAC_OVERFLOW: a work list overflowed, BBX_LAC_NEED_BG: a cosmic-ray pixel without
- * usable neighbours needs the global background level -- in both cases the lazy result is
- * incomplete and the call must be repeated with mode 1), [4+k] new CR pixels of iteration k.
+ * (BBX_LAC_OVERFLOW: a work list overflowed -> result incomplete, repeat with mode 1;
+ * BBX_LAC_NEED_BG (mode 0 only): a cosmic-ray pixel without any usable neighbour in its 5x5
+ * box needs the background level -> result incomplete, repeat with mode 2),
+ * [4+k] new CR pixels of iteration k.
  * The iteration loop runs on the device without host synchronisation; iterations after one
  * that found nothing are skipped (as the reference's `break`).
  * ------------------------------------------------------------------------------------- */
@@ -255,7 +259,7 @@ int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, i
 /* After bbx_lacosmic (same mode, same work buffer): mask[crmask != 0] |= cosmic_bit
  * (blackbox.py:4349; mask may be null) and out_ncosmics = number of 8-connected cosmic-ray
  * objects (ndimage.label, blackbox.py:4354-4355).  mode 0 walks the cosmic-ray pixel list of
- * the lazy path; mode 1 does dense passes.  labels: int32 [H*W] scratch. */
+ * the lazy path (also for mode 2); mode 1 does dense passes.  labels: int32 [H*W] scratch. */
 int bbx_lacosmic_finish(const uint8_t *crmask, uint8_t *mask, int cosmic_bit, int H, int W,
                         int mode, void *work, int32_t *labels, int32_t *out_ncosmics,
                         void *stream);

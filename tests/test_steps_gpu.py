@@ -112,8 +112,9 @@ def test_detect_cosmics_bit_exact(seed, niter, sigclip, mode):
 
 def test_detect_cosmics_background_level():
     """A fat cosmic-ray blob leaves interior pixels without usable neighbours: they get the
-    global background level (lower median of all unmasked input pixels), which the lazy path
-    finds from a sampled bracket + exact selection."""
+    global background level (lower median of all unmasked input pixels).  The lazy path finds
+    it from a sampled bracket + one histogram bin per float32 key inside the bracket (mode 0),
+    or from the dense radix select run up front (mode 2)."""
     from blackbox_b200 import reduce as bbr
     from oracle import lacosmic
     rng = np.random.default_rng(21)
@@ -128,10 +129,34 @@ def test_detect_cosmics_background_level():
         info_o, info_g = {}, {}
         cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=m, info=info_o, **kw)
         assert (clean_o == info_o['background']).any()         # the case is exercised
-        for mode in (bbr.LAC_LAZY, bbr.LAC_DENSE):
+        for mode in (bbr.LAC_LAZY, bbr.LAC_LAZY_BG, bbr.LAC_DENSE, None):
             cr_g, clean_g = bbr.detect_cosmics(img, inmask=m, info=info_g, mode=mode, **kw)
             assert np.array_equal(cr_g, cr_o) and np.array_equal(clean_g, clean_o)
             assert info_g['lazy_status'] == 0
+            assert info_g['iterations'] == info_o['iterations']
+
+
+def test_detect_cosmics_background_bracket_miss():
+    """Few unmasked pixels, half of them cosmic-ray values: the sampled bracket spans far more
+    float32 keys than the histogram has bins, so mode 0 must report that it needs the level
+    (never a wrong value) and the automatic mode must repeat with mode 2."""
+    from blackbox_b200 import reduce as bbr
+    from oracle import lacosmic
+    rng = np.random.default_rng(22)
+    img = (300 + 17 * rng.standard_normal((96, 120))).astype(np.float32)
+    img[40:49, 50:59] += rng.uniform(20000, 60000, (9, 9)).astype(np.float32)
+    mask = np.ones(img.shape, bool)
+    mask[38:51, 48:61] = False
+    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=4, readnoise=8.5, gain=1.0,
+              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    info_o, info_g = {}, {}
+    cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=mask, info=info_o, **kw)
+    assert (clean_o == info_o['background']).any()
+    with pytest.raises(RuntimeError):
+        bbr.detect_cosmics(img, inmask=mask, mode=bbr.LAC_LAZY, **kw)
+    cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g, **kw)
+    assert info_g['lazy_status'] == bbr.LAC_STATUS_NEED_BG
+    assert np.array_equal(cr_g, cr_o) and np.array_equal(clean_g, clean_o)
 
 
 def test_detect_cosmics_no_mask_and_early_stop():
