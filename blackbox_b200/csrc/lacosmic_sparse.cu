@@ -46,7 +46,9 @@
 struct SparseCounters {
     unsigned int nA[2];                  // list A of the current / previous iteration (ping-pong)
     unsigned int nB, nC0, nC1, nCR;
-    unsigned int bg_valid, pad;          // background level known (mode 2)
+    unsigned int bg_valid;               // background level known
+    unsigned int clean_lo, clean_hi;     // CR-list range that is new in the current iteration
+    unsigned int pad;
 };
 
 #define BG_SAMPLES 4096u
@@ -137,6 +139,14 @@ __device__ __forceinline__ bool flag_set(uint8_t *flags, size_t p, unsigned int 
         if (seen == old) return true;
         old = seen;
     }
+}
+
+// is `bit` set in the flag byte of pixel p for this stamp (plain read: a stale answer only costs
+// a redundant evaluation)
+__device__ __forceinline__ bool flag_has(const uint8_t *flags, size_t p, unsigned int stamp, unsigned int bit)
+{
+    const unsigned int b = flags[p];
+    return (b >> 4) == stamp && (b & bit) != 0;
 }
 
 __device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsigned int cap)
@@ -517,18 +527,22 @@ sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     const int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const float rn2 = lac_rn2(prm);
-    const unsigned long long total = (unsigned long long)n * 9ull;
-    for (unsigned long long t = warp; t < total; t += nwarps) {
-        const unsigned int r = src[t / 9];
-        const int k = (int)(t % 9);
+    const unsigned int total = n * 9u;                         // n <= capC = N/32: no overflow
+    for (unsigned int t = warp; t < total; t += nwarps) {
+        const unsigned int r = src[t / 9u];
+        const int k = (int)(t % 9u);
         const int ry = (int)(r / (unsigned int)W), rx = (int)(r - (unsigned int)ry * (unsigned int)W);
         const int qy = ry + k / 3 - 1, qx = rx + k % 3 - 1;
         if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
         const bool centre = (k == 4);
         if (!centre && (qy == 0 || qy == H - 1 || qx == 0 || qx == W - 1)) continue;
         const size_t q = (size_t)qy * W + qx;
+        // already accepted through another neighbour: nothing to add
+        if (flag_has(w.flags, q, stamp, STEP == 1 ? FLAG_C1 : FLAG_C2)) continue;
         if (inmask && inmask[q]) continue;
-        bool pass = centre && centre_implied;
+        // a member of the source set passed good & s' > sigclip before (c0 for step 1, c1 for
+        // step 2); that implies this step's test if its threshold is not higher
+        bool pass = centre_implied && (centre || flag_has(w.flags, q, stamp, STEP == 1 ? FLAG_C0 : FLAG_C1));
         if (!pass) {
             float s_c, nz_c;
             const float sp = warp_sprime(img, H, W, qy, qx, rn2, lane, s_c, nz_c);
@@ -555,6 +569,7 @@ __global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt, unsi
     if (threadIdx.x == 0) {
         cnt->nA[0] = cnt->nA[1] = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0;
         cnt->bg_valid = bg_valid; cnt->pad = 0;
+        cnt->clean_lo = cnt->clean_hi = 0;
     }
 }
 
@@ -565,40 +580,70 @@ __global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt
     info[INFO_ITERS] = iter + 1;
     if (info[INFO_NCR + iter] == 0) info[INFO_ACTIVE] = 0;
     cnt->nA[(iter + 1) & 1] = 0;           // destination of the next iteration's rescan
+    cnt->clean_lo = cnt->clean_hi;         // CR-list entries [clean_lo, clean_hi) are new in this iteration
+    cnt->clean_hi = cnt->nCR < 0xffffffffu ? cnt->nCR : 0xffffffffu;
     cnt->nB = cnt->nC0 = cnt->nC1 = 0;
 }
 
-// medmask cleaning of every pixel flagged so far (cumulative CR list)
+// medmask cleaning: a flagged pixel becomes the lower median of the unflagged, unmasked pixels of
+// its 5x5 box (read from the image: unflagged pixels are never rewritten, so the result only
+// depends on WHICH neighbours are flagged).  ALL: every pixel of the cumulative CR list (first
+// iteration: all of them are new).  !ALL: only flagged pixels with a newly flagged pixel in
+// their box can change -- walk the 5x5 boxes of the new CR-list entries (duplicates recompute
+// the same value).
+__device__ __forceinline__ void sp_clean_pixel(float *img, const uint8_t *__restrict__ crmask,
+                                               const uint8_t *__restrict__ inmask, int H, int W, int y, int x,
+                                               const SparseWork &w, long long *info)
+{
+    if (x < 2 || x >= W - 2 || y < 2 || y >= H - 2) return;
+    const size_t p = (size_t)y * W + x;
+    float v[25];
+    int m = 0;
+    for (int dy = -2; dy <= 2; dy++)
+        for (int dx = -2; dx <= 2; dx++) {
+            const size_t j = (size_t)(y + dy) * W + (x + dx);
+            const bool bad = crmask[j] || (inmask && inmask[j]);
+            if (!bad) v[m++] = img[j];
+        }
+    if (m == 0) {                      // no usable neighbour: the global background level
+        if (w.cnt->bg_valid) img[p] = *w.background;
+        else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
+        return;
+    }
+    for (int a = 1; a < m; a++) {
+        const float key = v[a];
+        int b = a - 1;
+        while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; b--; }
+        v[b + 1] = key;
+    }
+    img[p] = v[(m - 1) / 2];
+}
+
+template <bool ALL>
 __global__ void __launch_bounds__(128)
 sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *__restrict__ inmask, int H, int W,
                 SparseWork w, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
     const unsigned int n = list_len(&w.cnt->nCR, w.capCR);
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const unsigned int p = w.listCR[k];
-        const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
-        if (x < 2 || x >= W - 2 || y < 2 || y >= H - 2) continue;
-        float v[25];
-        int m = 0;
-        for (int dy = -2; dy <= 2; dy++)
-            for (int dx = -2; dx <= 2; dx++) {
-                const size_t j = (size_t)(y + dy) * W + (x + dx);
-                const bool bad = crmask[j] || (inmask && inmask[j]);
-                if (!bad) v[m++] = img[j];
-            }
-        if (m == 0) {                      // no usable neighbour: the global background level
-            if (w.cnt->bg_valid) img[p] = *w.background;
-            else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
-            continue;
+    if (ALL) {
+        for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            const unsigned int p = w.listCR[k];
+            const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
+            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info);
         }
-        for (int a = 1; a < m; a++) {
-            const float key = v[a];
-            int b = a - 1;
-            while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; b--; }
-            v[b + 1] = key;
+    } else {
+        const unsigned int lo = min(w.cnt->clean_lo, n), hi = min(w.cnt->clean_hi, n);
+        const unsigned long long total = (unsigned long long)(hi - lo) * 25ull;
+        for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+             t += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned int p = w.listCR[lo + (unsigned int)(t / 25ull)];
+            const int o = (int)(t % 25ull);
+            const int y = (int)(p / (unsigned int)W) + o / 5 - 2, x = (int)(p % (unsigned int)W) + o % 5 - 2;
+            if (x < 0 || x >= W || y < 0 || y >= H) continue;
+            if (!crmask[(size_t)y * W + x]) continue;
+            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info);
         }
-        img[p] = v[(m - 1) / 2];
     }
 }
 
@@ -631,7 +676,7 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     unsigned int stamp = (unsigned int)(it % 15) + 1;
     BBX_REQUIRE(ceil_div(H, SCAN_ROWS) <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
     const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
-    const int list_blocks = BBX_SM_COUNT * 8;
+    const int list_blocks = BBX_SM_COUNT * 8, warp_blocks = BBX_SM_COUNT * 16;
     if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {
         if (with_background) {
@@ -642,11 +687,12 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
         }
     } else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);
     sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, it, info);
-    sp_cand2_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
-    sp_grow_kernel<1><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
-    sp_grow_kernel<2><<<list_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_cand2_kernel<<<warp_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
+    sp_grow_kernel<1><<<warp_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_grow_kernel<2><<<warp_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
-    sp_clean_kernel<<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    if (it == 0) sp_clean_kernel<true><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    else sp_clean_kernel<false><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
     BBX_CHECK_LAUNCH("sparse_iteration");
     return 0;
 }

@@ -560,38 +560,15 @@ hos_stats_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 // ============================================================================================
 #define VSTD_CLUSTER 8
 #define VSTD_THREADS 1024
-#define VSTD_MAXV 8          // strip width <= 256, as in K1
+#define VSTD_MAXV 6          // strip width <= 192 (174 unbinned, 87 binned)
 #define VSTD_LIST_PER_WARP 320
 #define VSTD_CORE_SIGMA 2.25
 
 struct VstdPartial { double s, q, cs, cq; long long n, cn; int ovf, pad; };
 
-// The strip values are x = f32(f64(f32(raw) * gain) - fit[row]) [then - dlevel in the rows of the
-// horizontal overscan], used as float64.  The float32 <-> float64 conversions run on the
-// quarter-rate XU pipe and dominated the first version of this kernel (ncu: XU 74 %), so the
-// exact conversions are done with integer operations instead: widening a float32 is a shift of
-// the exponent/mantissa field, and f64 -> f32 -> f64 is a round-to-nearest-even of the low 29
-// mantissa bits.  Values outside the normal float32 range take the conversion instructions.
-__device__ __forceinline__ double widen_f32(float a)
-{
-    const unsigned int u = __float_as_uint(a);
-    const unsigned int e = (u >> 23) & 0xffu;
-    if (e == 0u || e == 255u) {
-        if ((u << 1) == 0u) return __hiloint2double((int)u, 0);      // signed zero
-        return (double)a;                                              // denormal, inf, nan
-    }
-    const unsigned int hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
-    return __hiloint2double((int)hi, (int)(u << 29));
-}
-// == (double)(float)d
-__device__ __forceinline__ double round_to_f32(double d)
-{
-    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
-    const unsigned int e = (unsigned int)(b >> 52) & 0x7ffu;
-    if (e < 897u || e >= 1150u) return (double)(float)d;   // zero, below float32's normal range, overflow, inf, nan
-    const unsigned long long r = b + 0x0fffffffull + ((b >> 29) & 1ull);
-    return __longlong_as_double((long long)(r & ~0x1fffffffull));
-}
+// u16 -> f32 through the exponent trick (2^23 + n) - 2^23: exact, and off the quarter-rate
+// conversion unit, which the float32 <-> float64 conversions below need (the first version of
+// this kernel walked the strip up to 7 times with ~13 XU operations per value: ncu XU 74 %)
 template <typename T> __device__ __forceinline__ float raw_to_f32_alu(T v);
 template <> __device__ __forceinline__ float raw_to_f32_alu<uint16_t>(uint16_t v)
 {
@@ -602,11 +579,11 @@ template <> __device__ __forceinline__ float raw_to_f32_alu<float>(float v) { re
 template <typename T>
 __device__ __forceinline__ bool vstd_value(T rawv, float gn, double fv, bool in_hos, double dlevel, double &xd)
 {
-    const float a = raw_to_f32_alu<T>(rawv) * gn;
-    double d = round_to_f32(widen_f32(a) - fv);
-    if (in_hos) d = round_to_f32(d - dlevel);
-    xd = d;
-    return isfinite(d) && !(fabs(d) <= (double)MASKED_ZERO_TOL);
+    float x = raw_to_f32_alu<T>(rawv) * gn;
+    x = sub_f64(x, fv);
+    if (in_hos) x = sub_f64(x, dlevel);
+    xd = (double)x;
+    return vos_valid(x);
 }
 
 // Each warp walks rows rank*rows_per_cta + warp, +nwarps, ...; a lane holds the <= 8 strip
@@ -640,10 +617,9 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     double *mylist = s_list + (size_t)warp * VSTD_LIST_PER_WARP;
     int nlist = 0;                                           // entries in this warp's list (warp-uniform)
 
-    __shared__ double scr_d[33];
-    __shared__ long long scr_l[33];
-    __shared__ int scr_i[33];
-    __shared__ VstdPartial part[2];     // double-buffered slot read by the other CTAs
+    __shared__ VstdPartial wpart[VSTD_THREADS / 32];   // per-warp partial sums
+    __shared__ VstdPartial part[2];     // this CTA's sums; double-buffered slot read by the other CTAs
+    __shared__ VstdPartial total;       // sums of the whole cluster
     int phase = 0;
 
     struct Mom { double S, Q; long long N; };
@@ -652,34 +628,36 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     bool use_list = false;
     double clo = 0.0, chi = 0.0;
 
-    // publish this CTA's partial sums, combine those of the cluster in rank order
+    // all fields through the fixed xor-butterfly: deterministic
+    auto warp_reduce = [&](VstdPartial &v) {
+        v.s = warp_sum(v.s); v.q = warp_sum(v.q); v.n = warp_sum(v.n);
+        v.cs = warp_sum(v.cs); v.cq = warp_sum(v.cq); v.cn = warp_sum(v.cn); v.ovf = warp_sum(v.ovf);
+    };
+    // publish this CTA's partial sums, combine those of the cluster (two block barriers and
+    // one cluster barrier per evaluation)
     auto exchange = [&](double s, double q, long long n, double cs, double cq, long long cn, int ovf,
                         Mom &m, bool with_core) {
-        s = block_sum(s, scr_d);
-        q = block_sum(q, scr_d);
-        n = block_sum(n, scr_l);
-        if (with_core) {
-            cs = block_sum(cs, scr_d);
-            cq = block_sum(cq, scr_d);
-            cn = block_sum(cn, scr_l);
-            ovf = block_sum(ovf, scr_i);
-        }
-        if (threadIdx.x == 0) {
-            VstdPartial &o = part[phase];
-            o.s = s; o.q = q; o.n = n; o.cs = cs; o.cq = cq; o.cn = cn; o.ovf = ovf;
+        VstdPartial v = {s, q, cs, cq, n, cn, ovf, 0};
+        warp_reduce(v);
+        if (lane == 0) wpart[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            VstdPartial t = {0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0};
+            if (lane < nwarps) t = wpart[lane];
+            warp_reduce(t);
+            if (lane == 0) part[phase] = t;
         }
         cluster.sync();
-        m.S = 0.0; m.Q = 0.0; m.N = 0;
-        double tcs = 0.0, tcq = 0.0;
-        long long tcn = 0;
-        int tovf = 0;
-        for (int k = 0; k < VSTD_CLUSTER; k++) {           // fixed order: deterministic
-            const VstdPartial *pp = cluster.map_shared_rank(part, k);
-            m.S += pp[phase].s; m.Q += pp[phase].q; m.N += pp[phase].n;
-            if (with_core) { tcs += pp[phase].cs; tcq += pp[phase].cq; tcn += pp[phase].cn; tovf += pp[phase].ovf; }
+        if (warp == 0) {
+            VstdPartial t = {0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0};
+            if (lane < VSTD_CLUSTER) t = cluster.map_shared_rank(part, lane)[phase];
+            warp_reduce(t);
+            if (lane == 0) total = t;
         }
-        if (with_core) { CS = tcs; CQ = tcq; CN = tcn; use_list = (tovf == 0); }
-        phase ^= 1;      // the next publish uses the other slot, so no second sync is needed
+        __syncthreads();
+        m.S = total.s; m.Q = total.q; m.N = total.n;
+        if (with_core) { CS = total.cs; CQ = total.cq; CN = total.cn; use_list = (total.ovf == 0); }
+        phase ^= 1;      // the next publish uses the other slot: no remote read can be overtaken
     };
 
     // one pass over this CTA's rows: moments of the valid values inside [lo, hi]; with BUILD
@@ -688,16 +666,20 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         double s = 0.0, q = 0.0, cs = 0.0, cq = 0.0;
         long long n = 0, cn = 0;
         int ovf = 0;
-        for (int trow = row0 + warp; trow < row1; trow += nwarps) {
+        T v[VSTD_MAXV], vn[VSTD_MAXV];
+        auto load_row = [&](int trow, T *dst) {
             const T *p = base + (size_t)trow * g.W;
-            const double fv = fitrow[trow];
-            const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
-            T v[VSTD_MAXV];
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
                 const int j = lane + 32 * k;
-                v[k] = (j < g.vos_w) ? p[j] : (T)0;
+                dst[k] = (j < g.vos_w) ? p[j] : (T)0;
             }
+        };
+        if (row0 + warp < row1) load_row(row0 + warp, v);
+        for (int trow = row0 + warp; trow < row1; trow += nwarps) {
+            if (trow + nwarps < row1) load_row(trow + nwarps, vn);     // next row in flight during the arithmetic
+            const double fv = fitrow[trow];
+            const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
                 const int j = lane + 32 * k;
@@ -718,6 +700,8 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
                     }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < VSTD_MAXV; k++) v[k] = vn[k];
         }
         exchange(s, q, n, cs, cq, cn, ovf, m, build);
     };

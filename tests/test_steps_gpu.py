@@ -119,7 +119,7 @@ def test_detect_cosmics_background_level():
     from oracle import lacosmic
     rng = np.random.default_rng(21)
     img = (300 + 17 * rng.standard_normal((96, 120))).astype(np.float32)
-    img[40:49, 50:59] += rng.uniform(20000, 60000, (9, 9)).astype(np.float32)
+    img[40:53, 50:63] += rng.uniform(20000, 60000, (13, 13)).astype(np.float32)
     img[10, 10] += 9000.0
     mask = np.zeros(img.shape, bool)
     mask[:, :7] = True
@@ -128,7 +128,7 @@ def test_detect_cosmics_background_level():
     for m in (None, mask):
         info_o, info_g = {}, {}
         cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=m, info=info_o, **kw)
-        assert (clean_o == info_o['background']).any()         # the case is exercised
+        assert (clean_o[cr_o] == info_o['background']).sum() > 3     # the case is exercised
         for mode in (bbr.LAC_LAZY, bbr.LAC_LAZY_BG, bbr.LAC_DENSE, None):
             cr_g, clean_g = bbr.detect_cosmics(img, inmask=m, info=info_g, mode=mode, **kw)
             assert np.array_equal(cr_g, cr_o) and np.array_equal(clean_g, clean_o)
@@ -137,21 +137,23 @@ def test_detect_cosmics_background_level():
 
 
 def test_detect_cosmics_background_bracket_miss():
-    """Few unmasked pixels, half of them cosmic-ray values: the sampled bracket spans far more
-    float32 keys than the histogram has bins, so mode 0 must report that it needs the level
-    (never a wrong value) and the automatic mode must repeat with mode 2."""
+    """Two pixel populations of equal size (sky ~300, nebula ~30000): the median sits at the
+    boundary, the sampled bracket spans far more float32 keys than the histogram has bins, so
+    mode 0 must report that it needs the level (never a wrong value) and the automatic mode
+    must repeat with mode 2."""
     from blackbox_b200 import reduce as bbr
     from oracle import lacosmic
     rng = np.random.default_rng(22)
     img = (300 + 17 * rng.standard_normal((96, 120))).astype(np.float32)
-    img[40:49, 50:59] += rng.uniform(20000, 60000, (9, 9)).astype(np.float32)
-    mask = np.ones(img.shape, bool)
-    mask[38:51, 48:61] = False
+    img[:, 60:] += 30000
+    img[:, 60:] += (170 * rng.standard_normal((96, 60))).astype(np.float32)
+    img[40:53, 20:33] += rng.uniform(20000, 60000, (13, 13)).astype(np.float32)
+    mask = None
     kw = dict(sigclip=15, sigfrac=0.01, objlim=3, niter=4, readnoise=8.5, gain=1.0,
               satlevel=np.inf, cleantype='medmask', sepmed=False)
     info_o, info_g = {}, {}
     cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=mask, info=info_o, **kw)
-    assert (clean_o == info_o['background']).any()
+    assert (clean_o[cr_o] == info_o['background']).sum() > 3
     with pytest.raises(RuntimeError):
         bbr.detect_cosmics(img, inmask=mask, mode=bbr.LAC_LAZY, **kw)
     cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g, **kw)
