@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--depth', type=int, default=2, help='frames in flight per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-rows', type=int, default=330,
@@ -122,7 +123,7 @@ def workload_config(args):
                         .format(TEL, args.batch, NITER),
             'frames_per_gpu_per_step': args.batch, 'lacosmic_niter': NITER,
             'l2': 'inputs larger than L2 (254 MB raw + 1 GB masters per frame vs 126 MB L2)',
-            'parallelism': 'frame k -> GPU k mod N, no collective; 2 frames in flight per GPU on 2 streams'}
+            'parallelism': 'frame k -> GPU k mod N, no collective; {0} frames in flight per GPU on {0} streams'.format(args.depth)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -201,11 +202,11 @@ def run_gpu(args, rank, world, local_rank):
             base = base + torch.randint(-3, 4, base.shape, device=dev, generator=gen, dtype=torch.int32)
         raws.append(base.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
     del base
-    batch = BatchReducer(TEL, raws[0].shape, depth=2, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
+    batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
                          niter=NITER)
     pipe = batch.pipes[0]
-    out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+    out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(args.depth)]
+    out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(args.depth)]
     out_img, out_mask = out_imgs[0], out_masks[0]
 
     def barrier():

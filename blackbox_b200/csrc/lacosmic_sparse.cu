@@ -186,6 +186,24 @@ __device__ __forceinline__ float lac_thr_lo(const LacParams &prm)
 // COLLECT (mode 0): also the statistics for the background level, see the file header.
 #define SCAN_THREADS 128
 #define SCAN_ROWS 16
+// One pixel the slow way (frame rows / columns, unaligned images)
+template <bool COLLECT>
+__device__ __forceinline__ void sp_scan_pixel(const float *__restrict__ img, const uint8_t *__restrict__ inmask,
+                                              int H, int W, int y, int x, float thr_lo, unsigned int key_a,
+                                              unsigned int width, unsigned int &n_valid, unsigned int &n_below,
+                                              const SparseWork &w, long long *info)
+{
+    const size_t i = (size_t)y * W + x;
+    if (COLLECT && !(inmask && inmask[i])) {
+        const unsigned int key = f32_key(img[i]);
+        n_valid++;
+        if (key < key_a) n_below++;
+        else if (key - key_a < width) atomicAdd(&w.bghist[key - key_a], 1u);
+    }
+    const float lp = laplace_plus_at(img, H, W, y, x);
+    if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)i, info);
+}
+
 template <bool COLLECT>
 __global__ void __launch_bounds__(SCAN_THREADS)
 sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
@@ -195,77 +213,87 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     __shared__ unsigned long long s_red[33];
     const float thr_lo = lac_thr_lo(prm);
     const float thr_s = __fmul_rd(thr_lo, thr_lo >= 0.f ? 0.99999952316284f : 1.00000047683716f);   // thr_lo (1 -+ 2^-21)
-    const bool vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    const bool mvec_ok = inmask && (W % 4 == 0) && (((uintptr_t)inmask & 3) == 0);
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const int ya = blockIdx.y * SCAN_ROWS, yb = min(ya + SCAN_ROWS, H);
     unsigned int n_valid = 0, n_below = 0;
     unsigned int key_a = 0, width = 0;
     if (COLLECT) { key_a = w.bg->key_a; width = w.bg->width; }
-    if (x0 < W) {
-        const bool fast_x = vec_ok && x0 > 0 && x0 + 4 < W;
-        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), cur = up, dn = up;
-        float mag_up = 0.f, mag_cur = 0.f, mag_dn = 0.f;       // largest |value| of the 4 own pixels of a row
-        if (fast_x) {
-            if (ya > 0) up = *reinterpret_cast<const float4 *>(img + (size_t)(ya - 1) * W + x0);
-            cur = *reinterpret_cast<const float4 *>(img + (size_t)ya * W + x0);
-            mag_up = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(up.z), fabsf(up.w)));
-            mag_cur = fmaxf(fmaxf(fabsf(cur.x), fabsf(cur.y)), fmaxf(fabsf(cur.z), fabsf(cur.w)));
+    // vector path: aligned rows, the 4 pixels and their left / right neighbours inside the row
+    const bool fast = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && x0 > 0 && x0 + 4 < W &&
+                      (!COLLECT || inmask == nullptr || ((uintptr_t)inmask & 3) == 0);
+    if (x0 < W && !fast) {
+        for (int y = ya; y < yb; y++)
+            for (int k = 0; k < 4 && x0 + k < W; k++)
+                sp_scan_pixel<COLLECT>(img, inmask, H, W, y, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+    } else if (x0 < W) {
+        int y0 = ya, y1 = yb;
+        if (y0 == 0) {                                     // first / last image row: no vector path
+            for (int k = 0; k < 4; k++)
+                sp_scan_pixel<COLLECT>(img, inmask, H, W, 0, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+            y0 = 1;
         }
-        for (int y = ya; y < yb; y++) {
-            const size_t i = (size_t)y * W + x0;
-            if (fast_x && y + 1 < H) {
-                dn = *reinterpret_cast<const float4 *>(img + i + W);
-                mag_dn = fmaxf(fmaxf(fabsf(dn.x), fabsf(dn.y)), fmaxf(fabsf(dn.z), fabsf(dn.w)));
-            }
-            if (COLLECT) {
+        if (y1 == H) {
+            y1 = H - 1;
+            if (y1 >= y0)
+                for (int k = 0; k < 4; k++)
+                    sp_scan_pixel<COLLECT>(img, inmask, H, W, H - 1, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+        }
+        if (y0 < y1) {
+            const float *row = img + (size_t)y0 * W + x0;                  // current row
+            const uint8_t *mrow = (COLLECT && inmask) ? inmask + (size_t)y0 * W + x0 : nullptr;
+            float4 up = *reinterpret_cast<const float4 *>(row - W);
+            float4 cur = *reinterpret_cast<const float4 *>(row);
+            float mag_up = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(up.z), fabsf(up.w)));
+            float mag_cur = fmaxf(fmaxf(fabsf(cur.x), fabsf(cur.y)), fmaxf(fabsf(cur.z), fabsf(cur.w)));
+            unsigned int pix = (unsigned int)((size_t)y0 * W + x0);
+            for (int y = y0; y < y1; y++, row += W, pix += (unsigned int)W) {
+                const float4 dn = *reinterpret_cast<const float4 *>(row + W);
+                const float lft = row[-1], rgt = row[4];
                 unsigned int mm = 0;
-                const bool mv = mvec_ok && x0 + 4 <= W;
-                if (mv) mm = *reinterpret_cast<const unsigned int *>(inmask + i);
-                const float cv4[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (x0 + k >= W) break;
-                    const bool masked = inmask ? (mv ? ((mm >> (8 * k)) & 0xffu) != 0 : inmask[i + k] != 0) : false;
-                    if (masked) continue;
-                    const unsigned int key = f32_key(fast_x ? cv4[k] : img[i + k]);
-                    n_valid++;
-                    const unsigned int d = key - key_a;
-                    if (key < key_a) n_below++;
-                    else if (d < width) atomicAdd(&w.bghist[d], 1u);
-                }
-            }
-            if (fast_x && y > 0 && y + 1 < H) {
-                const float lft = img[i - 1], rgt = img[i + 4];
+                if (COLLECT && mrow) { mm = *reinterpret_cast<const unsigned int *>(mrow); mrow += W; }
+                const float mag_dn = fmaxf(fmaxf(fabsf(dn.x), fabsf(dn.y)), fmaxf(fabsf(dn.z), fabsf(dn.w)));
                 const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
                 const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
-                float mag = fmaxf(fmaxf(mag_up, mag_dn), fmaxf(mag_cur, fmaxf(fabsf(lft), fabsf(rgt))));
+                if (COLLECT) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const bool ok = ((mm >> (8 * k)) & 0xffu) == 0;
+                        const unsigned int key = f32_key(cc[k + 1]);
+                        const unsigned int d = key - key_a;          // wraps to a huge value below the bracket
+                        n_valid += ok;
+                        n_below += ok && key < key_a;
+                        if (ok && d < width) atomicAdd(&w.bghist[d], 1u);
+                    }
+                }
+                const float mag = fmaxf(fmaxf(mag_up, mag_dn), fmaxf(mag_cur, fmaxf(fabsf(lft), fabsf(rgt))));
                 const float thr_row = __fmaf_rd(mag, -3.814697265625e-06f, thr_s);          // - 2^-18 mag
+                float t[4];
+                bool any = false;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const float cv = cc[k + 1], l = cc[k], r = cc[k + 2];
-                    float t = __fsub_ru(cv, fminf(l, r));
-                    t = __fadd_ru(t, cv);
-                    t = __fsub_ru(t, fminf(uu[k], dd[k]));
-                    if (t <= thr_row) continue;
-                    const float c4 = 4.0f * cv;
-                    float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
-                    float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
-                    float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
-                    float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
-                    s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
-                    float p = s00 + s01; p = p + s10; p = p + s11;
-                    const float lp = p * 0.25f;
-                    if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+                    t[k] = __fsub_ru(cc[k + 1], fminf(cc[k], cc[k + 2]));
+                    t[k] = __fadd_ru(t[k], cc[k + 1]);
+                    t[k] = __fsub_ru(t[k], fminf(uu[k], dd[k]));
+                    any |= !(t[k] <= thr_row);
                 }
-            } else {
-                for (int k = 0; k < 4 && x0 + k < W; k++) {
-                    const float lp = laplace_plus_at(img, H, W, y, x0 + k);
-                    if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, (unsigned int)(i + k), info);
+                if (any) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (t[k] <= thr_row) continue;
+                        const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                        float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - uu[k];
+                        float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - uu[k];
+                        float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - dd[k]; s10 = s10 - cv;
+                        float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - dd[k]; s11 = s11 - cv;
+                        s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                        float p = s00 + s01; p = p + s10; p = p + s11;
+                        const float lp = p * 0.25f;
+                        if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, pix + k, info);
+                    }
                 }
+                up = cur; cur = dn;
+                mag_up = mag_cur; mag_cur = mag_dn;
             }
-            up = cur; cur = dn;
-            mag_up = mag_cur; mag_cur = mag_dn;
         }
     }
     if (COLLECT) {
