@@ -13,7 +13,9 @@ Printed JSON (rank 0, one line):
   value      frames/s over all GPUs, raw frames already resident in HBM
   e2e        frames/s through the public API with HOST (pinned) raw frames in and HOST image +
              mask out, H2D / D2H copies inside the timed region
-  roofline   the LACosmic iteration (the dominant unit of work) against the measured HBM peak
+  roofline   the dominant single kernel of the chain (largest mean device time among the
+             one-kernel stages, CUDA events on the launching stream INSIDE the timed region) against
+             the measured HBM peak; roofline_stages lists every stage the same way
   cpu_baseline  the CPU oracle (restatement of the reference's numpy/astropy/astroscrappy
              path) on a bounded sample, one frame-slice per host core (the reference's own
              one-process-per-frame scheme, blackbox.py:378)
@@ -38,16 +40,28 @@ FULL_NPIX = 10560 * 10560
 # algorithmic bytes per frame
 ALGO_BYTES_LAC_ITER = 10 * FULL_NPIX            # img r+w (8 B) + mask r (1 B) + crmask w (1 B)
 ALGO_BYTES_CHAIN_4IT = 7563e6
+# stage -> (kernels behind it, algorithmic bytes per frame [SURVEY.md 8d], single kernel?)
+STAGES = {
+    'overscan': ('vos_rowstats, vos_fit, hos_satcount, hos_stats, vos_std, hos_fit, satlevels (S1)', 60e6, False),
+    'apply': ('reduce_apply_strip_kernel<uint16> (S2: raw u16 + mbias + mflat + bpm -> img f32 + mask u8)', 1815.6e6, True),
+    'mask_morph': ('ms_* / hole_* / ccl kernels (S3)', 223e6, False),
+    'lacosmic': ('sp_scan + sparse candidate / grow / clean kernels, %d iterations (S4)' % NITER, NITER * 1115.1e6, False),
+    'lacosmic_finish': ('cosmic-ray bit + NCOSMICS from the CR list', None, False),
+    'xtalk': ('xtalk_tile_kernel (S5: img r+w + mask r)', 1003.6e6, True),
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--depth', type=int, default=2, help='frames in flight per GPU')
+    ap.add_argument('--depth', type=int, default=3, help='frames in flight per GPU')
+    ap.add_argument('--split-priority', type=int, default=1,
+                    help='1: overscan stage on a high-priority stream of its own')
+    ap.add_argument('--graphs', type=int, default=1, help='1: replay the stages as CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-rows', type=int, default=330,
@@ -123,7 +137,10 @@ def workload_config(args):
                         .format(TEL, args.batch, NITER),
             'frames_per_gpu_per_step': args.batch, 'lacosmic_niter': NITER,
             'l2': 'inputs larger than L2 (254 MB raw + 1 GB masters per frame vs 126 MB L2)',
-            'parallelism': 'frame k -> GPU k mod N, no collective; {0} frames in flight per GPU on {0} streams'.format(args.depth)}
+            'parallelism': 'frame k -> GPU k mod N, no collective; {} frames in flight per GPU, overscan stage '
+                           'of the next frame {}ahead of the HBM-bound stage of the current one, stages {}'.format(
+                               args.depth, 'on a high-priority stream ' if args.split_priority else '',
+                               'replayed as CUDA graphs' if args.graphs else 'launched eagerly')}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -202,11 +219,12 @@ def run_gpu(args, rank, world, local_rank):
             base = base + torch.randint(-3, 4, base.shape, device=dev, generator=gen, dtype=torch.int32)
         raws.append(base.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
     del base
-    batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs,
-                         niter=NITER)
+    batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, split_priority=bool(args.split_priority),
+                         use_graphs=bool(args.graphs), mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=NITER)
     pipe = batch.pipes[0]
-    out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(args.depth)]
-    out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(args.depth)]
+    nout = max(args.depth, B)      # frame k -> output buffer k: every (raw, output) pair recurs each step
+    out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(nout)]
+    out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(nout)]
     out_img, out_mask = out_imgs[0], out_masks[0]
 
     def barrier():
@@ -225,6 +243,8 @@ def run_gpu(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         step()
+    for p in batch.pipes:
+        p.enable_stage_timing(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -248,14 +268,16 @@ def run_gpu(args, rank, world, local_rank):
     launches = args.steps * B * pipe_launches(TEL, NITER)
 
     # ---- roofline: one LACosmic iteration, timed with CUDA events on the launching stream ---
-    roof = None
+    roof = stages = None
     if rank == 0:
-        roof = measure_lacosmic_iteration(pipe, raws, out_img, out_mask)
+        roof, stages = stage_rooflines(batch.pipes)
+    for p in batch.pipes:
+        p.enable_stage_timing(False)
 
     # ---- end to end: pinned host raw in, pinned host image + mask out -----------------------
     e2e = None
     if not args.no_e2e:
-        e2e_ms = measure_e2e(args, pipe, raws, red_shape, dev, barrier)
+        e2e_ms = measure_e2e(args, batch, raws, red_shape, barrier)
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -277,10 +299,11 @@ def run_gpu(args, rank, world, local_rank):
             'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args), 'roofline': roof, 'cpu_baseline': cpu,
+            'config': workload_config(args), 'roofline': roof, 'roofline_stages': stages, 'cpu_baseline': cpu,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
             'chain_hbm_frac': (ALGO_BYTES_CHAIN_4IT * frames / world / (ms_total * 1e-3)) / (peak_hbm()[0] * 1e9),
             'frames_redone': redo, 'host_spline_columns': spline_cols[0],
+            'graph_replays': sum(p.graph_replays for p in batch.pipes),
         }
         print(json.dumps(line))
     if world > 1:
@@ -304,89 +327,77 @@ def peak_hbm():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def measure_lacosmic_iteration(pipe, raws, out_img, out_mask, reps=3):
-    """Average device time of one LACosmic iteration (stage1 + stage2 + grow + control + clean
-    kernels) on full frames, CUDA events on the launching stream."""
-    import ctypes as C
-    import torch
-    from blackbox_b200 import reduce as R, set_bb
-    from blackbox_b200._lib import call
-    H, W = out_img.shape
-    times = []
-    for k in range(min(reps, len(raws))):
-        # a fresh reduced frame + mask (chain without LACosmic / crosstalk), then begin
-        R.overscan_enqueue(raws[k], pipe.geom, pipe.tel, gain=pipe.gain, state=pipe.st)
-        call('bbx_header_means', R._ptr(pipe.st.biasm), R._ptr(pipe.st.std_vos), R._ptr(pipe.means), R._stream())
-        R.apply_enqueue(raws[k], pipe.geom, pipe.tel, st=pipe.st, gain=pipe.gain, mbias=pipe.mbias,
-                        mflat=pipe.mflat, bpm=pipe.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
-                        mwork=pipe.mwork)
-        R.mask_morph_enqueue(out_mask, pipe.tel, pipe.mwork)
-        call('bbx_lacosmic_begin', R._ptr(out_img), R._ptr(out_mask), R._ptr(pipe.crmask), H, W, NITER, 0,
-             R._ptr(pipe.lwork.buf), R._ptr(pipe.lwork.info), R._stream())
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        call('bbx_lacosmic_iteration', R._ptr(out_img), R._ptr(out_mask), R._ptr(pipe.crmask), H, W,
-             float(set_bb.get_par(set_bb.sigclip, pipe.tel)), float(np.float32(set_bb.sigfrac)),
-             float(set_bb.objlim), 0.0, R._ptr(pipe.means[1:]), 0, 0, R._ptr(pipe.lwork.buf),
-             R._ptr(pipe.lwork.info), R._stream())
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
+def ncu_traffic():
+    """kernel name -> DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the
+    committed `ncu --set full` capture, profiles/*_traffic.json); {} if there is none."""
+    import glob
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json'))):
+        try:
+            with open(path) as fh:
+                out.update(json.load(fh))
+        except (OSError, ValueError):
+            pass
+    return out
+
+
+def stage_rooflines(pipes):
+    """Mean device time of every stage of the chain over the frames of the timed region (CUDA
+    events recorded on the launching streams by FramePipeline), each against the measured HBM
+    peak with SURVEY.md 8(d)'s algorithmic bytes.  -> (roofline of the dominant single kernel,
+    list of all stages)."""
     peak, how = peak_hbm()
-    achieved = ALGO_BYTES_LAC_ITER / (ms * 1e-3) / 1e9
-    return {'bound': 'hbm', 'kernel': 'lacosmic_iteration (sp_scan dense pass + sparse candidate/grow/clean kernels)',
-            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-            'traffic': None, 'ms_per_launch': ms, 'algorithmic_bytes': ALGO_BYTES_LAC_ITER,
-            'peak_source': how,
-            'note': 'lazy LACosmic: one dense Laplacian pass (4 B/px read) per iteration, medians only at candidates; see DESIGN.md'}
+    acc = {}
+    for p in pipes:
+        for name, (ms, n) in p.stage_times_ms().items():
+            a = acc.setdefault(name, [0.0, 0])
+            a[0] += ms * n
+            a[1] += n
+    traffic = ncu_traffic()
+    stages, best = [], None
+    for name, (tot, n) in acc.items():
+        ms = tot / n
+        kernels, nbytes, single = STAGES.get(name, (name, None, False))
+        ent = {'stage': name, 'kernels': kernels, 'ms_per_frame': ms, 'frames': n,
+               'algorithmic_bytes': nbytes, 'single_kernel': single}
+        if nbytes:
+            ent['achieved'] = nbytes / (ms * 1e-3) / 1e9
+            ent['frac'] = ent['achieved'] / peak
+        stages.append(ent)
+        if single and (best is None or ms > best['ms_per_frame']):
+            best = ent
+    stages.sort(key=lambda e: -e['ms_per_frame'])
+    if best is None:
+        return None, stages
+    kname = best['kernels'].split(' ')[0].split('<')[0]
+    roof = {'bound': 'hbm', 'kernel': best['kernels'], 'achieved': best['achieved'], 'peak': peak,
+            'unit': 'GB/s', 'frac': best['frac'], 'traffic': traffic.get(kname),
+            'ms_per_launch': best['ms_per_frame'], 'launches_timed': best['frames'],
+            'algorithmic_bytes': best['algorithmic_bytes'], 'peak_source': how,
+            'note': 'dominant single kernel by mean device time inside the timed region (two frames in '
+                    'flight: other streams\' kernels share the GPU during the launch)'}
+    return roof, stages
 
 
-def measure_e2e(args, pipe, raws, red_shape, dev, barrier):
-    """Public API with host buffers: pinned uint16 raw frames in, pinned f32 image + u8 mask
-    out; H2D, chain and D2H overlap on three streams with double buffering."""
+def measure_e2e(args, batch, raws, red_shape, barrier):
+    """Public API with host buffers (BatchReducer.run_host): pinned uint16 raw frames in, pinned
+    f32 image + u8 mask out; host-to-device copies, the chain and device-to-host copies overlap
+    on their own streams, `--depth` frames in flight."""
     import torch
     B = args.batch
     host_raw = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(B)]
     for k in range(B):
         host_raw[k].copy_(raws[k].cpu())
-    host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
-    host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    d_raw = [torch.empty(raws[0].shape, dtype=torch.uint16, device=dev) for _ in range(2)]
-    d_img = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    d_mask = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_cmp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    status = torch.zeros((B, 1), dtype=torch.int32).pin_memory()
+    nring = min(max(2, args.depth), B) if B > 1 else 1
+    host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nring)]
+    host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(nring)]
 
     def run(nsteps):
-        n = 0
+        redo = 0
         for _ in range(nsteps):
-            for k in range(B):
-                b = n % 2
-                with torch.cuda.stream(s_in):
-                    s_in.wait_event(ev_cmp[b])              # raw buffer b free again
-                    d_raw[b].copy_(host_raw[k], non_blocking=True)
-                    ev_in[b].record(s_in)
-                with torch.cuda.stream(s_cmp):
-                    s_cmp.wait_event(ev_in[b])
-                    s_cmp.wait_event(ev_out[b])             # output buffer b copied out
-                    pipe.enqueue(d_raw[b], d_img[b], d_mask[b])
-                    pipe.enqueue_status(status[k])
-                    ev_cmp[b].record(s_cmp)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_cmp[b])
-                    host_img[b].copy_(d_img[b], non_blocking=True)
-                    host_mask[b].copy_(d_mask[b], non_blocking=True)
-                    ev_out[b].record(s_out)
-                n += 1
-        for s in (s_in, s_cmp, s_out):
-            s.synchronize()
-        if int(status.sum()) != 0:
-            raise RuntimeError('e2e: hole filling of a frame did not converge (status {})'.format(status.tolist()))
+            for res in batch.run_host(host_raw, host_img, host_mask):
+                redo += res.redo
+        return redo
 
     run(1)
     barrier()

@@ -67,9 +67,12 @@ _SIGNATURES = {
     'bbx_gain_corr': [P, GEOM, P, P],
     'bbx_binary_inplace': [P, P, SZ, I, P],
     'bbx_mask_or': [P, P, SZ, I, P],
+    'bbx_chanmed_work_bytes': [],
+    'bbx_channel_medians': [P, I, I, I, I, P, P, P],
+    'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],
 }
 _RESTYPES = {'bbx_fill_holes_work_bytes': SZ, 'bbx_lacosmic_work_bytes': SZ,
-             'bbx_select_work_bytes': SZ}
+             'bbx_select_work_bytes': SZ, 'bbx_chanmed_work_bytes': SZ}
 
 EXPORTS = tuple(sorted(list(_SIGNATURES) + ['bbx_last_error']))
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT_DIR, 'libbbx.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = (['-DVSTD_DEBUG'] if os.environ.get('VSTD_DEBUG') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-fmad=false',
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-fmad=false',
          '-std=c++17', '--compiler-options', '-fPIC', '-Xptxas', '-v']
 
 

@@ -15,9 +15,12 @@
 //
 //   scan   (dense)   L+ -> list A  = { s_ub > sigclip }
 //   cand1  (list A)  good, med5(img), s > sigclip            -> list B
-//   cand2  (list B)  warp per pixel: s on 5x5, s' ; f on 7x7 -> c0 flag, list C0
-//   grow1  (C0 x 9)  warp per neighbour: s' > sigclip & good -> c1 flag, list C1
-//   grow2  (C1 x 9)  warp per neighbour: s' > sigcliplow & good -> c2: count, crmask, CR list
+//   cand2  (list B)  warp per pixel: s on 5x5, s' > sigclip -> S1 flag; f on 7x7 -> c0 flag, list C0
+//   grow1  (C0 x 9)  thread per neighbour q: c1 = S1(q)  (good & s' > sigclip implies q in list B,
+//                    and cand2 has tested every pixel of B: no arithmetic left)   -> list C1
+//   grow2a (C1 x 9)  thread per neighbour q: members of C1 pass (s' > sigclip >= sigcliplow);
+//                    every other unmasked q is queued ONCE (T2 flag)            -> list Q
+//   grow2b (list Q)  warp per pixel: s' > sigcliplow                  -> c2: count, crmask, CR list
 //   clean  (CR list) lower median of the unflagged 5x5 neighbours
 //
 // Iterations after the first do not rescan the image: L+ of a pixel changes only if the pixel or
@@ -42,13 +45,18 @@
 #define FLAG_C1 2u
 #define FLAG_C2 4u
 #define FLAG_A 8u
+#define FLAG_S1 16u          // good & s' > sigclip (set by cand2 for the pixels of list B that pass)
+#define FLAG_T2 32u          // queued for the s' > sigcliplow test of growth step 2 (list Q)
+#define FLAG_BITS 6          // flag byte = (iteration stamp << FLAG_BITS) | FLAG_*: stamps 1..3
+#define FLAG_MASK 0x3fu
+#define STAMP_PERIOD 3
 
 struct SparseCounters {
     unsigned int nA[2];                  // list A of the current / previous iteration (ping-pong)
     unsigned int nB, nC0, nC1, nCR;
     unsigned int bg_valid;               // background level known
     unsigned int clean_lo, clean_hi;     // CR-list range that is new in the current iteration
-    unsigned int pad;
+    unsigned int nQ;                     // list Q (shares the storage of list B, which is spent by then)
 };
 
 #define BG_SAMPLES 4096u
@@ -60,7 +68,7 @@ struct BgState {
 };
 
 struct SparseWork {
-    uint8_t *flags;              // [N] per pixel: (iteration stamp << 4) | FLAG_*
+    uint8_t *flags;              // [N] per pixel: (iteration stamp << FLAG_BITS) | FLAG_*
     BgState *bg;
     unsigned int *bghist;        // [BG_BINS] pixels per float32 key inside the bracket
     unsigned int *listA[2], *listB, *listC0, *listC1, *listCR;
@@ -131,9 +139,9 @@ __device__ __forceinline__ bool flag_set(uint8_t *flags, size_t p, unsigned int 
     unsigned int old = *word;
     for (;;) {
         const unsigned int b = (old >> shift) & 0xffu;
-        const unsigned int cur = ((b >> 4) == stamp) ? (b & 0xfu) : 0u;
+        const unsigned int cur = ((b >> FLAG_BITS) == stamp) ? (b & FLAG_MASK) : 0u;
         if (cur & bit) return false;
-        const unsigned int nb = (stamp << 4) | cur | bit;
+        const unsigned int nb = (stamp << FLAG_BITS) | cur | bit;
         const unsigned int nw = (old & ~(0xffu << shift)) | (nb << shift);
         const unsigned int seen = atomicCAS(word, old, nw);
         if (seen == old) return true;
@@ -146,7 +154,7 @@ __device__ __forceinline__ bool flag_set(uint8_t *flags, size_t p, unsigned int 
 __device__ __forceinline__ bool flag_has(const uint8_t *flags, size_t p, unsigned int stamp, unsigned int bit)
 {
     const unsigned int b = flags[p];
-    return (b >> 4) == stamp && (b & bit) != 0;
+    return (b >> FLAG_BITS) == stamp && (b & bit) != 0;
 }
 
 __device__ __forceinline__ unsigned int list_len(const unsigned int *count, unsigned int cap)
@@ -530,6 +538,7 @@ sp_cand2_kernel(const float *__restrict__ img, int H, int W, LacParams prm, Spar
         float s_c, nz_c;
         const float sp = warp_sprime(img, H, W, y, x, rn2, lane, s_c, nz_c);
         if (!(sp > prm.sigclip)) continue;                        // warp-uniform
+        if (lane == 0) flag_set(w.flags, p, stamp, FLAG_S1);
         const float f = warp_fine(img, H, W, y, x, nz_c, lane);
         const float ratio = sp / f;
         if (ratio > prm.objlim && lane == 0) {
@@ -538,55 +547,84 @@ sp_cand2_kernel(const float *__restrict__ img, int H, int W, LacParams prm, Spar
     }
 }
 
-// one growth step: for every listed pixel r and each of its 9 neighbours q (dilate3 copies its
-// input in the 1-pixel frame, so a frame pixel q only counts for q == r), test
-// good(q) & s'(q) > thr; warp per (r, q)
-template <int STEP>
+// The two growth steps.  For every listed pixel r and each of its 9 neighbours q (dilate3 copies
+// its input in the 1-pixel frame, so a frame pixel q only counts for q == r) the reference tests
+// good(q) & s'(q) > thr.  No kernel below lets a racy flag read steer a warp collective: the
+// per-neighbour kernels are thread-per-item, the warp-per-pixel kernel reads no flags.
+__device__ __forceinline__ bool grow_neighbour(unsigned int r, int k, int H, int W, size_t &q, bool &centre)
+{
+    const int ry = (int)(r / (unsigned int)W), rx = (int)(r - (unsigned int)ry * (unsigned int)W);
+    const int qy = ry + k / 3 - 1, qx = rx + k % 3 - 1;
+    if (qy < 0 || qy >= H || qx < 0 || qx >= W) return false;
+    centre = (k == 4);
+    if (!centre && (qy == 0 || qy == H - 1 || qx == 0 || qx == W - 1)) return false;
+    q = (size_t)qy * W + qx;
+    return true;
+}
+
+// a pixel has passed growth step 2: count it, mark it, list it (once per LACosmic call)
+__device__ __forceinline__ void grow_accept(uint8_t *__restrict__ crmask, size_t q, const SparseWork &w, int iter,
+                                            long long *info)
+{
+    atomicAdd((unsigned long long *)&info[INFO_NCR + iter], 1ull);
+    if (crmask[q] == 0) {
+        crmask[q] = 1;
+        list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
+    }
+}
+
 __global__ void __launch_bounds__(128)
-sp_grow_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, uint8_t *__restrict__ crmask,
-               int H, int W, LacParams prm, SparseWork w, unsigned int stamp, int iter, long long *info)
+sp_grow1_kernel(int H, int W, SparseWork w, unsigned int stamp, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
-    const unsigned int *src = STEP == 1 ? w.listC0 : w.listC1;
-    const unsigned int n = STEP == 1 ? list_len(&w.cnt->nC0, w.capC) : list_len(&w.cnt->nC1, w.capC);
-    const float thr = STEP == 1 ? prm.sigclip : prm.sigcliplow;
-    // the centre pixel passed s' > sigclip already; that implies the step threshold if it is lower
-    const bool centre_implied = STEP == 1 || prm.sigcliplow <= prm.sigclip;
+    const unsigned int total = list_len(&w.cnt->nC0, w.capC) * 9u;          // <= 9 capC: no overflow
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        size_t q;
+        bool centre;
+        if (!grow_neighbour(w.listC0[t / 9u], (int)(t % 9u), H, W, q, centre)) continue;
+        // S1 flags are complete (previous kernel); a member of C0 carries S1 as well
+        if (!flag_has(w.flags, q, stamp, FLAG_S1)) continue;
+        if (flag_set(w.flags, q, stamp, FLAG_C1)) list_push(w.listC1, &w.cnt->nC1, w.capC, (unsigned int)q, info);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sp_grow2a_kernel(const uint8_t *__restrict__ inmask, uint8_t *__restrict__ crmask, int H, int W, LacParams prm,
+                 SparseWork w, unsigned int stamp, int iter, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int total = list_len(&w.cnt->nC1, w.capC) * 9u;
+    // a member of C1 passed good & s' > sigclip; that implies this step's test if sigcliplow is not higher
+    const bool implied = prm.sigcliplow <= prm.sigclip;
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        size_t q;
+        bool centre;
+        if (!grow_neighbour(w.listC1[t / 9u], (int)(t % 9u), H, W, q, centre)) continue;
+        if (inmask && inmask[q]) continue;
+        if (implied && (centre || flag_has(w.flags, q, stamp, FLAG_C1))) {      // C1 flags are complete
+            if (flag_set(w.flags, q, stamp, FLAG_C2)) grow_accept(crmask, q, w, iter, info);
+        } else if (flag_set(w.flags, q, stamp, FLAG_T2)) {
+            list_push(w.listB, &w.cnt->nQ, w.capB, (unsigned int)q, info);      // list Q
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sp_grow2b_kernel(const float *__restrict__ img, uint8_t *__restrict__ crmask, int H, int W, LacParams prm,
+                 SparseWork w, unsigned int stamp, int iter, long long *info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int n = list_len(&w.cnt->nQ, w.capB);
     const int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const float rn2 = lac_rn2(prm);
-    const unsigned int total = n * 9u;                         // n <= capC = N/32: no overflow
-    for (unsigned int t = warp; t < total; t += nwarps) {
-        const unsigned int r = src[t / 9u];
-        const int k = (int)(t % 9u);
-        const int ry = (int)(r / (unsigned int)W), rx = (int)(r - (unsigned int)ry * (unsigned int)W);
-        const int qy = ry + k / 3 - 1, qx = rx + k % 3 - 1;
-        if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
-        const bool centre = (k == 4);
-        if (!centre && (qy == 0 || qy == H - 1 || qx == 0 || qx == W - 1)) continue;
-        const size_t q = (size_t)qy * W + qx;
-        // already accepted through another neighbour: nothing to add
-        if (flag_has(w.flags, q, stamp, STEP == 1 ? FLAG_C1 : FLAG_C2)) continue;
-        if (inmask && inmask[q]) continue;
-        // a member of the source set passed good & s' > sigclip before (c0 for step 1, c1 for
-        // step 2); that implies this step's test if its threshold is not higher
-        bool pass = centre_implied && (centre || flag_has(w.flags, q, stamp, STEP == 1 ? FLAG_C0 : FLAG_C1));
-        if (!pass) {
-            float s_c, nz_c;
-            const float sp = warp_sprime(img, H, W, qy, qx, rn2, lane, s_c, nz_c);
-            pass = sp > thr;
-        }
-        if (!pass || lane != 0) continue;
-        if (STEP == 1) {
-            if (flag_set(w.flags, q, stamp, FLAG_C1)) list_push(w.listC1, &w.cnt->nC1, w.capC, (unsigned int)q, info);
-        } else {
-            if (flag_set(w.flags, q, stamp, FLAG_C2)) {
-                atomicAdd((unsigned long long *)&info[INFO_NCR + iter], 1ull);
-                if (crmask[q] == 0) {
-                    crmask[q] = 1;
-                    list_push(w.listCR, &w.cnt->nCR, w.capCR, (unsigned int)q, info);
-                }
-            }
+    for (unsigned int k = warp; k < n; k += nwarps) {
+        const unsigned int q = w.listB[k];
+        const int qy = (int)(q / (unsigned int)W), qx = (int)(q - (unsigned int)qy * (unsigned int)W);
+        float s_c, nz_c;
+        const float sp = warp_sprime(img, H, W, qy, qx, rn2, lane, s_c, nz_c);
+        if (sp > prm.sigcliplow && lane == 0) {
+            if (flag_set(w.flags, q, stamp, FLAG_C2)) grow_accept(crmask, q, w, iter, info);
         }
     }
 }
@@ -596,7 +634,7 @@ __global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt, unsi
     for (int i = threadIdx.x; i < n; i += blockDim.x) info[i] = (i == INFO_ACTIVE) ? 1 : 0;
     if (threadIdx.x == 0) {
         cnt->nA[0] = cnt->nA[1] = cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nCR = 0;
-        cnt->bg_valid = bg_valid; cnt->pad = 0;
+        cnt->bg_valid = bg_valid; cnt->nQ = 0;
         cnt->clean_lo = cnt->clean_hi = 0;
     }
 }
@@ -610,7 +648,7 @@ __global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt
     cnt->nA[(iter + 1) & 1] = 0;           // destination of the next iteration's rescan
     cnt->clean_lo = cnt->clean_hi;         // CR-list entries [clean_lo, clean_hi) are new in this iteration
     cnt->clean_hi = cnt->nCR < 0xffffffffu ? cnt->nCR : 0xffffffffu;
-    cnt->nB = cnt->nC0 = cnt->nC1 = 0;
+    cnt->nB = cnt->nC0 = cnt->nC1 = cnt->nQ = 0;
 }
 
 // medmask cleaning: a flagged pixel becomes the lower median of the unflagged, unmasked pixels of
@@ -701,11 +739,11 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
 {
     const size_t n = (size_t)H * W;
     SparseWork w = carve_sparse(work, n);
-    unsigned int stamp = (unsigned int)(it % 15) + 1;
+    unsigned int stamp = (unsigned int)(it % STAMP_PERIOD) + 1;
     BBX_REQUIRE(ceil_div(H, SCAN_ROWS) <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
     const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
     const int list_blocks = BBX_SM_COUNT * 8, warp_blocks = BBX_SM_COUNT * 16;
-    if (it > 0 && it % 15 == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
+    if (it > 0 && it % STAMP_PERIOD == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {
         if (with_background) {
             sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
@@ -716,8 +754,9 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     } else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);
     sp_cand1_kernel<<<list_blocks, 128, 0, st>>>(img, inmask, H, W, prm, w, it, info);
     sp_cand2_kernel<<<warp_blocks, 128, 0, st>>>(img, H, W, prm, w, stamp, info);
-    sp_grow_kernel<1><<<warp_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
-    sp_grow_kernel<2><<<warp_blocks, 128, 0, st>>>(img, inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_grow1_kernel<<<list_blocks, 128, 0, st>>>(H, W, w, stamp, info);
+    sp_grow2a_kernel<<<list_blocks, 128, 0, st>>>(inmask, crmask, H, W, prm, w, stamp, it, info);
+    sp_grow2b_kernel<<<warp_blocks, 128, 0, st>>>(img, crmask, H, W, prm, w, stamp, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
     if (it == 0) sp_clean_kernel<true><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
     else sp_clean_kernel<false><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);

@@ -559,16 +559,16 @@ hos_stats_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 // distributed shared memory and combined in rank order (deterministic)
 // ============================================================================================
 #define VSTD_CLUSTER 8
-#define VSTD_THREADS 1024
+#define VSTD_THREADS 512
 #define VSTD_MAXV 6          // strip width <= 192 (174 unbinned, 87 binned)
-#define VSTD_LIST_PER_WARP 320
+#define VSTD_LIST_PER_WARP 640
 #define VSTD_CORE_SIGMA 2.25
+#define VSTD_SAMPLE_ROWS 8
 
 struct VstdPartial { double s, q, cs, cq; long long n, cn; int ovf, pad; };
 
 // u16 -> f32 through the exponent trick (2^23 + n) - 2^23: exact, and off the quarter-rate
-// conversion unit, which the float32 <-> float64 conversions below need (the first version of
-// this kernel walked the strip up to 7 times with ~13 XU operations per value: ncu XU 74 %)
+// conversion unit, which the float32 <-> float64 conversions below need
 template <typename T> __device__ __forceinline__ float raw_to_f32_alu(T v);
 template <> __device__ __forceinline__ float raw_to_f32_alu<uint16_t>(uint16_t v)
 {
@@ -576,33 +576,27 @@ template <> __device__ __forceinline__ float raw_to_f32_alu<uint16_t>(uint16_t v
 }
 template <> __device__ __forceinline__ float raw_to_f32_alu<float>(float v) { return v; }
 
+// The strip is walked ONCE in the common case.  A warp owns rows rank*rows_per_cta + warp,
+// +nwarps, ...; a lane holds the <= 6 strip values of its row in registers (the next row's
+// loads are in flight during the arithmetic).  Every clip iteration needs (count, sum, sum of
+// squares) inside the current interval; the population variance follows as q/n - mean^2 (the
+// values are overscan residuals of a few e-, so there is no cancellation to speak of).
+//
+// The single walk accumulates the moments of all valid values (the first evaluation), the
+// moments of the values inside a core band, and parks every value outside the band (a few per
+// cent) in a per-warp shared-memory list, in a deterministic order.  The band is
+// mean +- 2.25 sd of a once-clipped sample of VSTD_SAMPLE_ROWS rows spread over the channel
+// (float32 bounds, so the band test is a float32 comparison).  As long as the clip bounds of
+// an evaluation contain the band (they are 3 sigma bounds of the whole strip, so they do unless
+// the sample is unrepresentative) the evaluation is "band moments + the listed values inside
+// the bounds"; otherwise, or if a list overflows, it walks the strip again.
 template <typename T>
-__device__ __forceinline__ bool vstd_value(T rawv, float gn, double fv, bool in_hos, double dlevel, double &xd)
-{
-    float x = raw_to_f32_alu<T>(rawv) * gn;
-    x = sub_f64(x, fv);
-    if (in_hos) x = sub_f64(x, dlevel);
-    xd = (double)x;
-    return vos_valid(x);
-}
-
-// Each warp walks rows rank*rows_per_cta + warp, +nwarps, ...; a lane holds the <= 8 strip
-// values of its row in registers, so one pass issues all loads of a row at once.  Every clip
-// iteration needs (count, sum, sum of squares) inside the current interval; the population
-// variance follows as q/n - mean^2 (the values are overscan residuals of a few e-, so there is
-// no cancellation to speak of).
-// Only the first two evaluations walk the strip: the second one also parks every value outside
-// the core band mean0 +- 2.25 sd0 (a few per cent) in a per-warp shared-memory list, in a
-// deterministic order, and accumulates the moments of the band.  As long as the later clip
-// bounds contain the band (they are 3 sigma bounds, so they do unless sd0 was inflated by more
-// than a third) an evaluation is "band moments + the listed values inside the bounds".
-template <typename T>
-__global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS)
+__global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS, 1)
 vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
                const double *__restrict__ vos_fit, const double *__restrict__ dlevel_arr,
                double *__restrict__ out_std)
 {
-    extern __shared__ double s_list[];                       // [warps][VSTD_LIST_PER_WARP]
+    extern __shared__ float s_list[];                        // [warps][VSTD_LIST_PER_WARP]
     cg::cluster_group cluster = cg::this_cluster();
     const int ch = blockIdx.y, r = ch / g.nx, c = ch - r * g.nx;
     const int rank = (int)cluster.block_rank();
@@ -614,19 +608,20 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     const double dlevel = dlevel_arr[ch];
     const int hos_t0 = ((r == 0) ? g.hos_y0_bot : g.hos_y0_top) - r * g.dy;
     const T *base = raw + (size_t)(r * g.dy) * g.W + (size_t)c * g.dx + g.vos_x0;
-    double *mylist = s_list + (size_t)warp * VSTD_LIST_PER_WARP;
+    float *mylist = s_list + (size_t)warp * VSTD_LIST_PER_WARP;
     int nlist = 0;                                           // entries in this warp's list (warp-uniform)
 
     __shared__ VstdPartial wpart[VSTD_THREADS / 32];   // per-warp partial sums
     __shared__ VstdPartial part[2];     // this CTA's sums; double-buffered slot read by the other CTAs
     __shared__ VstdPartial total;       // sums of the whole cluster
+    __shared__ float s_band[2];
     int phase = 0;
 
     struct Mom { double S, Q; long long N; };
     double CS = 0.0, CQ = 0.0;          // band moments of the whole channel
     long long CN = 0;
     bool use_list = false;
-    double clo = 0.0, chi = 0.0;
+    float clo = 0.f, chi = 0.f;         // core band (float32 values; empty if clo > chi)
 
     // all fields through the fixed xor-butterfly: deterministic
     auto warp_reduce = [&](VstdPartial &v) {
@@ -660,21 +655,85 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         phase ^= 1;      // the next publish uses the other slot: no remote read can be overtaken
     };
 
-    // one pass over this CTA's rows: moments of the valid values inside [lo, hi]; with BUILD
-    // also the band moments and the list of the values outside the band
-    auto strip_pass = [&](double lo, double hi, bool closed_nan_ok, bool build, Mom &m) {
-        double s = 0.0, q = 0.0, cs = 0.0, cq = 0.0;
-        long long n = 0, cn = 0;
-        int ovf = 0;
-        T v[VSTD_MAXV], vn[VSTD_MAXV];
-        auto load_row = [&](int trow, T *dst) {
-            const T *p = base + (size_t)trow * g.W;
+    auto load_row = [&](int trow, T *dst) {
+        const T *p = base + (size_t)trow * g.W;
+#pragma unroll
+        for (int k = 0; k < VSTD_MAXV; k++) {
+            const int j = lane + 32 * k;
+            dst[k] = (j < g.vos_w) ? p[j] : (T)0;
+        }
+    };
+    // the overscan-subtracted value of one strip pixel (float32, as the reference holds it)
+    auto value = [&](T rawv, double fv, bool in_hos) {
+        float x = raw_to_f32_alu<T>(rawv) * gn;
+        x = sub_f64(x, fv);
+        if (in_hos) x = sub_f64(x, dlevel);
+        return x;
+    };
+
+    // which of this lane's VSTD_MAXV strip columns exist (bit k: column lane + 32 k < vos_w)
+    unsigned int kmask = 0;
+#pragma unroll
+    for (int k = 0; k < VSTD_MAXV; k++) kmask |= (lane + 32 * k < g.vos_w) ? (1u << k) : 0u;
+
+    // ---- core band from a once-clipped sample: VSTD_SAMPLE_ROWS rows spread over the channel,
+    // one warp per row, combined in warp order (every CTA of the cluster computes the same numbers)
+    {
+        __shared__ double s_smp[VSTD_SAMPLE_ROWS][3];
+        __shared__ double s_lohi[2];
+        float xs[VSTD_MAXV];
+        bool ok[VSTD_MAXV];
+        if (warp < VSTD_SAMPLE_ROWS) {
+            const int trow = (int)(((long long)g.dy * (2 * warp + 1)) / (2 * VSTD_SAMPLE_ROWS));
+            T v[VSTD_MAXV];
+            load_row(trow, v);
+            const double fv = fitrow[trow];
+            const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
-                const int j = lane + 32 * k;
-                dst[k] = (j < g.vos_w) ? p[j] : (T)0;
+                xs[k] = value(v[k], fv, in_hos);
+                ok[k] = ((kmask >> k) & 1u) && vos_valid(xs[k]);
             }
-        };
+        }
+        double lo = -INFINITY, hi = INFINITY;
+        for (int pass = 0; pass < 2; pass++) {
+            if (warp < VSTD_SAMPLE_ROWS) {
+                double sm = 0.0, qm = 0.0, nm = 0.0;
+#pragma unroll
+                for (int k = 0; k < VSTD_MAXV; k++) {
+                    const double xd = (double)xs[k];
+                    if (ok[k] && xd >= lo && xd <= hi) { nm += 1.0; sm += xd; qm += xd * xd; }
+                }
+                sm = warp_sum(sm); qm = warp_sum(qm); nm = warp_sum(nm);
+                if (lane == 0) { s_smp[warp][0] = nm; s_smp[warp][1] = sm; s_smp[warp][2] = qm; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double nm = 0.0, sm = 0.0, qm = 0.0;
+                for (int t = 0; t < VSTD_SAMPLE_ROWS; t++) { nm += s_smp[t][0]; sm += s_smp[t][1]; qm += s_smp[t][2]; }
+                const double mean = nm > 0.0 ? sm / nm : 0.0;
+                const double sd = nm > 0.0 ? sqrt(fmax(qm / nm - mean * mean, 0.0)) : -1.0;
+                if (pass == 0) { s_lohi[0] = mean - 3.0 * sd; s_lohi[1] = mean + 3.0 * sd; }
+                else {
+                    // empty band (clo > chi) if the sample is unusable: every value goes to the lists
+                    s_band[0] = sd > 0.0 ? (float)(mean - VSTD_CORE_SIGMA * sd) : 1.0f;
+                    s_band[1] = sd > 0.0 ? (float)(mean + VSTD_CORE_SIGMA * sd) : 0.0f;
+                }
+            }
+            __syncthreads();
+            lo = s_lohi[0]; hi = s_lohi[1];
+        }
+    }
+    clo = s_band[0]; chi = s_band[1];
+
+    // The walk over this CTA's rows.  BUILD (the first walk): moments of the values inside the
+    // band, every other valid value into the list -- the moments of ALL valid values are then
+    // "band + whole list".  Otherwise: moments of the valid values inside [lo, hi].
+    auto strip_pass = [&](double lo, double hi, bool closed_nan_ok, bool build, Mom &m) {
+        double s = 0.0, q = 0.0;
+        int n = 0;
+        int ovf = 0;
+        T v[VSTD_MAXV], vn[VSTD_MAXV];
         if (row0 + warp < row1) load_row(row0 + warp, v);
         for (int trow = row0 + warp; trow < row1; trow += nwarps) {
             if (trow + nwarps < row1) load_row(trow + nwarps, vn);     // next row in flight during the arithmetic
@@ -682,28 +741,31 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
             const bool in_hos = trow >= hos_t0 && trow < hos_t0 + g.hos_rows;
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) {
-                const int j = lane + 32 * k;
-                if (32 * k >= g.vos_w) break;                 // warp-uniform
-                double xd = 0.0;
-                const bool valid = (j < g.vos_w) && vstd_value<T>(v[k], gn, fv, in_hos, dlevel, xd);
-                const bool in = valid && (closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi));
-                if (in) { n++; s += xd; q += xd * xd; }
+                const float x = value(v[k], fv, in_hos);
+                const double xd = (double)x;
+                const float ax = fabsf(x);
+                const bool valid = ((kmask >> k) & 1u) && ax > MASKED_ZERO_TOL && ax <= 3.402823466e+38f;
                 if (build) {
-                    const bool core = valid && xd >= clo && xd <= chi;
-                    if (core) { cn++; cs += xd; cq += xd * xd; }
-                    const bool tail = valid && !core;
-                    const unsigned int ballot = __ballot_sync(0xffffffffu, tail);
+                    const bool core = valid && x >= clo && x <= chi;
+                    const double xm = core ? xd : 0.0;
+                    n += core; s += xm; q = fma(xm, xm, q);
+                    const unsigned int ballot = __ballot_sync(0xffffffffu, valid && !core);
                     if (ballot) {
                         const int pos = nlist + __popc(ballot & ((1u << lane) - 1u));
-                        if (tail) { if (pos < VSTD_LIST_PER_WARP) mylist[pos] = xd; else ovf = 1; }
+                        if (valid && !core) { if (pos < VSTD_LIST_PER_WARP) mylist[pos] = x; else ovf = 1; }
                         nlist += __popc(ballot);
                     }
+                } else {
+                    const bool in = valid && (closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi));
+                    const double xm = in ? xd : 0.0;
+                    n += in; s += xm; q = fma(xm, xm, q);
                 }
             }
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) v[k] = vn[k];
         }
-        exchange(s, q, n, cs, cq, cn, ovf, m, build);
+        if (build) exchange(0.0, 0.0, 0, s, q, (long long)n, ovf, m, true);
+        else exchange(s, q, (long long)n, 0.0, 0.0, 0, 0, m, false);
     };
 
     // band moments + the listed values inside [lo, hi]
@@ -711,22 +773,24 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         double s = 0.0, q = 0.0;
         long long n = 0;
         for (int j = lane; j < nlist; j += 32) {
-            const double xd = mylist[j];
+            const double xd = (double)mylist[j];
             const bool in = closed_nan_ok ? (!(xd < lo) && !(xd > hi)) : (xd >= lo && xd <= hi);
-            if (in) { n++; s += xd; q += xd * xd; }
+            if (in) { n++; s += xd; q = fma(xd, xd, q); }
         }
         exchange(s, q, n, 0.0, 0.0, 0, 0, m, false);
         m.S += CS; m.Q += CQ; m.N += CN;
     };
 
     auto eval = [&](double lo, double hi, bool closed_nan_ok, Mom &m) {
-        if (use_list && lo <= clo && hi >= chi) list_pass(lo, hi, closed_nan_ok, m);
+        if (use_list && clo <= chi && lo <= (double)clo && hi >= (double)chi) list_pass(lo, hi, closed_nan_ok, m);
+        else if (use_list && clo > chi) list_pass(lo, hi, closed_nan_ok, m);      // empty band: the lists hold everything
         else strip_pass(lo, hi, closed_nan_ok, false, m);
     };
 
     double LO = -INFINITY, HI = INFINITY, flo = NAN, fhi = NAN;
     Mom m;
-    strip_pass(LO, HI, false, false, m);
+    strip_pass(LO, HI, false, true, m);       // band moments + lists
+    eval(LO, HI, false, m);                   // all valid values: band + whole lists (or a second walk)
     for (int it = 0; it < 5 && m.N > 0; it++) {
         const double mean = m.S / (double)m.N;
         const double var = fmax(m.Q / (double)m.N - mean * mean, 0.0);
@@ -736,13 +800,7 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         LO = fmax(LO, flo);
         HI = fmin(HI, fhi);
         Mom m2;
-        if (it == 0) {
-            clo = mean - VSTD_CORE_SIGMA * sd;
-            chi = mean + VSTD_CORE_SIGMA * sd;
-            strip_pass(LO, HI, false, true, m2);
-        } else {
-            eval(LO, HI, false, m2);
-        }
+        eval(LO, HI, false, m2);
         const bool done = (m2.N == m.N);
         m = m2;
         if (done) break;
@@ -953,7 +1011,7 @@ extern "C" int bbx_vos_std(const void *raw, int raw_type, const bbx_geom *g, con
     ChanF32 gn; fill_chan_f32(gn, gain_h);
     dim3 grid(VSTD_CLUSTER, BBX_NCHAN);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(double) * (VSTD_THREADS / 32) * VSTD_LIST_PER_WARP;
+    const size_t smem = sizeof(float) * (VSTD_THREADS / 32) * VSTD_LIST_PER_WARP;
     if (raw_type == BBX_RAW_U16) {
         BBX_CUDA(cudaFuncSetAttribute(vos_std_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         vos_std_kernel<uint16_t><<<grid, VSTD_THREADS, smem, s>>>((const uint16_t *)raw, *g, gn, vos_fit, dlevel, out_std);

@@ -19,7 +19,7 @@
 #include <stdlib.h>
 #include "bbx_common.cuh"
 
-struct XtalkCoef { double c[16][16]; };   // [source][victim], kernel parameter (constant bank)
+struct XtalkCoef { double c[16][16]; };   // [victim][source] (the order the dot products walk), kernel parameter (constant bank)
 
 // PX = 4 (float4 + 32-bit mask words), 2 or 1 pixels per thread and channel.  Only the pixel
 // values and two 64-bit flag words are kept in registers; the masked source value
@@ -76,9 +76,9 @@ xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int x
                 // same-half sources first (quadrant q=0 / q=3), then the mirrored half
                 double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[same0 + s][vch], a);
+                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[vch][same0 + s], a);
 #pragma unroll
-                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[other0 + s][vch], b);
+                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[vch][other0 + s], b);
                 double corr = 0.0 + a;
                 corr = corr + b;
                 corr = corr * (((vic_ok >> (vch * PX + p)) & 1ull) ? 1.0 : 0.0);
@@ -98,7 +98,8 @@ xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int x
 
 #define XT_TILE 128          // tile positions per CTA pass (= threads per CTA)
 
-__global__ void __launch_bounds__(XT_TILE)
+template <int MINB>
+__global__ void __launch_bounds__(XT_TILE, MINB)
 xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int xsc, XtalkCoef k,
                   uint32_t bits_src_bad, uint32_t bit_edge)
 {
@@ -108,7 +109,11 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
     const long long ngroups = (long long)ysc * gpr;
     const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
     const int g4 = threadIdx.x & 31, c0 = threadIdx.x >> 5;    // load role: group in tile, first channel
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // one tile per CTA (no tile loop: the compiler would hoist the 256 loop-invariant coefficient
+    // loads out of it into registers; this way they stay LDCU.128 next to their DFMAs)
+    {
+        const long long t = blockIdx.x;
+        if (t >= ntiles) return;
         // ---- stage: thread (c0, g4) moves group g4 of channels c0, c0+4, c0+8, c0+12
         const long long G = t * (XT_TILE / 4) + g4;
         const bool live = G < ngroups;
@@ -155,9 +160,9 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
                 // same-half sources first (quadrant q=0 / q=3), then the mirrored half
                 double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[same0 + s][vch], a);
+                for (int s = 0; s < 8; s++) a = fma(S[same0 + s], k.c[vch][same0 + s], a);
 #pragma unroll
-                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[other0 + s][vch], b);
+                for (int s = 0; s < 8; s++) b = fma(S[other0 + s], k.c[vch][other0 + s], b);
                 double corr = 0.0 + a;
                 corr = corr + b;
                 corr = corr * (((vic_ok >> vch) & 1u) ? 1.0 : 0.0);
@@ -173,7 +178,6 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
                 *reinterpret_cast<float4 *>(img + off[i]) = *reinterpret_cast<const float4 *>(&tile[c][g4 * 4]);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -183,15 +187,23 @@ extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysiz
     BBX_REQUIRE(img && coeffs_h && bits, "bbx_xtalk: null argument");
     BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_xtalk: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
     XtalkCoef k;
-    for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[s][v] = coeffs_h[s * 16 + v];
+    for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[v][s] = coeffs_h[s * 16 + v];
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
     const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
     if (px4 && getenv("BBX_XTALK_PX") == nullptr) {
         const long long ngroups = (long long)ysize_chan * (xsize_chan / 4);
         const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
-        const int blocks = (int)(ntiles < (long long)BBX_SM_COUNT * 32 ? ntiles : (long long)BBX_SM_COUNT * 32);
-        xtalk_tile_kernel<<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        BBX_REQUIRE(ntiles < 2147483647LL, "bbx_xtalk: frame too large");
+        const int blocks = (int)ntiles;
+        // resident CTAs per SM the register allocation is capped for: 6 (80 registers, no spills);
+        // BBX_XTALK_MINB=7|8 selects the 72- / 64-register builds (development switch)
+        const char *mb = getenv("BBX_XTALK_MINB");
+        const int minb = mb ? atoi(mb) : 6;
+        if (minb == 8) xtalk_tile_kernel<8><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        else if (minb == 7) xtalk_tile_kernel<7><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        else if (minb == 5) xtalk_tile_kernel<5><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        else xtalk_tile_kernel<6><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
         BBX_CHECK_LAUNCH("xtalk_tile_kernel");
         return 0;
     }

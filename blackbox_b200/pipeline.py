@@ -13,6 +13,8 @@ more rounds) and returns the header values.
 Frames are independent, so a night batch shards one frame per GPU (``shard_frames``); nothing
 is exchanged between ranks.
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -34,8 +36,22 @@ class FrameResult:
 
 
 class FramePipeline:
+    """One frame after the other through the device-resident chain.
+
+    The chain is enqueued in two halves: stage A (overscan statistics and fits, a dozen small
+    latency-bound kernels, plus one device-to-host copy of the fit flags and column statistics)
+    and stage B (fused per-pixel pass, mask morphology, LACosmic, crosstalk: the HBM-bound
+    kernels).  Between them the host looks at the flags (``stage_a_resolve``) and evaluates the
+    FITPACK spline for the few channels that need it.  ``BatchReducer`` runs stage A of the next
+    frames ahead of stage B of the current one so the GPU never waits for the host.
+
+    ``use_graphs``: every stage is captured into a CUDA graph the second time it is enqueued
+    with the same (raw, image, mask) buffers and replayed from then on -- one launch call per
+    stage instead of ~60 per frame.
+    """
+
     def __init__(self, tel, raw_shape, mbias=None, mflat=None, bpm=None, coeffs=None, niter=None,
-                 xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True):
+                 xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True, use_graphs=False):
         self.tel = tel
         self.device = device if device is not None else R._device()
         self.geom = Geometry.from_raw_shape(tuple(raw_shape), xbin=xbin, ybin=ybin, tel=tel)
@@ -56,50 +72,158 @@ class FramePipeline:
         self.crmask = torch.empty((RH, RW), dtype=torch.uint8, device=dev)
         self.means = torch.zeros(2, dtype=torch.float64, device=dev)      # BIASMEAN, RDNOISE
         self.ncosmic = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._flags_host = torch.zeros(2 * self.geom.nchans, dtype=torch.uint8).pin_memory()
+        # pinned status words of stage B: [0:4] mask morphology (int32), [8:16] LACosmic (int64)
+        self._status_host = torch.zeros(16, dtype=torch.uint8).pin_memory()
+        self._ev_a = torch.cuda.Event()
+        self._ev_b = torch.cuda.Event()
         self._raw = None
         self._out = None
         self._spline_cols = 0
+        self.stage_events = None       # dict stage -> [(start, end) CUDA events] when timing is on
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}              # (stage, buffer pointers) -> CUDAGraph | 'seen' | 'eager'
+        self.graph_replays = 0
+
+    # ---------------------------------------------------------------------------------------
+    def enable_stage_timing(self, on=True):
+        """Record a pair of CUDA events around every stage of the chain on the launching stream
+        (bench.py reads them after its timed region; ``stage_times_ms`` averages them)."""
+        self.stage_events = {} if on else None
+
+    def stage_times_ms(self):
+        """Mean device time per stage over the recorded frames (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in (self.stage_events or {}).items():
+            out[name] = (sum(a.elapsed_time(b) for a, b in evs) / len(evs), len(evs))
+        return out
+
+    def _run(self, name, key, fn):
+        """Run one stage on the current stream: eagerly, or (``use_graphs``) as a CUDA graph
+        captured on the second use of the same buffers; with stage timing on, between a pair of
+        CUDA events."""
+        timing = self.stage_events is not None
+        if timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        g = self._graphs.get((name, key)) if self.use_graphs else 'eager'
+        if g is None:
+            fn()
+            self._graphs[(name, key)] = 'seen'
+        elif g == 'seen':
+            graph = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                    fn()
+            except Exception:                          # not capturable here: stay eager for this stage
+                self._graphs[(name, key)] = 'eager'
+                torch.cuda.synchronize()
+                with torch.cuda.stream(cur):
+                    fn()
+            else:
+                self._graphs[(name, key)] = graph
+                graph.replay()
+                self.graph_replays += 1
+        elif g == 'eager':
+            fn()
+        else:
+            g.replay()
+            self.graph_replays += 1
+        if timing:
+            e1.record()
+            self.stage_events.setdefault(name, []).append((e0, e1))
 
     # ---------------------------------------------------------------------------------------
     def _gain_for(self, raw_t):
         return self.gain if R._raw_type(raw_t) == 0 else None
 
-    def _overscan(self, raw_t):
-        """Overscan statistics + fits on the device, then the one host round trip."""
+    def stage_a_enqueue(self, raw_t):
+        """Stage A on the current stream: overscan kernels, header means, and the copy of the
+        fit flags / column statistics into the pinned mirror of the overscan state."""
         st = self.st
-        R.overscan_enqueue(raw_t, self.geom, self.tel, gain=self._gain_for(raw_t), state=st)
-        flags = torch.cat([st.need_spline.any(dim=1).to(torch.uint8),
-                           (st.fit_status != 0).to(torch.uint8)])
-        self._flags_host.copy_(flags, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        f = self._flags_host.numpy()
-        n = self.geom.nchans
+
+        def body():
+            R.overscan_enqueue(raw_t, self.geom, self.tel, gain=self._gain_for(raw_t), state=st)
+            call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
+            st.fetch_async()
+
+        if st._pinned is None:
+            st._pinned = torch.empty(st._host_bytes, dtype=torch.uint8).pin_memory()
+        self._run('overscan', raw_t.data_ptr(), body)
+        self._ev_a.record()
+
+    def stage_a_resolve(self):
+        """The one host round trip of the chain: wait for stage A, read the flags, evaluate the
+        spline for the channels that need it and patch the device overscan vector (on the
+        current stream)."""
+        self._ev_a.synchronize()
+        st = self.st
         self._spline_cols = 0
-        if f[n:].any() or f[:n].any():
-            self._spline_cols = R.overscan_resolve_spline(st, strict=False)
-        call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
+        if st.host('need_spline').any() or st.host('fit_status').any():
+            self._spline_cols = R.overscan_resolve_spline(st, strict=False, fetched=True)
+
+    def _overscan(self, raw_t):
+        self.stage_a_enqueue(raw_t)
+        self.stage_a_resolve()
 
     def _rest(self, raw_t, out_img, out_mask, dense_morph=False, lac_mode=R.LAC_LAZY):
         tel, geom = self.tel, self.geom
         RH, RW = geom.red_shape
-        s = R._stream()
-        R.apply_enqueue(raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias,
-                        mflat=self.mflat, bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
-                        mwork=None if dense_morph else self.mwork)
-        R.mask_morph_enqueue(out_mask, tel, self.mwork, count_objects=self.count_objects,
-                             sparse=not dense_morph)
+        key = (raw_t.data_ptr(), out_img.data_ptr(), out_mask.data_ptr())
+        if dense_morph or lac_mode != R.LAC_LAZY:
+            key = None                                   # the rare redo path stays eager
+
+        def run(name, fn):
+            if key is None:
+                fn()
+            else:
+                self._run(name, key, fn)
+
+        run('apply', lambda: R.apply_enqueue(
+            raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias, mflat=self.mflat,
+            bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
+            mwork=None if dense_morph else self.mwork))
+        run('mask_morph', lambda: R.mask_morph_enqueue(
+            out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=not dense_morph))
         if dense_morph:
             R.mask_morph_finish(out_mask, tel, self.mwork, sparse=False)
         if self.niter > 0:
-            R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
-                               get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
-                               self.niter, self.lwork, readnoise_dev=self.means[1:], mode=lac_mode)
             bit = int(get_par(set_bb.mask_value, tel)['cosmic ray'])
-            call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW, int(lac_mode),
-                 R._ptr(self.lwork.buf), R._ptr(self.mwork.labels), R._ptr(self.ncosmic), s)
+
+            def lac():
+                R.lacosmic_enqueue(out_img, out_mask, self.crmask, get_par(set_bb.sigclip, tel),
+                                   get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel), 0.0,
+                                   self.niter, self.lwork, readnoise_dev=self.means[1:], mode=lac_mode)
+
+            def lac_finish():
+                call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW, int(lac_mode),
+                     R._ptr(self.lwork.buf), R._ptr(self.mwork.labels), R._ptr(self.ncosmic), R._stream())
+
+            run('lacosmic', lac)
+            run('lacosmic_finish', lac_finish)
+
+        def tail():
+            if self.coeffs is not None:
+                R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
+
+        def status():
+            self._status_host[0:4].copy_(self.mwork.status.view(torch.uint8)[0:4], non_blocking=True)
+            if self.niter > 0:
+                self._status_host[8:16].copy_(self.lwork.info.view(torch.uint8)[16:24], non_blocking=True)
+
         if self.coeffs is not None:
-            R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
+            run('xtalk', tail)
+        run('status', status)
+
+    def stage_b_enqueue(self, raw_t, out_img, out_mask):
+        """Stage B on the current stream (which must be ordered after stage A and the spline
+        patch): everything from the fused per-pixel pass to the crosstalk correction, then the
+        status words into pinned memory."""
+        self._rest(raw_t, out_img, out_mask)
+        self._ev_b.record()
+        self._raw, self._out = raw_t, (out_img, out_mask)
+        return out_img, out_mask
 
     def enqueue(self, raw_t, out_img=None, out_mask=None):
         """Run the overscan stage and enqueue the rest of the chain for one raw frame (uint16
@@ -110,9 +234,7 @@ class FramePipeline:
         if out_mask is None:
             out_mask = torch.empty((RH, RW), dtype=torch.uint8, device=self.device)
         self._overscan(raw_t)
-        self._rest(raw_t, out_img, out_mask)
-        self._raw, self._out = raw_t, (out_img, out_mask)
-        return out_img, out_mask
+        return self.stage_b_enqueue(raw_t, out_img, out_mask)
 
     def enqueue_status(self, host_slot):
         """Enqueue a copy of the frame's status (hole filling unconverged | lazy LACosmic
@@ -126,13 +248,15 @@ class FramePipeline:
 
     # ---------------------------------------------------------------------------------------
     def finish(self, fill_header=True):
-        """Synchronise, verify the device status of the last enqueued frame and return its
+        """Wait for stage B of the last enqueued frame, verify its device status and return its
         FrameResult."""
         st = self.st
         out_img, out_mask = self._out
         redo = False
-        morph_bad = int(self.mwork.status[0].item()) != 0
-        lac_status = int(self.lwork.info[2].item()) if self.niter > 0 else 0
+        self._ev_b.synchronize()
+        sh = self._status_host.numpy()
+        morph_bad = int(sh[0:4].view(np.int32)[0]) != 0
+        lac_status = int(sh[8:16].view(np.int64)[0]) if self.niter > 0 else 0
         if morph_bad or lac_status != 0:
             # the sparse mask morphology overflowed / did not converge (the mask LACosmic saw was
             # not final) or the lazy LACosmic needs the background level / its dense twin: redo
@@ -175,15 +299,22 @@ def shard_frames(nframes, rank, world_size):
 
 
 class BatchReducer:
-    """Reduce a batch of raw frames with ``depth`` FramePipelines ping-ponging on their own CUDA
-    streams: while the host waits for the overscan flags of one frame (the single round trip of
-    the chain) and enqueues its remaining kernels, the GPU is busy with the other frame, so the
-    device never idles on the host.  Results are identical to running the frames one by one."""
+    """Reduce a batch of raw frames with ``depth`` FramePipelines in flight.
 
-    def __init__(self, tel, raw_shape, depth=2, **pipeline_kwargs):
-        self.depth = int(depth)
+    Software pipeline over the frames (host order): stage A of frame k+1 is enqueued on a
+    high-priority stream BEFORE the host waits for stage A of frame k, looks at its flags,
+    evaluates the spline where needed and enqueues stage B of frame k.  The GPU therefore always
+    has stage B of the previous frame (and stage A of the next) to work on while the host is
+    busy, and the small latency-bound overscan kernels run next to the HBM-bound kernels of
+    another frame instead of in front of them.  Results are identical to running the frames one
+    by one."""
+
+    def __init__(self, tel, raw_shape, depth=3, split_priority=True, **pipeline_kwargs):
+        self.depth = max(int(depth), 2)
         self.pipes = [FramePipeline(tel, raw_shape, **pipeline_kwargs) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
+        self.hi_streams = ([torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
+                           if split_priority else self.streams)
 
     def run(self, raws, out_imgs, out_masks, fill_header=False):
         """raws: CUDA tensors; out_imgs / out_masks: at least ``depth`` output tensors, frame k
@@ -195,15 +326,109 @@ class BatchReducer:
             raise ValueError('need at least depth={} output buffers'.format(d))
         results = [None] * n
         caller = torch.cuda.current_stream()
-        for s in self.streams:
+        for s in set(self.streams + self.hi_streams):
             s.wait_stream(caller)
-        for k in range(n + d):
+
+        def stage_a(k):
+            j = k % d
+            if k >= d:                                   # slot j still holds frame k-d
+                with torch.cuda.stream(self.streams[j]):
+                    results[k - d] = self.pipes[j].finish(fill_header=fill_header)
+            with torch.cuda.stream(self.hi_streams[j]):
+                self.hi_streams[j].wait_stream(self.streams[j])
+                self.pipes[j].stage_a_enqueue(raws[k])
+
+        if n:
+            stage_a(0)
+        for k in range(n):
+            j = k % d
+            if k + 1 < n:
+                stage_a(k + 1)
+            with torch.cuda.stream(self.hi_streams[j]):
+                self.pipes[j].stage_a_resolve()
+            with torch.cuda.stream(self.streams[j]):
+                self.streams[j].wait_stream(self.hi_streams[j])
+                self.pipes[j].stage_b_enqueue(raws[k], out_imgs[k % nout], out_masks[k % nout])
+        for k in range(max(n - d, 0), n):
             j = k % d
             with torch.cuda.stream(self.streams[j]):
-                if k >= d:
-                    results[k - d] = self.pipes[j].finish(fill_header=fill_header)
-                if k < n:
-                    self.pipes[j].enqueue(raws[k], out_imgs[k % nout], out_masks[k % nout])
-        for s in self.streams:
+                results[k] = self.pipes[j].finish(fill_header=fill_header)
+        for s in set(self.streams + self.hi_streams):
+            caller.wait_stream(s)
+        return results
+
+    # ---------------------------------------------------------------------------------------
+    def run_host(self, host_raws, host_imgs, host_masks, fill_header=False):
+        """The same batch with HOST buffers on both sides: ``host_raws`` pinned uint16 (or
+        float32) raw frames, ``host_imgs`` / ``host_masks`` pinned float32 / uint8 outputs (rings:
+        frame k goes to index k % len; a ring slot must have been consumed by the caller before
+        its next use comes up).  Host-to-device copies, the chain and device-to-host copies run
+        on their own streams, ``depth`` frames in flight.  Returns the FrameResults; the host
+        outputs of all frames are complete on return."""
+        n, d = len(host_raws), self.depth
+        if n == 0:
+            return []
+        dev = self.pipes[0].device
+        RH, RW = self.pipes[0].geom.red_shape
+        if getattr(self, '_hbuf', None) is None or self._hbuf[0][0].dtype != host_raws[0].dtype:
+            self._hbuf = [(torch.empty(tuple(host_raws[0].shape), dtype=host_raws[0].dtype, device=dev),
+                           torch.empty((RH, RW), dtype=torch.float32, device=dev),
+                           torch.empty((RH, RW), dtype=torch.uint8, device=dev)) for _ in range(d)]
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self._ev_in = [torch.cuda.Event() for _ in range(d)]
+            self._ev_out = [torch.cuda.Event() for _ in range(d)]
+            self._ev_done = [torch.cuda.Event() for _ in range(d)]
+        results = [None] * n
+        caller = torch.cuda.current_stream()
+        for s in set(self.streams + self.hi_streams) | {self._s_in, self._s_out}:
+            s.wait_stream(caller)
+        ni, nm = len(host_imgs), len(host_masks)
+
+        def copy_out(k):
+            j = k % d
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(self._ev_done[j])
+                host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
+                host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
+                self._ev_out[j].record()
+
+        def retire(k):
+            j = k % d
+            with torch.cuda.stream(self.streams[j]):
+                results[k] = self.pipes[j].finish(fill_header=fill_header)
+                if results[k].redo:                      # rare: outputs were re-made after the copy
+                    self._ev_done[j].record()
+            if results[k].redo:
+                copy_out(k)
+
+        def stage_a(k):
+            j = k % d
+            if k >= d:
+                retire(k - d)
+            with torch.cuda.stream(self._s_in):
+                self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
+                self._hbuf[j][0].copy_(host_raws[k], non_blocking=True)
+                self._ev_in[j].record()
+            with torch.cuda.stream(self.hi_streams[j]):
+                self.hi_streams[j].wait_event(self._ev_in[j])
+                self.pipes[j].stage_a_enqueue(self._hbuf[j][0])
+
+        stage_a(0)
+        for k in range(n):
+            j = k % d
+            if k + 1 < n:
+                stage_a(k + 1)
+            with torch.cuda.stream(self.hi_streams[j]):
+                self.pipes[j].stage_a_resolve()
+            with torch.cuda.stream(self.streams[j]):
+                self.streams[j].wait_stream(self.hi_streams[j])
+                self.streams[j].wait_event(self._ev_out[j])          # outputs of frame k-d copied out
+                self.pipes[j].stage_b_enqueue(*self._hbuf[j])
+                self._ev_done[j].record()
+            copy_out(k)
+        for k in range(max(n - d, 0), n):
+            retire(k)
+        self._s_out.synchronize()
+        for s in set(self.streams + self.hi_streams) | {self._s_in, self._s_out}:
             caller.wait_stream(s)
         return results

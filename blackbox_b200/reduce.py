@@ -139,29 +139,48 @@ def _reduced_geometry(shape, tel_):
 # overscan
 # -------------------------------------------------------------------------------------------
 class OverscanState:
-    """Device-resident intermediates of the overscan correction of one frame."""
+    """Device-resident intermediates of the overscan correction of one frame.
+
+    Every field is a view into ONE device buffer; the fields the host needs for the spline
+    decision (``HOST_FIELDS``: they sit at the front of the buffer) travel in a single
+    device-to-host copy into a pinned mirror (``fetch_async`` / ``host``)."""
+
+    HOST_FIELDS = ('fit_status', 'need_spline', 'hos_n', 'hos_mean', 'hos_std', 'oscan')
 
     def __init__(self, geom, device):
         n, dy, nc = geom.nchans, geom.dy, geom.xsize_chan
         f64, f32, i32, u8 = torch.float64, torch.float32, torch.int32, torch.uint8
-        z = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        fields = [('fit_status', (n,), i32), ('need_spline', (n, nc), u8), ('hos_n', (n, nc), i32),
+                  ('hos_mean', (n, nc), f32), ('hos_std', (n, nc), f32), ('oscan', (n, nc), f64),
+                  ('mean_vos', (n, dy), f64), ('vos_fit', (n, dy), f64), ('vos_coef', (n, 8), f64),
+                  ('biasm', (n,), f64), ('vfit_ok', (n,), i32), ('satcnt', (n, 2, nc), i32),
+                  ('dlevel', (n,), f64), ('satcol', (n, nc), u8), ('std_vos', (n,), f64),
+                  ('satlevel', (n,), f64)]
         self.geom = geom
-        self.mean_vos = z((n, dy), f64)
-        self.vos_fit = z((n, dy), f64)
-        self.vos_coef = z((n, 8), f64)
-        self.biasm = z((n,), f64)
-        self.vfit_ok = z((n,), i32)
-        self.satcnt = z((n, 2, nc), i32)
-        self.dlevel = z((n,), f64)
-        self.hos_mean = z((n, nc), f32)
-        self.hos_std = z((n, nc), f32)
-        self.hos_n = z((n, nc), i32)
-        self.satcol = z((n, nc), u8)
-        self.std_vos = z((n,), f64)
-        self.oscan = z((n, nc), f64)
-        self.need_spline = z((n, nc), u8)
-        self.fit_status = z((n,), i32)
-        self.satlevel = z((n,), f64)
+        self._layout = {}
+        off = 0
+        for name, shape, dt in fields:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._layout[name] = (off, nbytes, shape, dt)
+            off = (off + nbytes + 15) // 16 * 16
+            if name == self.HOST_FIELDS[-1]:
+                self._host_bytes = off
+        self.buf = torch.zeros(off, dtype=u8, device=device)
+        for name, (o, nb, shape, dt) in self._layout.items():
+            setattr(self, name, self.buf[o:o + nb].view(dt).view(shape))
+        self._pinned = None
+
+    def fetch_async(self):
+        """Enqueue the copy of the host-side fields into the pinned mirror (current stream)."""
+        if self._pinned is None:
+            self._pinned = torch.empty(self._host_bytes, dtype=torch.uint8).pin_memory()
+        self._pinned.copy_(self.buf[:self._host_bytes], non_blocking=True)
+
+    def host(self, name):
+        """numpy view of a HOST_FIELDS member in the pinned mirror (valid once the stream that
+        ran ``fetch_async`` has been synchronised)."""
+        o, nb, shape, dt = self._layout[name]
+        return self._pinned[o:o + nb].view(dt).view(shape).numpy()
 
 
 def overscan_enqueue(raw_t, geom, tel_, gain=None, data_limit=2000, state=None):
@@ -197,30 +216,35 @@ def overscan_enqueue(raw_t, geom, tel_, gain=None, data_limit=2000, state=None):
     return st
 
 
-def overscan_resolve_spline(st, strict):
+def overscan_resolve_spline(st, strict, fetched=False):
     """Host step: evaluate FITPACK's smoothing spline for the columns that need it (all
-    channels if ``strict``) and patch ``st.oscan``.  Synchronises the current stream.
-    Raises RuntimeError if a polynomial fit had too few points (the reference raises from
-    np.polyfit in that case)."""
-    status = st.fit_status.cpu().numpy()
+    channels if ``strict``) and patch ``st.oscan``.  Unless ``fetched`` (the caller has run
+    ``st.fetch_async()`` and synchronised) this synchronises the current stream.  Returns the
+    number of patched columns.  Raises RuntimeError if a polynomial fit had too few points
+    (the reference raises from np.polyfit in that case)."""
+    if not fetched:
+        st.fetch_async()
+        torch.cuda.current_stream().synchronize()
+    status = st.host('fit_status')
     if status.any():
         raise RuntimeError('horizontal-overscan polynomial fit failed for channel(s) {} '
                            '(too few valid columns)'.format(
                                [int(i) + 1 for i in np.nonzero(status)[0]]))
-    need = st.need_spline.cpu().numpy().astype(bool)
+    need = st.host('need_spline').astype(bool)
     chans = range(st.geom.nchans) if strict else np.nonzero(need.any(axis=1))[0]
     if len(chans) == 0:
         return 0
-    mean = st.hos_mean.cpu().numpy()
-    std = st.hos_std.cpu().numpy()
-    n = st.hos_n.cpu().numpy()
+    mean, std, n, oscan = st.host('hos_mean'), st.host('hos_std'), st.host('hos_n'), st.host('oscan')
+    o, _, _, _ = st._layout['oscan']
     patched = 0
     for i in chans:
-        spl = hostfit.hos_spline(mean[i], std[i], n[i])
         cols = np.nonzero(need[i])[0]
+        spl = hostfit.hos_spline(mean[i], std[i], n[i])
         if len(cols):
-            vals = torch.from_numpy(np.ascontiguousarray(spl[cols])).to(st.oscan.device)
-            st.oscan[i, torch.from_numpy(cols).to(st.oscan.device)] = vals
+            oscan[i, cols] = spl[cols]
+            # the patched row goes back from the pinned mirror (one small async copy per channel)
+            st.oscan[i].copy_(st._pinned[o:o + oscan.nbytes].view(torch.float64).view(oscan.shape)[i],
+                              non_blocking=True)
             patched += len(cols)
     return patched
 
@@ -595,6 +619,40 @@ def cosmics_corr(data, header, data_mask, header_mask):
         data_mask.copy_(m)
         m = data_mask
     return clean, m
+
+
+# -------------------------------------------------------------------------------------------
+# edge pixels (blackbox.py:1958-1974)
+# -------------------------------------------------------------------------------------------
+def channel_medians(data):
+    """np.median of each of the 16 channels of a reduced frame -> float32 [16] CUDA tensor."""
+    t = _to_dev(data, torch.float32)
+    H, W = t.shape
+    ny, nx = set_bb.ny, set_bb.nx
+    if H % ny or W % nx:
+        raise ValueError('frame {} is not {} x {} channels'.format(tuple(t.shape), ny, nx))
+    work = torch.empty(query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=t.device)
+    med = torch.empty(ny * nx, dtype=torch.float32, device=t.device)
+    call('bbx_channel_medians', _ptr(t), H, W, H // ny, W // nx, _ptr(work), _ptr(med), _stream())
+    return med
+
+
+def fill_edge_pixels(data, data_mask, medians=None):
+    """In place: every 'edge' pixel becomes the median of its channel ("to avoid initial
+    source-extractor run leading to a wrong background estimation near the edge",
+    blackbox.py:1958-1974).  Uses the module-global ``tel``.  Returns the channel medians."""
+    is_np = isinstance(data, np.ndarray)
+    t = _to_dev(data, torch.float32)
+    m = _to_dev(data_mask, torch.uint8)
+    if tuple(m.shape) != tuple(t.shape):
+        raise ValueError('mask shape {} does not match data {}'.format(tuple(m.shape), tuple(t.shape)))
+    med = channel_medians(t) if medians is None else _to_dev(medians, torch.float32)
+    H, W = t.shape
+    edge = int(get_par(set_bb.mask_value, tel)['edge'])
+    call('bbx_fill_edge', _ptr(t), _ptr(m), H, W, H // set_bb.ny, W // set_bb.nx, edge, _ptr(med), _stream())
+    if is_np:
+        data[...] = t.cpu().numpy()
+    return med
 
 
 # -------------------------------------------------------------------------------------------

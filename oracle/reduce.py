@@ -403,6 +403,19 @@ def master_median(frames, imgtype='bias', medsec=None, bpm=None, tel=None):
     return out, scales
 
 
+def fill_edge_pixels(data, data_mask, tel=None):
+    """In place: edge pixels -> median of their channel; blackbox.py:1958-1974."""
+    value_edge = get_par(set_bb.mask_value, tel)['edge']
+    mask_edge = (data_mask & value_edge == value_edge)
+    data_sec_red = define_sections(data.shape, tel=tel)[4]
+    meds = []
+    for sec in data_sec_red:
+        med = np.median(data[sec])
+        meds.append(med)
+        data[sec][mask_edge[sec]] = med
+    return np.array(meds, dtype=F32)
+
+
 # -------------------------------------------------------------------------------------------
 def reduce_frame(raw, tel, mbias=None, mflat=None, bpm=None, coeffs=None, exptime=60.0,
                  niter=None, steps=('gain', 'os', 'bias', 'mask', 'flat', 'cosmics', 'xtalk'),

@@ -77,8 +77,10 @@ def test_chain_spline_redo(small_bb):
     assert np.mean(img == data_o) > 0.999
 
 
-def test_batch_reducer_equals_single_pipeline(small_bb):
-    """Two frames in flight on two streams give the bits of the one-by-one pipeline."""
+@pytest.mark.parametrize('depth,graphs,prio', [(2, False, False), (3, False, True), (3, True, True)])
+def test_batch_reducer_equals_single_pipeline(depth, graphs, prio, small_bb):
+    """Several frames in flight (stage A run ahead on a high-priority stream, stages replayed as
+    CUDA graphs) give the bits of the one-by-one pipeline; so does the host-buffer entry."""
     import torch
     from blackbox_b200 import reduce as bbr
     from blackbox_b200.pipeline import BatchReducer, FramePipeline
@@ -86,19 +88,38 @@ def test_batch_reducer_equals_single_pipeline(small_bb):
     small_bb(ysc)
     raw0, mbias, mflat, bpm, coeffs = _inputs(tel, 4200, ysc)
     raws = [raw0] + [_inputs(tel, 4200 + i, ysc)[0] for i in (1, 2, 3, 4)]
+    raws[2][100:120, 1500 * 2 + 20:1500 * 2 + 24] = 65535     # frame 2 needs the host spline
     kw = dict(mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=2)
     single = FramePipeline(tel, raw0.shape, **kw)
     want = []
     for r in raws:
         res = single.reduce(r)
-        want.append((res.img.cpu().numpy().copy(), res.mask.cpu().numpy().copy(), res.header['NCOSMICS']))
-    batch = BatchReducer(tel, raw0.shape, depth=2, **kw)
+        want.append((res.img.cpu().numpy().copy(), res.mask.cpu().numpy().copy(), res.header['NCOSMICS'],
+                     res.spline_columns))
+    assert want[2][3] >= 4
+    batch = BatchReducer(tel, raw0.shape, depth=depth, split_priority=prio, use_graphs=graphs, **kw)
     raws_t = [bbr._to_dev(r) for r in raws]
     imgs = [torch.empty((2 * ysc, 10560), dtype=torch.float32, device='cuda') for _ in raws]
     masks = [torch.empty((2 * ysc, 10560), dtype=torch.uint8, device='cuda') for _ in raws]
-    results = batch.run(raws_t, imgs, masks, fill_header=True)
-    torch.cuda.synchronize()
-    for k, (img, mask, nc) in enumerate(want):
-        assert np.array_equal(imgs[k].cpu().numpy(), img, equal_nan=True), k
-        assert np.array_equal(masks[k].cpu().numpy(), mask), k
-        assert results[k].header['NCOSMICS'] == nc
+    for rep in range(3):                      # graphs are captured on the second pass and replayed on the third
+        for t in imgs + masks:
+            t.zero_()
+        results = batch.run(raws_t, imgs, masks, fill_header=True)
+        torch.cuda.synchronize()
+        for k, (img, mask, nc, ncols) in enumerate(want):
+            assert np.array_equal(imgs[k].cpu().numpy(), img, equal_nan=True), (rep, k)
+            assert np.array_equal(masks[k].cpu().numpy(), mask), (rep, k)
+            assert results[k].header['NCOSMICS'] == nc
+            assert results[k].spline_columns == ncols
+    if graphs:
+        assert sum(p.graph_replays for p in batch.pipes) > 0
+    # host buffers in, host buffers out
+    host_raws = [torch.from_numpy(r.view(np.int16)).view(torch.uint16).pin_memory() for r in raws]
+    host_imgs = [torch.empty((2 * ysc, 10560), dtype=torch.float32).pin_memory() for _ in raws]
+    host_masks = [torch.empty((2 * ysc, 10560), dtype=torch.uint8).pin_memory() for _ in raws]
+    for rep in range(3):
+        results = batch.run_host(host_raws, host_imgs, host_masks, fill_header=True)
+        for k, (img, mask, nc, _) in enumerate(want):
+            assert np.array_equal(host_imgs[k].numpy(), img, equal_nan=True), (rep, k)
+            assert np.array_equal(host_masks[k].numpy(), mask), (rep, k)
+            assert results[k].header['NCOSMICS'] == nc

@@ -110,6 +110,28 @@ def test_detect_cosmics_bit_exact(seed, niter, sigclip, mode):
     assert np.array_equal(info_g['ncr_per_iter'], info_o['ncr_per_iter'])
 
 
+@pytest.mark.parametrize('sigclip,sigfrac,niter', [(5.0, 0.01, 5), (12.0, 0.3, 4)])
+def test_detect_cosmics_many_hits_lazy_equals_dense_equals_oracle(sigclip, sigfrac, niter):
+    """A busy 1500 x 2000 frame (thousands of overlapping cosmic-ray tracks, low thresholds, more
+    iterations than flag stamps): the work lists of the lazy path are long, neighbourhoods of
+    different candidates overlap heavily and the growth steps meet every pixel from several
+    sides -- still the dense twin's and the oracle's bits, run after run."""
+    from blackbox_b200 import reduce as bbr
+    from oracle import lacosmic
+    img, mask = _lacosmic_case(11, shape=(1500, 2000), ncr=6000, masked_frac=0.02)
+    kw = dict(sigclip=sigclip, sigfrac=sigfrac, objlim=2, niter=niter, readnoise=8.5, gain=1.0,
+              satlevel=np.inf, cleantype='medmask', sepmed=False)
+    info_o = {}
+    cr_o, clean_o = lacosmic.detect_cosmics(img, inmask=mask, info=info_o, **kw)
+    assert cr_o.sum() > 10000
+    for mode in (bbr.LAC_LAZY, bbr.LAC_LAZY, bbr.LAC_DENSE, None):
+        info_g = {}
+        cr_g, clean_g = bbr.detect_cosmics(img, inmask=mask, info=info_g, mode=mode, **kw)
+        assert np.array_equal(info_g['ncr_per_iter'], info_o['ncr_per_iter']), mode
+        assert np.array_equal(cr_g, cr_o), mode
+        assert np.array_equal(clean_g.view(np.uint32), clean_o.view(np.uint32)), mode
+
+
 def test_detect_cosmics_background_level():
     """A fat cosmic-ray blob leaves interior pixels without usable neighbours: they get the
     global background level (lower median of all unmasked input pixels).  The lazy path finds
@@ -368,3 +390,41 @@ def test_cosmics_corr_parity(as_tensor, small_bb):
     assert (m_o & set_bb.mask_value['cosmic ray']).sum() > 0
     assert np.array_equal(m_g, m_o) and np.array_equal(d_g, d_o)
     assert hdr_g['NCOSMICS'] == hdr_o['NCOSMICS'] == hm_g['NCOSMICS'] > 0
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('ysc,xsc', [(33, 41), (64, 40), (7, 4)])
+def test_channel_medians_and_edge_fill_bit_exact(ysc, xsc, small_bb):
+    """np.median per channel (odd and even pixel counts, ties, negative values, infinities) and
+    the edge-pixel fill of blackbox.py:1958-1974 against the oracle."""
+    import torch
+    from blackbox_b200 import reduce as bbr, set_bb
+    from oracle import reduce as R
+    small_bb(ysc, xsc)
+    rng = np.random.default_rng(ysc * 100 + xsc)
+    H, W = 2 * ysc, 8 * xsc
+    data = (300 + 30 * rng.standard_normal((H, W))).astype(np.float32)
+    data[:ysc, :xsc] = np.round(data[:ysc, :xsc])               # channel 1: many ties
+    data[:ysc, xsc:2 * xsc] -= 310                              # channel 2: both signs
+    data[ysc:, :xsc][::3, ::2] = np.inf                         # channel 9: infinities
+    data[ysc:, xsc:2 * xsc] = 5.0                               # channel 10: constant
+    mask = np.zeros((H, W), dtype=np.uint8)
+    e = set_bb.mask_value['edge']
+    mask[:2, :] = e
+    mask[:, -3:] = e | set_bb.mask_value['bad']
+    mask[rng.random((H, W)) < 0.01] |= set_bb.mask_value['cosmic ray']
+    want = data.copy()
+    meds_o = R.fill_edge_pixels(want, mask, tel='BG3')
+    bbr.tel = 'BG3'
+    meds = bbr.channel_medians(data).cpu().numpy()
+    assert np.array_equal(meds.view(np.uint32), meds_o.view(np.uint32))
+    got = torch.from_numpy(data.copy()).cuda()
+    bbr.fill_edge_pixels(got, torch.from_numpy(mask).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    data_np = data.copy()
+    bbr.fill_edge_pixels(data_np, mask)                         # numpy in, mutated in place
+    assert np.array_equal(data_np, want)
+    # a NaN makes its channel's median NaN (np.median), the others are unaffected
+    data[ysc + 1, 3 * xsc + 1] = np.nan
+    meds2 = bbr.channel_medians(data).cpu().numpy()
+    assert np.isnan(meds2[8 + 3]) and np.array_equal(np.delete(meds2, 11), np.delete(meds, 11))
