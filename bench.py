@@ -56,9 +56,11 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=64,
+                    help='frames per GPU per step (BASELINE.json config 4: a night batch of 64 frames)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--depth', type=int, default=3, help='frames in flight per GPU')
+    ap.add_argument('--depth', type=int, default=4, help='frames in flight per GPU')
+    ap.add_argument('--ahead', type=int, default=2, help='frames the overscan stage runs ahead')
     ap.add_argument('--split-priority', type=int, default=1,
                     help='1: overscan stage on a high-priority stream of its own')
     ap.add_argument('--graphs', type=int, default=1, help='1: replay the stages as CUDA graphs')
@@ -219,10 +221,10 @@ def run_gpu(args, rank, world, local_rank):
             base = base + torch.randint(-3, 4, base.shape, device=dev, generator=gen, dtype=torch.int32)
         raws.append(base.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
     del base
-    batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, split_priority=bool(args.split_priority),
+    batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, ahead=args.ahead, split_priority=bool(args.split_priority),
                          use_graphs=bool(args.graphs), mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=NITER)
     pipe = batch.pipes[0]
-    nout = max(args.depth, B)      # frame k -> output buffer k: every (raw, output) pair recurs each step
+    nout = args.depth              # frame k -> output buffer k % depth: every (raw, output) pair recurs each step
     out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(nout)]
     out_masks = [torch.empty(red_shape, dtype=torch.uint8, device=dev) for _ in range(nout)]
     out_img, out_mask = out_imgs[0], out_masks[0]
@@ -385,9 +387,11 @@ def measure_e2e(args, batch, raws, red_shape, barrier):
     on their own streams, `--depth` frames in flight."""
     import torch
     B = args.batch
-    host_raw = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(B)]
-    for k in range(B):
-        host_raw[k].copy_(raws[k].cpu())
+    nring = min(B, 8)              # 8 distinct pinned raw frames (2 GB), cycled through the batch
+    ring = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(nring)]
+    for k in range(nring):
+        ring[k].copy_(raws[k].cpu())
+    host_raw = [ring[k % nring] for k in range(B)]
     nring = min(max(2, args.depth), B) if B > 1 else 1
     host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nring)]
     host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(nring)]

@@ -67,6 +67,8 @@ _SIGNATURES = {
     'bbx_gain_corr': [P, GEOM, P, P],
     'bbx_binary_inplace': [P, P, SZ, I, P],
     'bbx_mask_or': [P, P, SZ, I, P],
+    'bbx_fits_decode': [P, I, I, SZ, P, P],
+    'bbx_fits_encode': [P, I, I, SZ, P, P],
     'bbx_chanmed_work_bytes': [],
     'bbx_channel_medians': [P, I, I, I, I, P, P, P],
     'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],

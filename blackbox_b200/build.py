@@ -16,7 +16,7 @@ OUT_DIR = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT_DIR, 'libbbx.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-fmad=false',
-         '-std=c++17', '--compiler-options', '-fPIC', '-Xptxas', '-v']
+         '-std=c++17', '--compiler-options', '-fPIC', '-Xptxas', '-v'] + os.environ.get('BBX_NVCC_EXTRA', '').split()
 
 
 def sources():

@@ -249,28 +249,43 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
         if (y0 < y1) {
             const float *row = img + (size_t)y0 * W + x0;                  // current row
             const uint8_t *mrow = (COLLECT && inmask) ? inmask + (size_t)y0 * W + x0 : nullptr;
-            float4 up = *reinterpret_cast<const float4 *>(row - W);
-            float4 cur = *reinterpret_cast<const float4 *>(row);
-            float mag_up = fmaxf(fmaxf(fabsf(up.x), fabsf(up.y)), fmaxf(fabsf(up.z), fabsf(up.w)));
-            float mag_cur = fmaxf(fmaxf(fabsf(cur.x), fabsf(cur.y)), fmaxf(fabsf(cur.z), fabsf(cur.w)));
             unsigned int pix = (unsigned int)((size_t)y0 * W + x0);
-            for (int y = y0; y < y1; y++, row += W, pix += (unsigned int)W) {
-                const float4 dn = *reinterpret_cast<const float4 *>(row + W);
+            // background statistics on the raw float bits when the bracket starts at a
+            // non-negative value (key_a >= 0x80000000): key < key_a  <=>  (int)bits < (int)lo_bits,
+            // key - key_a = bits - lo_bits for every value at or above the bracket's lower end,
+            // and a negative value's difference wraps far beyond any bracket width (< 2^20)
+            const bool raw_bits = COLLECT && key_a >= 0x80000000u;
+            const int lo_bits = (int)(key_a & 0x7fffffffu);
+            auto mag4 = [](const float4 &v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); };
+            // one row of 4 pixels; rows are held in three rotating register sets (no moves)
+            auto proc = [&](const float4 &up, const float4 &cur, const float4 &dn, float mag_up, float mag_cur,
+                            float mag_dn) {
                 const float lft = row[-1], rgt = row[4];
                 unsigned int mm = 0;
                 if (COLLECT && mrow) { mm = *reinterpret_cast<const unsigned int *>(mrow); mrow += W; }
-                const float mag_dn = fmaxf(fmaxf(fabsf(dn.x), fabsf(dn.y)), fmaxf(fabsf(dn.z), fabsf(dn.w)));
                 const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
                 const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
                 if (COLLECT) {
+                    if (raw_bits) {
+                        n_valid += (unsigned int)__popc(__vcmpeq4(mm, 0u)) >> 3;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const bool ok = ((mm >> (8 * k)) & 0xffu) == 0;
-                        const unsigned int key = f32_key(cc[k + 1]);
-                        const unsigned int d = key - key_a;          // wraps to a huge value below the bracket
-                        n_valid += ok;
-                        n_below += ok && key < key_a;
-                        if (ok && d < width) atomicAdd(&w.bghist[d], 1u);
+                        for (int k = 0; k < 4; k++) {
+                            // a masked pixel is given the bits of +NaN: neither below nor inside
+                            const int bits = ((mm >> (8 * k)) & 0xffu) ? 0x7fffffff : __float_as_int(cc[k + 1]);
+                            n_below += bits < lo_bits;
+                            const unsigned int d = (unsigned int)bits - (unsigned int)lo_bits;
+                            if (d < width) atomicAdd(&w.bghist[d], 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const bool ok = ((mm >> (8 * k)) & 0xffu) == 0;
+                            const unsigned int key = f32_key(cc[k + 1]);
+                            const unsigned int d = key - key_a;          // wraps to a huge value below the bracket
+                            n_valid += ok;
+                            n_below += ok && key < key_a;
+                            if (ok && d < width) atomicAdd(&w.bghist[d], 1u);
+                        }
                     }
                 }
                 const float mag = fmaxf(fmaxf(mag_up, mag_dn), fmaxf(mag_cur, fmaxf(fabsf(lft), fabsf(rgt))));
@@ -299,8 +314,22 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
                         if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, pix + k, info);
                     }
                 }
-                up = cur; cur = dn;
-                mag_up = mag_cur; mag_cur = mag_dn;
+                row += W; pix += (unsigned int)W;
+            };
+            float4 ra = *reinterpret_cast<const float4 *>(row - W);
+            float4 rb = *reinterpret_cast<const float4 *>(row);
+            float4 rc;
+            float ma = mag4(ra), mb = mag4(rb), mc;
+            int y = y0;
+            for (; y + 3 <= y1; y += 3) {
+                rc = *reinterpret_cast<const float4 *>(row + W); mc = mag4(rc); proc(ra, rb, rc, ma, mb, mc);
+                ra = *reinterpret_cast<const float4 *>(row + W); ma = mag4(ra); proc(rb, rc, ra, mb, mc, ma);
+                rb = *reinterpret_cast<const float4 *>(row + W); mb = mag4(rb); proc(rc, ra, rb, mc, ma, mb);
+            }
+            if (y < y1) {
+                rc = *reinterpret_cast<const float4 *>(row + W); mc = mag4(rc); proc(ra, rb, rc, ma, mb, mc);
+                y++;
+                if (y < y1) { ra = *reinterpret_cast<const float4 *>(row + W); ma = mag4(ra); proc(rb, rc, ra, mb, mc, ma); }
             }
         }
     }
@@ -742,7 +771,10 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     unsigned int stamp = (unsigned int)(it % STAMP_PERIOD) + 1;
     BBX_REQUIRE(ceil_div(H, SCAN_ROWS) <= 65535, "lazy LACosmic: %d rows exceed the scan grid (use the dense mode)", H);
     const dim3 scan_blocks(ceil_div((W + 3) / 4, SCAN_THREADS), ceil_div(H, SCAN_ROWS));
-    const int list_blocks = BBX_SM_COUNT * 8, warp_blocks = BBX_SM_COUNT * 16;
+    // iterations after the first work on short lists (what the cleaning step touched): a full
+    // grid would mostly launch and retire idle CTAs
+    const int list_blocks = it == 0 ? BBX_SM_COUNT * 8 : BBX_SM_COUNT * 2;
+    const int warp_blocks = it == 0 ? BBX_SM_COUNT * 16 : BBX_SM_COUNT * 4;
     if (it > 0 && it % STAMP_PERIOD == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {
         if (with_background) {

@@ -567,6 +567,25 @@ hos_stats_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 
 struct VstdPartial { double s, q, cs, cq; long long n, cn; int ovf, pad; };
 
+#ifdef VSTD_PROFILE
+// development build only (BBX_NVCC_EXTRA=-DVSTD_PROFILE): clock64 at the phase boundaries of CTA 0
+__device__ long long g_vstd_clk[32];
+__device__ int g_vstd_nclk;
+#define VSTD_TICK() do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_vstd_nclk < 32) g_vstd_clk[g_vstd_nclk++] = clock64(); } while (0)
+extern "C" int bbx_debug_vstd_clocks(long long *out_h, int *n_h)
+{
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_vstd_nclk, sizeof(int));
+    cudaMemcpyFromSymbol(out_h, g_vstd_clk, sizeof(long long) * 32);
+    *n_h = n;
+    n = 0;
+    cudaMemcpyToSymbol(g_vstd_nclk, &n, sizeof(int));
+    return 0;
+}
+#else
+#define VSTD_TICK() do { } while (0)
+#endif
+
 // u16 -> f32 through the exponent trick (2^23 + n) - 2^23: exact, and off the quarter-rate
 // conversion unit, which the float32 <-> float64 conversions below need
 template <typename T> __device__ __forceinline__ float raw_to_f32_alu(T v);
@@ -671,6 +690,7 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         return x;
     };
 
+    VSTD_TICK();
     // which of this lane's VSTD_MAXV strip columns exist (bit k: column lane + 32 k < vos_w)
     unsigned int kmask = 0;
 #pragma unroll
@@ -725,6 +745,7 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         }
     }
     clo = s_band[0]; chi = s_band[1];
+    VSTD_TICK();
 
     // The walk over this CTA's rows.  BUILD (the first walk): moments of the values inside the
     // band, every other valid value into the list -- the moments of ALL valid values are then
@@ -764,8 +785,10 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
 #pragma unroll
             for (int k = 0; k < VSTD_MAXV; k++) v[k] = vn[k];
         }
+        VSTD_TICK();
         if (build) exchange(0.0, 0.0, 0, s, q, (long long)n, ovf, m, true);
         else exchange(s, q, (long long)n, 0.0, 0.0, 0, 0, m, false);
+        VSTD_TICK();
     };
 
     // band moments + the listed values inside [lo, hi]
@@ -779,6 +802,7 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
         }
         exchange(s, q, n, 0.0, 0.0, 0, 0, m, false);
         m.S += CS; m.Q += CQ; m.N += CN;
+        VSTD_TICK();
     };
 
     auto eval = [&](double lo, double hi, bool closed_nan_ok, Mom &m) {
@@ -814,6 +838,7 @@ vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
     }
     if (rank == 0 && threadIdx.x == 0) out_std[ch] = result;
     cluster.sync();     // keep every CTA's shared memory alive until all remote reads are done
+    VSTD_TICK();
 }
 
 // ============================================================================================

@@ -1,0 +1,243 @@
+"""Minimal FITS primary-HDU reader / writer for the boundary of the hot path.
+
+The reference reads raw frames with ``read_hdulist(..., dtype='float32')`` (astropy.io.fits on
+fpacked files, blackbox.py:7653-7771; the raw data are 16-bit integers with BZERO = 32768, i.e.
+unsigned counts) and writes the reduced float32 image and the uint8 mask with ``fits.writeto``
+(blackbox.py:1987-1990).  astropy is not a dependency here; this module does the two things the
+GPU path needs:
+
+  * ``read_primary``  parse the header cards of an UNCOMPRESSED primary HDU and hand back the data
+                      unit exactly as it is on disk (big-endian), as a numpy array or a pinned
+                      ``torch`` tensor -- the byte swap and the BZERO offset happen on the GPU
+                      (``reduce.fits_decode`` -> ``bbx_fits_decode``), so the host only moves bytes;
+  * ``write_primary`` write a header + a data unit; the data may already be big-endian bytes
+                      produced on the GPU (``reduce.fits_encode`` -> ``bbx_fits_encode``).
+
+Tile-compressed (``.fz``, Rice) files are outside this module: ``funpack`` them first, or read
+them with astropy and hand the arrays to ``reduce`` / ``pipeline`` directly.
+"""
+import collections
+import os
+
+import numpy as np
+
+BLOCK = 2880
+_DTYPES = {8: '>u1', 16: '>i2', 32: '>i4', 64: '>i8', -32: '>f4', -64: '>f8'}
+
+
+class FitsError(ValueError):
+    pass
+
+
+def _parse_value(text):
+    t = text.strip()
+    if not t:
+        return None
+    if t.startswith("'"):
+        end = 1
+        out = []
+        while end < len(t):                       # '' inside a string is a literal quote
+            if t[end] == "'":
+                if end + 1 < len(t) and t[end + 1] == "'":
+                    out.append("'")
+                    end += 2
+                    continue
+                break
+            out.append(t[end])
+            end += 1
+        return ''.join(out).rstrip()
+    if t in ('T', 'F'):
+        return t == 'T'
+    try:
+        return int(t)
+    except ValueError:
+        pass
+    try:
+        return float(t.replace('D', 'E').replace('d', 'e'))
+    except ValueError:
+        return t
+
+
+def _split_card(card):
+    """-> (key, value, comment) of one 80-character card (value None for commentary cards)."""
+    key = card[:8].strip()
+    if card[8:10] != '= ' or key in ('COMMENT', 'HISTORY', ''):
+        return key, None, card[8:].rstrip()
+    body = card[10:]
+    if body.lstrip().startswith("'"):
+        # the comment separator is the first '/' after the closing quote
+        i = body.index("'") + 1
+        while i < len(body):
+            if body[i] == "'":
+                if i + 1 < len(body) and body[i + 1] == "'":
+                    i += 2
+                    continue
+                break
+            i += 1
+        rest = body[i + 1:]
+        value = _parse_value(body[:i + 1])
+        comment = rest.split('/', 1)[1].strip() if '/' in rest else ''
+        return key, value, comment
+    if '/' in body:
+        v, c = body.split('/', 1)
+        return key, _parse_value(v), c.strip()
+    return key, _parse_value(body), ''
+
+
+def read_header(fh):
+    """Read the header of the HDU at the current file position.  -> (OrderedDict key ->
+    (value, comment), number of header bytes)."""
+    hdr = collections.OrderedDict()
+    nbytes = 0
+    while True:
+        block = fh.read(BLOCK)
+        if len(block) != BLOCK:
+            raise FitsError('truncated FITS header')
+        nbytes += BLOCK
+        text = block.decode('ascii', 'replace')
+        for i in range(0, BLOCK, 80):
+            card = text[i:i + 80]
+            key, value, comment = _split_card(card)
+            if key == 'END':
+                return hdr, nbytes
+            if value is None:
+                if key in ('COMMENT', 'HISTORY'):
+                    hdr.setdefault(key, ([], ''))[0].append(comment)
+                continue
+            hdr[key] = (value, comment)
+
+
+def read_primary(path, pinned=False):
+    """-> (header, data, info).  ``data`` is the primary data unit as stored: a big-endian numpy
+    array of shape (NAXIS2, NAXIS1) (a read-only memory map), or with ``pinned`` a pinned uint8
+    ``torch`` tensor holding the same bytes (ready for an asynchronous host-to-device copy).
+    ``info``: dict(bitpix, shape, bzero, bscale, offset).  Raises FitsError for anything but a
+    2-D uncompressed image in the primary HDU."""
+    with open(path, 'rb') as fh:
+        hdr, hbytes = read_header(fh)
+    if hdr.get('SIMPLE', (False,))[0] is not True:
+        raise FitsError('{}: not a standard FITS file (SIMPLE != T)'.format(path))
+    bitpix = hdr['BITPIX'][0]
+    if hdr.get('NAXIS', (0,))[0] != 2 or bitpix not in _DTYPES:
+        raise FitsError('{}: primary HDU is not a 2-D image (NAXIS={}, BITPIX={}); tile-compressed '
+                        'files have to be funpacked first'.format(path, hdr.get('NAXIS', (None,))[0], bitpix))
+    shape = (int(hdr['NAXIS2'][0]), int(hdr['NAXIS1'][0]))
+    dt = np.dtype(_DTYPES[bitpix])
+    nbytes = shape[0] * shape[1] * dt.itemsize
+    if os.path.getsize(path) < hbytes + nbytes:
+        raise FitsError('{}: truncated data unit'.format(path))
+    info = dict(bitpix=bitpix, shape=shape, bzero=float(hdr.get('BZERO', (0.0,))[0]),
+                bscale=float(hdr.get('BSCALE', (1.0,))[0]), offset=hbytes)
+    if pinned:
+        import torch
+        buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        with open(path, 'rb') as fh:
+            fh.seek(hbytes)
+            got = fh.readinto(buf.numpy())
+        if got != nbytes:
+            raise FitsError('{}: short read'.format(path))
+        return hdr, buf, info
+    data = np.memmap(path, dtype=dt, mode='r', offset=hbytes, shape=shape)
+    return hdr, data, info
+
+
+def to_native(data, info):
+    """Host-side decode of ``read_primary``'s array (tests, small frames): unsigned 16-bit counts
+    for BITPIX 16 / BZERO 32768 / BSCALE 1, float32 ``bscale * x + bzero`` otherwise."""
+    if info['bitpix'] == 16 and info['bzero'] == 32768.0 and info['bscale'] == 1.0:
+        return (np.asarray(data).astype(np.int32) + 32768).astype(np.uint16)
+    out = np.asarray(data).astype(np.float32)
+    if info['bscale'] != 1.0:
+        out *= np.float32(info['bscale'])
+    if info['bzero'] != 0.0:
+        out += np.float32(info['bzero'])
+    return out
+
+
+# -------------------------------------------------------------------------------------------
+def _format_value(value):
+    if isinstance(value, (bool, np.bool_)):
+        return '{:>20}'.format('T' if value else 'F')
+    if isinstance(value, (int, np.integer)):
+        return '{:>20d}'.format(int(value))
+    if isinstance(value, (float, np.floating)):
+        v = float(value)
+        if not np.isfinite(v):
+            return "'{:<8}'".format(str(v))
+        text = repr(v).upper()
+        if 'E' not in text and '.' not in text:
+            text += '.'
+        return '{:>20}'.format(text)
+    text = str(value).replace("'", "''")
+    return "'{:<8}'".format(text[:68])
+
+
+def _card(key, value, comment=''):
+    key = str(key).upper()
+    if len(key) > 8:
+        raise FitsError('keyword {!r} is longer than 8 characters'.format(key))
+    card = '{:<8}= {}'.format(key, _format_value(value))
+    if comment:
+        card += ' / ' + str(comment)
+    return card[:80].ljust(80)
+
+
+def build_header(shape, bitpix, header=None, bzero=None):
+    """ASCII header block(s) of a primary HDU for an image of ``shape`` (rows, columns)."""
+    cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', bitpix, 'array data type'),
+             _card('NAXIS', 2, 'number of array dimensions'), _card('NAXIS1', shape[1]), _card('NAXIS2', shape[0])]
+    if bzero is not None:
+        cards += [_card('BSCALE', 1), _card('BZERO', int(bzero))]
+    skip = {'SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'BSCALE', 'BZERO', 'END', 'EXTEND'}
+    for key, val in (header.items() if header is not None else ()):
+        if str(key).upper() in skip:
+            continue
+        if str(key).upper() in ('COMMENT', 'HISTORY'):
+            lines = val[0] if isinstance(val, tuple) else val
+            for ln in ([lines] if isinstance(lines, str) else lines):
+                cards.append('{:<8}{}'.format(str(key).upper(), str(ln))[:80].ljust(80))
+            continue
+        value, comment = (val if isinstance(val, tuple) and len(val) == 2 else (val, ''))
+        cards.append(_card(key, value, comment))
+    cards.append('END'.ljust(80))
+    text = ''.join(cards)
+    text += ' ' * (-len(text) % BLOCK)
+    return text.encode('ascii', 'replace')
+
+
+def write_primary(path, data, header=None, be_bytes=False, shape=None, bitpix=None, bzero=None):
+    """Write a primary HDU.  ``data``: a numpy array (float32 / uint8 / int16 / uint16 -- uint16 is
+    stored as int16 with BZERO 32768), or with ``be_bytes`` a buffer (numpy uint8 array / pinned
+    torch tensor) that already holds the big-endian data unit of an image of ``shape`` and
+    ``bitpix`` (``reduce.fits_encode``; ``bzero=32768`` for encoded uint16 counts).  The file is
+    written to a temporary name and renamed."""
+    if be_bytes:
+        if shape is None or bitpix not in _DTYPES:
+            raise FitsError('be_bytes needs shape and bitpix')
+        raw = data.numpy() if hasattr(data, 'numpy') else np.asarray(data)
+        raw = raw.reshape(-1).view(np.uint8)
+        if raw.size != shape[0] * shape[1] * abs(bitpix) // 8:
+            raise FitsError('buffer size {} does not match shape {} / BITPIX {}'.format(raw.size, shape, bitpix))
+    else:
+        a = np.asarray(data)
+        if a.ndim != 2:
+            raise FitsError('only 2-D images are supported')
+        shape = a.shape
+        if a.dtype == np.uint16:
+            bitpix, bzero = 16, 32768
+            a = (a.astype(np.int32) - 32768).astype('>i2')
+        else:
+            table = {np.dtype(np.float32): -32, np.dtype(np.float64): -64, np.dtype(np.uint8): 8,
+                     np.dtype(np.int16): 16, np.dtype(np.int32): 32}
+            if a.dtype.newbyteorder('=') not in table:
+                raise FitsError('unsupported dtype {}'.format(a.dtype))
+            bitpix = table[a.dtype.newbyteorder('=')]
+            a = a.astype(_DTYPES[bitpix], copy=False)
+        raw = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    tmp = '{}.tmp{}'.format(path, os.getpid())
+    with open(tmp, 'wb') as fh:
+        fh.write(build_header(shape, bitpix, header, bzero=bzero))
+        fh.write(raw.tobytes() if not raw.flags['C_CONTIGUOUS'] else memoryview(raw))
+        fh.write(b'\0' * (-raw.size % BLOCK))
+    os.replace(tmp, path)
+    return path

@@ -98,6 +98,14 @@ class FramePipeline:
             out[name] = (sum(a.elapsed_time(b) for a, b in evs) / len(evs), len(evs))
         return out
 
+    _cap_stream = None
+
+    @staticmethod
+    def _capture_stream():
+        if FramePipeline._cap_stream is None:
+            FramePipeline._cap_stream = torch.cuda.Stream()
+        return FramePipeline._cap_stream
+
     def _run(self, name, key, fn):
         """Run one stage on the current stream: eagerly, or (``use_graphs``) as a CUDA graph
         captured on the second use of the same buffers; with stage timing on, between a pair of
@@ -113,18 +121,27 @@ class FramePipeline:
         elif g == 'seen':
             graph = torch.cuda.CUDAGraph()
             cur = torch.cuda.current_stream()
-            try:
-                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
-                    fn()
-            except Exception:                          # not capturable here: stay eager for this stage
-                self._graphs[(name, key)] = 'eager'
-                torch.cuda.synchronize()
-                with torch.cuda.stream(cur):
-                    fn()
-            else:
+            cap = FramePipeline._capture_stream()
+            cap.wait_stream(cur)
+            ok = True
+            with torch.cuda.stream(cap):
+                try:
+                    graph.capture_begin(capture_error_mode='thread_local')
+                    try:
+                        fn()
+                    finally:
+                        graph.capture_end()
+                except Exception:                      # not capturable here: stay eager for this stage
+                    ok = False
+            cur.wait_stream(cap)
+            if ok:
                 self._graphs[(name, key)] = graph
                 graph.replay()
                 self.graph_replays += 1
+            else:
+                self._graphs[(name, key)] = 'eager'
+                torch.cuda.synchronize()
+                fn()
         elif g == 'eager':
             fn()
         else:
@@ -302,15 +319,19 @@ class BatchReducer:
     """Reduce a batch of raw frames with ``depth`` FramePipelines in flight.
 
     Software pipeline over the frames (host order): stage A of frame k+1 is enqueued on a
-    high-priority stream BEFORE the host waits for stage A of frame k, looks at its flags,
+    high-priority stream (and of frame k+2, ... up to ``ahead``) BEFORE the host waits for stage A
+    of frame k, looks at its flags,
     evaluates the spline where needed and enqueues stage B of frame k.  The GPU therefore always
     has stage B of the previous frame (and stage A of the next) to work on while the host is
     busy, and the small latency-bound overscan kernels run next to the HBM-bound kernels of
     another frame instead of in front of them.  Results are identical to running the frames one
     by one."""
 
-    def __init__(self, tel, raw_shape, depth=3, split_priority=True, **pipeline_kwargs):
+    def __init__(self, tel, raw_shape, depth=4, ahead=None, split_priority=True, **pipeline_kwargs):
         self.depth = max(int(depth), 2)
+        # stage A runs `ahead` frames in front of stage B; a slot is recycled only once its frame
+        # is two behind the one being enqueued, so the host never waits for the frame in progress
+        self.ahead = max(1, min(self.depth - 2, 2 if ahead is None else int(ahead))) if self.depth > 2 else 1
         self.pipes = [FramePipeline(tel, raw_shape, **pipeline_kwargs) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
         self.hi_streams = ([torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
@@ -338,12 +359,13 @@ class BatchReducer:
                 self.hi_streams[j].wait_stream(self.streams[j])
                 self.pipes[j].stage_a_enqueue(raws[k])
 
-        if n:
-            stage_a(0)
+        a = self.ahead
+        for k in range(min(a, n)):
+            stage_a(k)
         for k in range(n):
             j = k % d
-            if k + 1 < n:
-                stage_a(k + 1)
+            if k + a < n:
+                stage_a(k + a)
             with torch.cuda.stream(self.hi_streams[j]):
                 self.pipes[j].stage_a_resolve()
             with torch.cuda.stream(self.streams[j]):
@@ -413,11 +435,13 @@ class BatchReducer:
                 self.hi_streams[j].wait_event(self._ev_in[j])
                 self.pipes[j].stage_a_enqueue(self._hbuf[j][0])
 
-        stage_a(0)
+        a = self.ahead
+        for k in range(min(a, n)):
+            stage_a(k)
         for k in range(n):
             j = k % d
-            if k + 1 < n:
-                stage_a(k + 1)
+            if k + a < n:
+                stage_a(k + a)
             with torch.cuda.stream(self.hi_streams[j]):
                 self.pipes[j].stage_a_resolve()
             with torch.cuda.stream(self.streams[j]):

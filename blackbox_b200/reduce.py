@@ -622,6 +622,54 @@ def cosmics_corr(data, header, data_mask, header_mask):
 
 
 # -------------------------------------------------------------------------------------------
+# FITS data units (fitsio.py reads / writes the files; the byte order is handled here)
+# -------------------------------------------------------------------------------------------
+def fits_decode(be, info, out=None):
+    """Big-endian data unit (uint8 CUDA / pinned / numpy buffer as returned by
+    ``fitsio.read_primary``) -> native CUDA tensor of shape ``info['shape']``: uint16 counts for
+    raw frames (BITPIX 16, BZERO 32768), float32 for BITPIX -32."""
+    bitpix, shape = info['bitpix'], tuple(info['shape'])
+    t = _to_dev(be if not isinstance(be, np.ndarray) else np.ascontiguousarray(be).view(np.uint8).reshape(-1))
+    t = t.view(torch.uint8).reshape(-1)
+    n = shape[0] * shape[1]
+    if bitpix == 16:
+        u16 = info.get('bzero', 0.0) == 32768.0 and info.get('bscale', 1.0) == 1.0
+        if not u16 and (info.get('bzero', 0.0) != 0.0 or info.get('bscale', 1.0) != 1.0):
+            raise NotImplementedError('fits_decode: BITPIX 16 with BZERO {} / BSCALE {}'.format(
+                info.get('bzero'), info.get('bscale')))
+        dt = torch.uint16 if u16 else torch.int16
+    elif bitpix == -32:
+        u16, dt = False, torch.float32
+    else:
+        raise NotImplementedError('fits_decode: BITPIX {}'.format(bitpix))
+    if t.numel() != n * abs(bitpix) // 8:
+        raise ValueError('fits_decode: {} bytes for shape {} / BITPIX {}'.format(t.numel(), shape, bitpix))
+    if out is None:
+        out = torch.empty(shape, dtype=dt, device=t.device)
+    call('bbx_fits_decode', _ptr(t), int(bitpix), int(u16), n, _ptr(out), _stream())
+    return out
+
+
+def fits_encode(data, out=None):
+    """Native CUDA tensor (float32, uint16, int16 or uint8) -> big-endian data unit as a uint8
+    CUDA tensor (uint16 is stored as int16 with BZERO 32768; uint8 needs no swap)."""
+    t = _to_dev(data)
+    n = t.numel()
+    if t.dtype == torch.uint8:
+        return t.reshape(-1), 8
+    if t.dtype == torch.float32:
+        bitpix, u16 = -32, 0
+    elif t.dtype in (torch.uint16, torch.int16):
+        bitpix, u16 = 16, int(t.dtype == torch.uint16)
+    else:
+        raise NotImplementedError('fits_encode: dtype {}'.format(t.dtype))
+    if out is None:
+        out = torch.empty(n * abs(bitpix) // 8, dtype=torch.uint8, device=t.device)
+    call('bbx_fits_encode', _ptr(t), bitpix, u16, n, _ptr(out), _stream())
+    return out, bitpix
+
+
+# -------------------------------------------------------------------------------------------
 # edge pixels (blackbox.py:1958-1974)
 # -------------------------------------------------------------------------------------------
 def channel_medians(data):

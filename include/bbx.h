@@ -289,6 +289,17 @@ int bbx_fill_edge(float *img, const uint8_t *mask, int H, int W, int ysize_chan,
                   int edge_bit, const float *med, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * FITS data units on the device (the boundary either side of the path: raw frames come out of
+ * read_hdulist, blackbox.py:1451 / 7653-7771, reduced images go into fits.writeto,
+ * blackbox.py:1987-1990).  The host moves the file's bytes; these turn them into native arrays
+ * and back.  n = number of pixels; buffers 16-byte aligned; in == out is allowed.
+ * bbx_fits_decode: big-endian BITPIX 16 (unsigned16 != 0: BZERO 32768 -> uint16 counts, else
+ * int16) or BITPIX -32 (float32) -> native.   bbx_fits_encode: the inverse.
+ * ------------------------------------------------------------------------------------- */
+int bbx_fits_decode(const void *be, int bitpix, int unsigned16, size_t n, void *out, void *stream);
+int bbx_fits_encode(const void *in, int bitpix, int unsigned16, size_t n, void *out_be, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * small elementwise helpers for the drop-in functions used one step at a time
  * ------------------------------------------------------------------------------------- */
 /* gain_corr on a float32 raw frame in place (blackbox.py:7459-7460) */

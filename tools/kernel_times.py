@@ -22,7 +22,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=8)
     ap.add_argument('--tel', default='BG3')
-    ap.add_argument('--depth', type=int, default=3)
+    ap.add_argument('--depth', type=int, default=4)
+    ap.add_argument('--ahead', type=int, default=2)
     args = ap.parse_args()
     tel = args.tel
     raw = synth.make_raw(tel, 4001)[0]
@@ -30,7 +31,7 @@ def main():
     mbias, mflat, bpm = synth.make_masters(tel, 9, red)
     coeffs = synth.make_xtalk(3)[3]
     raws = [R._to_dev(raw) for _ in range(max(2, args.depth))]
-    batch = BatchReducer(tel, raw.shape, depth=args.depth, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=4)
+    batch = BatchReducer(tel, raw.shape, depth=args.depth, ahead=args.ahead, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=4)
     imgs = [torch.empty(red, dtype=torch.float32, device='cuda') for _ in range(max(2, args.depth))]
     masks = [torch.empty(red, dtype=torch.uint8, device='cuda') for _ in range(max(2, args.depth))]
     frames = [raws[k % 2] for k in range(args.frames)]

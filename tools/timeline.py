@@ -68,7 +68,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=8)
     ap.add_argument('--tel', default='BG3')
-    ap.add_argument('--depth', type=int, default=3)
+    ap.add_argument('--depth', type=int, default=4)
+    ap.add_argument('--ahead', type=int, default=2)
     ap.add_argument('--graphs', type=int, default=0)
     ap.add_argument('--split-priority', type=int, default=1)
     ap.add_argument('--out', default='gpurun_out/trace.json')
@@ -79,7 +80,7 @@ def main():
     mbias, mflat, bpm = synth.make_masters(tel, 9, red)
     coeffs = synth.make_xtalk(3)[3]
     raws = [R._to_dev(raw) for _ in range(2)]
-    batch = BatchReducer(tel, raw.shape, depth=args.depth, split_priority=bool(args.split_priority), use_graphs=bool(args.graphs), mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=4)
+    batch = BatchReducer(tel, raw.shape, depth=args.depth, ahead=args.ahead, split_priority=bool(args.split_priority), use_graphs=bool(args.graphs), mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=4)
     nbuf = args.frames
     imgs = [torch.empty(red, dtype=torch.float32, device='cuda') for _ in range(nbuf)]
     masks = [torch.empty(red, dtype=torch.uint8, device='cuda') for _ in range(nbuf)]
