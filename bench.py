@@ -66,8 +66,9 @@ def parse_args():
     ap.add_argument('--graphs', type=int, default=1, help='1: replay the stages as CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--cpu-rows', type=int, default=330,
-                    help='rows per channel of the CPU sample frame (full frame: 5280)')
+    ap.add_argument('--cpu-rows', type=int, default=0,
+                    help='rows per channel of the CPU sample frame (full frame: 5280); 0 = 330 for the '
+                         'cpu_baseline of the GPU arm, scaled to the step count for --impl reference')
     return ap.parse_args()
 
 
@@ -91,32 +92,61 @@ def _cpu_worker(job):
     return time.perf_counter() - t0
 
 
-def cpu_sample(rows, cores):
-    """-> (frames/s equivalent, wall seconds, description)"""
-    import multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    jobs = [(5000 + i, rows) for i in range(cores)]
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(1, 40)] * cores)              # start-up, library build / load
+class CpuArm:
+    """The oracle on all host cores, one process per frame slice (pool kept alive across steps)."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context('spawn').Pool(cores)
+        self.pool.map(_cpu_worker, [(1, 40)] * cores)          # start-up: imports, oracle library load
+
+    def sample(self, rows):
+        """-> (frames/s equivalent, wall seconds, description)"""
+        jobs = [(5000 + i, rows) for i in range(self.cores)]
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, jobs)
+        self.pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
-    frac = (2 * rows * 8 * 1320) / float(FULL_NPIX)
-    value = cores * frac / wall
-    sample = ('{} slices of {}x10560 px (1/{:.0f} of a 10560^2 frame each), full chain niter={}, '
-              'one process per slice, OMP_NUM_THREADS=1'.format(cores, 2 * rows, 1 / frac, NITER))
-    return value, wall, sample
+        frac = (2 * rows * 8 * 1320) / float(FULL_NPIX)
+        value = self.cores * frac / wall
+        sample = ('{} slices of {}x10560 px (1/{:.1f} of a 10560^2 frame each), full chain niter={}, '
+                  'one process per slice, OMP_NUM_THREADS=1'.format(self.cores, 2 * rows, 1 / frac, NITER))
+        return value, wall, sample
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_sample(rows, cores):
+    arm = CpuArm(cores)
+    try:
+        return arm.sample(rows)
+    finally:
+        arm.close()
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (the oracle port; the reference itself cannot be
+    installed here) on all host cores.  Each step is a bounded sample: a
+    330-row slice per core costs ~35 s, so the slice height is scaled to keep the whole
+    --steps / --warmup run within a few minutes."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    rows = args.cpu_rows
+    if rows <= 0:
+        budget = 150.0 / max(args.steps + args.warmup, 1)          # seconds per step
+        rows = int(max(40, min(330, 330 * budget / 35.0))) // 4 * 4
+    arm = CpuArm(cores)
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, wall, sample = cpu_sample(args.cpu_rows, cores)
-        if i >= args.warmup:
-            vals.append((v, wall))
+    try:
+        for i in range(args.warmup + args.steps):
+            v, wall, sample = arm.sample(rows)
+            if i >= args.warmup:
+                vals.append((v, wall))
+    finally:
+        arm.close()
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(w for _, w in vals) / len(vals)
     line = {
@@ -293,7 +323,7 @@ def run_gpu(args, rank, world, local_rank):
         cpu = None
         if args.gpus == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, wall, sample = cpu_sample(args.cpu_rows, cores)
+            v, wall, sample = cpu_sample(args.cpu_rows or 330, cores)
             cpu = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample,
                    'wall_s': wall}
         line = {

@@ -55,6 +55,7 @@ _SIGNATURES = {
     'bbx_mask_counts': [P, SZ, P, P],
     'bbx_xtalk': [P, P, I, I, I, I, P, BITS, P],
     'bbx_stack_median': [P, P, I, SZ, I, P, I, P, P],
+    'bbx_stack_clipped_median': [P, P, I, SZ, D, I, I, P, I, P, P],
     'bbx_lacosmic_work_bytes': [I, I],
     'bbx_lacosmic': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],
     'bbx_lacosmic_begin': [P, P, P, I, I, I, I, P, P, P],
@@ -67,6 +68,7 @@ _SIGNATURES = {
     'bbx_gain_corr': [P, GEOM, P, P],
     'bbx_binary_inplace': [P, P, SZ, I, P],
     'bbx_mask_or': [P, P, SZ, I, P],
+    'bbx_nonlin_corr': [P, I, I, I, I, P, P, P, P, P, I, F, P],
     'bbx_fits_decode': [P, I, I, SZ, P, P],
     'bbx_fits_encode': [P, I, I, SZ, P, P],
     'bbx_chanmed_work_bytes': [],

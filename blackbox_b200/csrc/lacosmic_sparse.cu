@@ -193,15 +193,18 @@ __device__ __forceinline__ float lac_thr_lo(const LacParams &prm)
 //
 // COLLECT (mode 0): also the statistics for the background level, see the file header.
 #define SCAN_THREADS 128
-#define SCAN_ROWS 16
+#define SCAN_ROWS 32
 // One pixel the slow way (frame rows / columns, unaligned images)
 template <bool COLLECT>
 __device__ __forceinline__ void sp_scan_pixel(const float *__restrict__ img, const uint8_t *__restrict__ inmask,
+                                              uint8_t *__restrict__ crmask,
                                               int H, int W, int y, int x, float thr_lo, unsigned int key_a,
                                               unsigned int width, unsigned int &n_valid, unsigned int &n_below,
                                               const SparseWork &w, long long *info)
 {
     const size_t i = (size_t)y * W + x;
+    crmask[i] = 0;                       // the scan also clears the two per-pixel byte maps
+    w.flags[i] = 0;
     if (COLLECT && !(inmask && inmask[i])) {
         const unsigned int key = f32_key(img[i]);
         n_valid++;
@@ -214,11 +217,10 @@ __device__ __forceinline__ void sp_scan_pixel(const float *__restrict__ img, con
 
 template <bool COLLECT>
 __global__ void __launch_bounds__(SCAN_THREADS)
-sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, int H, int W, LacParams prm,
-               SparseWork w, long long *info)
+sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, uint8_t *__restrict__ crmask,
+               int H, int W, LacParams prm, SparseWork w, long long *info)
 {
     if (!info[INFO_ACTIVE]) return;
-    __shared__ unsigned long long s_red[33];
     const float thr_lo = lac_thr_lo(prm);
     const float thr_s = __fmul_rd(thr_lo, thr_lo >= 0.f ? 0.99999952316284f : 1.00000047683716f);   // thr_lo (1 -+ 2^-21)
     const int x0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
@@ -232,23 +234,21 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     if (x0 < W && !fast) {
         for (int y = ya; y < yb; y++)
             for (int k = 0; k < 4 && x0 + k < W; k++)
-                sp_scan_pixel<COLLECT>(img, inmask, H, W, y, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+                sp_scan_pixel<COLLECT>(img, inmask, crmask, H, W, y, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
     } else if (x0 < W) {
         int y0 = ya, y1 = yb;
         if (y0 == 0) {                                     // first / last image row: no vector path
             for (int k = 0; k < 4; k++)
-                sp_scan_pixel<COLLECT>(img, inmask, H, W, 0, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+                sp_scan_pixel<COLLECT>(img, inmask, crmask, H, W, 0, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
             y0 = 1;
         }
         if (y1 == H) {
             y1 = H - 1;
             if (y1 >= y0)
                 for (int k = 0; k < 4; k++)
-                    sp_scan_pixel<COLLECT>(img, inmask, H, W, H - 1, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
+                    sp_scan_pixel<COLLECT>(img, inmask, crmask, H, W, H - 1, x0 + k, thr_lo, key_a, width, n_valid, n_below, w, info);
         }
         if (y0 < y1) {
-            const float *row = img + (size_t)y0 * W + x0;                  // current row
-            const uint8_t *mrow = (COLLECT && inmask) ? inmask + (size_t)y0 * W + x0 : nullptr;
             unsigned int pix = (unsigned int)((size_t)y0 * W + x0);
             // background statistics on the raw float bits when the bracket starts at a
             // non-negative value (key_a >= 0x80000000): key < key_a  <=>  (int)bits < (int)lo_bits,
@@ -257,12 +257,26 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
             const bool raw_bits = COLLECT && key_a >= 0x80000000u;
             const int lo_bits = (int)(key_a & 0x7fffffffu);
             auto mag4 = [](const float4 &v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); };
-            // one row of 4 pixels; rows are held in three rotating register sets (no moves)
-            auto proc = [&](const float4 &up, const float4 &cur, const float4 &dn, float mag_up, float mag_cur,
-                            float mag_dn) {
-                const float lft = row[-1], rgt = row[4];
-                unsigned int mm = 0;
-                if (COLLECT && mrow) { mm = *reinterpret_cast<const unsigned int *>(mrow); mrow += W; }
+            // A row bundle: the 4 pixels, their left / right neighbours and the mask word, all
+            // loaded when the row first comes into reach (two rows before it is the centre row,
+            // so every load has a full row of arithmetic to hide behind); four bundles rotate
+            // through the roles next -> down -> centre -> up without register moves.
+            struct Row { float4 v; float l, r; unsigned int mm; };
+            auto load_row = [&](Row &q, int yy) {
+                if (yy >= H) return;                             // beyond the frame: never read
+                const float *src = img + (size_t)yy * W + x0;
+                q.v = *reinterpret_cast<const float4 *>(src);
+                q.l = src[-1]; q.r = src[4];
+                q.mm = 0;
+                if (COLLECT && inmask) q.mm = *reinterpret_cast<const unsigned int *>(inmask + (size_t)yy * W + x0);
+            };
+            auto proc = [&](const Row &U, const Row &Cn, const Row &D) {
+                const float4 &up = U.v, &cur = Cn.v, &dn = D.v;
+                const float lft = Cn.l, rgt = Cn.r;
+                const unsigned int mm = Cn.mm;
+                const float mag_up = mag4(up), mag_cur = mag4(cur), mag_dn = mag4(dn);
+                *reinterpret_cast<unsigned int *>(crmask + pix) = 0u;
+                *reinterpret_cast<unsigned int *>(w.flags + pix) = 0u;
                 const float cc[6] = {lft, cur.x, cur.y, cur.z, cur.w, rgt};
                 const float uu[4] = {up.x, up.y, up.z, up.w}, dd[4] = {dn.x, dn.y, dn.z, dn.w};
                 if (COLLECT) {
@@ -314,31 +328,27 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
                         if (lp > thr_lo) list_push(w.listA[0], &w.cnt->nA[0], w.capA, pix + k, info);
                     }
                 }
-                row += W; pix += (unsigned int)W;
+                pix += (unsigned int)W;
             };
-            float4 ra = *reinterpret_cast<const float4 *>(row - W);
-            float4 rb = *reinterpret_cast<const float4 *>(row);
-            float4 rc;
-            float ma = mag4(ra), mb = mag4(rb), mc;
+            Row ra, rb, rc, rd;
+            load_row(ra, y0 - 1); load_row(rb, y0); load_row(rc, y0 + 1);
             int y = y0;
-            for (; y + 3 <= y1; y += 3) {
-                rc = *reinterpret_cast<const float4 *>(row + W); mc = mag4(rc); proc(ra, rb, rc, ma, mb, mc);
-                ra = *reinterpret_cast<const float4 *>(row + W); ma = mag4(ra); proc(rb, rc, ra, mb, mc, ma);
-                rb = *reinterpret_cast<const float4 *>(row + W); mb = mag4(rb); proc(rc, ra, rb, mc, ma, mb);
+            for (; y + 4 <= y1; y += 4) {
+                load_row(rd, y + 2); proc(ra, rb, rc);
+                load_row(ra, y + 3); proc(rb, rc, rd);
+                load_row(rb, y + 4); proc(rc, rd, ra);
+                load_row(rc, y + 5); proc(rd, ra, rb);
             }
-            if (y < y1) {
-                rc = *reinterpret_cast<const float4 *>(row + W); mc = mag4(rc); proc(ra, rb, rc, ma, mb, mc);
-                y++;
-                if (y < y1) { ra = *reinterpret_cast<const float4 *>(row + W); ma = mag4(ra); proc(rb, rc, ra, mb, mc, ma); }
-            }
+            if (y < y1) { load_row(rd, y + 2); proc(ra, rb, rc); y++; }
+            if (y < y1) { load_row(ra, y + 2); proc(rb, rc, rd); y++; }
+            if (y < y1) { proc(rc, rd, ra); y++; }
         }
     }
     if (COLLECT) {
-        const unsigned long long tv = block_sum((unsigned long long)n_valid, s_red);
-        const unsigned long long tb = block_sum((unsigned long long)n_below, s_red);
-        if (threadIdx.x == 0) {
-            if (tv) atomicAdd(&w.bg->n_valid, tv);
-            if (tb) atomicAdd(&w.bg->n_below, tb);
+        const unsigned int tv = (unsigned int)warp_sum((int)n_valid), tb = (unsigned int)warp_sum((int)n_below);
+        if ((threadIdx.x & 31) == 0) {
+            if (tv) atomicAdd(&w.bg->n_valid, (unsigned long long)tv);
+            if (tb) atomicAdd(&w.bg->n_below, (unsigned long long)tb);
         }
     }
 }
@@ -750,8 +760,9 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
 {
     const size_t n = (size_t)H * W;
     const SparseWork w = carve_sparse(work, n);
-    BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
-    BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));
+    // crmask and the flag bytes are cleared by the dense scan of iteration 0 (it visits every
+    // pixel anyway and has store bandwidth to spare); niter == 0 never scans
+    if (niter <= 0) BBX_CUDA(cudaMemsetAsync(crmask, 0, n, st));
     if (with_background) {
         if (bbx_masked_lower_median(img, inmask, n, w.sel, w.background, st)) return -2;
     } else {
@@ -778,9 +789,9 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     if (it > 0 && it % STAMP_PERIOD == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0) {
         if (with_background) {
-            sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
+            sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, crmask, H, W, prm, w, info);
         } else {
-            sp_scan_kernel<true><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, H, W, prm, w, info);
+            sp_scan_kernel<true><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, crmask, H, W, prm, w, info);
             sp_bg_rank_kernel<<<1, 1024, 0, st>>>(w);
         }
     } else sp_rescan_kernel<<<list_blocks, 128, 0, st>>>(img, H, W, prm, w, it, stamp, info);

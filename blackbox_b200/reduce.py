@@ -622,6 +622,59 @@ def cosmics_corr(data, header, data_mask, header_mask):
 
 
 # -------------------------------------------------------------------------------------------
+# non-linearity (blackbox.py:7392-7437; off in the reference's settings)
+# -------------------------------------------------------------------------------------------
+def spline_tck(spl):
+    """(knots, coefficients, degree) of a scipy spline object (UnivariateSpline and its
+    subclasses, BSpline) or of a ``(t, c, k)`` tuple."""
+    if isinstance(spl, (tuple, list)) and len(spl) == 3:
+        t, c, k = spl
+    elif hasattr(spl, '_eval_args'):
+        t, c, k = spl._eval_args
+    elif hasattr(spl, 't') and hasattr(spl, 'c') and hasattr(spl, 'k'):
+        t, c, k = spl.t, spl.c, spl.k
+    else:
+        raise TypeError('nonlin_corr: cannot take knots / coefficients from {!r}'.format(type(spl)))
+    return np.asarray(t, dtype=np.float64), np.asarray(c, dtype=np.float64), int(k)
+
+
+def nonlin_corr(data, nonlin_corr_file, max_counts=50000):
+    """In place ``data /= (frac_corr + 1)`` with the per-channel spline of the fractional
+    non-linearity evaluated at the counts ``data / gain`` (blackbox.py:7392-7437).
+    ``nonlin_corr_file``: path of the pickled list of 16 spline objects the reference reads, or
+    that list itself.  Uses the module-global ``tel``.  Returns ``data``."""
+    if isinstance(nonlin_corr_file, (str, bytes)):
+        import pickle
+        with open(nonlin_corr_file, 'rb') as fh:
+            splines = pickle.load(fh)
+    else:
+        splines = nonlin_corr_file
+    nchans = set_bb.ny * set_bb.nx
+    if len(splines) != nchans:
+        raise ValueError('nonlin_corr: {} splines for {} channels'.format(len(splines), nchans))
+    tck = [spline_tck(sp) for sp in splines]
+    maxn = max(len(t) for t, _, _ in tck)
+    knots = np.zeros((nchans, maxn))
+    coefs = np.zeros((nchans, maxn))
+    for i, (t, c, k) in enumerate(tck):
+        knots[i, :len(t)] = t
+        coefs[i, :min(len(c), len(t))] = c[:len(t)]
+    nk = (C.c_int * nchans)(*[len(t) for t, _, _ in tck])
+    deg = (C.c_int * nchans)(*[k for _, _, k in tck])
+    is_np = isinstance(data, np.ndarray)
+    t_ = _to_dev(data, torch.float32)
+    H, W = t_.shape
+    gain = get_par(set_bb.gain, tel)
+    call('bbx_nonlin_corr', _ptr(t_), H, W, H // set_bb.ny, W // set_bb.nx,
+         _harr([float(np.float32(g)) for g in gain], C.c_float), knots.ctypes.data_as(C.c_void_p),
+         coefs.ctypes.data_as(C.c_void_p), nk, deg, int(maxn), float(max_counts), _stream())
+    if is_np:
+        data[...] = t_.cpu().numpy()
+        return data
+    return t_
+
+
+# -------------------------------------------------------------------------------------------
 # FITS data units (fitsio.py reads / writes the files; the byte order is handled here)
 # -------------------------------------------------------------------------------------------
 def fits_decode(be, info, out=None):
@@ -754,12 +807,17 @@ def xtalk_corr(data, crosstalk_file, data_mask=None):
 # -------------------------------------------------------------------------------------------
 # master frames
 # -------------------------------------------------------------------------------------------
-def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=None):
+def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=None, clip_sigma=None,
+                   clip_maxiters=5):
     """Arithmetic core of master_prep (blackbox.py:4908-4984, 5063-5073): per-pixel median of
     the stack; flats are first divided by their normalisation median (``medsec[i]`` = the
     header's MEDSEC, else the median over set_bb.flat_norm_sec) and get edge / non-positive
     pixels set to 1 afterwards.  ``frames``: sequence of float32 arrays / CUDA tensors of one
-    shape (or a 3-D array).  Returns (master, scales)."""
+    shape (or a 3-D array).  Returns (master, scales).
+
+    ``clip_sigma`` (default None = the reference's plain median): sigma-clip every pixel's stack
+    first (astropy.stats.sigma_clip, cenfunc='median', ``clip_maxiters`` rounds) and take the
+    median of what is left -- the combine BASELINE.json words; not what master_prep does."""
     is_np = isinstance(frames[0], np.ndarray)
     ts = [_to_dev(f, torch.float32) for f in frames]
     n = len(ts)
@@ -779,9 +837,14 @@ def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=ts[0].device)
     ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
-    call('bbx_stack_median', ptrs, _harr([float(np.float32(s)) for s in scales], C.c_float), n,
-         out.numel(), 1 if (imgtype == 'flat' and bpm_t is not None) else 0, _ptr(bpm_t),
-         int(get_par(set_bb.mask_value, tel)['edge']), _ptr(out), _stream())
+    scale_h = _harr([float(np.float32(s)) for s in scales], C.c_float)
+    flat_fix = 1 if (imgtype == 'flat' and bpm_t is not None) else 0
+    edge = int(get_par(set_bb.mask_value, tel)['edge'])
+    if clip_sigma is None:
+        call('bbx_stack_median', ptrs, scale_h, n, out.numel(), flat_fix, _ptr(bpm_t), edge, _ptr(out), _stream())
+    else:
+        call('bbx_stack_clipped_median', ptrs, scale_h, n, out.numel(), float(clip_sigma), int(clip_maxiters),
+             flat_fix, _ptr(bpm_t), edge, _ptr(out), _stream())
     return (out.cpu().numpy() if is_np else out), scales
 
 

@@ -215,6 +215,15 @@ int bbx_stack_median(const float *const *frames_h, const float *scale_h, int N, 
                      int flat_fix, const uint8_t *bpm, int edge_value, float *out,
                      void *stream);
 
+/* Optional sigma-clipped combine (BASELINE.json's wording; the reference's master_prep uses the
+ * plain median above, so this is off by default in reduce.master_combine): per pixel
+ * astropy.stats.sigma_clip(cube, sigma, maxiters, cenfunc='median', stdfunc='std', axis=0)
+ * followed by np.ma.median -- (a+b)/2 in float32, NaN if nothing survives; non-finite inputs
+ * never take part.  Same frame / scale / flat_fix arguments as bbx_stack_median. */
+int bbx_stack_clipped_median(const float *const *frames_h, const float *scale_h, int N, size_t npix,
+                             double sigma, int maxiters, int flat_fix, const uint8_t *bpm,
+                             int edge_value, float *out, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * LACosmic -- astroscrappy.detect_cosmics 1.0.8 (sepmed=False, fsmode='median',
  * cleantype='medmask', gain=1, pssl=0, satlevel=inf), call site blackbox.py:4323-4332
@@ -246,9 +255,10 @@ int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int 
                  long long *out_info, void *stream);
 
 /* The same in two parts, so one iteration can be enqueued (and timed) on its own:
- * _begin zeroes crmask / out_info (mode 1: also computes the background level), _iteration
- * enqueues the kernels of iteration `iter` (a no-op on the device once an earlier iteration
- * found nothing). */
+ * _begin resets out_info and the work lists (mode 1 / 2: also computes the background level),
+ * _iteration enqueues the kernels of iteration `iter` (a no-op on the device once an earlier
+ * iteration found nothing).  crmask is valid after iteration 0: in modes 0 and 2 its dense scan
+ * clears it (_begin does when niter == 0). */
 int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
                        int niter, int mode, void *work, long long *out_info, void *stream);
 int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,
@@ -287,6 +297,19 @@ int bbx_channel_medians(const float *img, int H, int W, int ysize_chan, int xsiz
                         void *work, float *out_med, void *stream);
 int bbx_fill_edge(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                   int edge_bit, const float *med, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Non-linearity correction -- nonlin_corr blackbox.py:7392-7437 (off in the reference's settings).
+ * Per channel a FITPACK B-spline s (knots_h / coefs_h: float64 [16][max_knots], nknots_h, degree_h
+ * <= 5; what scipy's UnivariateSpline._eval_args holds) gives the fractional deviation from
+ * linearity as a function of the counts: img = f32(f64(img) / (frac + 1)) with
+ * frac = (img / gain <= max_counts) ? s(img / gain) : 1 -- the reference's arithmetic, including
+ * its division by 2 above the limit.  s is evaluated as FITPACK's splev does (bit-identical
+ * float64 values).  img: reduced frame (2 x 8 channels), in place.
+ * ------------------------------------------------------------------------------------- */
+int bbx_nonlin_corr(float *img, int H, int W, int ysize_chan, int xsize_chan, const float *gain_h,
+                    const double *knots_h, const double *coefs_h, const int *nknots_h,
+                    const int *degree_h, int max_knots, float max_counts, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * FITS data units on the device (the boundary either side of the path: raw frames come out of

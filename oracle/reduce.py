@@ -403,6 +403,36 @@ def master_median(frames, imgtype='bias', medsec=None, bpm=None, tel=None):
     return out, scales
 
 
+def nonlin_corr(data, fit_splines, tel=None):
+    """In place; blackbox.py:7392-7437 verbatim (fit_splines: the unpickled list of 16 spline
+    objects).  Note the reference's ``frac_corr = np.ones(...)``: above 50000 counts the data are
+    divided by 2."""
+    gain = get_par(set_bb.gain, tel)
+    data_sec_red = define_sections(np.shape(data), tel=tel)[4]
+    for i_chan in range(len(data_sec_red)):
+        data_counts = data[data_sec_red[i_chan]] / gain[i_chan]
+        frac_corr = np.ones(data_counts.shape)
+        with np.errstate(invalid='ignore'):
+            mask_corr = (data_counts <= 50000)
+        frac_corr[mask_corr] = fit_splines[i_chan](data_counts[mask_corr])
+        data[data_sec_red[i_chan]] /= (frac_corr + 1)
+    return data
+
+
+def master_median_clipped(frames, sigma=3.0, maxiters=5, scales=None):
+    """Sigma-clipped median combine (NOT the reference's master_prep, which takes the plain
+    median, blackbox.py:4984; BASELINE.json's wording): astropy.stats.sigma_clip along the stack
+    axis with cenfunc='median', then np.ma.median; NaN where nothing survives."""
+    cube = np.stack([np.asarray(f, dtype=F32) for f in frames])
+    if scales is not None:
+        for i, sc in enumerate(scales):
+            if sc != 0:
+                cube[i] /= F32(sc)
+    clipped = sigma_clip(cube, sigma=sigma, maxiters=maxiters, cenfunc='median', axis=0, masked=True)
+    med = np.ma.median(clipped, axis=0)
+    return np.ma.filled(med.astype(F32), np.nan).astype(F32)
+
+
 def fill_edge_pixels(data, data_mask, tel=None):
     """In place: edge pixels -> median of their channel; blackbox.py:1958-1974."""
     value_edge = get_par(set_bb.mask_value, tel)['edge']

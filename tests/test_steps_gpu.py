@@ -428,3 +428,87 @@ def test_channel_medians_and_edge_fill_bit_exact(ysc, xsc, small_bb):
     data[ysc + 1, 3 * xsc + 1] = np.nan
     meds2 = bbr.channel_medians(data).cpu().numpy()
     assert np.isnan(meds2[8 + 3]) and np.array_equal(np.delete(meds2, 11), np.delete(meds, 11))
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,sigma,maxiters', [(1, 3.0, 5), (2, 3.0, 5), (5, 2.0, 5), (20, 3.0, 5), (20, 2.5, 1),
+                                               (33, 3.0, 5), (64, 3.0, 3)])
+def test_clipped_stack_median_bit_exact(n, sigma, maxiters):
+    """The optional sigma-clipped combine against astropy's sigma_clip + np.ma.median as the
+    oracle restates them: outliers, ties, constant stacks, NaN / inf inputs, fully rejected pixels."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from oracle import reduce as R
+    rng = np.random.default_rng(100 + n)
+    shape = (37, 53)
+    frames = [(1000 + 10 * rng.standard_normal(shape)).astype(np.float32) for _ in range(n)]
+    for k in range(0, n, 4):                                     # outliers (cosmic rays in single frames)
+        hit = rng.random(shape) < 0.05
+        frames[k][hit] += rng.uniform(100, 5000, hit.sum()).astype(np.float32)
+    for f in frames:
+        f[0, :10] = 7.0                                          # a constant stack (std = 0)
+        f[1, :10] = np.round(f[1, :10])                          # ties
+    frames[0][2, 0] = np.nan
+    frames[n // 2][2, 1] = np.inf
+    frames[n - 1][2, 2] = -np.inf
+    for f in frames:
+        f[3, 0] = np.nan                                         # nothing survives
+    want = R.master_median_clipped(frames, sigma=sigma, maxiters=maxiters)
+    got, _ = bbr.master_combine([torch.from_numpy(f).cuda() for f in frames], 'bias', clip_sigma=sigma,
+                                clip_maxiters=maxiters)
+    got = got.cpu().numpy()
+    assert np.isnan(want[3, 0]) and np.isnan(got[3, 0])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or np.array_equal(got, want, equal_nan=True)
+    # the plain median stays the default and differs where outliers matter
+    plain, _ = bbr.master_combine([torch.from_numpy(f).cuda() for f in frames], 'bias')
+    assert np.array_equal(plain.cpu().numpy(), np.median(np.stack(frames), axis=0), equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------
+def _nonlin_splines(seed):
+    from scipy import interpolate
+    rng = np.random.default_rng(seed)
+    splines = []
+    for i in range(16):
+        x = np.linspace(0, 60000, 120)
+        y = 2e-3 * np.sin(x / (7000.0 + 300 * i)) - 3e-7 * x + 2e-4 * rng.standard_normal(x.size)
+        k = (3, 3, 2, 5)[i % 4]
+        splines.append(interpolate.UnivariateSpline(x, y, k=k, s=x.size * (2e-4) ** 2))
+    return splines
+
+
+def test_nonlin_corr_parity(small_bb):
+    """nonlin_corr (blackbox.py:7392-7437) against the reference's own arithmetic on scipy spline
+    objects: bit-exact, including the counts above 50000 (divided by 2, as the reference does) and
+    negative / NaN pixels."""
+    import pickle
+    import torch
+    from blackbox_b200 import reduce as bbr, set_bb
+    from oracle import reduce as R
+    small_bb(96, 200)
+    rng = np.random.default_rng(9)
+    H, W = 2 * 96, 8 * 200
+    data = rng.uniform(-500, 140000, size=(H, W)).astype(np.float32)       # electrons; counts up to ~53000
+    data[5, 7], data[100, 900] = np.nan, 0.0
+    splines = _nonlin_splines(4)
+    want = R.nonlin_corr(data.copy(), splines, tel='BG3')
+    bbr.tel = 'BG3'
+    got = bbr.nonlin_corr(torch.from_numpy(data.copy()).cuda(), splines).cpu().numpy()
+    assert (data / np.float32(set_bb.gain['BG3'][0]) > 50000).sum() > 100
+    assert np.array_equal(got, want, equal_nan=True)
+    got_np = bbr.nonlin_corr(data.copy(), splines)                         # numpy in, list in
+    assert np.array_equal(got_np, want, equal_nan=True)
+
+
+def test_nonlin_corr_reads_the_pickle(small_bb, tmp_path):
+    import pickle
+    from blackbox_b200 import reduce as bbr
+    from oracle import reduce as R
+    small_bb(16, 40)
+    data = np.random.default_rng(1).uniform(0, 90000, size=(32, 320)).astype(np.float32)
+    splines = _nonlin_splines(5)
+    path = tmp_path / 'nonlin.pkl'
+    path.write_bytes(pickle.dumps(splines))
+    bbr.tel = 'ML1'
+    got = bbr.nonlin_corr(data.copy(), str(path))
+    assert np.array_equal(got, R.nonlin_corr(data.copy(), splines, tel='ML1'))
