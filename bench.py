@@ -48,6 +48,7 @@ STAGES = {
     'lacosmic': ('sp_scan + sparse candidate / grow / clean kernels, %d iterations (S4)' % NITER, NITER * 1115.1e6, False),
     'lacosmic_finish': ('cosmic-ray bit + NCOSMICS from the CR list', None, False),
     'xtalk': ('xtalk_tile_kernel (S5: img r+w + mask r)', 1003.6e6, True),
+    'edge_fill': ('cs_hist x3 + cs_find x3 + cs_fill_edge (3 x img r + mask r)', 3 * 446.1e6 + 111.5e6, False),
 }
 
 
@@ -64,6 +65,10 @@ def parse_args():
     ap.add_argument('--split-priority', type=int, default=1,
                     help='1: overscan stage on a high-priority stream of its own')
     ap.add_argument('--graphs', type=int, default=1, help='1: replay the stages as CUDA graphs')
+    ap.add_argument('--fill-edge', type=int, default=0,
+                    help='1: append the edge-pixel fill (blackbox.py:1958-1974) to the chain (not part of the metric)')
+    ap.add_argument('--fits', type=int, default=0,
+                    help='1: e2e with FITS data units on the host side (byte swaps on the device)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-rows', type=int, default=0,
@@ -252,7 +257,8 @@ def run_gpu(args, rank, world, local_rank):
         raws.append(base.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
     del base
     batch = BatchReducer(TEL, raws[0].shape, depth=args.depth, ahead=args.ahead, split_priority=bool(args.split_priority),
-                         use_graphs=bool(args.graphs), mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=NITER)
+                         use_graphs=bool(args.graphs), fill_edge=bool(args.fill_edge), mbias=mbias, mflat=mflat, bpm=bpm,
+                         coeffs=coeffs, niter=NITER)
     pipe = batch.pipes[0]
     nout = args.depth              # frame k -> output buffer k % depth: every (raw, output) pair recurs each step
     out_imgs = [torch.empty(red_shape, dtype=torch.float32, device=dev) for _ in range(nout)]
@@ -297,7 +303,7 @@ def run_gpu(args, rank, world, local_rank):
     ms_total = float(t.item())
     frames = world * B * args.steps
     value = frames / (ms_total * 1e-3)
-    launches = args.steps * B * pipe_launches(TEL, NITER)
+    launches = world * args.steps * B * pipe_launches(TEL, NITER)
 
     # ---- roofline: one LACosmic iteration, timed with CUDA events on the launching stream ---
     roof = stages = None
@@ -316,8 +322,8 @@ def run_gpu(args, rank, world, local_rank):
         e2e_ms = float(t.item())
         raw_bytes = raws[0].numel() * 2
         e2e = {'value': world * B * args.steps / (e2e_ms * 1e-3), 'unit': 'frames/s',
-               'h2d_bytes_per_step': B * raw_bytes,
-               'd2h_bytes_per_step': B * (out_img.numel() * 4 + out_mask.numel())}
+               'h2d_bytes_per_step': world * B * raw_bytes,
+               'd2h_bytes_per_step': world * B * (out_img.numel() * 4 + out_mask.numel())}
 
     if rank == 0:
         cpu = None
@@ -343,11 +349,12 @@ def run_gpu(args, rank, world, local_rank):
 
 
 def pipe_launches(tel, niter):
-    """Kernels of libbbx.so launched per frame by FramePipeline.enqueue (memsets not counted):
-    overscan 8 (+1 BlackGEM saturated-column count), header means 1, fused apply 1, sparse mask
-    morphology 11, LACosmic 2 + 7 in the first iteration + 7 per iteration, cosmic bit + object count 3,
+    """Kernels of libbbx.so launched per frame by FramePipeline (memsets and copies not counted;
+    cross-checked against the ncu launch list under profiles/): overscan 6 (+1 BlackGEM
+    saturated-column count) + header means 1, fused apply 1, sparse mask morphology 11, LACosmic
+    2 (begin) + 9 (first iteration) + 8 per further iteration, cosmic-ray bit + object count 3,
     crosstalk 1."""
-    return 8 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 7 + 7 * niter + 3 + 1
+    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1
 
 
 def peak_hbm():
@@ -421,6 +428,10 @@ def measure_e2e(args, batch, raws, red_shape, barrier):
     ring = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(nring)]
     for k in range(nring):
         ring[k].copy_(raws[k].cpu())
+        if args.fits:             # as the data unit of a raw FITS file: big-endian int16, BZERO 32768
+            a = ring[k].view(torch.int16).numpy()
+            be = (a.view(np.uint16).astype(np.int32) - 32768).astype('>i2')
+            a[...] = be.view(np.int16)
     host_raw = [ring[k % nring] for k in range(B)]
     nring = min(max(2, args.depth), B) if B > 1 else 1
     host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nring)]
@@ -429,7 +440,7 @@ def measure_e2e(args, batch, raws, red_shape, barrier):
     def run(nsteps):
         redo = 0
         for _ in range(nsteps):
-            for res in batch.run_host(host_raw, host_img, host_mask):
+            for res in batch.run_host(host_raw, host_img, host_mask, fits=bool(args.fits)):
                 redo += res.redo
         return redo
 

@@ -6,15 +6,14 @@
 // middle order statistics; any NaN in the channel makes it NaN.  Both ranks are found by a
 // three-pass radix select on the order-preserving 32-bit key of a float32 (11 + 11 + 10 bits),
 // all 16 channels at once: every pass reads the frame once (446 MB) and histograms, per channel,
-// the next key digit of the pixels that still match the prefix of either rank.  A thread owns a
-// run of consecutive pixels of one channel row and only touches the shared-memory histogram
-// when the digit changes (pass 0: practically every pixel of a sky-dominated frame has the same
-// top 11 bits, so plain atomics would serialise 32-fold).
+// the next key digit of the pixels that still match the prefix of either rank.  A thread only
+// touches the shared-memory histogram when the digit differs from that of its previous pixel
+// (pass 0: practically every pixel of a sky-dominated frame has the same top 11 bits, so plain
+// atomics would serialise 32-fold).
 #include "bbx_common.cuh"
 
 #define CS_BINS 2048
 #define CS_THREADS 256
-#define CS_RUN 16                 // consecutive pixels per thread
 
 struct ChanSel {
     unsigned long long k[2];      // rank still to find inside the current prefix, per target
@@ -63,36 +62,47 @@ cs_hist_kernel(const float *__restrict__ img, int W, int ysc, int xsc, int rows_
     const unsigned int p0 = cs.prefix[0], p1 = cs.prefix[1];
     const bool two = PASS > 0 && cs.two && p1 != p0;
     const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, ysc);
-    const int runs_per_row = (xsc + CS_RUN - 1) / CS_RUN;
-    const int total = (y1 - y0) * runs_per_row;
+    // coalesced float4 reads: consecutive threads take consecutive groups of 4 pixels of a channel
+    // row (when the channel rows start 16-byte aligned, i.e. xsc % 4 == 0; scalar reads otherwise); a
+    // thread's successive pixels are 4 KB apart but almost always fall into the same bin in pass
+    // 0, which is all the run-length trick needs
     unsigned int nan = 0;
-    for (int t = blockIdx.x * CS_THREADS + threadIdx.x; t < total; t += gridDim.x * CS_THREADS) {
-        const int yy = y0 + t / runs_per_row, x0 = (t % runs_per_row) * CS_RUN;
-        const float *row = img + (size_t)(r * ysc + yy) * W + (size_t)c * xsc;
-        int cur = -1, cur_t = 0;
-        unsigned int cnt = 0;
-        const int xe = min(x0 + CS_RUN, xsc);
-        for (int x = x0; x < xe; x++) {
-            const float v = row[x];
-            if (PASS == 0 && v != v) { nan++; continue; }
-            const unsigned int key = cs_key(v);
-            int bin, tgt = 0;
-            if (PASS == 0) bin = (int)(key >> 21);
-            else if (PASS == 1) {
-                const unsigned int pre = key >> 21;
-                if (pre == p0) tgt = 0; else if (two && pre == p1) tgt = 1; else continue;
-                bin = (int)((key >> 10) & 2047u);
-            } else {
-                const unsigned int pre = key >> 10;
-                if (pre == p0) tgt = 0; else if (two && pre == p1) tgt = 1; else continue;
-                bin = (int)(key & 1023u);
-            }
-            if (bin == cur && tgt == cur_t) { cnt++; continue; }
-            if (cnt) atomicAdd(&h[cur_t][cur], cnt);
-            cur = bin; cur_t = tgt; cnt = 1;
+    int cur = -1, cur_t = 0;
+    unsigned int cnt = 0;
+    auto consume = [&](float v) {
+        if (PASS == 0 && v != v) { nan++; return; }
+        const unsigned int key = cs_key(v);
+        int bin, tgt = 0;
+        if (PASS == 0) bin = (int)(key >> 21);
+        else if (PASS == 1) {
+            const unsigned int pre = key >> 21;
+            if (pre == p0) tgt = 0; else if (two && pre == p1) tgt = 1; else return;
+            bin = (int)((key >> 10) & 2047u);
+        } else {
+            const unsigned int pre = key >> 10;
+            if (pre == p0) tgt = 0; else if (two && pre == p1) tgt = 1; else return;
+            bin = (int)(key & 1023u);
         }
+        if (bin == cur && tgt == cur_t) { cnt++; return; }
         if (cnt) atomicAdd(&h[cur_t][cur], cnt);
+        cur = bin; cur_t = tgt; cnt = 1;
+    };
+    if (xsc % 4 == 0 && ((uintptr_t)img & 15) == 0) {
+        const int g4 = xsc / 4;
+        const int total = (y1 - y0) * g4;
+        for (int t = blockIdx.x * CS_THREADS + threadIdx.x; t < total; t += gridDim.x * CS_THREADS) {
+            const int yy = y0 + t / g4, xg = t % g4;
+            const float4 q = *reinterpret_cast<const float4 *>(img + (size_t)(r * ysc + yy) * W + (size_t)c * xsc + 4 * xg);
+            consume(q.x); consume(q.y); consume(q.z); consume(q.w);
+        }
+    } else {                                                  // any width / alignment
+        const int total = (y1 - y0) * xsc;
+        for (int t = blockIdx.x * CS_THREADS + threadIdx.x; t < total; t += gridDim.x * CS_THREADS) {
+            const int yy = y0 + t / xsc, x = t % xsc;
+            consume(img[(size_t)(r * ysc + yy) * W + (size_t)c * xsc + x]);
+        }
     }
+    if (cnt) atomicAdd(&h[cur_t][cur], cnt);
     if (PASS == 0 && nan) atomicAdd(&s_nan, nan);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * CS_BINS; i += CS_THREADS) {
@@ -185,8 +195,8 @@ extern "C" int bbx_channel_medians(const float *img, int H, int W, int ysize_cha
     ChanSel *sel = (ChanSel *)work;
     const unsigned long long n = (unsigned long long)ysize_chan * xsize_chan;
     const int rows_per_block = 64;
-    const int runs = rows_per_block * ((xsize_chan + CS_RUN - 1) / CS_RUN);
-    dim3 grid((unsigned int)max(1, min(4, (runs + CS_THREADS * 4 - 1) / (CS_THREADS * 4))),
+    const int groups = rows_per_block * (xsize_chan / 4);
+    dim3 grid((unsigned int)max(1, min(4, (groups + CS_THREADS * 8 - 1) / (CS_THREADS * 8))),
               (unsigned int)ceil_div(ysize_chan, rows_per_block), BBX_NCHAN);
     cs_init_kernel<<<BBX_NCHAN, CS_THREADS, 0, st>>>(sel, n);
     cs_hist_kernel<0><<<grid, CS_THREADS, 0, st>>>(img, W, ysize_chan, xsize_chan, rows_per_block, sel);

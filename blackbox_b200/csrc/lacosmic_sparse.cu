@@ -29,10 +29,10 @@
 //
 // The reference's background level (lower median of all unmasked pixels of the INPUT image,
 // used for CR pixels without any usable neighbour -- the interior of a fat cosmic-ray blob, which
-// sigfrac = 0.01 makes common) costs no extra pass: a strided sample of 4096 pixels brackets the
+// sigfrac = 0.01 makes common) costs no extra pass: a strided sample of 32768 pixels brackets the
 // median rank (+-5 sigma of the sampling error); the dense scan, which touches every pixel
 // anyway, counts the unmasked pixels below the bracket and histograms those inside it with ONE
-// BIN PER FLOAT32 KEY (the bracket is a few e- wide: ~1e5 distinct keys, a 4 MB table of global
+// BIN PER FLOAT32 KEY (the bracket is an e- or two wide: a few 1e4 distinct keys, a 4 MB table of global
 // atomics with next to no contention); the median is the key whose cumulative count reaches the
 // wanted rank.  Exact, no list of values, no selection passes.  If the bracket misses (or is
 // wider than the table) and the level is then actually needed, LAC_STATUS_NEED_BG is raised and
@@ -59,7 +59,7 @@ struct SparseCounters {
     unsigned int nQ;                     // list Q (shares the storage of list B, which is spent by then)
 };
 
-#define BG_SAMPLES 4096u
+#define BG_SAMPLES 32768u
 #define BG_BINS (1u << 20)
 
 struct BgState {
@@ -354,49 +354,104 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
 }
 
 // ---- background level ----------------------------------------------------------------------
-// One block: gather a strided sample of the unmasked pixels into shared memory, bitonic-sort it
-// and bracket the median rank by +-(2.5 sqrt(ns) + 8) sample ranks (5 sigma of the binomial
-// sampling error of the median's rank).
+// One block: a strided sample of BG_SAMPLES unmasked pixels brackets the median rank by
+// +-(2.625 sqrt(ns) + 8) sample ranks (5.25 sigma of the binomial sampling error of the median's
+// rank).  The two bracketing sample order statistics are located with a two-pass radix select
+// (11 + 11 key bits) on the sample held in shared memory; the remaining 10 bits are rounded
+// outwards, which widens the bracket by at most 2 x 1024 of its ~1e5 keys.
+#define BG_SEL_BINS 2048
+
+__device__ __forceinline__ void bg_find_bin(const unsigned int *hist, unsigned int rank, unsigned int *part,
+                                            unsigned int *out_bin, unsigned int *out_rank)
+{
+    // 1024 threads: warp q sums bins [64 q, 64 q + 64); thread 0 walks the 32 warp sums, then
+    // the 64 bins of the warp that holds the rank
+    const int t = threadIdx.x, lane = t & 31, wq = t >> 5;
+    const unsigned int mine = (unsigned int)warp_sum((int)(hist[2 * t] + hist[2 * t + 1]));
+    if (lane == 0) part[wq] = mine;
+    __syncthreads();
+    if (t == 0) {
+        unsigned int acc = 0;
+        int seg = 31;
+        for (int q = 0; q < 32; q++) {
+            if (acc + part[q] > rank) { seg = q; break; }
+            acc += part[q];
+        }
+        unsigned int bin = 64 * seg + 63;
+        for (int j = 0; j < 64; j++) {
+            const unsigned int hv = hist[64 * seg + j];
+            if (acc + hv > rank) { bin = 64 * seg + j; break; }
+            acc += hv;
+        }
+        *out_bin = bin;
+        *out_rank = rank - acc;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024)
 sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
 {
-    __shared__ unsigned int smp[BG_SAMPLES];            // float32 keys
-    __shared__ unsigned int s_ns;
-    if (threadIdx.x == 0) s_ns = 0;
-    for (unsigned int j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) smp[j] = 0xffffffffu;
+    extern __shared__ unsigned int smp[];               // [BG_SAMPLES] float32 keys of the sample
+    __shared__ unsigned int hist[2][BG_SEL_BINS];
+    __shared__ unsigned int part[1024];
+    __shared__ unsigned int s_ns, s_bin[2], s_rank[2], s_sub[2], s_dummy;
+    const int t = threadIdx.x;
+    if (t == 0) s_ns = 0;
+    for (int i = t; i < 2 * BG_SEL_BINS; i += 1024) (&hist[0][0])[i] = 0;
     __syncthreads();
     const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
-    for (size_t j = threadIdx.x; j < BG_SAMPLES; j += blockDim.x) {
-        const size_t i = j * stride;
-        if (i >= n) break;
-        if (inmask && inmask[i]) continue;
-        const float v = img[i];
-        if (v != v) continue;                           // NaNs are left to the full-frame statistics
-        smp[atomicAdd(&s_ns, 1u)] = f32_key(v);
+    {
+        // the top 11 key bits are the same for practically the whole sample of a sky-dominated
+        // frame: count runs per thread instead of hammering one shared-memory word
+        unsigned int run_bin = 0xffffffffu, run = 0;
+        for (size_t j = t; j < BG_SAMPLES; j += 1024) {
+            const size_t i = j * stride;
+            if (i >= n) break;
+            if (inmask && inmask[i]) continue;
+            const float v = img[i];
+            if (v != v) continue;                       // NaNs are left to the full-frame statistics
+            const unsigned int key = f32_key(v);
+            smp[atomicAdd(&s_ns, 1u)] = key;
+            if ((key >> 21) == run_bin) { run++; continue; }
+            if (run) atomicAdd(&hist[0][run_bin], run);
+            run_bin = key >> 21; run = 1;
+        }
+        if (run) atomicAdd(&hist[0][run_bin], run);
     }
     __syncthreads();
     const unsigned int ns = s_ns;
-    for (unsigned int k = 2; k <= BG_SAMPLES; k <<= 1)
-        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned int i = threadIdx.x; i < BG_SAMPLES; i += blockDim.x) {
-                const unsigned int l = i ^ j;
-                if (l > i) {
-                    const unsigned int x = smp[i], y = smp[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { smp[i] = y; smp[l] = x; }
-                }
-            }
-            __syncthreads();
+    unsigned int key_a = 0, width = 0;
+    bool ok = false;
+    unsigned int mid = 0, d = 0;
+    if (ns > 0) {
+        mid = (ns - 1) / 2;
+        d = (unsigned int)(2.625f * sqrtf((float)ns)) + 8u;
+        ok = mid > d && mid + d < ns - 1;
+    }
+    if (ok) {                                           // block-uniform
+        // pass 1: the top 11 bits of both order statistics
+        bg_find_bin(hist[0], mid - d, part, &s_bin[0], &s_rank[0]);
+        bg_find_bin(hist[0], mid + d, part, &s_bin[1], &s_rank[1]);
+        const unsigned int b0 = s_bin[0], b1 = s_bin[1];
+        for (int i = t; i < 2 * BG_SEL_BINS; i += 1024) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        // pass 2: the next 11 bits inside those two bins
+        for (unsigned int j = t; j < ns; j += 1024) {
+            const unsigned int key = smp[j], top = key >> 21, sub = (key >> 10) & 2047u;
+            if (top == b0) atomicAdd(&hist[0][sub], 1u);
+            if (top == b1) atomicAdd(&hist[1][sub], 1u);
         }
-    if (threadIdx.x == 0) {
-        unsigned int key_a = 0, width = 0;
-        if (ns > 0) {
-            const unsigned int mid = (ns - 1) / 2, d = (unsigned int)(2.5f * sqrtf((float)ns)) + 8u;
-            if (mid > d && mid + d < ns - 1) {
-                const unsigned int ka = smp[mid - d], kb = smp[mid + d];
-                if (kb - ka < BG_BINS) { key_a = ka; width = kb - ka + 1u; }
-            }
+        __syncthreads();
+        bg_find_bin(hist[0], s_rank[0], part, &s_sub[0], &s_dummy);
+        bg_find_bin(hist[1], s_rank[1], part, &s_sub[1], &s_dummy);
+        if (t == 0) {
+            const unsigned int ka = (b0 << 21) | (s_sub[0] << 10);                    // rounded down
+            const unsigned int kb = (b1 << 21) | (s_sub[1] << 10) | 1023u;            // rounded up
+            if (kb >= ka && kb - ka < BG_BINS) { key_a = ka; width = kb - ka + 1u; }
         }
+    }
+    if (t == 0) {
         w.bg->key_a = key_a; w.bg->width = width;
         w.bg->n_valid = 0; w.bg->n_below = 0;
     }
@@ -767,7 +822,13 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
         if (bbx_masked_lower_median(img, inmask, n, w.sel, w.background, st)) return -2;
     } else {
         BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
-        sp_bg_sample_kernel<<<1, 1024, 0, st>>>(img, inmask, n, w);
+        static bool smem_set = false;
+        if (!smem_set) {
+            BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(sizeof(unsigned int) * BG_SAMPLES)));
+            smem_set = true;
+        }
+        sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(img, inmask, n, w);
     }
     sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt, with_background ? 1u : 0u);
     BBX_CHECK_LAUNCH("sparse_begin");

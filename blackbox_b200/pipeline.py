@@ -51,7 +51,8 @@ class FramePipeline:
     """
 
     def __init__(self, tel, raw_shape, mbias=None, mflat=None, bpm=None, coeffs=None, niter=None,
-                 xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True, use_graphs=False):
+                 xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True, use_graphs=False,
+                 fill_edge=False):
         self.tel = tel
         self.device = device if device is not None else R._device()
         self.geom = Geometry.from_raw_shape(tuple(raw_shape), xbin=xbin, ybin=ybin, tel=tel)
@@ -72,6 +73,11 @@ class FramePipeline:
         self.crmask = torch.empty((RH, RW), dtype=torch.uint8, device=dev)
         self.means = torch.zeros(2, dtype=torch.float64, device=dev)      # BIASMEAN, RDNOISE
         self.ncosmic = torch.zeros(1, dtype=torch.int32, device=dev)
+        # optional last step of blackbox_reduce (blackbox.py:1958-1974): edge pixels -> channel median
+        self.fill_edge = bool(fill_edge)
+        self.chan_med = torch.zeros(self.geom.nchans, dtype=torch.float32, device=dev)
+        self._cm_work = (torch.empty(R.query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=dev)
+                         if self.fill_edge else None)
         # pinned status words of stage B: [0:4] mask morphology (int32), [8:16] LACosmic (int64)
         self._status_host = torch.zeros(16, dtype=torch.uint8).pin_memory()
         self._ev_a = torch.cuda.Event()
@@ -231,6 +237,14 @@ class FramePipeline:
 
         if self.coeffs is not None:
             run('xtalk', tail)
+        if self.fill_edge:
+            def edge():
+                ysc, xsc = geom.ysize_chan, geom.xsize_chan
+                call('bbx_channel_medians', R._ptr(out_img), RH, RW, ysc, xsc, R._ptr(self._cm_work),
+                     R._ptr(self.chan_med), R._stream())
+                call('bbx_fill_edge', R._ptr(out_img), R._ptr(out_mask), RH, RW, ysc, xsc,
+                     int(get_par(set_bb.mask_value, tel)['edge']), R._ptr(self.chan_med), R._stream())
+            run('edge_fill', edge)
         run('status', status)
 
     def stage_b_enqueue(self, raw_t, out_img, out_mask):
@@ -380,13 +394,19 @@ class BatchReducer:
         return results
 
     # ---------------------------------------------------------------------------------------
-    def run_host(self, host_raws, host_imgs, host_masks, fill_header=False):
+    def run_host(self, host_raws, host_imgs, host_masks, fill_header=False, fits=False):
         """The same batch with HOST buffers on both sides: ``host_raws`` pinned uint16 (or
         float32) raw frames, ``host_imgs`` / ``host_masks`` pinned float32 / uint8 outputs (rings:
         frame k goes to index k % len; a ring slot must have been consumed by the caller before
         its next use comes up).  Host-to-device copies, the chain and device-to-host copies run
         on their own streams, ``depth`` frames in flight.  Returns the FrameResults; the host
-        outputs of all frames are complete on return."""
+        outputs of all frames are complete on return.
+
+        ``fits``: the host buffers hold FITS data units as they are on disk -- ``host_raws`` the
+        big-endian 16-bit data unit of a raw frame (BZERO 32768; ``fitsio.read_primary(...,
+        pinned=True)`` reshaped to the frame, any 2-byte dtype), ``host_imgs`` receives the
+        big-endian float32 data unit of the reduced image (``fitsio.write_primary(..., be_bytes=True)``).
+        The byte swaps run on the device, in place, next to the copies."""
         n, d = len(host_raws), self.depth
         if n == 0:
             return []
@@ -410,6 +430,9 @@ class BatchReducer:
             j = k % d
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(self._ev_done[j])
+                if fits:
+                    img = self._hbuf[j][1]
+                    call('bbx_fits_encode', R._ptr(img), -32, 0, img.numel(), R._ptr(img), R._stream())
                 host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
                 host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
                 self._ev_out[j].record()
@@ -430,6 +453,9 @@ class BatchReducer:
             with torch.cuda.stream(self._s_in):
                 self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
                 self._hbuf[j][0].copy_(host_raws[k], non_blocking=True)
+                if fits:
+                    raw = self._hbuf[j][0]
+                    call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
                 self._ev_in[j].record()
             with torch.cuda.stream(self.hi_streams[j]):
                 self.hi_streams[j].wait_event(self._ev_in[j])

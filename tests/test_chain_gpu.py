@@ -123,3 +123,61 @@ def test_batch_reducer_equals_single_pipeline(depth, graphs, prio, small_bb):
             assert np.array_equal(host_imgs[k].numpy(), img, equal_nan=True), (rep, k)
             assert np.array_equal(host_masks[k].numpy(), mask), (rep, k)
             assert results[k].header['NCOSMICS'] == nc
+
+
+def test_run_host_with_fits_data_units(small_bb, tmp_path):
+    """Raw FITS file -> pinned big-endian bytes -> run_host(fits=True) -> big-endian float32 bytes
+    -> reduced FITS file: the file reads back to the image the plain pipeline produces."""
+    import torch
+    from blackbox_b200 import fitsio
+    from blackbox_b200.pipeline import BatchReducer, FramePipeline
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw0, mbias, mflat, bpm, coeffs = _inputs(tel, 4300, ysc)
+    raws = [raw0, _inputs(tel, 4301, ysc)[0], _inputs(tel, 4302, ysc)[0]]
+    kw = dict(mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=2)
+    single = FramePipeline(tel, raw0.shape, **kw)
+    want = []
+    for r in raws:
+        res = single.reduce(r)
+        want.append((res.img.cpu().numpy().copy(), res.mask.cpu().numpy().copy()))
+    host_raws = []
+    for k, r in enumerate(raws):
+        path = str(tmp_path / 'raw{}.fits'.format(k))
+        fitsio.write_primary(path, r, {'EXPTIME': 60.0})
+        _, buf, info = fitsio.read_primary(path, pinned=True)
+        assert info['bitpix'] == 16 and info['bzero'] == 32768.0
+        host_raws.append(buf.view(torch.uint16).view(info['shape']))
+    shape = (2 * ysc, 10560)
+    host_imgs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in raws]
+    host_masks = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in raws]
+    batch = BatchReducer(tel, raw0.shape, depth=3, **kw)
+    for rep in range(2):
+        batch.run_host(host_raws, host_imgs, host_masks, fits=True)
+        for k, (img, mask) in enumerate(want):
+            out = str(tmp_path / 'red{}.fits'.format(k))
+            fitsio.write_primary(out, host_imgs[k].view(torch.uint8).reshape(-1), {'REDFILE': 'x'}, be_bytes=True,
+                                 shape=shape, bitpix=-32)
+            _, data, info = fitsio.read_primary(out)
+            assert np.array_equal(fitsio.to_native(data, info), img, equal_nan=True), (rep, k)
+            assert np.array_equal(host_masks[k].numpy(), mask), (rep, k)
+
+
+def test_pipeline_edge_fill_option(small_bb):
+    """fill_edge=True appends the edge-pixel fill of blackbox.py:1958-1974 to the chain."""
+    from blackbox_b200.pipeline import FramePipeline
+    from oracle import reduce as R
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw, mbias, mflat, bpm, coeffs = _inputs(tel, 4400, ysc)
+    data_o, mask_o, _, _ = R.reduce_frame(raw, tel, mbias, mflat, bpm, coeffs, niter=2)
+    meds_o = R.fill_edge_pixels(data_o, mask_o, tel=tel)
+    pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=2, fill_edge=True)
+    res = pipe.reduce(raw)
+    img, mask = res.img.cpu().numpy(), res.mask.cpu().numpy()
+    assert np.array_equal(mask, mask_o)
+    edge = (mask & 32) != 0
+    assert edge.sum() > 1000
+    np.testing.assert_allclose(pipe.chan_med.cpu().numpy(), meds_o, rtol=1e-5)
+    assert np.mean(img == data_o) > 0.999
+    assert np.allclose(img[edge], data_o[edge], rtol=1e-5)

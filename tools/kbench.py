@@ -98,6 +98,10 @@ def main():
     timeit('lacosmic_4it', lac_all, 4460.5e6, setup=lac_setup)
     timeit('lacosmic_begin', lac_begin, setup=lac_setup)
     timeit('lacosmic_it0', lac_it0, 1115.1e6, setup=lambda: (lac_setup(), lac_begin()))
+    R.tel = tel
+    e_img = img.clone()
+    timeit('channel_medians', lambda: R.channel_medians(e_img), 3 * 446.1e6)
+    timeit('fill_edge_pixels', lambda: R.fill_edge_pixels(e_img, mask), 3 * 446.1e6 + 111.5e6)
     print('info', work.info.cpu().numpy())
 
 
