@@ -413,7 +413,7 @@ def stage_rooflines(pipes):
             'unit': 'GB/s', 'frac': best['frac'], 'traffic': traffic.get(kname),
             'ms_per_launch': best['ms_per_frame'], 'launches_timed': best['frames'],
             'algorithmic_bytes': best['algorithmic_bytes'], 'peak_source': how,
-            'note': 'dominant single kernel by mean device time inside the timed region (two frames in '
+            'note': 'dominant single kernel by mean device time inside the timed region (several frames in '
                     'flight: other streams\' kernels share the GPU during the launch)'}
     return roof, stages
 

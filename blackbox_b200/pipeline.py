@@ -123,6 +123,8 @@ class FramePipeline:
         g = self._graphs.get((name, key)) if self.use_graphs else 'eager'
         if g is None:
             fn()
+            if len(self._graphs) > 4096:               # callers that never reuse buffers: forget the markers
+                self._graphs = {k: v for k, v in self._graphs.items() if not isinstance(v, str)}
             self._graphs[(name, key)] = 'seen'
         elif g == 'seen':
             graph = torch.cuda.CUDAGraph()

@@ -62,11 +62,46 @@ def lacosmic_case(seed):
             'clean_sha256': digest(clean), 'ncr': int(crmask.sum())}
 
 
+def extras_case(seed):
+    """Master combine (plain and sigma-clipped), nonlin_corr, edge-pixel fill, FITS round trip."""
+    from scipy import interpolate
+    rng = np.random.default_rng(seed)
+    saved = (set_bb.ysize_chan, set_bb.xsize_chan)
+    set_bb.ysize_chan, set_bb.xsize_chan = 24, 40
+    try:
+        shape = (48, 320)
+        frames = [(1000 + 10 * rng.standard_normal(shape)).astype(np.float32) for _ in range(20)]
+        for k in (0, 7, 13):
+            hit = rng.random(shape) < 0.03
+            frames[k][hit] += rng.uniform(100, 5000, hit.sum()).astype(np.float32)
+        plain, _ = R.master_median(frames, 'bias')
+        clipped = R.master_median_clipped(frames, sigma=3.0, maxiters=5)
+        splines = []
+        for i in range(16):
+            x = np.linspace(0, 60000, 80)
+            y = 2e-3 * np.sin(x / (7000.0 + 300 * i)) - 3e-7 * x + 2e-4 * rng.standard_normal(x.size)
+            splines.append(interpolate.UnivariateSpline(x, y, k=3, s=x.size * 4e-8))
+        data = rng.uniform(-500, 140000, size=shape).astype(np.float32)
+        nl = R.nonlin_corr(data.copy(), splines, tel='BG3')
+        mask = np.zeros(shape, dtype=np.uint8)
+        mask[:2] = 32
+        mask[:, -3:] = 33
+        filled = data.copy()
+        meds = R.fill_edge_pixels(filled, mask, tel='BG3')
+    finally:
+        set_bb.ysize_chan, set_bb.xsize_chan = saved
+    return {'seed': seed, 'median20_sha256': digest(plain), 'clipped20_sha256': digest(clipped),
+            'clipped_differs_from_plain': int((plain != clipped).sum()),
+            'nonlin_sha256': digest(nl), 'nonlin_spots': spots(nl),
+            'edge_fill_sha256': digest(filled), 'channel_medians': [float(m) for m in meds]}
+
+
 def main():
     saved = (set_bb.ysize_chan, dict(set_bb.hos_sat_ypix_lim))
     out = {'numpy': np.__version__,
            'chain': [chain_case('ML1', 1001), chain_case('BG3', 4001), chain_case('BG2', 4002, niter=1)],
-           'lacosmic': [lacosmic_case(3), lacosmic_case(4)]}
+           'lacosmic': [lacosmic_case(3), lacosmic_case(4)],
+           'extras': [extras_case(7)]}
     set_bb.ysize_chan, set_bb.hos_sat_ypix_lim = saved
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden.json')
     with open(path, 'w') as fh:

@@ -181,3 +181,54 @@ def test_pipeline_edge_fill_option(small_bb):
     np.testing.assert_allclose(pipe.chan_med.cpu().numpy(), meds_o, rtol=1e-5)
     assert np.mean(img == data_o) > 0.999
     assert np.allclose(img[edge], data_o[edge], rtol=1e-5)
+
+
+def _bimodal_raw(tel, seed, ysc):
+    """A frame whose median sits between two populations (sky / bright nebula half) with a fat
+    cosmic-ray blob: the lazy LACosmic needs the background level and its sampled bracket misses."""
+    from blackbox_b200 import set_bb, synth
+    sky, _ = synth.make_sky(tel, seed, ysc, set_bb.xsize_chan, nstars=50, ncosmics=40)
+    half = int(sky.shape[1] * 0.505)              # the median rank sits just inside the dark half: the bracket straddles both
+    rng = np.random.default_rng(seed)
+    sky[:, half:] += 9000.0 + 60.0 * rng.standard_normal((sky.shape[0], sky.shape[1] - half)).astype(np.float32)
+    sky[70:83, 300:313] += rng.uniform(8000, 20000, (13, 13)).astype(np.float32)
+    raw, _ = synth.make_raw(tel, seed, sky=sky)
+    return raw
+
+
+def test_chain_redo_when_the_lazy_lacosmic_needs_the_background(small_bb):
+    """FramePipeline.finish repeats the stage-B chain with the background level computed up
+    front when the lazy path reports that it needs it; the result is the oracle's.  The same
+    frame in the middle of a BatchReducer run (graphs on) is redone without disturbing its
+    neighbours."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from blackbox_b200.pipeline import BatchReducer, FramePipeline
+    from oracle import reduce as R
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw0, mbias, mflat, bpm, coeffs = _inputs(tel, 4500, ysc)
+    bad = _bimodal_raw(tel, 4501, ysc)
+    kw = dict(mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=3)
+    data_o, mask_o, hdr_o, _ = R.reduce_frame(bad, tel, mbias, mflat, bpm, coeffs, niter=3)
+    pipe = FramePipeline(tel, bad.shape, **kw)
+    res = pipe.reduce(bad)
+    assert res.redo
+    assert np.mean(res.mask.cpu().numpy() != mask_o) <= 1e-5
+    assert np.mean(res.img.cpu().numpy() == data_o) > 0.999
+    want_bad = (res.img.cpu().numpy().copy(), res.mask.cpu().numpy().copy())
+    res0 = pipe.reduce(raw0)
+    assert not res0.redo
+    want0 = (res0.img.cpu().numpy().copy(), res0.mask.cpu().numpy().copy())
+    raws = [bbr._to_dev(r) for r in (raw0, bad, raw0, raw0, bad, raw0)]
+    batch = BatchReducer(tel, raw0.shape, depth=4, use_graphs=True, **kw)
+    imgs = [torch.empty_like(res.img) for _ in raws]
+    masks = [torch.empty_like(res.mask) for _ in raws]
+    for rep in range(3):
+        results = batch.run(raws, imgs, masks)
+        torch.cuda.synchronize()
+        for k, r in enumerate(results):
+            want = want_bad if k in (1, 4) else want0
+            assert r.redo == (k in (1, 4)), (rep, k)
+            assert np.array_equal(imgs[k].cpu().numpy(), want[0], equal_nan=True), (rep, k)
+            assert np.array_equal(masks[k].cpu().numpy(), want[1]), (rep, k)
