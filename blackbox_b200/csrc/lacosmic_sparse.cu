@@ -216,7 +216,7 @@ __device__ __forceinline__ void sp_scan_pixel(const float *__restrict__ img, con
 }
 
 template <bool COLLECT>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 8)
 sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, uint8_t *__restrict__ crmask,
                int H, int W, LacParams prm, SparseWork w, long long *info)
 {

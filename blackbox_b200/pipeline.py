@@ -269,16 +269,6 @@ class FramePipeline:
         self._overscan(raw_t)
         return self.stage_b_enqueue(raw_t, out_img, out_mask)
 
-    def enqueue_status(self, host_slot):
-        """Enqueue a copy of the frame's status (hole filling unconverged | lazy LACosmic
-        incomplete) into the pinned int32[1] tensor ``host_slot`` (valid after the stream is
-        synchronised): non-zero means the frame has to be finished with ``finish()`` before its
-        outputs are used."""
-        stat = self.mwork.status[0:1]
-        if self.niter > 0:
-            stat = stat | self.lwork.info[2:3].to(torch.int32)
-        host_slot.copy_(stat, non_blocking=True)
-
     # ---------------------------------------------------------------------------------------
     def finish(self, fill_header=True):
         """Wait for stage B of the last enqueued frame, verify its device status and return its

@@ -232,3 +232,43 @@ def test_chain_redo_when_the_lazy_lacosmic_needs_the_background(small_bb):
             assert r.redo == (k in (1, 4)), (rep, k)
             assert np.array_equal(imgs[k].cpu().numpy(), want[0], equal_nan=True), (rep, k)
             assert np.array_equal(masks[k].cpu().numpy(), want[1]), (rep, k)
+
+
+def test_reduce_night_tool_files_in_files_out(small_bb, tmp_path):
+    """tools/reduce_night.py: raw FITS files in, _red.fits / _mask.fits out, equal to the
+    oracle's chain; header keywords of the reduction steps end up in the files."""
+    import importlib.util
+    import os
+    from blackbox_b200 import fitsio, synth
+    from oracle import reduce as R
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw_dir, out_dir = tmp_path / 'raw', tmp_path / 'red'
+    raw_dir.mkdir()
+    raws = [_inputs(tel, 4600 + k, ysc)[0] for k in range(3)]
+    _, mbias, mflat, bpm, coeffs = _inputs(tel, 4600, ysc)
+    for k, r in enumerate(raws):
+        fitsio.write_primary(str(raw_dir / 'BG3_2026_{:02d}.fits'.format(k)), r, {'EXPTIME': 60.0, 'FILTER': 'q'})
+    fitsio.write_primary(str(tmp_path / 'mbias.fits'), mbias)
+    fitsio.write_primary(str(tmp_path / 'mflat.fits'), mflat)
+    fitsio.write_primary(str(tmp_path / 'bpm.fits'), bpm)
+    victim, source, corr, _ = synth.make_xtalk(4602)
+    synth.write_xtalk_file(str(tmp_path / 'xtalk.txt'), victim, source, corr)
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('reduce_night', os.path.join(here, 'tools', 'reduce_night.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    n = tool.main([str(raw_dir), str(out_dir), '--tel', tel, '--mbias', str(tmp_path / 'mbias.fits'),
+                   '--mflat', str(tmp_path / 'mflat.fits'), '--bpm', str(tmp_path / 'bpm.fits'),
+                   '--xtalk', str(tmp_path / 'xtalk.txt'), '--niter', '2'])
+    assert n == 3
+    for k, r in enumerate(raws):
+        data_o, mask_o, hdr_o, _ = R.reduce_frame(r, tel, mbias, mflat, bpm, coeffs, niter=2)
+        h, d, info = fitsio.read_primary(str(out_dir / 'BG3_2026_{:02d}_red.fits'.format(k)))
+        img = fitsio.to_native(d, info)
+        _, m, _ = fitsio.read_primary(str(out_dir / 'BG3_2026_{:02d}_mask.fits'.format(k)))
+        assert np.mean(np.asarray(m) != mask_o) <= 1e-5
+        assert np.mean(img == data_o) > 0.999
+        assert h['FILTER'][0] == 'q' and h['REDFILE'][0].endswith('_red')
+        assert h['BIASMEAN'][0] == pytest.approx(hdr_o['BIASMEAN'], rel=1e-9)
+        assert h['NOBJ-SAT'][0] == hdr_o['NOBJ-SAT']
