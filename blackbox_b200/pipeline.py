@@ -338,6 +338,10 @@ class BatchReducer:
         # stage A runs `ahead` frames in front of stage B; a slot is recycled only once its frame
         # is two behind the one being enqueued, so the host never waits for the frame in progress
         self.ahead = max(1, min(self.depth - 2, 2 if ahead is None else int(ahead))) if self.depth > 2 else 1
+        # the masters go to the device once and are shared by all pipelines
+        for name, dt in (('mbias', torch.float32), ('mflat', torch.float32), ('bpm', torch.uint8)):
+            if pipeline_kwargs.get(name) is not None:
+                pipeline_kwargs[name] = R._to_dev(pipeline_kwargs[name], dt)
         self.pipes = [FramePipeline(tel, raw_shape, **pipeline_kwargs) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
         self.hi_streams = ([torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
