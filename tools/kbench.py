@@ -98,6 +98,17 @@ def main():
     timeit('lacosmic_4it', lac_all, 4460.5e6, setup=lac_setup)
     timeit('lacosmic_begin', lac_begin, setup=lac_setup)
     timeit('lacosmic_it0', lac_it0, 1115.1e6, setup=lambda: (lac_setup(), lac_begin()))
+    if not only or only & {'stack20_bias', 'stack20_flat', 'stack20_clipped'}:
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(1)
+        frames = [torch.randn((H, W), generator=gen, device='cuda') * 100 + 20000 for _ in range(20)]
+        medsec = [20000.0 + 10 * k for k in range(20)]
+        out = torch.empty((H, W), dtype=torch.float32, device='cuda')
+        nb = 21 * H * W * 4
+        timeit('stack20_bias', lambda: R.master_combine(frames, 'bias', out=out), nb)
+        timeit('stack20_flat', lambda: R.master_combine(frames, 'flat', medsec=medsec, bpm=pipe.bpm, tel=tel, out=out), nb + H * W)
+        timeit('stack20_clipped', lambda: R.master_combine(frames, 'bias', out=out, clip_sigma=3.0), nb)
+        del frames
     R.tel = tel
     e_img = img.clone()
     timeit('channel_medians', lambda: R.channel_medians(e_img), 3 * 446.1e6)
