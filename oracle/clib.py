@@ -29,7 +29,7 @@ def clip_bounds(v, valid, use_median, maxiters, sig_lo, sig_hi):
     lo = np.empty(ns)
     hi = np.empty(ns)
     lib().bbo_clip_bounds(_p(v), _p(valid), C.c_long(ns), C.c_long(n), C.c_int(int(use_median)),
-                          C.c_int(-1 if np.isinf(maxiters) else int(maxiters)),
+                          C.c_int(-1 if (maxiters is None or np.isinf(maxiters)) else int(maxiters)),
                           C.c_double(sig_lo), C.c_double(sig_hi), _p(lo), _p(hi))
     return lo, hi
 

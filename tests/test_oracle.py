@@ -277,3 +277,23 @@ def test_os_corr_recovers_injected_levels(small_bb):
         assert hdr['VFITOK{}'.format(i + 1)] is True
     # the sky level (150 ADU) survives, the bias level (3050 ADU) does not
     assert 250 < np.median(out) < 400
+
+
+def test_sigma_clip_mean_matches_scipy_sigmaclip():
+    """An independent published implementation of the same loop: scipy.stats.sigmaclip (mean and
+    population std of the survivors, keep lo <= x <= hi, until nothing is rejected) is
+    astropy's sigma_clip with cenfunc='mean' and no iteration limit.  The restatement must keep
+    the same survivors and end on the same bounds."""
+    from scipy import stats as sstats
+    from oracle.stats import sigma_clip
+    rng = np.random.default_rng(8)
+    for n, nout in [(50, 3), (1000, 40), (5000, 0), (7, 1)]:
+        x = rng.normal(100.0, 5.0, n)
+        x[:nout] += rng.uniform(30, 500, nout)
+        for sig in (2.0, 3.0):
+            kept, lo, hi = sstats.sigmaclip(x, sig, sig)
+            ours = sigma_clip(x, sigma=sig, maxiters=None, cenfunc='mean', masked=True)
+            assert np.array_equal(np.sort(ours.compressed()), np.sort(kept)), (n, nout, sig)
+            surv = ours.compressed()
+            assert lo == pytest.approx(surv.mean() - sig * surv.std(), rel=1e-12)
+            assert hi == pytest.approx(surv.mean() + sig * surv.std(), rel=1e-12)
