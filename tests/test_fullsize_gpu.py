@@ -91,15 +91,15 @@ def test_fullsize_xtalk_rows_against_oracle(full, small_bb):
 
 
 def test_fullsize_lacosmic_against_oracle(full):
-    """detect_cosmics on the full 10560^2 frame (reference settings: sigclip 20, sigfrac 0.01,
-    objlim 3, niter 3; set_blackbox.py:211-218) against the C oracle: mask and cleaned image
-    bit for bit."""
+    """BASELINE.json config 3: detect_cosmics, 4 iterations, on the full 10560^2 reduced frame
+    (reference settings otherwise: sigclip 20, sigfrac 0.01, objlim 3; set_blackbox.py:211-218)
+    against the C oracle: mask and cleaned image bit for bit."""
     from blackbox_b200 import reduce as bbr
     from oracle import lacosmic as L
     rn = float(full['hdr_pre']['RDNOISE'])
     inmask = (full['mask_pre'] != 0)
     info_g, info_o = {}, {}
-    kw = dict(sigclip=20, sigfrac=0.01, objlim=3, gain=1.0, readnoise=rn, satlevel=np.inf, niter=3,
+    kw = dict(sigclip=20, sigfrac=0.01, objlim=3, gain=1.0, readnoise=rn, satlevel=np.inf, niter=4,
               sepmed=False, cleantype='medmask')
     cr_g, clean_g = bbr.detect_cosmics(full['img_pre'], inmask=inmask, info=info_g, **kw)
     cr_o, clean_o = L.detect_cosmics(full['img_pre'].cpu().numpy(), inmask.cpu().numpy(), info=info_o, **kw)
@@ -196,3 +196,33 @@ def test_fullsize_master_flat_of_20(full):
         le += (v <= master).to(torch.int16)
         ge += (v >= master).to(torch.int16)
     assert int(le[free].min()) >= n // 2 and int(ge[free].min()) >= n // 2
+
+
+def test_fullsize_config1_meerlicht_chain_against_oracle():
+    """BASELINE.json config 1 at full size: one MeerLICHT 10600 x 12000 raw frame through gain +
+    overscan + mask_init + master flat + crosstalk (ML1 subtracts no master bias,
+    set_blackbox.py:37) against the oracle's whole-frame result."""
+    import torch
+    from conftest import float_class_ok
+    from blackbox_b200 import set_bb, synth
+    from blackbox_b200.pipeline import FramePipeline
+    from oracle import reduce as R
+    tel = 'ML1'
+    raw, _ = synth.make_raw(tel, 1001)
+    shape = (10560, 10560)
+    mbias, mflat, bpm = synth.make_masters(tel, 1002, shape)
+    coeffs = synth.make_xtalk(1003)[3]
+    data_o, mask_o, hdr_o, _ = R.reduce_frame(raw, tel, mbias, mflat, bpm, coeffs,
+                                              steps=('gain', 'os', 'bias', 'mask', 'flat', 'xtalk'))
+    pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=0)
+    res = pipe.reduce(raw)
+    mask = res.mask.cpu().numpy()
+    assert np.array_equal(mask, mask_o)
+    assert hdr_o['NOBJ-SAT'] > 10 and res.header['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
+    for key in ('BIASMEAN', 'RDNOISE', 'SATURATE'):
+        assert res.header[key] == pytest.approx(hdr_o[key], rel=1e-9)
+    img = res.img.cpu().numpy()
+    del res, pipe
+    torch.cuda.empty_cache()
+    assert float_class_ok(img, data_o, scale=hdr_o['BIASMEAN']).all()
+    assert np.mean(img == data_o) > 0.999
