@@ -226,3 +226,48 @@ def test_fullsize_config1_meerlicht_chain_against_oracle():
     torch.cuda.empty_cache()
     assert float_class_ok(img, data_o, scale=hdr_o['BIASMEAN']).all()
     assert np.mean(img == data_o) > 0.999
+
+
+def test_fullsize_batch_reducer_equals_sequential(full):
+    """Full-size frames through BatchReducer (4 pipelines in flight, overscan stage two frames
+    ahead on high-priority streams, CUDA-graph replay) and through run_host: the bits of the
+    one-by-one pipeline, pass after pass."""
+    import torch
+    from blackbox_b200.pipeline import BatchReducer, FramePipeline
+    kw = dict(mbias=full['mbias'], mflat=full['mflat'], bpm=full['bpm'], coeffs=full['coeffs'], niter=4)
+    base = full['raw_t']
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(77)
+    raws = [base]
+    for _ in range(2):                                   # two more noise realisations of the frame
+        r = (base.view(torch.int16).to(torch.int32) & 0xffff) + torch.randint(-3, 4, base.shape, device='cuda',
+                                                                             generator=gen, dtype=torch.int32)
+        raws.append(r.clamp_(0, 65535).to(torch.int16).view(torch.uint16).contiguous())
+    single = FramePipeline(TEL, full['raw'].shape, **kw)
+    want = []
+    for r in raws:
+        res = single.reduce(r)
+        want.append((res.img.clone(), res.mask.clone()))
+    del single
+    order = [0, 1, 2, 1, 0, 2, 2]
+    frames = [raws[i] for i in order]
+    batch = BatchReducer(TEL, full['raw'].shape, depth=4, ahead=2, use_graphs=True, **kw)
+    imgs = [torch.empty_like(want[0][0]) for _ in order]
+    masks = [torch.empty_like(want[0][1]) for _ in order]
+    for rep in range(3):
+        results = batch.run(frames, imgs, masks)
+        torch.cuda.synchronize()
+        for k, i in enumerate(order):
+            assert not results[k].redo
+            assert torch.equal(imgs[k], want[i][0]), (rep, k)
+            assert torch.equal(masks[k], want[i][1]), (rep, k)
+    assert sum(p.graph_replays for p in batch.pipes) > 0
+    del imgs, masks
+    host_raws = [r.cpu().pin_memory() for r in raws]
+    host_imgs = [torch.empty(want[0][0].shape, dtype=torch.float32).pin_memory() for _ in raws]
+    host_masks = [torch.empty(want[0][1].shape, dtype=torch.uint8).pin_memory() for _ in raws]
+    for rep in range(2):
+        batch.run_host(host_raws, host_imgs, host_masks)
+        for i in range(len(raws)):
+            assert torch.equal(host_imgs[i], want[i][0].cpu()), (rep, i)
+            assert torch.equal(host_masks[i], want[i][1].cpu()), (rep, i)
