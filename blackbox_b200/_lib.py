@@ -72,7 +72,7 @@ _SIGNATURES = {
     'bbx_fits_decode': [P, I, I, SZ, P, P],
     'bbx_fits_encode': [P, I, I, SZ, P, P],
     'bbx_chanmed_work_bytes': [],
-    'bbx_channel_medians': [P, I, I, I, I, P, P, P],
+    'bbx_channel_medians': [P, I, I, I, I, I, P, P, P],
     'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],
 }
 _RESTYPES = {'bbx_fill_holes_work_bytes': SZ, 'bbx_lacosmic_work_bytes': SZ,

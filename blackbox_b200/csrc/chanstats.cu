@@ -20,6 +20,8 @@ struct ChanSel {
     unsigned int prefix[2];       // key bits fixed so far (right-aligned)
     unsigned int two;             // 1: two targets (even count), 0: one
     unsigned int nan_count;
+    unsigned long long n;         // pixels of the channel
+    unsigned int ignore_nan, pad; // 1: np.nanmedian (NaNs do not count), 0: np.median (any NaN -> NaN)
     unsigned int hist[2][CS_BINS];
 };
 
@@ -33,7 +35,7 @@ __device__ __forceinline__ float cs_unkey(unsigned int k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void cs_init_kernel(ChanSel *sel, unsigned long long n)
+__global__ void cs_init_kernel(ChanSel *sel, unsigned long long n, unsigned int ignore_nan)
 {
     ChanSel &s = sel[blockIdx.x];
     for (int i = threadIdx.x; i < 2 * CS_BINS; i += blockDim.x) (&s.hist[0][0])[i] = 0;
@@ -43,6 +45,8 @@ __global__ void cs_init_kernel(ChanSel *sel, unsigned long long n)
         s.k[1] = n / 2;
         s.prefix[0] = s.prefix[1] = 0;
         s.nan_count = 0;
+        s.n = n;
+        s.ignore_nan = ignore_nan; s.pad = 0;
     }
 }
 
@@ -121,6 +125,16 @@ cs_find_kernel(ChanSel *sel, float *out_med)
     __shared__ unsigned long long part[CS_THREADS];
     ChanSel &cs = sel[blockIdx.x];
     const int nb = PASS == 2 ? 1024 : CS_BINS, per = nb / CS_THREADS;
+    if (PASS == 0 && cs.ignore_nan) {                           // the ranks among the non-NaN pixels
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long m = cs.n - cs.nan_count;
+            cs.two = (m % 2 == 0 && m > 0) ? 1u : 0u;
+            cs.k[0] = m == 0 ? 0 : (cs.two ? m / 2 - 1 : m / 2);
+            cs.k[1] = m / 2;
+        }
+        __syncthreads();
+    }
     const int ntgt = cs.two ? 2 : 1;
     const bool shared_hist = PASS == 0 || cs.prefix[0] == cs.prefix[1];
     unsigned int newp[2] = {0, 0};
@@ -158,7 +172,7 @@ cs_find_kernel(ChanSel *sel, float *out_med)
         cs.k[0] = newk[0]; cs.k[1] = newk[1];
         if (PASS == 2) {
             float med;
-            if (cs.nan_count) med = __int_as_float(0x7fc00000);
+            if (cs.ignore_nan ? (cs.n == cs.nan_count) : (cs.nan_count != 0)) med = __int_as_float(0x7fc00000);
             else if (cs.two) { const float s = cs_unkey(newp[0]) + cs_unkey(newp[1]); med = s / 2.0f; }
             else med = cs_unkey(newp[0]);
             out_med[blockIdx.x] = med;
@@ -185,8 +199,8 @@ cs_fill_edge_kernel(float *img, const uint8_t *__restrict__ mask, int H, int W, 
 
 extern "C" size_t bbx_chanmed_work_bytes(void) { return sizeof(ChanSel) * BBX_NCHAN; }
 
-extern "C" int bbx_channel_medians(const float *img, int H, int W, int ysize_chan, int xsize_chan, void *work,
-                                   float *out_med, void *stream)
+extern "C" int bbx_channel_medians(const float *img, int H, int W, int ysize_chan, int xsize_chan, int ignore_nan,
+                                   void *work, float *out_med, void *stream)
 {
     BBX_REQUIRE(img && work && out_med, "bbx_channel_medians: null argument");
     BBX_REQUIRE(ysize_chan > 0 && xsize_chan > 0 && H == 2 * ysize_chan && W == 8 * xsize_chan,
@@ -198,7 +212,7 @@ extern "C" int bbx_channel_medians(const float *img, int H, int W, int ysize_cha
     const int groups = rows_per_block * (xsize_chan / 4);
     dim3 grid((unsigned int)max(1, min(4, (groups + CS_THREADS * 8 - 1) / (CS_THREADS * 8))),
               (unsigned int)ceil_div(ysize_chan, rows_per_block), BBX_NCHAN);
-    cs_init_kernel<<<BBX_NCHAN, CS_THREADS, 0, st>>>(sel, n);
+    cs_init_kernel<<<BBX_NCHAN, CS_THREADS, 0, st>>>(sel, n, ignore_nan ? 1u : 0u);
     cs_hist_kernel<0><<<grid, CS_THREADS, 0, st>>>(img, W, ysize_chan, xsize_chan, rows_per_block, sel);
     cs_find_kernel<0><<<BBX_NCHAN, CS_THREADS, 0, st>>>(sel, out_med);
     cs_hist_kernel<1><<<grid, CS_THREADS, 0, st>>>(img, W, ysize_chan, xsize_chan, rows_per_block, sel);

@@ -242,7 +242,7 @@ class FramePipeline:
         if self.fill_edge:
             def edge():
                 ysc, xsc = geom.ysize_chan, geom.xsize_chan
-                call('bbx_channel_medians', R._ptr(out_img), RH, RW, ysc, xsc, R._ptr(self._cm_work),
+                call('bbx_channel_medians', R._ptr(out_img), RH, RW, ysc, xsc, 0, R._ptr(self._cm_work),
                      R._ptr(self.chan_med), R._stream())
                 call('bbx_fill_edge', R._ptr(out_img), R._ptr(out_mask), RH, RW, ysc, xsc,
                      int(get_par(set_bb.mask_value, tel)['edge']), R._ptr(self.chan_med), R._stream())

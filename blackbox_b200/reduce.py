@@ -725,8 +725,9 @@ def fits_encode(data, out=None):
 # -------------------------------------------------------------------------------------------
 # edge pixels (blackbox.py:1958-1974)
 # -------------------------------------------------------------------------------------------
-def channel_medians(data):
-    """np.median of each of the 16 channels of a reduced frame -> float32 [16] CUDA tensor."""
+def channel_medians(data, ignore_nan=False):
+    """np.median (``ignore_nan``: np.nanmedian, as get_flatstats takes it, blackbox.py:3728-3733)
+    of each of the 16 channels of a reduced frame -> float32 [16] CUDA tensor."""
     t = _to_dev(data, torch.float32)
     H, W = t.shape
     ny, nx = set_bb.ny, set_bb.nx
@@ -734,7 +735,8 @@ def channel_medians(data):
         raise ValueError('frame {} is not {} x {} channels'.format(tuple(t.shape), ny, nx))
     work = torch.empty(query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=t.device)
     med = torch.empty(ny * nx, dtype=torch.float32, device=t.device)
-    call('bbx_channel_medians', _ptr(t), H, W, H // ny, W // nx, _ptr(work), _ptr(med), _stream())
+    call('bbx_channel_medians', _ptr(t), H, W, H // ny, W // nx, int(bool(ignore_nan)), _ptr(work), _ptr(med),
+         _stream())
     return med
 
 

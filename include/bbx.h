@@ -288,13 +288,14 @@ int bbx_laplace_plus(const float *in, float *out, int H, int W, void *stream);
  * Per-channel medians and the edge-pixel fill at the end of blackbox_reduce
  * (blackbox.py:1958-1974: for every channel, data[sec][mask_edge[sec]] = np.median(data[sec])).
  * bbx_channel_medians: out_med float32 [16] device = np.median of each channel of a reduced
- * frame (float32 mean of the two middle order statistics for the even pixel count; NaN if the
- * channel holds a NaN), by a three-pass radix select over all channels at once.
+ * frame (float32 mean of the two middle order statistics for an even pixel count; NaN if the
+ * channel holds a NaN -- or, with ignore_nan != 0, np.nanmedian as get_flatstats uses it,
+ * blackbox.py:3728-3733), by a three-pass radix select over all channels at once.
  * work >= bbx_chanmed_work_bytes().  bbx_fill_edge: img[(mask & edge_bit) != 0] = med[channel].
  * ------------------------------------------------------------------------------------- */
 size_t bbx_chanmed_work_bytes(void);
 int bbx_channel_medians(const float *img, int H, int W, int ysize_chan, int xsize_chan,
-                        void *work, float *out_med, void *stream);
+                        int ignore_nan, void *work, float *out_med, void *stream);
 int bbx_fill_edge(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                   int edge_bit, const float *med, void *stream);
 

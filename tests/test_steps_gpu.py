@@ -428,6 +428,17 @@ def test_channel_medians_and_edge_fill_bit_exact(ysc, xsc, small_bb):
     data[ysc + 1, 3 * xsc + 1] = np.nan
     meds2 = bbr.channel_medians(data).cpu().numpy()
     assert np.isnan(meds2[8 + 3]) and np.array_equal(np.delete(meds2, 11), np.delete(meds, 11))
+    # np.nanmedian semantics (get_flatstats): NaNs do not count; an all-NaN channel gives NaN
+    data[:ysc, 5 * xsc:6 * xsc][::2] = np.nan
+    data[ysc:, 7 * xsc:8 * xsc] = np.nan
+    meds3 = bbr.channel_medians(data, ignore_nan=True).cpu().numpy()
+    with np.errstate(all='ignore'):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            want3 = np.array([np.nanmedian(data[(i // 8) * ysc:(i // 8 + 1) * ysc, (i % 8) * xsc:(i % 8 + 1) * xsc])
+                              for i in range(16)], dtype=np.float32)
+    assert np.isnan(meds3[15]) and np.array_equal(meds3, want3, equal_nan=True)
 
 
 # ------------------------------------------------------------------------------------------
