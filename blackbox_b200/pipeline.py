@@ -62,6 +62,13 @@ class FramePipeline:
         self.mflat = R._to_dev(mflat, torch.float32)
         self.bpm = R._to_dev(bpm, torch.uint8)
         self.coeffs = None if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+        for name, t in (('mbias', self.mbias), ('mflat', self.mflat), ('bpm', self.bpm)):
+            if t is not None and tuple(t.shape) != tuple(self.geom.red_shape):
+                raise ValueError('{} has shape {}, the reduced frame is {}'.format(
+                    name, tuple(t.shape), tuple(self.geom.red_shape)))
+        if self.coeffs is not None and self.coeffs.shape != (self.geom.nchans, self.geom.nchans):
+            raise ValueError('crosstalk coefficients have shape {}, expected {}'.format(
+                self.coeffs.shape, (self.geom.nchans, self.geom.nchans)))
         self.niter = int(get_par(set_bb.niter, tel) if niter is None else niter)
         self.exptime = float(exptime)
         self.count_objects = count_objects
@@ -163,9 +170,24 @@ class FramePipeline:
     def _gain_for(self, raw_t):
         return self.gain if R._raw_type(raw_t) == 0 else None
 
+    def _check_frame(self, raw_t, out_img=None, out_mask=None):
+        """The kernels take bare pointers: refuse anything whose shape, dtype, device or layout is
+        not what the geometry of this pipeline says."""
+        if tuple(raw_t.shape) != (self.geom.H, self.geom.W) or not raw_t.is_cuda or not raw_t.is_contiguous():
+            raise ValueError('raw frame must be a contiguous CUDA tensor of shape {}, got {} ({})'.format(
+                (self.geom.H, self.geom.W), tuple(raw_t.shape), raw_t.device))
+        R._raw_type(raw_t)
+        for name, t, dt in (('output image', out_img, torch.float32), ('output mask', out_mask, torch.uint8)):
+            if t is None:
+                continue
+            if tuple(t.shape) != tuple(self.geom.red_shape) or t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+                raise ValueError('{} must be a contiguous CUDA {} tensor of shape {}, got {} {}'.format(
+                    name, dt, tuple(self.geom.red_shape), t.dtype, tuple(t.shape)))
+
     def stage_a_enqueue(self, raw_t):
         """Stage A on the current stream: overscan kernels, header means, and the copy of the
         fit flags / column statistics into the pinned mirror of the overscan state."""
+        self._check_frame(raw_t)
         st = self.st
 
         def body():
@@ -253,6 +275,7 @@ class FramePipeline:
         """Stage B on the current stream (which must be ordered after stage A and the spline
         patch): everything from the fused per-pixel pass to the crosstalk correction, then the
         status words into pinned memory."""
+        self._check_frame(raw_t, out_img, out_mask)
         self._rest(raw_t, out_img, out_mask)
         self._ev_b.record()
         self._raw, self._out = raw_t, (out_img, out_mask)

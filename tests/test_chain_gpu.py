@@ -272,3 +272,32 @@ def test_reduce_night_tool_files_in_files_out(small_bb, tmp_path):
         assert h['FILTER'][0] == 'q' and h['REDFILE'][0].endswith('_red')
         assert h['BIASMEAN'][0] == pytest.approx(hdr_o['BIASMEAN'], rel=1e-9)
         assert h['NOBJ-SAT'][0] == hdr_o['NOBJ-SAT']
+
+
+def test_pipeline_refuses_mismatched_buffers(small_bb):
+    """The C ABI takes bare pointers; the host layer must reject wrong shapes / dtypes / devices
+    before anything is launched."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from blackbox_b200.pipeline import FramePipeline
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    raw, mbias, mflat, bpm, coeffs = _inputs(tel, 4700, ysc)
+    with pytest.raises(ValueError):
+        FramePipeline(tel, raw.shape, mbias=mbias[:-1], mflat=mflat, bpm=bpm, coeffs=coeffs)
+    with pytest.raises(ValueError):
+        FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs[:8])
+    with pytest.raises(ValueError):
+        FramePipeline(tel, (raw.shape[0] + 1, raw.shape[1]), mbias=mbias, mflat=mflat, bpm=bpm)
+    pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=1)
+    raw_t = bbr._to_dev(raw)
+    with pytest.raises(ValueError):
+        pipe.enqueue(raw_t[:-2])
+    with pytest.raises(TypeError):
+        pipe.enqueue(raw_t.to(torch.int32))
+    with pytest.raises(ValueError):
+        pipe.enqueue(raw_t, torch.empty((2 * ysc, 10560), dtype=torch.float64, device='cuda'), None)
+    with pytest.raises(ValueError):
+        pipe.enqueue(raw_t, torch.empty((2 * ysc, 10560), dtype=torch.float32, device='cuda').t().contiguous().t(), None)
+    res = pipe.reduce(raw)                      # and it still works afterwards
+    assert res.img.shape == (2 * ysc, 10560)
