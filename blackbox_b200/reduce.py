@@ -543,6 +543,11 @@ def detect_cosmics(indat, inmask=None, sigclip=4.5, sigfrac=0.3, objlim=5.0, gai
     if inmask is not None:
         inmask_t = _to_dev(inmask)
         inmask_t = (inmask_t != 0).to(torch.uint8) if inmask_t.dtype != torch.uint8 else inmask_t
+        if tuple(inmask_t.shape) != tuple(src.shape):
+            raise ValueError('detect_cosmics: inmask shape {} does not match indat {}'.format(
+                tuple(inmask_t.shape), tuple(src.shape)))
+    if src.dim() != 2:
+        raise ValueError('detect_cosmics: indat must be a 2-D image, got shape {}'.format(tuple(src.shape)))
     clean, crmask, work, used_mode, inf, status = _detect_cosmics_dev(
         src, inmask_t, sigclip, sigfrac, objlim, gain, readnoise, niter, mode)
     if info is not None:
@@ -801,6 +806,10 @@ def xtalk_corr(data, crosstalk_file, data_mask=None):
             m = m.to(torch.uint8)
     if t.shape[0] % 2 or t.shape[1] % 8:
         raise ValueError('xtalk_corr: frame {} is not 2 x 8 channels'.format(tuple(t.shape)))
+    if m is not None and tuple(m.shape) != tuple(t.shape):
+        raise ValueError('xtalk_corr: mask shape {} does not match data {}'.format(tuple(m.shape), tuple(t.shape)))
+    if np.shape(coeffs) != (16, 16):
+        raise ValueError('xtalk_corr: coefficient matrix has shape {}, expected (16, 16)'.format(np.shape(coeffs)))
     xtalk_enqueue(t, m, coeffs, tel)
     if is_np:
         data[...] = t.cpu().numpy()
@@ -826,6 +835,14 @@ def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=
     if n < 1 or n > 64:
         raise ValueError('master_combine: {} frames (supported: 1..64)'.format(n))
     shape = tuple(ts[0].shape)
+    for i, t in enumerate(ts):
+        if tuple(t.shape) != shape:
+            raise ValueError('master_combine: frame {} has shape {}, frame 0 has {}'.format(i, tuple(t.shape), shape))
+    if imgtype == 'flat' and medsec is not None and len(medsec) != n:
+        raise ValueError('master_combine: {} normalisation medians for {} frames'.format(len(medsec), n))
+    if bpm is not None and imgtype == 'flat' and tuple(np.shape(bpm)) != shape:
+        raise ValueError('master_combine: bad-pixel mask shape {} does not match the frames {}'.format(
+            tuple(np.shape(bpm)), shape))
     scales = [0.0] * n
     if imgtype == 'flat':
         sec = get_par(set_bb.flat_norm_sec, tel)

@@ -523,3 +523,25 @@ def test_nonlin_corr_reads_the_pickle(small_bb, tmp_path):
     bbr.tel = 'ML1'
     got = bbr.nonlin_corr(data.copy(), str(path))
     assert np.array_equal(got, R.nonlin_corr(data.copy(), splines, tel='ML1'))
+
+
+def test_drop_in_functions_refuse_mismatched_shapes(small_bb):
+    import torch
+    from blackbox_b200 import reduce as bbr
+    small_bb(24, 40)
+    img = np.zeros((48, 320), dtype=np.float32)
+    bbr.tel = 'BG3'
+    with pytest.raises(ValueError):
+        bbr.xtalk_corr(img, np.zeros((16, 16)), data_mask=np.zeros((48, 300), np.uint8))
+    with pytest.raises(ValueError):
+        bbr.xtalk_corr(img, np.zeros((15, 16)))
+    with pytest.raises(ValueError):
+        bbr.master_combine([img, img[:-1]], 'bias')
+    with pytest.raises(ValueError):
+        bbr.master_combine([img, img], 'flat', medsec=[1.0])
+    with pytest.raises(ValueError):
+        bbr.detect_cosmics(img, inmask=np.zeros((48, 319), bool), satlevel=np.inf, sepmed=False, cleantype='medmask')
+    with pytest.raises(ValueError):
+        bbr.fill_edge_pixels(img, np.zeros((47, 320), np.uint8))
+    with pytest.raises(ValueError):
+        bbr.subtract_mbias(torch.zeros((48, 320), device='cuda'), torch.zeros((48, 319), device='cuda'))
