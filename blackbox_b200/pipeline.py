@@ -328,6 +328,7 @@ class FramePipeline:
                 header['NCOSMICS'] = header_mask['NCOSMICS'] = nc
                 info = self.lwork.info.cpu().numpy()
                 header['LAC-NIT'] = int(info[0])
+            R.mask_header(out_mask, header_mask, tel_=self.tel)      # M-*NUM pixel counts, blackbox.py:4601-4620
         return FrameResult(out_img, out_mask, header, header_mask, self._spline_cols, redo)
 
     # ---------------------------------------------------------------------------------------

@@ -470,15 +470,16 @@ def _apply_seed(t, geom, satlevel_t, bpm_t, out_img, work):
     return out_mask
 
 
-def mask_header(data_mask, header_mask):
-    """Per-type pixel counts M-*NUM etc. (blackbox.py:4601-4620)."""
+def mask_header(data_mask, header_mask, tel_=None):
+    """Per-type pixel counts M-*NUM etc. (blackbox.py:4601-4620).  ``tel_``: telescope name
+    (default: the module-global ``tel``, as in the reference)."""
     t = _to_dev(data_mask, torch.uint8)
     counts = torch.zeros(8, dtype=torch.int64, device=t.device)
     call('bbx_mask_counts', _ptr(t), t.numel(), _ptr(counts), _stream())
     counts = counts.cpu().numpy()
     text = {'bad': 'BP', 'edge': 'EP', 'saturated': 'SP', 'saturated-connected': 'SCP',
             'satellite trail': 'STP', 'cosmic ray': 'CRP'}
-    mv = get_par(set_bb.mask_value, tel)
+    mv = get_par(set_bb.mask_value, tel if tel_ is None else tel_)
     for mask_type, short in text.items():
         value = mv[mask_type]
         _set(header_mask, 'M-{}'.format(short), True, '{} pixels included in mask?'.format(mask_type))

@@ -48,6 +48,11 @@ def test_full_chain_parity(tel, niter, small_bb):
     assert res.header['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
     if mism == 0:
         assert res.header['NCOSMICS'] == pytest.approx(hdr_o['NCOSMICS'])
+        # mask_header keywords (blackbox.py:4601-4620): pixel counts per mask type
+        for name, short in (('bad', 'BP'), ('edge', 'EP'), ('saturated', 'SP'), ('saturated-connected', 'SCP'),
+                            ('cosmic ray', 'CRP')):
+            assert res.header_mask['M-{}NUM'.format(short)] == int(((mask_o & mv[name]) != 0).sum()), name
+            assert res.header_mask['M-{}VAL'.format(short)] == mv[name]
     # a second frame through the same pipeline object (buffers are reused)
     raw2, *_ = _inputs(tel, 4002, ysc)
     data_o2, mask_o2, _, _ = R.reduce_frame(raw2, tel, mbias, mflat, bpm, coeffs, niter=niter)
