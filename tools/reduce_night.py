@@ -26,7 +26,7 @@ def _master(path, dtype):
     if not path:
         return None
     _, data, info = fitsio.read_primary(path)
-    return np.ascontiguousarray(fitsio.to_native(data, info) if dtype != np.uint8 else np.asarray(data), dtype=dtype)
+    return np.array(fitsio.to_native(data, info) if dtype != np.uint8 else np.asarray(data), dtype=dtype, order='C', copy=True)
 
 
 def main(argv=None):
