@@ -230,6 +230,7 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
     if (COLLECT) { key_a = w.bg->key_a; width = w.bg->width; }
     // vector path: aligned rows, the 4 pixels and their left / right neighbours inside the row
     const bool fast = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && x0 > 0 && x0 + 4 < W &&
+                      (((uintptr_t)crmask | (uintptr_t)w.flags) & 3) == 0 &&
                       (!COLLECT || inmask == nullptr || ((uintptr_t)inmask & 3) == 0);
     if (x0 < W && !fast) {
         for (int y = ya; y < yb; y++)
@@ -822,12 +823,8 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
         if (bbx_masked_lower_median(img, inmask, n, w.sel, w.background, st)) return -2;
     } else {
         BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
-        static bool smem_set = false;
-        if (!smem_set) {
-            BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(sizeof(unsigned int) * BG_SAMPLES)));
-            smem_set = true;
-        }
+        BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned int) * BG_SAMPLES)));
         sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(img, inmask, n, w);
     }
     sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt, with_background ? 1u : 0u);
