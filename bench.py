@@ -142,7 +142,7 @@ def run_reference(args, rank):
     rows = args.cpu_rows
     if rows <= 0:
         budget = 150.0 / max(args.steps + args.warmup, 1)          # seconds per step
-        rows = int(max(40, min(330, 330 * budget / 35.0))) // 4 * 4
+        rows = int(max(96, min(330, 330 * budget / 35.0))) // 4 * 4   # >= 96: keeps the per-slice fixed costs small
     arm = CpuArm(cores)
     vals = []
     try:
