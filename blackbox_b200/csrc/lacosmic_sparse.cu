@@ -752,32 +752,43 @@ __global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt
 // iteration: all of them are new).  !ALL: only flagged pixels with a newly flagged pixel in
 // their box can change -- walk the 5x5 boxes of the new CR-list entries (duplicates recompute
 // the same value).
+// One warp per pixel: lanes 0..24 fetch the 5x5 box in one round trip, every usable value finds its
+// position in the stable sorted order with 25 shuffles, and the lane holding the lower median
+// writes it (the first version walked the box and insertion-sorted it in one thread: 42 us for
+// the 21 000 cosmic-ray pixels of a frame, 8 % of the warps active).
 __device__ __forceinline__ void sp_clean_pixel(float *img, const uint8_t *__restrict__ crmask,
                                                const uint8_t *__restrict__ inmask, int H, int W, int y, int x,
-                                               const SparseWork &w, long long *info)
+                                               const SparseWork &w, long long *info, int lane)
 {
-    if (x < 2 || x >= W - 2 || y < 2 || y >= H - 2) return;
+    if (x < 2 || x >= W - 2 || y < 2 || y >= H - 2) return;         // warp-uniform
     const size_t p = (size_t)y * W + x;
-    float v[25];
-    int m = 0;
-    for (int dy = -2; dy <= 2; dy++)
-        for (int dx = -2; dx <= 2; dx++) {
-            const size_t j = (size_t)(y + dy) * W + (x + dx);
-            const bool bad = crmask[j] || (inmask && inmask[j]);
-            if (!bad) v[m++] = img[j];
-        }
+    float v = 0.f;
+    bool ok = false;
+    if (lane < 25) {
+        const size_t j = (size_t)(y + lane / 5 - 2) * W + (x + lane % 5 - 2);
+        ok = !(crmask[j] || (inmask && inmask[j]));
+        if (ok) v = img[j];
+    }
+    const unsigned int usable = __ballot_sync(0xffffffffu, ok);
+    const int m = __popc(usable);
     if (m == 0) {                      // no usable neighbour: the global background level
-        if (w.cnt->bg_valid) img[p] = *w.background;
-        else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
+        if (lane == 0) {
+            if (w.cnt->bg_valid) img[p] = *w.background;
+            else atomicOr((unsigned long long *)&info[INFO_STATUS], (unsigned long long)LAC_STATUS_NEED_BG);
+        }
         return;
     }
-    for (int a = 1; a < m; a++) {
-        const float key = v[a];
-        int b = a - 1;
-        while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; b--; }
-        v[b + 1] = key;
+    // position in the stable ascending order of the usable values (NaNs last)
+    const float mine = (v != v) ? INFINITY : v;
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+        float vk = __shfl_sync(0xffffffffu, v, k);
+        vk = (vk != vk) ? INFINITY : vk;
+        const bool okk = (usable >> k) & 1u;
+        rank += okk && (vk < mine || (vk == mine && k < lane));
     }
-    img[p] = v[(m - 1) / 2];
+    if (ok && rank == (m - 1) / 2) img[p] = v;
 }
 
 template <bool ALL>
@@ -787,23 +798,25 @@ sp_clean_kernel(float *img, const uint8_t *__restrict__ crmask, const uint8_t *_
 {
     if (!info[INFO_ACTIVE]) return;
     const unsigned int n = list_len(&w.cnt->nCR, w.capCR);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     if (ALL) {
-        for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        for (unsigned long long k = warp; k < n; k += nwarps) {
             const unsigned int p = w.listCR[k];
             const int y = (int)(p / (unsigned int)W), x = (int)(p - (unsigned int)y * (unsigned int)W);
-            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info);
+            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info, lane);
         }
     } else {
         const unsigned int lo = min(w.cnt->clean_lo, n), hi = min(w.cnt->clean_hi, n);
         const unsigned long long total = (unsigned long long)(hi - lo) * 25ull;
-        for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-             t += (unsigned long long)gridDim.x * blockDim.x) {
+        for (unsigned long long t = warp; t < total; t += nwarps) {
             const unsigned int p = w.listCR[lo + (unsigned int)(t / 25ull)];
             const int o = (int)(t % 25ull);
             const int y = (int)(p / (unsigned int)W) + o / 5 - 2, x = (int)(p % (unsigned int)W) + o % 5 - 2;
             if (x < 0 || x >= W || y < 0 || y >= H) continue;
-            if (!crmask[(size_t)y * W + x]) continue;
-            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info);
+            if (!crmask[(size_t)y * W + x]) continue;                 // crmask is final here: warp-uniform
+            sp_clean_pixel(img, crmask, inmask, H, W, y, x, w, info, lane);
         }
     }
 }
@@ -859,8 +872,8 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     sp_grow2a_kernel<<<list_blocks, 128, 0, st>>>(inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_grow2b_kernel<<<warp_blocks, 128, 0, st>>>(img, crmask, H, W, prm, w, stamp, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
-    if (it == 0) sp_clean_kernel<true><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
-    else sp_clean_kernel<false><<<list_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    if (it == 0) sp_clean_kernel<true><<<warp_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
+    else sp_clean_kernel<false><<<warp_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
     BBX_CHECK_LAUNCH("sparse_iteration");
     return 0;
 }
