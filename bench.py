@@ -5,9 +5,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A step = one pass of the full chain (gain + overscan + master bias + mask_init + master flat +
-LACosmic + crosstalk; blackbox.py:1479-1902) over a batch of synthetic 10600x12000 uint16 raw
-BlackGEM frames, `--batch` frames per GPU (weak scaling: frames are independent, frame k ->
-GPU k mod N, no collective on the data path).
+LACosmic with 4 iterations + crosstalk; blackbox.py:1479-1902) over a night batch of synthetic
+10600x12000 uint16 raw BlackGEM frames: `--batch` (64, BASELINE.json config 4) frames per GPU,
+resident in HBM (16.3 GB).  Weak scaling: frames are independent, frame k -> GPU k mod N, no
+collective on the data path.  Per GPU `--depth` (4) frames are in flight, the overscan stage
+`--ahead` (2) frames in front on a high-priority stream, stages replayed as CUDA graphs.
+`--impl reference`: the CPU arm (the oracle port of the reference path on all host cores, bounded
+sample per step) as a run of its own, rank 0 only.
 
 Printed JSON (rank 0, one line):
   value      frames/s over all GPUs, raw frames already resident in HBM
