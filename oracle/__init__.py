@@ -6,9 +6,12 @@ A CPU restatement of the reference's numpy/astropy/astroscrappy reduction path
 ``blackbox_b200`` never does.
 
 Pinning status ("Oracle"):
-  * numpy / scipy pieces (np.median, np.polyfit, np.matmul, scipy.ndimage morphology,
-    UnivariateSpline) call the very libraries the reference calls -> pinned by construction.
+  * everything the reference computes itself (define_sections, gain_corr, os_corr, mask_init,
+    cosmics_corr's wrapper, xtalk_corr, nonlin_corr) is pinned against the REFERENCE'S OWN CODE
+    executed with stub modules for its absent dependencies: tests/golden/make_reference_golden.py
+    -> tests/golden/reference_golden.json -> tests/test_reference_golden.py (bit for bit).
   * astropy sigma clipping and astroscrappy.detect_cosmics are restated from their published
     algorithms; the libraries are absent here and the reference has no tests or golden
-    vectors -> PARITY UNPINNED for those two pieces.
+    vectors -> PARITY UNPINNED for those two pieces (sigma_clip with a mean centre is checked
+    against scipy.stats.sigmaclip).
 """

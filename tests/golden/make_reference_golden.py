@@ -1,0 +1,237 @@
+#!/usr/bin/env python
+"""Generate tests/golden/reference_golden.json by EXECUTING THE REFERENCE'S OWN CODE.
+
+/root/reference/blackbox.py cannot be imported as it stands (astropy, astroscrappy, zogy, set_zogy,
+fitsio, ephem, watchdog, acstools, ASTA, match2SSO, matplotlib are absent here), but its reduction
+functions only need numpy / scipy plus a handful of names from those modules.  This script puts
+stub modules in ``sys.modules`` -- empty shells for everything the hot path never touches, and
+
+    astropy.stats.sigma_clipped_stats / sigma_clip   -> oracle.stats      (restated, UNPINNED)
+    astroscrappy.detect_cosmics                      -> oracle.lacosmic   (restated, UNPINNED)
+    zogy: np, ndimage, interpolate, get_par, fits.Header (a dict), Table.read (3-column ASCII
+          reader), read_hdulist / already_exists (in-memory bad-pixel mask)
+    set_zogy.mask_value                              -> ZOGY's published defaults
+
+-- imports the reference, and runs define_sections, gain_corr, os_corr, mask_init, cosmics_corr,
+xtalk_corr and nonlin_corr UNMODIFIED on seeded synthetic frames.  What is stored are digests,
+spot values and header values of the outputs, so tests/test_reference_golden.py can hold the
+oracle (and the GPU path) against the reference's own control flow, slicing, dtype promotion,
+np.polyfit / UnivariateSpline / ndimage / np.matmul calls.  Only the two stubbed third-party
+algorithms stay unpinned.  Needs /root/reference; run here (the fixtures travel, it does not):
+
+    python tests/golden/make_reference_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+from scipy import interpolate, ndimage
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+
+MASK_VALUE = {'bad': 1, 'cosmic ray': 2, 'saturated': 4, 'saturated-connected': 8,
+              'satellite trail': 16, 'edge': 32, 'crosstalk': 64}
+_files = {}          # "file name" -> array, served by the read_hdulist stub
+
+
+class _Sink:
+    def __init__(self, name='x'):
+        self._n = name
+
+    def __getattr__(self, k):
+        return _Sink(self._n + '.' + k)
+
+    def __call__(self, *a, **k):
+        return _Sink(self._n + '()')
+
+    def __iter__(self):
+        return iter(())
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__getattr__ = lambda k, _n=name: _Sink(_n + '.' + k)
+    sys.modules[name] = m
+    return m
+
+
+class Header(dict):
+    """astropy.io.fits.Header stand-in: header[key] = (value, comment) stores the value."""
+
+    def __setitem__(self, key, value):
+        if isinstance(value, tuple) and len(value) == 2:
+            value = value[0]
+        dict.__setitem__(self, key, value)
+
+
+class _Column:
+    def __init__(self, value):
+        self.value = value
+
+
+class _Rows(dict):
+    def __len__(self):
+        return len(next(iter(self.values())).value)
+
+
+class _Table:
+    """astropy.table.Table.read(..., format='ascii') stand-in: column names on the first line,
+    integer columns where every entry is an integer (as astropy's guesser types them)."""
+
+    @staticmethod
+    def read(path, format=None, names=None):
+        rows = [ln.split() for ln in open(path) if ln.strip() and not ln.lstrip().startswith('#')]
+        out = _Rows()
+        for i, name in enumerate(rows[0]):
+            col = [r[i] for r in rows[1:]]
+            try:
+                out[name] = _Column(np.array([int(c) for c in col]))
+            except ValueError:
+                out[name] = _Column(np.array([float(c) for c in col]))
+        return out
+
+
+def load_reference():
+    from blackbox_b200.set_bb import get_par
+    from oracle import lacosmic as olac, stats as ostats
+    _stub('set_zogy', mask_value=dict(MASK_VALUE), timing=False, display=False, verbose=False)
+    for n in ('set_match2SSO', 'match2SSO', 'acstools', 'acstools.satdet', 'ephem', 'watchdog',
+              'watchdog.observers', 'watchdog.observers.polling', 'watchdog.events', 'qc', 'ASTA', 'matplotlib',
+              'matplotlib.pyplot', 'matplotlib.colors', 'fitsio', 'PIL', 'dateutil', 'dateutil.tz', 'astropy',
+              'astropy.coordinates', 'astropy.time', 'astropy.units', 'astropy.visualization', 'astropy.utils',
+              'astropy.utils.iers', 'astropy.io', 'astropy.io.fits', 'astropy.table', 'astropy.wcs'):
+        _stub(n)
+    sys.modules['watchdog.events'].FileSystemEventHandler = type('FileSystemEventHandler', (), {})
+    _stub('astropy.stats', sigma_clipped_stats=ostats.sigma_clipped_stats, sigma_clip=ostats.sigma_clip)
+    _stub('astroscrappy', detect_cosmics=olac.detect_cosmics)
+    fits = types.SimpleNamespace(Header=Header)
+    zogy = _stub('zogy', np=np, ndimage=ndimage, interpolate=interpolate, get_par=get_par, fits=fits, Table=_Table,
+                 read_hdulist=lambda name, dtype=None, **k: np.array(_files[name], dtype=dtype, copy=True),
+                 sigma_clip=ostats.sigma_clip, sigma_clipped_stats=ostats.sigma_clipped_stats,
+                 log_timing_memory=lambda *a, **k: None, mem_use=lambda *a, **k: None, isfile=os.path.isfile)
+    zogy.__all__ = ['np', 'ndimage', 'interpolate', 'get_par', 'fits', 'Table', 'read_hdulist', 'log_timing_memory',
+                    'mem_use', 'sigma_clip', 'sigma_clipped_stats', 'isfile']
+    sys.path.insert(0, os.path.join(REF, 'Settings'))
+    sys.path.insert(0, REF)
+    import blackbox
+    blackbox.already_exists = lambda name, get_filename=False: ((name in _files, name) if get_filename
+                                                               else name in _files)
+    return blackbox
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def spots(a, n=8):
+    flat = np.asarray(a).ravel()
+    return [float(flat[i]) for i in np.linspace(0, flat.size - 1, n).astype(int)]
+
+
+def sections_as_lists(secs):
+    return [[[[s.start, s.stop] for s in pair] for pair in tup] for tup in secs]
+
+
+def frame_case(bb, tel, seed, ysc):
+    """gain_corr -> os_corr -> (bias) -> mask_init -> flat -> cosmics_corr -> xtalk_corr, the order of
+    blackbox_reduce (blackbox.py:1479-1902), every step the reference's own function."""
+    from blackbox_b200 import set_bb as my_set_bb, synth
+    ref_set_bb = sys.modules['set_blackbox']
+    saved = (my_set_bb.ysize_chan, ref_set_bb.ysize_chan)
+    my_set_bb.ysize_chan = ref_set_bb.ysize_chan = ysc
+    try:
+        bb.tel = tel
+        raw, _ = synth.make_raw(tel, seed, nstars=400, ncosmics=150)
+        if tel != 'ML1':
+            raw[ysc - 50:ysc, 300:304] = 65535                   # saturated columns next to the overscan
+            raw[ysc - 900:ysc - 880, 1500 * 2 + 20:1500 * 2 + 24] = 65535
+        raw[40:48, 2000:2008] = 65535
+        shape = (2 * ysc, 8 * my_set_bb.xsize_chan)
+        mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
+        victim, source, corr, coeffs = synth.make_xtalk(seed + 2)
+        out = {'tel': tel, 'seed': seed, 'ysize_chan': ysc, 'raw_sha256': digest(raw)}
+        header = Header(EXPTIME=60.0)
+        data = np.array(raw, dtype='float32')
+        bb.gain_corr(data, header, tel=tel)
+        out['gain_sha256'] = digest(data)
+        data = bb.os_corr(data, header, 'object', tel=tel)
+        out['os_sha256'] = digest(data)
+        out['os_spots'] = spots(data)
+        out['os_header'] = {k: (v if isinstance(v, (bool, str)) else float(v)) for k, v in header.items()
+                            if k.startswith(('BIASM', 'RDN', 'VFITOK', 'BIAS')) }
+        if bb.get_par(ref_set_bb.subtract_mbias, tel):
+            data -= mbias
+        _files.clear()
+        fits_bpm = bb.get_par(ref_set_bb.bad_pixel_mask, tel).replace('bpm', 'bpm_q')
+        _files[fits_bpm] = bpm
+        data_mask, header_mask = bb.mask_init(data, header, 'q', 'object')
+        out['mask_init_sha256'] = digest(data_mask)
+        out['mask_counts'] = {str(b): int(((data_mask & b) != 0).sum()) for b in (1, 4, 8, 32, 64)}
+        out['mask_header'] = {k: float(v) for k, v in header_mask.items()}
+        data /= mflat
+        data, data_mask = bb.cosmics_corr(data, header, data_mask, header_mask)
+        out['cosmics_sha256'] = digest(data)
+        out['cosmics_mask_sha256'] = digest(data_mask)
+        out['NCOSMICS'] = float(header['NCOSMICS'])
+        path = '/tmp/_ref_xtalk_{}.txt'.format(os.getpid())
+        synth.write_xtalk_file(path, victim, source, corr)
+        bb.xtalk_corr(data, path, data_mask)
+        os.remove(path)
+        out['xtalk_sha256'] = digest(data)
+        out['final_spots'] = spots(data)
+        return out
+    finally:
+        my_set_bb.ysize_chan, ref_set_bb.ysize_chan = saved
+
+
+def nonlin_case(bb, seed):
+    import pickle
+    from blackbox_b200 import set_bb as my_set_bb
+    ref_set_bb = sys.modules['set_blackbox']
+    saved = (my_set_bb.ysize_chan, my_set_bb.xsize_chan, ref_set_bb.ysize_chan, ref_set_bb.xsize_chan)
+    my_set_bb.ysize_chan = ref_set_bb.ysize_chan = 48
+    my_set_bb.xsize_chan = ref_set_bb.xsize_chan = 60
+    try:
+        bb.tel = 'BG3'
+        rng = np.random.default_rng(seed)
+        splines = []
+        for i in range(16):
+            x = np.linspace(0, 60000, 80)
+            y = 2e-3 * np.sin(x / (7000.0 + 300 * i)) - 3e-7 * x + 2e-4 * rng.standard_normal(x.size)
+            splines.append(interpolate.UnivariateSpline(x, y, k=3, s=x.size * 4e-8))
+        data = rng.uniform(-500, 140000, size=(96, 480)).astype(np.float32)
+        path = '/tmp/_ref_nonlin_{}.pkl'.format(os.getpid())
+        with open(path, 'wb') as fh:
+            pickle.dump(splines, fh)
+        want = bb.nonlin_corr(data.copy(), path)
+        os.remove(path)
+        return {'seed': seed, 'input_sha256': digest(data), 'output_sha256': digest(want), 'output_spots': spots(want)}
+    finally:
+        my_set_bb.ysize_chan, my_set_bb.xsize_chan, ref_set_bb.ysize_chan, ref_set_bb.xsize_chan = saved
+
+
+def main():
+    bb = load_reference()
+    out = {'reference_version': bb.__version__, 'numpy': np.__version__,
+           'sections': {}, 'frames': [], 'nonlin': []}
+    for shape, xb in (((10600, 12000), 1), ((5300, 6000), 2), ((10560, 10560), 1)):
+        out['sections']['{}x{}_bin{}'.format(shape[0], shape[1], xb)] = sections_as_lists(
+            bb.define_sections(shape, xbin=xb, ybin=xb, tel='BG3'))
+    out['frames'].append(frame_case(bb, 'ML1', 1001, 200))
+    out['frames'].append(frame_case(bb, 'BG3', 4001, 2640))
+    out['nonlin'].append(nonlin_case(bb, 11))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_golden.json')
+    with open(path, 'w') as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print('wrote', path)
+    return out
+
+
+if __name__ == '__main__':
+    main()
