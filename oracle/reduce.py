@@ -330,6 +330,18 @@ def mask_init(data, header, bpm, imgtype, tel=None, diag=None):
     return data_mask.astype('uint8'), header_mask
 
 
+def mask_header(data_mask, header_mask, tel=None):
+    """blackbox.py:4601-4620: M-<type>, M-<type>VAL, M-<type>NUM per mask type."""
+    text = {'bad': 'BP', 'edge': 'EP', 'saturated': 'SP', 'saturated-connected': 'SCP',
+            'satellite trail': 'STP', 'cosmic ray': 'CRP'}
+    mask_value = get_par(set_bb.mask_value, tel)
+    for mask_type, short in text.items():
+        value = mask_value[mask_type]
+        header_mask['M-' + short] = True
+        header_mask['M-{}VAL'.format(short)] = value
+        header_mask['M-{}NUM'.format(short)] = int(np.sum(data_mask & value == value))
+
+
 # -------------------------------------------------------------------------------------------
 def cosmics_corr(data, header, data_mask, header_mask, tel=None, niter=None):
     """blackbox.py:4259-4370; returns (cleaned data, mask with the cosmic-ray bit)."""

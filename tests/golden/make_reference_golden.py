@@ -138,7 +138,7 @@ def sections_as_lists(secs):
     return [[[[s.start, s.stop] for s in pair] for pair in tup] for tup in secs]
 
 
-def frame_case(bb, tel, seed, ysc):
+def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1):
     """gain_corr -> os_corr -> (bias) -> mask_init -> flat -> cosmics_corr -> xtalk_corr, the order of
     blackbox_reduce (blackbox.py:1479-1902), every step the reference's own function."""
     from blackbox_b200 import set_bb as my_set_bb, synth
@@ -147,6 +147,20 @@ def frame_case(bb, tel, seed, ysc):
     my_set_bb.ysize_chan = ref_set_bb.ysize_chan = ysc
     try:
         bb.tel = tel
+        if xbin == 2:
+            raw, _ = synth.make_raw(tel, seed, ysize_chan=ysc // 2, xsize_chan=660, os_rows=10, os_cols=90,
+                                    nstars=300, ncosmics=60)
+            out = {'tel': tel, 'seed': seed, 'ysize_chan': ysc, 'xbin': 2, 'raw_sha256': digest(raw)}
+            header = Header(EXPTIME=60.0)
+            data = np.array(raw, dtype='float32')
+            bb.gain_corr(data, header, tel=tel)
+            out['gain_sha256'] = digest(data)
+            data = bb.os_corr(data, header, 'object', xbin=2, ybin=2, tel=tel)
+            out['os_sha256'] = digest(data)
+            out['os_spots'] = spots(data)
+            out['os_header'] = {k: (v if isinstance(v, (bool, str)) else float(v)) for k, v in header.items()
+                                if k.startswith(('BIASM', 'RDN', 'VFITOK', 'BIAS'))}
+            return out
         raw, _ = synth.make_raw(tel, seed, nstars=400, ncosmics=150)
         if tel != 'ML1':
             raw[ysc - 50:ysc, 300:304] = 65535                   # saturated columns next to the overscan
@@ -155,7 +169,7 @@ def frame_case(bb, tel, seed, ysc):
         shape = (2 * ysc, 8 * my_set_bb.xsize_chan)
         mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
         victim, source, corr, coeffs = synth.make_xtalk(seed + 2)
-        out = {'tel': tel, 'seed': seed, 'ysize_chan': ysc, 'raw_sha256': digest(raw)}
+        out = {'tel': tel, 'seed': seed, 'ysize_chan': ysc, 'xbin': 1, 'cosmics': bool(cosmics), 'raw_sha256': digest(raw)}
         header = Header(EXPTIME=60.0)
         data = np.array(raw, dtype='float32')
         bb.gain_corr(data, header, tel=tel)
@@ -175,10 +189,14 @@ def frame_case(bb, tel, seed, ysc):
         out['mask_counts'] = {str(b): int(((data_mask & b) != 0).sum()) for b in (1, 4, 8, 32, 64)}
         out['mask_header'] = {k: float(v) for k, v in header_mask.items()}
         data /= mflat
-        data, data_mask = bb.cosmics_corr(data, header, data_mask, header_mask)
-        out['cosmics_sha256'] = digest(data)
-        out['cosmics_mask_sha256'] = digest(data_mask)
-        out['NCOSMICS'] = float(header['NCOSMICS'])
+        if cosmics:
+            data, data_mask = bb.cosmics_corr(data, header, data_mask, header_mask)
+            out['cosmics_sha256'] = digest(data)
+            out['cosmics_mask_sha256'] = digest(data_mask)
+            out['NCOSMICS'] = float(header['NCOSMICS'])
+        hm2 = Header()
+        bb.mask_header(data_mask, hm2)
+        out['mask_header_counts'] = {k: int(v) for k, v in hm2.items() if k.endswith('NUM')}
         path = '/tmp/_ref_xtalk_{}.txt'.format(os.getpid())
         synth.write_xtalk_file(path, victim, source, corr)
         bb.xtalk_corr(data, path, data_mask)
@@ -225,6 +243,8 @@ def main():
             bb.define_sections(shape, xbin=xb, ybin=xb, tel='BG3'))
     out['frames'].append(frame_case(bb, 'ML1', 1001, 200))
     out['frames'].append(frame_case(bb, 'BG3', 4001, 2640))
+    out['frames'].append(frame_case(bb, 'BG2', 4002, 5280, cosmics=False))     # full size: channel-9 split fit
+    out['frames'].append(frame_case(bb, 'ML1', 5001, 400, xbin=2))             # 2x2 binned frame
     out['nonlin'].append(nonlin_case(bb, 11))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_golden.json')
     with open(path, 'w') as fh:

@@ -27,6 +27,11 @@ def spots(a, n=8):
 def _inputs(g):
     from blackbox_b200 import set_bb, synth
     tel, seed, ysc = g['tel'], g['seed'], g['ysize_chan']
+    if g.get('xbin', 1) == 2:
+        raw, _ = synth.make_raw(tel, seed, ysize_chan=ysc // 2, xsize_chan=660, os_rows=10, os_cols=90,
+                                nstars=300, ncosmics=60)
+        assert digest(raw) == g['raw_sha256']
+        return raw, None, None, None, None
     raw, _ = synth.make_raw(tel, seed, nstars=400, ncosmics=150)
     if tel != 'ML1':
         raw[ysc - 50:ysc, 300:304] = 65535
@@ -51,9 +56,11 @@ def test_define_sections_equals_the_reference():
 
 @pytest.mark.parametrize('idx', range(len(GOLD['frames'])))
 def test_oracle_equals_the_reference_step_by_step(idx, small_bb):
-    """gain_corr, os_corr, mask_init bit for bit (and, on the small MeerLICHT frame, cosmics_corr and
-    xtalk_corr too: the big BlackGEM frame's LACosmic takes minutes on the CPU and is left to the
-    GPU test below)."""
+    """gain_corr, os_corr, mask_init, mask_header bit for bit (and, on the small MeerLICHT frame,
+    cosmics_corr and xtalk_corr too: the big BlackGEM frame's LACosmic takes minutes on the CPU and
+    is left to the GPU test below).  Case 2 is a FULL-SIZE BG2 frame (the only size at which the
+    reference's saturated-column windows of BG2 exist: channel-9 split fit, blackbox.py:6716-6760),
+    without cosmics_corr; case 3 a 2x2-binned frame through gain_corr + os_corr."""
     from blackbox_b200 import set_bb
     from oracle import reduce as R
     g = GOLD['frames'][idx]
@@ -64,11 +71,14 @@ def test_oracle_equals_the_reference_step_by_step(idx, small_bb):
     data = np.array(raw, dtype=np.float32)
     R.gain_corr(data, header, tel=tel)
     assert digest(data) == g['gain_sha256']
-    data = R.os_corr(data, header, 'object', tel=tel)
+    xbin = g.get('xbin', 1)
+    data = R.os_corr(data, header, 'object', xbin=xbin, ybin=xbin, tel=tel)
     assert spots(data) == pytest.approx(g['os_spots'], rel=1e-6)
     assert digest(data) == g['os_sha256']
     for key, want in g['os_header'].items():
         assert header[key] == want, key
+    if xbin == 2:
+        return
     if set_bb.get_par(set_bb.subtract_mbias, tel):
         data -= mbias
     data_mask, header_mask = R.mask_init(data, header, bpm, 'object', tel=tel)
@@ -77,12 +87,16 @@ def test_oracle_equals_the_reference_step_by_step(idx, small_bb):
     for key, want in g['mask_header'].items():
         if key != 'NCOSMICS':
             assert float(header_mask[key]) == want, key
-    if g['ysize_chan'] > 400:
+    if g['ysize_chan'] > 400 and g['cosmics']:
         return
     data /= mflat
-    data, data_mask = R.cosmics_corr(data, header, data_mask, header_mask, tel=tel)
-    assert digest(data_mask) == g['cosmics_mask_sha256'] and digest(data) == g['cosmics_sha256']
-    assert header['NCOSMICS'] == g['NCOSMICS']
+    if g['cosmics']:
+        data, data_mask = R.cosmics_corr(data, header, data_mask, header_mask, tel=tel)
+        assert digest(data_mask) == g['cosmics_mask_sha256'] and digest(data) == g['cosmics_sha256']
+        assert header['NCOSMICS'] == g['NCOSMICS']
+    hm2 = {}
+    R.mask_header(data_mask, hm2, tel=tel)
+    assert {k: int(v) for k, v in hm2.items() if k.endswith('NUM')} == g['mask_header_counts']
     R.xtalk_corr(data, coeffs, data_mask, tel=tel)
     assert digest(data) == g['xtalk_sha256']
 
@@ -114,9 +128,12 @@ def test_gpu_chain_against_the_reference(idx, small_bb):
     tel = g['tel']
     small_bb(g['ysize_chan'], lim=dict(set_bb.hos_sat_ypix_lim))
     raw, mbias, mflat, bpm, coeffs = _inputs(g)
+    if g.get('xbin', 1) == 2 or not g['cosmics']:
+        return _gpu_steps(g, raw, mbias, mflat, bpm, coeffs)
     pipe = FramePipeline(tel, raw.shape, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, exptime=60.0)
     res = pipe.reduce(raw)
     assert digest(res.mask.cpu().numpy()) == g['cosmics_mask_sha256']
+    assert {k: int(v) for k, v in res.header_mask.items() if k.endswith('NUM')} == g['mask_header_counts']
     assert res.header['NCOSMICS'] == g['NCOSMICS']
     for key in ('BIASMEAN', 'RDNOISE'):
         assert res.header[key] == pytest.approx(g['os_header'][key], rel=1e-9)
@@ -124,6 +141,37 @@ def test_gpu_chain_against_the_reference(idx, small_bb):
     assert res.header['NOBJ-SAT'] == g['mask_header']['NOBJ-SAT']
     img = res.img.cpu().numpy()
     got, want = np.array(spots(img)), np.array(g['final_spots'])
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5 * g['os_header']['BIASMEAN'])
+    assert np.mean(got == want) >= 0.75
+
+
+def _gpu_steps(g, raw, mbias, mflat, bpm, coeffs):
+    """The cases that stop short of the whole chain, through the step functions."""
+    import torch
+    from blackbox_b200 import reduce as bbr, set_bb
+    tel, xbin = g['tel'], g.get('xbin', 1)
+    bbr.tel = tel
+    header = {'EXPTIME': 60.0}
+    data = bbr.os_corr(raw, header, 'object', xbin=xbin, ybin=xbin, tel=tel)
+    for key in ('BIASMEAN', 'RDNOISE'):
+        assert header[key] == pytest.approx(g['os_header'][key], rel=1e-9)
+    got, want = np.array(spots(data)), np.array(g['os_spots'])
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5 * g['os_header']['BIASMEAN'])
+    if xbin == 2:
+        assert np.mean(got == want) >= 0.75
+        return
+    dev = torch.from_numpy(data).cuda()
+    if set_bb.get_par(set_bb.subtract_mbias, tel):
+        dev -= torch.from_numpy(mbias).cuda()
+    mask, header_mask = bbr.mask_init(dev, header, 'q', 'object', bpm=bpm)
+    assert digest(mask.cpu().numpy()) == g['mask_init_sha256']
+    assert float(header_mask['SATURATE']) == pytest.approx(g['mask_header']['SATURATE'], rel=1e-9)
+    hm2 = {}
+    bbr.mask_header(mask, hm2)
+    assert {k: int(v) for k, v in hm2.items() if k.endswith('NUM')} == g['mask_header_counts']
+    dev /= torch.from_numpy(mflat).cuda()
+    bbr.xtalk_corr(dev, coeffs, mask)
+    got, want = np.array(spots(dev.cpu().numpy())), np.array(g['final_spots'])
     assert np.allclose(got, want, rtol=1e-5, atol=1e-5 * g['os_header']['BIASMEAN'])
     assert np.mean(got == want) >= 0.75
 
