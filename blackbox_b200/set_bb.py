@@ -15,6 +15,29 @@ subtract_mbias = {'ML1': False, 'BG': True}
 # maximum number of calibration frames combined into a master (set_blackbox.py:49)
 ncal_max = {'bias': 20, 'dark': 20, 'flat': 15}
 
+# days either side of the evening date whose calibration frames go into a master
+# (set_blackbox.py:47)
+cal_window = {'bias': 3, 'dark': 3, 'flat': 7}
+
+# BlackGEM evening flats show a reflection and are not used (set_blackbox.py:331)
+flat_reject_eve = {'ML': False, 'BG': True}
+
+# site folders read by master_prep (set_blackbox.py:89-152 derive them from the processing
+# environment; here plain per-telescope settings, to be pointed at the site's folders):
+# reduced frames live in [red_dir]/yyyy/mm/dd/[imgtype]/, masters in
+# [master_dir]/yyyy/mm/dd/[imgtype]/ (blackbox.py:1127-1128, 1649, 1797)
+red_dir = {'ML1': '/data/red/ML1', 'BG2': '/data/red/BG2', 'BG3': '/data/red/BG3', 'BG4': '/data/red/BG4'}
+master_dir = {'ML1': '/data/masters/ML1', 'BG2': '/data/masters/BG2', 'BG3': '/data/masters/BG3',
+              'BG4': '/data/masters/BG4'}
+
+# bad-pixel masks; master_prep and mask_init insert the filter: 'bpm' -> 'bpm_<filt>'
+# (set_blackbox.py:187-193)
+cal_dir = '/data/CalFiles'
+bad_pixel_mask = {'ML1': cal_dir + '/BPM/ML1/ML1_bpm_0p2_20200727.fits',
+                  'BG2': cal_dir + '/BPM/BG2/BG2_bpm_0p2_20250130.fits',
+                  'BG3': cal_dir + '/BPM/BG3/BG3_bpm_0p2_20250130.fits',
+                  'BG4': cal_dir + '/BPM/BG4/BG4_bpm_0p2_20250130.fits'}
+
 # degree of the polynomial fitted to the vertical-overscan row means (set_blackbox.py:52)
 voscan_poldeg = 3
 

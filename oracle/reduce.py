@@ -415,6 +415,52 @@ def master_median(frames, imgtype='bias', medsec=None, bpm=None, tel=None):
     return out, scales
 
 
+def master_flat_stats(frames, medsec=None, bpm=None, tel=None):
+    """The deterministic part of the master-flat header (blackbox.py:5006-5013, 5081-5161):
+    MFMEDSEC / MFSTDSEC over flat_norm_sec of the median BEFORE the edge / non-positive fix, and
+    the channel factors GAINCF of the fixed master.  -> (master, dict)."""
+    master_median, _ = master_median_unfixed(frames, medsec, tel)
+    sec_tmp = get_par(set_bb.flat_norm_sec, tel)
+    out = {'MFMEDSEC': np.median(master_median[sec_tmp]), 'MFSTDSEC': np.std(master_median[sec_tmp])}
+    if bpm is not None:
+        master_median[(bpm == get_par(set_bb.mask_value, tel)['edge']) | (master_median <= 0)] = 1
+    data_shape = master_median.shape
+    data_sec_red = define_sections(data_shape, tel=tel)[4]
+    nchans = np.shape(data_sec_red)[0]
+    med_chan_cntr = np.zeros(nchans)
+    master_median_corr = np.copy(master_median)
+    nrows = 200
+    for i_chan in range(nchans):
+        data_chan = master_median_corr[data_sec_red[i_chan]]
+        if i_chan < 8:
+            med_chan_cntr[i_chan] = np.median(data_chan[-nrows:, :])
+        else:
+            med_chan_cntr[i_chan] = np.median(data_chan[0:nrows, :])
+        master_median_corr[data_sec_red[i_chan]] /= med_chan_cntr[i_chan]
+    factor_chan = 1. / med_chan_cntr
+    ysize, xsize = data_shape
+    ny, nx = get_par(set_bb.ny, tel), get_par(set_bb.nx, tel)
+    dy, dx = ysize // ny, xsize // nx
+    nrows, ncols = 2000, 200
+    for i in range(1, nx):
+        y_index, x_index = dy, i * dx
+        data_stat1 = master_median_corr[y_index - nrows:y_index + nrows, x_index - ncols:x_index]
+        data_stat2 = master_median_corr[y_index - nrows:y_index + nrows, x_index:x_index + ncols]
+        ratio = np.median(data_stat1) / np.nanmedian(data_stat2)
+        master_median_corr[data_sec_red[i]] *= ratio
+        master_median_corr[data_sec_red[i + nx]] *= ratio
+        factor_chan[i] *= ratio
+        factor_chan[i + nx] *= ratio
+    factor_chan /= np.mean(factor_chan)
+    for i_chan in range(nchans):
+        out['GAINCF{}'.format(i_chan + 1)] = factor_chan[i_chan]
+    return master_median, out
+
+
+def master_median_unfixed(frames, medsec=None, tel=None):
+    return master_median(frames, imgtype='flat', medsec=medsec, bpm=None, tel=tel)
+
+
 def nonlin_corr(data, fit_splines, tel=None):
     """In place; blackbox.py:7392-7437 verbatim (fit_splines: the unpickled list of 16 spline
     objects).  Note the reference's ``frac_corr = np.ones(...)``: above 50000 counts the data are

@@ -64,6 +64,11 @@ def _stub(name, **attrs):
 class Header(dict):
     """astropy.io.fits.Header stand-in: header[key] = (value, comment) stores the value."""
 
+    @property
+    def comments(self):
+        import collections
+        return collections.defaultdict(str)
+
     def __setitem__(self, key, value):
         if isinstance(value, tuple) and len(value) == 2:
             value = value[0]
@@ -97,6 +102,52 @@ class _Table:
         return out
 
 
+class Time:
+    """astropy.time.Time stand-in for what master_prep needs: Time(iso string or list).mjd,
+    Time(mjd, format='mjd').isot, Time.now().isot (UTC; an MJD in UTC involves no leap seconds)."""
+    _EPOCH = __import__('datetime').datetime(1858, 11, 17)
+
+    def __init__(self, val, format=None):
+        import datetime
+        if format == 'mjd':
+            self.mjd = float(val)
+        elif isinstance(val, (list, tuple)):
+            self.mjd = np.array([Time(v).mjd for v in val])
+        else:
+            d = datetime.datetime.fromisoformat(str(val).strip().replace(' ', 'T')) - self._EPOCH
+            self.mjd = d.days + (d.seconds + d.microseconds * 1e-6) / 86400.0
+
+    @property
+    def isot(self):
+        import datetime
+        return (self._EPOCH + datetime.timedelta(days=self.mjd)).isoformat(timespec='milliseconds')
+
+    @classmethod
+    def now(cls):
+        return cls(60000.0, format='mjd')
+
+
+def _read_hdulist(name, get_data=True, get_header=False, dtype=None, **k):
+    """zogy.read_hdulist stand-in over the in-memory files: entries are arrays or (array, Header)."""
+    entry = _files[name]
+    data, header = entry if isinstance(entry, tuple) else (entry, Header())
+    if get_data and get_header:
+        return np.array(data, dtype=dtype, copy=True), header
+    if get_header:
+        return header
+    return np.array(data, dtype=dtype, copy=True)
+
+
+def _list_files(path, search_str='', end_str='', start_str=None, recursive=False):
+    return [k for k in _files if k.startswith(path) and search_str in k[len(path):] and k.endswith(end_str)]
+
+
+def _haversine(ra1, dec1, ra2, dec2):
+    r1, d1, r2, d2 = (np.radians(np.asarray(v, dtype=float)) for v in (ra1, dec1, ra2, dec2))
+    a = np.sin((d2 - d1) / 2) ** 2 + np.cos(d1) * np.cos(d2) * np.sin((r2 - r1) / 2) ** 2
+    return np.degrees(2 * np.arcsin(np.sqrt(a)))
+
+
 def load_reference():
     from blackbox_b200.set_bb import get_par
     from oracle import lacosmic as olac, stats as ostats
@@ -112,7 +163,7 @@ def load_reference():
     _stub('astroscrappy', detect_cosmics=olac.detect_cosmics)
     fits = types.SimpleNamespace(Header=Header)
     zogy = _stub('zogy', np=np, ndimage=ndimage, interpolate=interpolate, get_par=get_par, fits=fits, Table=_Table,
-                 read_hdulist=lambda name, dtype=None, **k: np.array(_files[name], dtype=dtype, copy=True),
+                 read_hdulist=_read_hdulist,
                  sigma_clip=ostats.sigma_clip, sigma_clipped_stats=ostats.sigma_clipped_stats,
                  log_timing_memory=lambda *a, **k: None, mem_use=lambda *a, **k: None, isfile=os.path.isfile)
     zogy.__all__ = ['np', 'ndimage', 'interpolate', 'get_par', 'fits', 'Table', 'read_hdulist', 'log_timing_memory',
@@ -120,6 +171,11 @@ def load_reference():
     sys.path.insert(0, os.path.join(REF, 'Settings'))
     sys.path.insert(0, REF)
     import blackbox
+    blackbox.Time = Time
+    blackbox.list_files = _list_files
+    blackbox.haversine = _haversine
+    blackbox.run_qc_check = lambda header, tel, *a, **k: None
+    blackbox.get_rand_indices = lambda shape, fraction=0.2: tuple(slice(None) for _ in shape)
     blackbox.already_exists = lambda name, get_filename=False: ((name in _files, name) if get_filename
                                                                else name in _files)
     return blackbox
@@ -234,10 +290,52 @@ def nonlin_case(bb, seed):
         my_set_bb.ysize_chan, my_set_bb.xsize_chan, ref_set_bb.ysize_chan, ref_set_bb.xsize_chan = saved
 
 
+def master_case(bb, tel, imgtype, seed, ysc, date_eve='20240105', filt='q'):
+    """master_prep (blackbox.py:4625-5247) on a synthetic night held in memory: the reference's
+    own file selection, stack median, flat post-fix and header; write_fits is intercepted."""
+    from blackbox_b200 import set_bb as my_set_bb, synth
+    ref_set_bb = sys.modules['set_blackbox']
+    saved = (my_set_bb.ysize_chan, ref_set_bb.ysize_chan)
+    my_set_bb.ysize_chan = ref_set_bb.ysize_chan = ysc
+    written = {}
+
+    def write_fits(fits_out, data, header, **k):
+        written['name'], written['data'], written['header'] = fits_out, np.array(data), dict(header)
+        return fits_out
+
+    bb.write_fits = write_fits
+    try:
+        bb.tel = tel
+        shape = (2 * ysc, 8 * my_set_bb.xsize_chan)
+        red_dir = bb.get_par(ref_set_bb.red_dir, tel)
+        master_dir = bb.get_par(ref_set_bb.master_dir, tel)
+        _files.clear()
+        for name, frame, hdr in synth.make_cal_night(tel, imgtype, seed, shape, date_eve, filt):
+            _files['{}/{}'.format(red_dir, name)] = (frame, Header(hdr))
+        if imgtype == 'flat':
+            bpm = synth.make_masters(tel, seed + 1, shape)[2]
+            _files[bb.get_par(ref_set_bb.bad_pixel_mask, tel).replace('bpm', 'bpm_' + filt)] = bpm
+        tail = '_' + filt if imgtype == 'flat' else ''
+        fits_master = '{}/{}/{}/{}/{}/{}_{}_{}{}.fits'.format(master_dir, date_eve[0:4], date_eve[4:6], date_eve[6:8],
+                                                          imgtype, tel, imgtype, date_eve, tail)
+        got = bb.master_prep(fits_master, shape, True, pick_alt=False, tel=tel, proc_mode=None)
+        assert got == fits_master and written['name'] == fits_master, (got, written.get('name'))
+        skip = ('DATEFILE', 'MFMED', 'MFSTD', 'MBMEAN', 'MBRDN')
+        hdr = {k: (v if isinstance(v, (bool, str)) else (int(v) if isinstance(v, (int, np.integer)) else float(v)))
+               for k, v in written['header'].items()
+               if k not in skip and not k.startswith(('MBIASM', 'MBRDN'))}
+        return {'tel': tel, 'imgtype': imgtype, 'seed': seed, 'ysize_chan': ysc, 'date_eve': date_eve, 'filt': filt,
+                'master_sha256': digest(written['data'].astype(np.float32)), 'master_spots': spots(written['data']),
+                'header': hdr}
+    finally:
+        my_set_bb.ysize_chan, ref_set_bb.ysize_chan = saved
+        _files.clear()
+
+
 def main():
     bb = load_reference()
     out = {'reference_version': bb.__version__, 'numpy': np.__version__,
-           'sections': {}, 'frames': [], 'nonlin': []}
+           'sections': {}, 'frames': [], 'nonlin': [], 'masters': []}
     for shape, xb in (((10600, 12000), 1), ((5300, 6000), 2), ((10560, 10560), 1)):
         out['sections']['{}x{}_bin{}'.format(shape[0], shape[1], xb)] = sections_as_lists(
             bb.define_sections(shape, xbin=xb, ybin=xb, tel='BG3'))
@@ -246,6 +344,7 @@ def main():
     out['frames'].append(frame_case(bb, 'BG2', 4002, 5280, cosmics=False))     # full size: channel-9 split fit
     out['frames'].append(frame_case(bb, 'ML1', 5001, 400, xbin=2))             # 2x2 binned frame
     out['nonlin'].append(nonlin_case(bb, 11))
+    out['masters'] = [master_case(bb, 'ML1', 'bias', 7001, 40), master_case(bb, 'BG3', 'flat', 7101, 2000)]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_golden.json')
     with open(path, 'w') as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
