@@ -190,11 +190,12 @@ def write_xtalk_file(path, victim, source, corr):
 # -------------------------------------------------------------------------------------------
 # a night's worth of reduced calibration frames for master_prep (blackbox.py:4625-5247)
 # -------------------------------------------------------------------------------------------
-def make_cal_night(tel, imgtype, seed, shape, date_eve='20240105', filt='q'):
+def make_cal_night(tel, imgtype, seed, shape, date_eve='20240105', filt='q', with_data=True):
     """-> list of (relative path below red_dir, float32 frame, header dict) of reduced bias /
     flat frames around the evening date ``date_eve``, with what master_prep's selection has to
     deal with: a red-flagged frame, evening flats, frames of neighbouring nights, flats with and
-    without MEDSEC, a cluster of non-positive pixels inside the statistics section."""
+    without MEDSEC, a cluster of non-positive pixels inside the statistics section.
+    ``with_data=False``: names and headers only (frames None, no MEDSEC), for the selection logic."""
     import datetime
     rng = np.random.default_rng(seed)
     d0 = datetime.datetime.strptime(date_eve, '%Y%m%d')
@@ -202,24 +203,26 @@ def make_cal_night(tel, imgtype, seed, shape, date_eve='20240105', filt='q'):
     out = []
     if imgtype == 'flat':
         chan_level = 1.0 + 0.02 * rng.standard_normal(16)
-        resp = make_flat_response(seed + 1, shape, pix_noise=0.005)
+        resp = make_flat_response(seed + 1, shape, pix_noise=0.005) if with_data else None
         ysc, xsc = shape[0] // 2, shape[1] // 8
-        for c in range(16):
+        for c in range(16 if with_data else 0):
             resp[(c // 8) * ysc:(c // 8 + 1) * ysc, (c % 8) * xsc:(c % 8 + 1) * xsc] *= np.float32(chan_level[c])
         sec = set_bb.get_par(set_bb.flat_norm_sec, tel)
         # morning flats of the next UT day (fraction 0.3-0.45), two evening flats, one red-flagged
         plan = [(1, 0.30 + 0.02 * k, None) for k in range(7)] + [(0, 0.75, None), (1, 0.05, None), (1, 0.44, 'red')]
         for k, (day, frac, flag) in enumerate(plan):
             level = 20000.0 * (1.0 + 0.2 * rng.uniform(-1, 1))
-            frame = (np.float32(level) * resp * (1.0 + 0.004 * rng.standard_normal(shape, dtype=np.float32))
-                     ).astype(np.float32)
-            frame[sec[0].start + 10:sec[0].start + 13, sec[1].start + 20:sec[1].start + 24] = -5.0
-            frame[5, 7] = 0.0
+            frame = None
+            if with_data:
+                frame = (np.float32(level) * resp * (1.0 + 0.004 * rng.standard_normal(shape, dtype=np.float32))
+                         ).astype(np.float32)
+                frame[sec[0].start + 10:sec[0].start + 13, sec[1].start + 20:sec[1].start + 24] = -5.0
+                frame[5, 7] = 0.0
             mjd = mjd_eve + day + frac
             t = datetime.datetime(1858, 11, 17) + datetime.timedelta(days=mjd)
             hdr = {'IMAGETYP': 'flat', 'FILTER': filt, 'MJD-OBS': float(mjd), 'DATE-OBS': t.isoformat(),
                    'RA': 150.0 + 0.004 * k * (k % 3 != 0), 'DEC': -30.0 + 0.003 * k, 'ORIGFILE': 'raw_{:03d}'.format(k)}
-            if k % 2 == 0:
+            if k % 2 == 0 and with_data:
                 hdr['MEDSEC'] = float(np.median(frame[sec])) * 1.0005      # the header value wins
             if flag:
                 hdr['QC-FLAG'] = flag
@@ -233,7 +236,8 @@ def make_cal_night(tel, imgtype, seed, shape, date_eve='20240105', filt='q'):
         frac = 0.60 + 0.01 * k if k % 2 else 0.20 + 0.01 * k
         mjd = mjd_eve + night + frac
         t = datetime.datetime(1858, 11, 17) + datetime.timedelta(days=mjd)
-        frame = (3.0 * rng.standard_normal(shape, dtype=np.float32) + np.float32(0.1 * k)).astype(np.float32)
+        frame = (3.0 * rng.standard_normal(shape, dtype=np.float32) + np.float32(0.1 * k)).astype(np.float32) \
+            if with_data else None
         hdr = {'IMAGETYP': 'bias', 'MJD-OBS': float(mjd), 'DATE-OBS': t.isoformat(), 'ORIGFILE': 'raw_{:03d}'.format(k)}
         if k == 4:
             hdr['QC-FLAG'] = 'red'

@@ -19,10 +19,11 @@ def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def _night(g):
+def _night(g, with_data=True):
     from blackbox_b200 import set_bb, synth
     shape = (2 * g['ysize_chan'], 8 * set_bb.xsize_chan)
-    return shape, synth.make_cal_night(g['tel'], g['imgtype'], g['seed'], shape, g['date_eve'], g['filt'])
+    return shape, synth.make_cal_night(g['tel'], g['imgtype'], g['seed'], shape, g['date_eve'], g['filt'],
+                                       with_data=with_data)
 
 
 def _used(g, night):
@@ -86,7 +87,7 @@ def test_file_selection_equals_the_reference(idx, site, monkeypatch):
     to midnight); headers only -- the combine is stubbed, nothing touches the GPU."""
     from blackbox_b200 import masters
     g = GOLD[idx]
-    shape, night = _night(g)
+    shape, night = _night(g, with_data=False)
     _write_night(site, g, night, data=False)
     seen = {}
 
@@ -111,7 +112,7 @@ def test_master_prep_fallbacks(site, monkeypatch):
     (blackbox.py:4663-4676, 4802-4847, 5294-5395)."""
     from blackbox_b200 import fitsio, masters
     g = GOLD[0]
-    shape, night = _night(g)
+    shape, night = _night(g, with_data=False)
     tiny = np.zeros((2, 2), np.float32)
     monkeypatch.setattr(masters, 'combine_files', lambda *a: (None, {}))
     made = []
@@ -155,7 +156,7 @@ def test_all_frames_older_than_12_hours(site, monkeypatch):
     """blackbox.py:4876-4884."""
     from blackbox_b200 import masters
     g = dict(GOLD[0], date_eve='20240109')
-    shape, night = _night(GOLD[0])                         # frames of 2024-01-04 .. 06
+    shape, night = _night(GOLD[0], with_data=False)        # frames of 2024-01-04 .. 06
     _write_night(site, g, night, data=False)
     monkeypatch.setattr(masters, 'combine_files', lambda *a: pytest.fail('must not combine'))
     assert masters.master_prep(_fits_master(site, g), shape, True, pick_alt=False, tel='ML1') is None
