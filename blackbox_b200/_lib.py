@@ -71,6 +71,7 @@ _SIGNATURES = {
     'bbx_nonlin_corr': [P, I, I, I, I, P, P, P, P, P, I, F, P],
     'bbx_fits_decode': [P, I, I, SZ, P, P],
     'bbx_fits_encode': [P, I, I, SZ, P, P],
+    'bbx_rice_decode16': [P, SZ, P, P, I, I, I, I, P, P, P],
     'bbx_chanmed_work_bytes': [],
     'bbx_channel_medians': [P, I, I, I, I, I, P, P, P],
     'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],

@@ -13,8 +13,12 @@ GPU path needs:
   * ``write_primary`` write a header + a data unit; the data may already be big-endian bytes
                       produced on the GPU (``reduce.fits_encode`` -> ``bbx_fits_encode``).
 
-Tile-compressed (``.fz``, Rice) files are outside this module: ``funpack`` them first, or read
-them with astropy and hand the arrays to ``reduce`` / ``pipeline`` directly.
+  * ``read_compressed`` parse a tile-compressed image (``.fits.fz`` as written by fpack: an empty
+                      primary HDU and a binary table whose heap holds one Rice-coded tile per
+                      image row) and hand back the heap bytes plus the per-tile descriptors --
+                      the decoding is ``reduce.rice_decode`` -> ``bbx_rice_decode16`` on the GPU.
+                      Only what raw frames use: ZCMPTYPE RICE_1, ZBITPIX 16, BYTEPIX 2,
+                      BLOCKSIZE 32, row tiles; anything else raises FitsError.
 """
 import collections
 import os
@@ -139,6 +143,111 @@ def read_primary(path, pinned=False):
         return hdr, buf, info
     data = np.memmap(path, dtype=dt, mode='r', offset=hbytes, shape=shape)
     return hdr, data, info
+
+
+_TFORM_BYTES = {'L': 1, 'X': 1, 'B': 1, 'I': 2, 'J': 4, 'K': 8, 'A': 1, 'E': 4, 'D': 8, 'C': 8, 'M': 16,
+                'P': 8, 'Q': 16}
+
+
+def _tform_width(tform):
+    """Bytes a binary-table column takes in a row: rTa / rPt(max) / rQt(max)."""
+    t = str(tform).strip()
+    i = 0
+    while i < len(t) and t[i].isdigit():
+        i += 1
+    repeat = int(t[:i]) if i else 1
+    code = t[i] if i < len(t) else ''
+    if code not in _TFORM_BYTES:
+        raise FitsError('unsupported TFORM {!r}'.format(tform))
+    if code == 'X':
+        return (repeat + 7) // 8, code
+    return repeat * _TFORM_BYTES[code], code
+
+
+def read_compressed(path, pinned=False):
+    """-> (header, heap, offsets, lengths, info) of the first tile-compressed image of ``path``.
+    ``heap``: the table's heap as a uint8 numpy array (a memory map) or, with ``pinned``, a pinned
+    ``torch`` tensor; ``offsets`` (int64) / ``lengths`` (int32): one entry per tile, byte offset
+    into the heap and compressed size; ``info``: dict(bitpix, shape, bzero, bscale, blocksize,
+    bytepix, tile_shape).  ``header`` merges the primary and the extension keywords."""
+    with open(path, 'rb') as fh:
+        hdr, hbytes = read_header(fh)
+        if hdr.get('NAXIS', (0,))[0] != 0:
+            raise FitsError('{}: the primary HDU holds data; not an fpacked image'.format(path))
+        ext, ebytes = read_header(fh)
+        table_start = hbytes + ebytes
+        get = lambda k, d=None: ext[k][0] if k in ext else d
+        if get('XTENSION') != 'BINTABLE' or get('ZIMAGE') is not True:
+            raise FitsError('{}: the first extension is not a tile-compressed image'.format(path))
+        cmptype = str(get('ZCMPTYPE', '')).strip()
+        if cmptype not in ('RICE_1', 'RICE_ONE'):
+            raise FitsError('{}: ZCMPTYPE {!r} (RICE_1 is supported)'.format(path, cmptype))
+        if get('ZBITPIX') != 16 or get('ZNAXIS') != 2:
+            raise FitsError('{}: ZBITPIX {} / ZNAXIS {} (16-bit 2-D images are supported)'.format(
+                path, get('ZBITPIX'), get('ZNAXIS')))
+        shape = (int(get('ZNAXIS2')), int(get('ZNAXIS1')))
+        tile = (int(get('ZTILE2', 1)), int(get('ZTILE1', shape[1])))
+        if tile != (1, shape[1]):
+            raise FitsError('{}: tiles of {} (row tiles are supported)'.format(path, tile))
+        blocksize, bytepix = 32, 4
+        n = 1
+        while 'ZNAME{}'.format(n) in ext:
+            name = str(get('ZNAME{}'.format(n))).strip()
+            if name == 'BLOCKSIZE':
+                blocksize = int(get('ZVAL{}'.format(n)))
+            elif name == 'BYTEPIX':
+                bytepix = int(get('ZVAL{}'.format(n)))
+            n += 1
+        if blocksize != 32 or bytepix != 2:
+            raise FitsError('{}: BLOCKSIZE {} / BYTEPIX {} (32 / 2 are supported)'.format(path, blocksize, bytepix))
+        rowlen, nrows, pcount = int(get('NAXIS1')), int(get('NAXIS2')), int(get('PCOUNT', 0))
+        if nrows != shape[0]:
+            raise FitsError('{}: {} table rows for {} tiles'.format(path, nrows, shape[0]))
+        col_off, found = 0, None
+        for c in range(1, int(get('TFIELDS')) + 1):
+            width, code = _tform_width(get('TFORM{}'.format(c)))
+            if str(get('TTYPE{}'.format(c), '')).strip() == 'COMPRESSED_DATA':
+                found = (col_off, code)
+            col_off += width
+        if found is None or found[1] not in ('P', 'Q'):
+            raise FitsError('{}: no COMPRESSED_DATA column of variable-length bytes'.format(path))
+        fh.seek(table_start)
+        table = fh.read(rowlen * nrows)
+        if len(table) != rowlen * nrows:
+            raise FitsError('{}: truncated table'.format(path))
+        rows = np.frombuffer(table, dtype=np.uint8).reshape(nrows, rowlen)
+        if found[1] == 'P':
+            desc = rows[:, found[0]:found[0] + 8].copy().view('>i4').astype(np.int64)
+        else:
+            desc = rows[:, found[0]:found[0] + 16].copy().view('>i8').astype(np.int64)
+        lengths, offsets = desc[:, 0], desc[:, 1]
+        if (lengths <= 0).any():
+            raise FitsError('{}: {} tile(s) without Rice-coded bytes (stored in a fall-back column)'.format(
+                path, int((lengths <= 0).sum())))
+        theap = int(get('THEAP', rowlen * nrows))
+        heap_start = table_start + theap
+        heap_bytes = pcount - (theap - rowlen * nrows)
+        if (offsets < 0).any() or (offsets + lengths > heap_bytes).any():
+            raise FitsError('{}: tile descriptors point outside the heap'.format(path))
+        if os.path.getsize(path) < heap_start + heap_bytes:
+            raise FitsError('{}: truncated heap'.format(path))
+        if pinned:
+            import torch
+            heap = torch.empty(heap_bytes, dtype=torch.uint8).pin_memory()
+            fh.seek(heap_start)
+            if fh.readinto(heap.numpy()) != heap_bytes:
+                raise FitsError('{}: short read'.format(path))
+        else:
+            heap = np.memmap(path, dtype=np.uint8, mode='r', offset=heap_start, shape=(heap_bytes,))
+    merged = collections.OrderedDict(hdr)
+    for k, v in ext.items():
+        if k not in ('XTENSION', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'PCOUNT', 'GCOUNT', 'TFIELDS', 'THEAP') \
+                and not k.startswith(('TTYPE', 'TFORM', 'ZNAME', 'ZVAL', 'ZTILE', 'ZNAXIS')) \
+                and k not in ('ZIMAGE', 'ZCMPTYPE', 'ZBITPIX', 'ZSIMPLE', 'ZEXTEND', 'ZQUANTIZ', 'ZDITHER0'):
+            merged[k] = v
+    info = dict(bitpix=16, shape=shape, bzero=float(get('BZERO', 0.0)), bscale=float(get('BSCALE', 1.0)),
+                blocksize=blocksize, bytepix=bytepix, tile_shape=tile)
+    return merged, heap, offsets.astype(np.int64), lengths.astype(np.int32), info
 
 
 def to_native(data, info):

@@ -709,6 +709,36 @@ def fits_decode(be, info, out=None):
     return out
 
 
+def rice_decode(heap, offsets, lengths, info, out=None, check=True):
+    """Tile-compressed raw frame (``fitsio.read_compressed``: heap bytes + per-tile descriptors)
+    -> native CUDA tensor of shape ``info['shape']``: uint16 counts for BZERO 32768, else int16
+    (what read_hdulist returns for an fpacked raw frame, blackbox.py:1451).  The heap crosses
+    PCIe compressed; ``bbx_rice_decode16`` unpacks it.  ``check``: synchronise and raise on a
+    corrupt tile (pass False inside a pipeline and test ``rice_status`` later)."""
+    shape = tuple(info['shape'])
+    if info.get('bitpix') != 16 or info.get('bytepix', 2) != 2:
+        raise NotImplementedError('rice_decode: BITPIX {} / BYTEPIX {}'.format(info.get('bitpix'), info.get('bytepix')))
+    u16 = info.get('bzero', 0.0) == 32768.0 and info.get('bscale', 1.0) == 1.0
+    if not u16 and (info.get('bzero', 0.0) != 0.0 or info.get('bscale', 1.0) != 1.0):
+        raise NotImplementedError('rice_decode: BZERO {} / BSCALE {}'.format(info.get('bzero'), info.get('bscale')))
+    h = _to_dev(heap if not isinstance(heap, np.ndarray) else np.ascontiguousarray(heap)).view(torch.uint8).reshape(-1)
+    offs = _to_dev(np.ascontiguousarray(offsets, dtype=np.int64) if not isinstance(offsets, torch.Tensor) else offsets)
+    lens = _to_dev(np.ascontiguousarray(lengths, dtype=np.int32) if not isinstance(lengths, torch.Tensor) else lengths)
+    if offs.numel() != shape[0] or lens.numel() != shape[0] or offs.dtype != torch.int64 or lens.dtype != torch.int32:
+        raise ValueError('rice_decode: {} / {} descriptors for {} tiles'.format(offs.numel(), lens.numel(), shape[0]))
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint16 if u16 else torch.int16, device=h.device)
+    status = torch.empty(1, dtype=torch.int32, device=h.device)
+    call('bbx_rice_decode16', _ptr(h), h.numel(), _ptr(offs), _ptr(lens), shape[0], shape[1],
+         int(info.get('blocksize', 32)), int(u16), _ptr(out), _ptr(status), _stream())
+    if check:
+        code = int(status.item())
+        if code:
+            raise ValueError('rice_decode: corrupt compressed tile(s), status {}'.format(code))
+        return out
+    return out, status
+
+
 def fits_encode(data, out=None):
     """Native CUDA tensor (float32, uint16, int16 or uint8) -> big-endian data unit as a uint8
     CUDA tensor (uint16 is stored as int16 with BZERO 32768; uint8 needs no swap)."""

@@ -323,6 +323,18 @@ int bbx_nonlin_corr(float *img, int H, int W, int ysize_chan, int xsize_chan, co
 int bbx_fits_decode(const void *be, int bitpix, int unsigned16, size_t n, void *out, void *stream);
 int bbx_fits_encode(const void *in, int bitpix, int unsigned16, size_t n, void *out_be, void *stream);
 
+/* Tile-compressed images (.fits.fz, ZCMPTYPE 'RICE_1', 16-bit pixels: ZBITPIX 16, BYTEPIX 2,
+ * BLOCKSIZE 32, row tiles) -- what read_hdulist (blackbox.py:1451; astropy / CFITSIO on the host
+ * in the reference) unpacks for every raw frame.  heap: the binary table's heap (device,
+ * heap_bytes); offs / lens: device arrays, one entry per tile = byte offset into the heap and
+ * compressed length (the COMPRESSED_DATA column's descriptors); ntiles tiles of nx pixels, tile t
+ * = row t of out.  unsigned16 != 0: stored int16 + BZERO 32768 -> uint16 counts.  status: device
+ * int, zeroed by the call; afterwards bit 0 = a tile ran past its bytes, bit 1 = a descriptor
+ * points outside the heap (the affected rows are undefined); read it after synchronising. */
+int bbx_rice_decode16(const void *heap, size_t heap_bytes, const long long *offs, const int *lens,
+                      int ntiles, int nx, int blocksize, int unsigned16, void *out, int *status,
+                      void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * small elementwise helpers for the drop-in functions used one step at a time
  * ------------------------------------------------------------------------------------- */
