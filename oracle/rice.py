@@ -15,7 +15,7 @@ fits_rdecomp_short; FITS tiled-image convention, Pence, White & Seaman 2010):
           any FS decodes)
 
 PARITY UNPINNED: no fpack / CFITSIO / astropy here to produce or read a real .fz file; the two
-hand-derived known-answer vectors in tests/test_rice.py follow from the format text above.
+hand-derived known-answer vectors in tests/test_zz_rice_fz.py follow from the format text above.
 """
 import numpy as np
 
