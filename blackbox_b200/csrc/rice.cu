@@ -15,13 +15,18 @@
 //   diff   = zig-zag mapped (even = +d/2, odd = ~(d >> 1)) difference to the previous pixel,
 //            modulo 2^16; bits are packed MSB first.
 // The bit position of a block is only known once the block before it is decoded, so a tile is a
-// serial job: one thread per tile (a frame has 10600 of them).  The 32 threads of a warp decode
-// one 32-pixel block each into shared memory, then the warp stores 32 row segments of 64
-// contiguous bytes -- the global stores are whole sectors although every thread works on its own
-// row.  Reads are byte loads through the read-only path (each 32-byte sector serves ~25 pixels).
+// serial job: one thread per tile (a frame has 10600 of them), and every step of it depends on
+// the one before, so what limits the kernel is instruction latency, not bandwidth.  Hence only
+// RICE_TILES = 4 lanes of a warp decode (a 32-pixel block each, into shared memory): 2650 warps
+// instead of 332 give every scheduler several warps to switch between, and fewer lanes means
+// fewer divergent paths per warp (measured on B200, full frame: 32 tiles per warp 3.7 ms).  The
+// whole warp then stores the staged row segments, 64 contiguous bytes per row -- whole sectors,
+// although every decoding thread works on its own row.  Reads are byte loads through the
+// read-only path (each 32-byte sector serves ~25 pixels).
 #include "bbx_common.cuh"
 
 #define RICE_WARPS 4
+#define RICE_TILES 4             // tiles (= decoding lanes) per warp
 #define RICE_BLOCK 32
 #define RICE_ROW   34            // uint16 per staging row: 17 words, odd, so lanes spread over the banks
 
@@ -44,12 +49,12 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
                      const int *__restrict__ lens, int ntiles, int nx, uint16_t *__restrict__ out,
                      int *__restrict__ status)
 {
-    __shared__ uint16_t stage[RICE_WARPS][32][RICE_ROW];
+    __shared__ uint16_t stage[RICE_WARPS][RICE_TILES][RICE_ROW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile0 = (blockIdx.x * RICE_WARPS + warp) * 32;
+    const int tile0 = (blockIdx.x * RICE_WARPS + warp) * RICE_TILES;
     if (tile0 >= ntiles) return;
     const int tile = tile0 + lane;
-    const bool live = tile < ntiles;
+    const bool live = lane < RICE_TILES && tile < ntiles;
 
     RiceReader r;
     r.c = r.end = heap;
@@ -70,7 +75,7 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
     const int fsbits = 4, fsmax = 14, bbits = 16;
     for (int i = 0; i < nx; i += RICE_BLOCK) {
         const int nthis = min(RICE_BLOCK, nx - i);
-        uint16_t *row = stage[warp][lane];
+        uint16_t *row = stage[warp][lane & (RICE_TILES - 1)];
         if (live && !bad) {
             r.nbits -= fsbits;
             while (r.nbits < 0) { r.b = (r.b << 8) | r.next(); r.nbits += 8; }
@@ -114,7 +119,7 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
         }
         __syncwarp();
         if (lane < nthis) {
-            const int rows = min(32, ntiles - tile0);
+            const int rows = min(RICE_TILES, ntiles - tile0);
             for (int t = 0; t < rows; t++) {
                 uint16_t v = stage[warp][t][lane];
                 if (FLIP) v ^= 0x8000u;                         // BZERO = 32768: stored int16 -> counts
@@ -144,7 +149,7 @@ extern "C" int bbx_rice_decode16(const void *heap, size_t heap_bytes, const long
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
     BBX_REQUIRE(e == cudaSuccess, "bbx_rice_decode16: %s", cudaGetErrorString(e));
-    const int per_block = RICE_WARPS * 32;
+    const int per_block = RICE_WARPS * RICE_TILES;
     const int blocks = (ntiles + per_block - 1) / per_block;
     if (unsigned16)
         rice16_decode_kernel<true><<<blocks, RICE_WARPS * 32, 0, st>>>((const uint8_t *)heap, heap_bytes, offs, lens,
