@@ -15,31 +15,58 @@
 //   diff   = zig-zag mapped (even = +d/2, odd = ~(d >> 1)) difference to the previous pixel,
 //            modulo 2^16; bits are packed MSB first.
 // The bit position of a block is only known once the block before it is decoded, so a tile is a
-// serial job: one thread per tile (a frame has 10600 of them), and every step of it depends on
-// the one before, so what limits the kernel is instruction latency, not bandwidth.  Hence only
-// RICE_TILES = 4 lanes of a warp decode (a 32-pixel block each, into shared memory): 2650 warps
-// instead of 332 give every scheduler several warps to switch between, and fewer lanes means
-// fewer divergent paths per warp (measured on B200, full frame: 32 tiles per warp 3.7 ms).  The
-// whole warp then stores the staged row segments, 64 contiguous bytes per row -- whole sectors,
-// although every decoding thread works on its own row.  Reads are byte loads through the
-// read-only path (each 32-byte sector serves ~25 pixels).
+// serial job: one thread per tile (a frame has 10600 of them), every step depending on the one
+// before.  What decides the speed is therefore (1) that the lanes of a warp, each in its own
+// tile, run the SAME instructions -- a decoder written as CFITSIO's byte-at-a-time loops diverges
+// completely and the warp executes its 32 tiles one after the other (measured on B200, full
+// 10600 x 12000 frame: 3.7 ms; this version 2.45 ms, profiles/r01_rice_bench.txt) -- and (2) the
+// length of the dependent chain per pixel, which is what is left (about 390 cycles per pixel and
+// tile; two tiles per thread would give the scheduler independent work).  So:
+//   * the stream is read through a 64-bit window (bit 63 = next bit) refilled with one aligned
+//     32-bit load whenever 32 bits or fewer are left -- one predicated block, no loops;
+//   * a pixel is decoded without branches: count-leading-zeros of the top 32 bits gives the unary
+//     part, two shifts the FS low bits; the "all zero" and "raw 16 bit" block types are selects
+//     on the same values; only a code longer than 32 bits (a rare outlier) takes a side path;
+//   * RICE_TILES = 8 lanes of a warp decode (1325 warps for a frame, so every scheduler has
+//     warps to switch between); all 32 lanes then store the staged 32-pixel row segments, 64
+//     contiguous bytes per row -- whole sectors, although every decoder works on its own row.
 #include "bbx_common.cuh"
 
 #define RICE_WARPS 4
-#define RICE_TILES 4             // tiles (= decoding lanes) per warp
+#define RICE_TILES 8             // tiles (= decoding lanes) per warp
 #define RICE_BLOCK 32
 #define RICE_ROW   34            // uint16 per staging row: 17 words, odd, so lanes spread over the banks
 
 struct RiceReader {
-    const uint8_t *c, *end;
-    unsigned int b;
-    int nbits;
-    bool overrun;
-    __device__ __forceinline__ unsigned int next()
+    const uint8_t *heap, *heap_end;
+    const uint8_t *next;         // next aligned word to load
+    unsigned long long win;
+    int have;                    // valid bits in win
+    long long loaded;            // bits loaded so far
+
+    // 32 bits at an aligned address, big-endian; bytes outside the heap read as 0xff (a one bit
+    // ends every unary run, so a corrupt tile cannot loop past the end of the heap)
+    __device__ __forceinline__ unsigned int word(const uint8_t *a) const
     {
-        if (c < end) return __ldg(c++);
-        overrun = true;
-        return 0xffu;            // a one bit ends every unary run: no endless loop on a truncated tile
+        if (a >= heap && a + 4 <= heap_end)
+            return __byte_perm(__ldg(reinterpret_cast<const unsigned int *>(a)), 0, 0x0123);
+        unsigned int w = 0;
+        for (int k = 0; k < 4; k++) w = (w << 8) | ((a + k >= heap && a + k < heap_end) ? __ldg(a + k) : 0xffu);
+        return w;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (have <= 32) {
+            win |= (unsigned long long)word(next) << (32 - have);
+            next += 4; have += 32; loaded += 32;
+        }
+    }
+    __device__ __forceinline__ void drop(int n) { win <<= n; have -= n; }              // n in [0, 32]
+    __device__ __forceinline__ unsigned int take(int n)                                // n in [1, 32]
+    {
+        const unsigned int v = (unsigned int)(win >> (64 - n));
+        drop(n);
+        return v;
     }
 };
 
@@ -57,9 +84,11 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
     const bool live = lane < RICE_TILES && tile < ntiles;
 
     RiceReader r;
-    r.c = r.end = heap;
-    r.b = 0; r.nbits = 8; r.overrun = false;
+    r.heap = heap; r.heap_end = heap + heap_bytes;
+    r.next = heap; r.win = 0; r.have = 0; r.loaded = 0;
     bool bad = false;
+    long long tile_bits = 0;
+    int skip = 0;
     unsigned int lastpix = 0;
     if (live) {
         const long long o = offs[tile];
@@ -67,54 +96,54 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
         if (o < 0 || n < 3 || (unsigned long long)o + (unsigned long long)n > heap_bytes) {
             bad = true;
         } else {
-            r.c = heap + o; r.end = r.c + n;
-            lastpix = (r.next() << 8) | r.next();
-            r.b = r.next();
+            const uintptr_t start = (uintptr_t)(heap + o);
+            skip = (int)(start & 3) * 8;                        // bits in front of the tile in its first word
+            r.next = reinterpret_cast<const uint8_t *>(start & ~(uintptr_t)3);
+            tile_bits = 8ll * n;
+            r.refill();
+            r.drop(skip);
+            r.refill();
+            lastpix = r.take(16);
         }
     }
-    const int fsbits = 4, fsmax = 14, bbits = 16;
+    const bool work = live && !bad;
     for (int i = 0; i < nx; i += RICE_BLOCK) {
         const int nthis = min(RICE_BLOCK, nx - i);
         uint16_t *row = stage[warp][lane & (RICE_TILES - 1)];
-        if (live && !bad) {
-            r.nbits -= fsbits;
-            while (r.nbits < 0) { r.b = (r.b << 8) | r.next(); r.nbits += 8; }
-            const int fs = (int)(r.b >> r.nbits) - 1;
-            r.b &= (1u << r.nbits) - 1u;
-            if (fs < 0) {
-                for (int k = 0; k < nthis; k++) row[k] = (uint16_t)lastpix;
-            } else if (fs == fsmax) {
-                for (int k = 0; k < nthis; k++) {
-                    int s = bbits - r.nbits;
-                    unsigned int diff = r.b << s;
-                    for (s -= 8; s >= 0; s -= 8) { r.b = r.next(); diff |= r.b << s; }
-                    if (r.nbits > 0) { r.b = r.next(); diff |= r.b >> (-s); r.b &= (1u << r.nbits) - 1u; }
-                    else r.b = 0;
-                    diff &= 0xffffu;
-                    diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
-                    lastpix = (lastpix + diff) & 0xffffu;
-                    row[k] = (uint16_t)lastpix;
-                }
-            } else {
-                for (int k = 0; k < nthis; k++) {
-                    unsigned int nzero = 0;
-                    while (r.b == 0) {
-                        nzero += r.nbits;            // the rest of the window is zeros
-                        r.nbits = 8; r.b = r.next();
-                        if (r.overrun) break;
+        if (work) {
+            r.refill();
+            const int fs = (int)r.take(4) - 1;
+            const bool raw = fs == 14, zero = fs < 0;
+            const int fsn = max(fs, 0);
+            for (int k = 0; k < nthis; k++) {
+                r.refill();                                     // at least 33 bits in the window
+                const unsigned int top = (unsigned int)(r.win >> 32);
+                const int z = __clz(top);                       // 32 if the top half is all zeros
+                const int len = raw ? 16 : zero ? 0 : z + 1 + fsn;
+                unsigned int diff;
+                if (len <= 32) {
+                    const unsigned long long rest = r.win << (z + 1);
+                    const unsigned int low = (unsigned int)((rest >> 1) >> (63 - fsn));   // fs = 0: nothing
+                    diff = raw ? (top >> 16) : zero ? 0u : (((unsigned int)z << fsn) | low);
+                    r.drop(len);
+                } else {
+                    // a code longer than 32 bits: count the zeros across refills, then the low bits
+                    unsigned int nz = 0;
+                    for (;;) {
+                        r.refill();
+                        if (r.win == 0) { nz += r.have; r.have = 0; continue; }
+                        const int zz = __clzll((long long)r.win);
+                        nz += zz;
+                        r.win = (r.win << zz) << 1; r.have -= zz + 1;
+                        break;
                     }
-                    const int top = 32 - __clz(r.b);            // position of the leading one, 1-based
-                    nzero += r.nbits - top;
-                    r.nbits = top - 1;
-                    r.b ^= 1u << r.nbits;
-                    r.nbits -= fs;
-                    while (r.nbits < 0) { r.b = (r.b << 8) | r.next(); r.nbits += 8; }
-                    unsigned int diff = (nzero << fs) | (r.b >> r.nbits);
-                    r.b &= (1u << r.nbits) - 1u;
-                    diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
-                    lastpix = (lastpix + diff) & 0xffffu;
-                    row[k] = (uint16_t)lastpix;
+                    r.refill();
+                    diff = nz << fsn;
+                    if (fsn > 0) diff |= r.take(fsn);
                 }
+                diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
+                lastpix = (lastpix + diff) & 0xffffu;
+                row[k] = (uint16_t)lastpix;
             }
         }
         __syncwarp();
@@ -128,7 +157,9 @@ rice16_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const 
         }
         __syncwarp();
     }
-    if (live && (bad || r.overrun)) atomicOr(status, bad ? 2 : 1);
+    // bits consumed beyond the tile's own bytes: a truncated or corrupt tile
+    const bool overrun = work && (r.loaded - r.have - skip > tile_bits);
+    if (live && (bad || overrun)) atomicOr(status, bad ? 2 : 1);
 }
 
 // ---------------------------------------------------------------------------------------------
