@@ -237,7 +237,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from blackbox_b200 import reduce as R, set_bb, synth
-    from blackbox_b200.pipeline import BatchReducer, FramePipeline
+    from blackbox_b200.pipeline import BatchReducer
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)

@@ -13,7 +13,6 @@ more rounds) and returns the header values.
 Frames are independent, so a night batch shards one frame per GPU (``shard_frames``); nothing
 is exchanged between ranks.
 """
-import contextlib
 
 import numpy as np
 import torch

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib, hostfit, set_bb
 from ._lib import BbxMaskBits, call, query
-from .geometry import Geometry, define_sections
+from .geometry import Geometry, define_sections  # noqa: F401  (define_sections: part of the mirrored surface)
 from .set_bb import get_par
 
 tel = None          # module-global telescope name, as in the reference (blackbox.py:141)
