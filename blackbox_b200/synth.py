@@ -245,3 +245,21 @@ def make_cal_night(tel, imgtype, seed, shape, date_eve='20240105', filt='q', wit
         name = '{}/bias/{}_{}_{}_red.fits'.format(sub, tel, t.strftime('%Y%m%d'), t.strftime('%H%M%S'))
         out.append((name, frame, hdr))
     return out
+
+
+def add_hos_contamination(raw, ysize_chan, os_rows=20, xsize_chan=None, os_cols=180, level=3000):
+    """Bright charge leaking into the horizontal overscan (what MeerLICHT's ``data_limit`` mask in
+    os_corr is for, blackbox.py:6586-6614): in channels 3 (bottom) and 12 (top) one isolated
+    column and a six-column band get ``level`` ADU more over the overscan rows and the data rows
+    next to them, and one isolated column in only 3 of the overscan rows (less than half the
+    height: it stays masked pixel by pixel).  In place."""
+    xs = set_bb.xsize_chan if xsize_chan is None else xsize_chan
+    wchan = xs + os_cols
+    hchan = ysize_chan + os_rows
+    for chan, rows in ((2, slice(hchan - os_rows - 30, hchan)), (11, slice(hchan, hchan + os_rows + 30))):
+        x0 = (chan % 8) * wchan
+        for cols in (slice(x0 + 400, x0 + 401), slice(x0 + 700, x0 + 706)):
+            raw[rows, cols] = np.minimum(raw[rows, cols].astype(np.int64) + level, 65535).astype(raw.dtype)
+        short = slice(hchan - 8, hchan - 5) if chan < 8 else slice(hchan + 5, hchan + 8)
+        raw[short, x0 + 900] = np.minimum(raw[short, x0 + 900].astype(np.int64) + level, 65535).astype(raw.dtype)
+    return raw

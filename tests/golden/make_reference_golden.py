@@ -194,7 +194,7 @@ def sections_as_lists(secs):
     return [[[[s.start, s.stop] for s in pair] for pair in tup] for tup in secs]
 
 
-def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1):
+def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1, variant=None):
     """gain_corr -> os_corr -> (bias) -> mask_init -> flat -> cosmics_corr -> xtalk_corr, the order of
     blackbox_reduce (blackbox.py:1479-1902), every step the reference's own function."""
     from blackbox_b200 import set_bb as my_set_bb, synth
@@ -222,10 +222,14 @@ def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1):
             raw[ysc - 50:ysc, 300:304] = 65535                   # saturated columns next to the overscan
             raw[ysc - 900:ysc - 880, 1500 * 2 + 20:1500 * 2 + 24] = 65535
         raw[40:48, 2000:2008] = 65535
+        if variant == 'hos':
+            synth.add_hos_contamination(raw, ysc)
         shape = (2 * ysc, 8 * my_set_bb.xsize_chan)
         mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
         victim, source, corr, coeffs = synth.make_xtalk(seed + 2)
         out = {'tel': tel, 'seed': seed, 'ysize_chan': ysc, 'xbin': 1, 'cosmics': bool(cosmics), 'raw_sha256': digest(raw)}
+        if variant:
+            out['variant'] = variant
         header = Header(EXPTIME=60.0)
         data = np.array(raw, dtype='float32')
         bb.gain_corr(data, header, tel=tel)
@@ -343,6 +347,7 @@ def main():
     out['frames'].append(frame_case(bb, 'BG3', 4001, 2640))
     out['frames'].append(frame_case(bb, 'BG2', 4002, 5280, cosmics=False))     # full size: channel-9 split fit
     out['frames'].append(frame_case(bb, 'ML1', 5001, 400, xbin=2))             # 2x2 binned frame
+    out['frames'].append(frame_case(bb, 'ML1', 1002, 200, variant='hos'))      # charge in the horizontal overscan
     out['nonlin'].append(nonlin_case(bb, 11))
     out['masters'] = [master_case(bb, 'ML1', 'bias', 7001, 40), master_case(bb, 'BG3', 'flat', 7101, 2000)]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_golden.json')

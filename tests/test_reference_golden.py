@@ -37,6 +37,8 @@ def _inputs(g):
         raw[ysc - 50:ysc, 300:304] = 65535
         raw[ysc - 900:ysc - 880, 1500 * 2 + 20:1500 * 2 + 24] = 65535
     raw[40:48, 2000:2008] = 65535
+    if g.get('variant') == 'hos':
+        synth.add_hos_contamination(raw, ysc)
     assert digest(raw) == g['raw_sha256']
     shape = (2 * ysc, 8 * set_bb.xsize_chan)
     mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
