@@ -229,15 +229,15 @@ def master_prep(fits_master, data_shape, create_master, pick_alt=True, tel=None,
     master_present, fits_master = already_exists(fits_master, get_filename=True)
     master_ok = True
     if master_present:
-        log.info('master %s %s exists', imgtype, fits_master)
+        log.info('%s master already on disk: %s', imgtype, fits_master)
         if qc_flagged(fits_master):
             master_ok = False
-            log.warning('existing master %s %s contains a red flag', imgtype, fits_master)
+            log.warning('%s master %s is red-flagged', imgtype, fits_master)
     if master_present and master_ok:
         return fits_master
 
     if proc_mode == 'night' and not fits_master.startswith('gs://') and NIGHT_WAIT_S > 0:
-        log.warning('waiting for %ds for all individual calibration frames to have been reduced', NIGHT_WAIT_S)
+        log.warning('night mode: giving the calibration frames %d s to land on disk', NIGHT_WAIT_S)
         time.sleep(NIGHT_WAIT_S)
 
     nwindow = int(get_par(set_bb.cal_window, tel)[imgtype])
@@ -265,7 +265,7 @@ def master_prep(fits_master, data_shape, create_master, pick_alt=True, tel=None,
                 keep[i] = False
             if imgtype == 'flat' and get_par(set_bb.flat_reject_eve, tel) and \
                     (mjd_obs[i] % 1 > 0.5 or mjd_obs[i] % 1 < 0.1):
-                log.warning('rejecting evening flat %s', name)
+                log.warning('evening flat left out: %s', name)
                 keep[i] = False
         file_list = np.array(file_list)[keep]
         mjd_obs = mjd_obs[keep]
@@ -276,16 +276,16 @@ def master_prep(fits_master, data_shape, create_master, pick_alt=True, tel=None,
     if nfiles < 5 or not master_ok or not create_master:
         if not (pick_alt or not create_master):
             if master_ok:
-                log.warning('too few good frames available to produce master %s for evening date %s +/- window '
-                            'of %d days', msg, date_eve, nwindow)
+                log.warning('fewer than 5 usable frames for a master %s within %d days of %s', msg, nwindow,
+                            date_eve)
             return None
         near = get_nearest_master(date_eve, imgtype, fits_master, filt=filt, tel=tel)
         if near is None:
             if wanted:
-                log.error('no alternative master %s found', msg)
+                log.error('no nearby master %s to fall back on', msg)
             return None
         if wanted:
-            log.warning('using %s as master for evening date %s', near, date_eve)
+            log.warning('evening date %s: falling back on master %s', date_eve, near)
         return near
 
     nmax = int(get_par(set_bb.ncal_max, tel)[imgtype])
@@ -295,14 +295,13 @@ def master_prep(fits_master, data_shape, create_master, pick_alt=True, tel=None,
     delta = delta[order][0:nmax]
     nfiles_orig, nfiles = nfiles, len(file_list)
     if np.amin(np.abs(delta)) > 0.5 and np.all(delta < 0):
-        log.warning('all %d selected calibration files closest in time to midnight of %s are from before this '
-                    'date and taken longer than 12 hours ago; no point in making master %s', nmax, date_eve,
-                    fits_master)
+        log.warning('the %d frames nearest to midnight of %s all predate it by more than 12 hours; %s would '
+                    'repeat an older master and is not made', nmax, date_eve, fits_master)
         return None
-    log.info('making %s master %s for night %s from the following files:\n%s', tel, msg, date_eve, file_list)
+    log.info('%s master %s of %s from:\n%s', tel, msg, date_eve, file_list)
     if nfiles_orig > nmax:
-        log.warning('number of available %s frames (%d) exceeds the maximum specified (%d); using the frames '
-                    'closest in time to midnight of the evening date (%s)', imgtype, nfiles_orig, nmax, date_eve)
+        log.warning('%d %s frames found, ncal_max is %d: keeping the ones nearest to midnight of %s', nfiles_orig,
+                    imgtype, nmax, date_eve)
 
     master, header = combine_files(list(file_list), tuple(data_shape), imgtype, filt, nwindow, tel)
     return write_master(fits_master, master, header)
