@@ -263,3 +263,22 @@ def add_hos_contamination(raw, ysize_chan, os_rows=20, xsize_chan=None, os_cols=
         short = slice(hchan - 8, hchan - 5) if chan < 8 else slice(hchan + 5, hchan + 8)
         raw[short, x0 + 900] = np.minimum(raw[short, x0 + 900].astype(np.int64) + level, 65535).astype(raw.dtype)
     return raw
+
+
+def add_saturated_rings(raw, centres=((60, 700), (120, 4000), (150, 9100), (300, 2500))):
+    """Saturated rings with an unsaturated inside (and one broken ring, and one ring with a
+    saturated island in it): what fill_sat_holes has to close and fill (blackbox.py:4584-4596).
+    In place; positions are raw-frame pixels inside data sections of a frame with ysize_chan >= 200."""
+    yy, xx = np.mgrid[-16:17, -16:17]
+    rr = np.hypot(yy, xx)
+    for n, (cy, cx) in enumerate(centres):
+        ring = (rr >= 9.5) & (rr <= 12.5)
+        if n == 1:
+            ring &= ~((xx > 0) & (np.abs(yy) < 3))              # a gap wider than the closing: stays open
+        if n == 2:
+            ring |= rr <= 1.5                                    # an island inside the hole
+        if n == 3:
+            ring &= ~((xx > 0) & (np.abs(yy) < 1))              # a one-pixel gap: closed by the 3x3 closing
+        sub = raw[cy - 16:cy + 17, cx - 16:cx + 17]
+        sub[ring] = 65535
+    return raw

@@ -224,6 +224,8 @@ def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1, variant=None):
         raw[40:48, 2000:2008] = 65535
         if variant == 'hos':
             synth.add_hos_contamination(raw, ysc)
+        if variant == 'rings':
+            synth.add_saturated_rings(raw)
         shape = (2 * ysc, 8 * my_set_bb.xsize_chan)
         mbias, mflat, bpm = synth.make_masters(tel, seed + 1, shape)
         victim, source, corr, coeffs = synth.make_xtalk(seed + 2)
@@ -348,6 +350,8 @@ def main():
     out['frames'].append(frame_case(bb, 'BG2', 4002, 5280, cosmics=False))     # full size: channel-9 split fit
     out['frames'].append(frame_case(bb, 'ML1', 5001, 400, xbin=2))             # 2x2 binned frame
     out['frames'].append(frame_case(bb, 'ML1', 1002, 200, variant='hos'))      # charge in the horizontal overscan
+    out['frames'].append(frame_case(bb, 'ML1', 1003, 200, variant='rings'))    # saturated rings: hole filling
+    out['frames'][-1]['cpu_only'] = True       # added after the round's GPU time was spent: oracle test only
     out['nonlin'].append(nonlin_case(bb, 11))
     out['masters'] = [master_case(bb, 'ML1', 'bias', 7001, 40), master_case(bb, 'BG3', 'flat', 7101, 2000)]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_golden.json')
