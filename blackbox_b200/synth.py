@@ -282,3 +282,16 @@ def add_saturated_rings(raw, centres=((60, 700), (120, 4000), (150, 9100), (300,
         sub = raw[cy - 16:cy + 17, cx - 16:cx + 17]
         sub[ring] = 65535
     return raw
+
+
+def add_nonfinite(data, bpm):
+    """NaN / inf pixels in an overscan-corrected frame, two of them on pixels the bad-pixel mask
+    already flags: mask_init zeroes them and marks the unflagged ones 'bad'
+    (blackbox.py:4405-4413).  In place."""
+    data[100, 100:104] = np.nan
+    data[50, 5000] = np.inf
+    data[51, 5000] = -np.inf
+    ys, xs = np.nonzero(bpm[60:140, 2000:3000])
+    for y, x in list(zip(ys, xs))[:2]:
+        data[60 + y, 2000 + x] = np.nan
+    return data

@@ -246,6 +246,8 @@ def frame_case(bb, tel, seed, ysc, cosmics=True, xbin=1, variant=None):
         _files.clear()
         fits_bpm = bb.get_par(ref_set_bb.bad_pixel_mask, tel).replace('bpm', 'bpm_q')
         _files[fits_bpm] = bpm
+        if variant == 'rings':
+            synth.add_nonfinite(data, bpm)
         data_mask, header_mask = bb.mask_init(data, header, 'q', 'object')
         out['mask_init_sha256'] = digest(data_mask)
         out['mask_counts'] = {str(b): int(((data_mask & b) != 0).sum()) for b in (1, 4, 8, 32, 64)}
