@@ -25,6 +25,14 @@ def test_known_answers_from_the_format_text():
     #   code 0001 | 1 | 001 | 0001 -> 0001 1001 0001 0000
     assert rice.encode_tile16(np.array([-1, 0, -2], np.int16)) == bytes([0xff, 0xff, 0x19, 0x10])
     assert list(rice.decode_tile16(bytes([0xff, 0xff, 0x19, 0x10]), 3)) == [-1, 0, -2]
+    # [0, 3, 0, 3]: diffs 0, +3, -3, +3 -> 0, 6, 5, 6; sum 17, (17-2-1)/4 = 3.5 -> psum 1 -> FS 1
+    #   code 0010 | 1 0 | 0001 0 | 001 1 | 0001 0 -> 0010 1000 0100 0110 0010 (0000)
+    assert rice.encode_tile16(np.array([0, 3, 0, 3], np.int16)) == bytes.fromhex('0000284620')
+    assert list(rice.decode_tile16(bytes.fromhex('0000284620'), 4)) == [0, 3, 0, 3]
+    # [0, 20000]: diffs 0, 40000; (40000-1-1)/2 = 19999 -> psum 9999 -> FS 14 = FSMAX: raw block,
+    #   code 1111 | 0x0000 | 0x9c40
+    assert rice.encode_tile16(np.array([0, 20000], np.int16)) == bytes.fromhex('0000f00009c400')
+    assert list(rice.decode_tile16(bytes.fromhex('0000f00009c400'), 2)) == [0, 20000]
 
 
 @pytest.mark.parametrize('nx', [1, 31, 32, 33, 1000, 1500])
