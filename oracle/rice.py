@@ -154,10 +154,11 @@ def decode_tile16(buf, nx, nblock=32):
     return out.astype(np.uint16).view(np.int16)
 
 
-def write_fz(path, counts, header=None, pointer='P'):
+def write_fz(path, counts, header=None, pointer='P', lead_column=False):
     """A tile-compressed FITS file of a uint16 image as fpack lays it out: empty primary HDU,
     BINTABLE with one COMPRESSED_DATA column of row tiles (BZERO 32768, RICE_1, BLOCKSIZE 32,
-    BYTEPIX 2).  ``pointer``: 'P' (32-bit descriptors) or 'Q' (64-bit)."""
+    BYTEPIX 2).  ``pointer``: 'P' (32-bit descriptors) or 'Q' (64-bit).  ``lead_column``: put an
+    (empty) GZIP_COMPRESSED_DATA column in front, as CFITSIO does when it keeps a fall-back column."""
     from blackbox_b200 import fitsio
     counts = np.asarray(counts, dtype=np.uint16)
     H, W = counts.shape
@@ -167,12 +168,17 @@ def write_fz(path, counts, header=None, pointer='P'):
     offs = np.concatenate(([0], np.cumsum(lens)[:-1]))
     heap = b''.join(tiles)
     desc = np.stack([lens, offs], axis=1).astype('>i4' if pointer == 'P' else '>i8')
-    width = desc.dtype.itemsize * 2
+    if lead_column:
+        desc = np.concatenate([np.zeros_like(desc), desc], axis=1)
+    width = desc.dtype.itemsize * desc.shape[1]
     card = fitsio._card
     primary = [card('SIMPLE', True), card('BITPIX', 16), card('NAXIS', 0), card('EXTEND', True), 'END'.ljust(80)]
     ext = [("XTENSION= 'BINTABLE'").ljust(80), card('BITPIX', 8), card('NAXIS', 2), card('NAXIS1', width),
-           card('NAXIS2', H), card('PCOUNT', len(heap)), card('GCOUNT', 1), card('TFIELDS', 1),
-           card('TTYPE1', 'COMPRESSED_DATA'), card('TFORM1', '1{}B({})'.format(pointer, int(lens.max()))),
+           card('NAXIS2', H), card('PCOUNT', len(heap)), card('GCOUNT', 1), card('TFIELDS', 2 if lead_column else 1)]
+    cols = (['GZIP_COMPRESSED_DATA'] if lead_column else []) + ['COMPRESSED_DATA']
+    for n, name in enumerate(cols, 1):
+        ext += [card('TTYPE{}'.format(n), name), card('TFORM{}'.format(n), '1{}B({})'.format(pointer, int(lens.max())))]
+    ext += [
            card('ZIMAGE', True), card('ZSIMPLE', True), card('ZBITPIX', 16), card('ZNAXIS', 2), card('ZNAXIS1', W),
            card('ZNAXIS2', H), card('ZTILE1', W), card('ZTILE2', 1), card('ZCMPTYPE', 'RICE_1'),
            card('ZNAME1', 'BLOCKSIZE'), card('ZVAL1', 32), card('ZNAME2', 'BYTEPIX'), card('ZVAL2', 2),

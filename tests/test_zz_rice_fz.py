@@ -47,12 +47,13 @@ def test_oracle_round_trip(nx):
     assert len(rice.encode_tile16(stored[4])) >= 2 * nx
 
 
-@pytest.mark.parametrize('pointer', ['P', 'Q'])
-def test_read_compressed_parses_the_table(tmp_path, pointer):
+@pytest.mark.parametrize('pointer,lead', [('P', False), ('Q', False), ('P', True), ('Q', True)])
+def test_read_compressed_parses_the_table(tmp_path, pointer, lead):
     from blackbox_b200 import fitsio
     from oracle import rice
     rows = _rows(3, 700)
-    path = rice.write_fz(str(tmp_path / 'raw.fits.fz'), rows, {'EXPTIME': 60.0, 'FILTER': 'q'}, pointer=pointer)
+    path = rice.write_fz(str(tmp_path / 'raw.fits.fz'), rows, {'EXPTIME': 60.0, 'FILTER': 'q'}, pointer=pointer,
+                         lead_column=lead)
     hdr, heap, offs, lens, info = fitsio.read_compressed(path)
     assert info['shape'] == rows.shape and info['bzero'] == 32768.0 and info['blocksize'] == 32
     assert hdr['EXPTIME'][0] == 60.0 and hdr['FILTER'][0] == 'q' and 'TFORM1' not in hdr
