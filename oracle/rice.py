@@ -169,7 +169,7 @@ def write_fz(path, counts, header=None, pointer='P', lead_column=False):
     heap = b''.join(tiles)
     desc = np.stack([lens, offs], axis=1).astype('>i4' if pointer == 'P' else '>i8')
     if lead_column:
-        desc = np.concatenate([np.zeros_like(desc), desc], axis=1)
+        desc = np.concatenate([np.zeros_like(desc), desc], axis=1).astype(desc.dtype)   # keeps big-endian
     width = desc.dtype.itemsize * desc.shape[1]
     card = fitsio._card
     primary = [card('SIMPLE', True), card('BITPIX', 16), card('NAXIS', 0), card('EXTEND', True), 'END'.ljust(80)]
