@@ -197,3 +197,28 @@ def test_gpu_nonlin_against_the_reference(small_bb):
     data = rng.uniform(-500, 140000, size=(96, 480)).astype(np.float32)
     bbr.tel = 'BG3'
     assert digest(bbr.nonlin_corr(data.copy(), splines)) == g['output_sha256']
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/blackbox.py'), reason='the reference tree is not on this box')
+def test_generator_still_imports_and_runs_the_reference():
+    """Where the reference is present (the build container), the generator's stub modules still let
+    blackbox.py import, and its define_sections / gain_corr give what the fixture file holds --
+    i.e. the committed vectors can be regenerated.  In a subprocess: the stubs go into sys.modules."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, numpy as np\n"
+        "sys.path.insert(0, {gold!r}); sys.path.insert(0, {root!r})\n"
+        "import make_reference_golden as g\n"
+        "bb = g.load_reference()\n"
+        "secs = g.sections_as_lists(bb.define_sections((10600, 12000), xbin=1, ybin=1, tel='BG3'))\n"
+        "data = np.full((440, 12000), 2.0, dtype='float32'); hdr = g.Header()\n"
+        "bb.gain_corr(data, hdr, tel='ML1')\n"
+        "print(json.dumps({{'version': bb.__version__, 'secs': secs, 'gain1': hdr['GAIN1'], 'px': float(data[0, 0])}}))\n"
+    ).format(gold=os.path.join(HERE, 'golden'), root=os.path.dirname(HERE))
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out['version'] == GOLD['reference_version']
+    assert out['secs'] == GOLD['sections']['10600x12000_bin1']
+    assert out['gain1'] == 2.112 and out['px'] == float(np.float32(2.0) * np.float32(2.112))
