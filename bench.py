@@ -20,6 +20,16 @@ Printed JSON (rank 0, one line):
   roofline   the dominant single kernel of the chain (largest mean device time among the
              one-kernel stages, CUDA events on the launching stream INSIDE the timed region) against
              the measured HBM peak; roofline_stages lists every stage the same way
+  strong_scaling  the same night batch as ONE job of `--batch` frames in total, frame k -> GPU
+             k mod N (pipeline.shard_frames; the reference's pool over a fixed file list,
+             blackbox.py:378): frames/s incl. pipeline fill / drain at batch/N frames per GPU
+  master_sharded  BASELINE.json configs 5 and 2 on the same N GPUs: master bias of 50 binned
+             5280^2 frames and master flat of 20 full 10560^2 frames, row stripes per GPU, the
+             stack-median kernel writing into its slot of the gather buffer, ONE NCCL all-gather
+             (distributed.master_combine_sharded; blackbox.py:4908-4984); time = max over ranks,
+             compared bit for bit with the one-GPU combine of the same stack
+  link       measured pinned host<->device copy bandwidth of this rank-0 GPU (H2D alone, D2H
+             alone, both at once): the ceiling of every end-to-end number
   cpu_baseline  the CPU oracle (restatement of the reference's numpy/astropy/astroscrappy
              path) on a bounded sample, one frame-slice per host core (the reference's own
              one-process-per-frame scheme, blackbox.py:378)
@@ -75,6 +85,8 @@ def parse_args():
                     help='1: e2e with FITS data units on the host side (byte swaps on the device)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-masters', action='store_true', help='skip the sharded master-combine workloads')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling pass')
     ap.add_argument('--cpu-rows', type=int, default=0,
                     help='rows per channel of the CPU sample frame (full frame: 5280); 0 = 330 for the '
                          'cpu_baseline of the GPU arm, scaled to the step count for --impl reference')
@@ -278,7 +290,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def step():
         redo = 0
-        for res in batch.run(raws, out_imgs, out_masks):
+        for res in batch.run(raws, out_imgs, out_masks, fill_header=True):
             redo += res.redo
             spline_cols[0] += res.spline_columns
         return redo
@@ -329,6 +341,19 @@ def run_gpu(args, rank, world, local_rank):
                'h2d_bytes_per_step': world * B * raw_bytes,
                'd2h_bytes_per_step': world * B * (out_img.numel() * 4 + out_mask.numel())}
 
+    # ---- strong scaling: the night batch as one job of B frames in total -----------------------
+    strong = None
+    if not args.no_strong:
+        strong = measure_strong(args, batch, raws, out_imgs, out_masks, rank, world, dev, barrier)
+
+    # ---- sharded master combine (configs 5 and 2): row stripes + one all-gather ------------------
+    masters = None
+    if not args.no_masters:
+        del raws[2:]                       # the stacks need the room of the resident night batch
+        torch.cuda.empty_cache()
+        masters = measure_master_sharded(args, rank, world, dev, barrier)
+    link = measure_link(dev) if (rank == 0 and not args.no_e2e) else None
+
     if rank == 0:
         cpu = None
         if args.gpus == 1 and not args.no_cpu_baseline:
@@ -346,10 +371,175 @@ def run_gpu(args, rank, world, local_rank):
             'chain_hbm_frac': (ALGO_BYTES_CHAIN_4IT * frames / world / (ms_total * 1e-3)) / (peak_hbm()[0] * 1e9),
             'frames_redone': redo, 'host_spline_columns': spline_cols[0],
             'graph_replays': sum(p.graph_replays for p in batch.pipes),
+            'strong_scaling': strong, 'master_sharded': masters, 'link': link,
+            'header': 'fill_header=True in both timed paths: every header scalar (BIASM/RDN x16, BIASMEAN, '
+                      'RDNOISE, SATLEV x16, NOBJ-SAT, NCOSMICS, LAC-NIT, M-*NUM) arrives in one pinned copy per frame',
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_strong(args, batch, raws, out_imgs, out_masks, rank, world, dev, barrier):
+    """Config 4 as the reference runs it: ONE batch of `--batch` frames in total, frame k -> GPU
+    k mod N (pipeline.shard_frames), nothing exchanged.  Each rank reduces its share of its resident
+    frames; time = max over ranks of the device time of one whole job, mean of 3 jobs after one
+    warm-up job (pipeline fill and drain are inside, which is the point)."""
+    import torch
+    import torch.distributed as dist
+    from blackbox_b200.pipeline import shard_frames
+    mine = [raws[i] for i in range(len(shard_frames(args.batch, rank, world)))]
+
+    def job():
+        if mine:
+            batch.run(mine, out_imgs, out_masks)
+
+    job()
+    reps = 3
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        job()
+        barrier()                          # a job is over when its last rank is
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {'frames_total': args.batch, 'frames_per_gpu': len(mine), 'ms_per_job': ms,
+            'value': args.batch / (ms * 1e-3), 'unit': 'frames/s', 'scaling': 'strong',
+            'note': 'one job = the whole batch sharded frame k -> GPU k mod N; barrier after every job'}
+
+
+def measure_master_sharded(args, rank, world, dev, barrier):
+    """BASELINE.json config 5 (master bias of 50 2x2-binned 5280^2 frames) and config 2 (master flat
+    of 20 full 10560^2 frames) through distributed.master_combine_sharded: every rank holds its
+    row stripe of every frame, combines it with bbx_stack_median straight into its slot of the
+    gather buffer, one in-place NCCL all-gather assembles the master on every rank.  Rank 0 also
+    holds the whole stack and runs the one-GPU combine: the sharded master must equal it bit for
+    bit.  Times: CUDA events, 10 repetitions after 3 warm-ups, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from blackbox_b200 import distributed as D, reduce as R
+    peak = peak_hbm()[0]
+    out = {}
+    cases = (('bias50_5280', 'bias', 50, (5280, 5280), 5000), ('flat20_10560', 'flat', 20, (10560, 10560), 2000))
+    for name, imgtype, n, shape, seed0 in cases:
+        H, W = shape
+        r0, r1 = D.stripe_bounds(H, rank, world)
+        gen = torch.Generator(device=dev)
+        stripes, full = [], []
+        for i in range(n):
+            gen.manual_seed(seed0 + i)                       # the same frame on every rank
+            if imgtype == 'bias':
+                f = torch.randn(shape, device=dev, generator=gen) * 9.0
+            else:
+                f = (1.0 + 0.01 * torch.randn(shape, device=dev, generator=gen)) * (20000.0 * (0.8 + 0.4 * i / n))
+            stripes.append(f[r0:r1].clone())
+            if rank == 0 and world > 1:
+                full.append(f)
+            del f
+        medsec = [20000.0 * (0.8 + 0.4 * i / n) for i in range(n)] if imgtype == 'flat' else None
+        bpm = None
+        if imgtype == 'flat':
+            bpm = torch.zeros(shape, dtype=torch.uint8, device=dev)
+            bpm[:20] = 32
+            bpm[-20:] = 32
+            bpm[:, :20] = 32
+            bpm[:, -20:] = 32
+        gather = torch.empty((world * D.stripe_rows(H, world), W), dtype=torch.float32, device=dev)
+
+        def sharded():
+            return D.master_combine_sharded(stripes, shape, imgtype, medsec=medsec,
+                                            bpm_stripe=None if bpm is None else bpm[r0:r1], tel=TEL, out=gather)
+
+        def local_only():
+            R.master_combine(stripes, imgtype, medsec=medsec, bpm=None if bpm is None else bpm[r0:r1], tel=TEL,
+                             out=gather[rank * D.stripe_rows(H, world):rank * D.stripe_rows(H, world) + (r1 - r0)])
+
+        def timed(fn, reps=10, warm=3):
+            for _ in range(warm):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        ms = timed(sharded)
+        ms_kernel = timed(local_only)
+        master = sharded()
+        equal, ms_1gpu = None, ms
+        if world > 1:
+            flag = torch.ones(1, dtype=torch.int32, device=dev)
+            t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+            if rank == 0:
+                ref = torch.empty(shape, dtype=torch.float32, device=dev)
+                one = lambda: R.master_combine(full, imgtype, medsec=medsec, bpm=bpm, tel=TEL, out=ref)
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                t1[0] = e0.elapsed_time(e1) / 10
+                same = torch.equal(master.view(torch.int32), ref.view(torch.int32))
+                flag[0] = 1 if same else 0
+                del ref
+            dist.broadcast(flag, 0)
+            dist.broadcast(t1, 0)
+            equal, ms_1gpu = bool(flag.item()), float(t1.item())
+        nbytes = (n + 1) * H * W * 4 + (H * W if bpm is not None else 0)
+        out[name] = {'frames': n, 'shape': [H, W], 'imgtype': imgtype, 'rows_per_gpu': r1 - r0, 'ms': ms,
+                     'ms_stack_median_stripe': ms_kernel, 'allgather_ms': max(ms - ms_kernel, 0.0),
+                     'ms_1gpu': ms_1gpu, 'speedup_vs_1gpu': ms_1gpu / ms, 'equal_to_1gpu': equal,
+                     'algorithmic_bytes': nbytes, 'achieved_GBs': nbytes / (ms * 1e-3) / 1e9,
+                     'frac': nbytes / (ms * 1e-3) / 1e9 / (peak * world),
+                     'frac_note': 'of N x the measured HBM peak; the all-gather is inside the time'}
+        del stripes, full, gather, master, bpm
+        torch.cuda.empty_cache()
+    return out
+
+
+def measure_link(dev):
+    """Pinned host <-> device copy bandwidth of this GPU: H2D alone, D2H alone, both directions at
+    once (what BatchReducer.run_host does) -- the ceiling of the end-to-end number."""
+    import torch
+    n = 512 << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h, reps=4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * n / (time.perf_counter() - t0) / 1e9
+
+    run(True, True, 1)
+    both = run(True, True)
+    return {'h2d_GBs': run(True, False), 'd2h_GBs': run(False, True), 'both_each_GBs': both, 'unit': 'GB/s',
+            'note': 'pinned memory, 512 MiB copies; both_each = per direction with H2D and D2H running concurrently'}
 
 
 def pipe_launches(tel, niter):
@@ -357,8 +547,8 @@ def pipe_launches(tel, niter):
     cross-checked against the ncu launch list under profiles/): overscan 6 (+1 BlackGEM
     saturated-column count) + header means 1, fused apply 1, sparse mask morphology 11, LACosmic
     2 (begin) + 9 (first iteration) + 8 per further iteration, cosmic-ray bit + object count 3,
-    crosstalk 1."""
-    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1
+    crosstalk 1, per-bit mask counts 1."""
+    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1 + 1
 
 
 def peak_hbm():
@@ -444,7 +634,7 @@ def measure_e2e(args, batch, raws, red_shape, barrier):
     def run(nsteps):
         redo = 0
         for _ in range(nsteps):
-            for res in batch.run_host(host_raw, host_img, host_mask, fits=bool(args.fits)):
+            for res in batch.run_host(host_raw, host_img, host_mask, fits=bool(args.fits), fill_header=True):
                 redo += res.redo
         return redo
 

@@ -7,7 +7,9 @@
 
 #include "../../include/bbx.h"
 
-#define BBX_SM_COUNT 148
+// SM count of the current device (queried once per device, api.cu); grids are sized from it
+int bbx_sm_count(void);
+#define BBX_SM_COUNT bbx_sm_count()
 
 void bbx_set_error(const char *fmt, ...);
 

@@ -9,7 +9,7 @@
 #include "bbx_common.cuh"
 
 __global__ void __launch_bounds__(256)
-fits_swap16_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n16, unsigned int flip)
+fits_swap16_kernel(const uint4 *in, uint4 *out, size_t n16, unsigned int flip)
 {
     // 8 pixels per thread: swap the bytes of every 16-bit lane, then flip the sign bit (BZERO)
     const size_t n = n16 / 8;
@@ -30,7 +30,7 @@ fits_swap16_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t
 }
 
 __global__ void __launch_bounds__(256)
-fits_swap32_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n32)
+fits_swap32_kernel(const uint4 *in, uint4 *out, size_t n32)
 {
     const size_t n = n32 / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

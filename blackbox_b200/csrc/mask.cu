@@ -458,19 +458,40 @@ extern "C" int bbx_count_objects(const uint8_t *mask, int bit, int H, int W, int
 // --------------------------------------------------------------------------------------------
 // per-bit pixel counts
 // --------------------------------------------------------------------------------------------
+// 16 mask bytes per load; bit plane k of a 32-bit word is (w >> k) & 0x01010101, its population
+// count the number of pixels carrying bit k.  Counts stay in registers (int: < 2^31 bytes per
+// thread), one warp reduction and one atomic per warp and bit at the end.
 __global__ void __launch_bounds__(256)
 mask_counts_kernel(const uint8_t *__restrict__ mask, size_t n, unsigned long long *__restrict__ out)
 {
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)mask & 15)) & 15));     // bytes before 16-byte alignment
+    const size_t nvec = (n - head) / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(mask + head);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < nvec; i += nth) {
+        const uint4 q = ld_stream_u4(v + i);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t pl = 0x01010101u << k;
+            c[k] += __popc(q.x & pl) + __popc(q.y & pl) + __popc(q.z & pl) + __popc(q.w & pl);
+        }
+    }
+    // the unaligned head and the tail, byte by byte
+    for (size_t p = tid; p < head; p += nth) {
+        const uint32_t m = mask[p];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] += (m >> k) & 1;
+    }
+    for (size_t p = head + nvec * 16 + tid; p < n; p += nth) {
         const uint32_t m = mask[p];
 #pragma unroll
         for (int k = 0; k < 8; k++) c[k] += (m >> k) & 1;
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int v = warp_sum(c[k]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&out[k], (unsigned long long)v);
+        const int t = warp_sum(c[k]);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&out[k], (unsigned long long)t);
     }
 }
 
@@ -480,7 +501,7 @@ extern "C" int bbx_mask_counts(const uint8_t *mask, size_t n, unsigned long long
     cudaStream_t s = (cudaStream_t)stream;
     BBX_CUDA(cudaMemsetAsync(out_counts, 0, 8 * sizeof(unsigned long long), s));
     if (n == 0) return 0;
-    mask_counts_kernel<<<BBX_SM_COUNT * 8, 256, 0, s>>>(mask, n, out_counts);
+    mask_counts_kernel<<<BBX_SM_COUNT * 4, 256, 0, s>>>(mask, n, out_counts);
     BBX_CHECK_LAUNCH("mask_counts_kernel");
     return 0;
 }

@@ -16,7 +16,6 @@
 // shared memory (16 + 4 live doubles: ~64 registers, 6+ CTAs per SM hide the loads of the other
 // CTAs behind the FP64 work), and the tile goes back with 128-bit stores.
 // xtalk_kernel<PX>: generic fallback (any width / alignment), registers only.
-#include <stdlib.h>
 #include "bbx_common.cuh"
 
 struct XtalkCoef { double c[16][16]; };   // [victim][source] (the order the dot products walk), kernel parameter (constant bank)
@@ -184,14 +183,23 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
 extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                          const double *coeffs_h, const bbx_maskbits *bits, void *stream)
 {
+    return bbx_xtalk_variant(img, mask, H, W, ysize_chan, xsize_chan, coeffs_h, bits, 0, stream);
+}
+
+// variant 0: the kernel bbx_xtalk picks (tiled when the layout allows); 1 / 2 / 4: the generic
+// register-only kernel with that many pixels per thread and channel (parity tests, tools/xt_bench.py)
+extern "C" int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                 const double *coeffs_h, const bbx_maskbits *bits, int variant, void *stream)
+{
     BBX_REQUIRE(img && coeffs_h && bits, "bbx_xtalk: null argument");
+    BBX_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 4, "bbx_xtalk: variant %d", variant);
     BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_xtalk: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
     XtalkCoef k;
     for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[v][s] = coeffs_h[s * 16 + v];
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
     const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
-    if (px4 && getenv("BBX_XTALK_PX") == nullptr) {
+    if (px4 && variant == 0) {
         const long long ngroups = (long long)ysize_chan * (xsize_chan / 4);
         const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
         BBX_REQUIRE(ntiles < 2147483647LL, "bbx_xtalk: frame too large");
@@ -206,7 +214,8 @@ extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysiz
     // measured on B200 (10560^2, tools/xt_bench.py): 2 px/thread 0.395 ms, 4 px/thread 0.435 ms
     // (255 registers), 1 px/thread 0.76 ms
     int px = px2 ? 2 : 1;
-    if (const char *e = getenv("BBX_XTALK_PX")) { const int want_px = atoi(e); if (want_px == 4 && px4) px = 4; if (want_px == 1) px = 1; }
+    if (variant == 4 && px4) px = 4;
+    if (variant == 1 || (variant == 2 && !px2)) px = 1;
     const long long total = (long long)ysize_chan * (xsize_chan / px);
     long long want = (total + 127) / 128;
     const int blocks = (int)(want < BBX_SM_COUNT * 16 ? want : BBX_SM_COUNT * 16);

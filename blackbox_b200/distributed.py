@@ -29,15 +29,15 @@ def stripe_bounds(H, rank, world_size):
     return r0, min(r0 + n, H)
 
 
-def _default_combine(stripes, scales, flat_fix, bpm_stripe, tel):
+def _default_combine(stripes, scales, flat_fix, bpm_stripe, tel, out=None):
     from . import reduce as R
-    out, _ = R.master_combine(stripes, 'flat' if flat_fix else 'bias',
-                              medsec=scales if flat_fix else None, bpm=bpm_stripe, tel=tel)
-    return out
+    res, _ = R.master_combine(stripes, 'flat' if flat_fix else 'bias',
+                              medsec=scales if flat_fix else None, bpm=bpm_stripe, tel=tel, out=out)
+    return res
 
 
 def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stripe=None, tel=None,
-                           group=None, combine=None):
+                           group=None, combine=None, out=None):
     """Row-stripe sharded master combine.
 
     stripes     this rank's row stripe of each of the N frames: float32 [r1-r0, W] tensors
@@ -47,9 +47,11 @@ def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stri
                 required here because a frame's normalisation section spans several stripes
     bpm_stripe  flats: this rank's rows of the bad-pixel mask (edge pixels -> 1)
     combine     test hook: callable(stripes, scales, flat_fix, bpm_stripe, tel) -> stripe master
+    out         optional float32 [world * stripe_rows(H, world), W] gather buffer to reuse
 
-    Returns the full (H, W) master on every rank.
-    """
+    Returns the full (H, W) master on every rank (a view of the gather buffer).  The stack-median
+    kernel writes this rank's stripe straight into its slot of the gather buffer and the
+    all-gather runs in place on it: no staging copy, no zero fill."""
     H, W = shape
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -63,23 +65,25 @@ def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stri
     flat = imgtype == 'flat'
     if flat and medsec is None:
         raise ValueError('sharded flat combine needs the MEDSEC normalisation medians')
-    fn = combine if combine is not None else _default_combine
     dev = stripes[0].device
+    if out is None:
+        out = torch.empty((world * nrows, W), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (world * nrows, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError('gather buffer must be a contiguous float32 tensor of shape {}'.format((world * nrows, W)))
+    slot = out[rank * nrows:(rank + 1) * nrows]            # this rank's contribution (last rows may be padding)
     if r1 > r0:
-        mine = fn(stripes, medsec, flat, bpm_stripe, tel)
-        if not isinstance(mine, torch.Tensor):
-            mine = torch.from_numpy(np.ascontiguousarray(mine))
-        mine = mine.to(dev)
-    else:
-        mine = torch.empty((0, W), dtype=torch.float32, device=dev)
-    if world == 1:
-        return mine
-    # equal-sized contributions for the single all-gather: pad the last stripe
-    padded = torch.zeros((nrows, W), dtype=torch.float32, device=dev)
-    padded[:r1 - r0] = mine
-    full = torch.empty((world * nrows, W), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(full, padded, group=group)
-    return full[:H]
+        mine = slot[:r1 - r0]
+        if combine is not None:
+            res = combine(stripes, medsec, flat, bpm_stripe, tel)
+            if not isinstance(res, torch.Tensor):
+                res = torch.from_numpy(np.ascontiguousarray(res))
+            mine.copy_(res)
+        else:
+            _default_combine(stripes, medsec, flat, bpm_stripe, tel, out=mine)
+    if world > 1:
+        # in place: the input is this rank's slot of the output (what NCCL calls an in-place all-gather)
+        dist.all_gather_into_tensor(out, slot, group=group)
+    return out[:H]
 
 
 def flat_scale_from_region(frames_full, tel=None):

@@ -33,6 +33,16 @@ class FitsError(ValueError):
     pass
 
 
+def already_exists(filename, get_filename=False):
+    """blackbox.py:787-807: is ``filename`` there, possibly fpacked / gzipped (or the other way
+    round)?  With ``get_filename`` -> (exists, name of the file found)."""
+    cands = [filename, filename + '.fz', filename + '.gz', filename.replace('.fz', ''), filename.replace('.gz', '')]
+    for c in dict.fromkeys(cands):
+        if os.path.isfile(c):
+            return (True, c) if get_filename else True
+    return (False, filename) if get_filename else False
+
+
 def _parse_value(text):
     t = text.strip()
     if not t:
@@ -319,7 +329,7 @@ def write_primary(path, data, header=None, be_bytes=False, shape=None, bitpix=No
     stored as int16 with BZERO 32768), or with ``be_bytes`` a buffer (numpy uint8 array / pinned
     torch tensor) that already holds the big-endian data unit of an image of ``shape`` and
     ``bitpix`` (``reduce.fits_encode``; ``bzero=32768`` for encoded uint16 counts).  The file is
-    written to a temporary name and renamed."""
+    written to a temporary name (one no ``*.fits*`` listing can pick up) and renamed."""
     if be_bytes:
         if shape is None or bitpix not in _DTYPES:
             raise FitsError('be_bytes needs shape and bitpix')
@@ -343,7 +353,8 @@ def write_primary(path, data, header=None, be_bytes=False, shape=None, bitpix=No
             bitpix = table[a.dtype.newbyteorder('=')]
             a = a.astype(_DTYPES[bitpix], copy=False)
         raw = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
-    tmp = '{}.tmp{}'.format(path, os.getpid())
+    tmp = os.path.join(os.path.dirname(path) or '.', '.{}.{}.part'.format(
+        os.path.basename(path).replace('.fits', '_fits'), os.getpid()))
     with open(tmp, 'wb') as fh:
         fh.write(build_header(shape, bitpix, header, bzero=bzero))
         fh.write(raw.tobytes() if not raw.flags['C_CONTIGUOUS'] else memoryview(raw))

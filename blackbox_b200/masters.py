@@ -73,13 +73,7 @@ def mjd2date(mjd):
     return (_MJD0 + datetime.timedelta(days=float(mjd))).strftime('%Y/%m/%d')
 
 
-def already_exists(filename, get_filename=False):
-    """blackbox.py:787-807."""
-    cands = [filename, filename + '.fz', filename + '.gz', filename.replace('.fz', ''), filename.replace('.gz', '')]
-    for c in dict.fromkeys(cands):
-        if os.path.isfile(c):
-            return (True, c) if get_filename else True
-    return (False, filename) if get_filename else False
+already_exists = fitsio.already_exists          # blackbox.py:787-807
 
 
 def list_files(path, search_str='', end_str='', start_str=None, recursive=False):

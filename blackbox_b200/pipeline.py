@@ -73,23 +73,26 @@ class FramePipeline:
         self.count_objects = count_objects
         RH, RW = self.geom.red_shape
         dev = self.device
-        self.st = R.OverscanState(self.geom, dev)
-        self.mwork = R.MaskWork(RH, RW, dev)
-        self.lwork = R.LacosmicWork(RH, RW, self.niter, dev)
+        # every scalar that ends up in a header lives in the header block of the overscan state
+        # and reaches the host in ONE pinned copy at the end of stage B (see finish)
+        self.st = R.OverscanState(self.geom, dev, niter=self.niter)
+        self.mwork = R.MaskWork(RH, RW, dev, status=self.st.mstatus, nobj=self.st.nobj)
+        self.lwork = R.LacosmicWork(RH, RW, self.niter, dev, info=self.st.lacinfo)
         self.crmask = torch.empty((RH, RW), dtype=torch.uint8, device=dev)
-        self.means = torch.zeros(2, dtype=torch.float64, device=dev)      # BIASMEAN, RDNOISE
-        self.ncosmic = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.st._pinned = torch.empty(self.st._host_bytes, dtype=torch.uint8).pin_memory()
+        self.st._pinned_hdr = torch.empty(self.st._hdr_bytes, dtype=torch.uint8).pin_memory()
+        self.means = self.st.means                                        # BIASMEAN, RDNOISE
+        self.ncosmic = self.st.ncosmic
         # optional last step of blackbox_reduce (blackbox.py:1958-1974): edge pixels -> channel median
         self.fill_edge = bool(fill_edge)
         self.chan_med = torch.zeros(self.geom.nchans, dtype=torch.float32, device=dev)
         self._cm_work = (torch.empty(R.query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=dev)
                          if self.fill_edge else None)
-        # pinned status words of stage B: [0:4] mask morphology (int32), [8:16] LACosmic (int64)
-        self._status_host = torch.zeros(16, dtype=torch.uint8).pin_memory()
         self._ev_a = torch.cuda.Event()
         self._ev_b = torch.cuda.Event()
         self._raw = None
         self._out = None
+        self._exptime = self.exptime
         self._spline_cols = 0
         self.stage_events = None       # dict stage -> [(start, end) CUDA events] when timing is on
         self.use_graphs = bool(use_graphs)
@@ -194,8 +197,6 @@ class FramePipeline:
             call('bbx_header_means', R._ptr(st.biasm), R._ptr(st.std_vos), R._ptr(self.means), R._stream())
             st.fetch_async()
 
-        if st._pinned is None:
-            st._pinned = torch.empty(st._host_bytes, dtype=torch.uint8).pin_memory()
         self._run('overscan', raw_t.data_ptr(), body)
         self._ev_a.record()
 
@@ -254,9 +255,11 @@ class FramePipeline:
                 R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
 
         def status():
-            self._status_host[0:4].copy_(self.mwork.status.view(torch.uint8)[0:4], non_blocking=True)
-            if self.niter > 0:
-                self._status_host[8:16].copy_(self.lwork.info.view(torch.uint8)[16:24], non_blocking=True)
+            # the mask is final here (cosmic-ray bit set): per-bit pixel counts for mask_header,
+            # then the whole header block -- os_corr keywords, SATLEV, NOBJ-SAT, NCOSMICS, the
+            # status words of the morphology and of LACosmic -- in one copy into pinned memory
+            call('bbx_mask_counts', R._ptr(out_mask), out_mask.numel(), R._ptr(self.st.mcounts), R._stream())
+            self.st.fetch_header_async()
 
         if self.coeffs is not None:
             run('xtalk', tail)
@@ -270,17 +273,19 @@ class FramePipeline:
             run('edge_fill', edge)
         run('status', status)
 
-    def stage_b_enqueue(self, raw_t, out_img, out_mask):
+    def stage_b_enqueue(self, raw_t, out_img, out_mask, exptime=None):
         """Stage B on the current stream (which must be ordered after stage A and the spline
         patch): everything from the fused per-pixel pass to the crosstalk correction, then the
-        status words into pinned memory."""
+        header block into pinned memory.  ``exptime``: the frame's EXPTIME [s] (NCOSMICS is a rate,
+        blackbox.py:4354-4361); default: the pipeline's constructor value."""
         self._check_frame(raw_t, out_img, out_mask)
         self._rest(raw_t, out_img, out_mask)
         self._ev_b.record()
         self._raw, self._out = raw_t, (out_img, out_mask)
+        self._exptime = self.exptime if exptime is None else float(exptime)
         return out_img, out_mask
 
-    def enqueue(self, raw_t, out_img=None, out_mask=None):
+    def enqueue(self, raw_t, out_img=None, out_mask=None, exptime=None):
         """Run the overscan stage and enqueue the rest of the chain for one raw frame (uint16
         or float32 CUDA tensor).  Returns the output tensors (valid after ``finish``)."""
         RH, RW = self.geom.red_shape
@@ -289,19 +294,19 @@ class FramePipeline:
         if out_mask is None:
             out_mask = torch.empty((RH, RW), dtype=torch.uint8, device=self.device)
         self._overscan(raw_t)
-        return self.stage_b_enqueue(raw_t, out_img, out_mask)
+        return self.stage_b_enqueue(raw_t, out_img, out_mask, exptime=exptime)
 
     # ---------------------------------------------------------------------------------------
     def finish(self, fill_header=True):
         """Wait for stage B of the last enqueued frame, verify its device status and return its
-        FrameResult."""
+        FrameResult.  Everything read here comes out of the pinned header block that stage B
+        copied: no further device synchronisation, no ``.item()``."""
         st = self.st
         out_img, out_mask = self._out
         redo = False
         self._ev_b.synchronize()
-        sh = self._status_host.numpy()
-        morph_bad = int(sh[0:4].view(np.int32)[0]) != 0
-        lac_status = int(sh[8:16].view(np.int64)[0]) if self.niter > 0 else 0
+        morph_bad = int(st.hhost('mstatus')[0]) != 0
+        lac_status = int(st.hhost('lacinfo')[2]) if self.niter > 0 else 0
         if morph_bad or lac_status != 0:
             # the sparse mask morphology overflowed / did not converge (the mask LACosmic saw was
             # not final) or the lazy LACosmic needs the background level / its dense twin: redo
@@ -310,24 +315,24 @@ class FramePipeline:
             self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad,
                        lac_mode=R.lac_retry_mode(lac_status) if lac_status != 0 else R.LAC_LAZY)
             torch.cuda.current_stream().synchronize()
-            if self.niter > 0 and int(self.lwork.info[2].item()) != 0:
+            if self.niter > 0 and int(st.hhost('lacinfo')[2]) != 0:
                 self._rest(self._raw, out_img, out_mask, dense_morph=morph_bad, lac_mode=R.LAC_DENSE)
                 torch.cuda.current_stream().synchronize()
         header, header_mask = {}, {}
         if fill_header:
-            R.fill_os_header(header, st)
-            nobj = int(self.mwork.nobj.item())
+            R.fill_os_header(header, st, fetched=True)
+            nobj = int(st.hhost('nobj')[0])
             header['NOBJ-SAT'] = header_mask['NOBJ-SAT'] = nobj
-            sat = st.satlevel.cpu().numpy()
+            sat = st.hhost('satlevel')
             header['SATURATE'] = header_mask['SATURATE'] = float(np.mean(sat))
             for i in range(self.geom.nchans):
                 header['SATLEV{}'.format(i + 1)] = header_mask['SATLEV{}'.format(i + 1)] = round(float(sat[i]), 1)
             if self.niter > 0:
-                nc = int(self.ncosmic.item()) / self.exptime
+                nc = int(st.hhost('ncosmic')[0]) / self._exptime
                 header['NCOSMICS'] = header_mask['NCOSMICS'] = nc
-                info = self.lwork.info.cpu().numpy()
-                header['LAC-NIT'] = int(info[0])
-            R.mask_header(out_mask, header_mask, tel_=self.tel)      # M-*NUM pixel counts, blackbox.py:4601-4620
+                header['LAC-NIT'] = int(st.hhost('lacinfo')[0])
+            # M-*NUM pixel counts, blackbox.py:4601-4620
+            R.mask_header(None, header_mask, tel_=self.tel, counts=st.hhost('mcounts'))
         return FrameResult(out_img, out_mask, header, header_mask, self._spline_cols, redo)
 
     # ---------------------------------------------------------------------------------------
@@ -370,11 +375,14 @@ class BatchReducer:
         self.hi_streams = ([torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
                            if split_priority else self.streams)
 
-    def run(self, raws, out_imgs, out_masks, fill_header=False):
+    def run(self, raws, out_imgs, out_masks, fill_header=True, exptimes=None):
         """raws: CUDA tensors; out_imgs / out_masks: at least ``depth`` output tensors, frame k
-        is written to index k % len(out_imgs).  Returns the FrameResults in order (a frame's
-        output buffers are only valid until they are reused)."""
+        is written to index k % len(out_imgs).  ``exptimes``: EXPTIME [s] of every frame (NCOSMICS
+        is a rate per second).  Returns the FrameResults in order (a frame's output buffers are
+        only valid until they are reused)."""
         n, d = len(raws), self.depth
+        if exptimes is not None and len(exptimes) != n:
+            raise ValueError('{} exposure times for {} frames'.format(len(exptimes), n))
         nout = len(out_imgs)
         if nout < d or len(out_masks) != nout:
             raise ValueError('need at least depth={} output buffers'.format(d))
@@ -403,7 +411,8 @@ class BatchReducer:
                 self.pipes[j].stage_a_resolve()
             with torch.cuda.stream(self.streams[j]):
                 self.streams[j].wait_stream(self.hi_streams[j])
-                self.pipes[j].stage_b_enqueue(raws[k], out_imgs[k % nout], out_masks[k % nout])
+                self.pipes[j].stage_b_enqueue(raws[k], out_imgs[k % nout], out_masks[k % nout],
+                                              exptime=None if exptimes is None else exptimes[k])
         for k in range(max(n - d, 0), n):
             j = k % d
             with torch.cuda.stream(self.streams[j]):
@@ -413,7 +422,7 @@ class BatchReducer:
         return results
 
     # ---------------------------------------------------------------------------------------
-    def run_host(self, host_raws, host_imgs, host_masks, fill_header=False, fits=False):
+    def run_host(self, host_raws, host_imgs, host_masks, fill_header=True, fits=False, exptimes=None):
         """The same batch with HOST buffers on both sides: ``host_raws`` pinned uint16 (or
         float32) raw frames, ``host_imgs`` / ``host_masks`` pinned float32 / uint8 outputs (rings:
         frame k goes to index k % len; a ring slot must have been consumed by the caller before
@@ -431,8 +440,15 @@ class BatchReducer:
             return []
         dev = self.pipes[0].device
         RH, RW = self.pipes[0].geom.red_shape
-        if getattr(self, '_hbuf', None) is None or self._hbuf[0][0].dtype != host_raws[0].dtype:
-            self._hbuf = [(torch.empty(tuple(host_raws[0].shape), dtype=host_raws[0].dtype, device=dev),
+        if exptimes is not None and len(exptimes) != n:
+            raise ValueError('{} exposure times for {} frames'.format(len(exptimes), n))
+        # device-side raw buffers: 2-byte host frames of any dtype (a FITS data unit read as int16,
+        # say) are bytes to the copy engine and uint16 counts to the kernels
+        raw_dt = torch.float32 if host_raws[0].dtype == torch.float32 else torch.uint16
+        if host_raws[0].element_size() != (4 if raw_dt == torch.float32 else 2):
+            raise TypeError('host raw frames must be 2-byte counts or float32, got {}'.format(host_raws[0].dtype))
+        if getattr(self, '_hbuf', None) is None or self._hbuf[0][0].dtype != raw_dt:
+            self._hbuf = [(torch.empty(tuple(host_raws[0].shape), dtype=raw_dt, device=dev),
                            torch.empty((RH, RW), dtype=torch.float32, device=dev),
                            torch.empty((RH, RW), dtype=torch.uint8, device=dev)) for _ in range(d)]
             self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -471,7 +487,8 @@ class BatchReducer:
                 retire(k - d)
             with torch.cuda.stream(self._s_in):
                 self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
-                self._hbuf[j][0].copy_(host_raws[k], non_blocking=True)
+                src = host_raws[k]
+                self._hbuf[j][0].copy_(src if src.dtype == raw_dt else src.view(raw_dt), non_blocking=True)
                 if fits:
                     raw = self._hbuf[j][0]
                     call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
@@ -492,7 +509,7 @@ class BatchReducer:
             with torch.cuda.stream(self.streams[j]):
                 self.streams[j].wait_stream(self.hi_streams[j])
                 self.streams[j].wait_event(self._ev_out[j])          # outputs of frame k-d copied out
-                self.pipes[j].stage_b_enqueue(*self._hbuf[j])
+                self.pipes[j].stage_b_enqueue(*self._hbuf[j], exptime=None if exptimes is None else exptimes[k])
                 self._ev_done[j].record()
             copy_out(k)
         for k in range(max(n - d, 0), n):

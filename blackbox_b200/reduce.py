@@ -19,18 +19,22 @@ All arithmetic happens in libbbx.so (hand-written sm_100a kernels, include/bbx.h
 no CPU fallback.  The only host numerics are FITPACK's smoothing spline (hostfit.py).
 """
 import ctypes as C
+import logging
+import os
 
 import numpy as np
 import torch
 
-from . import _lib, hostfit, set_bb
+from . import _lib, fitsio, hostfit, set_bb
 from ._lib import BbxMaskBits, call, query
 from .geometry import Geometry, define_sections  # noqa: F401  (define_sections: part of the mirrored surface)
 from .set_bb import get_par
 
 tel = None          # module-global telescope name, as in the reference (blackbox.py:141)
+log = logging.getLogger(__name__)
 
 _bpm_registry = {}  # filter -> bad-pixel mask (numpy or CUDA tensor); see set_bad_pixel_mask
+_bpm_cache = {}     # path -> (mtime, size, uint8 CUDA tensor) of the masks mask_init read from disk
 
 MASK_MORPH_SPARSE = True   # mask_init: seed-list driven morphology (False: dense passes; same result)
 
@@ -83,11 +87,25 @@ def _set(header, key, value, comment=None):
 
 
 def _raw_type(t):
-    if t.dtype == torch.uint16 or t.dtype == torch.int16:
+    if t.dtype == torch.uint16:
         return 0
     if t.dtype == torch.float32:
         return 1
-    raise TypeError('raw frame must be uint16 or float32, got {}'.format(t.dtype))
+    # int16 is what a BZERO = 0 frame decodes to: its negative counts must not be read as 32768+
+    raise TypeError('raw frame must be uint16 (counts) or float32, got {}'.format(t.dtype))
+
+
+def _inplace_target(a, dtype, who):
+    """The tensor an in-place entry point works on: numpy arrays are copied to the device (and
+    copied back by the caller); a torch tensor must already BE the thing to modify -- a CUDA,
+    contiguous tensor of ``dtype`` -- because a silent copy would swallow the result."""
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda or not a.is_contiguous() or a.dtype != dtype:
+            raise TypeError('{}: works in place and needs a contiguous CUDA {} tensor (got {} on {}, '
+                            'contiguous={}); pass a numpy array or convert first'.format(
+                                who, dtype, a.dtype, a.device, a.is_contiguous()))
+        return a
+    return _to_dev(a, dtype)
 
 
 def _bits(tel_):
@@ -105,9 +123,9 @@ def gain_corr(data, header, tel=None):
     """In place ``data[chan] *= gain[chan]``; header GAIN1..16 (blackbox.py:7442-7465)."""
     gain = get_par(set_bb.gain, tel)
     is_np = isinstance(data, np.ndarray)
-    t = _to_dev(data)
-    if t.dtype != torch.float32:
+    if is_np and data.dtype != np.float32:
         raise TypeError('gain_corr expects a float32 frame (as read_hdulist(dtype="float32"))')
+    t = _inplace_target(data, torch.float32, 'gain_corr')
     geom = Geometry.from_raw_shape(tuple(t.shape), tel=tel) if _has_overscan(t.shape, tel) \
         else _reduced_geometry(tuple(t.shape), tel)
     g = geom.as_struct()
@@ -139,36 +157,52 @@ def _reduced_geometry(shape, tel_):
 # overscan
 # -------------------------------------------------------------------------------------------
 class OverscanState:
-    """Device-resident intermediates of the overscan correction of one frame.
+    """Device-resident intermediates and header scalars of one frame.
 
-    Every field is a view into ONE device buffer; the fields the host needs for the spline
-    decision (``HOST_FIELDS``: they sit at the front of the buffer) travel in a single
-    device-to-host copy into a pinned mirror (``fetch_async`` / ``host``)."""
+    Every field is a view into ONE device buffer.  The fields the host needs for the spline
+    decision (``HOST_FIELDS``, at the front of the buffer) travel in a single device-to-host copy
+    into a pinned mirror right after the overscan stage (``fetch_async`` / ``host``); every
+    scalar that ends up in the FITS header (``HEADER_FIELDS``, at the end of the buffer: the
+    os_corr keywords, the saturation levels, NOBJ-SAT, NCOSMICS, the LACosmic and morphology
+    status words, the per-bit mask counts) travels in ONE copy at the end of the chain
+    (``fetch_header_async`` / ``hhost``) -- no ``.item()`` anywhere on the frame path."""
 
     HOST_FIELDS = ('fit_status', 'need_spline', 'hos_n', 'hos_mean', 'hos_std', 'oscan')
+    HEADER_FIELDS = ('vos_coef', 'biasm', 'vfit_ok', 'std_vos', 'satlevel', 'means', 'mstatus', 'nobj',
+                     'ncosmic', 'lacinfo', 'mcounts')
 
-    def __init__(self, geom, device):
+    def __init__(self, geom, device, niter=4):
         n, dy, nc = geom.nchans, geom.dy, geom.xsize_chan
-        f64, f32, i32, u8 = torch.float64, torch.float32, torch.int32, torch.uint8
+        f64, f32, i32, i64, u8 = torch.float64, torch.float32, torch.int32, torch.int64, torch.uint8
         fields = [('fit_status', (n,), i32), ('need_spline', (n, nc), u8), ('hos_n', (n, nc), i32),
                   ('hos_mean', (n, nc), f32), ('hos_std', (n, nc), f32), ('oscan', (n, nc), f64),
-                  ('mean_vos', (n, dy), f64), ('vos_fit', (n, dy), f64), ('vos_coef', (n, 8), f64),
-                  ('biasm', (n,), f64), ('vfit_ok', (n,), i32), ('satcnt', (n, 2, nc), i32),
-                  ('dlevel', (n,), f64), ('satcol', (n, nc), u8), ('std_vos', (n,), f64),
-                  ('satlevel', (n,), f64)]
+                  ('mean_vos', (n, dy), f64), ('vos_fit', (n, dy), f64), ('satcnt', (n, 2, nc), i32),
+                  ('dlevel', (n,), f64), ('satcol', (n, nc), u8),
+                  # ---- header block (HEADER_FIELDS, contiguous) ----
+                  ('vos_coef', (n, 8), f64), ('biasm', (n,), f64), ('vfit_ok', (n,), i32),
+                  ('std_vos', (n,), f64), ('satlevel', (n,), f64),
+                  ('means', (2,), f64),                       # BIASMEAN, RDNOISE
+                  ('mstatus', (2,), i32),                     # mask morphology status (bbx_mask_morph_sparse)
+                  ('nobj', (1,), i32), ('ncosmic', (1,), i32),
+                  ('lacinfo', (4 + max(int(niter), 1),), i64),   # bbx_lacosmic out_info
+                  ('mcounts', (8,), i64)]                     # pixels per mask bit (mask_header)
         self.geom = geom
         self._layout = {}
         off = 0
         for name, shape, dt in fields:
+            if name == self.HEADER_FIELDS[0]:
+                self._hdr_off = off
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
             self._layout[name] = (off, nbytes, shape, dt)
             off = (off + nbytes + 15) // 16 * 16
             if name == self.HOST_FIELDS[-1]:
                 self._host_bytes = off
+        self._hdr_bytes = off - self._hdr_off
         self.buf = torch.zeros(off, dtype=u8, device=device)
         for name, (o, nb, shape, dt) in self._layout.items():
             setattr(self, name, self.buf[o:o + nb].view(dt).view(shape))
         self._pinned = None
+        self._pinned_hdr = None
 
     def fetch_async(self):
         """Enqueue the copy of the host-side fields into the pinned mirror (current stream)."""
@@ -181,6 +215,19 @@ class OverscanState:
         ran ``fetch_async`` has been synchronised)."""
         o, nb, shape, dt = self._layout[name]
         return self._pinned[o:o + nb].view(dt).view(shape).numpy()
+
+    def fetch_header_async(self):
+        """Enqueue the copy of the header block into its pinned mirror (current stream)."""
+        if self._pinned_hdr is None:
+            self._pinned_hdr = torch.empty(self._hdr_bytes, dtype=torch.uint8).pin_memory()
+        self._pinned_hdr.copy_(self.buf[self._hdr_off:self._hdr_off + self._hdr_bytes], non_blocking=True)
+
+    def hhost(self, name):
+        """numpy view of a HEADER_FIELDS member in the pinned header mirror (valid once the stream
+        that ran ``fetch_header_async`` has been synchronised)."""
+        o, nb, shape, dt = self._layout[name]
+        o -= self._hdr_off
+        return self._pinned_hdr[o:o + nb].view(dt).view(shape).numpy()
 
 
 def overscan_enqueue(raw_t, geom, tel_, gain=None, data_limit=2000, state=None):
@@ -296,12 +343,15 @@ def os_corr(data, header, imgtype, xbin=1, ybin=1, data_limit=2000, tel=None, st
     return out.cpu().numpy() if is_np else out
 
 
-def fill_os_header(header, st):
-    """Header keywords of os_corr from the device state (synchronises)."""
-    coef = st.vos_coef.cpu().numpy()
-    ok = st.vfit_ok.cpu().numpy()
-    biasm = st.biasm.cpu().numpy()
-    rdn = st.std_vos.cpu().numpy()
+def fill_os_header(header, st, fetched=False):
+    """Header keywords of os_corr from the state's header block.  Unless ``fetched`` (the caller
+    has run ``st.fetch_header_async()`` and synchronised that stream) this enqueues the copy and
+    synchronises the current stream."""
+    if not fetched:
+        st.fetch_header_async()
+        torch.cuda.current_stream().synchronize()
+    coef, ok = st.hhost('vos_coef'), st.hhost('vfit_ok')
+    biasm, rdn = st.hhost('biasm'), st.hhost('std_vos')
     deg = int(set_bb.voscan_poldeg)
     n = st.geom.nchans
     for i in range(n):
@@ -336,7 +386,7 @@ def divide_mflat(data, data_mflat):
 
 def _binary_inplace(a, b, op):
     is_np = isinstance(a, np.ndarray)
-    ta, tb = _to_dev(a, torch.float32), _to_dev(b, torch.float32)
+    ta, tb = _inplace_target(a, torch.float32, 'subtract_mbias / divide_mflat'), _to_dev(b, torch.float32)
     if ta.shape != tb.shape:
         raise ValueError('shape mismatch {} vs {}'.format(tuple(ta.shape), tuple(tb.shape)))
     call('bbx_binary_inplace', _ptr(ta), _ptr(tb), ta.numel(), op, _stream())
@@ -361,16 +411,18 @@ def set_bad_pixel_mask(filt, bpm):
 class MaskWork:
     """Scratch buffers of the mask morphology for one frame shape (reusable)."""
 
-    def __init__(self, H, W, device):
+    def __init__(self, H, W, device, status=None, nobj=None):
+        """``status`` (int32[2]) / ``nobj`` (int32[1]): device tensors to use for the status words
+        and NOBJ-SAT (FramePipeline points them into the frame's header block)."""
         self.H, self.W = H, W
         self.holes = torch.empty(query('bbx_fill_holes_work_bytes', H, W), dtype=torch.uint8, device=device)
         self.labels = torch.empty(H * W, dtype=torch.int32, device=device)
         self.unconverged = torch.zeros(1, dtype=torch.int32, device=device)
-        self.nobj = torch.zeros(1, dtype=torch.int32, device=device)
+        self.nobj = nobj if nobj is not None else torch.zeros(1, dtype=torch.int32, device=device)
         self.seed_cap = H * W // 8 + 1024
         self.seeds = torch.empty(self.seed_cap, dtype=torch.int32, device=device)
         self.seed_count = torch.zeros(1, dtype=torch.int32, device=device)
-        self.status = torch.zeros(2, dtype=torch.int32, device=device)
+        self.status = status if status is not None else torch.zeros(2, dtype=torch.int32, device=device)
 
 
 def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=4096, sparse=True):
@@ -407,17 +459,44 @@ def mask_morph_finish(mask_t, tel_, work, rounds=1024, sparse=True):
     return int(work.nobj.item()), True
 
 
+def _load_bpm(filt, shape, device):
+    """The bad-pixel mask of filter ``filt`` as mask_init finds it (blackbox.py:4386-4398):
+    ``set_bb.bad_pixel_mask`` with 'bpm' -> 'bpm_<filt>', fpacked or not (``already_exists``); a
+    mask registered with ``set_bad_pixel_mask`` takes precedence.  A missing file is a logged
+    warning and a mask of zeros, as in the reference -- never silent.  Files are read once and
+    kept on the device until they change on disk."""
+    if filt in _bpm_registry:
+        return _to_dev(_bpm_registry[filt], torch.uint8)
+    name = get_par(set_bb.bad_pixel_mask, tel)
+    if not isinstance(name, str):
+        log.warning('no bad pixel mask configured for telescope %s (set_bb.bad_pixel_mask)', tel)
+        return None
+    fits_bpm = name.replace('bpm', 'bpm_{}'.format(filt))
+    present, fits_bpm = fitsio.already_exists(fits_bpm, get_filename=True)
+    if not present:
+        log.warning('bad pixel mask %s does not exist', fits_bpm)
+        return None
+    stat = os.stat(fits_bpm)
+    hit = _bpm_cache.get(fits_bpm)
+    if hit is not None and hit[0] == stat.st_mtime_ns and hit[1] == stat.st_size and hit[2].device == device:
+        return hit[2]
+    _, bpm_t = read_fits_image(fits_bpm, dtype=torch.uint8)
+    log.info('using bad pixel mask %s', fits_bpm)
+    _bpm_cache[fits_bpm] = (stat.st_mtime_ns, stat.st_size, bpm_t)
+    return bpm_t
+
+
 def mask_init(data, header, filt, imgtype, bpm=None):
     """Initial mask from the bad-pixel mask, non-finite pixels, per-channel saturation,
     crosstalk victims, saturated-connected pixels and filled holes
     (blackbox.py:4375-4579, 4584-4596).  Returns (uint8 mask, header_mask dict); ``data``
-    has its non-finite pixels zeroed in place.  Uses the module-global ``tel``."""
+    has its non-finite pixels zeroed in place.  Uses the module-global ``tel``.  The bad-pixel
+    mask is read from ``set_bb.bad_pixel_mask`` as the reference does (see ``_load_bpm``) unless
+    ``bpm`` is given."""
     is_np = isinstance(data, np.ndarray)
-    t = _to_dev(data, torch.float32)
+    t = _inplace_target(data, torch.float32, 'mask_init')
     H, W = t.shape
-    if bpm is None:
-        bpm = _bpm_registry.get(filt)
-    bpm_t = _to_dev(bpm, torch.uint8)
+    bpm_t = _to_dev(bpm, torch.uint8) if bpm is not None else _load_bpm(filt, (H, W), t.device)
     if bpm_t is not None and tuple(bpm_t.shape) != (H, W):
         raise ValueError('bad pixel mask shape {} does not match data {}'.format(tuple(bpm_t.shape), (H, W)))
     header_mask = {}
@@ -470,13 +549,16 @@ def _apply_seed(t, geom, satlevel_t, bpm_t, out_img, work):
     return out_mask
 
 
-def mask_header(data_mask, header_mask, tel_=None):
+def mask_header(data_mask, header_mask, tel_=None, counts=None):
     """Per-type pixel counts M-*NUM etc. (blackbox.py:4601-4620).  ``tel_``: telescope name
-    (default: the module-global ``tel``, as in the reference)."""
-    t = _to_dev(data_mask, torch.uint8)
-    counts = torch.zeros(8, dtype=torch.int64, device=t.device)
-    call('bbx_mask_counts', _ptr(t), t.numel(), _ptr(counts), _stream())
-    counts = counts.cpu().numpy()
+    (default: the module-global ``tel``, as in the reference).  ``counts``: the eight per-bit pixel
+    counts if they are already on the host (FramePipeline takes them from the header block);
+    otherwise they are counted here (one pass over the mask, synchronises)."""
+    if counts is None:
+        t = _to_dev(data_mask, torch.uint8)
+        dev_counts = torch.zeros(8, dtype=torch.int64, device=t.device)
+        call('bbx_mask_counts', _ptr(t), t.numel(), _ptr(dev_counts), _stream())
+        counts = dev_counts.cpu().numpy()
     text = {'bad': 'BP', 'edge': 'EP', 'saturated': 'SP', 'saturated-connected': 'SCP',
             'satellite trail': 'STP', 'cosmic ray': 'CRP'}
     mv = get_par(set_bb.mask_value, tel if tel_ is None else tel_)
@@ -492,9 +574,9 @@ def mask_header(data_mask, header_mask, tel_=None):
 # cosmic rays
 # -------------------------------------------------------------------------------------------
 class LacosmicWork:
-    def __init__(self, H, W, niter, device):
+    def __init__(self, H, W, niter, device, info=None):
         self.buf = torch.empty(query('bbx_lacosmic_work_bytes', H, W), dtype=torch.uint8, device=device)
-        self.info = torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
+        self.info = info if info is not None else torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
 
 
 LAC_LAZY, LAC_DENSE, LAC_LAZY_BG = 0, 1, 2
@@ -668,7 +750,7 @@ def nonlin_corr(data, nonlin_corr_file, max_counts=50000):
     nk = (C.c_int * nchans)(*[len(t) for t, _, _ in tck])
     deg = (C.c_int * nchans)(*[k for _, _, k in tck])
     is_np = isinstance(data, np.ndarray)
-    t_ = _to_dev(data, torch.float32)
+    t_ = _inplace_target(data, torch.float32, 'nonlin_corr')
     H, W = t_.shape
     gain = get_par(set_bb.gain, tel)
     call('bbx_nonlin_corr', _ptr(t_), H, W, H // set_bb.ny, W // set_bb.nx,
@@ -683,6 +765,30 @@ def nonlin_corr(data, nonlin_corr_file, max_counts=50000):
 # -------------------------------------------------------------------------------------------
 # FITS data units (fitsio.py reads / writes the files; the byte order is handled here)
 # -------------------------------------------------------------------------------------------
+def read_fits_image(path, dtype=None):
+    """A FITS image file -> (header dict key -> value, CUDA tensor), whatever its packing: an
+    uncompressed primary HDU (big-endian bytes decoded by ``bbx_fits_decode``) or an fpacked
+    ``.fits.fz`` (Rice-coded tiles decoded by ``bbx_rice_decode``; float images are un-quantised on
+    the device).  Stands in for the reference's ``read_hdulist(fits, dtype=...)``
+    (blackbox.py:7653-7771) at the places where the hot path reads a file itself: the bad-pixel
+    mask of mask_init and the calibration frames of master_prep.  ``dtype``: torch dtype to convert
+    to (None: uint16 counts / float32 / uint8 as stored)."""
+    with open(path, 'rb') as fh:
+        hdr, _ = fitsio.read_header(fh)
+    if hdr.get('NAXIS', (0,))[0] == 0:
+        hdr, heap, offs, lens, info = fitsio.read_compressed(path, pinned=True)
+        t = rice_decode(heap.to(_device(), non_blocking=True), offs, lens, info)
+    else:
+        hdr, buf, info = fitsio.read_primary(path, pinned=True)
+        if info['bitpix'] == 8:
+            t = buf.to(_device(), non_blocking=True).view(info['shape'])
+        else:
+            t = fits_decode(buf.to(_device(), non_blocking=True), info)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return {k: v[0] for k, v in hdr.items()}, t
+
+
 def fits_decode(be, info, out=None):
     """Big-endian data unit (uint8 CUDA / pinned / numpy buffer as returned by
     ``fitsio.read_primary``) -> native CUDA tensor of shape ``info['shape']``: uint16 counts for
@@ -781,7 +887,7 @@ def fill_edge_pixels(data, data_mask, medians=None):
     source-extractor run leading to a wrong background estimation near the edge",
     blackbox.py:1958-1974).  Uses the module-global ``tel``.  Returns the channel medians."""
     is_np = isinstance(data, np.ndarray)
-    t = _to_dev(data, torch.float32)
+    t = _inplace_target(data, torch.float32, 'fill_edge_pixels')
     m = _to_dev(data_mask, torch.uint8)
     if tuple(m.shape) != tuple(t.shape):
         raise ValueError('mask shape {} does not match data {}'.format(tuple(m.shape), tuple(t.shape)))
@@ -829,7 +935,7 @@ def xtalk_corr(data, crosstalk_file, data_mask=None):
     left unchanged.  Uses the module-global ``tel``."""
     coeffs = crosstalk_file if isinstance(crosstalk_file, np.ndarray) else read_crosstalk_file(crosstalk_file)
     is_np = isinstance(data, np.ndarray)
-    t = _to_dev(data, torch.float32)
+    t = _inplace_target(data, torch.float32, 'xtalk_corr')
     m = None
     if data_mask is not None:
         m = _to_dev(data_mask)

@@ -228,6 +228,41 @@ def test_fullsize_config1_meerlicht_chain_against_oracle():
     assert np.mean(img == data_o) > 0.999
 
 
+def test_fullsize_config4_blackgem_chain_against_oracle(full):
+    """The bench's own frame: one full-size BlackGEM (BG3, seed 4001) 10600 x 12000 raw frame
+    through the WHOLE chain -- gain, overscan, master bias, mask_init, master flat, LACosmic with
+    4 iterations, crosstalk (BASELINE.json config 4) -- against the oracle's whole-frame result:
+    mask bit for bit, header counts, image in the float class with > 99.9 % identical pixels."""
+    import torch
+    from conftest import float_class_ok
+    from blackbox_b200.pipeline import FramePipeline
+    from oracle import reduce as R
+    data_o, mask_o, hdr_o, hm_o = R.reduce_frame(full['raw'], TEL, full['mbias'], full['mflat'], full['bpm'],
+                                                 full['coeffs'], exptime=45.0, niter=4)
+    R.mask_header(mask_o, hm_o, tel=TEL)
+    pipe = FramePipeline(TEL, full['raw'].shape, mbias=full['mbias'], mflat=full['mflat'], bpm=full['bpm'],
+                         coeffs=full['coeffs'], niter=4)
+    pipe.enqueue(full['raw_t'], exptime=45.0)
+    res = pipe.finish()
+    assert not res.redo
+    mask = res.mask.cpu().numpy()
+    assert np.array_equal(mask, mask_o)
+    assert hdr_o['NOBJ-SAT'] > 10 and res.header['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
+    assert hdr_o['NCOSMICS'] > 1 and res.header['NCOSMICS'] == hdr_o['NCOSMICS']
+    assert ({k: int(v) for k, v in res.header_mask.items() if k.endswith('NUM')}
+            == {k: int(v) for k, v in hm_o.items() if k.endswith('NUM')})
+    for key in ('BIASMEAN', 'RDNOISE', 'SATURATE'):
+        assert res.header[key] == pytest.approx(hdr_o[key], rel=1e-9)
+    for i in range(16):
+        for key in ('BIASM{}'.format(i + 1), 'RDN{}'.format(i + 1)):
+            assert res.header[key] == pytest.approx(hdr_o[key], rel=1e-8), key
+    img = res.img.cpu().numpy()
+    del res, pipe
+    torch.cuda.empty_cache()
+    assert float_class_ok(img, data_o, scale=hdr_o['BIASMEAN']).all()
+    assert np.mean(img == data_o) > 0.999
+
+
 def test_fullsize_batch_reducer_equals_sequential(full):
     """Full-size frames through BatchReducer (4 pipelines in flight, overscan stage two frames
     ahead on high-priority streams, CUDA-graph replay) and through run_host: the bits of the

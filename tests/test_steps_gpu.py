@@ -278,6 +278,53 @@ def test_mask_init_no_saturation_and_no_bpm(small_bb):
     assert not mask_o.any() and np.array_equal(mask_g, mask_o)
 
 
+def test_mask_init_reads_the_bad_pixel_mask_like_the_reference(small_bb, tmp_path, monkeypatch, caplog):
+    """The reference-style call mask_init(data, header, filt, imgtype) -- no mask passed in -- reads
+    set_bb.bad_pixel_mask with 'bpm' -> 'bpm_<filt>' from disk (blackbox.py:4386-4398); a missing
+    file is a warning and a mask of zeros, never silent."""
+    import logging
+    from blackbox_b200 import fitsio, reduce as bbr, set_bb
+    from oracle import reduce as R
+    small_bb(96, 132)
+    data, bpm = _mask_case(9)
+    hdr = {'BIASM{}'.format(i + 1): 6500.0 + i for i in range(16)}
+    monkeypatch.setattr(set_bb, 'bad_pixel_mask', {'ML1': str(tmp_path / 'ML1_bpm_0p2.fits')})
+    bbr._bpm_registry.clear()
+    bbr.tel = 'ML1'
+    fitsio.write_primary(str(tmp_path / 'ML1_bpm_q_0p2.fits'), bpm)
+    mask_o, _ = R.mask_init(data.copy(), dict(hdr), bpm, 'object', tel='ML1')
+    mask_g, _ = bbr.mask_init(data.copy(), dict(hdr), 'q', 'object')
+    assert np.array_equal(mask_g, mask_o) and (mask_g & 32).any()
+    # a second call is served from the device cache; a rewritten file is read again
+    mask_g2, _ = bbr.mask_init(data.copy(), dict(hdr), 'q', 'object')
+    assert np.array_equal(mask_g2, mask_o)
+    # another filter: no file -> warning + zeros (as the reference)
+    with caplog.at_level(logging.WARNING, logger='blackbox_b200.reduce'):
+        mask_u, _ = bbr.mask_init(data.copy(), dict(hdr), 'u', 'object')
+    assert any('does not exist' in r.getMessage() for r in caplog.records)
+    mask_z, _ = R.mask_init(data.copy(), dict(hdr), None, 'object', tel='ML1')
+    assert np.array_equal(mask_u, mask_z) and not (mask_u & 32).any()
+
+
+def test_in_place_steps_refuse_tensors_they_would_have_to_copy(small_bb):
+    """xtalk_corr / gain_corr / mask_init / fill_edge_pixels work in place: a CUDA tensor that is not
+    contiguous float32 would be silently copied and the result lost -- they raise instead."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    small_bb(24, 132)
+    bbr.tel = 'ML1'
+    big = torch.zeros((48, 2 * 1056), dtype=torch.float32, device='cuda')
+    view = big[:, :1056]                                           # a non-contiguous view
+    with pytest.raises(TypeError):
+        bbr.xtalk_corr(view, np.zeros((16, 16)))
+    with pytest.raises(TypeError):
+        bbr.gain_corr(view, {}, tel='ML1')
+    with pytest.raises(TypeError):
+        bbr.xtalk_corr(torch.zeros((48, 1056), dtype=torch.float64, device='cuda'), np.zeros((16, 16)))
+    with pytest.raises(TypeError):
+        bbr.os_corr(torch.zeros((48 + 40, 12000), dtype=torch.int16, device='cuda'), {}, 'object', tel='ML1')
+
+
 def test_mask_header_counts(small_bb):
     from blackbox_b200 import reduce as bbr
     rng = np.random.default_rng(2)

@@ -63,7 +63,8 @@ def main(argv=None):
     RH, RW = batch.pipes[0].geom.red_shape
     imgs = [torch.empty((RH, RW), dtype=torch.float32).pin_memory() for _ in files]
     masks = [torch.empty((RH, RW), dtype=torch.uint8).pin_memory() for _ in files]
-    results = batch.run_host(raws, imgs, masks, fill_header=True, fits=True)
+    exptimes = [float(h['EXPTIME'][0]) if 'EXPTIME' in h else 60.0 for h in headers]     # NCOSMICS is a rate
+    results = batch.run_host(raws, imgs, masks, fill_header=True, fits=True, exptimes=exptimes)
     for path, hdr, res, img, mask in zip(files, headers, results, imgs, masks):
         base = os.path.splitext(os.path.basename(path))[0]
         out_hdr = {k: v for k, v in hdr.items() if k not in ('COMMENT', 'HISTORY')}
