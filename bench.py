@@ -15,8 +15,11 @@ sample per step) as a run of its own, rank 0 only.
 
 Printed JSON (rank 0, one line):
   value      frames/s over all GPUs, raw frames already resident in HBM
-  e2e        frames/s through the public API with HOST (pinned) raw frames in and HOST image +
-             mask out, H2D / D2H copies inside the timed region
+  e2e        frames/s through the public API (BatchReducer.run_host) with HOST buffers on both
+             sides, H2D / D2H copies inside the timed region: the fpacked raw frame in (as the
+             telescope delivers it; Rice-decoded on the device), the float32 image and the Rice-coded
+             mask (the reference's fpack -D -Y product) out.  e2e_uncompressed: plain uint16 frame in,
+             image + plain mask out (round 1's definition), fewer steps
   roofline   the dominant single kernel of the chain (largest mean device time among the
              one-kernel stages, CUDA events on the launching stream INSIDE the timed region) against
              the measured HBM peak; roofline_stages lists every stage the same way
@@ -329,17 +332,21 @@ def run_gpu(args, rank, world, local_rank):
         p.enable_stage_timing(False)
 
     # ---- end to end: pinned host raw in, pinned host image + mask out -----------------------
-    e2e = None
+    e2e = e2e_plain = None
     if not args.no_e2e:
-        e2e_ms = measure_e2e(args, batch, raws, red_shape, barrier)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        raw_bytes = raws[0].numel() * 2
-        e2e = {'value': world * B * args.steps / (e2e_ms * 1e-3), 'unit': 'frames/s',
-               'h2d_bytes_per_step': world * B * raw_bytes,
-               'd2h_bytes_per_step': world * B * (out_img.numel() * 4 + out_mask.numel())}
+        def e2e_entry(packed, steps):
+            ms, h2d, d2h = measure_e2e(args, batch, raws, red_shape, barrier, packed=packed, steps=steps)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return {'value': world * B * steps / (float(t.item()) * 1e-3), 'unit': 'frames/s',
+                    'h2d_bytes_per_step': int(world * B * h2d), 'd2h_bytes_per_step': int(world * B * d2h),
+                    'steps': steps}
+        e2e = e2e_entry(True, args.steps)
+        e2e['io'] = ('in: fpacked raw frame (Rice-coded heap + tile descriptors, pinned host memory), decoded on '
+                     'the device; out: float32 image + Rice-coded uint8 mask (the reference\'s fpack -D -Y product)')
+        e2e_plain = e2e_entry(False, max(1, min(args.steps, 3)))
+        e2e_plain['io'] = 'in: uint16 raw frame; out: float32 image + plain uint8 mask (round 1\'s e2e)'
 
     # ---- strong scaling: the night batch as one job of B frames in total -----------------------
     strong = None
@@ -367,7 +374,7 @@ def run_gpu(args, rank, world, local_rank):
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args), 'roofline': roof, 'roofline_stages': stages, 'cpu_baseline': cpu,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'e2e': e2e, 'e2e_uncompressed': e2e_plain, 'gpu_launches': launches,
             'chain_hbm_frac': (ALGO_BYTES_CHAIN_4IT * frames / world / (ms_total * 1e-3)) / (peak_hbm()[0] * 1e9),
             'frames_redone': redo, 'host_spline_columns': spline_cols[0],
             'graph_replays': sum(p.graph_replays for p in batch.pipes),
@@ -612,29 +619,53 @@ def stage_rooflines(pipes):
     return roof, stages
 
 
-def measure_e2e(args, batch, raws, red_shape, barrier):
-    """Public API with host buffers (BatchReducer.run_host): pinned uint16 raw frames in, pinned
-    f32 image + u8 mask out; host-to-device copies, the chain and device-to-host copies overlap
-    on their own streams, `--depth` frames in flight."""
+def measure_e2e(args, batch, raws, red_shape, barrier, packed=True, steps=None):
+    """Public API with host buffers (BatchReducer.run_host), H2D / D2H copies, the chain and the
+    codecs overlapping on their own streams, `--depth` frames in flight.
+    packed (the headline): every raw frame arrives as the telescope delivers it -- an fpacked
+    .fits.fz, i.e. a pinned host buffer with its Rice-coded heap (~1/3 of the frame) plus tile
+    descriptors, decoded on the device -- and the mask leaves as the reference's own product, the
+    losslessly Rice-coded uint8 image (`fpack -D -Y`); the float32 image leaves as it is.
+    not packed: pinned uint16 raw frames in, float32 image + plain uint8 mask out (round 1's e2e).
+    -> (ms, h2d bytes per frame, d2h bytes per frame)"""
     import torch
+    from blackbox_b200 import fitsio, reduce as R
     B = args.batch
-    nring = min(B, 8)              # 8 distinct pinned raw frames (2 GB), cycled through the batch
-    ring = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(nring)]
-    for k in range(nring):
-        ring[k].copy_(raws[k].cpu())
-        if args.fits:             # as the data unit of a raw FITS file: big-endian int16, BZERO 32768
-            a = ring[k].view(torch.int16).numpy()
-            be = (a.view(np.uint16).astype(np.int32) - 32768).astype('>i2')
-            a[...] = be.view(np.int16)
+    steps = args.steps if steps is None else steps
+    nring = min(B, 8)              # 8 distinct pinned raw frames, cycled through the batch
+    nout = min(max(2, args.depth), B) if B > 1 else 1
+    host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nout)]
+    if packed:
+        ring = []
+        for k in range(nring):     # set-up, outside the timed region: fpack the synthetic frames
+            heap, lens = R.rice_encode(raws[k])
+            offs = np.concatenate(([0], np.cumsum(lens.astype(np.int64))[:-1]))
+            info = dict(shape=tuple(raws[k].shape), bitpix=16, bytepix=2, bzero=32768.0, bscale=1.0, blocksize=32)
+            ring.append(fitsio.CompressedImage({}, torch.from_numpy(heap).pin_memory(), offs, lens.astype(np.int32), info))
+            ring[-1].descriptors()
+        h2d = sum(c.heap.numel() + c.descriptors().numel() for c in ring) / len(ring)
+        nbytes = batch.mask_fz_bytes()
+        host_mask = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(nout)]
+        d2h = red_shape[0] * red_shape[1] * 4 + nbytes
+        kw = dict(mask_fz=True)
+    else:
+        ring = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(nring)]
+        for k in range(nring):
+            ring[k].copy_(raws[k].cpu())
+            if args.fits:             # as the data unit of a raw FITS file: big-endian int16, BZERO 32768
+                a = ring[k].view(torch.int16).numpy()
+                be = (a.view(np.uint16).astype(np.int32) - 32768).astype('>i2')
+                a[...] = be.view(np.int16)
+        h2d = raws[0].numel() * 2
+        host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(nout)]
+        d2h = red_shape[0] * red_shape[1] * 5
+        kw = dict(fits=bool(args.fits))
     host_raw = [ring[k % nring] for k in range(B)]
-    nring = min(max(2, args.depth), B) if B > 1 else 1
-    host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nring)]
-    host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(nring)]
 
     def run(nsteps):
         redo = 0
         for _ in range(nsteps):
-            for res in batch.run_host(host_raw, host_img, host_mask, fits=bool(args.fits), fill_header=True):
+            for res in batch.run_host(host_raw, host_img, host_mask, fill_header=True, **kw):
                 redo += res.redo
         return redo
 
@@ -644,12 +675,12 @@ def measure_e2e(args, batch, raws, red_shape, barrier):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     w0 = time.perf_counter()
-    run(args.steps)
+    run(steps)
     torch.cuda.synchronize()
     t1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    return max(t0.elapsed_time(t1), wall_ms)
+    return max(t0.elapsed_time(t1), wall_ms), h2d, d2h
 
 
 def main():

@@ -73,12 +73,18 @@ _SIGNATURES = {
     'bbx_fits_decode': [P, I, I, SZ, P, P],
     'bbx_fits_encode': [P, I, I, SZ, P, P],
     'bbx_rice_decode16': [P, SZ, P, P, I, I, I, I, P, P, P],
+    'bbx_rice_decode': [P, SZ, P, P, I, I, I, I, I, P, P, P],
+    'bbx_unquantize': [P, I, I, P, P, P, I, I, I, I, P, P],
+    'bbx_rice_encode_work_bytes': [I, I, I],
+    'bbx_rice_encode_out_bytes': [I, I, I],
+    'bbx_rice_encode': [P, I, I, I, P, SZ, P, SZ, P],
     'bbx_chanmed_work_bytes': [],
     'bbx_channel_medians': [P, I, I, I, I, I, P, P, P],
     'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],
 }
 _RESTYPES = {'bbx_fill_holes_work_bytes': SZ, 'bbx_lacosmic_work_bytes': SZ,
-             'bbx_select_work_bytes': SZ, 'bbx_chanmed_work_bytes': SZ}
+             'bbx_select_work_bytes': SZ, 'bbx_chanmed_work_bytes': SZ,
+             'bbx_rice_encode_work_bytes': SZ, 'bbx_rice_encode_out_bytes': SZ}
 
 EXPORTS = tuple(sorted(list(_SIGNATURES) + ['bbx_last_error']))
 

@@ -16,9 +16,12 @@ GPU path needs:
   * ``read_compressed`` parse a tile-compressed image (``.fits.fz`` as written by fpack: an empty
                       primary HDU and a binary table whose heap holds one Rice-coded tile per
                       image row) and hand back the heap bytes plus the per-tile descriptors --
-                      the decoding is ``reduce.rice_decode`` -> ``bbx_rice_decode16`` on the GPU.
-                      Only what raw frames use: ZCMPTYPE RICE_1, ZBITPIX 16, BYTEPIX 2,
-                      BLOCKSIZE 32, row tiles; anything else raises FitsError.
+                      the decoding is ``reduce.rice_decode`` -> ``bbx_rice_decode`` on the GPU.
+                      ZCMPTYPE RICE_1, BLOCKSIZE 32, row tiles: 16-bit raw frames, 8-bit masks,
+                      32-bit integers and quantised float images (ZSCALE / ZZERO, dithering);
+                      anything else raises FitsError.
+  * ``write_compressed`` the way back for tiles Rice-coded on the GPU (``reduce.rice_encode`` ->
+                      ``bbx_rice_encode``): the losslessly fpacked uint8 mask of the reference.
 """
 import collections
 import os
@@ -174,12 +177,42 @@ def _tform_width(tform):
     return repeat * _TFORM_BYTES[code], code
 
 
+class CompressedImage:
+    """A tile-compressed image as it sits in the file, ready for the GPU: ``heap`` (the table's heap:
+    numpy memory map or pinned torch tensor), ``offsets`` (int64) / ``lengths`` (int32) one per
+    tile, ``info`` (see ``read_compressed``), ``header``; for float images ``zscale`` / ``zzero``
+    (float64 per tile)."""
+
+    def __init__(self, header, heap, offsets, lengths, info, zscale=None, zzero=None):
+        self.header, self.heap, self.offsets, self.lengths, self.info = header, heap, offsets, lengths, info
+        self.zscale, self.zzero = zscale, zzero
+        self._desc = None
+
+    def __iter__(self):                 # (header, heap, offsets, lengths, info) = read_compressed(...)
+        return iter((self.header, self.heap, self.offsets, self.lengths, self.info))
+
+    def descriptors(self):
+        """offsets (int64) then lengths (int32) in ONE pinned uint8 tensor: a single host-to-device
+        copy next to the heap's."""
+        if self._desc is None:
+            import torch
+            n = len(self.offsets)
+            buf = torch.empty(12 * n, dtype=torch.uint8).pin_memory()
+            buf[:8 * n].view(torch.int64).copy_(torch.from_numpy(np.ascontiguousarray(self.offsets, dtype=np.int64)))
+            buf[8 * n:].view(torch.int32).copy_(torch.from_numpy(np.ascontiguousarray(self.lengths, dtype=np.int32)))
+            self._desc = buf
+        return self._desc
+
+
 def read_compressed(path, pinned=False):
-    """-> (header, heap, offsets, lengths, info) of the first tile-compressed image of ``path``.
-    ``heap``: the table's heap as a uint8 numpy array (a memory map) or, with ``pinned``, a pinned
-    ``torch`` tensor; ``offsets`` (int64) / ``lengths`` (int32): one entry per tile, byte offset
-    into the heap and compressed size; ``info``: dict(bitpix, shape, bzero, bscale, blocksize,
-    bytepix, tile_shape).  ``header`` merges the primary and the extension keywords."""
+    """-> CompressedImage (unpacks as ``(header, heap, offsets, lengths, info)``) of the first
+    tile-compressed image of ``path``.  ``heap``: the table's heap as a uint8 numpy array (a memory
+    map) or, with ``pinned``, a pinned ``torch`` tensor; ``offsets`` (int64) / ``lengths`` (int32):
+    one entry per tile, byte offset into the heap and compressed size; ``info``: dict(bitpix, shape,
+    bzero, bscale, blocksize, bytepix, tile_shape, quantize, zdither0, zblank).  ``header`` merges the
+    primary and the extension keywords.  Supported: RICE_1, BLOCKSIZE 32, row tiles, ZBITPIX 8 / 16 /
+    32 with BYTEPIX 1 / 2 / 4 and ZBITPIX -32 (float images quantised to int32, ZSCALE / ZZERO
+    columns, NO_DITHER / SUBTRACTIVE_DITHER_1 / _2); anything else raises FitsError."""
     with open(path, 'rb') as fh:
         hdr, hbytes = read_header(fh)
         if hdr.get('NAXIS', (0,))[0] != 0:
@@ -192,9 +225,10 @@ def read_compressed(path, pinned=False):
         cmptype = str(get('ZCMPTYPE', '')).strip()
         if cmptype not in ('RICE_1', 'RICE_ONE'):
             raise FitsError('{}: ZCMPTYPE {!r} (RICE_1 is supported)'.format(path, cmptype))
-        if get('ZBITPIX') != 16 or get('ZNAXIS') != 2:
-            raise FitsError('{}: ZBITPIX {} / ZNAXIS {} (16-bit 2-D images are supported)'.format(
-                path, get('ZBITPIX'), get('ZNAXIS')))
+        zbitpix = get('ZBITPIX')
+        if zbitpix not in (8, 16, 32, -32) or get('ZNAXIS') != 2:
+            raise FitsError('{}: ZBITPIX {} / ZNAXIS {} (8 / 16 / 32 / -32-bit 2-D images are supported)'.format(
+                path, zbitpix, get('ZNAXIS')))
         shape = (int(get('ZNAXIS2')), int(get('ZNAXIS1')))
         tile = (int(get('ZTILE2', 1)), int(get('ZTILE1', shape[1])))
         if tile != (1, shape[1]):
@@ -208,17 +242,19 @@ def read_compressed(path, pinned=False):
             elif name == 'BYTEPIX':
                 bytepix = int(get('ZVAL{}'.format(n)))
             n += 1
-        if blocksize != 32 or bytepix != 2:
-            raise FitsError('{}: BLOCKSIZE {} / BYTEPIX {} (32 / 2 are supported)'.format(path, blocksize, bytepix))
+        want_bp = {8: (1,), 16: (2,), 32: (4,), -32: (4,)}[zbitpix]
+        if blocksize != 32 or bytepix not in want_bp:
+            raise FitsError('{}: BLOCKSIZE {} / BYTEPIX {} for ZBITPIX {} (32 / {} are supported)'.format(
+                path, blocksize, bytepix, zbitpix, want_bp[0]))
         rowlen, nrows, pcount = int(get('NAXIS1')), int(get('NAXIS2')), int(get('PCOUNT', 0))
         if nrows != shape[0]:
             raise FitsError('{}: {} table rows for {} tiles'.format(path, nrows, shape[0]))
-        col_off, found = 0, None
+        col_off, cols = 0, {}
         for c in range(1, int(get('TFIELDS')) + 1):
             width, code = _tform_width(get('TFORM{}'.format(c)))
-            if str(get('TTYPE{}'.format(c), '')).strip() == 'COMPRESSED_DATA':
-                found = (col_off, code)
+            cols[str(get('TTYPE{}'.format(c), '')).strip()] = (col_off, code, width)
             col_off += width
+        found = cols.get('COMPRESSED_DATA')
         if found is None or found[1] not in ('P', 'Q'):
             raise FitsError('{}: no COMPRESSED_DATA column of variable-length bytes'.format(path))
         fh.seek(table_start)
@@ -234,6 +270,28 @@ def read_compressed(path, pinned=False):
         if (lengths <= 0).any():
             raise FitsError('{}: {} tile(s) without Rice-coded bytes (stored in a fall-back column)'.format(
                 path, int((lengths <= 0).sum())))
+        zscale = zzero = None
+        quantize, zdither0, zblank = None, 0, None
+        if zbitpix == -32:
+            quantize = str(get('ZQUANTIZ', 'NO_DITHER')).strip().upper()
+            if quantize not in ('NO_DITHER', 'SUBTRACTIVE_DITHER_1', 'SUBTRACTIVE_DITHER_2'):
+                raise FitsError('{}: ZQUANTIZ {!r}'.format(path, quantize))
+            per_tile = {}
+            for name in ('ZSCALE', 'ZZERO'):
+                if name in cols:
+                    o, code, width = cols[name]
+                    if code not in ('D', 'E') or width not in (8, 4):
+                        raise FitsError('{}: column {} has TFORM code {}'.format(path, name, code))
+                    per_tile[name] = rows[:, o:o + width].copy().view('>f8' if code == 'D' else '>f4')[:, 0].astype(np.float64)
+                elif name in ext:
+                    per_tile[name] = np.full(nrows, float(get(name)))
+                else:
+                    raise FitsError('{}: float image without {}'.format(path, name))
+            zscale, zzero = per_tile['ZSCALE'], per_tile['ZZERO']
+            zdither0 = int(get('ZDITHER0', 1))
+            if 'ZBLANK' in cols:
+                raise FitsError('{}: per-tile ZBLANK column'.format(path))
+            zblank = int(get('ZBLANK')) if 'ZBLANK' in ext else None
         theap = int(get('THEAP', rowlen * nrows))
         heap_start = table_start + theap
         heap_bytes = pcount - (theap - rowlen * nrows)
@@ -253,11 +311,83 @@ def read_compressed(path, pinned=False):
     for k, v in ext.items():
         if k not in ('XTENSION', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'PCOUNT', 'GCOUNT', 'TFIELDS', 'THEAP') \
                 and not k.startswith(('TTYPE', 'TFORM', 'ZNAME', 'ZVAL', 'ZTILE', 'ZNAXIS')) \
-                and k not in ('ZIMAGE', 'ZCMPTYPE', 'ZBITPIX', 'ZSIMPLE', 'ZEXTEND', 'ZQUANTIZ', 'ZDITHER0'):
+                and k not in ('ZIMAGE', 'ZCMPTYPE', 'ZBITPIX', 'ZSIMPLE', 'ZEXTEND', 'ZQUANTIZ', 'ZDITHER0', 'ZBLANK'):
             merged[k] = v
-    info = dict(bitpix=16, shape=shape, bzero=float(get('BZERO', 0.0)), bscale=float(get('BSCALE', 1.0)),
-                blocksize=blocksize, bytepix=bytepix, tile_shape=tile)
-    return merged, heap, offsets.astype(np.int64), lengths.astype(np.int32), info
+    info = dict(bitpix=zbitpix, shape=shape, bzero=float(get('BZERO', 0.0)), bscale=float(get('BSCALE', 1.0)),
+                blocksize=blocksize, bytepix=bytepix, tile_shape=tile, quantize=quantize, zdither0=zdither0,
+                zblank=zblank)
+    return CompressedImage(merged, heap, offsets.astype(np.int64), lengths.astype(np.int32), info, zscale, zzero)
+
+
+_dither_table = None
+
+
+def dither_random_table():
+    """The 10000 random numbers the FITS standard defines for (un)dithering quantised float
+    images: Park & Miller's minimal standard generator (a = 16807, m = 2^31 - 1, seed 1), value =
+    seed / m in float32; the 10000th seed is 1043618065 (the standard's check value)."""
+    global _dither_table
+    if _dither_table is None:
+        a, m, seed = 16807.0, 2147483647.0, 1.0
+        out = np.empty(10000, dtype=np.float32)
+        for i in range(10000):
+            temp = a * seed
+            seed = temp - m * int(temp / m)
+            out[i] = seed / m
+        if int(seed) != 1043618065:
+            raise FitsError('dither table self-check failed')
+        _dither_table = out
+    return _dither_table
+
+
+def write_compressed(path, heap, lengths, shape, zbitpix, header=None):
+    """Write a tile-compressed image the way fpack lays it out (empty primary HDU; BINTABLE with one
+    COMPRESSED_DATA column of row tiles, RICE_1, BLOCKSIZE 32) from Rice-coded tiles that already
+    exist -- ``heap``: the tiles back to back (numpy uint8 / pinned torch tensor), ``lengths``:
+    bytes per tile, as ``bbx_rice_encode`` leaves them.  ``zbitpix`` 8 (the mask: what the reference
+    gets from ``fpack -D -Y``, blackbox.py:826-827), 16 or 32."""
+    if zbitpix not in (8, 16, 32):
+        raise FitsError('write_compressed: ZBITPIX {}'.format(zbitpix))
+    H, W = shape
+    lens = np.asarray(lengths, dtype=np.int64)
+    if lens.shape != (H,):
+        raise FitsError('write_compressed: {} tile sizes for {} rows'.format(lens.size, H))
+    raw = heap.numpy() if hasattr(heap, 'numpy') else np.asarray(heap)
+    raw = raw.reshape(-1).view(np.uint8)
+    total = int(lens.sum())
+    if raw.size < total:
+        raise FitsError('write_compressed: heap holds {} bytes, the tiles need {}'.format(raw.size, total))
+    offs = np.concatenate(([0], np.cumsum(lens)[:-1]))
+    pointer = 'P' if total < 2 ** 31 else 'Q'
+    desc = np.stack([lens, offs], axis=1).astype('>i4' if pointer == 'P' else '>i8')
+    width = desc.dtype.itemsize * 2
+    primary = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0),
+               _card('EXTEND', True), 'END'.ljust(80)]
+    ext = ["XTENSION= 'BINTABLE'".ljust(80), _card('BITPIX', 8), _card('NAXIS', 2), _card('NAXIS1', width),
+           _card('NAXIS2', H), _card('PCOUNT', total), _card('GCOUNT', 1), _card('TFIELDS', 1),
+           _card('TTYPE1', 'COMPRESSED_DATA'), _card('TFORM1', '1{}B({})'.format(pointer, int(lens.max()))),
+           _card('ZIMAGE', True), _card('ZSIMPLE', True), _card('ZBITPIX', zbitpix), _card('ZNAXIS', 2),
+           _card('ZNAXIS1', W), _card('ZNAXIS2', H), _card('ZTILE1', W), _card('ZTILE2', 1),
+           _card('ZCMPTYPE', 'RICE_1'), _card('ZNAME1', 'BLOCKSIZE'), _card('ZVAL1', 32),
+           _card('ZNAME2', 'BYTEPIX'), _card('ZVAL2', zbitpix // 8)]
+    skip = {'SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'END', 'EXTEND', 'XTENSION', 'PCOUNT', 'GCOUNT', 'TFIELDS'}
+    for key, val in (header.items() if header is not None else ()):
+        if str(key).upper() in skip or str(key).upper() in ('COMMENT', 'HISTORY'):
+            continue
+        value, comment = (val if isinstance(val, tuple) and len(val) == 2 else (val, ''))
+        ext.append(_card(key, value, comment))
+    ext.append('END'.ljust(80))
+    tmp = os.path.join(os.path.dirname(path) or '.', '.{}.{}.part'.format(
+        os.path.basename(path).replace('.fits', '_fits'), os.getpid()))
+    with open(tmp, 'wb') as fh:
+        for cards in (primary, ext):
+            text = ''.join(cards)
+            fh.write((text + ' ' * (-len(text) % BLOCK)).encode('ascii', 'replace'))
+        fh.write(desc.tobytes())
+        fh.write(memoryview(np.ascontiguousarray(raw[:total])))
+        fh.write(b'\0' * (-(desc.nbytes + total) % BLOCK))
+    os.replace(tmp, path)
+    return path
 
 
 def to_native(data, info):

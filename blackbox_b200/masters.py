@@ -22,9 +22,11 @@ What is mirrored, step by step:
 Left out on purpose: the header statistics drawn from a RANDOM subsample (MFMED / MFSTD, MBMEAN /
 MBRDN, MBIASM / MBRDN per channel; ``get_rand_indices`` of the absent zogy module, not
 reproducible), the QC flags (``run_qc_check``, qc.py: policy, out of scope), fpack and the jpg.
-Files are read and written with ``fitsio`` (uncompressed primary HDUs); a ``.fz`` file in the
-list raises ``fitsio.FitsError`` -- funpack the night first (tools/reduce_night.py writes
-uncompressed files).
+Files are read with ``reduce.read_fits_image``: plain primary HDUs or fpacked ``.fits.fz`` (what the
+reference's folders hold; Rice tiles decoded and float images un-quantised on the GPU), the
+bad-pixel mask likewise; the master is written as an uncompressed float32 primary HDU.  An input
+this reader cannot unpack ends, as any unusable input does in the reference, with the nearest
+existing master and a logged error.
 
 The individual frames go to the GPU one by one (pinned big-endian bytes, decoded there); the
 whole stack stays resident (15 x 446 MB for a full-size master flat)."""
@@ -297,7 +299,15 @@ def master_prep(fits_master, data_shape, create_master, pick_alt=True, tel=None,
         log.warning('%d %s frames found, ncal_max is %d: keeping the ones nearest to midnight of %s', nfiles_orig,
                     imgtype, nmax, date_eve)
 
-    master, header = combine_files(list(file_list), tuple(data_shape), imgtype, filt, nwindow, tel)
+    try:
+        master, header = combine_files(list(file_list), tuple(data_shape), imgtype, filt, nwindow, tel)
+    except (fitsio.FitsError, NotImplementedError) as exc:
+        # an input this reader cannot unpack (a tile kept in a gzip fall-back column, say): as for
+        # any other unusable input the reference ends up with a nearby master, not with a raise
+        log.error('master %s of %s not made, unreadable input: %s', msg, date_eve, exc)
+        if not pick_alt:
+            return None
+        return get_nearest_master(date_eve, imgtype, fits_master, filt=filt, tel=tel)
     return write_master(fits_master, master, header)
 
 
@@ -352,10 +362,9 @@ def combine_files(file_list, data_shape, imgtype, filt, nwindow, tel):
         fits_bpm = get_par(set_bb.bad_pixel_mask, tel).replace('bpm', 'bpm_{}'.format(filt))
         present, fits_bpm = already_exists(fits_bpm, get_filename=True)
         if present:
-            _, raw, info = fitsio.read_primary(fits_bpm)
-            if info['bitpix'] != 8:
-                raise fitsio.FitsError('{}: bad-pixel mask with BITPIX {}'.format(fits_bpm, info['bitpix']))
-            bpm = torch.from_numpy(np.array(raw, dtype=np.uint8)).to(dev)
+            _, bpm = R.read_fits_image(fits_bpm)               # plain or fpacked (set_blackbox.py:187-193: .fits.fz)
+            if bpm.dtype != torch.uint8:
+                raise fitsio.FitsError('{}: bad-pixel mask is not an 8-bit image ({})'.format(fits_bpm, bpm.dtype))
     master, scales = R.master_combine(frames, imgtype=imgtype, medsec=medsec if imgtype == 'flat' else None,
                                       bpm=bpm, tel=tel)
     if imgtype == 'flat':

@@ -32,6 +32,7 @@ class FrameResult:
         self.header, self.header_mask = header, header_mask
         self.spline_columns = spline_columns   # overscan columns taken from the host spline
         self.redo = redo                       # hole filling needed extra rounds -> chain redone
+        self.mask_fz = None                    # (heap, lengths) of the Rice-coded mask (run_host(mask_fz=True))
 
 
 class FramePipeline:
@@ -422,7 +423,15 @@ class BatchReducer:
         return results
 
     # ---------------------------------------------------------------------------------------
-    def run_host(self, host_raws, host_imgs, host_masks, fill_header=True, fits=False, exptimes=None):
+    def mask_fz_bytes(self, heap_bytes=8 << 20):
+        """Size of a pinned host buffer that receives a frame's Rice-coded mask (``run_host(...,
+        mask_fz=True)``): the descriptor block plus ``heap_bytes`` of heap.  A mask of a science frame
+        compresses to ~2 MB; one that does not fit is fetched in full by ``finish`` (rare, slow)."""
+        RH, RW = self.pipes[0].geom.red_shape
+        return 16 + (4 * RH + 15) // 16 * 16 + int(heap_bytes)
+
+    def run_host(self, host_raws, host_imgs, host_masks, fill_header=True, fits=False, exptimes=None,
+                 mask_fz=False):
         """The same batch with HOST buffers on both sides: ``host_raws`` pinned uint16 (or
         float32) raw frames, ``host_imgs`` / ``host_masks`` pinned float32 / uint8 outputs (rings:
         frame k goes to index k % len; a ring slot must have been consumed by the caller before
@@ -430,31 +439,68 @@ class BatchReducer:
         on their own streams, ``depth`` frames in flight.  Returns the FrameResults; the host
         outputs of all frames are complete on return.
 
+        ``host_raws`` may also hold ``fitsio.CompressedImage`` objects (``fitsio.read_compressed(path,
+        pinned=True)``): the frame as it is on disk at the telescope, an fpacked ``.fits.fz``.  Its
+        Rice-coded heap (a third of the frame's bytes) is what crosses PCIe; ``bbx_rice_decode``
+        unpacks it on the device, on the copy stream, next to the other frames' kernels.
+
         ``fits``: the host buffers hold FITS data units as they are on disk -- ``host_raws`` the
         big-endian 16-bit data unit of a raw frame (BZERO 32768; ``fitsio.read_primary(...,
         pinned=True)`` reshaped to the frame, any 2-byte dtype), ``host_imgs`` receives the
         big-endian float32 data unit of the reduced image (``fitsio.write_primary(..., be_bytes=True)``).
-        The byte swaps run on the device, in place, next to the copies."""
+        The byte swaps run on the device, in place, next to the copies.
+
+        ``mask_fz``: the mask leaves the device Rice-coded -- the losslessly fpacked uint8 image the
+        reference writes (``fpack -D -Y``, blackbox.py:826-827, 1990); ``host_masks`` are then pinned
+        uint8 buffers of ``mask_fz_bytes()`` bytes and every FrameResult carries ``mask_fz = (heap,
+        lengths)`` (views into its ring slot) for ``fitsio.write_compressed(path, heap, lengths, shape,
+        8, header_mask)``."""
         n, d = len(host_raws), self.depth
         if n == 0:
             return []
         dev = self.pipes[0].device
-        RH, RW = self.pipes[0].geom.red_shape
+        geom = self.pipes[0].geom
+        RH, RW = geom.red_shape
         if exptimes is not None and len(exptimes) != n:
             raise ValueError('{} exposure times for {} frames'.format(len(exptimes), n))
+        packed = [hasattr(r, 'heap') for r in host_raws]
         # device-side raw buffers: 2-byte host frames of any dtype (a FITS data unit read as int16,
         # say) are bytes to the copy engine and uint16 counts to the kernels
-        raw_dt = torch.float32 if host_raws[0].dtype == torch.float32 else torch.uint16
-        if host_raws[0].element_size() != (4 if raw_dt == torch.float32 else 2):
-            raise TypeError('host raw frames must be 2-byte counts or float32, got {}'.format(host_raws[0].dtype))
+        first = next((r for r, p in zip(host_raws, packed) if not p), None)
+        raw_dt = torch.float32 if (first is not None and first.dtype == torch.float32) else torch.uint16
+        for r, p in zip(host_raws, packed):
+            if p:
+                if tuple(r.info['shape']) != (geom.H, geom.W) or r.info['bitpix'] != 16 or r.info['bzero'] != 32768.0:
+                    raise ValueError('compressed raw frame: expected 16-bit counts (BZERO 32768) of shape {}, got '
+                                     'BITPIX {} / BZERO {} / shape {}'.format((geom.H, geom.W), r.info['bitpix'],
+                                                                             r.info['bzero'], r.info['shape']))
+                if raw_dt != torch.uint16 or fits:
+                    raise ValueError('compressed raw frames cannot be mixed with float32 frames or fits=True')
+            elif r.element_size() != (4 if raw_dt == torch.float32 else 2):
+                raise TypeError('host raw frames must be 2-byte counts or float32, got {}'.format(r.dtype))
         if getattr(self, '_hbuf', None) is None or self._hbuf[0][0].dtype != raw_dt:
-            self._hbuf = [(torch.empty(tuple(host_raws[0].shape), dtype=raw_dt, device=dev),
+            self._hbuf = [(torch.empty((geom.H, geom.W), dtype=raw_dt, device=dev),
                            torch.empty((RH, RW), dtype=torch.float32, device=dev),
                            torch.empty((RH, RW), dtype=torch.uint8, device=dev)) for _ in range(d)]
             self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
             self._ev_in = [torch.cuda.Event() for _ in range(d)]
             self._ev_out = [torch.cuda.Event() for _ in range(d)]
             self._ev_done = [torch.cuda.Event() for _ in range(d)]
+            self._fz_in = self._fz_out = None
+        if any(packed) and self._fz_in is None:
+            cap = geom.H * geom.W * 2 + geom.H * 8 + 4096          # Rice never grows a row by more than 1/32 + 4 B
+            self._fz_in = [dict(heap=torch.empty(cap, dtype=torch.uint8, device=dev),
+                                desc=torch.empty(12 * geom.H, dtype=torch.uint8, device=dev),
+                                status=torch.zeros(1, dtype=torch.int32, device=dev),
+                                status_host=torch.zeros(1, dtype=torch.int32).pin_memory()) for _ in range(d)]
+        if mask_fz:
+            want = host_masks[0].numel()
+            if self._fz_out is None or self._fz_out[0].out_bytes != want:
+                self._fz_out = [R.RiceEncoder((RH, RW), 1, dev, out_bytes=want) for _ in range(d)]
+            for m in host_masks:
+                if m.dtype != torch.uint8 or m.numel() != want or want < self.mask_fz_bytes(0) + 16:
+                    raise ValueError('mask_fz: host mask buffers must be equal-sized pinned uint8 buffers of at '
+                                     'least mask_fz_bytes(0) + 16 bytes')
         results = [None] * n
         caller = torch.cuda.current_stream()
         for s in set(self.streams + self.hi_streams) | {self._s_in, self._s_out}:
@@ -469,7 +515,10 @@ class BatchReducer:
                     img = self._hbuf[j][1]
                     call('bbx_fits_encode', R._ptr(img), -32, 0, img.numel(), R._ptr(img), R._stream())
                 host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
-                host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
+                if mask_fz:
+                    host_masks[k % nm].copy_(self._fz_out[j].enqueue(self._hbuf[j][2]), non_blocking=True)
+                else:
+                    host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
                 self._ev_out[j].record()
 
         def retire(k):
@@ -480,18 +529,45 @@ class BatchReducer:
                     self._ev_done[j].record()
             if results[k].redo:
                 copy_out(k)
+            if packed[k] or mask_fz:
+                self._ev_out[j].synchronize()
+            if packed[k] and int(self._fz_in[j]['status_host'][0]) != 0:
+                raise ValueError('frame {}: corrupt Rice-coded tile(s) in the compressed raw frame (status {})'.format(
+                    k, int(self._fz_in[j]['status_host'][0])))
+            if mask_fz:
+                enc = self._fz_out[j]
+                total, lens, heap, fits_in = enc.parse(host_masks[k % nm])
+                if not fits_in:                          # rare: a mask that hardly compresses
+                    with torch.cuda.stream(self._s_out):
+                        big = R.RiceEncoder((RH, RW), 1, dev)
+                        host = big.enqueue(self._hbuf[j][2]).cpu()
+                    total, lens, heap, _ = big.parse(host)
+                results[k].mask_fz = (heap, lens)
 
         def stage_a(k):
             j = k % d
             if k >= d:
                 retire(k - d)
             with torch.cuda.stream(self._s_in):
-                self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
                 src = host_raws[k]
-                self._hbuf[j][0].copy_(src if src.dtype == raw_dt else src.view(raw_dt), non_blocking=True)
-                if fits:
-                    raw = self._hbuf[j][0]
-                    call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
+                if packed[k]:
+                    fz = self._fz_in[j]
+                    nheap = src.heap.numel()
+                    if nheap > fz['heap'].numel():
+                        raise ValueError('frame {}: compressed heap of {} bytes is larger than the frame'.format(k, nheap))
+                    fz['heap'][:nheap].copy_(src.heap, non_blocking=True)
+                    fz['desc'].copy_(src.descriptors(), non_blocking=True)
+                    self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
+                    call('bbx_rice_decode', R._ptr(fz['heap']), nheap, R._ptr(fz['desc']),
+                         R._ptr(fz['desc'][8 * geom.H:]), geom.H, geom.W, int(src.info.get('blocksize', 32)), 2, 1,
+                         R._ptr(self._hbuf[j][0]), R._ptr(fz['status']), R._stream())
+                    fz['status_host'].copy_(fz['status'], non_blocking=True)
+                else:
+                    self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
+                    self._hbuf[j][0].copy_(src if src.dtype == raw_dt else src.view(raw_dt), non_blocking=True)
+                    if fits:
+                        raw = self._hbuf[j][0]
+                        call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
                 self._ev_in[j].record()
             with torch.cuda.stream(self.hi_streams[j]):
                 self.hi_streams[j].wait_event(self._ev_in[j])

@@ -776,8 +776,10 @@ def read_fits_image(path, dtype=None):
     with open(path, 'rb') as fh:
         hdr, _ = fitsio.read_header(fh)
     if hdr.get('NAXIS', (0,))[0] == 0:
-        hdr, heap, offs, lens, info = fitsio.read_compressed(path, pinned=True)
-        t = rice_decode(heap.to(_device(), non_blocking=True), offs, lens, info)
+        ci = fitsio.read_compressed(path, pinned=True)
+        hdr = ci.header
+        t = rice_decode(ci.heap.to(_device(), non_blocking=True), ci.offsets, ci.lengths, ci.info,
+                        zscale=ci.zscale, zzero=ci.zzero)
     else:
         hdr, buf, info = fitsio.read_primary(path, pinned=True)
         if info['bitpix'] == 8:
@@ -815,34 +817,107 @@ def fits_decode(be, info, out=None):
     return out
 
 
-def rice_decode(heap, offsets, lengths, info, out=None, check=True):
-    """Tile-compressed raw frame (``fitsio.read_compressed``: heap bytes + per-tile descriptors)
-    -> native CUDA tensor of shape ``info['shape']``: uint16 counts for BZERO 32768, else int16
-    (what read_hdulist returns for an fpacked raw frame, blackbox.py:1451).  The heap crosses
-    PCIe compressed; ``bbx_rice_decode16`` unpacks it.  ``check``: synchronise and raise on a
-    corrupt tile (pass False inside a pipeline and test ``rice_status`` later)."""
+_RICE_DTYPES = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+
+
+def rice_decode(heap, offsets, lengths, info, out=None, check=True, zscale=None, zzero=None):
+    """Tile-compressed image (``fitsio.read_compressed``: heap bytes + per-tile descriptors) ->
+    native CUDA tensor of shape ``info['shape']``: uint16 counts for BITPIX 16 / BZERO 32768 (what
+    read_hdulist returns for an fpacked raw frame, blackbox.py:1451), int16 / uint8 / int32 for the
+    other integer images, float32 for quantised float images (``zscale`` / ``zzero``: the table's
+    per-tile columns).  The heap crosses PCIe compressed; ``bbx_rice_decode`` unpacks it.
+    ``check``: synchronise and raise on a corrupt tile (pass False inside a pipeline and test the
+    returned status later)."""
     shape = tuple(info['shape'])
-    if info.get('bitpix') != 16 or info.get('bytepix', 2) != 2:
-        raise NotImplementedError('rice_decode: BITPIX {} / BYTEPIX {}'.format(info.get('bitpix'), info.get('bytepix')))
-    u16 = info.get('bzero', 0.0) == 32768.0 and info.get('bscale', 1.0) == 1.0
-    if not u16 and (info.get('bzero', 0.0) != 0.0 or info.get('bscale', 1.0) != 1.0):
+    bitpix, bytepix = info.get('bitpix'), info.get('bytepix', 2)
+    if (bitpix, bytepix) not in ((8, 1), (16, 2), (32, 4), (-32, 4)):
+        raise NotImplementedError('rice_decode: BITPIX {} / BYTEPIX {}'.format(bitpix, bytepix))
+    u16 = bitpix == 16 and info.get('bzero', 0.0) == 32768.0 and info.get('bscale', 1.0) == 1.0
+    if bitpix != -32 and not u16 and (info.get('bzero', 0.0) != 0.0 or info.get('bscale', 1.0) != 1.0):
         raise NotImplementedError('rice_decode: BZERO {} / BSCALE {}'.format(info.get('bzero'), info.get('bscale')))
     h = _to_dev(heap if not isinstance(heap, np.ndarray) else np.ascontiguousarray(heap)).view(torch.uint8).reshape(-1)
     offs = _to_dev(np.ascontiguousarray(offsets, dtype=np.int64) if not isinstance(offsets, torch.Tensor) else offsets)
     lens = _to_dev(np.ascontiguousarray(lengths, dtype=np.int32) if not isinstance(lengths, torch.Tensor) else lengths)
     if offs.numel() != shape[0] or lens.numel() != shape[0] or offs.dtype != torch.int64 or lens.dtype != torch.int32:
         raise ValueError('rice_decode: {} / {} descriptors for {} tiles'.format(offs.numel(), lens.numel(), shape[0]))
-    if out is None:
-        out = torch.empty(shape, dtype=torch.uint16 if u16 else torch.int16, device=h.device)
+    dt = torch.uint16 if u16 else _RICE_DTYPES[bytepix]
+    ints = out if (out is not None and bitpix != -32) else torch.empty(shape, dtype=dt, device=h.device)
+    if ints.dtype != dt or tuple(ints.shape) != shape:
+        raise ValueError('rice_decode: output must be a {} tensor of shape {}'.format(dt, shape))
     status = torch.empty(1, dtype=torch.int32, device=h.device)
-    call('bbx_rice_decode16', _ptr(h), h.numel(), _ptr(offs), _ptr(lens), shape[0], shape[1],
-         int(info.get('blocksize', 32)), int(u16), _ptr(out), _ptr(status), _stream())
+    call('bbx_rice_decode', _ptr(h), h.numel(), _ptr(offs), _ptr(lens), shape[0], shape[1],
+         int(info.get('blocksize', 32)), int(bytepix), int(u16), _ptr(ints), _ptr(status), _stream())
+    res = ints
+    if bitpix == -32:
+        if zscale is None or zzero is None:
+            raise ValueError('rice_decode: a quantised float image needs its ZSCALE / ZZERO columns')
+        method = {'NO_DITHER': 0, 'SUBTRACTIVE_DITHER_1': 1, 'SUBTRACTIVE_DITHER_2': 2}[info.get('quantize') or 'NO_DITHER']
+        zs = _to_dev(np.ascontiguousarray(zscale, dtype=np.float64))
+        zz = _to_dev(np.ascontiguousarray(zzero, dtype=np.float64))
+        rnd = _to_dev(fitsio.dither_random_table()) if method else None
+        res = out if out is not None else torch.empty(shape, dtype=torch.float32, device=h.device)
+        zblank = info.get('zblank')
+        call('bbx_unquantize', _ptr(ints), shape[0], shape[1], _ptr(zs), _ptr(zz), _ptr(rnd), method,
+             int(info.get('zdither0', 1) or 1), int(zblank if zblank is not None else 0), int(zblank is not None),
+             _ptr(res), _stream())
     if check:
         code = int(status.item())
         if code:
             raise ValueError('rice_decode: corrupt compressed tile(s), status {}'.format(code))
-        return out
-    return out, status
+        return res
+    return res, status
+
+
+class RiceEncoder:
+    """Scratch and output buffers of ``bbx_rice_encode`` for images of one shape (reusable).
+    ``out_bytes``: size of the device output buffer (descriptors + heap); None = the size that
+    always fits.  The mask compresses ~50-fold, so FramePipeline asks for a few MB."""
+
+    def __init__(self, shape, bytepix, device, out_bytes=None):
+        self.shape, self.bytepix = tuple(shape), int(bytepix)
+        H, W = self.shape
+        self.work = torch.empty(query('bbx_rice_encode_work_bytes', H, W, self.bytepix), dtype=torch.uint8, device=device)
+        full = query('bbx_rice_encode_out_bytes', H, W, self.bytepix)
+        self.heap_offset = 16 + (4 * H + 15) // 16 * 16
+        self.out_bytes = int(full if out_bytes is None else max(int(out_bytes), self.heap_offset + 16))
+        self.out = torch.empty(self.out_bytes, dtype=torch.uint8, device=device)
+
+    def enqueue(self, img_t):
+        H, W = self.shape
+        if tuple(img_t.shape) != self.shape or img_t.element_size() != self.bytepix or not img_t.is_contiguous():
+            raise ValueError('rice_encode: expected a contiguous {}-byte image of shape {}'.format(self.bytepix, self.shape))
+        call('bbx_rice_encode', _ptr(img_t), H, W, self.bytepix, _ptr(self.work), self.work.numel(),
+             _ptr(self.out), self.out.numel(), _stream())
+        return self.out
+
+    def parse(self, host_buf):
+        """(total heap bytes, lengths int32 [H], heap view, fits) of an output buffer copied to the
+        host (numpy uint8 / pinned tensor).  ``fits`` False: the heap was larger than the buffer."""
+        raw = host_buf.numpy() if hasattr(host_buf, 'numpy') else np.asarray(host_buf)
+        total = int(raw[0:8].view(np.int64)[0])
+        status = int(raw[12:16].view(np.int32)[0])
+        H = self.shape[0]
+        lens = raw[16:16 + 4 * H].view(np.int32)
+        fits = status == 0 and self.heap_offset + total <= raw.size
+        return total, lens, raw[self.heap_offset:self.heap_offset + min(total, raw.size - self.heap_offset)], fits
+
+
+def rice_encode(data):
+    """uint8 / int16 / uint16 / int32 image (numpy or CUDA tensor) -> (heap uint8 numpy array,
+    lengths int32 [rows]): every row Rice-coded as fits_rcomp_byte / _short / fits_rcomp would
+    (uint16 counts are stored as int16 with BZERO 32768, as FITS does).  Feed them to
+    ``fitsio.write_compressed``.  Synchronises."""
+    t = _to_dev(data)
+    if t.dtype == torch.uint16:
+        t = (t.view(torch.int16) ^ torch.tensor(-32768, dtype=torch.int16, device=t.device))
+    if t.dtype not in (torch.uint8, torch.int16, torch.int32) or t.dim() != 2:
+        raise NotImplementedError('rice_encode: dtype {} / {} dimensions'.format(t.dtype, t.dim()))
+    enc = RiceEncoder(tuple(t.shape), t.element_size(), t.device)
+    host = enc.enqueue(t.contiguous()).cpu().numpy()
+    total, lens, heap, fits = enc.parse(host)
+    if not fits:
+        raise RuntimeError('rice_encode: output buffer too small')
+    return heap.copy(), lens.copy()
 
 
 def fits_encode(data, out=None):

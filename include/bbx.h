@@ -327,17 +327,50 @@ int bbx_nonlin_corr(float *img, int H, int W, int ysize_chan, int xsize_chan, co
 int bbx_fits_decode(const void *be, int bitpix, int unsigned16, size_t n, void *out, void *stream);
 int bbx_fits_encode(const void *in, int bitpix, int unsigned16, size_t n, void *out_be, void *stream);
 
-/* Tile-compressed images (.fits.fz, ZCMPTYPE 'RICE_1', 16-bit pixels: ZBITPIX 16, BYTEPIX 2,
- * BLOCKSIZE 32, row tiles) -- what read_hdulist (blackbox.py:1451; astropy / CFITSIO on the host
- * in the reference) unpacks for every raw frame.  heap: the binary table's heap (device,
- * heap_bytes); offs / lens: device arrays, one entry per tile = byte offset into the heap and
- * compressed length (the COMPRESSED_DATA column's descriptors); ntiles tiles of nx pixels, tile t
- * = row t of out.  unsigned16 != 0: stored int16 + BZERO 32768 -> uint16 counts.  status: device
- * int, zeroed by the call; afterwards bit 0 = a tile ran past its bytes, bit 1 = a descriptor
- * points outside the heap (the affected rows are undefined); read it after synchronising. */
+/* Tile-compressed images (.fits.fz, ZCMPTYPE 'RICE_1', BLOCKSIZE 32, row tiles, BYTEPIX 1 / 2 / 4)
+ * -- what read_hdulist (astropy / CFITSIO on the host in the reference) unpacks for every raw frame
+ * (blackbox.py:1451), for the fpacked bad-pixel mask mask_init reads (blackbox.py:4386-4398,
+ * Settings/set_blackbox.py:187-193) and for the fpacked reduced calibration frames master_prep
+ * lists (blackbox.py:4698-4730).  heap: the binary table's heap (device, heap_bytes); offs / lens:
+ * device arrays, one entry per tile = byte offset into the heap and compressed length (the
+ * COMPRESSED_DATA column's descriptors); ntiles tiles of nx pixels, tile t = row t of out (uint8 /
+ * int16 / int32 as BYTEPIX says).  flip_sign != 0: the sign bit of every pixel is inverted (BYTEPIX
+ * 2 with BZERO 32768: stored int16 -> uint16 counts).  status: device int, zeroed by the call;
+ * afterwards bit 0 = a tile ran past its bytes, bit 1 = a descriptor points outside the heap (the
+ * affected rows are undefined); read it after synchronising.  No byte outside the heap is read. */
+int bbx_rice_decode(const void *heap, size_t heap_bytes, const long long *offs, const int *lens,
+                    int ntiles, int nx, int blocksize, int bytepix, int flip_sign, void *out,
+                    int *status, void *stream);
+/* BYTEPIX 2 shorthand (raw frames) */
 int bbx_rice_decode16(const void *heap, size_t heap_bytes, const long long *offs, const int *lens,
                       int ntiles, int nx, int blocksize, int unsigned16, void *out, int *status,
                       void *stream);
+
+/* Float images in a tile-compressed file are stored as scaled integers (ZQUANTIZ): this turns
+ * the decoded int32 rows back into float32.  zscale / zzero: device float64 [ntiles] (the table's
+ * ZSCALE / ZZERO columns); dither 0 = NO_DITHER: q * zscale + zzero; 1 / 2 = SUBTRACTIVE_DITHER_1 /
+ * _2: (q - R[i] + 0.5) * zscale + zzero with R = rand10000 (device float32 [10000], the random
+ * sequence the FITS standard defines for this purpose), restarted per tile from ZDITHER0;
+ * dither 2: q == -2147483646 is an exact zero.  have_blank != 0: q == zblank -> NaN.
+ * Reference side: read_hdulist(..., dtype='float32') of a `fpack -q` file (blackbox.py:826-840). */
+int bbx_unquantize(const int32_t *q, int ntiles, int nx, const double *zscale, const double *zzero,
+                   const float *rand10000, int dither, int zdither0, int zblank, int have_blank,
+                   float *out, void *stream);
+
+/* The other direction, for the product the reference fpacks losslessly (`fpack -D -Y` of the
+ * uint8 mask, blackbox.py:826-827, 1990): img (device; ntiles rows of nx pixels of BYTEPIX 1 / 2 /
+ * 4 bytes) -> out (device):
+ *     [0:8)   int64  total heap bytes           [8:12) int32 ntiles
+ *     [12:16) int32  status (bit 0: the heap did not fit into out_bytes; the sizes are still valid)
+ *     [16 : 16 + 4 ntiles)  int32 compressed bytes of every tile (the descriptors of the
+ *                            COMPRESSED_DATA column; offsets = their running sum), padded to 16
+ *     then the heap: the tiles back to back, each the bytes fits_rcomp / _short / _byte produce.
+ * work >= bbx_rice_encode_work_bytes(ntiles, nx, bytepix); bbx_rice_encode_out_bytes is the
+ * out_bytes that always fits; a smaller out (the mask compresses 50-fold) is fine, status tells. */
+size_t bbx_rice_encode_work_bytes(int ntiles, int nx, int bytepix);
+size_t bbx_rice_encode_out_bytes(int ntiles, int nx, int bytepix);
+int bbx_rice_encode(const void *img, int ntiles, int nx, int bytepix, void *work, size_t work_bytes,
+                    void *out, size_t out_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * small elementwise helpers for the drop-in functions used one step at a time

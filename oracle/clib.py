@@ -14,6 +14,8 @@ def lib():
         _lib = C.CDLL(_build.build())
         _lib.bbo_lower_median_f.restype = C.c_float
         _lib.bbo_detect_cosmics.restype = C.c_int
+        _lib.bbo_rice_encode.restype = C.c_long
+        _lib.bbo_rice_decode.restype = C.c_int
     return _lib
 
 
@@ -136,4 +138,25 @@ def stack_median(frames, scale=None):
     sc = None if scale is None else np.ascontiguousarray(scale, np.float32)
     out = np.empty(frames[0].shape, np.float32)
     lib().bbo_stack_median(ptrs, _p(sc), C.c_int(n), C.c_long(out.size), _p(out))
+    return out
+
+
+def rice_encode(a, bytepix):
+    """One tile (stored int8 / int16 / int32 pixels) -> coded bytes (bbo_rice_encode)."""
+    dt = {1: np.int8, 2: np.int16, 4: np.int32}[bytepix]
+    a = np.ascontiguousarray(np.asarray(a).astype(dt))
+    cap = a.size * bytepix + a.size // 8 + 64 + bytepix * 40
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib().bbo_rice_encode(_p(a), C.c_long(a.size), C.c_int(bytepix), _p(out), C.c_long(cap))
+    if n < 0:
+        raise ValueError('rice_encode: output buffer too small')
+    return out[:n].tobytes()
+
+
+def rice_decode(buf, nx, bytepix):
+    """Coded bytes -> nx stored pixels as uint8 / uint16 / uint32 (bbo_rice_decode)."""
+    c = np.frombuffer(bytes(buf), dtype=np.uint8)
+    out = np.empty(nx, dtype={1: np.uint8, 2: np.uint16, 4: np.uint32}[bytepix])
+    if lib().bbo_rice_decode(_p(c), C.c_long(c.size), C.c_long(nx), C.c_int(bytepix), _p(out)) != 0:
+        raise ValueError('rice_decode: the stream ends before the tile does')
     return out

@@ -479,3 +479,126 @@ BBO_API void bbo_stack_median(const float *const *frames, const float *scale, in
         free(buf);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Rice coding of image tiles (CFITSIO's ricecomp.c: fits_rcomp_byte / _short / fits_rcomp and
+ * the matching fits_rdecomp_*; FITS tiled-image convention).  Third-party code absent from
+ * /root/reference, restated from its published form -- PARITY UNPINNED (no fpack / CFITSIO here).
+ * The same statements as oracle/rice.py's pure-Python codec, which the tests hold it against;
+ * this copy exists so that whole frames can be coded in seconds.
+ *   bytepix 1 / 2 / 4: fsbits 3 / 4 / 5, fsmax 6 / 14 / 25, bbits 8 / 16 / 32; nblock = 32.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { uint8_t *out; long pos, cap; uint64_t acc; int n; int overflow; } bbo_bitw;
+
+static void bw_put(bbo_bitw *w, uint32_t value, int nbits)
+{
+    if (nbits == 0) return;
+    w->acc = (w->acc << nbits) | (nbits == 32 ? (uint64_t)value : ((uint64_t)value & ((1ull << nbits) - 1)));
+    w->n += nbits;
+    while (w->n >= 8) {
+        w->n -= 8;
+        if (w->pos < w->cap) w->out[w->pos] = (uint8_t)(w->acc >> w->n); else w->overflow = 1;
+        w->pos++;
+    }
+    w->acc &= (1ull << w->n) - 1;
+}
+
+/* a: nx stored pixels of width bytepix (native endian); returns the coded length, or -1 if cap is too small */
+BBO_API long bbo_rice_encode(const void *a, long nx, int bytepix, uint8_t *out, long cap)
+{
+    const int fsbits = bytepix == 1 ? 3 : bytepix == 2 ? 4 : 5;
+    const int fsmax = bytepix == 1 ? 6 : bytepix == 2 ? 14 : 25;
+    const int bbits = 8 * bytepix;
+    const int nblock = 32;
+    bbo_bitw w = { out, 0, cap, 0, 0, 0 };
+    uint32_t diff[32];
+#define PIX(i) (bytepix == 1 ? (int64_t)((const int8_t *)a)[i] : bytepix == 2 ? (int64_t)((const int16_t *)a)[i] \
+                                                                             : (int64_t)((const int32_t *)a)[i])
+    int64_t lastpix = PIX(0);
+    bw_put(&w, (uint32_t)lastpix, bbits);
+    for (long i = 0; i < nx; i += nblock) {
+        const int thisblock = (int)((nx - i) < nblock ? (nx - i) : nblock);
+        double pixelsum = 0.0;
+        for (int j = 0; j < thisblock; j++) {
+            const int64_t nextpix = PIX(i + j);
+            int64_t pdiff = nextpix - lastpix;
+            /* the difference is held in the pixel's own signed type: it wraps */
+            if (bytepix == 1) pdiff = (int8_t)pdiff;
+            else if (bytepix == 2) pdiff = (int16_t)pdiff;
+            else pdiff = (int32_t)pdiff;
+            diff[j] = (uint32_t)((pdiff < 0) ? ~((uint64_t)pdiff << 1) : ((uint64_t)pdiff << 1));
+            pixelsum += diff[j];
+            lastpix = nextpix;
+        }
+        double dpsum = (pixelsum - (thisblock / 2) - 1) / thisblock;
+        if (dpsum < 0) dpsum = 0.0;
+        uint32_t psum;
+        if (bytepix == 1) psum = ((uint8_t)(uint64_t)dpsum) >> 1;
+        else if (bytepix == 2) psum = ((uint16_t)(uint64_t)dpsum) >> 1;
+        else psum = ((uint32_t)(uint64_t)dpsum) >> 1;
+        int fs;
+        for (fs = 0; psum > 0; fs++) psum >>= 1;
+        if (fs >= fsmax) {
+            bw_put(&w, (uint32_t)(fsmax + 1), fsbits);
+            for (int j = 0; j < thisblock; j++) bw_put(&w, diff[j], bbits);
+        } else if (fs == 0 && pixelsum == 0) {
+            bw_put(&w, 0, fsbits);
+        } else {
+            bw_put(&w, (uint32_t)(fs + 1), fsbits);
+            for (int j = 0; j < thisblock; j++) {
+                const uint32_t v = diff[j];
+                uint32_t top = v >> fs;
+                while (top >= 24) { bw_put(&w, 0, 24); top -= 24; }
+                bw_put(&w, 1, (int)top + 1);
+                bw_put(&w, v & ((1u << fs) - 1u), fs);
+            }
+        }
+    }
+#undef PIX
+    if (w.n) { if (w.pos < w.cap) w.out[w.pos] = (uint8_t)(w.acc << (8 - w.n)); else w.overflow = 1; w.pos++; }
+    return w.overflow ? -1 : w.pos;
+}
+
+/* c: clen coded bytes -> out: nx pixels of width bytepix.  Returns 0, or -1 if the stream runs out. */
+BBO_API int bbo_rice_decode(const uint8_t *c, long clen, long nx, int bytepix, void *out)
+{
+    const int fsbits = bytepix == 1 ? 3 : bytepix == 2 ? 4 : 5;
+    const int fsmax = bytepix == 1 ? 6 : bytepix == 2 ? 14 : 25;
+    const int bbits = 8 * bytepix;
+    const uint32_t vmask = bytepix == 4 ? 0xffffffffu : ((1u << bbits) - 1u);
+    long pos = 0;
+    uint64_t acc = 0;
+    int n = 0;
+#define NEED(k) while (n < (k)) { if (pos >= clen) return -1; acc = (acc << 8) | c[pos++]; n += 8; }
+#define TAKE(dst, k) do { NEED(k); dst = (uint32_t)((acc >> (n - (k))) & ((k) == 32 ? 0xffffffffull : ((1ull << (k)) - 1))); n -= (k); } while (0)
+    uint32_t lastpix;
+    TAKE(lastpix, bbits);
+    for (long i = 0; i < nx; ) {
+        uint32_t code;
+        TAKE(code, fsbits);
+        const int fs = (int)code - 1;
+        const long imax = (i + 32 < nx) ? i + 32 : nx;
+        for (; i < imax; i++) {
+            uint32_t diff = 0;
+            if (fs < 0) {
+                diff = 0;
+            } else if (fs == fsmax) {
+                TAKE(diff, bbits);
+            } else {
+                uint32_t nzero = 0, bit;
+                for (;;) { TAKE(bit, 1); if (bit) break; nzero++; }
+                uint32_t low = 0;
+                if (fs > 0) TAKE(low, fs);
+                diff = (nzero << fs) | low;
+            }
+            diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
+            lastpix = (lastpix + diff) & vmask;
+            if (bytepix == 1) ((uint8_t *)out)[i] = (uint8_t)lastpix;
+            else if (bytepix == 2) ((uint16_t *)out)[i] = (uint16_t)lastpix;
+            else ((uint32_t *)out)[i] = lastpix;
+        }
+    }
+#undef NEED
+#undef TAKE
+    return 0;
+}

@@ -199,3 +199,71 @@ def test_master_prep_on_the_gpu_equals_the_reference(idx, site, small_bb):
             assert got[key] == want, key
     # a second call finds the master
     assert masters.master_prep(fits_master, shape, True, pick_alt=False, tel=g['tel']) == fits_master
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('idx', range(len(GOLD)))
+def test_master_prep_over_an_fpacked_night(idx, site, small_bb):
+    """What the reference's folders really hold (blackbox.py:826-840: every reduced frame and the
+    bad-pixel mask are fpacked): .fits.fz reduced frames -- float images quantised with subtractive
+    dithering, Rice-coded -- and an fpacked 8-bit mask.  The master must be the median of the
+    frames AS A READER SEES THEM (the oracle's un-quantised values)."""
+    from blackbox_b200 import fitsio, masters, set_bb, synth
+    from oracle import reduce as R, rice
+    g = GOLD[idx]
+    small_bb(g['ysize_chan'])
+    shape, night = _night(g)
+    seen = {}
+    for name, frame, hdr in night:
+        path = os.path.join(site, 'red', name) + '.fz'
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        _, back = rice.write_fz_f32(path, frame, hdr, q=16.0, dither=1, zdither0=1 + len(seen))
+        seen[os.path.basename(name).split('.fits')[0]] = (back, hdr)
+    bpm = None
+    if g['imgtype'] == 'flat':
+        bpm = synth.make_masters(g['tel'], g['seed'] + 1, shape)[2]
+        name = set_bb.get_par(set_bb.bad_pixel_mask, g['tel']).replace('bpm', 'bpm_' + g['filt'])
+        os.makedirs(os.path.dirname(name), exist_ok=True)
+        rice.write_fz_u8(name + '.fz', bpm)
+    fits_master = _fits_master(site, g)
+    assert masters.master_prep(fits_master, shape, True, pick_alt=False, tel=g['tel']) == fits_master
+    hdr, data, info = fitsio.read_primary(fits_master)
+    got = {k: v[0] for k, v in hdr.items()}
+    up = g['imgtype'].upper()
+    used = [seen[got['{}{}'.format(up, i + 1)]] for i in range(got['N' + up])]
+    assert [got['{}{}'.format(up, i + 1)] for i in range(got['N' + up])] == \
+        [g['header']['{}{}'.format(up, i + 1)] for i in range(g['header']['N' + up])]
+    frames = [f for f, _ in used]
+    if g['imgtype'] == 'bias':
+        want, _ = R.master_median(frames, imgtype='bias', tel=g['tel'])
+    else:
+        want, _ = R.master_flat_stats(frames, medsec=[h.get('MEDSEC') for _, h in used], bpm=bpm, tel=g['tel'])
+    assert np.array_equal(fitsio.to_native(data, info), want)
+
+
+@pytest.mark.gpu
+def test_master_prep_degrades_on_an_unreadable_frame(site, small_bb, caplog):
+    """A frame this reader cannot unpack (here: GZIP_1 tiles) must not raise out of master_prep: a
+    logged error and the nearest existing master, as the reference ends up for unusable input."""
+    import logging
+    from blackbox_b200 import fitsio, masters
+    from oracle import rice
+    g = GOLD[0]
+    small_bb(g['ysize_chan'])
+    shape, night = _night(g)
+    for k, (name, frame, hdr) in enumerate(night):
+        path = os.path.join(site, 'red', name) + '.fz'
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        rice.write_fz_f32(path, frame, hdr)
+        if k == 2:
+            raw = open(path, 'rb').read().replace(b"'RICE_1  '", b"'GZIP_1  '")
+            open(path, 'wb').write(raw)
+    fits_master = _fits_master(site, g)
+    yest = fits_master.replace('20240105', '20240104').replace('2024/01/05', '2024/01/04')
+    os.makedirs(os.path.dirname(yest), exist_ok=True)
+    fitsio.write_primary(yest, np.zeros((2, 2), np.float32), {})
+    with caplog.at_level(logging.ERROR, logger='blackbox_b200.masters'):
+        assert masters.master_prep(fits_master, shape, True, pick_alt=True, tel=g['tel']) == yest
+        assert masters.master_prep(fits_master, shape, True, pick_alt=False, tel=g['tel']) is None
+    assert any('unreadable input' in r.getMessage() for r in caplog.records)
+    assert not os.path.exists(fits_master)

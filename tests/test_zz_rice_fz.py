@@ -1,5 +1,7 @@
 """Tile-compressed (.fits.fz, RICE_1) raw frames: the oracle codec against hand-derived vectors,
 the host parser of blackbox_b200.fitsio, and the GPU decoder (bbx_rice_decode16)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -111,3 +113,262 @@ def test_gpu_decodes_what_the_oracle_encodes(tmp_path, shape):
     offs2[0] = heap.numel()
     with pytest.raises(ValueError):
         bbr.rice_decode(heap.cuda(), offs2, lens, info)
+
+
+# ---------------------------------------------------------------------------------------------
+# 8- and 32-bit tiles, quantised float images, and the encoder on the GPU
+# ---------------------------------------------------------------------------------------------
+def _int_rows(seed, nx, bytepix):
+    """Rows for every branch of the coder at a given pixel width (values as stored: signed)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = -(1 << (8 * bytepix - 1)), (1 << (8 * bytepix - 1))
+    rows = [np.full(nx, 7), rng.normal(100, 2, nx), rng.normal(0, 40, nx), rng.integers(lo, hi, nx),
+            np.where(rng.random(nx) < 0.01, 64, 0), np.cumsum(rng.integers(-3, 4, nx)),
+            np.where(np.arange(nx) % 97 < 50, lo, hi - 1),
+            np.concatenate([np.zeros(nx // 2), rng.integers(lo, hi, nx - nx // 2)]),
+            np.where(np.arange(nx) == nx // 3, hi - 1, 0)]            # one huge outlier in a quiet row
+    rows = np.clip(np.round(np.array(rows, dtype=np.float64)), lo, hi - 1).astype(np.int64)
+    return rows.astype({1: np.int8, 2: np.int16, 4: np.int32}[bytepix])
+
+
+def test_known_answers_for_bytes_and_ints():
+    from oracle import rice
+    # BYTEPIX 1: first pixel 8 bits, 3-bit block code.  32 zeros: 0x00 | 000 -> 00 00
+    assert rice.encode_tile(np.zeros(32, np.int8), 1) == bytes([0x00, 0x00])
+    # [0, 1]: mapped diffs 0, 2; FS 0 -> code 001 | 1 | 001 -> 0011 0010
+    assert rice.encode_tile(np.array([0, 1], np.int8), 1) == bytes([0x00, 0x32])
+    assert list(rice.decode_tile(bytes([0x00, 0x32]), 2, 1)) == [0, 1]
+    # a mask row: 40 zeros, one 64, zeros: block 0 all-zero (000), block 1 has diffs +64, -64 -> 128, 127
+    row = np.zeros(64, np.int8); row[40] = 64
+    buf = rice.encode_tile(row, 1)
+    assert list(rice.decode_tile(buf, 64, 1)) == list(row.astype(np.int64))
+    # BYTEPIX 4: first pixel 32 bits, 5-bit code.  [5, 5]: 00 00 00 05 | 00000 -> 5 bytes
+    assert rice.encode_tile(np.array([5, 5], np.int32), 4) == bytes([0, 0, 0, 5, 0])
+    # [0, -1]: mapped diffs 0, 1; (1 - 1 - 1)/2 < 0 -> FS 0 -> code 00001 | 1 | 01 -> 0000 1101
+    assert rice.encode_tile(np.array([0, -1], np.int32), 4) == bytes([0, 0, 0, 0, 0x0d])
+    assert list(rice.decode_tile(bytes([0, 0, 0, 0, 0x0d]), 2, 4)) == [0, 0xffffffff]
+
+
+@pytest.mark.parametrize('bytepix', [1, 2, 4])
+@pytest.mark.parametrize('nx', [1, 31, 32, 33, 700])
+def test_oracle_round_trip_all_widths(bytepix, nx):
+    from oracle import rice
+    for r in _int_rows(nx + bytepix, nx, bytepix):
+        buf = rice.encode_tile(r, bytepix)
+        want = r.astype(np.int64) & ((1 << (8 * bytepix)) - 1)
+        assert np.array_equal(rice.decode_tile(buf, nx, bytepix), want)
+
+
+def test_dither_table_is_the_published_sequence():
+    """Park-Miller minimal standard generator; the FITS standard's check value for the 10000th seed
+    is asserted inside both implementations."""
+    from blackbox_b200 import fitsio
+    from oracle import rice
+    a, b = fitsio.dither_random_table(), rice.random_table()
+    assert a.dtype == np.float32 and a.shape == (10000,) and np.array_equal(a, b)
+    assert a[0] == np.float32(16807.0 / 2147483647.0)
+
+
+def test_fz_files_of_masks_and_float_images_parse(tmp_path):
+    from blackbox_b200 import fitsio
+    from oracle import rice
+    rng = np.random.default_rng(4)
+    mask = np.where(rng.random((40, 300)) < 0.01, rng.choice([1, 2, 4, 8, 32, 64], (40, 300)), 0).astype(np.uint8)
+    ci = fitsio.read_compressed(rice.write_fz_u8(str(tmp_path / 'bpm.fits.fz'), mask, {'FILTER': 'q'}))
+    assert ci.info['bitpix'] == 8 and ci.info['bytepix'] == 1 and ci.info['shape'] == mask.shape
+    heap = np.asarray(ci.heap)
+    for r in range(mask.shape[0]):
+        got = rice.decode_tile(heap[ci.offsets[r]:ci.offsets[r] + ci.lengths[r]].tobytes(), mask.shape[1], 1)
+        assert np.array_equal(got.astype(np.uint8), mask[r])
+    img = rng.normal(300, 12, (20, 257)).astype(np.float32)
+    img[3, 7] = np.nan
+    for dither in (0, 1, 2):
+        if dither == 2:
+            img[5, 9] = 0.0
+        path, back = rice.write_fz_f32(str(tmp_path / 'red{}.fits.fz'.format(dither)), img, {'MEDSEC': 301.5},
+                                       dither=dither, zdither0=37)
+        ci = fitsio.read_compressed(path)
+        assert ci.info['bitpix'] == -32 and ci.info['bytepix'] == 4 and ci.info['zdither0'] == (37 if dither else 1)
+        assert ci.header['MEDSEC'][0] == 301.5 and ci.zscale.shape == (20,) and ci.zzero.dtype == np.float64
+        # quantisation error below half a step, NaN and exact zero survive
+        err = np.abs(back - img)
+        assert np.nanmax(err / ci.zscale[:, None]) <= 0.5 + 1e-6 and np.isnan(back[3, 7])
+        if dither == 2:
+            assert back[5, 9] == 0.0
+
+
+def test_write_compressed_round_trip_on_the_host(tmp_path):
+    """fitsio.write_compressed lays out tiles coded elsewhere (here: by the oracle) so that
+    read_compressed and the oracle decoder get the image back."""
+    from blackbox_b200 import fitsio
+    from oracle import rice
+    rng = np.random.default_rng(8)
+    mask = np.where(rng.random((33, 500)) < 0.02, 4, 0).astype(np.uint8)
+    tiles = [rice.encode_tile(mask[r], 1) for r in range(mask.shape[0])]
+    path = fitsio.write_compressed(str(tmp_path / 'x_mask.fits.fz'), np.frombuffer(b''.join(tiles), np.uint8),
+                                   [len(t) for t in tiles], mask.shape, 8, {'M-BPNUM': (3, 'number of bad pixels')})
+    ci = fitsio.read_compressed(path)
+    assert ci.header['M-BPNUM'][0] == 3 and ci.info['bitpix'] == 8
+    heap = np.asarray(ci.heap)
+    for r in range(mask.shape[0]):
+        got = rice.decode_tile(heap[ci.offsets[r]:ci.offsets[r] + ci.lengths[r]].tobytes(), mask.shape[1], 1)
+        assert np.array_equal(got.astype(np.uint8), mask[r])
+    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith('.part')]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bytepix', [1, 2, 4])
+@pytest.mark.parametrize('nx', [1, 33, 96, 1000, 1504])
+def test_gpu_codec_equals_the_oracle_byte_for_byte(bytepix, nx):
+    """bbx_rice_encode writes the very bytes the restated fits_rcomp_* writes, for every kind of
+    block; bbx_rice_decode reads them back; both for all three pixel widths."""
+    import torch
+    from blackbox_b200 import reduce as bbr
+    from oracle import rice
+    rows = np.concatenate([_int_rows(nx + 10 * s, nx, bytepix) for s in range(4)])
+    H = rows.shape[0]
+    heap, lens = bbr.rice_encode(rows.view(np.uint8) if bytepix == 1 else rows)
+    want = [rice.encode_tile(rows[r], bytepix) for r in range(H)]
+    assert list(lens) == [len(t) for t in want]
+    assert heap.tobytes() == b''.join(want)
+    offs = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+    info = dict(shape=(H, nx), bitpix=8 * bytepix, bytepix=bytepix, bzero=0.0, bscale=1.0, blocksize=32)
+    got = bbr.rice_decode(torch.from_numpy(heap).cuda(), offs, lens.astype(np.int32), info)
+    assert np.array_equal(got.cpu().numpy().view(rows.dtype), rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dither', [0, 1, 2])
+def test_gpu_reads_fpacked_float_images(tmp_path, dither):
+    """read_fits_image on a quantised float image (what `fpack -q` leaves in the reference's red
+    folders): the oracle's un-quantised values bit for bit, NaN / exact-zero pixels included."""
+    from blackbox_b200 import reduce as bbr
+    from oracle import rice
+    rng = np.random.default_rng(21)
+    img = rng.normal(500, 20, (37, 12000 if dither == 1 else 333)).astype(np.float32)   # 12000: the dither sequence wraps
+    img[2, 5] = np.nan
+    img[4, 6] = 0.0
+    path, back = rice.write_fz_f32(str(tmp_path / 'f.fits.fz'), img, {'MEDSEC': 499.0}, dither=dither, zdither0=9990)
+    hdr, got = bbr.read_fits_image(path)
+    assert hdr['MEDSEC'] == 499.0 and got.dtype.is_floating_point
+    assert np.array_equal(got.cpu().numpy(), back, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_fullsize_mask_and_raw_frame_round_trip():
+    """Size-independent property at BASELINE's full size: encode -> decode is the identity for a
+    10560^2 mask and a 10600 x 12000 raw frame; sizes are what the bench moves over PCIe."""
+    import torch
+    from blackbox_b200 import reduce as bbr, synth
+    rng = np.random.default_rng(3)
+    mask = np.zeros((10560, 10560), np.uint8)
+    ys, xs = rng.integers(0, 10560, 200000), rng.integers(0, 10560, 200000)
+    mask[ys, xs] = rng.choice([1, 2, 4, 8, 64], 200000).astype(np.uint8)
+    mask[:20] |= 32; mask[-20:] |= 32; mask[:, :20] |= 32; mask[:, -20:] |= 32
+    heap, lens = bbr.rice_encode(mask)
+    assert heap.size < mask.size // 20
+    offs = np.concatenate(([0], np.cumsum(lens.astype(np.int64))[:-1]))
+    info = dict(shape=mask.shape, bitpix=8, bytepix=1, bzero=0.0, bscale=1.0, blocksize=32)
+    got = bbr.rice_decode(torch.from_numpy(heap).cuda(), offs, lens, info)
+    assert torch.equal(got.cpu(), torch.from_numpy(mask))
+    del got
+    raw = synth.make_raw('BG3', 4001)[0]
+    heap, lens = bbr.rice_encode(raw)
+    assert heap.size < raw.size * 2 * 0.45
+    offs = np.concatenate(([0], np.cumsum(lens.astype(np.int64))[:-1]))
+    info = dict(shape=raw.shape, bitpix=16, bytepix=2, bzero=32768.0, bscale=1.0, blocksize=32)
+    got = bbr.rice_decode(torch.from_numpy(heap).cuda(), offs, lens, info)
+    assert got.dtype == torch.uint16 and np.array_equal(got.cpu().numpy(), raw)
+
+
+@pytest.mark.gpu
+def test_mask_init_reads_an_fpacked_bad_pixel_mask(tmp_path, small_bb, monkeypatch):
+    """The reference's bad-pixel masks are .fits.fz (Settings/set_blackbox.py:187-193): mask_init finds
+    the fpacked file through already_exists and decodes it on the GPU."""
+    from blackbox_b200 import reduce as bbr, set_bb
+    from oracle import reduce as R, rice
+    small_bb(96, 132)
+    rng = np.random.default_rng(12)
+    data = rng.normal(300, 10, (192, 1056)).astype(np.float32)
+    data[50:54, 100:104] = 3e5
+    bpm = np.zeros(data.shape, np.uint8)
+    bpm[rng.random(data.shape) < 0.003] = 1
+    bpm[:4] = 32; bpm[-4:] = 32
+    rice.write_fz_u8(str(tmp_path / 'BG3_bpm_q_0p2.fits.fz'), bpm)
+    monkeypatch.setattr(set_bb, 'bad_pixel_mask', {'BG3': str(tmp_path / 'BG3_bpm_0p2.fits.fz')})
+    bbr._bpm_registry.clear()
+    bbr.tel = 'BG3'
+    hdr = {'BIASM{}'.format(i + 1): 3200.0 for i in range(16)}
+    mask_o, _ = R.mask_init(data.copy(), dict(hdr), bpm, 'object', tel='BG3')
+    mask_g, _ = bbr.mask_init(data.copy(), dict(hdr), 'q', 'object')
+    assert np.array_equal(mask_g, mask_o) and (mask_g & 32).any() and (mask_g & 1).any()
+
+
+@pytest.mark.gpu
+def test_run_host_with_fpacked_frames_in_and_rice_coded_mask_out(tmp_path, small_bb):
+    """BatchReducer.run_host fed with .fits.fz raw frames (CompressedImage) and asked for the mask as
+    the reference's fpacked product: image and (decoded) mask equal the plain path bit for bit; the
+    mask file written from the device's bytes reads back through the oracle."""
+    import torch
+    from blackbox_b200 import fitsio, reduce as bbr, set_bb, synth
+    from blackbox_b200.pipeline import BatchReducer
+    from oracle import rice
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    shape = (2 * ysc, 8 * set_bb.xsize_chan)
+    mbias, mflat, bpm = synth.make_masters(tel, 43, shape)
+    coeffs = synth.make_xtalk(44)[3]
+    raws = []
+    for seed in (42, 43, 44, 45, 46):
+        raw = synth.make_raw(tel, seed, nstars=100, ncosmics=60)[0]
+        raw[40:46, 2000:2006] = 65535
+        raws.append(raw)
+    batch = BatchReducer(tel, raws[0].shape, depth=3, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=3)
+    plain_in = [torch.from_numpy(r.view(np.int16)).view(torch.uint16).pin_memory() for r in raws]
+    imgs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in raws]
+    masks = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in raws]
+    want = batch.run_host(plain_in, imgs, masks, exptimes=[30.0 + k for k in range(len(raws))])
+    packed = []
+    for k, r in enumerate(raws):
+        path = rice.write_fz(str(tmp_path / 'raw{}.fits.fz'.format(k)), r, {'EXPTIME': 30.0 + k})
+        packed.append(fitsio.read_compressed(path, pinned=True))
+    imgs2 = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in raws]
+    nbytes = batch.mask_fz_bytes(1 << 20)
+    masks2 = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in raws]
+    for rep in range(2):
+        got = batch.run_host(packed, imgs2, masks2, mask_fz=True,
+                             exptimes=[float(p.header['EXPTIME'][0]) for p in packed])
+        for k in range(len(raws)):
+            assert torch.equal(imgs2[k], imgs[k]), (rep, k)
+            heap, lens = got[k].mask_fz
+            assert heap.size < shape[0] * shape[1] // 8
+            for row in (0, 7, shape[0] // 2, shape[0] - 1):
+                o = int(np.sum(lens[:row], dtype=np.int64))
+                dec = rice.decode_tile(heap[o:o + lens[row]].tobytes(), shape[1], 1).astype(np.uint8)
+                assert np.array_equal(dec, masks[k][row].numpy()), (rep, k, row)
+            assert got[k].header['NCOSMICS'] == want[k].header['NCOSMICS']
+            assert got[k].header_mask == want[k].header_mask
+    heap, lens = got[2].mask_fz
+    path = fitsio.write_compressed(str(tmp_path / 'f_mask.fits.fz'), heap, lens, shape, 8,
+                                   {k: (v, '') for k, v in got[2].header_mask.items()})
+    _, back = bbr.read_fits_image(path)
+    assert torch.equal(back.cpu(), masks[2])
+    # a corrupt frame is reported
+    bad = fitsio.read_compressed(str(tmp_path / 'raw0.fits.fz'), pinned=True)
+    bad.lengths[5] = 3
+    with pytest.raises(ValueError):
+        batch.run_host([bad], imgs2, masks2, mask_fz=True)
+
+
+@pytest.mark.parametrize('bytepix', [1, 2, 4])
+def test_c_copy_of_the_codec_equals_the_python_statement(bytepix):
+    """oracle/csrc/bbo.c holds the same coder in C (whole frames in seconds): same bytes, same pixels."""
+    from oracle import rice
+    for nx in (1, 32, 33, 700):
+        for r in _int_rows(nx + 3 * bytepix, nx, bytepix):
+            slow = rice.encode_tile(r, bytepix, fast=False)
+            assert rice.encode_tile(r, bytepix, fast=True) == slow
+            assert np.array_equal(rice.decode_tile(slow, nx, bytepix, fast=True),
+                                  rice.decode_tile(slow, nx, bytepix, fast=False))
+    with pytest.raises(ValueError):
+        rice.decode_tile(rice.encode_tile(np.arange(300) * 7, bytepix)[:-20], 300, bytepix, fast=True)
