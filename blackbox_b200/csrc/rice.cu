@@ -22,9 +22,9 @@
 // tile is a serial job: one thread per tile (a frame has 10600 of them), all 32 lanes of a warp
 // decoding, each its own tile.  What decides the speed is the dependent chain per pixel, so:
 //   * the stream is read through a 64-bit window (bit 63 = next bit), refilled 32 bits at a time
-//     from a REGISTER queue of two 16-byte chunks -- the chunk after the one in use is always
-//     already loaded, so no global-memory latency sits on the chain (round 1 loaded a word when
-//     the window ran dry and waited for it: 390 cycles per pixel);
+//     from a per-lane ring in shared memory that cp.async keeps 31 chunks ahead of the reader --
+//     no global-memory latency sits on the chain (round 1 loaded a word when the window ran dry
+//     and the whole warp waited for it: 390 cycles per pixel);
 //   * a pixel is decoded without branches: count-leading-zeros of the top 32 bits gives the unary
 //     part, two shifts the FS low bits; "all zero" and "raw" blocks are selects on the same
 //     values; only a code longer than 32 bits (a rare outlier) takes a side path;
@@ -45,60 +45,90 @@ template <> struct RiceP<4> { static constexpr int FSBITS = 5, FSMAX = 25, BBITS
 // ---------------------------------------------------------------------------------------------
 // decoder
 // ---------------------------------------------------------------------------------------------
+// Per-lane ring of compressed bytes in shared memory: RDEC_CHUNKS 16-byte chunks per lane, chunk c
+// of lane l at ring[c % RDEC_CHUNKS][l].  It is topped up with cp.async (global -> shared, no
+// register in between) once per 32-pixel block -- the one place where all lanes of the warp are at
+// the same point of the program -- and a block later the data are there: no global-memory latency
+// on the per-pixel chain.  (Round 1 loaded a word into a register when a lane's window ran dry;
+// with 32 lanes running dry at different pixels the warp waited for SOME lane's load at almost
+// every step: 390-800 cycles per pixel.)  A block consumes at most 9 chunks (see rice_block_bytes),
+// the ring is refilled to 31: what a block reads has always landed one block earlier.
+#define RDEC_CHUNKS 32
+
 struct RiceIn {
     const uint8_t *heap, *heap_end;
-    const uint8_t *next;         // address of the chunk to prefetch next (16-byte aligned)
-    uint4 cur, nxt;              // chunk in use, chunk after it
-    int widx;                    // next word of `cur`
+    const uint8_t *next;         // global address of the next chunk to fetch (16-byte aligned)
+    uint4 *ring;                 // this lane's column of the ring: chunk c at ring[(c % RDEC_CHUNKS) * 32]
+    uint32_t fetched;            // chunks requested so far
+    uint32_t rdw;                // index (in 32-bit words from the first chunk) of the word held in nw
+    uint32_t nw;                 // that word, read from the ring one step before it is needed
     unsigned long long win;      // bit 63 = next bit of the stream
     int have;                    // valid bits in win
     long long popped;            // bits handed to the window so far
 
-    // 16 bytes at an aligned address; bytes outside the heap read as 0xff (a one bit ends every
-    // unary run, so a corrupt tile cannot run away) and are never touched
-    __device__ __forceinline__ uint4 chunk(const uint8_t *a) const
+    // one chunk global -> ring; bytes outside the heap read as 0xff (a one bit ends every unary
+    // run, so a corrupt tile cannot run away) and are never touched
+    __device__ __forceinline__ void fetch()
     {
-        if (a >= heap && a + 16 <= heap_end) return __ldg(reinterpret_cast<const uint4 *>(a));
-        uint32_t w[4];
+        uint4 *dst = ring + (size_t)(fetched % RDEC_CHUNKS) * 32;
+        const uint8_t *a = next;
+        if (a >= heap && a + 16 <= heap_end) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(a) : "memory");
+        } else {
+            uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t v = 0;
+            for (int i = 0; i < 4; i++) {
+                uint32_t v = 0;
 #pragma unroll
-            for (int k = 3; k >= 0; k--) {
-                const uint8_t *b = a + 4 * i + k;
-                v = (v << 8) | ((b >= heap && b < heap_end) ? (uint32_t)__ldg(b) : 0xffu);
+                for (int k = 3; k >= 0; k--) {
+                    const uint8_t *b = a + 4 * i + k;
+                    v = (v << 8) | ((b >= heap && b < heap_end) ? (uint32_t)__ldg(b) : 0xffu);
+                }
+                w[i] = v;
             }
-            w[i] = v;
+            *dst = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+        next += 16; fetched++;
+    }
+    __device__ __forceinline__ void landed() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
+    // refill the ring up to RDEC_CHUNKS - 1 chunks ahead of the chunk being read
+    __device__ __forceinline__ void top_up()
+    {
+        const uint32_t want = (rdw >> 2) + (RDEC_CHUNKS - 1);
+        while (fetched < want) fetch();
+    }
+    __device__ __forceinline__ uint32_t ring_word(uint32_t wi) const
+    {
+        const uint32_t *c = reinterpret_cast<const uint32_t *>(ring + (size_t)((wi >> 2) % RDEC_CHUNKS) * 32);
+        return c[wi & 3];
     }
     __device__ __forceinline__ void open(const uint8_t *start)
     {
         const uintptr_t s = (uintptr_t)start;
-        const uint8_t *a = reinterpret_cast<const uint8_t *>(s & ~(uintptr_t)15);
-        cur = chunk(a);
-        nxt = chunk(a + 16);
-        next = a + 32;
-        widx = (int)((s & 15) >> 2);
+        next = reinterpret_cast<const uint8_t *>(s & ~(uintptr_t)15);
+        fetched = 0;
+        rdw = (uint32_t)((s & 15) >> 2);
+        top_up();
+        landed();
+        nw = ring_word(rdw);
         win = 0; have = 0; popped = 0;
         refill();
         const int skip = (int)(s & 3) * 8;            // bytes of the first word in front of the tile
         win <<= skip; have -= skip; popped -= skip;
         refill();
     }
-    __device__ __forceinline__ uint32_t word()
-    {
-        uint32_t w = widx == 0 ? cur.x : widx == 1 ? cur.y : widx == 2 ? cur.z : cur.w;
-        w = __byte_perm(w, 0, 0x0123);                // big-endian bit order
-        if (++widx == 4) { cur = nxt; nxt = chunk(next); next += 16; widx = 0; }
-        return w;
-    }
+    // Branch-free: every lane runs the same instructions whether or not its window needs a word
+    // (lanes run dry at different pixels; a branch here would split the warp at every step).
     __device__ __forceinline__ void refill()
     {
-        if (have <= 32) {
-            win |= (unsigned long long)word() << (32 - have);
-            have += 32; popped += 32;
-        }
+        const bool need = have <= 32;
+        const unsigned long long add = (unsigned long long)__byte_perm(nw, 0, 0x0123) << ((32 - have) & 63);   // big-endian bit order
+        win |= need ? add : 0ull;
+        have += need ? 32 : 0;
+        popped += need ? 32 : 0;
+        rdw += need ? 1u : 0u;
+        nw = ring_word(rdw);                          // needed one refill later at the earliest
     }
     __device__ __forceinline__ void drop(int n) { win <<= n; have -= n; }              // n in [0, 32]
     __device__ __forceinline__ uint32_t take(int n)                                    // n in [1, 32]
@@ -120,11 +150,13 @@ rice_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const lo
     typedef RiceP<BP> P;
     constexpr int G = 16 / BP;                                  // pixels per 16-byte store
     constexpr uint32_t VMASK = BP == 4 ? 0xffffffffu : ((1u << (P::BBITS & 31)) - 1u);
+    __shared__ uint4 ring[RDEC_CHUNKS][32];
     const int tile = blockIdx.x * 32 + threadIdx.x;
     if (tile >= ntiles) return;
 
     RiceIn r;
     r.heap = heap; r.heap_end = heap + heap_bytes;
+    r.ring = &ring[0][threadIdx.x];
     const long long o = offs[tile];
     const int n = lens[tile];
     if (o < 0 || n < BP + 1 || (unsigned long long)o + (unsigned long long)n > heap_bytes) {
@@ -137,6 +169,8 @@ rice_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const lo
 
     for (int i = 0; i < nx; i += RICE_BLOCK) {
         const int nthis = min(RICE_BLOCK, nx - i);
+        r.landed();                                             // what the last block asked for is there
+        r.top_up();                                             // ask for what the next blocks will read
         r.refill();
         const int fs = (int)r.take(P::FSBITS) - 1;
         const bool raw = fs == P::FSMAX, zero = fs < 0;
@@ -159,9 +193,10 @@ rice_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const lo
                         diff = raw ? (top >> (32 - P::BBITS)) : zero ? 0u : (((uint32_t)z << fsn) | low);
                         r.drop(len);
                     } else {
-                        // a code longer than 32 bits: count the zeros across refills, then the low bits
+                        // a code longer than 32 bits: count the zeros across refills, then the low
+                        // bits.  (Bounded by the ring: a valid block never needs more than 9 chunks.)
                         uint32_t nz = 0;
-                        for (;;) {
+                        for (int guard = 0; guard < 64; guard++) {
                             r.refill();
                             if (r.win == 0) { nz += r.have; r.have = 0; continue; }
                             const int zz = __clzll((long long)r.win);

@@ -332,12 +332,13 @@ def combine_files(file_list, data_shape, imgtype, filt, nwindow, tel):
     ra, dec = [], []
     up = imgtype.upper()
     for i, name in enumerate(file_list):
-        hdr, data, info = fitsio.read_primary(name, pinned=True)
-        if info['shape'] != tuple(data_shape):
-            raise ValueError('{}: shape {} instead of {}'.format(name, info['shape'], tuple(data_shape)))
-        frames.append(R.fits_decode(data.to(dev, non_blocking=True), info))
-        val = {k: v[0] for k, v in hdr.items()}
-        com = {k: v[1] for k, v in hdr.items()}
+        # plain or fpacked (the reference's red_dir holds .fits.fz: Rice-coded, float images
+        # quantised; blackbox.py:4698-4730 lists '*.fits*'): decoded on the GPU either way
+        val, frame = R.read_fits_image(name, dtype=torch.float32)
+        com = read_header(name)[1]
+        if tuple(frame.shape) != tuple(data_shape):
+            raise ValueError('{}: shape {} instead of {}'.format(name, tuple(frame.shape), tuple(data_shape)))
+        frames.append(frame)
         if imgtype == 'flat':
             medsec.append(val.get('MEDSEC'))
             if 'RA' in val and 'DEC' in val:

@@ -89,6 +89,8 @@ class FramePipeline:
         self.chan_med = torch.zeros(self.geom.nchans, dtype=torch.float32, device=dev)
         self._cm_work = (torch.empty(R.query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=dev)
                          if self.fill_edge else None)
+        # optional: the mask also leaves stage B Rice-coded (BatchReducer.run_host(mask_fz=True))
+        self.mask_encoder = None
         self._ev_a = torch.cuda.Event()
         self._ev_b = torch.cuda.Event()
         self._raw = None
@@ -222,11 +224,11 @@ class FramePipeline:
         if dense_morph or lac_mode != R.LAC_LAZY:
             key = None                                   # the rare redo path stays eager
 
-        def run(name, fn):
+        def run(name, fn, extra=()):
             if key is None:
                 fn()
             else:
-                self._run(name, key, fn)
+                self._run(name, key + tuple(extra), fn)
 
         run('apply', lambda: R.apply_enqueue(
             raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias, mflat=self.mflat,
@@ -272,6 +274,10 @@ class FramePipeline:
                 call('bbx_fill_edge', R._ptr(out_img), R._ptr(out_mask), RH, RW, ysc, xsc,
                      int(get_par(set_bb.mask_value, tel)['edge']), R._ptr(self.chan_med), R._stream())
             run('edge_fill', edge)
+        if self.mask_encoder is not None:
+            # the reference's mask product is the losslessly fpacked uint8 image (blackbox.py:826-827)
+            enc = self.mask_encoder
+            run('mask_fz', lambda: enc.enqueue(out_mask), extra=(enc.out.data_ptr(), enc.work.data_ptr()))
         run('status', status)
 
     def stage_b_enqueue(self, raw_t, out_img, out_mask, exptime=None):
@@ -501,6 +507,8 @@ class BatchReducer:
                 if m.dtype != torch.uint8 or m.numel() != want or want < self.mask_fz_bytes(0) + 16:
                     raise ValueError('mask_fz: host mask buffers must be equal-sized pinned uint8 buffers of at '
                                      'least mask_fz_bytes(0) + 16 bytes')
+        for j, p in enumerate(self.pipes):
+            p.mask_encoder = self._fz_out[j] if mask_fz else None
         results = [None] * n
         caller = torch.cuda.current_stream()
         for s in set(self.streams + self.hi_streams) | {self._s_in, self._s_out}:
@@ -516,7 +524,7 @@ class BatchReducer:
                     call('bbx_fits_encode', R._ptr(img), -32, 0, img.numel(), R._ptr(img), R._stream())
                 host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
                 if mask_fz:
-                    host_masks[k % nm].copy_(self._fz_out[j].enqueue(self._hbuf[j][2]), non_blocking=True)
+                    host_masks[k % nm].copy_(self._fz_out[j].out, non_blocking=True)     # coded at the end of stage B
                 else:
                     host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
                 self._ev_out[j].record()
