@@ -55,6 +55,7 @@ _SIGNATURES = {
     'bbx_mask_counts': [P, SZ, P, P],
     'bbx_xtalk': [P, P, I, I, I, I, P, BITS, P],
     'bbx_xtalk_variant': [P, P, I, I, I, I, P, BITS, I, P],
+    'bbx_xtalk_counts': [P, P, I, I, I, I, P, BITS, I, P, P],
     'bbx_stack_median': [P, P, I, SZ, I, P, I, P, P],
     'bbx_stack_clipped_median': [P, P, I, SZ, D, I, I, P, I, P, P],
     'bbx_lacosmic_work_bytes': [I, I],

@@ -71,6 +71,7 @@ struct SparseWork {
     uint8_t *flags;              // [N] per pixel: (iteration stamp << FLAG_BITS) | FLAG_*
     BgState *bg;
     unsigned int *bghist;        // [BG_BINS] pixels per float32 key inside the bracket
+    unsigned int *bgsample;      // [BG_SAMPLES] float32 keys of the strided sample (0xffffffff: not usable)
     unsigned int *listA[2], *listB, *listC0, *listC1, *listCR;
     unsigned int capA, capB, capC, capCR;
     SparseCounters *cnt;
@@ -96,7 +97,7 @@ size_t lac_sparse_work_bytes(int H, int W)
     sparse_caps(n, a, b, c, cr);
     return sp_align(n) + 2 * sp_align(4ull * a) + sp_align(4ull * b) + 2 * sp_align(4ull * c) + sp_align(4ull * cr) +
            sp_align(sizeof(SparseCounters)) + sp_align(sizeof(SelState)) + sp_align(sizeof(BgState)) +
-           sp_align(4ull * BG_BINS) + 512;
+           sp_align(4ull * BG_BINS) + sp_align(4ull * BG_SAMPLES) + 512;
 }
 
 static SparseWork carve_sparse(void *work, size_t n)
@@ -115,6 +116,7 @@ static SparseWork carve_sparse(void *work, size_t n)
     w.sel = (SelState *)p; p += sp_align(sizeof(SelState));
     w.bg = (BgState *)p; p += sp_align(sizeof(BgState));
     w.bghist = (unsigned int *)p; p += sp_align(4ull * BG_BINS);
+    w.bgsample = (unsigned int *)p; p += sp_align(4ull * BG_SAMPLES);
     w.background = (float *)p;
     return w;
 }
@@ -390,8 +392,26 @@ __device__ __forceinline__ void bg_find_bin(const unsigned int *hist, unsigned i
     __syncthreads();
 }
 
+// The sample is gathered by a kernel of its own, one pixel per thread over 32 CTAs: 65536 scattered
+// sector reads are a few microseconds spread over the chip and 50+ when one SM issues them all
+// (round 1: 79 us on one SM in front of every frame).
 __global__ void __launch_bounds__(1024)
-sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
+sp_bg_gather_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask, size_t n, SparseWork w)
+{
+    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= BG_SAMPLES) return;
+    const size_t i = j * stride;
+    unsigned int key = 0xffffffffu;
+    if (i < n && !(inmask && inmask[i])) {
+        const float v = img[i];
+        if (v == v) key = f32_key(v);                   // NaNs are left to the full-frame statistics
+    }
+    w.bgsample[j] = key;                                // (no finite float has the key 0xffffffff)
+}
+
+__global__ void __launch_bounds__(1024)
+sp_bg_sample_kernel(SparseWork w)
 {
     extern __shared__ unsigned int smp[];               // [BG_SAMPLES] float32 keys of the sample
     __shared__ unsigned int hist[2][BG_SEL_BINS];
@@ -401,19 +421,25 @@ sp_bg_sample_kernel(const float *__restrict__ img, const uint8_t *__restrict__ i
     if (t == 0) s_ns = 0;
     for (int i = t; i < 2 * BG_SEL_BINS; i += 1024) (&hist[0][0])[i] = 0;
     __syncthreads();
-    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
     {
-        // the top 11 key bits are the same for practically the whole sample of a sky-dominated
-        // frame: count runs per thread instead of hammering one shared-memory word
+        // 32 independent coalesced loads per thread, then: the top 11 key bits are the same for
+        // practically the whole sample of a sky-dominated frame -- count runs per thread instead
+        // of hammering one shared-memory word
+        unsigned int keys[BG_SAMPLES / 1024];
+#pragma unroll
+        for (int q = 0; q < (int)(BG_SAMPLES / 1024); q++) keys[q] = w.bgsample[q * 1024 + t];
         unsigned int run_bin = 0xffffffffu, run = 0;
-        for (size_t j = t; j < BG_SAMPLES; j += 1024) {
-            const size_t i = j * stride;
-            if (i >= n) break;
-            if (inmask && inmask[i]) continue;
-            const float v = img[i];
-            if (v != v) continue;                       // NaNs are left to the full-frame statistics
-            const unsigned int key = f32_key(v);
-            smp[atomicAdd(&s_ns, 1u)] = key;
+#pragma unroll
+        for (int q = 0; q < (int)(BG_SAMPLES / 1024); q++) {
+            const unsigned int key = keys[q];
+            // warp-aggregated append: one shared-memory atomic per warp instead of one per sample
+            const bool usable = key != 0xffffffffu;
+            const unsigned int vote = __ballot_sync(0xffffffffu, usable);
+            unsigned int base = 0;
+            if ((t & 31) == 0 && vote) base = atomicAdd(&s_ns, (unsigned int)__popc(vote));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!usable) continue;
+            smp[base + __popc(vote & ((1u << (t & 31)) - 1u))] = key;
             if ((key >> 21) == run_bin) { run++; continue; }
             if (run) atomicAdd(&hist[0][run_bin], run);
             run_bin = key >> 21; run = 1;
@@ -838,7 +864,8 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
         BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
         BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(unsigned int) * BG_SAMPLES)));
-        sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(img, inmask, n, w);
+        sp_bg_gather_kernel<<<BG_SAMPLES / 1024, 1024, 0, st>>>(img, inmask, n, w);
+        sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(w);
     }
     sp_init_kernel<<<1, 32, 0, st>>>(info, INFO_NCR + niter, w.cnt, with_background ? 1u : 0u);
     BBX_CHECK_LAUNCH("sparse_begin");

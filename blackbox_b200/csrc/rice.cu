@@ -60,8 +60,8 @@ struct RiceIn {
     const uint8_t *next;         // global address of the next chunk to fetch (16-byte aligned)
     uint4 *ring;                 // this lane's column of the ring: chunk c at ring[(c % RDEC_CHUNKS) * 32]
     uint32_t fetched;            // chunks requested so far
-    uint32_t rdw;                // index (in 32-bit words from the first chunk) of the word held in nw
-    uint32_t nw;                 // that word, read from the ring one step before it is needed
+    uint32_t rdw;                // index (in 32-bit words from the first chunk) of the word held in w0
+    uint32_t w0, w1;             // words rdw and rdw + 1, read from the ring well before they are needed
     unsigned long long win;      // bit 63 = next bit of the stream
     int have;                    // valid bits in win
     long long popped;            // bits handed to the window so far
@@ -111,7 +111,8 @@ struct RiceIn {
         rdw = (uint32_t)((s & 15) >> 2);
         top_up();
         landed();
-        nw = ring_word(rdw);
+        w0 = ring_word(rdw);
+        w1 = ring_word(rdw + 1);
         win = 0; have = 0; popped = 0;
         refill();
         const int skip = (int)(s & 3) * 8;            // bytes of the first word in front of the tile
@@ -119,16 +120,20 @@ struct RiceIn {
         refill();
     }
     // Branch-free: every lane runs the same instructions whether or not its window needs a word
-    // (lanes run dry at different pixels; a branch here would split the warp at every step).
+    // (lanes run dry at different pixels; a branch here would split the warp at every step).  The
+    // shared-memory read is kept OFF the dependent chain window -> code length -> window: the word
+    // that goes into the window was read two refills ago (w0), the read issued here (w1) is only
+    // moved between registers at the next step.
     __device__ __forceinline__ void refill()
     {
         const bool need = have <= 32;
-        const unsigned long long add = (unsigned long long)__byte_perm(nw, 0, 0x0123) << ((32 - have) & 63);   // big-endian bit order
+        const unsigned long long add = (unsigned long long)__byte_perm(w0, 0, 0x0123) << ((32 - have) & 63);   // big-endian bit order
         win |= need ? add : 0ull;
         have += need ? 32 : 0;
         popped += need ? 32 : 0;
         rdw += need ? 1u : 0u;
-        nw = ring_word(rdw);                          // needed one refill later at the earliest
+        w0 = need ? w1 : w0;
+        w1 = ring_word(rdw + 1);
     }
     __device__ __forceinline__ void drop(int n) { win <<= n; have -= n; }              // n in [0, 32]
     __device__ __forceinline__ uint32_t take(int n)                                    // n in [1, 32]
@@ -175,53 +180,50 @@ rice_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const lo
         const int fs = (int)r.take(P::FSBITS) - 1;
         const bool raw = fs == P::FSMAX, zero = fs < 0;
         const int fsn = max(fs, 0);
-#pragma unroll 1
-        for (int g = 0; g < RICE_BLOCK; g += G) {
-            if (g >= nthis) break;
-            uint32_t pw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int k = 0; k < G; k++) {
-                if (g + k < nthis) {
-                    r.refill();                                 // at least 33 bits in the window
-                    const uint32_t top = (uint32_t)(r.win >> 32);
-                    const int z = __clz(top);                   // 32 if the top half is all zeros
-                    const int len = raw ? P::BBITS : zero ? 0 : z + 1 + fsn;
-                    uint32_t diff;
-                    if (len <= 32) {
-                        const unsigned long long rest = r.win << (z + 1);
-                        const uint32_t low = (uint32_t)((rest >> 1) >> (63 - fsn));       // fs = 0: nothing
-                        diff = raw ? (top >> (32 - P::BBITS)) : zero ? 0u : (((uint32_t)z << fsn) | low);
-                        r.drop(len);
-                    } else {
-                        // a code longer than 32 bits: count the zeros across refills, then the low
-                        // bits.  (Bounded by the ring: a valid block never needs more than 9 chunks.)
-                        uint32_t nz = 0;
-                        for (int guard = 0; guard < 64; guard++) {
-                            r.refill();
-                            if (r.win == 0) { nz += r.have; r.have = 0; continue; }
-                            const int zz = __clzll((long long)r.win);
-                            nz += zz;
-                            r.win = (r.win << zz) << 1; r.have -= zz + 1;
-                            break;
-                        }
-                        r.refill();
-                        diff = nz << fsn;
-                        if (fsn > 0) diff |= r.take(fsn);
-                    }
-                    diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
-                    lastpix = (lastpix + diff) & VMASK;
-                    uint32_t v = lastpix;
-                    if (FLIP) v ^= 1u << (P::BBITS - 1);
-                    pw[(k * BP) >> 2] |= v << (8 * ((k * BP) & 3));
-                }
-            }
-            if (vec_ok && g + G <= nthis) {
-                *reinterpret_cast<uint4 *>(row + i + g) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        // one pixel: window -> difference -> pixel value
+        auto pixel = [&]() -> uint32_t {
+            r.refill();                                         // at least 33 bits in the window
+            const uint32_t top = (uint32_t)(r.win >> 32);
+            const int z = __clz(top);                           // 32 if the top half is all zeros
+            const int len = raw ? P::BBITS : zero ? 0 : z + 1 + fsn;
+            uint32_t diff;
+            if (len <= 32) {
+                const unsigned long long rest = r.win << (z + 1);
+                const uint32_t low = (uint32_t)((rest >> 1) >> (63 - fsn));               // fs = 0: nothing
+                diff = raw ? (top >> (32 - P::BBITS)) : zero ? 0u : (((uint32_t)z << fsn) | low);
+                r.drop(len);
             } else {
-#pragma unroll
-                for (int k = 0; k < G; k++)
-                    if (g + k < nthis) row[i + g + k] = (typename P::T)(pw[(k * BP) >> 2] >> (8 * ((k * BP) & 3)));
+                // a code longer than 32 bits: count the zeros across refills, then the low bits.
+                // (Bounded by the ring: a valid block never needs more than 9 chunks.)
+                uint32_t nz = 0;
+                for (int guard = 0; guard < 64; guard++) {
+                    r.refill();
+                    if (r.win == 0) { nz += r.have; r.have = 0; continue; }
+                    const int zz = __clzll((long long)r.win);
+                    nz += zz;
+                    r.win = (r.win << zz) << 1; r.have -= zz + 1;
+                    break;
+                }
+                r.refill();
+                diff = nz << fsn;
+                if (fsn > 0) diff |= r.take(fsn);
             }
+            diff = (diff & 1u) ? ~(diff >> 1) : (diff >> 1);
+            lastpix = (lastpix + diff) & VMASK;
+            return FLIP ? (lastpix ^ (1u << (P::BBITS - 1))) : lastpix;
+        };
+        if (nthis == RICE_BLOCK && vec_ok) {
+            // a whole block, rows 16-byte aligned: no per-pixel bookkeeping, 16-byte stores
+#pragma unroll 1
+            for (int g = 0; g < RICE_BLOCK; g += G) {
+                uint32_t pw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int k = 0; k < G; k++) pw[(k * BP) >> 2] |= pixel() << (8 * ((k * BP) & 3));
+                *reinterpret_cast<uint4 *>(row + i + g) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < nthis; k++) row[i + k] = (typename P::T)pixel();
         }
     }
     // bits consumed beyond the tile's own bytes: a truncated or corrupt tile

@@ -16,6 +16,17 @@
 // shared memory (16 + 4 live doubles: ~64 registers, 6+ CTAs per SM hide the loads of the other
 // CTAs behind the FP64 work), and the tile goes back with 128-bit stores.
 // xtalk_kernel<PX>: generic fallback (any width / alignment), registers only.
+//
+// xtalk_tma_kernel (what bbx_xtalk runs when the layout allows): the same tile walk as a
+// PERSISTENT kernel with asynchronous staging.  The image is described to the TMA unit as a 3-D
+// tensor (x within channel, channel column, row), so ONE cp.async.bulk.tensor box {BX, 8, 1} brings
+// the 8 bottom channels of a tile row into shared memory and a second one the 8 mirrored top
+// channels (8 KB per tile, no thread touches an address); a 4-stage mbarrier ring keeps the loads
+// of tile k+2 and the store of tile k-1 in flight while the 256 DFMAs per thread of tile k run;
+// results go back with cp.async.bulk.tensor stores straight from the stage.  The mask bytes of
+// tile k+1 wait in registers.  The kernel also counts the pixels per mask bit on its way (the
+// mask is final here: mask_header's M-*NUM, blackbox.py:4601-4620, cost no extra pass).
+#include <cuda.h>
 #include "bbx_common.cuh"
 
 struct XtalkCoef { double c[16][16]; };   // [victim][source] (the order the dot products walk), kernel parameter (constant bank)
@@ -180,26 +191,245 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// TMA path
+// --------------------------------------------------------------------------------------------
+#define XT_STAGES 4
+#define XT_THREADS 128
+
+__device__ __forceinline__ uint32_t xt_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xt_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(xt_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void xt_mbar_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(xt_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xt_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "XT_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XT_DONE;\n\t"
+        "bra XT_WAIT;\n\t"
+        "XT_DONE:\n\t}"
+        :: "r"(xt_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void xt_tma_load(void *dst, const CUtensorMap *map, int x, int ch, int row, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(xt_smem(dst)), "l"(map), "r"(x), "r"(ch), "r"(row), "r"(xt_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void xt_tma_store(const CUtensorMap *map, const void *src, int x, int ch, int row)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(map), "r"(xt_smem(src)), "r"(x), "r"(ch), "r"(row) : "memory");
+}
+
+// BX: tile positions per pass (120 divides the 1320 columns of a channel; 128 otherwise, the
+// last box of a row is then clipped by the TMA unit: zero fill on load, no write beyond the channel)
+template <int BX>
+__global__ void __launch_bounds__(XT_THREADS, 5)
+xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ mask, int W, int ysc, int xsc,
+                 XtalkCoef k, uint32_t bits_src_bad, uint32_t bit_edge, unsigned long long *__restrict__ counts)
+{
+    __shared__ __align__(128) float stage[XT_STAGES][16][BX];
+    __shared__ __align__(8) uint64_t full[XT_STAGES];
+    __shared__ unsigned int s_cnt[8];
+    const int p = threadIdx.x;
+    const int nxb = (xsc + BX - 1) / BX;
+    const long long ntiles = (long long)ysc * nxb;
+    if (p == 0) {
+#pragma unroll
+        for (int s = 0; s < XT_STAGES; s++) xt_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p < 8) s_cnt[p] = 0;
+    __syncthreads();
+
+    auto issue = [&](long long t, int s) {                       // thread 0: both boxes of tile t into stage s
+        const int ly = (int)(t / nxb), x0 = (int)(t - (long long)ly * nxb) * BX;
+        xt_mbar_expect(&full[s], 16u * BX * 4u);
+        xt_tma_load(&stage[s][0][0], &map, x0, 0, ly, &full[s]);
+        xt_tma_load(&stage[s][8][0], &map, x0, 0, ysc + (ysc - 1 - ly), &full[s]);
+    };
+    auto load_mask = [&](long long t, uint32_t (&mm)[4]) {       // the 16 mask bytes of position p of tile t
+        mm[0] = mm[1] = mm[2] = mm[3] = 0u;
+        if (t >= ntiles || mask == nullptr) return;
+        const int ly = (int)(t / nxb), x = (int)(t - (long long)ly * nxb) * BX + p;
+        if (p >= BX || x >= xsc) return;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
+            const uint32_t b = __ldg(mask + (size_t)row * W + (size_t)(c & 7) * xsc + x);
+            mm[c >> 2] |= b << (8 * (c & 3));
+        }
+    };
+
+    const long long first = blockIdx.x, step = gridDim.x;
+    if (p == 0) {
+        if (first < ntiles) issue(first, 0);
+        if (first + step < ntiles) issue(first + step, 1);
+    }
+    uint32_t mcur[4], mnext[4];
+    load_mask(first, mcur);
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int it = 0;
+    for (long long t = first; t < ntiles; t += step, it++) {
+        const int s = it % XT_STAGES;
+        if (p == 0) {
+            // the stage tile it+2 goes into was last used by tile it-2: its store has been read
+            // out of shared memory once at most one younger store group is pending
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (t + 2 * step < ntiles) issue(t + 2 * step, (it + 2) % XT_STAGES);
+        }
+        load_mask(t + step, mnext);                              // used in the next pass
+        xt_mbar_wait(&full[s], (uint32_t)(it / XT_STAGES) & 1u);
+        const int ly = (int)(t / nxb), x0 = (int)(t - (long long)ly * nxb) * BX;
+        if (p < BX && x0 + p < xsc) {
+            float (*tile)[BX] = stage[s];
+            double S[16];
+            uint32_t vic_ok = 0;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const float v = tile[c][p];
+                const uint32_t m = (mcur[c >> 2] >> (8 * (c & 3))) & 0xffu;
+                const bool ok = (v > 0.0f) && !(m & bits_src_bad);
+                const float sf = v * (ok ? 1.0f : 0.0f);
+                S[c] = (double)sf;
+                if (!(m & bit_edge)) vic_ok |= 1u << c;
+            }
+#pragma unroll
+            for (int vch = 0; vch < 16; vch++) {
+                const int same0 = (vch < 8) ? 0 : 8, other0 = 8 - same0;
+                // same-half sources first (quadrant q=0 / q=3), then the mirrored half
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int sidx = 0; sidx < 8; sidx++) a = fma(S[same0 + sidx], k.c[vch][same0 + sidx], a);
+#pragma unroll
+                for (int sidx = 0; sidx < 8; sidx++) b = fma(S[other0 + sidx], k.c[vch][other0 + sidx], b);
+                double corr = 0.0 + a;
+                corr = corr + b;
+                corr = corr * (((vic_ok >> vch) & 1u) ? 1.0 : 0.0);
+                tile[vch][p] = (float)((double)tile[vch][p] - corr);
+            }
+            if (counts) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const uint32_t pl = 0x01010101u << b;
+                    cnt[b] += __popc(mcur[0] & pl) + __popc(mcur[1] & pl) + __popc(mcur[2] & pl) + __popc(mcur[3] & pl);
+                }
+            }
+        }
+        // the stage now holds the corrected tile: hand it to the TMA unit
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (p == 0) {
+            xt_tma_store(&map, &stage[s][0][0], x0, 0, ly);
+            xt_tma_store(&map, &stage[s][8][0], x0, 0, ysc + (ysc - 1 - ly));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) mcur[i] = mnext[i];
+    }
+    if (p == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete before the CTA retires
+    if (counts) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int v = warp_sum(cnt[b]);
+            if ((p & 31) == 0 && v) atomicAdd(&s_cnt[b], (unsigned int)v);
+        }
+        __syncthreads();
+        if (p < 8 && s_cnt[p]) atomicAdd(&counts[p], (unsigned long long)s_cnt[p]);
+    }
+}
+
+typedef CUresult (*xt_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime (libbbx.so does not link libcuda)
+static xt_encode_fn xt_encoder(void)
+{
+    static xt_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (xt_encode_fn)sym;
+    }
+    return fn;
+}
+
+// 0 = launched; 1 = this layout / driver cannot take the TMA path (caller falls back); < 0 = error
+static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int ysc, int xsc, const XtalkCoef &k,
+                            uint32_t src_bad, uint32_t edge, unsigned long long *counts, cudaStream_t st)
+{
+    if (xsc % 4 != 0 || ((uintptr_t)img % 16) != 0 || W != 8 * xsc || H != 2 * ysc) return 1;
+    xt_encode_fn enc = xt_encoder();
+    if (!enc) return 1;
+    const int bx = (xsc % 120 == 0) ? 120 : 128;
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)xsc, 8, (cuuint64_t)H};
+    const cuuint64_t strides[2] = {(cuuint64_t)xsc * 4, (cuuint64_t)W * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, 8, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    if (counts) BBX_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned long long), st));
+    const long long ntiles = (long long)ysc * ((xsc + bx - 1) / bx);
+    long long want = (long long)BBX_SM_COUNT * 5;
+    const int blocks = (int)(ntiles < want ? ntiles : want);
+    if (bx == 120)
+        xtalk_tma_kernel<120><<<blocks, XT_THREADS, 0, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
+    else
+        xtalk_tma_kernel<128><<<blocks, XT_THREADS, 0, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
+    BBX_CHECK_LAUNCH("xtalk_tma_kernel");
+    return 0;
+}
+
 extern "C" int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                          const double *coeffs_h, const bbx_maskbits *bits, void *stream)
 {
-    return bbx_xtalk_variant(img, mask, H, W, ysize_chan, xsize_chan, coeffs_h, bits, 0, stream);
+    return bbx_xtalk_counts(img, mask, H, W, ysize_chan, xsize_chan, coeffs_h, bits, 0, nullptr, stream);
 }
 
-// variant 0: the kernel bbx_xtalk picks (tiled when the layout allows); 1 / 2 / 4: the generic
-// register-only kernel with that many pixels per thread and channel (parity tests, tools/xt_bench.py)
 extern "C" int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                                  const double *coeffs_h, const bbx_maskbits *bits, int variant, void *stream)
 {
+    return bbx_xtalk_counts(img, mask, H, W, ysize_chan, xsize_chan, coeffs_h, bits, variant, nullptr, stream);
+}
+
+// variant 0: the kernel bbx_xtalk picks (TMA-staged persistent kernel when the layout allows, else
+// the synchronous tile kernel, else the generic one); 3: the synchronous tile kernel; 1 / 2 / 4: the
+// generic register-only kernel with that many pixels per thread and channel (parity tests,
+// tools/xt_bench.py).  out_counts (device uint64 [8], may be null): pixels per mask bit of `mask`,
+// zeroed and filled by the call (by the crosstalk kernel itself on the TMA path).
+extern "C" int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                const double *coeffs_h, const bbx_maskbits *bits, int variant,
+                                unsigned long long *out_counts, void *stream)
+{
     BBX_REQUIRE(img && coeffs_h && bits, "bbx_xtalk: null argument");
-    BBX_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 4, "bbx_xtalk: variant %d", variant);
+    BBX_REQUIRE(variant >= 0 && variant <= 4, "bbx_xtalk: variant %d", variant);
     BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_xtalk: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
+    BBX_REQUIRE(out_counts == nullptr || mask != nullptr, "bbx_xtalk: mask counts asked for without a mask");
     XtalkCoef k;
     for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[v][s] = coeffs_h[s * 16 + v];
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
+    if (variant == 0) {
+        const int rc = xtalk_tma_launch(img, mask, H, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge, out_counts, st);
+        if (rc <= 0) return rc;
+    }
+    if (out_counts && bbx_mask_counts(mask, (size_t)H * W, out_counts, stream)) return -2;
     const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
-    if (px4 && variant == 0) {
+    if (px4 && (variant == 0 || variant == 3)) {
         const long long ngroups = (long long)ysize_chan * (xsize_chan / 4);
         const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
         BBX_REQUIRE(ntiles < 2147483647LL, "bbx_xtalk: frame too large");

@@ -254,14 +254,15 @@ class FramePipeline:
             run('lacosmic_finish', lac_finish)
 
         def tail():
-            if self.coeffs is not None:
-                R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel)
+            # the mask is final here (cosmic-ray bit set): the crosstalk kernel reads every mask byte
+            # anyway and counts the pixels per bit on its way (mask_header, blackbox.py:4601-4620)
+            R.xtalk_enqueue(out_img, out_mask, self.coeffs, tel, counts=self.st.mcounts)
 
         def status():
-            # the mask is final here (cosmic-ray bit set): per-bit pixel counts for mask_header,
-            # then the whole header block -- os_corr keywords, SATLEV, NOBJ-SAT, NCOSMICS, the
-            # status words of the morphology and of LACosmic -- in one copy into pinned memory
-            call('bbx_mask_counts', R._ptr(out_mask), out_mask.numel(), R._ptr(self.st.mcounts), R._stream())
+            # the whole header block -- os_corr keywords, SATLEV, NOBJ-SAT, NCOSMICS, the status words
+            # of the morphology and of LACosmic, the per-bit mask counts -- in one copy into pinned memory
+            if self.coeffs is None:
+                call('bbx_mask_counts', R._ptr(out_mask), out_mask.numel(), R._ptr(self.st.mcounts), R._stream())
             self.st.fetch_header_async()
 
         if self.coeffs is not None:

@@ -996,12 +996,15 @@ def read_crosstalk_file(crosstalk_file, nchans=16):
     return coeffs
 
 
-def xtalk_enqueue(img_t, mask_t, coeffs, tel_):
+def xtalk_enqueue(img_t, mask_t, coeffs, tel_, counts=None, variant=0):
+    """Enqueue the crosstalk correction.  ``counts`` (int64 [8] device tensor): also receives the
+    pixels per mask bit (the kernel sees every mask byte anyway).  ``variant``: 0 = the kernel
+    bbx_xtalk picks, 1..4 see include/bbx.h."""
     H, W = img_t.shape
     bits = _bits(tel_)
     c = np.ascontiguousarray(coeffs, dtype=np.float64)
-    call('bbx_xtalk', _ptr(img_t), _ptr(mask_t), H, W, H // 2, W // 8,
-         c.ctypes.data_as(C.c_void_p), C.byref(bits), _stream())
+    call('bbx_xtalk_counts', _ptr(img_t), _ptr(mask_t), H, W, H // 2, W // 8,
+         c.ctypes.data_as(C.c_void_p), C.byref(bits), int(variant), _ptr(counts), _stream())
 
 
 def xtalk_corr(data, crosstalk_file, data_mask=None):

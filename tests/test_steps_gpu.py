@@ -369,6 +369,48 @@ def test_xtalk_parity(with_mask, small_bb, tmp_path):
     assert np.abs(d_o - data).max() > 1.0          # the correction did something
 
 
+@pytest.mark.parametrize('shape', [(128, 1056), (2 * 77, 8 * 1320), (2 * 40, 8 * 660), (2 * 33, 8 * 100), (2 * 9, 8 * 30)])
+def test_xtalk_kernels_agree_and_count_the_mask(shape):
+    """Every crosstalk kernel -- the TMA-staged persistent one bbx_xtalk runs (boxes of 120 or 128
+    positions, clipped at the channel edge), the synchronous tile kernel, the generic ones -- gives
+    the same bits as the oracle class allows (> 99.99 % identical, 1e-6), and identical bits among
+    themselves; the per-bit mask counts taken on the way equal numpy's (blackbox.py:4601-4620)."""
+    import ctypes as C
+    import torch
+    from blackbox_b200 import reduce as bbr, set_bb, synth
+    from blackbox_b200._lib import call
+    from oracle import reduce as R
+    H, W = shape
+    saved = (set_bb.ysize_chan, set_bb.xsize_chan)
+    set_bb.ysize_chan, set_bb.xsize_chan = H // 2, W // 8
+    try:
+        rng = np.random.default_rng(H + W)
+        data = _rng_img(rng, shape, level=50.0)
+        data[rng.random(shape) < 0.01] += 60000.0
+        data[rng.random(shape) < 0.01] = -3.0
+        mask = rng.choice(np.array([0, 0, 0, 1, 2, 4, 8, 32, 64, 33, 12], np.uint8), size=shape)
+        coeffs = np.ascontiguousarray(synth.make_xtalk(11, amp=3e-4)[3], dtype=np.float64)
+        d_o = data.copy()
+        R.xtalk_corr(d_o, coeffs, mask.copy(), tel='BG3')
+        bits = bbr._bits('BG3')
+        m_t = torch.from_numpy(mask).cuda()
+        outs = {}
+        for variant in (0, 3, 4, 2, 1):
+            img = torch.from_numpy(data.copy()).cuda()
+            counts = torch.full((8,), -1, dtype=torch.int64, device='cuda')
+            call('bbx_xtalk_counts', bbr._ptr(img), bbr._ptr(m_t), H, W, H // 2, W // 8,
+                 coeffs.ctypes.data_as(C.c_void_p), C.byref(bits), variant, bbr._ptr(counts), bbr._stream())
+            outs[variant] = img.cpu().numpy()
+            assert counts.cpu().tolist() == [int(((mask >> b) & 1).sum()) for b in range(8)], variant
+        assert torch.equal(m_t.cpu(), torch.from_numpy(mask))
+        for variant, got in outs.items():
+            assert np.array_equal(got, outs[1]), variant
+        assert np.mean(outs[0] == d_o) > 0.9999
+        np.testing.assert_allclose(outs[0], d_o, rtol=1e-6, atol=0)
+    finally:
+        set_bb.ysize_chan, set_bb.xsize_chan = saved
+
+
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('n', [1, 2, 3, 15, 20, 33, 50, 64])
 def test_stack_median_bit_exact(n):
