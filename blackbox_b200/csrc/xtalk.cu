@@ -228,19 +228,37 @@ __device__ __forceinline__ void xt_tma_store(const CUtensorMap *map, const void 
                  :: "l"(map), "r"(xt_smem(src)), "r"(x), "r"(ch), "r"(row) : "memory");
 }
 
-// BX: tile positions per pass (120 divides the 1320 columns of a channel; 128 otherwise, the
-// last box of a row is then clipped by the TMA unit: zero fill on load, no write beyond the channel)
-template <int BX>
-__global__ void __launch_bounds__(XT_THREADS, 5)
-xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ mask, int W, int ysc, int xsc,
-                 XtalkCoef k, uint32_t bits_src_bad, uint32_t bit_edge, unsigned long long *__restrict__ counts)
+__device__ __forceinline__ void xt_tma_load2(void *dst, const CUtensorMap *map, int x, int row, uint64_t *bar)
 {
-    __shared__ __align__(128) float stage[XT_STAGES][16][BX];
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(xt_smem(dst)), "l"(map), "r"(x), "r"(row), "r"(xt_smem(bar)) : "memory");
+}
+
+// The kernel is bound by instruction issue (256 DFMAs per position plus everything around them:
+// the synchronous tile kernel spends ~900 instructions per position, 0.17 ms of issue time on 148
+// SMs), so the point of the TMA staging is as much the instructions it removes -- no address
+// arithmetic, no loads, no stores in the threads -- as the latency it hides.
+//   image: 3-D tensor map (x in channel, channel column, row), box {128, 8, 1}: two loads per tile
+//   mask:  2-D tensor map (x, row) of bytes (a channel is 1320 bytes wide: not a legal TMA stride),
+//          box {128, 1}: sixteen small loads per tile, all on the same mbarrier
+// A box that sticks out of its channel (the 11th of a 1320-wide channel) is clipped by the TMA
+// unit on the image side and simply reads the neighbouring channel's bytes on the mask side; the
+// threads beyond the channel edge sit the tile out.
+#define XT_BX 128
+struct XtStage { float img[16][XT_BX]; uint8_t msk[16][XT_BX]; };
+
+__global__ void __launch_bounds__(XT_THREADS, 5)
+xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap mmap, int have_mask,
+                 int ysc, int xsc, XtalkCoef k, uint32_t bits_src_bad, uint32_t bit_edge,
+                 unsigned long long *__restrict__ counts)
+{
+    extern __shared__ __align__(128) unsigned char xt_raw[];
+    XtStage *stage = reinterpret_cast<XtStage *>(xt_raw);
     __shared__ __align__(8) uint64_t full[XT_STAGES];
     __shared__ unsigned int s_cnt[8];
     const int p = threadIdx.x;
-    const int nxb = (xsc + BX - 1) / BX;
-    const long long ntiles = (long long)ysc * nxb;
+    const int nxb = (xsc + XT_BX - 1) / XT_BX;
+    const int ntiles = ysc * nxb;
     if (p == 0) {
 #pragma unroll
         for (int s = 0; s < XT_STAGES; s++) xt_mbar_init(&full[s], 1);
@@ -249,55 +267,56 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
     if (p < 8) s_cnt[p] = 0;
     __syncthreads();
 
-    auto issue = [&](long long t, int s) {                       // thread 0: both boxes of tile t into stage s
-        const int ly = (int)(t / nxb), x0 = (int)(t - (long long)ly * nxb) * BX;
-        xt_mbar_expect(&full[s], 16u * BX * 4u);
-        xt_tma_load(&stage[s][0][0], &map, x0, 0, ly, &full[s]);
-        xt_tma_load(&stage[s][8][0], &map, x0, 0, ysc + (ysc - 1 - ly), &full[s]);
-    };
-    auto load_mask = [&](long long t, uint32_t (&mm)[4]) {       // the 16 mask bytes of position p of tile t
-        mm[0] = mm[1] = mm[2] = mm[3] = 0u;
-        if (t >= ntiles || mask == nullptr) return;
-        const int ly = (int)(t / nxb), x = (int)(t - (long long)ly * nxb) * BX + p;
-        if (p >= BX || x >= xsc) return;
+    const uint32_t tile_bytes = 16u * XT_BX * 4u + (have_mask ? 16u * XT_BX : 0u);
+    auto issue = [&](int ly, int xb, int s) {                    // thread 0: every box of tile (ly, xb) into stage s
+        const int x0 = xb * XT_BX, top = ysc + (ysc - 1 - ly);
+        xt_mbar_expect(&full[s], tile_bytes);
+        xt_tma_load(&stage[s].img[0][0], &map, x0, 0, ly, &full[s]);
+        xt_tma_load(&stage[s].img[8][0], &map, x0, 0, top, &full[s]);
+        if (have_mask) {
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-            const int row = (c < 8) ? ly : (ysc + (ysc - 1 - ly));
-            const uint32_t b = __ldg(mask + (size_t)row * W + (size_t)(c & 7) * xsc + x);
-            mm[c >> 2] |= b << (8 * (c & 3));
+            for (int c = 0; c < 8; c++) {
+                xt_tma_load2(&stage[s].msk[c][0], &mmap, c * xsc + x0, ly, &full[s]);
+                xt_tma_load2(&stage[s].msk[8 + c][0], &mmap, c * xsc + x0, top, &full[s]);
+            }
         }
     };
-
-    const long long first = blockIdx.x, step = gridDim.x;
-    if (p == 0) {
-        if (first < ntiles) issue(first, 0);
-        if (first + step < ntiles) issue(first + step, 1);
-    }
-    uint32_t mcur[4], mnext[4];
-    load_mask(first, mcur);
+    // tile walk: t = blockIdx.x + i gridDim.x, kept as (row, box) without divisions in the loop
+    const int step = gridDim.x, dly = step / nxb, dxb = step - dly * nxb;
+    auto advance = [&](int &ly, int &xb) {
+        ly += dly; xb += dxb;
+        if (xb >= nxb) { xb -= nxb; ly++; }
+    };
+    int ly = (int)blockIdx.x / nxb, xb = (int)blockIdx.x - ly * nxb;       // current tile
+    int ly2 = ly, xb2 = xb;                                               // the tile two ahead (next to issue)
+    if (p == 0 && ly2 < ysc) issue(ly2, xb2, 0);
+    advance(ly2, xb2);
+    if (p == 0 && ly2 < ysc) issue(ly2, xb2, 1);
+    advance(ly2, xb2);
+    (void)ntiles;
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int it = 0;
-    for (long long t = first; t < ntiles; t += step, it++) {
+    for (int it = 0; ly < ysc; it++) {
         const int s = it % XT_STAGES;
         if (p == 0) {
             // the stage tile it+2 goes into was last used by tile it-2: its store has been read
             // out of shared memory once at most one younger store group is pending
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (t + 2 * step < ntiles) issue(t + 2 * step, (it + 2) % XT_STAGES);
+            if (ly2 < ysc) issue(ly2, xb2, (it + 2) % XT_STAGES);
         }
-        load_mask(t + step, mnext);                              // used in the next pass
+        advance(ly2, xb2);
         xt_mbar_wait(&full[s], (uint32_t)(it / XT_STAGES) & 1u);
-        const int ly = (int)(t / nxb), x0 = (int)(t - (long long)ly * nxb) * BX;
-        if (p < BX && x0 + p < xsc) {
-            float (*tile)[BX] = stage[s];
+        const int x0 = xb * XT_BX;
+        if (x0 + p < xsc) {
+            XtStage &st = stage[s];
             double S[16];
-            uint32_t vic_ok = 0;
+            uint32_t vic_ok = 0, mw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int c = 0; c < 16; c++) {
-                const float v = tile[c][p];
-                const uint32_t m = (mcur[c >> 2] >> (8 * (c & 3))) & 0xffu;
+                const float v = st.img[c][p];
+                const uint32_t m = have_mask ? (uint32_t)st.msk[c][p] : 0u;
+                mw[c >> 2] |= m << (8 * (c & 3));
                 const bool ok = (v > 0.0f) && !(m & bits_src_bad);
-                const float sf = v * (ok ? 1.0f : 0.0f);
+                const float sf = v * (ok ? 1.0f : 0.0f);        // the reference's data * mask (NaN stays NaN)
                 S[c] = (double)sf;
                 if (!(m & bit_edge)) vic_ok |= 1u << c;
             }
@@ -313,13 +332,13 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
                 double corr = 0.0 + a;
                 corr = corr + b;
                 corr = corr * (((vic_ok >> vch) & 1u) ? 1.0 : 0.0);
-                tile[vch][p] = (float)((double)tile[vch][p] - corr);
+                st.img[vch][p] = (float)((double)st.img[vch][p] - corr);
             }
-            if (counts) {
+            if (counts && (mw[0] | mw[1] | mw[2] | mw[3])) {     // most positions carry no mask bit at all
 #pragma unroll
                 for (int b = 0; b < 8; b++) {
                     const uint32_t pl = 0x01010101u << b;
-                    cnt[b] += __popc(mcur[0] & pl) + __popc(mcur[1] & pl) + __popc(mcur[2] & pl) + __popc(mcur[3] & pl);
+                    cnt[b] += __popc(mw[0] & pl) + __popc(mw[1] & pl) + __popc(mw[2] & pl) + __popc(mw[3] & pl);
                 }
             }
         }
@@ -327,12 +346,11 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (p == 0) {
-            xt_tma_store(&map, &stage[s][0][0], x0, 0, ly);
-            xt_tma_store(&map, &stage[s][8][0], x0, 0, ysc + (ysc - 1 - ly));
+            xt_tma_store(&map, &stage[s].img[0][0], x0, 0, ly);
+            xt_tma_store(&map, &stage[s].img[8][0], x0, 0, ysc + (ysc - 1 - ly));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++) mcur[i] = mnext[i];
+        advance(ly, xb);
     }
     if (p == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete before the CTA retires
     if (counts) {
@@ -370,26 +388,43 @@ static xt_encode_fn xt_encoder(void)
 static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int ysc, int xsc, const XtalkCoef &k,
                             uint32_t src_bad, uint32_t edge, unsigned long long *counts, cudaStream_t st)
 {
-    if (xsc % 4 != 0 || ((uintptr_t)img % 16) != 0 || W != 8 * xsc || H != 2 * ysc) return 1;
+    if (xsc % 4 != 0 || W % 16 != 0 || ((uintptr_t)img % 16) != 0 || ((uintptr_t)mask % 16) != 0 ||
+        W != 8 * xsc || H != 2 * ysc || xsc < XT_BX)
+        return 1;
     xt_encode_fn enc = xt_encoder();
     if (!enc) return 1;
-    const int bx = (xsc % 120 == 0) ? 120 : 128;
-    CUtensorMap map;
-    const cuuint64_t dims[3] = {(cuuint64_t)xsc, 8, (cuuint64_t)H};
-    const cuuint64_t strides[2] = {(cuuint64_t)xsc * 4, (cuuint64_t)W * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)bx, 8, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return 1;
+    CUtensorMap map, mmap;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)xsc, 8, (cuuint64_t)H};
+        const cuuint64_t strides[2] = {(cuuint64_t)xsc * 4, (cuuint64_t)W * 4};
+        const cuuint32_t box[3] = {XT_BX, 8, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    }
+    if (mask) {
+        const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+        const cuuint64_t strides[1] = {(cuuint64_t)W};
+        const cuuint32_t box[2] = {XT_BX, 1};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&mmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)mask, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 1;
+    } else {
+        mmap = map;
+    }
+    static bool attr_set = false;
+    const int smem = (int)(XT_STAGES * sizeof(XtStage));
+    if (!attr_set) {
+        BBX_CUDA(cudaFuncSetAttribute(xtalk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
     if (counts) BBX_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned long long), st));
-    const long long ntiles = (long long)ysc * ((xsc + bx - 1) / bx);
+    const long long ntiles = (long long)ysc * ((xsc + XT_BX - 1) / XT_BX);
     long long want = (long long)BBX_SM_COUNT * 5;
     const int blocks = (int)(ntiles < want ? ntiles : want);
-    if (bx == 120)
-        xtalk_tma_kernel<120><<<blocks, XT_THREADS, 0, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
-    else
-        xtalk_tma_kernel<128><<<blocks, XT_THREADS, 0, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
+    xtalk_tma_kernel<<<blocks, XT_THREADS, smem, st>>>(map, mmap, mask != nullptr, ysc, xsc, k, src_bad, edge, counts);
     BBX_CHECK_LAUNCH("xtalk_tma_kernel");
     return 0;
 }

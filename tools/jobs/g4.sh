@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_steps_gpu.py tests/test_zz_rice_fz.py tests/test_chain_gpu.py -m gpu -x -q > gpurun_out/g4_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/g4_pytest.log
+tail -12 gpurun_out/g4_pytest.log
+timeout 200 python tools/xt_bench.py > gpurun_out/g4_xt.txt 2>&1; cat gpurun_out/g4_xt.txt
+timeout 300 python tools/rice_bench.py > gpurun_out/g4_rice.txt 2>&1; cat gpurun_out/g4_rice.txt
+timeout 300 python tools/kbench.py > gpurun_out/g4_kbench.txt 2>&1; grep -E "lacosmic|xtalk" gpurun_out/g4_kbench.txt
