@@ -228,27 +228,23 @@ __device__ __forceinline__ void xt_tma_store(const CUtensorMap *map, const void 
                  :: "l"(map), "r"(xt_smem(src)), "r"(x), "r"(ch), "r"(row) : "memory");
 }
 
-__device__ __forceinline__ void xt_tma_load2(void *dst, const CUtensorMap *map, int x, int row, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(xt_smem(dst)), "l"(map), "r"(x), "r"(row), "r"(xt_smem(bar)) : "memory");
-}
-
 // The kernel is bound by instruction issue (256 DFMAs per position plus everything around them:
 // the synchronous tile kernel spends ~900 instructions per position, 0.17 ms of issue time on 148
 // SMs), so the point of the TMA staging is as much the instructions it removes -- no address
 // arithmetic, no loads, no stores in the threads -- as the latency it hides.
 //   image: 3-D tensor map (x in channel, channel column, row), box {128, 8, 1}: two loads per tile
-//   mask:  2-D tensor map (x, row) of bytes (a channel is 1320 bytes wide: not a legal TMA stride),
-//          box {128, 1}: sixteen small loads per tile, all on the same mbarrier
+//   mask:  a channel is 1320 bytes wide -- neither a legal TMA stride nor (for odd channels) a
+//          16-byte aligned box origin, which the TMA unit insists on (an unaligned origin is an
+//          illegal-instruction fault, found the hard way) -- so the 2 KB of mask bytes of a tile
+//          come with four 4-byte cp.async per thread, completing on the SAME mbarrier as the
+//          image boxes (cp.async.mbarrier.arrive.noinc)
 // A box that sticks out of its channel (the 11th of a 1320-wide channel) is clipped by the TMA
-// unit on the image side and simply reads the neighbouring channel's bytes on the mask side; the
-// threads beyond the channel edge sit the tile out.
+// unit; the threads beyond the channel edge sit the tile out.
 #define XT_BX 128
 struct XtStage { float img[16][XT_BX]; uint8_t msk[16][XT_BX]; };
 
 __global__ void __launch_bounds__(XT_THREADS, 5)
-xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap mmap, int have_mask,
+xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ mask, int W,
                  int ysc, int xsc, XtalkCoef k, uint32_t bits_src_bad, uint32_t bit_edge,
                  unsigned long long *__restrict__ counts)
 {
@@ -259,26 +255,37 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant_
     const int p = threadIdx.x;
     const int nxb = (xsc + XT_BX - 1) / XT_BX;
     const int ntiles = ysc * nxb;
+    const bool have_mask = mask != nullptr;
     if (p == 0) {
+        // arrivals per phase: thread 0's expect_tx for the two image boxes, plus (with a mask) one
+        // per thread when its cp.async of the mask bytes have landed
 #pragma unroll
-        for (int s = 0; s < XT_STAGES; s++) xt_mbar_init(&full[s], 1);
+        for (int s = 0; s < XT_STAGES; s++) xt_mbar_init(&full[s], have_mask ? 1 + XT_THREADS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (p < 8) s_cnt[p] = 0;
     __syncthreads();
 
-    const uint32_t tile_bytes = 16u * XT_BX * 4u + (have_mask ? 16u * XT_BX : 0u);
-    auto issue = [&](int ly, int xb, int s) {                    // thread 0: every box of tile (ly, xb) into stage s
+    auto issue = [&](int ly, int xb, int s) {                    // tile (ly, xb) into stage s
         const int x0 = xb * XT_BX, top = ysc + (ysc - 1 - ly);
-        xt_mbar_expect(&full[s], tile_bytes);
-        xt_tma_load(&stage[s].img[0][0], &map, x0, 0, ly, &full[s]);
-        xt_tma_load(&stage[s].img[8][0], &map, x0, 0, top, &full[s]);
+        if (p == 0) {
+            xt_mbar_expect(&full[s], 16u * XT_BX * 4u);
+            xt_tma_load(&stage[s].img[0][0], &map, x0, 0, ly, &full[s]);
+            xt_tma_load(&stage[s].img[8][0], &map, x0, 0, top, &full[s]);
+        }
         if (have_mask) {
+            // 16 channels x 32 words: thread p moves word (p % 32) of channels p / 32, + 4, + 8, + 12
+            const int wx = x0 + 4 * (p & 31);
+            if (wx < xsc) {                                      // xsc % 4 == 0: the word lies inside the channel
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                xt_tma_load2(&stage[s].msk[c][0], &mmap, c * xsc + x0, ly, &full[s]);
-                xt_tma_load2(&stage[s].msk[8 + c][0], &mmap, c * xsc + x0, top, &full[s]);
+                for (int i = 0; i < 4; i++) {
+                    const int c = (p >> 5) + 4 * i;
+                    const uint8_t *src = mask + (size_t)((c < 8) ? ly : top) * W + (size_t)(c & 7) * xsc + wx;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                 :: "r"(xt_smem(&stage[s].msk[c][4 * (p & 31)])), "l"(src) : "memory");
+                }
             }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(xt_smem(&full[s])) : "memory");
         }
     };
     // tile walk: t = blockIdx.x + i gridDim.x, kept as (row, box) without divisions in the loop
@@ -289,20 +296,19 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant_
     };
     int ly = (int)blockIdx.x / nxb, xb = (int)blockIdx.x - ly * nxb;       // current tile
     int ly2 = ly, xb2 = xb;                                               // the tile two ahead (next to issue)
-    if (p == 0 && ly2 < ysc) issue(ly2, xb2, 0);
+    if (ly2 < ysc) issue(ly2, xb2, 0);
     advance(ly2, xb2);
-    if (p == 0 && ly2 < ysc) issue(ly2, xb2, 1);
+    if (ly2 < ysc) issue(ly2, xb2, 1);
     advance(ly2, xb2);
     (void)ntiles;
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int it = 0; ly < ysc; it++) {
         const int s = it % XT_STAGES;
-        if (p == 0) {
-            // the stage tile it+2 goes into was last used by tile it-2: its store has been read
-            // out of shared memory once at most one younger store group is pending
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (ly2 < ysc) issue(ly2, xb2, (it + 2) % XT_STAGES);
-        }
+        // the stage tile it+2 goes into was last used by tile it-2: its store has been read out
+        // of shared memory once at most one younger store group is pending (the mask bytes are
+        // not part of the store: every thread may refill them right away)
+        if (p == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (ly2 < ysc) issue(ly2, xb2, (it + 2) % XT_STAGES);
         advance(ly2, xb2);
         xt_mbar_wait(&full[s], (uint32_t)(it / XT_STAGES) & 1u);
         const int x0 = xb * XT_BX;
@@ -388,12 +394,12 @@ static xt_encode_fn xt_encoder(void)
 static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int ysc, int xsc, const XtalkCoef &k,
                             uint32_t src_bad, uint32_t edge, unsigned long long *counts, cudaStream_t st)
 {
-    if (xsc % 4 != 0 || W % 16 != 0 || ((uintptr_t)img % 16) != 0 || ((uintptr_t)mask % 16) != 0 ||
-        W != 8 * xsc || H != 2 * ysc || xsc < XT_BX)
+    if (xsc % 4 != 0 || ((uintptr_t)img % 16) != 0 || ((uintptr_t)mask % 4) != 0 || W != 8 * xsc || H != 2 * ysc ||
+        xsc < XT_BX)
         return 1;
     xt_encode_fn enc = xt_encoder();
     if (!enc) return 1;
-    CUtensorMap map, mmap;
+    CUtensorMap map;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)xsc, 8, (cuuint64_t)H};
         const cuuint64_t strides[2] = {(cuuint64_t)xsc * 4, (cuuint64_t)W * 4};
@@ -402,17 +408,6 @@ static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int y
         if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 1;
-    }
-    if (mask) {
-        const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
-        const cuuint64_t strides[1] = {(cuuint64_t)W};
-        const cuuint32_t box[2] = {XT_BX, 1};
-        const cuuint32_t estr[2] = {1, 1};
-        if (enc(&mmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)mask, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return 1;
-    } else {
-        mmap = map;
     }
     static bool attr_set = false;
     const int smem = (int)(XT_STAGES * sizeof(XtStage));
@@ -424,7 +419,7 @@ static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int y
     const long long ntiles = (long long)ysc * ((xsc + XT_BX - 1) / XT_BX);
     long long want = (long long)BBX_SM_COUNT * 5;
     const int blocks = (int)(ntiles < want ? ntiles : want);
-    xtalk_tma_kernel<<<blocks, XT_THREADS, smem, st>>>(map, mmap, mask != nullptr, ysc, xsc, k, src_bad, edge, counts);
+    xtalk_tma_kernel<<<blocks, XT_THREADS, smem, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
     BBX_CHECK_LAUNCH("xtalk_tma_kernel");
     return 0;
 }
