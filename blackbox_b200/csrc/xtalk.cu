@@ -22,9 +22,10 @@
 // tensor (x within channel, channel column, row), so ONE cp.async.bulk.tensor box {BX, 8, 1} brings
 // the 8 bottom channels of a tile row into shared memory and a second one the 8 mirrored top
 // channels (8 KB per tile, no thread touches an address); a 4-stage mbarrier ring keeps the loads
-// of tile k+2 and the store of tile k-1 in flight while the 256 DFMAs per thread of tile k run;
-// results go back with cp.async.bulk.tensor stores straight from the stage.  The mask bytes of
-// tile k+1 wait in registers.  The kernel also counts the pixels per mask bit on its way (the
+// of tile k+2 in flight while the 256 DFMAs per thread of tile k run; the results leave through
+// registers as full-line stores.  (Storing back through the stage with cp.async.bulk.tensor needs a
+// fence.proxy.async + block barrier per tile, which made every thread wait for its own prefetches:
+// slower than no TMA at all.)  The kernel also counts the pixels per mask bit on its way (the
 // mask is final here: mask_header's M-*NUM, blackbox.py:4601-4620, cost no extra pass).
 #include <cuda.h>
 #include "bbx_common.cuh"
@@ -244,7 +245,7 @@ __device__ __forceinline__ void xt_tma_store(const CUtensorMap *map, const void 
 struct XtStage { float img[16][XT_BX]; uint8_t msk[16][XT_BX]; };
 
 __global__ void __launch_bounds__(XT_THREADS, 5)
-xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ mask, int W,
+xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, float *__restrict__ img, const uint8_t *__restrict__ mask, int W,
                  int ysc, int xsc, XtalkCoef k, uint32_t bits_src_bad, uint32_t bit_edge,
                  unsigned long long *__restrict__ counts)
 {
@@ -304,10 +305,10 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int it = 0; ly < ysc; it++) {
         const int s = it % XT_STAGES;
-        // the stage tile it+2 goes into was last used by tile it-2: its store has been read out
-        // of shared memory once at most one younger store group is pending (the mask bytes are
-        // not part of the store: every thread may refill them right away)
-        if (p == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the stage tile it+2 goes into was last read by tile it-2: one block barrier per pass
+        // keeps the refill behind every thread's reads (the results leave through registers,
+        // nothing reads a stage after its pass)
+        __syncthreads();
         if (ly2 < ysc) issue(ly2, xb2, (it + 2) % XT_STAGES);
         advance(ly2, xb2);
         xt_mbar_wait(&full[s], (uint32_t)(it / XT_STAGES) & 1u);
@@ -338,7 +339,9 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
                 double corr = 0.0 + a;
                 corr = corr + b;
                 corr = corr * (((vic_ok >> vch) & 1u) ? 1.0 : 0.0);
-                st.img[vch][p] = (float)((double)st.img[vch][p] - corr);
+                const float res = (float)((double)st.img[vch][p] - corr);
+                // 32 consecutive floats per warp and channel: a full 128-byte line per store
+                img[(size_t)((vch < 8) ? ly : ysc + (ysc - 1 - ly)) * W + (size_t)(vch & 7) * xsc + x0 + p] = res;
             }
             if (counts && (mw[0] | mw[1] | mw[2] | mw[3])) {     // most positions carry no mask bit at all
 #pragma unroll
@@ -348,17 +351,8 @@ xtalk_tma_kernel(const __grid_constant__ CUtensorMap map, const uint8_t *__restr
                 }
             }
         }
-        // the stage now holds the corrected tile: hand it to the TMA unit
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (p == 0) {
-            xt_tma_store(&map, &stage[s].img[0][0], x0, 0, ly);
-            xt_tma_store(&map, &stage[s].img[8][0], x0, 0, ysc + (ysc - 1 - ly));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
         advance(ly, xb);
     }
-    if (p == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete before the CTA retires
     if (counts) {
 #pragma unroll
         for (int b = 0; b < 8; b++) {
@@ -419,7 +413,7 @@ static int xtalk_tma_launch(float *img, const uint8_t *mask, int H, int W, int y
     const long long ntiles = (long long)ysc * ((xsc + XT_BX - 1) / XT_BX);
     long long want = (long long)BBX_SM_COUNT * 5;
     const int blocks = (int)(ntiles < want ? ntiles : want);
-    xtalk_tma_kernel<<<blocks, XT_THREADS, smem, st>>>(map, mask, W, ysc, xsc, k, src_bad, edge, counts);
+    xtalk_tma_kernel<<<blocks, XT_THREADS, smem, st>>>(map, img, mask, W, ysc, xsc, k, src_bad, edge, counts);
     BBX_CHECK_LAUNCH("xtalk_tma_kernel");
     return 0;
 }
