@@ -64,7 +64,7 @@ STAGES = {
     'mask_morph': ('ms_* / hole_* / ccl kernels (S3)', 223e6, False),
     'lacosmic': ('sp_scan + sparse candidate / grow / clean kernels, %d iterations (S4)' % NITER, NITER * 1115.1e6, False),
     'lacosmic_finish': ('cosmic-ray bit + NCOSMICS from the CR list', None, False),
-    'xtalk': ('xtalk_tma_kernel (S5: img r+w + mask r; also counts the mask bits)', 1003.6e6, True),
+    'xtalk': ('xtalk_tile_kernel + mask_counts_kernel (S5: img r+w + mask r; M-*NUM counts: mask r)', 1003.6e6 + 111.5e6, False),
     'edge_fill': ('cs_hist x3 + cs_find x3 + cs_fill_edge (3 x img r + mask r)', 3 * 446.1e6 + 111.5e6, False),
 }
 
@@ -554,8 +554,8 @@ def pipe_launches(tel, niter):
     cross-checked against the ncu launch list under profiles/): overscan 6 (+1 BlackGEM
     saturated-column count) + header means 1, fused apply 1, sparse mask morphology 11, LACosmic
     2 (begin) + 9 (first iteration) + 8 per further iteration, cosmic-ray bit + object count 3,
-    crosstalk 1 (it also counts the mask bits)."""
-    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1
+    crosstalk 1, per-bit mask counts 1."""
+    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1 + 1
 
 
 def peak_hbm():

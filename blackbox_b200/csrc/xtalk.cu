@@ -17,15 +17,22 @@
 // CTAs behind the FP64 work), and the tile goes back with 128-bit stores.
 // xtalk_kernel<PX>: generic fallback (any width / alignment), registers only.
 //
-// xtalk_tma_kernel (what bbx_xtalk runs when the layout allows): the same tile walk as a
-// PERSISTENT kernel with asynchronous staging.  The image is described to the TMA unit as a 3-D
+// xtalk_tma_kernel (variant 5; NOT the default -- measured on B200, 10560^2: 0.32 ms against the
+// tile kernel's 0.227 ms, see below): the same tile walk as a PERSISTENT kernel with asynchronous
+// staging.  The image is described to the TMA unit as a 3-D
 // tensor (x within channel, channel column, row), so ONE cp.async.bulk.tensor box {BX, 8, 1} brings
 // the 8 bottom channels of a tile row into shared memory and a second one the 8 mirrored top
 // channels (8 KB per tile, no thread touches an address); a 4-stage mbarrier ring keeps the loads
 // of tile k+2 in flight while the 256 DFMAs per thread of tile k run; the results leave through
-// registers as full-line stores.  (Storing back through the stage with cp.async.bulk.tensor needs a
-// fence.proxy.async + block barrier per tile, which made every thread wait for its own prefetches:
-// slower than no TMA at all.)  The kernel also counts the pixels per mask bit on its way (the
+// registers as full-line stores.  Measured (tools/xt_bench.py, profiles/r02_xtalk_variants.txt):
+// 0.333 ms with the results stored back through the stage by cp.async.bulk.tensor, 0.317 ms with the
+// mask through cp.async, 0.320 ms with register stores -- against 0.227 ms for the synchronous
+// tile kernel.  The kernel is bound by instruction issue, not by load latency: ~900 instructions per
+// tile position (256 DFMA + 144 LDCU for the coefficients + conversions) are 0.17 ms of issue time
+// on 148 SMs, the FP64 pipe needs 0.10 ms, HBM 0.155 ms; the one-tile-per-CTA kernel with 6 CTAs
+// per SM already overlaps its loads with other CTAs' DFMAs, and the persistent loop makes the
+// compiler keep part of the coefficient matrix in registers (96 registers, 5 CTAs per SM).  Kept
+// as a tested variant and as the record of the experiment.  The kernel also counts the pixels per mask bit on its way (the
 // mask is final here: mask_header's M-*NUM, blackbox.py:4601-4620, cost no extra pass).
 #include <cuda.h>
 #include "bbx_common.cuh"
@@ -430,24 +437,25 @@ extern "C" int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, 
     return bbx_xtalk_counts(img, mask, H, W, ysize_chan, xsize_chan, coeffs_h, bits, variant, nullptr, stream);
 }
 
-// variant 0: the kernel bbx_xtalk picks (TMA-staged persistent kernel when the layout allows, else
-// the synchronous tile kernel, else the generic one); 3: the synchronous tile kernel; 1 / 2 / 4: the
-// generic register-only kernel with that many pixels per thread and channel (parity tests,
-// tools/xt_bench.py).  out_counts (device uint64 [8], may be null): pixels per mask bit of `mask`,
-// zeroed and filled by the call (by the crosstalk kernel itself on the TMA path).
+// variant 0: the kernel bbx_xtalk picks (the tile kernel when the layout allows, else the generic
+// one); 3: the tile kernel; 5: the TMA-staged persistent kernel (falls back to 0 where the layout
+// does not allow it); 1 / 2 / 4: the generic register-only kernel with that many pixels per thread
+// and channel (parity tests, tools/xt_bench.py).  out_counts (device uint64 [8], may be null):
+// pixels per mask bit of `mask`, zeroed and filled by the call (by the crosstalk kernel itself on
+// the TMA path, by bbx_mask_counts' kernel otherwise).
 extern "C" int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                                 const double *coeffs_h, const bbx_maskbits *bits, int variant,
                                 unsigned long long *out_counts, void *stream)
 {
     BBX_REQUIRE(img && coeffs_h && bits, "bbx_xtalk: null argument");
-    BBX_REQUIRE(variant >= 0 && variant <= 4, "bbx_xtalk: variant %d", variant);
+    BBX_REQUIRE(variant >= 0 && variant <= 5, "bbx_xtalk: variant %d", variant);
     BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_xtalk: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
     BBX_REQUIRE(out_counts == nullptr || mask != nullptr, "bbx_xtalk: mask counts asked for without a mask");
     XtalkCoef k;
     for (int s = 0; s < 16; s++) for (int v = 0; v < 16; v++) k.c[v][s] = coeffs_h[s * 16 + v];
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t src_bad = (uint32_t)(bits->bad | bits->cosmic);
-    if (variant == 0) {
+    if (variant == 5) {
         const int rc = xtalk_tma_launch(img, mask, H, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge, out_counts, st);
         if (rc <= 0) return rc;
     }

@@ -204,9 +204,10 @@ int bbx_mask_counts(const uint8_t *mask, size_t n, unsigned long long *out_count
  * ------------------------------------------------------------------------------------- */
 int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
               const double *coeffs_h, const bbx_maskbits *bits, void *stream);
-/* the same with the kernel chosen by the caller: variant 0 = bbx_xtalk's own choice (the TMA-staged
- * persistent kernel when the layout allows), 3 = the synchronous tile kernel, 1 / 2 / 4 = the
- * generic register-only kernel with that many pixels per thread (parity tests, benchmarks) */
+/* the same with the kernel chosen by the caller: variant 0 = bbx_xtalk's own choice (the tile kernel
+ * when the layout allows), 3 = the tile kernel, 5 = the TMA-staged persistent kernel (measured
+ * slower: the kernel is issue-bound), 1 / 2 / 4 = the generic register-only kernel with that many
+ * pixels per thread (parity tests, benchmarks) */
 int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                       const double *coeffs_h, const bbx_maskbits *bits, int variant, void *stream);
 /* ... and with the per-bit pixel counts of the mask (mask_header, blackbox.py:4601-4620; the mask

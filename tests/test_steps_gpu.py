@@ -371,8 +371,8 @@ def test_xtalk_parity(with_mask, small_bb, tmp_path):
 
 @pytest.mark.parametrize('shape', [(128, 1056), (2 * 77, 8 * 1320), (2 * 40, 8 * 660), (2 * 33, 8 * 100), (2 * 9, 8 * 30)])
 def test_xtalk_kernels_agree_and_count_the_mask(shape):
-    """Every crosstalk kernel -- the TMA-staged persistent one bbx_xtalk runs (boxes of 120 or 128
-    positions, clipped at the channel edge), the synchronous tile kernel, the generic ones -- gives
+    """Every crosstalk kernel -- the tile kernel bbx_xtalk runs, the TMA-staged persistent one (boxes
+    of 128 positions, clipped at the channel edge), the generic ones -- gives
     the same bits as the oracle class allows (> 99.99 % identical, 1e-6), and identical bits among
     themselves; the per-bit mask counts taken on the way equal numpy's (blackbox.py:4601-4620)."""
     import ctypes as C
@@ -395,7 +395,7 @@ def test_xtalk_kernels_agree_and_count_the_mask(shape):
         bits = bbr._bits('BG3')
         m_t = torch.from_numpy(mask).cuda()
         outs = {}
-        for variant in (0, 3, 4, 2, 1):
+        for variant in (0, 3, 5, 4, 2, 1):
             img = torch.from_numpy(data.copy()).cuda()
             counts = torch.full((8,), -1, dtype=torch.int64, device='cuda')
             call('bbx_xtalk_counts', bbr._ptr(img), bbr._ptr(m_t), H, W, H // 2, W // 8,
