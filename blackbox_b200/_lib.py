@@ -44,10 +44,12 @@ _SIGNATURES = {
     'bbx_vos_std': [P, I, GEOM, P, P, P, P, P],
     'bbx_hos_fit': [P, P, P, P, GEOM, I, I, I, P, P, P, P],
     'bbx_reduce_apply': [P, I, GEOM, P, P, P, P, P, P, P, BITS, P, P, P, P, C.c_uint, P],
+    'bbx_reduce_apply_scan': [P, I, GEOM, P, P, P, P, P, P, P, BITS, P, P, P, P, C.c_uint, P, F, F, F, F, P, I, P, P, P],
     'bbx_satlevels': [P, P, P, P],
     'bbx_header_means': [P, P, P, P],
     'bbx_mask_sat_neighbours': [P, I, I, I, I, BITS, P],
     'bbx_mask_morph_sparse': [P, I, I, I, I, BITS, P, P, C.c_uint, P, P, P, I, P, P],
+    'bbx_mask_morph_sparse_track': [P, I, I, I, I, BITS, P, P, C.c_uint, P, P, P, I, P, P, P, P],
     'bbx_fill_holes_work_bytes': [I, I],
     'bbx_fill_sat_holes': [P, I, I, BITS, P, I, P, P],
     'bbx_fill_holes_more': [P, I, I, BITS, P, I, P, P],

@@ -22,43 +22,7 @@
 // saturation test: ncu showed the XU pipe at 63 % and DRAM at 53 %.)  The saturation test
 // f64(v) >= level is done in float32 against the smallest float32 >= level, which is the same
 // predicate.
-#include "bbx_common.cuh"
-
-struct ApplyArgs {
-    const double *vos_fit;     // [16][dy] or null
-    const double *oscan;       // [16][xsize_chan] or null
-    const float *mbias;        // [red] or null
-    const float *mflat;        // [red] or null
-    const uint8_t *bpm;        // [red] or null
-    const double *satlevel;    // [16] device, or null
-    float *out_img;            // [red]
-    uint8_t *out_mask;         // [red] or null
-    int bit_bad, bit_sat;
-    unsigned int *seeds;       // optional list of pixels that seed the mask morphology
-    unsigned int *seed_count;  // [0] entries appended (may exceed seed_cap: overflow)
-    unsigned int seed_cap;
-    unsigned int seed_bits;    // saturated | saturated-connected bit values
-};
-
-template <typename T> struct RawVec4;
-// u16 -> f32 through the exponent trick (2^23 + n) - 2^23: exact, and on the ALU / FMA pipes
-// instead of the quarter-rate conversion unit
-template <> struct RawVec4<uint16_t> {
-    static __device__ __forceinline__ void load(const uint16_t *p, float v[4]) {
-        const uint2 u = __ldcs(reinterpret_cast<const uint2 *>(p));
-        v[0] = __uint_as_float(0x4b000000u | (u.x & 0xffffu)) - 8388608.0f;
-        v[1] = __uint_as_float(0x4b000000u | (u.x >> 16)) - 8388608.0f;
-        v[2] = __uint_as_float(0x4b000000u | (u.y & 0xffffu)) - 8388608.0f;
-        v[3] = __uint_as_float(0x4b000000u | (u.y >> 16)) - 8388608.0f;
-    }
-};
-template <> struct RawVec4<float> {
-    static __device__ __forceinline__ void load(const float *p, float v[4]) {
-        const uint4 u = __ldcs(reinterpret_cast<const uint4 *>(p));
-        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y);
-        v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
-    }
-};
+#include "apply_common.cuh"
 
 template <typename T>
 __device__ __forceinline__ void apply_px(float &v, uint8_t &m, bool have_mask, float gn, double fitv,
@@ -145,14 +109,6 @@ reduce_apply_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyAr
 
 #define APPLY_THREADS 128
 #define APPLY_ROWS 16
-
-// smallest float32 t with (double)t >= level: for float32 v, (double)v >= level <=> v >= t
-__device__ __forceinline__ float f32_ceil_of(double level)
-{
-    float t = (float)level;                       // round to nearest
-    if ((double)t < level) t = nextafterf(t, INFINITY);
-    return t;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(APPLY_THREADS)

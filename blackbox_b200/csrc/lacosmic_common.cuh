@@ -3,6 +3,7 @@
 #pragma once
 #include "bbx_common.cuh"
 #include "median_networks.cuh"
+#include "bg_track.cuh"
 
 // out_info layout (int64): [0] iterations run, [1] active flag, [2] status bits,
 // [3] reserved, [4+k] new CR pixels of iteration k
@@ -89,16 +90,6 @@ struct SelState {
     unsigned int pad;
     unsigned int hist[3][SEL_BINS];
 };
-
-__device__ __forceinline__ unsigned int f32_key(float f)
-{
-    const unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_f32(unsigned int k)
-{
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 
 // Block-wide search (256 threads): first bin b of hist[0..nb) with cumulative count > k.
 // Returns b (clamped to nb-1) and the count below it in `below`; identical in all threads.

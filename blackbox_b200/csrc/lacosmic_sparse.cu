@@ -40,6 +40,7 @@
 // passes over image + mask) up front.  If a work list overflows, LAC_STATUS_OVERFLOW is raised
 // and the caller repeats the call with the dense implementation.
 #include "lacosmic_common.cuh"
+#include "apply_common.cuh"
 
 #define FLAG_C0 1u
 #define FLAG_C1 2u
@@ -62,10 +63,6 @@ struct SparseCounters {
 #define BG_SAMPLES 32768u
 #define BG_BINS (1u << 20)
 
-struct BgState {
-    unsigned int key_a, width;           // bracket: keys key_a .. key_a + width - 1 (width 0: no bracket)
-    unsigned long long n_valid, n_below; // unmasked pixels; unmasked pixels with key < key_a
-};
 
 struct SparseWork {
     uint8_t *flags;              // [N] per pixel: (iteration stamp << FLAG_BITS) | FLAG_*
@@ -354,6 +351,267 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
             if (tb) atomicAdd(&w.bg->n_below, (unsigned long long)tb);
         }
     }
+}
+
+// --------------------------------------------------------------------------------------------
+// The fused per-pixel pass (apply.cu) and the dense scan above in ONE kernel: the reduced image is
+// scanned for Laplacian candidates while it is being made, so LACosmic's first iteration does not
+// read the 446 MB it has just seen written (the scan alone: 0.25 ms per frame, the largest item
+// of the chain after the fused pass itself).
+//   * a thread owns 4 columns and walks down FUSE_ROWS rows plus one halo row at either end,
+//     holding the reduced values of three consecutive rows in registers; left / right neighbours
+//     come from the neighbouring lanes, and across a warp edge from apply_value_at (the same
+//     arithmetic on one pixel);
+//   * the statistics of the background level are taken against the SEED mask (bad-pixel mask,
+//     non-finite, saturated: all the fused pass knows); the mask morphology that follows takes every
+//     pixel it masks for the first time out again (bg_untrack, called where mask.cu sets a bit in
+//     a zero byte) -- the final mask is what detect_cosmics' inmask is;
+//   * the bracket of the background level comes from a sample evaluated through apply_value_at
+//     BEFORE the pass (sp_bg_gather_raw_kernel).
+// --------------------------------------------------------------------------------------------
+#define FUSE_THREADS 128
+#define FUSE_ROWS 32
+
+struct FuseArgs {
+    uint8_t *crmask;
+    LacParams prm;
+    SparseWork w;
+    long long *info;
+};
+
+// background statistics of one unmasked pixel value (the accounting of sp_scan_kernel<true>)
+__device__ __forceinline__ void bg_count(float v, unsigned int key_a, unsigned int width, unsigned int &n_valid,
+                                         unsigned int &n_below, unsigned int *__restrict__ hist)
+{
+    const unsigned int key = f32_key(v);
+    n_valid++;
+    if (key < key_a) n_below++;
+    else if (key - key_a < width) atomicAdd(&hist[key - key_a], 1u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FUSE_THREADS)
+reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a, FuseArgs f)
+{
+    const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
+    const int lane = threadIdx.x & 31;
+    const int x = (blockIdx.x * FUSE_THREADS + threadIdx.x) * 4;
+    const bool live = x < RW;                                  // whole warps stay: the lanes shuffle
+    const int xs = live ? x : 0;
+    const int c = xs / g.xsize_chan, lx = xs - c * g.xsize_chan;
+    const int ya = blockIdx.y * FUSE_ROWS, yb = min(ya + FUSE_ROWS, RH);
+    const bool has_bias = a.mbias != nullptr, has_flat = a.mflat != nullptr;
+    const unsigned int key_a = f.w.bg->key_a, width = f.w.bg->width;
+    const float thr_lo = lac_thr_lo(f.prm);
+    const float thr_s = __fmul_rd(thr_lo, thr_lo >= 0.f ? 0.99999952316284f : 1.00000047683716f);   // thr_lo (1 -+ 2^-21)
+    unsigned int n_valid = 0, n_below = 0;
+    int r_cur = -1;
+    double osc[4] = {0.0, 0.0, 0.0, 0.0};
+    float gn = 1.0f, satl = 0.0f;
+    bool has_sat = false;
+
+    struct RowIn { float v[4]; float4 mb, mf; uint32_t mm; double fitv; };
+    struct RowV { float v[4]; float l, r; };
+    auto load_row = [&](int y, RowIn &in) {
+        if (!live) return;
+        const int r = (y >= g.ysize_chan) ? 1 : 0;             // ny == 2
+        const int rr = (r == 0 ? g.data_y0_bot : g.data_y0_top) + (y - r * g.ysize_chan);
+        const size_t ro = (size_t)rr * g.W + (size_t)c * g.dx + lx;
+        const size_t oo = (size_t)y * RW + x;
+        RawVec4<T>::load(raw + ro, in.v);
+        in.mb = make_float4(0.f, 0.f, 0.f, 0.f);
+        in.mf = make_float4(1.f, 1.f, 1.f, 1.f);
+        in.mm = 0;
+        if (has_bias) in.mb = __ldcs(reinterpret_cast<const float4 *>(a.mbias + oo));
+        if (has_flat) in.mf = __ldcs(reinterpret_cast<const float4 *>(a.mflat + oo));
+        if (a.bpm) in.mm = __ldcs(reinterpret_cast<const unsigned int *>(a.bpm + oo));
+        in.fitv = a.vos_fit ? a.vos_fit[(size_t)(r * g.nx + c) * g.dy + (rr - r * g.dy)] : 0.0;
+    };
+    // the reduced values of row y (and, for the strip's own rows, everything the fused pass
+    // writes); `own`: the row belongs to this strip (halo rows are only computed)
+    auto finish_row = [&](int y, const RowIn &in, bool own, RowV &out) {
+        uint32_t mout = 0;
+        if (live) {
+            const int r = (y >= g.ysize_chan) ? 1 : 0;
+            if (r != r_cur) {                                  // once per strip (twice if it straddles the CCD halves)
+                r_cur = r;
+                const int ch = r * g.nx + c;
+                gn = gain.v[ch];
+                if (a.oscan) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) osc[k] = a.oscan[(size_t)ch * g.xsize_chan + lx + k];
+                }
+                has_sat = a.satlevel != nullptr;
+                if (has_sat) {
+                    const double lv = a.satlevel[ch];
+                    if (lv != lv) has_sat = false;             // NaN level: the comparison is never true
+                    else satl = f32_ceil_of(lv);
+                }
+            }
+            const float mb[4] = {in.mb.x, in.mb.y, in.mb.z, in.mb.w}, mf[4] = {in.mf.x, in.mf.y, in.mf.z, in.mf.w};
+            bool any_seed = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float w = in.v[k] * gn;
+                w = sub_f64(w, in.fitv);
+                w = sub_f64(w, osc[k]);
+                if (has_bias) w = w - mb[k];
+                uint32_t m = (in.mm >> (8 * k)) & 0xffu;
+                if (!isfinite(w)) { w = 0.f; if (m == 0) m |= (uint32_t)a.bit_bad; }
+                if (has_sat && w >= satl) m |= (uint32_t)(a.bit_sat | BBX_TMP_SAT);
+                any_seed |= (m & (BBX_TMP_SAT | a.seed_bits)) != 0;
+                if (has_flat) w = w / mf[k];
+                out.v[k] = w;
+                mout |= m << (8 * k);
+            }
+            if (own) {
+                const size_t oo = (size_t)y * RW + x;
+                if (a.seeds && any_seed) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t m = (mout >> (8 * k)) & 0xffu;
+                        const bool sat = (m & BBX_TMP_SAT) != 0;
+                        if (sat || (m & a.seed_bits)) {
+                            const unsigned int slot = atomicAdd(a.seed_count, 1u);
+                            if (slot < a.seed_cap) a.seeds[slot] = (unsigned int)(oo + k) | (sat ? 0u : 0x80000000u);
+                        }
+                    }
+                }
+                __stcs(reinterpret_cast<float4 *>(a.out_img + oo), make_float4(out.v[0], out.v[1], out.v[2], out.v[3]));
+                __stcs(reinterpret_cast<unsigned int *>(a.out_mask + oo), mout);
+                // what the dense scan cleared: the cosmic-ray mask and LACosmic's flag bytes
+                __stcs(reinterpret_cast<unsigned int *>(f.crmask + oo), 0u);
+                __stcs(reinterpret_cast<unsigned int *>(f.w.flags + oo), 0u);
+                // background statistics against the seed mask
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (((mout >> (8 * k)) & 0xffu) == 0) bg_count(out.v[k], key_a, width, n_valid, n_below, f.w.bghist);
+            }
+        } else {
+            out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.f;
+        }
+        // horizontal neighbours: the lanes either side; across the warp edge the pixel itself
+        out.l = __shfl_up_sync(0xffffffffu, out.v[3], 1);
+        out.r = __shfl_down_sync(0xffffffffu, out.v[0], 1);
+        if (live && own) {                                     // (halo rows only lend their own columns)
+            uint32_t dummy;
+            if (lane == 0) out.l = x > 0 ? apply_value_at<T>(raw, g, gain, a, y, x - 1, dummy) : 0.f;
+            if (lane == 31 || x + 4 >= RW) out.r = x + 4 < RW ? apply_value_at<T>(raw, g, gain, a, y, x + 4, dummy) : 0.f;
+        }
+    };
+    // L+ of the 4 pixels of row y: U / D are the rows above / below (hu / hd: they exist)
+    auto laplace_row = [&](int y, const RowV &U, const RowV &Cn, const RowV &D, bool hu, bool hd) {
+        if (!live) return;
+        const unsigned int pix = (unsigned int)((size_t)y * RW + x);
+        const float cc[6] = {Cn.l, Cn.v[0], Cn.v[1], Cn.v[2], Cn.v[3], Cn.r};
+        if (hu && hd && x > 0 && x + 4 < RW) {
+            // interior: the cheap rigorous bound first (see sp_scan_kernel), the full Laplacian for the few it lets through
+            auto mag4 = [](const float (&v)[4]) { return fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))); };
+            const float mag = fmaxf(fmaxf(mag4(U.v), mag4(D.v)), fmaxf(mag4(Cn.v), fmaxf(fabsf(Cn.l), fabsf(Cn.r))));
+            const float thr_row = __fmaf_rd(mag, -3.814697265625e-06f, thr_s);            // - 2^-18 mag
+            float t[4];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                t[k] = __fsub_ru(cc[k + 1], fminf(cc[k], cc[k + 2]));
+                t[k] = __fadd_ru(t[k], cc[k + 1]);
+                t[k] = __fsub_ru(t[k], fminf(U.v[k], D.v[k]));
+                any |= !(t[k] <= thr_row);
+            }
+            if (!any) return;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (t[k] <= thr_row) continue;
+                const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], c4 = 4.0f * cv;
+                float s00 = c4 - cv; s00 = s00 - l; s00 = s00 - cv; s00 = s00 - U.v[k];
+                float s01 = c4 - r; s01 = s01 - cv; s01 = s01 - cv; s01 = s01 - U.v[k];
+                float s10 = c4 - cv; s10 = s10 - l; s10 = s10 - D.v[k]; s10 = s10 - cv;
+                float s11 = c4 - r; s11 = s11 - cv; s11 = s11 - D.v[k]; s11 = s11 - cv;
+                s00 = fmaxf(s00, 0.f); s01 = fmaxf(s01, 0.f); s10 = fmaxf(s10, 0.f); s11 = fmaxf(s11, 0.f);
+                float p = s00 + s01; p = p + s10; p = p + s11;
+                const float lp = p * 0.25f;
+                if (lp > thr_lo) list_push(f.w.listA[0], &f.w.cnt->nA[0], f.w.capA, pix + k, f.info);
+            }
+            return;
+        }
+        // the frame of the image: missing neighbours drop out of the sub-pixel Laplacians (laplace_plus_at)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool hl = x + k > 0, hr = x + k + 1 < RW;
+            const float cv = cc[k + 1], l = cc[k], r = cc[k + 2], u = U.v[k], d = D.v[k], c4 = 4.0f * cv;
+            float s00 = c4 - cv; if (hl) s00 = s00 - l; s00 = s00 - cv; if (hu) s00 = s00 - u;
+            float s01 = c4; if (hr) s01 = s01 - r; s01 = s01 - cv; s01 = s01 - cv; if (hu) s01 = s01 - u;
+            float s10 = c4 - cv; if (hl) s10 = s10 - l; if (hd) s10 = s10 - d; s10 = s10 - cv;
+            float s11 = c4; if (hr) s11 = s11 - r; s11 = s11 - cv; if (hd) s11 = s11 - d; s11 = s11 - cv;
+            s00 = s00 < 0.f ? 0.f : s00; s01 = s01 < 0.f ? 0.f : s01;
+            s10 = s10 < 0.f ? 0.f : s10; s11 = s11 < 0.f ? 0.f : s11;
+            float p = s00 + s01;
+            p = p + s10;
+            p = p + s11;
+            const float lp = p / 4.0f;
+            if (lp > thr_lo) list_push(f.w.listA[0], &f.w.cnt->nA[0], f.w.capA, pix + k, f.info);
+        }
+    };
+
+    // rows ya-1 .. yb (clipped to the frame); three rows of values rotate through A, B, C
+    const int y0 = max(ya - 1, 0), y1 = min(yb, RH - 1);
+    RowIn in0, in1;
+    RowV A, B, C;
+    A.v[0] = A.v[1] = A.v[2] = A.v[3] = A.l = A.r = 0.f;
+    B = A; C = A;
+    load_row(y0, in0);
+    // step(y, in, next_in, P, Q, R): prefetch row y+1, finish row y into R, then the Laplacian of
+    // row y-1 (in Q) between P (row y-2) and R (row y)
+    auto step = [&](int y, RowIn &in, RowIn &nxt, const RowV &P, const RowV &Q, RowV &R) {
+        if (y + 1 <= y1) load_row(y + 1, nxt);
+        finish_row(y, in, y >= ya && y < yb, R);
+        const int ym = y - 1;
+        if (ym >= ya && ym < yb && ym >= y0) laplace_row(ym, P, Q, R, ym > 0, true);
+        // the last row of the image has no row below it
+        if (y == RH - 1) laplace_row(y, Q, R, R, y > 0, false);
+    };
+    int y = y0;
+    for (; y + 6 <= y1 + 1; y += 6) {
+        step(y, in0, in1, B, C, A);          // rows: P = y-2, Q = y-1, R = y
+        step(y + 1, in1, in0, C, A, B);
+        step(y + 2, in0, in1, A, B, C);
+        step(y + 3, in1, in0, B, C, A);
+        step(y + 4, in0, in1, C, A, B);
+        step(y + 5, in1, in0, A, B, C);
+    }
+    // the remaining 0..5 rows, same rotation
+    const int rem = y1 + 1 - y;
+    if (rem > 0) step(y, in0, in1, B, C, A);
+    if (rem > 1) step(y + 1, in1, in0, C, A, B);
+    if (rem > 2) step(y + 2, in0, in1, A, B, C);
+    if (rem > 3) step(y + 3, in1, in0, B, C, A);
+    if (rem > 4) step(y + 4, in0, in1, C, A, B);
+    const unsigned int tv = (unsigned int)warp_sum((int)n_valid), tb = (unsigned int)warp_sum((int)n_below);
+    if (lane == 0) {
+        if (tv) atomicAdd(&f.w.bg->n_valid, (unsigned long long)tv);
+        if (tb) atomicAdd(&f.w.bg->n_below, (unsigned long long)tb);
+    }
+}
+
+// the strided sample for the bracket of the background level, evaluated on the RAW frame through
+// the fused pass's own arithmetic (the reduced image does not exist yet); seed mask
+template <typename T>
+__global__ void __launch_bounds__(1024)
+sp_bg_gather_raw_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a, SparseWork w)
+{
+    const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
+    const size_t n = (size_t)RW * RH;
+    const size_t stride = n / BG_SAMPLES > 0 ? n / BG_SAMPLES : 1;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= BG_SAMPLES) return;
+    const size_t i = j * stride;
+    unsigned int key = 0xffffffffu;
+    if (i < n) {
+        uint32_t m;
+        const float v = apply_value_at<T>(raw, g, gain, a, (int)(i / RW), (int)(i % RW), m);
+        if (m == 0 && v == v) key = f32_key(v);
+    }
+    w.bgsample[j] = key;
 }
 
 // ---- background level ----------------------------------------------------------------------
@@ -873,7 +1131,8 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
 }
 
 static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
-                            int it, bool with_background, void *work, long long *info, cudaStream_t st)
+                            int it, bool with_background, void *work, long long *info, cudaStream_t st,
+                            bool prescanned = false)
 {
     const size_t n = (size_t)H * W;
     SparseWork w = carve_sparse(work, n);
@@ -885,7 +1144,11 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     const int list_blocks = it == 0 ? BBX_SM_COUNT * 8 : BBX_SM_COUNT * 2;
     const int warp_blocks = it == 0 ? BBX_SM_COUNT * 16 : BBX_SM_COUNT * 4;
     if (it > 0 && it % STAMP_PERIOD == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
-    if (it == 0) {
+    if (it == 0 && prescanned) {
+        // bbx_reduce_apply_scan has made list A, the statistics and the cleared byte maps; the mask
+        // morphology has corrected the statistics for the pixels it masked since
+        sp_bg_rank_kernel<<<1, 1024, 0, st>>>(w);
+    } else if (it == 0) {
         if (with_background) {
             sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, crmask, H, W, prm, w, info);
         } else {
@@ -905,6 +1168,78 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     return 0;
 }
 
+BgTrack lac_sparse_bg_track(const float *img, void *lac_work, int H, int W)
+{
+    BgTrack t = {nullptr, nullptr, nullptr};
+    if (img && lac_work) {
+        const SparseWork w = carve_sparse(lac_work, (size_t)H * W);
+        t.img = img; t.bg = w.bg; t.hist = w.bghist;
+    }
+    return t;
+}
+
+static inline bool fuse_aligned(const void *p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
+
+// bbx_reduce_apply + the dense scan of LACosmic's first iteration in one pass (see include/bbx.h)
+extern "C" int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                                     const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
+                                     const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
+                                     float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
+                                     unsigned int seed_cap, uint8_t *crmask, float sigclip, float sigfrac, float objlim,
+                                     float readnoise, const double *readnoise_dev, int niter, void *lac_work,
+                                     long long *lac_info, void *stream)
+{
+    BBX_REQUIRE(g && raw && out_img && out_mask && bits && crmask && lac_work && lac_info,
+                "bbx_reduce_apply_scan: null argument");
+    BBX_REQUIRE(g->ny == 2 && g->nx * g->ny == BBX_NCHAN, "bbx_reduce_apply_scan: expected 2 x 8 channels");
+    BBX_REQUIRE((const void *)out_img != raw, "bbx_reduce_apply_scan: output must not alias the raw frame");
+    BBX_REQUIRE((seeds == nullptr) == (seed_count == nullptr), "bbx_reduce_apply_scan: seeds and seed_count go together");
+    BBX_REQUIRE(niter > 0 && sigclip >= 0.f && sigfrac >= 0.f, "bbx_reduce_apply_scan: needs niter > 0 and non-negative thresholds");
+    const long long RW = (long long)g->nx * g->xsize_chan, RH = (long long)g->ny * g->ysize_chan;
+    BBX_REQUIRE(RH * RW < 2147483647LL, "bbx_reduce_apply_scan: frame too large for 31-bit pixel indices");
+    const size_t esz = raw_type == BBX_RAW_U16 ? 2 : 4;
+    const bool vec4 = (g->xsize_chan % 4 == 0) && (g->dx % 4 == 0) && (g->W % 4 == 0) && fuse_aligned(raw, 4 * esz) &&
+                      fuse_aligned(mbias, 16) && fuse_aligned(mflat, 16) && fuse_aligned(out_img, 16) &&
+                      fuse_aligned(bpm, 4) && fuse_aligned(out_mask, 4) && fuse_aligned(crmask, 4) &&
+                      (RH + FUSE_ROWS - 1) / FUSE_ROWS <= 65535;
+    BBX_REQUIRE(vec4, "bbx_reduce_apply_scan: layout not 4-pixel aligned (use bbx_reduce_apply + bbx_lacosmic)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ChanF32 gn;
+    for (int i = 0; i < BBX_NCHAN; i++) gn.v[i] = gain_h ? gain_h[i] : 1.0f;
+    ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits->bad, bits->saturated,
+                   seeds, seed_count, seed_cap, (unsigned int)(bits->saturated | bits->satcon)};
+    const size_t n = (size_t)(RH * RW);
+    SparseWork w = carve_sparse(lac_work, n);
+    FuseArgs f;
+    f.crmask = crmask;
+    f.prm = lac_make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
+    f.w = w;
+    f.info = lac_info;
+    if (seeds) BBX_CUDA(cudaMemsetAsync(seed_count, 0, sizeof(unsigned int), st));
+    // what bbx_lacosmic_begin does for the lazy path, with the sample taken through the fused pass's
+    // own arithmetic on the raw frame
+    BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned int) * BG_SAMPLES)));
+        attr_set = true;
+    }
+    if (raw_type == BBX_RAW_U16)
+        sp_bg_gather_raw_kernel<uint16_t><<<BG_SAMPLES / 1024, 1024, 0, st>>>((const uint16_t *)raw, *g, gn, a, w);
+    else
+        sp_bg_gather_raw_kernel<float><<<BG_SAMPLES / 1024, 1024, 0, st>>>((const float *)raw, *g, gn, a, w);
+    sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(w);
+    sp_init_kernel<<<1, 32, 0, st>>>(lac_info, INFO_NCR + niter, w.cnt, 0u);
+    const dim3 grid((unsigned int)((RW / 4 + FUSE_THREADS - 1) / FUSE_THREADS), (unsigned int)((RH + FUSE_ROWS - 1) / FUSE_ROWS));
+    if (raw_type == BBX_RAW_U16)
+        reduce_apply_scan_kernel<uint16_t><<<grid, FUSE_THREADS, 0, st>>>((const uint16_t *)raw, *g, gn, a, f);
+    else
+        reduce_apply_scan_kernel<float><<<grid, FUSE_THREADS, 0, st>>>((const float *)raw, *g, gn, a, f);
+    BBX_CHECK_LAUNCH("bbx_reduce_apply_scan");
+    return 0;
+}
+
 extern "C" size_t bbx_lacosmic_work_bytes(int H, int W)
 {
     const size_t a = lac_dense_work_bytes(H, W), b = lac_sparse_work_bytes(H, W);
@@ -916,8 +1251,9 @@ extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8
 {
     BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
     BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
-    BBX_REQUIRE(mode >= 0 && mode <= 2, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense, 2 = lazy with background level)", mode);
+    BBX_REQUIRE(mode >= 0 && mode <= 3, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense, 2 = lazy with background level, 3 = lazy, scanned by bbx_reduce_apply_scan)", mode);
     BBX_REQUIRE((long long)H * W < 4294967295LL, "bbx_lacosmic_begin: image too large for 32-bit pixel indices");
+    if (mode == 3) return 0;                     // bbx_reduce_apply_scan has done it
     if (mode == 1) return lac_dense_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
     return sparse_begin(img, inmask, crmask, H, W, niter, mode == 2, work, out_info, (cudaStream_t)stream);
 }
@@ -930,7 +1266,8 @@ extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t
     BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_iteration: null argument");
     const LacParams prm = lac_make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
     if (mode == 1) return lac_dense_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
-    return sparse_iteration(img, inmask, crmask, H, W, prm, iter, mode == 2, work, out_info, (cudaStream_t)stream);
+    return sparse_iteration(img, inmask, crmask, H, W, prm, iter, mode == 2, work, out_info, (cudaStream_t)stream,
+                            mode == 3);
 }
 
 extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,

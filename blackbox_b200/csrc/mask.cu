@@ -6,6 +6,7 @@
 // in the spare bit BBX_TMP_SAT (0x80) of the mask; bbx_fill_sat_holes clears it at the end.
 #include <cooperative_groups.h>
 #include "bbx_common.cuh"
+#include "bg_track.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -519,6 +520,15 @@ __device__ __forceinline__ void byte_or(uint8_t *base, size_t p, unsigned int bi
     unsigned int *word = reinterpret_cast<unsigned int *>(base + (p & ~(size_t)3));
     atomicOr(word, bits << ((unsigned int)(p & 3) * 8));
 }
+// the same on the frame mask, telling LACosmic's background statistics when this was the first
+// bit of the byte (bg_track.cuh: the pixel was counted as unmasked by the fused pass)
+__device__ __forceinline__ void mask_or(uint8_t *mask, size_t p, unsigned int bits, const BgTrack &trk)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(mask + (p & ~(size_t)3));
+    const unsigned int sh = (unsigned int)(p & 3) * 8;
+    const unsigned int old = atomicOr(word, bits << sh);
+    if (((old >> sh) & 0xffu) == 0 && bits != 0) bg_untrack(trk, p);
+}
 __device__ __forceinline__ void byte_and(uint8_t *base, size_t p, unsigned int bits)
 {
     unsigned int *word = reinterpret_cast<unsigned int *>(base + (p & ~(size_t)3));
@@ -538,7 +548,7 @@ __device__ __forceinline__ unsigned int seed_len(const unsigned int *count, unsi
 __global__ void __launch_bounds__(128)
 ms_neigh_kernel(uint8_t *mask, int H, int W, int ysc, int xsc, unsigned int bit_xtalk, unsigned int bit_satcon,
                 const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
-                int32_t *status)
+                int32_t *status, BgTrack trk)
 {
     const unsigned int n = seed_len(count, cap, status);
     // 24 work items per seed: 15 victims + 8 neighbours (+1 idle)
@@ -556,14 +566,14 @@ ms_neigh_kernel(uint8_t *mask, int H, int W, int ysc, int xsc, unsigned int bit_
             if (k == src) continue;
             const int vr = k / 8, vc = k % 8;
             const int vy = (vr == r) ? ly : (ysc - 1 - ly);
-            byte_or(mask, (size_t)(vr * ysc + vy) * W + (size_t)vc * xsc + lx, bit_xtalk);
+            mask_or(mask, (size_t)(vr * ysc + vy) * W + (size_t)vc * xsc + lx, bit_xtalk, trk);
         } else {
             const int j = k - 16;                     // 8 neighbours, skipping the centre
             const int o = j < 4 ? j : j + 1;
             const int qy = y + o / 3 - 1, qx = x + o % 3 - 1;
             if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
             const size_t q = (size_t)qy * W + qx;
-            if (!(mask[q] & BBX_TMP_SAT)) byte_or(mask, q, bit_satcon);
+            if (!(mask[q] & BBX_TMP_SAT)) mask_or(mask, q, bit_satcon, trk);
         }
     }
 }
@@ -671,7 +681,7 @@ ms_close_kernel(const uint8_t *__restrict__ mask, HoleWork hw, int H, int W, uns
 __global__ void __launch_bounds__(128)
 ms_commit_seeds_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bit_satcon,
                        const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count, unsigned int cap,
-                       const int32_t *__restrict__ unconverged, int32_t *status)
+                       const int32_t *__restrict__ unconverged, int32_t *status, BgTrack trk)
 {
     if (*unconverged) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 2); return; }
     const unsigned int n = min(*count, cap);
@@ -684,13 +694,13 @@ ms_commit_seeds_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bi
         const int qy = y + k / 5 - 2, qx = x + k % 5 - 2;
         if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
         const size_t q = (size_t)qy * W + qx;
-        if (hw.S[q] == 0 && (mask[q] & 0x7fu) == 0) byte_or(mask, q, bit_satcon);
+        if (hw.S[q] == 0 && (mask[q] & 0x7fu) == 0) mask_or(mask, q, bit_satcon, trk);
     }
 }
 
 __global__ void __launch_bounds__(256)
 ms_commit_tiles_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bit_satcon,
-                       const int32_t *__restrict__ unconverged)
+                       const int32_t *__restrict__ unconverged, BgTrack trk)
 {
     if (*unconverged) return;
     const int ntiles = hw.counters[0];
@@ -702,7 +712,7 @@ ms_commit_tiles_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bi
             const int gy = y0 + i / HOLE_TILE, gx = x0 + i % HOLE_TILE;
             if (gy >= H || gx >= W) continue;
             const size_t q = (size_t)gy * W + gx;
-            if (hw.S[q] == 1 && !hole_free_line(hw, gy, gx) && (mask[q] & 0x7fu) == 0) byte_or(mask, q, bit_satcon);
+            if (hw.S[q] == 1 && !hole_free_line(hw, gy, gx) && (mask[q] & 0x7fu) == 0) mask_or(mask, q, bit_satcon, trk);
         }
     }
 }
@@ -724,6 +734,20 @@ extern "C" int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan
                                      unsigned int seed_cap, void *work, int32_t *labels, int32_t *out_nobj, int rounds,
                                      int32_t *status, void *stream)
 {
+    return bbx_mask_morph_sparse_track(mask, H, W, ysize_chan, xsize_chan, bits, seeds, seed_count, seed_cap, work,
+                                       labels, out_nobj, rounds, status, nullptr, nullptr, stream);
+}
+
+// The same after bbx_reduce_apply_scan: img / lac_work (the reduced image and LACosmic's work
+// buffer of that call) let the morphology take every pixel it masks for the first time out of the
+// background statistics the fused pass has collected against the seed mask.
+extern "C" int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                           const bbx_maskbits *bits, const unsigned int *seeds,
+                                           const unsigned int *seed_count, unsigned int seed_cap, void *work,
+                                           int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
+                                           const float *img, void *lac_work, void *stream)
+{
+    const BgTrack trk = lac_sparse_bg_track(img, lac_work, H, W);
     BBX_REQUIRE(mask && bits && seeds && seed_count && work && labels && out_nobj && status, "bbx_mask_morph_sparse: null argument");
     BBX_REQUIRE(H == 2 * ysize_chan && W == 8 * xsize_chan, "bbx_mask_morph_sparse: %d x %d is not 2 x 8 channels of %d x %d", H, W, ysize_chan, xsize_chan);
     BBX_REQUIRE(((uintptr_t)mask & 3) == 0, "bbx_mask_morph_sparse: mask must be 4-byte aligned");
@@ -735,7 +759,7 @@ extern "C" int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan
     const unsigned int mbits = (unsigned int)(bits->saturated | bits->satcon);
     BBX_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     ms_neigh_kernel<<<lb, 128, 0, s>>>(mask, H, W, ysize_chan, xsize_chan, (unsigned int)bits->crosstalk,
-                                       (unsigned int)bits->satcon, seeds, seed_count, seed_cap, status);
+                                       (unsigned int)bits->satcon, seeds, seed_count, seed_cap, status, trk);
     ms_ccl_init_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
     ms_ccl_merge_kernel<<<lb, 128, 0, s>>>(mask, H, W, seeds, seed_count, seed_cap, labels);
     ms_ccl_count_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
@@ -750,8 +774,8 @@ extern "C" int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan
     int32_t *unconverged = status + 1;           // status[1]: scratch word of the propagation
     if (launch_propagate(hw, H, W, rounds, unconverged, s)) return -2;
     ms_commit_seeds_kernel<<<lb, 128, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, seeds, seed_count, seed_cap,
-                                              unconverged, status);
-    ms_commit_tiles_kernel<<<BBX_SM_COUNT * 2, 256, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, unconverged);
+                                              unconverged, status, trk);
+    ms_commit_tiles_kernel<<<BBX_SM_COUNT * 2, 256, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, unconverged, trk);
     ms_clear_marker_kernel<<<lb, 128, 0, s>>>(mask, seeds, seed_count, seed_cap, unconverged);
     BBX_CHECK_LAUNCH("bbx_mask_morph_sparse");
     return 0;

@@ -52,7 +52,7 @@ class FramePipeline:
 
     def __init__(self, tel, raw_shape, mbias=None, mflat=None, bpm=None, coeffs=None, niter=None,
                  xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True, use_graphs=False,
-                 fill_edge=False):
+                 fill_edge=False, fuse_scan=True):
         self.tel = tel
         self.device = device if device is not None else R._device()
         self.geom = Geometry.from_raw_shape(tuple(raw_shape), xbin=xbin, ybin=ybin, tel=tel)
@@ -86,6 +86,7 @@ class FramePipeline:
         self.ncosmic = self.st.ncosmic
         # optional last step of blackbox_reduce (blackbox.py:1958-1974): edge pixels -> channel median
         self.fill_edge = bool(fill_edge)
+        self.fuse_scan = bool(fuse_scan)          # LACosmic's dense scan inside the fused per-pixel pass
         self.chan_med = torch.zeros(self.geom.nchans, dtype=torch.float32, device=dev)
         self._cm_work = (torch.empty(R.query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=dev)
                          if self.fill_edge else None)
@@ -230,12 +231,27 @@ class FramePipeline:
             else:
                 self._run(name, key + tuple(extra), fn)
 
-        run('apply', lambda: R.apply_enqueue(
-            raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias, mflat=self.mflat,
-            bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
-            mwork=None if dense_morph else self.mwork))
-        run('mask_morph', lambda: R.mask_morph_enqueue(
-            out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=not dense_morph))
+        # The usual case fuses the dense Laplacian scan of LACosmic's first iteration into the
+        # per-pixel pass (the image is scanned while it is made); the rare repeats -- dense
+        # morphology, LACosmic with the background level up front or densely -- take the passes apart.
+        fused = (self.fuse_scan and not dense_morph and lac_mode == R.LAC_LAZY and self.niter > 0
+                 and R.fusable(geom, raw_t, out_img, out_mask, self.mbias, self.mflat, self.bpm, self.crmask))
+        lac_args = (get_par(set_bb.sigclip, tel), get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel))
+        if fused:
+            run('apply', lambda: R.apply_scan_enqueue(
+                raw_t, geom, tel, self.st, self._gain_for(raw_t), self.mbias, self.mflat, self.bpm, out_img, out_mask,
+                self.mwork, self.crmask, lac_args[0], lac_args[1], lac_args[2], self.niter, self.lwork,
+                readnoise_dev=self.means[1:]))
+            run('mask_morph', lambda: R.mask_morph_enqueue(
+                out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=True, track=(out_img, self.lwork)))
+            lac_mode = R.LAC_FUSED
+        else:
+            run('apply', lambda: R.apply_enqueue(
+                raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias, mflat=self.mflat,
+                bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,
+                mwork=None if dense_morph else self.mwork))
+            run('mask_morph', lambda: R.mask_morph_enqueue(
+                out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=not dense_morph))
         if dense_morph:
             R.mask_morph_finish(out_mask, tel, self.mwork, sparse=False)
         if self.niter > 0:
@@ -247,7 +263,8 @@ class FramePipeline:
                                    self.niter, self.lwork, readnoise_dev=self.means[1:], mode=lac_mode)
 
             def lac_finish():
-                call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW, int(lac_mode),
+                call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW,
+                     int(R.LAC_LAZY if lac_mode == R.LAC_FUSED else lac_mode),
                      R._ptr(self.lwork.buf), R._ptr(self.mwork.labels), R._ptr(self.ncosmic), R._stream())
 
             run('lacosmic', lac)

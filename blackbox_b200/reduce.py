@@ -320,6 +320,31 @@ def apply_enqueue(raw_t, geom, tel_, st=None, gain=None, mbias=None, mflat=None,
     return out_img, out_mask
 
 
+def fusable(geom, raw_t, *tensors):
+    """bbx_reduce_apply_scan needs the 4-pixel-aligned layout: channel width, tile width and frame
+    width multiples of 4, 16-byte aligned buffers (torch allocations are), at most 65535 x 32 rows."""
+    if geom.xsize_chan % 4 or geom.dx % 4 or geom.W % 4 or geom.red_shape[0] > 65535 * 32:
+        return False
+    return all(t is None or t.data_ptr() % 16 == 0 for t in (raw_t,) + tensors)
+
+
+def apply_scan_enqueue(raw_t, geom, tel_, st, gain, mbias, mflat, bpm, out_img, out_mask, mwork, crmask,
+                       sigclip, sigfrac, objlim, niter, lwork, readnoise=0.0, readnoise_dev=None):
+    """Enqueue the fused per-pixel pass TOGETHER with the dense Laplacian scan of detect_cosmics'
+    first iteration (include/bbx.h: bbx_reduce_apply_scan).  To be followed by
+    ``mask_morph_enqueue(..., track=(out_img, lwork))`` and ``lacosmic_enqueue(..., mode=LAC_FUSED)``
+    with the same thresholds, work buffer and cosmic-ray mask."""
+    g = geom.as_struct()
+    bits = _bits(tel_)
+    gain_h = _harr([float(x) for x in gain], C.c_float) if gain is not None else None
+    call('bbx_reduce_apply_scan', _ptr(raw_t), _raw_type(raw_t), C.byref(g), gain_h, _ptr(st.vos_fit), _ptr(st.oscan),
+         _ptr(mbias), _ptr(mflat), _ptr(bpm), _ptr(st.satlevel), C.byref(bits), _ptr(out_img), _ptr(out_mask),
+         _ptr(mwork.seeds), _ptr(mwork.seed_count), int(mwork.seed_cap), _ptr(crmask),
+         float(np.float32(sigclip)), float(np.float32(sigfrac)), float(np.float32(objlim)),
+         float(np.float32(readnoise)), _ptr(readnoise_dev), int(niter), _ptr(lwork.buf), _ptr(lwork.info), _stream())
+    return out_img, out_mask
+
+
 def os_corr(data, header, imgtype, xbin=1, ybin=1, data_limit=2000, tel=None, strict=True,
             return_state=False):
     """Overscan correction; returns the cropped float32 frame and fills the header keywords
@@ -425,18 +450,23 @@ class MaskWork:
         self.status = status if status is not None else torch.zeros(2, dtype=torch.int32, device=device)
 
 
-def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=4096, sparse=True):
+def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=4096, sparse=True, track=None):
     """Enqueue crosstalk-victim / saturated-connected / NOBJ-SAT / fill_sat_holes on a mask
     that carries the saturation marker written by bbx_reduce_apply.  ``sparse``: driven by the
-    seed list in ``work`` (filled by apply_enqueue(..., mwork=work)); otherwise dense passes."""
+    seed list in ``work`` (filled by apply_enqueue(..., mwork=work)); otherwise dense passes.
+    ``track``: (reduced image, LacosmicWork) after ``apply_scan_enqueue`` -- the morphology then
+    keeps LACosmic's background statistics right for the pixels it masks."""
     H, W = mask_t.shape
     bits = _bits(tel_)
     s = _stream()
     if sparse:
-        call('bbx_mask_morph_sparse', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), _ptr(work.seeds),
+        img_t, lwork = track if track is not None else (None, None)
+        call('bbx_mask_morph_sparse_track', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), _ptr(work.seeds),
              _ptr(work.seed_count), int(work.seed_cap), _ptr(work.holes), _ptr(work.labels), _ptr(work.nobj),
-             int(rounds), _ptr(work.status), s)
+             int(rounds), _ptr(work.status), _ptr(img_t), _ptr(lwork.buf) if lwork is not None else None, s)
         return
+    if track is not None:
+        raise ValueError('mask_morph_enqueue: tracking needs the sparse morphology')
     work.status.zero_()
     call('bbx_mask_sat_neighbours', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), s)
     if count_objects:
@@ -579,7 +609,7 @@ class LacosmicWork:
         self.info = info if info is not None else torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
 
 
-LAC_LAZY, LAC_DENSE, LAC_LAZY_BG = 0, 1, 2
+LAC_LAZY, LAC_DENSE, LAC_LAZY_BG, LAC_FUSED = 0, 1, 2, 3      # LAC_FUSED: after apply_scan_enqueue
 LAC_STATUS_OVERFLOW, LAC_STATUS_NEED_BG = 1, 2
 
 

@@ -145,6 +145,25 @@ int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g, const flo
                      unsigned int *seeds, unsigned int *seed_count, unsigned int seed_cap,
                      void *stream);
 
+/* bbx_reduce_apply AND the dense Laplacian scan of detect_cosmics' first iteration (the call at
+ * blackbox.py:4323-4332 comes right after mask_init and the flat division) in ONE pass over the
+ * frame: the reduced image is scanned for cosmic-ray candidates while it is being made, so
+ * LACosmic does not read back the 446 MB the fused pass has just written.  Same arguments as
+ * bbx_reduce_apply (out_mask required), plus those of bbx_lacosmic; the call also does what
+ * bbx_lacosmic_begin does.  Afterwards: bbx_mask_morph_sparse_track (which corrects the background
+ * statistics -- taken here against the seed mask -- for the pixels it masks), then
+ * bbx_lacosmic_iteration(..., mode 3) for iter = 0 .. niter-1 with the SAME thresholds and work
+ * buffer, bbx_lacosmic_finish(mode 0).  Bit-identical to the separate calls.  Requires the
+ * 4-pixel-aligned layout (xsize_chan, dx, W multiples of 4; 16-byte aligned images). */
+int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                          const double *vos_fit, const double *oscan, const float *mbias,
+                          const float *mflat, const uint8_t *bpm, const double *satlevel,
+                          const bbx_maskbits *bits, float *out_img, uint8_t *out_mask,
+                          unsigned int *seeds, unsigned int *seed_count, unsigned int seed_cap,
+                          uint8_t *crmask, float sigclip, float sigfrac, float objlim, float readnoise,
+                          const double *readnoise_dev, int niter, void *lac_work, long long *lac_info,
+                          void *stream);
+
 /* satlevel[i] = sat_e_h[i] - biasm[i] on the device (blackbox.py:4448-4454) */
 int bbx_satlevels(const double *sat_e_h, const double *biasm, double *out_satlevel,
                   void *stream);
@@ -188,6 +207,14 @@ int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan, int xsize
                           const unsigned int *seed_count, unsigned int seed_cap, void *work,
                           int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
                           void *stream);
+
+/* bbx_mask_morph_sparse after bbx_reduce_apply_scan: img = the reduced image, lac_work = the
+ * LACosmic work buffer of that call (both may be null: plain bbx_mask_morph_sparse) */
+int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
+                                const bbx_maskbits *bits, const unsigned int *seeds,
+                                const unsigned int *seed_count, unsigned int seed_cap, void *work,
+                                int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
+                                const float *img, void *lac_work, void *stream);
 
 /* number of 8-connected components of (mask & bit) != 0  (ndimage.label; blackbox.py:4354,
  * 4544).  labels: int32 [H*W] scratch; out_count device int32. */
@@ -250,6 +277,8 @@ int bbx_stack_clipped_median(const float *const *frames_h, const float *scale_h,
  *        1 = dense: every intermediate image is materialised
  *        2 = lazy, with the global background level (lower median of the unmasked input
  *            pixels) computed up front by three extra passes over image + mask
+ *        3 = lazy, the dense pass already done by bbx_reduce_apply_scan (bbx_lacosmic_iteration
+ *            only; bbx_lacosmic_begin is a no-op)
  * out_info int64 [4 + niter] device: [0] iterations run, [1] internal, [2] status bits
  * (BBX_LAC_OVERFLOW: a work list overflowed -> result incomplete, repeat with mode 1;
  * BBX_LAC_NEED_BG (mode 0 only): a cosmic-ray pixel without any usable neighbour in its 5x5

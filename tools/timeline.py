@@ -55,6 +55,25 @@ def analyse(path, frames):
     print('idle gaps > 5 us: %d, total %.3f ms; largest:' % (len(gaps), sum(g[1] for g in gaps) / 1e3))
     for at, g in sorted(gaps, key=lambda x: -x[1])[:8]:
         print('   at %.3f ms: %.1f us' % (at / 1e3, g))
+    # per kernel: device time per frame, and the part of it during which nothing else was resident
+    # ("alone": what the kernel really costs the frame rate)
+    bounds = sorted(set([e['ts'] for e in kern] + [e['ts'] + e['dur'] for e in kern]))
+    import bisect
+    cover = [0] * (len(bounds) - 1)
+    for e in kern:
+        a, b = bisect.bisect_left(bounds, e['ts']), bisect.bisect_left(bounds, e['ts'] + e['dur'])
+        for i in range(a, b):
+            cover[i] += 1
+    tot, alone = {}, {}
+    for e in kern:
+        name = e['name'].split('(')[0].split('<')[0][-44:]
+        a, b = bisect.bisect_left(bounds, e['ts']), bisect.bisect_left(bounds, e['ts'] + e['dur'])
+        tot[name] = tot.get(name, 0.0) + e['dur']
+        alone[name] = alone.get(name, 0.0) + sum(bounds[i + 1] - bounds[i] for i in range(a, b) if cover[i] == 1)
+    print('%-46s %10s %10s   (us per frame)' % ('kernel', 'device', 'alone'))
+    for name in sorted(tot, key=lambda n: -alone[n])[:28]:
+        print('%-46s %10.1f %10.1f' % (name, tot[name] / frames, alone[name] / frames))
+    print('%-46s %10.1f %10.1f' % ('TOTAL', sum(tot.values()) / frames, sum(alone.values()) / frames))
     if rt:
         h0 = min(e['ts'] for e in rt)
         h1 = max(e['ts'] + e['dur'] for e in rt)
