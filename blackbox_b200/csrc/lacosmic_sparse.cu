@@ -360,8 +360,11 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
 // of the chain after the fused pass itself).
 //   * a thread owns 4 columns and walks down FUSE_ROWS rows plus one halo row at either end,
 //     holding the reduced values of three consecutive rows in registers; left / right neighbours
-//     come from the neighbouring lanes, and across a warp edge from apply_value_at (the same
-//     arithmetic on one pixel);
+//     come from the neighbouring lanes by shuffle.  The first and the last lane of a warp are
+//     halo lanes: they compute their 4 columns like everybody else but own nothing (a warp covers
+//     128 columns and owns 120), so no thread ever needs a pixel outside its warp.  (The first
+//     version had the edge lanes evaluate the missing neighbour pixel by pixel: two dependent
+//     chains of scattered loads per row and warp, 2.2 ms per frame.);
 //   * the statistics of the background level are taken against the SEED mask (bad-pixel mask,
 //     non-finite, saturated: all the fused pass knows); the mask morphology that follows takes every
 //     pixel it masks for the first time out again (bg_untrack, called where mask.cu sets a bit in
@@ -395,8 +398,11 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
 {
     const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
     const int lane = threadIdx.x & 31;
-    const int x = (blockIdx.x * FUSE_THREADS + threadIdx.x) * 4;
-    const bool live = x < RW;                                  // whole warps stay: the lanes shuffle
+    // warp w of the grid row covers the 4-column groups 30 w - 1 .. 30 w + 30 and owns 30 w .. 30 w + 29
+    const int gwarp = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5);
+    const int x = (gwarp * 30 + lane - 1) * 4;
+    const bool live = x >= 0 && x < RW;                        // whole warps stay: the lanes shuffle
+    const bool own_col = live && lane >= 1 && lane <= 30;
     const int xs = live ? x : 0;
     const int c = xs / g.xsize_chan, lx = xs - c * g.xsize_chan;
     const int ya = blockIdx.y * FUSE_ROWS, yb = min(ya + FUSE_ROWS, RH);
@@ -464,7 +470,7 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
                 out.v[k] = w;
                 mout |= m << (8 * k);
             }
-            if (own) {
+            if (own && own_col) {
                 const size_t oo = (size_t)y * RW + x;
                 if (a.seeds && any_seed) {
 #pragma unroll
@@ -490,18 +496,13 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
         } else {
             out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.f;
         }
-        // horizontal neighbours: the lanes either side; across the warp edge the pixel itself
+        // horizontal neighbours: the lanes either side (the owning lanes 1 .. 30 always have both)
         out.l = __shfl_up_sync(0xffffffffu, out.v[3], 1);
         out.r = __shfl_down_sync(0xffffffffu, out.v[0], 1);
-        if (live && own) {                                     // (halo rows only lend their own columns)
-            uint32_t dummy;
-            if (lane == 0) out.l = x > 0 ? apply_value_at<T>(raw, g, gain, a, y, x - 1, dummy) : 0.f;
-            if (lane == 31 || x + 4 >= RW) out.r = x + 4 < RW ? apply_value_at<T>(raw, g, gain, a, y, x + 4, dummy) : 0.f;
-        }
     };
     // L+ of the 4 pixels of row y: U / D are the rows above / below (hu / hd: they exist)
     auto laplace_row = [&](int y, const RowV &U, const RowV &Cn, const RowV &D, bool hu, bool hd) {
-        if (!live) return;
+        if (!own_col) return;
         const unsigned int pix = (unsigned int)((size_t)y * RW + x);
         const float cc[6] = {Cn.l, Cn.v[0], Cn.v[1], Cn.v[2], Cn.v[3], Cn.r};
         if (hu && hd && x > 0 && x + 4 < RW) {
@@ -1231,7 +1232,8 @@ extern "C" int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_ge
         sp_bg_gather_raw_kernel<float><<<BG_SAMPLES / 1024, 1024, 0, st>>>((const float *)raw, *g, gn, a, w);
     sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(w);
     sp_init_kernel<<<1, 32, 0, st>>>(lac_info, INFO_NCR + niter, w.cnt, 0u);
-    const dim3 grid((unsigned int)((RW / 4 + FUSE_THREADS - 1) / FUSE_THREADS), (unsigned int)((RH + FUSE_ROWS - 1) / FUSE_ROWS));
+    const long long warps_x = (RW / 4 + 29) / 30;             // a warp owns 30 groups of 4 columns
+    const dim3 grid((unsigned int)((warps_x + FUSE_THREADS / 32 - 1) / (FUSE_THREADS / 32)), (unsigned int)((RH + FUSE_ROWS - 1) / FUSE_ROWS));
     if (raw_type == BBX_RAW_U16)
         reduce_apply_scan_kernel<uint16_t><<<grid, FUSE_THREADS, 0, st>>>((const uint16_t *)raw, *g, gn, a, f);
     else
