@@ -419,15 +419,17 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
     struct RowIn { float v[4]; float4 mb, mf; uint32_t mm; double fitv; };
     struct RowV { float v[4]; float l, r; };
     auto load_row = [&](int y, RowIn &in) {
+        in.mb = make_float4(0.f, 0.f, 0.f, 0.f);
+        in.mf = make_float4(1.f, 1.f, 1.f, 1.f);
+        in.mm = 0;
+        in.fitv = 0.0;
+        in.v[0] = in.v[1] = in.v[2] = in.v[3] = 0.f;
         if (!live) return;
         const int r = (y >= g.ysize_chan) ? 1 : 0;             // ny == 2
         const int rr = (r == 0 ? g.data_y0_bot : g.data_y0_top) + (y - r * g.ysize_chan);
         const size_t ro = (size_t)rr * g.W + (size_t)c * g.dx + lx;
         const size_t oo = (size_t)y * RW + x;
         RawVec4<T>::load(raw + ro, in.v);
-        in.mb = make_float4(0.f, 0.f, 0.f, 0.f);
-        in.mf = make_float4(1.f, 1.f, 1.f, 1.f);
-        in.mm = 0;
         if (has_bias) in.mb = __ldcs(reinterpret_cast<const float4 *>(a.mbias + oo));
         if (has_flat) in.mf = __ldcs(reinterpret_cast<const float4 *>(a.mflat + oo));
         if (a.bpm) in.mm = __ldcs(reinterpret_cast<const unsigned int *>(a.bpm + oo));
@@ -554,39 +556,25 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
         }
     };
 
-    // rows ya-1 .. yb (clipped to the frame); three rows of values rotate through A, B, C
-    const int y0 = max(ya - 1, 0), y1 = min(yb, RH - 1);
-    RowIn in0, in1;
-    RowV A, B, C;
-    A.v[0] = A.v[1] = A.v[2] = A.v[3] = A.l = A.r = 0.f;
-    B = A; C = A;
-    load_row(y0, in0);
-    // step(y, in, next_in, P, Q, R): prefetch row y+1, finish row y into R, then the Laplacian of
-    // row y-1 (in Q) between P (row y-2) and R (row y)
-    auto step = [&](int y, RowIn &in, RowIn &nxt, const RowV &P, const RowV &Q, RowV &R) {
-        if (y + 1 <= y1) load_row(y + 1, nxt);
-        finish_row(y, in, y >= ya && y < yb, R);
+    // rows ya-1 .. yb: row y is finished into R, then the Laplacian of row y-1 (Q) is taken between
+    // P (row y-2) and R.  ONE copy of the loop body (the rows move through P, Q, R by register
+    // copies): unrolled over the rotation it was 11 copies of ~1000 instructions and ran out of the
+    // instruction cache.  Row RH (below the image) is a virtual row: nothing to finish, it only
+    // triggers the Laplacian of the last image row, which has no row below it.
+    const int y0 = max(ya - 1, 0), y1 = yb;
+    RowIn cur, nxt;
+    RowV P, Q, R;
+    P.v[0] = P.v[1] = P.v[2] = P.v[3] = P.l = P.r = 0.f;
+    Q = P; R = P;
+    load_row(y0, cur);
+#pragma unroll 1
+    for (int y = y0; y <= y1; y++) {
+        if (y + 1 <= y1 && y + 1 < RH) load_row(y + 1, nxt);
+        if (y < RH) finish_row(y, cur, y >= ya && y < yb, R);
         const int ym = y - 1;
-        if (ym >= ya && ym < yb && ym >= y0) laplace_row(ym, P, Q, R, ym > 0, true);
-        // the last row of the image has no row below it
-        if (y == RH - 1) laplace_row(y, Q, R, R, y > 0, false);
-    };
-    int y = y0;
-    for (; y + 6 <= y1 + 1; y += 6) {
-        step(y, in0, in1, B, C, A);          // rows: P = y-2, Q = y-1, R = y
-        step(y + 1, in1, in0, C, A, B);
-        step(y + 2, in0, in1, A, B, C);
-        step(y + 3, in1, in0, B, C, A);
-        step(y + 4, in0, in1, C, A, B);
-        step(y + 5, in1, in0, A, B, C);
+        if (ym >= ya && ym >= y0) laplace_row(ym, P, Q, R, ym > 0, y < RH);
+        P = Q; Q = R; cur = nxt;
     }
-    // the remaining 0..5 rows, same rotation
-    const int rem = y1 + 1 - y;
-    if (rem > 0) step(y, in0, in1, B, C, A);
-    if (rem > 1) step(y + 1, in1, in0, C, A, B);
-    if (rem > 2) step(y + 2, in0, in1, A, B, C);
-    if (rem > 3) step(y + 3, in1, in0, B, C, A);
-    if (rem > 4) step(y + 4, in0, in1, C, A, B);
     const unsigned int tv = (unsigned int)warp_sum((int)n_valid), tb = (unsigned int)warp_sum((int)n_below);
     if (lane == 0) {
         if (tv) atomicAdd(&f.w.bg->n_valid, (unsigned long long)tv);
