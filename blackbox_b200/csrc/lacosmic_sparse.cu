@@ -373,7 +373,7 @@ sp_scan_kernel(const float *__restrict__ img, const uint8_t *__restrict__ inmask
 //     BEFORE the pass (sp_bg_gather_raw_kernel).
 // --------------------------------------------------------------------------------------------
 #define FUSE_THREADS 128
-#define FUSE_ROWS 32
+#define FUSE_ROWS 64
 
 struct FuseArgs {
     uint8_t *crmask;
@@ -393,7 +393,7 @@ __device__ __forceinline__ void bg_count(float v, unsigned int key_a, unsigned i
 }
 
 template <typename T>
-__global__ void __launch_bounds__(FUSE_THREADS)
+__global__ void __launch_bounds__(FUSE_THREADS, 6)
 reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a, FuseArgs f)
 {
     const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
@@ -408,6 +408,8 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
     const int ya = blockIdx.y * FUSE_ROWS, yb = min(ya + FUSE_ROWS, RH);
     const bool has_bias = a.mbias != nullptr, has_flat = a.mflat != nullptr;
     const unsigned int key_a = f.w.bg->key_a, width = f.w.bg->width;
+    const bool raw_bits = key_a >= 0x80000000u;
+    const int lo_bits = (int)(key_a & 0x7fffffffu);
     const float thr_lo = lac_thr_lo(f.prm);
     const float thr_s = __fmul_rd(thr_lo, thr_lo >= 0.f ? 0.99999952316284f : 1.00000047683716f);   // thr_lo (1 -+ 2^-21)
     unsigned int n_valid = 0, n_below = 0;
@@ -490,10 +492,23 @@ reduce_apply_scan_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, Ap
                 // what the dense scan cleared: the cosmic-ray mask and LACosmic's flag bytes
                 __stcs(reinterpret_cast<unsigned int *>(f.crmask + oo), 0u);
                 __stcs(reinterpret_cast<unsigned int *>(f.w.flags + oo), 0u);
-                // background statistics against the seed mask
+                // background statistics against the seed mask.  Nearly every group is unmasked and
+                // the bracket starts at a non-negative value: then the order-preserving keys are the
+                // raw float bits (see sp_scan_kernel) and the four pixels cost four compares
+                if (mout == 0 && raw_bits) {
+                    n_valid += 4;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (((mout >> (8 * k)) & 0xffu) == 0) bg_count(out.v[k], key_a, width, n_valid, n_below, f.w.bghist);
+                    for (int k = 0; k < 4; k++) {
+                        const int bits = __float_as_int(out.v[k]);
+                        n_below += bits < lo_bits;
+                        const unsigned int d = (unsigned int)bits - (unsigned int)lo_bits;
+                        if (d < width) atomicAdd(&f.w.bghist[d], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (((mout >> (8 * k)) & 0xffu) == 0) bg_count(out.v[k], key_a, width, n_valid, n_below, f.w.bghist);
+                }
             }
         } else {
             out.v[0] = out.v[1] = out.v[2] = out.v[3] = 0.f;
