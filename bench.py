@@ -30,7 +30,9 @@ Printed JSON (rank 0, one line):
              5280^2 frames and master flat of 20 full 10560^2 frames, row stripes per GPU, the
              stack-median kernel writing into its slot of the gather buffer, ONE NCCL all-gather
              (distributed.master_combine_sharded; blackbox.py:4908-4984); time = max over ranks,
-             compared bit for bit with the one-GPU combine of the same stack
+             compared bit for bit with the one-GPU combine of the same stack.  fused_allgather: the
+             combine kernel stores every master pixel into every rank's buffer itself over NVLink
+             (symmetric memory: plain peer stores / NVSwitch multicast) -- no NCCL on the data path
   link       measured pinned host<->device copy bandwidth of this rank-0 GPU (H2D alone, D2H
              alone, both at once): the ceiling of every end-to-end number
   cpu_baseline  the CPU oracle (restatement of the reference's numpy/astropy/astroscrappy
@@ -484,31 +486,36 @@ def measure_master_sharded(args, rank, world, dev, barrier):
         ms = timed(sharded)
         ms_kernel = timed(local_only)
         master = sharded()
-        equal, ms_1gpu = None, ms
+        # the same with the all-gather done BY the combine kernel: every master pixel stored into
+        # every rank's buffer over NVLink (symmetric memory), plain peer stores and NVSwitch multicast
+        peer = {}
         if world > 1:
-            flag = torch.ones(1, dtype=torch.int32, device=dev)
-            t1 = torch.zeros(1, dtype=torch.float64, device=dev)
-            if rank == 0:
-                ref = torch.empty(shape, dtype=torch.float32, device=dev)
-                one = lambda: R.master_combine(full, imgtype, medsec=medsec, bpm=bpm, tel=TEL, out=ref)
-                for _ in range(3):
-                    one()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(10):
-                    one()
-                e1.record()
-                torch.cuda.synchronize()
-                t1[0] = e0.elapsed_time(e1) / 10
-                same = torch.equal(master.view(torch.int32), ref.view(torch.int32))
-                flag[0] = 1 if same else 0
-                del ref
-            dist.broadcast(flag, 0)
-            dist.broadcast(t1, 0)
-            equal, ms_1gpu = bool(flag.item()), float(t1.item())
+            for label, mc in (('peer_stores', False), ('multicast', True)):
+                try:
+                    pm = D.PeerMaster(shape, multicast=mc)
+                    if mc and not pm.multicast:
+                        peer[label] = {'unavailable': 'no multicast support on this fabric / torch build'}
+                        continue
+                    fn = lambda: D.master_combine_sharded(stripes, shape, imgtype, medsec=medsec,
+                                                          bpm_stripe=None if bpm is None else bpm[r0:r1], tel=TEL, peers=pm)
+                    ms_p = timed(fn)
+                    got = fn()
+                    same = torch.tensor([1 if torch.equal(got.view(torch.int32), master.view(torch.int32)) else 0],
+                                        dtype=torch.int32, device=dev)
+                    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                    peer[label] = {'ms': ms_p, 'equal_to_allgather_path': bool(same.item())}
+                    del pm, got
+                except Exception as exc:           # symmetric memory not available here: say so, keep the bench alive
+                    peer[label] = {'unavailable': '{}: {}'.format(type(exc).__name__, str(exc)[:200])}
+        equal, ms_1gpu = None, ms
         nbytes = (n + 1) * H * W * 4 + (H * W if bpm is not None else 0)
+        for v in peer.values():
+            if 'ms' in v:
+                v['speedup_vs_1gpu'] = ms_1gpu / v['ms']
+                v['frac'] = nbytes / (v['ms'] * 1e-3) / 1e9 / (peak * world)
+        best = min([ms] + [v['ms'] for v in peer.values() if 'ms' in v and v.get('equal_to_allgather_path')])
         out[name] = {'frames': n, 'shape': [H, W], 'imgtype': imgtype, 'rows_per_gpu': r1 - r0, 'ms': ms,
+                     'fused_allgather': peer, 'ms_best': best, 'speedup_best_vs_1gpu': ms_1gpu / best,
                      'ms_stack_median_stripe': ms_kernel, 'allgather_ms': max(ms - ms_kernel, 0.0),
                      'ms_1gpu': ms_1gpu, 'speedup_vs_1gpu': ms_1gpu / ms, 'equal_to_1gpu': equal,
                      'algorithmic_bytes': nbytes, 'achieved_GBs': nbytes / (ms * 1e-3) / 1e9,

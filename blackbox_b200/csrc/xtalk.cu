@@ -116,13 +116,20 @@ xtalk_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int x
 
 #define XT_TILE 128          // tile positions per CTA pass (= threads per CTA)
 
-template <int MINB>
+// COUNT: also count the pixels per mask bit (mask_header's M-*NUM, blackbox.py:4601-4620; the mask
+// is final when the crosstalk correction runs, and this kernel sees every byte of it exactly once):
+// per warp and only where a warp holds any mask bit at all, per CTA into shared memory, per CTA
+// one atomic per non-zero bit into one of XT_SLOTS spread copies of the eight counters
+#define XT_SLOTS 16
+template <int MINB, bool COUNT>
 __global__ void __launch_bounds__(XT_TILE, MINB)
 xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, int xsc, XtalkCoef k,
-                  uint32_t bits_src_bad, uint32_t bit_edge)
+                  uint32_t bits_src_bad, uint32_t bit_edge, unsigned long long *__restrict__ slots)
 {
     __shared__ __align__(16) float tile[16][XT_TILE];
     __shared__ __align__(16) uint8_t mt[16][XT_TILE];
+    __shared__ unsigned int s_cnt[8];
+    if (COUNT && threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     const int gpr = xsc / 4;                                   // float4 groups per channel row
     const long long ngroups = (long long)ysc * gpr;
     const long long ntiles = (ngroups + XT_TILE / 4 - 1) / (XT_TILE / 4);
@@ -158,6 +165,18 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
             *reinterpret_cast<uint32_t *>(&mt[c][g4 * 4]) = mm[i];
         }
         __syncthreads();
+        if (COUNT) {
+            const uint32_t any = mm[0] | mm[1] | mm[2] | mm[3];
+            if (__any_sync(0xffffffffu, any != 0)) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const uint32_t pl = 0x01010101u << b;
+                    unsigned int v = (unsigned int)(__popc(mm[0] & pl) + __popc(mm[1] & pl) + __popc(mm[2] & pl) + __popc(mm[3] & pl));
+                    v = __reduce_add_sync(0xffffffffu, v);
+                    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[b], v);
+                }
+            }
+        }
         // ---- correct: thread p owns tile position p in all 16 channels
         {
             const int p = threadIdx.x;
@@ -196,7 +215,18 @@ xtalk_tile_kernel(float *img, const uint8_t *__restrict__ mask, int W, int ysc, 
                 *reinterpret_cast<float4 *>(img + off[i]) = *reinterpret_cast<const float4 *>(&tile[c][g4 * 4]);
             }
         }
+        if (COUNT && threadIdx.x < 8 && s_cnt[threadIdx.x])
+            atomicAdd(&slots[(blockIdx.x % XT_SLOTS) * 8 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     }
+}
+
+__global__ void xtalk_count_sum_kernel(const unsigned long long *__restrict__ slots, unsigned long long *__restrict__ out)
+{
+    const int b = threadIdx.x;
+    if (b >= 8) return;
+    unsigned long long t = 0;
+    for (int s = 0; s < XT_SLOTS; s++) t += slots[s * 8 + b];
+    out[b] = t;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -440,9 +470,9 @@ extern "C" int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, 
 // variant 0: the kernel bbx_xtalk picks (the tile kernel when the layout allows, else the generic
 // one); 3: the tile kernel; 5: the TMA-staged persistent kernel (falls back to 0 where the layout
 // does not allow it); 1 / 2 / 4: the generic register-only kernel with that many pixels per thread
-// and channel (parity tests, tools/xt_bench.py).  out_counts (device uint64 [8], may be null):
-// pixels per mask bit of `mask`, zeroed and filled by the call (by the crosstalk kernel itself on
-// the TMA path, by bbx_mask_counts' kernel otherwise).
+// and channel (parity tests, tools/xt_bench.py).  out_counts (device uint64 [BBX_XTALK_COUNTS_LEN],
+// may be null): [0:8] pixels per mask bit of `mask`, filled by the call -- by the crosstalk kernel
+// itself on the tile and TMA paths, by bbx_mask_counts' kernel otherwise; the rest is scratch.
 extern "C" int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                                 const double *coeffs_h, const bbx_maskbits *bits, int variant,
                                 unsigned long long *out_counts, void *stream)
@@ -459,7 +489,6 @@ extern "C" int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, i
         const int rc = xtalk_tma_launch(img, mask, H, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge, out_counts, st);
         if (rc <= 0) return rc;
     }
-    if (out_counts && bbx_mask_counts(mask, (size_t)H * W, out_counts, stream)) return -2;
     const bool px4 = (xsize_chan % 4 == 0) && ((uintptr_t)img % 16) == 0 && ((uintptr_t)mask % 4) == 0;
     if (px4 && (variant == 0 || variant == 3)) {
         const long long ngroups = (long long)ysize_chan * (xsize_chan / 4);
@@ -468,10 +497,20 @@ extern "C" int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, i
         const int blocks = (int)ntiles;
         // register allocation capped for 6 resident CTAs per SM (80 registers, no spills; measured
         // on B200: 5 -> 0.266 ms, 6 -> 0.248 ms, 7 -> 0.249 ms, 8 -> 0.252 ms with spills)
-        xtalk_tile_kernel<6><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad, (uint32_t)bits->edge);
+        if (out_counts) {
+            // the counts ride along: XT_SLOTS spread copies behind the eight results, summed by a 8-thread kernel
+            BBX_CUDA(cudaMemsetAsync(out_counts, 0, (8 + 8 * XT_SLOTS) * sizeof(unsigned long long), st));
+            xtalk_tile_kernel<6, true><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad,
+                                                                  (uint32_t)bits->edge, out_counts + 8);
+            xtalk_count_sum_kernel<<<1, 32, 0, st>>>(out_counts + 8, out_counts);
+        } else {
+            xtalk_tile_kernel<6, false><<<blocks, XT_TILE, 0, st>>>(img, mask, W, ysize_chan, xsize_chan, k, src_bad,
+                                                                   (uint32_t)bits->edge, nullptr);
+        }
         BBX_CHECK_LAUNCH("xtalk_tile_kernel");
         return 0;
     }
+    if (out_counts && bbx_mask_counts(mask, (size_t)H * W, out_counts, stream)) return -2;
     const bool px2 = (xsize_chan % 2 == 0) && ((uintptr_t)img % 8) == 0 && ((uintptr_t)mask % 2) == 0;
     // measured on B200 (10560^2, tools/xt_bench.py): 2 px/thread 0.395 ms, 4 px/thread 0.435 ms
     // (255 registers), 1 px/thread 0.76 ms

@@ -29,6 +29,44 @@ def stripe_bounds(H, rank, world_size):
     return r0, min(r0 + n, H)
 
 
+class PeerMaster:
+    """The gather buffer of the sharded master combine as SYMMETRIC memory: every rank's buffer is
+    mapped into every other rank's address space over NVLink / NVSwitch (``torch.distributed.
+    _symmetric_memory``), so the stack-median kernel stores each master pixel straight into all of
+    them (``bbx_stack_median_multi``) -- compute and all-gather in one kernel, the transfer under
+    the loads, no NCCL call on the data path.  ``multicast``: store once to the NVSwitch multicast
+    address instead and let the switch replicate (needs multicast support on the fabric)."""
+
+    def __init__(self, shape, group=None, device=None, multicast=False):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        H, W = shape
+        self.shape = (H, W)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nrows = stripe_rows(H, self.world)
+        dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.buf = symm.empty((self.world * self.nrows, W), dtype=torch.float32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.multicast = bool(multicast) and bool(getattr(self.hdl, 'has_multicast_support', False)) \
+            and int(getattr(self.hdl, 'multicast_ptr', 0) or 0) != 0
+        self.mc_ptr = int(self.hdl.multicast_ptr) if self.multicast else 0
+
+    def stripe_ptrs(self):
+        """Addresses of THIS rank's slot in every rank's buffer (own buffer first), or the one
+        multicast address of that slot."""
+        off = self.rank * self.nrows * self.shape[1] * 4
+        if self.multicast:
+            return [self.mc_ptr + off]
+        order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+        return [self.ptrs[r] + off for r in order]
+
+    def barrier(self):
+        """All ranks have reached this point of their current streams (device-side, no host sync)."""
+        self.hdl.barrier()
+
+
 def _default_combine(stripes, scales, flat_fix, bpm_stripe, tel, out=None):
     from . import reduce as R
     res, _ = R.master_combine(stripes, 'flat' if flat_fix else 'bias',
@@ -37,7 +75,7 @@ def _default_combine(stripes, scales, flat_fix, bpm_stripe, tel, out=None):
 
 
 def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stripe=None, tel=None,
-                           group=None, combine=None, out=None):
+                           group=None, combine=None, out=None, peers=None):
     """Row-stripe sharded master combine.
 
     stripes     this rank's row stripe of each of the N frames: float32 [r1-r0, W] tensors
@@ -48,6 +86,8 @@ def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stri
     bpm_stripe  flats: this rank's rows of the bad-pixel mask (edge pixels -> 1)
     combine     test hook: callable(stripes, scales, flat_fix, bpm_stripe, tel) -> stripe master
     out         optional float32 [world * stripe_rows(H, world), W] gather buffer to reuse
+    peers       a ``PeerMaster`` of this shape: the combine kernel writes every rank's copy itself
+                over NVLink (no NCCL all-gather); the result is ``peers.buf``
 
     Returns the full (H, W) master on every rank (a view of the gather buffer).  The stack-median
     kernel writes this rank's stripe straight into its slot of the gather buffer and the
@@ -66,6 +106,18 @@ def master_combine_sharded(stripes, shape, imgtype='bias', medsec=None, bpm_stri
     if flat and medsec is None:
         raise ValueError('sharded flat combine needs the MEDSEC normalisation medians')
     dev = stripes[0].device
+    if peers is not None:
+        if combine is not None or tuple(peers.shape) != (H, W) or peers.world > 8:
+            raise ValueError('peer-memory combine: needs the default combine, a PeerMaster of shape {} and at most '
+                             '8 ranks'.format((H, W)))
+        from . import reduce as R
+        peers.barrier()                      # nobody is still reading the previous master out of these buffers
+        if r1 > r0:
+            mine = peers.buf[rank * nrows:rank * nrows + (r1 - r0)]
+            R.master_combine(stripes, 'flat' if flat else 'bias', medsec=medsec if flat else None, bpm=bpm_stripe,
+                             tel=tel, out=mine, out_ptrs=peers.stripe_ptrs(), multicast=peers.multicast)
+        peers.barrier()                      # every stripe has landed everywhere
+        return peers.buf[:H]
     if out is None:
         out = torch.empty((world * nrows, W), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (world * nrows, W) or out.dtype != torch.float32 or not out.is_contiguous():

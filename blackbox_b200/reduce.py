@@ -185,7 +185,7 @@ class OverscanState:
                   ('mstatus', (2,), i32),                     # mask morphology status (bbx_mask_morph_sparse)
                   ('nobj', (1,), i32), ('ncosmic', (1,), i32),
                   ('lacinfo', (4 + max(int(niter), 1),), i64),   # bbx_lacosmic out_info
-                  ('mcounts', (8,), i64)]                     # pixels per mask bit (mask_header)
+                  ('mcounts', (136,), i64)]                   # [0:8] pixels per mask bit (mask_header); rest: scratch of bbx_xtalk_counts
         self.geom = geom
         self._layout = {}
         off = 0
@@ -1064,12 +1064,16 @@ def xtalk_corr(data, crosstalk_file, data_mask=None):
 # master frames
 # -------------------------------------------------------------------------------------------
 def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=None, clip_sigma=None,
-                   clip_maxiters=5):
+                   clip_maxiters=5, out_ptrs=None, multicast=False):
     """Arithmetic core of master_prep (blackbox.py:4908-4984, 5063-5073): per-pixel median of
     the stack; flats are first divided by their normalisation median (``medsec[i]`` = the
     header's MEDSEC, else the median over set_bb.flat_norm_sec) and get edge / non-positive
     pixels set to 1 afterwards.  ``frames``: sequence of float32 arrays / CUDA tensors of one
     shape (or a 3-D array).  Returns (master, scales).
+
+    ``out_ptrs``: raw device addresses (ints) of up to 8 buffers that all receive the result -- this
+    GPU's and its peers' (``distributed.PeerMaster``); ``multicast``: ``out_ptrs[0]`` is an NVSwitch
+    multicast address instead.  ``out`` is then only what is returned.
 
     ``clip_sigma`` (default None = the reference's plain median): sigma-clip every pixel's stack
     first (astropy.stats.sigma_clip, cenfunc='median', ``clip_maxiters`` rounds) and take the
@@ -1104,7 +1108,13 @@ def master_combine(frames, imgtype='bias', medsec=None, bpm=None, tel=None, out=
     scale_h = _harr([float(np.float32(s)) for s in scales], C.c_float)
     flat_fix = 1 if (imgtype == 'flat' and bpm_t is not None) else 0
     edge = int(get_par(set_bb.mask_value, tel)['edge'])
-    if clip_sigma is None:
+    if out_ptrs is not None:
+        if clip_sigma is not None:
+            raise ValueError('master_combine: the clipped combine writes to one buffer')
+        dsts = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        call('bbx_stack_median_multi', ptrs, scale_h, n, out.numel(), flat_fix, _ptr(bpm_t), edge, dsts,
+             len(out_ptrs), int(bool(multicast)), _stream())
+    elif clip_sigma is None:
         call('bbx_stack_median', ptrs, scale_h, n, out.numel(), flat_fix, _ptr(bpm_t), edge, _ptr(out), _stream())
     else:
         call('bbx_stack_clipped_median', ptrs, scale_h, n, out.numel(), float(clip_sigma), int(clip_maxiters),

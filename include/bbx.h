@@ -238,8 +238,10 @@ int bbx_xtalk(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int
 int bbx_xtalk_variant(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                       const double *coeffs_h, const bbx_maskbits *bits, int variant, void *stream);
 /* ... and with the per-bit pixel counts of the mask (mask_header, blackbox.py:4601-4620; the mask
- * is final when the crosstalk correction runs) taken on the way: out_counts device uint64 [8],
- * zeroed and filled by the call (null: not wanted) */
+ * is final when the crosstalk correction runs) taken on the way by the crosstalk kernel, which
+ * sees every mask byte anyway: out_counts device uint64 [BBX_XTALK_COUNTS_LEN], [0:8] = the counts,
+ * the rest scratch (spread partial counters); null: not wanted */
+#define BBX_XTALK_COUNTS_LEN 136
 int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                      const double *coeffs_h, const bbx_maskbits *bits, int variant,
                      unsigned long long *out_counts, void *stream);
@@ -253,6 +255,17 @@ int bbx_xtalk_counts(float *img, const uint8_t *mask, int H, int W, int ysize_ch
 int bbx_stack_median(const float *const *frames_h, const float *scale_h, int N, size_t npix,
                      int flat_fix, const uint8_t *bpm, int edge_value, float *out,
                      void *stream);
+
+/* The same with every master pixel stored to `ndst` (<= 8) buffers at once: outs_h = host array of
+ * device pointers.  For the row-stripe sharded combine (north_star: "the master-frame combine shards
+ * by row stripes ... NCCL only to assemble the stripes") the destinations are this GPU's slot of the
+ * gather buffer and the same slot in every peer's buffer, mapped into this process over NVLink /
+ * NVSwitch (torch symmetric memory): the combine kernel then IS the all-gather, and the transfer
+ * runs under the N loads per pixel instead of after them.  multicast != 0: outs_h[0] (ndst = 1) is
+ * an NVSwitch multicast address, written with multimem.st -- one store, replicated by the switch. */
+int bbx_stack_median_multi(const float *const *frames_h, const float *scale_h, int N, size_t npix,
+                           int flat_fix, const uint8_t *bpm, int edge_value, float *const *outs_h,
+                           int ndst, int multicast, void *stream);
 
 /* Optional sigma-clipped combine (BASELINE.json's wording; the reference's master_prep uses the
  * plain median above, so this is off by default in reduce.master_combine): per pixel

@@ -24,7 +24,7 @@ def run(variant):
          coeffs.ctypes.data_as(C.c_void_p), C.byref(bits), variant, R._ptr(counts) if variant in (0, 5) else None, R._stream())
 
 
-counts = torch.zeros(8, dtype=torch.int64, device='cuda')
+counts = torch.zeros(136, dtype=torch.int64, device='cuda')
 for variant in (0, 5, 4, 2, 1):
     for _ in range(3):
         run(variant)
