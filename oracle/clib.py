@@ -160,3 +160,34 @@ def rice_decode(buf, nx, bytepix):
     if lib().bbo_rice_decode(_p(c), C.c_long(c.size), C.c_long(nx), C.c_int(bytepix), _p(out)) != 0:
         raise ValueError('rice_decode: the stream ends before the tile does')
     return out
+
+
+# names of the recalled-choice switches of oracle/csrc/bbo.c (same order as its enum) and their alternatives
+CHOICES = [
+    ('REBIN_ORDER', {1: '2x2 mean summed column-major ((a+c)+b)+d', 2: '2x2 mean summed pairwise (a+b)+(c+d)'}),
+    ('LAPLACE_ORDER', {1: '4c -left -right -up -down', 2: '4c - ((l+r)+(u+d))'}),
+    ('LAPLACE_EDGE', {1: 'image edge replicated instead of zero padding'}),
+    ('CLEAN_MEDIAN', {1: 'medmask: upper median for even counts', 2: 'medmask: mean of the two middle values'}),
+    ('BACKGROUND_MEDIAN', {1: 'background level: upper median'}),
+    ('SIGCLIP_CMP', {1: "s' >= sigclip / sigcliplow instead of >"}),
+    ('OBJLIM_CMP', {1: "s'/f >= objlim instead of >"}),
+    ('M5_FLOOR', {1: 'med5 <= 0 -> 1e-5 instead of med5 < 1e-5 -> 1e-5', 2: 'no floor on med5'}),
+    ('MEDFILT_FRAME', {1: 'median-filter frame zero instead of a copy of the input'}),
+    ('DILATE3_FRAME', {1: '3x3 dilation zero-padded at the frame instead of copying it'}),
+    ('CLEAN_FRAME', {1: 'cleaning also in the 2-pixel frame'}),
+    ('FINE_MEDIAN7_OF', {1: 'fine structure med3 - med7(image) instead of med3 - med7(med3)'}),
+    ('CLIP_INCLUSIVE', {1: 'sigma clip keeps lo < x < hi instead of lo <= x <= hi'}),
+    ('CLIP_STD_ABOUT', {1: 'sigma clip std about the centre (median) instead of the mean'}),
+    ('CLIP_STOP', {1: 'sigma clip: one more bound computation after maxiters'}),
+]
+
+
+def set_choice(name, value):
+    """Flip one recalled choice of the C oracle (0 = the default this repo implements)."""
+    names = [n for n, _ in CHOICES]
+    assert lib().bbo_num_choices() == len(names)
+    lib().bbo_set_choice(C.c_int(names.index(name)), C.c_int(int(value)))
+
+
+def reset_choices():
+    lib().bbo_reset_choices()

@@ -29,6 +29,40 @@
 #define BBO_API __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------------------------
+ * RECALLED CHOICES.  The two third-party algorithms restated here (astropy's sigma clipping,
+ * astroscrappy 1.0.8's detect_cosmics) cannot be run in this image, so every detail that was
+ * recalled rather than read sits behind a named switch.  Value 0 is what this oracle (and the
+ * CUDA kernels, which implement value 0 only) believe the libraries do; the other values are
+ * the plausible alternatives.  tools/oracle_choice_matrix.py runs the seeded frames through every
+ * alternative and records how many mask / image pixels each one moves
+ * (profiles/r02_oracle_choice_matrix.txt): the day a wheel is available, tools/pin_oracle.py says
+ * which switch, if any, has to flip -- and the matrix says today how much is at stake.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    BBO_CH_REBIN_ORDER = 0,      /* 2x2 block mean: 0 ((a+b)+c)+d row-major, 1 ((a+c)+b)+d column-major, 2 (a+b)+(c+d) */
+    BBO_CH_LAPLACE_ORDER,        /* 0: 4c -right -left -down -up; 1: 4c -left -right -up -down; 2: 4c - ((l+r)+(u+d)) */
+    BBO_CH_LAPLACE_EDGE,         /* 0: neighbours outside the image omitted (zero padding); 1: edge replicated */
+    BBO_CH_CLEAN_MEDIAN,         /* medmask, even count: 0 lower a[(n-1)/2]; 1 upper a[n/2]; 2 mean of the two */
+    BBO_CH_BACKGROUND_MEDIAN,    /* background level, even count: 0 lower; 1 upper */
+    BBO_CH_SIGCLIP_CMP,          /* 0: s' > sigclip (and > sigcliplow); 1: >= */
+    BBO_CH_OBJLIM_CMP,           /* 0: s'/f > objlim; 1: >= */
+    BBO_CH_M5_FLOOR,             /* 0: med5 < 1e-5 -> 1e-5; 1: med5 <= 0 -> 1e-5; 2: no floor */
+    BBO_CH_MEDFILT_FRAME,        /* K/2-wide frame of a median filter: 0 copies the input; 1 is zero */
+    BBO_CH_DILATE3_FRAME,        /* 1-pixel frame of the 3x3 dilation: 0 copies the input; 1 dilates with zero padding */
+    BBO_CH_CLEAN_FRAME,          /* 2-pixel frame of the cleaning: 0 left alone; 1 cleaned from the clipped 5x5 box */
+    BBO_CH_FINE_MEDIAN7_OF,      /* fine structure: 0 med3 - med7(med3); 1 med3 - med7(image) */
+    BBO_CH_CLIP_INCLUSIVE,       /* sigma clip keeps 0: lo <= x <= hi; 1: lo < x < hi */
+    BBO_CH_CLIP_STD_ABOUT,       /* sigma clip std about 0: the mean (also for a median centre); 1: the centre */
+    BBO_CH_CLIP_STOP,            /* sigma clip stops 0: when nothing was rejected or after maxiters; 1: after maxiters + 1 bound computations */
+    BBO_NCHOICES
+};
+static int g_choice[BBO_NCHOICES];
+BBO_API int bbo_num_choices(void) { return BBO_NCHOICES; }
+BBO_API void bbo_set_choice(int which, int value) { if (which >= 0 && which < BBO_NCHOICES) g_choice[which] = value; }
+BBO_API int bbo_get_choice(int which) { return (which >= 0 && which < BBO_NCHOICES) ? g_choice[which] : -1; }
+BBO_API void bbo_reset_choices(void) { for (int i = 0; i < BBO_NCHOICES; i++) g_choice[i] = 0; }
+
+/* ------------------------------------------------------------------------------------------
  * selection helpers
  * ---------------------------------------------------------------------------------------- */
 
@@ -119,25 +153,33 @@ BBO_API void bbo_clip_bounds(const double *v, const uint8_t *valid, long nslices
                     long kept = 0;
                     for (long i = 0; i < count; i++) mean += buf[i];
                     mean /= (double)count;
-                    for (long i = 0; i < count; i++) {
-                        double d = mean - buf[i];
-                        std += d * d;
-                    }
-                    std = sqrt(std / (double)count);
                     if (use_median) {
                         memcpy(scratch, buf, sizeof(double) * (size_t)count);
                         cen = median_avg_d(scratch, count);
                     } else {
                         cen = mean;
                     }
+                    {
+                        const double about = g_choice[BBO_CH_CLIP_STD_ABOUT] ? cen : mean;
+                        for (long i = 0; i < count; i++) {
+                            double d = about - buf[i];
+                            std += d * d;
+                        }
+                    }
+                    std = sqrt(std / (double)count);
                     lo = cen - sig_lo * std;
                     hi = cen + sig_hi * std;
-                    for (long i = 0; i < count; i++)
-                        if (buf[i] >= lo && buf[i] <= hi) buf[kept++] = buf[i];
+                    if (g_choice[BBO_CH_CLIP_INCLUSIVE]) {
+                        for (long i = 0; i < count; i++)
+                            if (buf[i] > lo && buf[i] < hi) buf[kept++] = buf[i];
+                    } else {
+                        for (long i = 0; i < count; i++)
+                            if (buf[i] >= lo && buf[i] <= hi) buf[kept++] = buf[i];
+                    }
                     if (kept == count) break;
                     count = kept;
                     iteration++;
-                    if (maxiters >= 0 && iteration >= maxiters) break;
+                    if (maxiters >= 0 && iteration >= maxiters + (g_choice[BBO_CH_CLIP_STOP] ? 1 : 0)) break;
                     if (count == 0) break;
                 }
             }
@@ -212,10 +254,14 @@ static void medfilt(const float *in, float *out, int H, int W, int K)
         float win[49];
         const size_t row = (size_t)y * W;
         if (y < r || y >= H - r) {
-            memcpy(out + row, in + row, sizeof(float) * (size_t)W);
+            if (g_choice[BBO_CH_MEDFILT_FRAME]) memset(out + row, 0, sizeof(float) * (size_t)W);
+            else memcpy(out + row, in + row, sizeof(float) * (size_t)W);
             continue;
         }
-        for (int x = 0; x < r; x++) { out[row + x] = in[row + x]; out[row + W - 1 - x] = in[row + W - 1 - x]; }
+        for (int x = 0; x < r; x++) {
+            out[row + x] = g_choice[BBO_CH_MEDFILT_FRAME] ? 0.0f : in[row + x];
+            out[row + W - 1 - x] = g_choice[BBO_CH_MEDFILT_FRAME] ? 0.0f : in[row + W - 1 - x];
+        }
         for (int x = r; x < W - r; x++) {
             int c = 0;
             for (int dy = -r; dy <= r; dy++) {
@@ -253,10 +299,26 @@ BBO_API void bbo_laplace(const float *in, float *out, int H, int W)
         for (int x = 0; x < W; x++) {
             size_t i = (size_t)y * W + x;
             float p = 4.0f * in[i];
-            if (x + 1 < W) p = p - in[i + 1];
-            if (x > 0) p = p - in[i - 1];
-            if (y + 1 < H) p = p - in[i + W];
-            if (y > 0) p = p - in[i - W];
+            const int rep = g_choice[BBO_CH_LAPLACE_EDGE];
+            const int hr = x + 1 < W, hl = x > 0, hd = y + 1 < H, hu = y > 0;
+            const float r = hr ? in[i + 1] : in[i], l = hl ? in[i - 1] : in[i];
+            const float d = hd ? in[i + W] : in[i], u = hu ? in[i - W] : in[i];
+            if (g_choice[BBO_CH_LAPLACE_ORDER] == 0) {
+                if (hr || rep) p = p - r;
+                if (hl || rep) p = p - l;
+                if (hd || rep) p = p - d;
+                if (hu || rep) p = p - u;
+            } else if (g_choice[BBO_CH_LAPLACE_ORDER] == 1) {
+                if (hl || rep) p = p - l;
+                if (hr || rep) p = p - r;
+                if (hu || rep) p = p - u;
+                if (hd || rep) p = p - d;
+            } else {
+                float a = ((hl || rep) ? l : 0.0f) + ((hr || rep) ? r : 0.0f);
+                float b = ((hu || rep) ? u : 0.0f) + ((hd || rep) ? d : 0.0f);
+                a = a + b;
+                p = p - a;
+            }
             out[i] = p;
         }
 }
@@ -270,9 +332,19 @@ BBO_API void bbo_rebin(const float *in, float *out, int H, int W)
         for (int x = 0; x < W; x++) {
             size_t o = (size_t)(2 * y) * W2 + 2 * x;
             float p = in[o];
-            p = p + in[o + 1];
-            p = p + in[o + W2];
-            p = p + in[o + W2 + 1];
+            if (g_choice[BBO_CH_REBIN_ORDER] == 0) {
+                p = p + in[o + 1];
+                p = p + in[o + W2];
+                p = p + in[o + W2 + 1];
+            } else if (g_choice[BBO_CH_REBIN_ORDER] == 1) {
+                p = p + in[o + W2];
+                p = p + in[o + 1];
+                p = p + in[o + W2 + 1];
+            } else {
+                float q = in[o + W2] + in[o + W2 + 1];
+                p = p + in[o + 1];
+                p = p + q;
+            }
             out[(size_t)y * W + x] = p / 4.0f;
         }
 }
@@ -284,7 +356,17 @@ BBO_API void bbo_dilate3(const uint8_t *in, uint8_t *out, int H, int W)
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
             size_t i = (size_t)y * W + x;
-            if (y == 0 || y == H - 1 || x == 0 || x == W - 1) { out[i] = in[i]; continue; }
+            if (y == 0 || y == H - 1 || x == 0 || x == W - 1) {
+                if (!g_choice[BBO_CH_DILATE3_FRAME]) { out[i] = in[i]; continue; }
+                uint8_t p = 0;
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        int yy = y + dy, xx = x + dx;
+                        if (yy >= 0 && yy < H && xx >= 0 && xx < W && in[(size_t)yy * W + xx]) p = 1;
+                    }
+                out[i] = p;
+                continue;
+            }
             out[i] = in[i] || in[i + 1] || in[i - 1] || in[i + W] || in[i - W] ||
                      in[i + W + 1] || in[i + W - 1] || in[i - W + 1] || in[i - W - 1];
         }
@@ -321,19 +403,29 @@ BBO_API void bbo_dilate5(const uint8_t *in, uint8_t *out, int H, int W, int nite
 BBO_API void bbo_clean_medmask(float *clean, const uint8_t *crmask, const uint8_t *mask,
                                int H, int W, float background)
 {
+    const int fr = g_choice[BBO_CH_CLEAN_FRAME] ? 0 : 2;
 #pragma omp parallel for schedule(static)
-    for (int y = 2; y < H - 2; y++) {
+    for (int y = fr; y < H - fr; y++) {
         float win[25];
-        for (int x = 2; x < W - 2; x++) {
+        for (int x = fr; x < W - fr; x++) {
             size_t i = (size_t)y * W + x;
             int n = 0;
             if (!crmask[i]) continue;
             for (int dy = -2; dy <= 2; dy++)
                 for (int dx = -2; dx <= 2; dx++) {
-                    size_t j = (size_t)(y + dy) * W + (x + dx);
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    size_t j = (size_t)yy * W + xx;
                     if (!crmask[j] && !mask[j]) win[n++] = clean[j];
                 }
-            clean[i] = n ? kth_smallest_f(win, n, (n - 1) / 2) : background;
+            if (!n) { clean[i] = background; continue; }
+            if (g_choice[BBO_CH_CLEAN_MEDIAN] == 0 || (n & 1)) clean[i] = kth_smallest_f(win, n, (n - 1) / 2);
+            else if (g_choice[BBO_CH_CLEAN_MEDIAN] == 1) clean[i] = kth_smallest_f(win, n, n / 2);
+            else {
+                float a = kth_smallest_f(win, n, (n - 1) / 2), b = kth_smallest_f(win, n, n / 2);
+                a = a + b;
+                clean[i] = a / 2.0f;
+            }
         }
     }
 }
@@ -376,7 +468,7 @@ BBO_API int bbo_detect_cosmics(float *clean, uint8_t *mask, uint8_t *crmask, int
     {
         size_t ngood = 0;
         for (size_t i = 0; i < N; i++) if (!mask[i]) t1[ngood++] = clean[i];
-        background = ngood ? kth_smallest_f(t1, (long)ngood, (long)((ngood - 1) / 2)) : 0.0f;
+        background = ngood ? kth_smallest_f(t1, (long)ngood, (long)(g_choice[BBO_CH_BACKGROUND_MEDIAN] ? ngood / 2 : (ngood - 1) / 2)) : 0.0f;
         if (background_out) *background_out = background;
     }
 
@@ -395,7 +487,8 @@ BBO_API int bbo_detect_cosmics(float *clean, uint8_t *mask, uint8_t *crmask, int
         for (size_t i = 0; i < N; i++) {
             float m5 = t1[i];
             float nz, d;
-            if (m5 < 0.00001f) m5 = 0.00001f;
+            if (g_choice[BBO_CH_M5_FLOOR] == 0) { if (m5 < 0.00001f) m5 = 0.00001f; }
+            else if (g_choice[BBO_CH_M5_FLOOR] == 1) { if (m5 <= 0.0f) m5 = 0.00001f; }
             nz = m5 + rn2;
             nz = sqrtf(nz);
             noise[i] = nz;
@@ -408,7 +501,7 @@ BBO_API int bbo_detect_cosmics(float *clean, uint8_t *mask, uint8_t *crmask, int
         for (size_t i = 0; i < N; i++) s[i] = s[i] - t1[i];
         /* fine structure f = (med3 - med7(med3)) / noise, floored at 0.01 */
         medfilt(clean, t1, H, W, 3);
-        medfilt(t1, t2, H, W, 7);
+        medfilt(g_choice[BBO_CH_FINE_MEDIAN7_OF] ? clean : t1, t2, H, W, 7);
 #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < N; i++) {
             float f = t1[i] - t2[i];
@@ -422,21 +515,24 @@ BBO_API int bbo_detect_cosmics(float *clean, uint8_t *mask, uint8_t *crmask, int
             if (dump_noise) memcpy(dump_noise, noise, sizeof(float) * N);
         }
         /* candidates, then two growth steps with relaxed thresholds */
+        const int ge = g_choice[BBO_CH_SIGCLIP_CMP], oge = g_choice[BBO_CH_OBJLIM_CMP];
+#define ABOVE(v, t) (ge ? ((v) >= (t)) : ((v) > (t)))
 #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < N; i++) {
             float ratio = s[i] / t1[i];
-            cr[i] = (s[i] > sigclip) && !mask[i] && (ratio > objlim);
+            cr[i] = ABOVE(s[i], sigclip) && !mask[i] && (oge ? (ratio >= objlim) : (ratio > objlim));
         }
         bbo_dilate3(cr, cr2, H, W);
 #pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < N; i++) cr[i] = cr2[i] && !mask[i] && (s[i] > sigclip);
+        for (size_t i = 0; i < N; i++) cr[i] = cr2[i] && !mask[i] && ABOVE(s[i], sigclip);
         bbo_dilate3(cr, cr2, H, W);
 #pragma omp parallel for schedule(static) reduction(+ : ncr)
         for (size_t i = 0; i < N; i++) {
-            uint8_t c = cr2[i] && !mask[i] && (s[i] > sigcliplow);
+            uint8_t c = cr2[i] && !mask[i] && ABOVE(s[i], sigcliplow);
             ncr += c;
             crmask[i] = crmask[i] || c;
         }
+#undef ABOVE
         if (ncr_per_iter) ncr_per_iter[it] = ncr;
         if (ncr == 0) { it++; break; }
         bbo_clean_medmask(clean, crmask, mask, H, W, background);

@@ -34,6 +34,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 REF = '/root/reference'
 
+USE_REAL_LIBRARIES = '--real' in sys.argv      # default: the oracle's restatements stand in (see the module text)
+
 MASK_VALUE = {'bad': 1, 'cosmic ray': 2, 'saturated': 4, 'saturated-connected': 8,
               'satellite trail': 16, 'edge': 32, 'crosstalk': 64}
 _files = {}          # "file name" -> array, served by the read_hdulist stub
@@ -159,8 +161,19 @@ def load_reference():
               'astropy.utils.iers', 'astropy.io', 'astropy.io.fits', 'astropy.table', 'astropy.wcs'):
         _stub(n)
     sys.modules['watchdog.events'].FileSystemEventHandler = type('FileSystemEventHandler', (), {})
-    _stub('astropy.stats', sigma_clipped_stats=ostats.sigma_clipped_stats, sigma_clip=ostats.sigma_clip)
-    _stub('astroscrappy', detect_cosmics=olac.detect_cosmics)
+    if USE_REAL_LIBRARIES:
+        # tools/pin_oracle.py --write: the two third-party algorithms as the libraries themselves
+        # compute them (only possible where astropy and astroscrappy are installed)
+        import importlib
+        for n in [m for m in sys.modules if m == 'astropy' or m.startswith('astropy.')]:
+            del sys.modules[n]
+        real_stats = importlib.import_module('astropy.stats')
+        real_scrappy = importlib.import_module('astroscrappy')
+        sys.modules['astropy.stats'] = real_stats
+        sys.modules['astroscrappy'] = real_scrappy
+    else:
+        _stub('astropy.stats', sigma_clipped_stats=ostats.sigma_clipped_stats, sigma_clip=ostats.sigma_clip)
+        _stub('astroscrappy', detect_cosmics=olac.detect_cosmics)
     fits = types.SimpleNamespace(Header=Header)
     zogy = _stub('zogy', np=np, ndimage=ndimage, interpolate=interpolate, get_par=get_par, fits=fits, Table=_Table,
                  read_hdulist=_read_hdulist,
@@ -343,6 +356,7 @@ def master_case(bb, tel, imgtype, seed, ysc, date_eve='20240105', filt='q'):
 def main():
     bb = load_reference()
     out = {'reference_version': bb.__version__, 'numpy': np.__version__,
+           'third_party': 'astropy / astroscrappy as installed' if USE_REAL_LIBRARIES else 'oracle restatements (unpinned)',
            'sections': {}, 'frames': [], 'nonlin': [], 'masters': []}
     for shape, xb in (((10600, 12000), 1), ((5300, 6000), 2), ((10560, 10560), 1)):
         out['sections']['{}x{}_bin{}'.format(shape[0], shape[1], xb)] = sections_as_lists(

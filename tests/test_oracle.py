@@ -297,3 +297,46 @@ def test_sigma_clip_mean_matches_scipy_sigmaclip():
             surv = ours.compressed()
             assert lo == pytest.approx(surv.mean() - sig * surv.std(), rel=1e-12)
             assert hi == pytest.approx(surv.mean() + sig * surv.std(), rel=1e-12)
+
+
+def test_recalled_choices_are_switchable_and_default_to_what_is_implemented():
+    """Every recalled detail of the restated third-party algorithms sits behind a named switch of the
+    C oracle (value 0 = implemented by the oracle and by the CUDA kernels).  Flipping one changes the
+    result where it should, resetting restores it; the committed matrix
+    (tests/golden/oracle_choice_matrix.json, tools/oracle_choice_matrix.py) quantifies each on the
+    seeded frames."""
+    import json
+    import os
+    from oracle import clib, lacosmic as L
+    assert clib.lib().bbo_num_choices() == len(clib.CHOICES)
+    clib.reset_choices()
+    rng = np.random.default_rng(5)
+    img = rng.normal(100, 3, (40, 40)).astype(np.float32)
+    img[20, 20] += 4000.0                                  # a one-pixel cosmic ray
+    mask = np.zeros(img.shape, bool)
+    mask[19, 19] = True                                    # 25 - 1 (itself) - 1 (masked) = 23 usable... make it even:
+    mask[21, 21] = True                                    # 22 usable neighbours: lower != upper median
+    kw = dict(sigclip=15, sigfrac=0.01, objlim=3, gain=1.0, readnoise=5.0, satlevel=np.inf, niter=1,
+              sepmed=False, cleantype='medmask')
+    cr0, clean0 = L.detect_cosmics(img, mask, **kw)
+    assert cr0[20, 20]
+    try:
+        clib.set_choice('CLEAN_MEDIAN', 1)
+        cr1, clean1 = L.detect_cosmics(img, mask, **kw)
+        assert np.array_equal(cr1, cr0) and clean1[20, 20] > clean0[20, 20]
+        clib.set_choice('CLEAN_MEDIAN', 0)
+        clib.set_choice('SIGCLIP_CMP', 1)
+        cr2, clean2 = L.detect_cosmics(img, mask, **kw)
+        assert np.array_equal(cr2, cr0) and np.array_equal(clean2, clean0)
+    finally:
+        clib.reset_choices()
+    cr3, clean3 = L.detect_cosmics(img, mask, **kw)
+    assert np.array_equal(cr3, cr0) and np.array_equal(clean3, clean0)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oracle_choice_matrix.json')
+    rows = json.load(open(path))
+    assert {r['switch'] for r in rows} == {n for n, _ in clib.CHOICES}
+    moved = {r['switch'] for r in rows if any(f['cr_flags_changed'] or f['image_pixels_changed'] for f in r['frames'])}
+    # on the seeded frames only these recalled details change anything at all
+    assert moved == {'CLEAN_MEDIAN', 'LAPLACE_EDGE', 'MEDFILT_FRAME'}
+    worst = max(f['cr_flags_changed'] / f['npix'] for r in rows for f in r['frames'] if 'no BPM' not in f['frame'])
+    assert worst == 0.0                                   # with the bad-pixel mask's edge frame: no mask pixel moves
