@@ -18,15 +18,22 @@ struct StackArgs {
 // host).  Values whose exponent is outside [2^-60, 2^60] (zeros, denormals, inf, NaN included) take
 // the division itself.  Checked exhaustively over all 2^32 bit patterns of x for a set of divisors
 // (bbx_debug_div_check, tests/test_steps_gpu.py).
-__device__ __forceinline__ float stack_div_by(float x, float d, float r)
+__device__ __forceinline__ bool stack_div_in_range(float x)
 {
     const unsigned int ex = (__float_as_uint(x) >> 23) & 0xffu;
-    if (ex - 67u > 120u) return x / d;
+    return ex - 67u <= 120u;
+}
+__device__ __forceinline__ float stack_div_fast(float x, float d, float r)     // x in range (stack_div_in_range)
+{
     float q = __fmul_rn(x, r);
     float e = __fmaf_rn(-d, q, x);
     q = __fmaf_rn(e, r, q);
     e = __fmaf_rn(-d, q, x);
     return __fmaf_rn(e, r, q);
+}
+__device__ __forceinline__ float stack_div_by(float x, float d, float r)
+{
+    return stack_div_in_range(x) ? stack_div_fast(x, d, r) : x / d;
 }
 
 // host: RN(1/d) for a normal positive float d, and whether d qualifies for stack_div_by
