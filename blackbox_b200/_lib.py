@@ -49,7 +49,7 @@ _SIGNATURES = {
     'bbx_header_means': [P, P, P, P],
     'bbx_mask_sat_neighbours': [P, I, I, I, I, BITS, P],
     'bbx_mask_morph_sparse': [P, I, I, I, I, BITS, P, P, C.c_uint, P, P, P, I, P, P],
-    'bbx_mask_morph_sparse_track': [P, I, I, I, I, BITS, P, P, C.c_uint, P, P, P, I, P, P, P, P],
+    'bbx_mask_morph_sparse_track': [P, I, I, I, I, BITS, P, P, C.c_uint, P, P, P, I, P, P, P, I, P],
     'bbx_fill_holes_work_bytes': [I, I],
     'bbx_fill_sat_holes': [P, I, I, BITS, P, I, P, P],
     'bbx_fill_holes_more': [P, I, I, BITS, P, I, P, P],

@@ -717,6 +717,36 @@ ms_commit_tiles_kernel(uint8_t *mask, HoleWork hw, int H, int W, unsigned int bi
     }
 }
 
+// The state image goes back to "background everywhere" (1) where this frame touched it: the 5x5
+// boxes around the seeds (ms_close_kernel) and the candidate tiles (hole_propagate_kernel), so the
+// next frame needs no 111 MB memset.
+__global__ void __launch_bounds__(256)
+ms_restore_state_kernel(HoleWork hw, int H, int W, const unsigned int *__restrict__ seeds,
+                        const unsigned int *__restrict__ count, unsigned int cap)
+{
+    const unsigned int n = min(*count, cap);
+    const unsigned long long total = (unsigned long long)n * 25ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int sd = seeds[t / 25] & ~SEED_BPM;
+        const int k = (int)(t % 25);
+        const int y = (int)(sd / (unsigned int)W), x = (int)(sd - (unsigned int)y * (unsigned int)W);
+        const int qy = y + k / 5 - 2, qx = x + k % 5 - 2;
+        if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+        hw.S[(size_t)qy * W + qx] = 1;
+    }
+    const int ntiles = hw.counters[0];
+    const int tiles_x = (W + HOLE_TILE - 1) / HOLE_TILE;
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const int tile = hw.tiles[ti];
+        const int y0 = (tile / tiles_x) * HOLE_TILE, x0 = (tile % tiles_x) * HOLE_TILE;
+        for (int i = threadIdx.x; i < HOLE_TILE * HOLE_TILE; i += blockDim.x) {
+            const int gy = y0 + i / HOLE_TILE, gx = x0 + i % HOLE_TILE;
+            if (gy < H && gx < W) hw.S[(size_t)gy * W + gx] = 1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 ms_clear_marker_kernel(uint8_t *mask, const unsigned int *__restrict__ seeds, const unsigned int *__restrict__ count,
                        unsigned int cap, const int32_t *__restrict__ unconverged)
@@ -735,17 +765,20 @@ extern "C" int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan
                                      int32_t *status, void *stream)
 {
     return bbx_mask_morph_sparse_track(mask, H, W, ysize_chan, xsize_chan, bits, seeds, seed_count, seed_cap, work,
-                                       labels, out_nobj, rounds, status, nullptr, nullptr, stream);
+                                       labels, out_nobj, rounds, status, nullptr, nullptr, 0, stream);
 }
 
-// The same after bbx_reduce_apply_scan: img / lac_work (the reduced image and LACosmic's work
-// buffer of that call) let the morphology take every pixel it masks for the first time out of the
-// background statistics the fused pass has collected against the seed mask.
+// The same with two optional extras.  img / lac_work (after bbx_reduce_apply_scan: the reduced image
+// and LACosmic's work buffer of that call) let the morphology take every pixel it masks for the first
+// time out of the background statistics the fused pass has collected against the seed mask.
+// state_clean != 0: the first H * W bytes of `work` are all ones -- as a fresh caller sets them once
+// and as every call of this function leaves them -- so the 111 MB memset per frame is skipped
+// (the dense entry points bbx_fill_sat_holes / _more do not keep that promise).
 extern "C" int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                                            const bbx_maskbits *bits, const unsigned int *seeds,
                                            const unsigned int *seed_count, unsigned int seed_cap, void *work,
                                            int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
-                                           const float *img, void *lac_work, void *stream)
+                                           const float *img, void *lac_work, int state_clean, void *stream)
 {
     const BgTrack trk = lac_sparse_bg_track(img, lac_work, H, W);
     BBX_REQUIRE(mask && bits && seeds && seed_count && work && labels && out_nobj && status, "bbx_mask_morph_sparse: null argument");
@@ -763,8 +796,10 @@ extern "C" int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysiz
     ms_ccl_init_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
     ms_ccl_merge_kernel<<<lb, 128, 0, s>>>(mask, H, W, seeds, seed_count, seed_cap, labels);
     ms_ccl_count_kernel<<<lb, 128, 0, s>>>(seeds, seed_count, seed_cap, labels, out_nobj);
-    // hole filling: state image = background everywhere, closed foreground near the seeds
-    BBX_CUDA(cudaMemsetAsync(hw.S, 1, (size_t)H * W, s));
+    // hole filling: state image = background everywhere, closed foreground near the seeds.  A
+    // caller that keeps the work buffer between frames says so (state_clean): this function leaves the
+    // state image as it wants to find it, all ones
+    if (!state_clean) BBX_CUDA(cudaMemsetAsync(hw.S, 1, (size_t)H * W, s));
     const int n = H > W ? H : W;
     hole_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(hw, H, W);
     ms_close_kernel<<<lb, 128, 0, s>>>(mask, hw, H, W, mbits, seeds, seed_count, seed_cap);
@@ -777,6 +812,7 @@ extern "C" int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysiz
                                               unconverged, status, trk);
     ms_commit_tiles_kernel<<<BBX_SM_COUNT * 2, 256, 0, s>>>(mask, hw, H, W, (unsigned int)bits->satcon, unconverged, trk);
     ms_clear_marker_kernel<<<lb, 128, 0, s>>>(mask, seeds, seed_count, seed_cap, unconverged);
+    ms_restore_state_kernel<<<lb, 256, 0, s>>>(hw, H, W, seeds, seed_count, seed_cap);
     BBX_CHECK_LAUNCH("bbx_mask_morph_sparse");
     return 0;
 }

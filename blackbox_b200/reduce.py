@@ -441,6 +441,9 @@ class MaskWork:
         and NOBJ-SAT (FramePipeline points them into the frame's header block)."""
         self.H, self.W = H, W
         self.holes = torch.empty(query('bbx_fill_holes_work_bytes', H, W), dtype=torch.uint8, device=device)
+        # the hole-filling state image starts as "background everywhere"; the sparse morphology
+        # leaves it like that after every frame (no memset per frame), the dense one does not
+        self.holes[:H * W].fill_(1)
         self.labels = torch.empty(H * W, dtype=torch.int32, device=device)
         self.unconverged = torch.zeros(1, dtype=torch.int32, device=device)
         self.nobj = nobj if nobj is not None else torch.zeros(1, dtype=torch.int32, device=device)
@@ -463,7 +466,7 @@ def mask_morph_enqueue(mask_t, tel_, work, count_objects=True, rounds=4096, spar
         img_t, lwork = track if track is not None else (None, None)
         call('bbx_mask_morph_sparse_track', _ptr(mask_t), H, W, H // 2, W // 8, C.byref(bits), _ptr(work.seeds),
              _ptr(work.seed_count), int(work.seed_cap), _ptr(work.holes), _ptr(work.labels), _ptr(work.nobj),
-             int(rounds), _ptr(work.status), _ptr(img_t), _ptr(lwork.buf) if lwork is not None else None, s)
+             int(rounds), _ptr(work.status), _ptr(img_t), _ptr(lwork.buf) if lwork is not None else None, 1, s)
         return
     if track is not None:
         raise ValueError('mask_morph_enqueue: tracking needs the sparse morphology')
@@ -486,6 +489,7 @@ def mask_morph_finish(mask_t, tel_, work, rounds=1024, sparse=True):
     while int(work.unconverged.item()) != 0:
         call('bbx_fill_holes_more', _ptr(mask_t), H, W, C.byref(bits), _ptr(work.holes), rounds,
              _ptr(work.unconverged), _stream())
+    work.holes[:H * W].fill_(1)              # the dense passes used the state image: as the sparse path expects it again
     return int(work.nobj.item()), True
 
 

@@ -208,13 +208,16 @@ int bbx_mask_morph_sparse(uint8_t *mask, int H, int W, int ysize_chan, int xsize
                           int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
                           void *stream);
 
-/* bbx_mask_morph_sparse after bbx_reduce_apply_scan: img = the reduced image, lac_work = the
- * LACosmic work buffer of that call (both may be null: plain bbx_mask_morph_sparse) */
+/* bbx_mask_morph_sparse with two optional extras.  After bbx_reduce_apply_scan: img = the reduced
+ * image, lac_work = the LACosmic work buffer of that call (both may be null).  state_clean != 0: the
+ * first H * W bytes of `work` (the hole-filling state image) are all ones -- set once by the
+ * caller, left like that by every call of this function -- and the per-frame 111 MB memset is
+ * skipped; bbx_fill_sat_holes / bbx_fill_holes_more do NOT leave them like that. */
 int bbx_mask_morph_sparse_track(uint8_t *mask, int H, int W, int ysize_chan, int xsize_chan,
                                 const bbx_maskbits *bits, const unsigned int *seeds,
                                 const unsigned int *seed_count, unsigned int seed_cap, void *work,
                                 int32_t *labels, int32_t *out_nobj, int rounds, int32_t *status,
-                                const float *img, void *lac_work, void *stream);
+                                const float *img, void *lac_work, int state_clean, void *stream);
 
 /* number of 8-connected components of (mask & bit) != 0  (ndimage.label; blackbox.py:4354,
  * 4544).  labels: int32 [H*W] scratch; out_count device int32. */
