@@ -60,7 +60,6 @@ _SIGNATURES = {
     'bbx_xtalk_counts': [P, P, I, I, I, I, P, BITS, I, P, P],
     'bbx_stack_median': [P, P, I, SZ, I, P, I, P, P],
     'bbx_stack_median_multi': [P, P, I, SZ, I, P, I, P, I, I, P],
-    'bbx_debug_div_check': [P, I, P, P, P],
     'bbx_stack_clipped_median': [P, P, I, SZ, D, I, I, P, I, P, P],
     'bbx_lacosmic_work_bytes': [I, I],
     'bbx_lacosmic': [P, P, P, I, I, F, F, F, F, P, I, I, P, P, P],

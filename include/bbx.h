@@ -270,14 +270,6 @@ int bbx_stack_median_multi(const float *const *frames_h, const float *scale_h, i
                            int flat_fix, const uint8_t *bpm, int edge_value, float *const *outs_h,
                            int ndst, int multicast, void *stream);
 
-/* Test hook: the master-flat kernel divides every value of a frame by that frame's normalisation
- * median through a correctly rounded reciprocal and two residual corrections instead of the
- * compiler's division routine; this compares the two for ALL 2^32 bit patterns of the dividend and
- * each of the n divisors (host array).  out_mismatch: device uint64 = differing (x, d) pairs (must
- * be 0); out_skipped_h (host, may be null) = divisors that do not qualify for the fast path. */
-int bbx_debug_div_check(const float *scales_h, int n, unsigned long long *out_mismatch,
-                        int *out_skipped_h, void *stream);
-
 /* Optional sigma-clipped combine (BASELINE.json's wording; the reference's master_prep uses the
  * plain median above, so this is off by default in reduce.master_combine): per pixel
  * astropy.stats.sigma_clip(cube, sigma, maxiters, cenfunc='median', stdfunc='std', axis=0)

@@ -635,26 +635,3 @@ def test_drop_in_functions_refuse_mismatched_shapes(small_bb):
     with pytest.raises(ValueError):
         bbr.subtract_mbias(torch.zeros((48, 320), device='cuda'), torch.zeros((48, 319), device='cuda'))
 
-
-def test_master_flat_division_is_the_ieee_quotient_for_every_float():
-    """bbx_stack_median divides a flat by its normalisation median (blackbox.py:4941: frame / median) with a
-    correctly rounded reciprocal and two residual corrections instead of the compiler's division
-    routine.  Held against x / d for ALL 2^32 bit patterns of x, for divisors like the medians of real
-    flats and for awkward ones (significand near all ones / all zeros, tiny, huge); a divisor whose
-    significand IS all ones, a negative and an out-of-range one are disqualified by the host and take the
-    division itself."""
-    import ctypes as C
-    import torch
-    from blackbox_b200 import reduce as bbr
-    from blackbox_b200._lib import call
-    rng = np.random.default_rng(3)
-    scales = list(rng.uniform(15000, 25000, 6).astype(np.float32)) + [
-        np.float32(3.0), np.float32(7.0), np.float32(1.0000001), np.float32(1.9999996), np.float32(0.33333334),
-        np.float32(2.0 ** -29 * 1.37), np.float32(2.0 ** 29 * 1.61), np.float32(19494.4), np.float32(1.0)]
-    bad = [np.float32(1.9999999), np.float32(-20000.0), np.float32(1e-12)]        # disqualified: never on the fast path
-    arr = (C.c_float * (len(scales) + len(bad)))(*[float(s) for s in scales + bad])
-    mism = torch.zeros(1, dtype=torch.int64, device='cuda')
-    skipped = C.c_int(0)
-    call('bbx_debug_div_check', arr, len(scales) + len(bad), bbr._ptr(mism), C.byref(skipped), bbr._stream())
-    assert int(mism.item()) == 0
-    assert skipped.value == len(bad)
