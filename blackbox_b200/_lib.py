@@ -45,6 +45,7 @@ _SIGNATURES = {
     'bbx_hos_fit': [P, P, P, P, GEOM, I, I, I, P, P, P, P],
     'bbx_reduce_apply': [P, I, GEOM, P, P, P, P, P, P, P, BITS, P, P, P, P, C.c_uint, P],
     'bbx_reduce_apply_scan': [P, I, GEOM, P, P, P, P, P, P, P, BITS, P, P, P, P, C.c_uint, P, F, F, F, F, P, I, P, P, P],
+    'bbx_reduce_apply_stats': [P, I, GEOM, P, P, P, P, P, P, P, BITS, P, P, P, P, C.c_uint, I, P, P, P],
     'bbx_satlevels': [P, P, P, P],
     'bbx_header_means': [P, P, P, P],
     'bbx_mask_sat_neighbours': [P, I, I, I, I, BITS, P],

@@ -23,6 +23,7 @@
 // f64(v) >= level is done in float32 against the smallest float32 >= level, which is the same
 // predicate.
 #include "apply_common.cuh"
+#include "bg_track.cuh"
 
 template <typename T>
 __device__ __forceinline__ void apply_px(float &v, uint8_t &m, bool have_mask, float gn, double fitv,
@@ -110,9 +111,14 @@ reduce_apply_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyAr
 #define APPLY_THREADS 128
 #define APPLY_ROWS 16
 
-template <typename T>
-__global__ void __launch_bounds__(APPLY_THREADS)
-reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a)
+// STATS: also take the statistics of LACosmic's background level (the count of unmasked pixels, of
+// those below the bracket, the histogram inside it: lacosmic_sparse.cu) while the values are in
+// registers -- against the seed mask; the mask morphology that follows corrects them for the pixels
+// it masks (bg_track.cuh).  The dense Laplacian scan then reads neither the mask nor computes keys.
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(APPLY_THREADS, 8)
+reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a, BgState *bg,
+                          unsigned int *__restrict__ bghist)
 {
     const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
     const int x = (blockIdx.x * APPLY_THREADS + threadIdx.x) * 4;
@@ -125,6 +131,11 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
     double osc[4] = {0.0, 0.0, 0.0, 0.0};
     float gn = 1.0f, satl = 0.0f;
     bool has_sat = false;
+    unsigned int key_a = 0, width = 0, n_valid = 0, n_below = 0;
+    if (STATS) { key_a = bg->key_a; width = bg->width; }
+    // bracket at a non-negative value: the order-preserving keys are the raw float bits (sp_scan_kernel)
+    const bool raw_bits = key_a >= 0x80000000u;
+    const int lo_bits = (int)(key_a & 0x7fffffffu);
 
     struct RowIn { float v[4]; float4 mb, mf; uint32_t mm; double fitv; };
     // everything a row needs from memory, issued back to back (two rows are in flight at a time)
@@ -195,6 +206,27 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
         }
         __stcs(reinterpret_cast<float4 *>(a.out_img + oo), make_float4(v[0], v[1], v[2], v[3]));
         if (have_mask) __stcs(reinterpret_cast<unsigned int *>(a.out_mask + oo), mout);
+        if (STATS) {
+            if (mout == 0 && raw_bits) {
+                n_valid += 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int bits = __float_as_int(v[k]);
+                    n_below += bits < lo_bits;
+                    const unsigned int d = (unsigned int)bits - (unsigned int)lo_bits;
+                    if (d < width) atomicAdd(&bghist[d], 1u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if ((mout >> (8 * k)) & 0xffu) continue;
+                    const unsigned int key = f32_key(v[k]);
+                    n_valid++;
+                    if (key < key_a) n_below++;
+                    else if (key - key_a < width) atomicAdd(&bghist[key - key_a], 1u);
+                }
+            }
+        }
     };
 
     int y = ya;
@@ -209,6 +241,11 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
         RowIn in0;
         load_row(y, in0);
         finish_row(y, in0);
+    }
+    if (STATS) {
+        // (threads beyond the frame have left: the counters go out one atomic per thread that has any)
+        if (n_valid) atomicAdd(&bg->n_valid, (unsigned long long)n_valid);
+        if (n_below) atomicAdd(&bg->n_below, (unsigned long long)n_below);
     }
 }
 
@@ -248,6 +285,18 @@ extern "C" int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g
                                 float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
                                 unsigned int seed_cap, void *stream)
 {
+    return apply_launch(raw, raw_type, g, gain_h, vos_fit, oscan, mbias, mflat, bpm, satlevel, bits, out_img, out_mask,
+                        seeds, seed_count, seed_cap, nullptr, nullptr, stream);
+}
+
+// bg / bghist != null: the strip kernel also takes LACosmic's background statistics (the 4-pixel
+// aligned layout is then required)
+int apply_launch(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                 const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
+                 const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
+                 float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
+                 unsigned int seed_cap, void *bg_state, unsigned int *bghist, void *stream)
+{
     BBX_REQUIRE(g && raw && out_img, "bbx_reduce_apply: null raw / geometry / output");
     BBX_REQUIRE(g->ny == 2 && g->nx * g->ny == BBX_NCHAN, "bbx_reduce_apply: expected 2 x 8 channels");
     BBX_REQUIRE(out_mask == nullptr || bits != nullptr, "bbx_reduce_apply: mask output needs the mask bit values");
@@ -271,11 +320,19 @@ extern "C" int bbx_reduce_apply(const void *raw, int raw_type, const bbx_geom *g
     cudaStream_t s = (cudaStream_t)stream;
     if (vec4 && (RH + APPLY_ROWS - 1) / APPLY_ROWS <= 65535) {
         const dim3 grid((unsigned int)((RW / 4 + APPLY_THREADS - 1) / APPLY_THREADS), (unsigned int)((RH + APPLY_ROWS - 1) / APPLY_ROWS));
-        if (raw_type == BBX_RAW_U16) reduce_apply_strip_kernel<uint16_t><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a);
-        else reduce_apply_strip_kernel<float><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a);
+        BgState *bg = (BgState *)bg_state;
+        if (bg) {
+            BBX_REQUIRE(out_mask != nullptr && bghist != nullptr, "bbx_reduce_apply: statistics need the mask output");
+            if (raw_type == BBX_RAW_U16) reduce_apply_strip_kernel<uint16_t, true><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, bg, bghist);
+            else reduce_apply_strip_kernel<float, true><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, bg, bghist);
+        } else {
+            if (raw_type == BBX_RAW_U16) reduce_apply_strip_kernel<uint16_t, false><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, nullptr, nullptr);
+            else reduce_apply_strip_kernel<float, false><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, nullptr, nullptr);
+        }
         BBX_CHECK_LAUNCH("bbx_reduce_apply");
         return 0;
     }
+    BBX_REQUIRE(bg_state == nullptr, "bbx_reduce_apply: the statistics need the 4-pixel aligned layout");
     if (raw_type == BBX_RAW_U16) {
         if (vec4) reduce_apply_kernel<uint16_t, 4><<<blocks, 256, 0, s>>>((const uint16_t *)raw, *g, gn, a);
         else reduce_apply_kernel<uint16_t, 1><<<blocks, 256, 0, s>>>((const uint16_t *)raw, *g, gn, a);

@@ -80,3 +80,10 @@ __device__ __forceinline__ float apply_value_at(const T *__restrict__ raw, const
     mbyte = m;
     return w;
 }
+
+// the per-pixel pass; bg_state / bghist: optional background statistics of LACosmic (apply.cu)
+int apply_launch(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                 const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
+                 const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
+                 float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
+                 unsigned int seed_cap, void *bg_state, unsigned int *bghist, void *stream);

@@ -1136,7 +1136,7 @@ static int sparse_begin(const float *img, const uint8_t *inmask, uint8_t *crmask
 
 static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W, const LacParams &prm,
                             int it, bool with_background, void *work, long long *info, cudaStream_t st,
-                            bool prescanned = false)
+                            bool prescanned = false, bool stats_taken = false)
 {
     const size_t n = (size_t)H * W;
     SparseWork w = carve_sparse(work, n);
@@ -1151,6 +1151,11 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     if (it == 0 && prescanned) {
         // bbx_reduce_apply_scan has made list A, the statistics and the cleared byte maps; the mask
         // morphology has corrected the statistics for the pixels it masked since
+        sp_bg_rank_kernel<<<1, 1024, 0, st>>>(w);
+    } else if (it == 0 && stats_taken) {
+        // bbx_reduce_apply_stats has taken the statistics (and the morphology has corrected them):
+        // the scan is the Laplacian alone
+        sp_scan_kernel<false><<<scan_blocks, SCAN_THREADS, 0, st>>>(img, inmask, crmask, H, W, prm, w, info);
         sp_bg_rank_kernel<<<1, 1024, 0, st>>>(w);
     } else if (it == 0) {
         if (with_background) {
@@ -1245,6 +1250,44 @@ extern "C" int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_ge
     return 0;
 }
 
+// bbx_reduce_apply with LACosmic's background statistics taken on the way (see include/bbx.h): the
+// middle road between the separate passes and bbx_reduce_apply_scan -- the per-pixel pass keeps its
+// shape (HBM-bound, 64 registers), the dense scan keeps the Laplacian but sheds the mask read and the
+// key arithmetic.
+extern "C" int bbx_reduce_apply_stats(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                                      const double *vos_fit, const double *oscan, const float *mbias, const float *mflat,
+                                      const uint8_t *bpm, const double *satlevel, const bbx_maskbits *bits,
+                                      float *out_img, uint8_t *out_mask, unsigned int *seeds, unsigned int *seed_count,
+                                      unsigned int seed_cap, int niter, void *lac_work, long long *lac_info, void *stream)
+{
+    BBX_REQUIRE(g && raw && out_img && out_mask && bits && lac_work && lac_info, "bbx_reduce_apply_stats: null argument");
+    BBX_REQUIRE(niter > 0, "bbx_reduce_apply_stats: niter %d", niter);
+    const long long RW = (long long)g->nx * g->xsize_chan, RH = (long long)g->ny * g->ysize_chan;
+    BBX_REQUIRE(RH * RW < 2147483647LL, "bbx_reduce_apply_stats: frame too large for 31-bit pixel indices");
+    cudaStream_t st = (cudaStream_t)stream;
+    ChanF32 gn;
+    for (int i = 0; i < BBX_NCHAN; i++) gn.v[i] = gain_h ? gain_h[i] : 1.0f;
+    ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits->bad, bits->saturated,
+                   seeds, seed_count, seed_cap, (unsigned int)(bits->saturated | bits->satcon)};
+    SparseWork w = carve_sparse(lac_work, (size_t)(RH * RW));
+    BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        BBX_CUDA(cudaFuncSetAttribute(sp_bg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned int) * BG_SAMPLES)));
+        attr_set = true;
+    }
+    if (raw_type == BBX_RAW_U16)
+        sp_bg_gather_raw_kernel<uint16_t><<<BG_SAMPLES / 1024, 1024, 0, st>>>((const uint16_t *)raw, *g, gn, a, w);
+    else
+        sp_bg_gather_raw_kernel<float><<<BG_SAMPLES / 1024, 1024, 0, st>>>((const float *)raw, *g, gn, a, w);
+    sp_bg_sample_kernel<<<1, 1024, sizeof(unsigned int) * BG_SAMPLES, st>>>(w);
+    sp_init_kernel<<<1, 32, 0, st>>>(lac_info, INFO_NCR + niter, w.cnt, 0u);
+    BBX_CHECK_LAUNCH("bbx_reduce_apply_stats");
+    return apply_launch(raw, raw_type, g, gain_h, vos_fit, oscan, mbias, mflat, bpm, satlevel, bits, out_img, out_mask,
+                        seeds, seed_count, seed_cap, w.bg, w.bghist, stream);
+}
+
 extern "C" size_t bbx_lacosmic_work_bytes(int H, int W)
 {
     const size_t a = lac_dense_work_bytes(H, W), b = lac_sparse_work_bytes(H, W);
@@ -1256,9 +1299,9 @@ extern "C" int bbx_lacosmic_begin(const float *img, const uint8_t *inmask, uint8
 {
     BBX_REQUIRE(img && crmask && work && out_info, "bbx_lacosmic_begin: null argument");
     BBX_REQUIRE(H > 0 && W > 0 && niter >= 0, "bbx_lacosmic_begin: bad shape %d x %d or niter %d", H, W, niter);
-    BBX_REQUIRE(mode >= 0 && mode <= 3, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense, 2 = lazy with background level, 3 = lazy, scanned by bbx_reduce_apply_scan)", mode);
+    BBX_REQUIRE(mode >= 0 && mode <= 4, "bbx_lacosmic_begin: mode %d (0 = lazy, 1 = dense, 2 = lazy with background level, 3 = lazy, scanned by bbx_reduce_apply_scan, 4 = lazy, statistics by bbx_reduce_apply_stats)", mode);
     BBX_REQUIRE((long long)H * W < 4294967295LL, "bbx_lacosmic_begin: image too large for 32-bit pixel indices");
-    if (mode == 3) return 0;                     // bbx_reduce_apply_scan has done it
+    if (mode == 3 || mode == 4) return 0;        // bbx_reduce_apply_scan / _stats have done it
     if (mode == 1) return lac_dense_begin(img, inmask, crmask, H, W, niter, work, out_info, (cudaStream_t)stream);
     return sparse_begin(img, inmask, crmask, H, W, niter, mode == 2, work, out_info, (cudaStream_t)stream);
 }
@@ -1272,7 +1315,7 @@ extern "C" int bbx_lacosmic_iteration(float *img, const uint8_t *inmask, uint8_t
     const LacParams prm = lac_make_params(sigclip, sigfrac, objlim, readnoise, readnoise_dev);
     if (mode == 1) return lac_dense_iteration(img, inmask, crmask, H, W, prm, iter, work, out_info, (cudaStream_t)stream);
     return sparse_iteration(img, inmask, crmask, H, W, prm, iter, mode == 2, work, out_info, (cudaStream_t)stream,
-                            mode == 3);
+                            mode == 3, mode == 4);
 }
 
 extern "C" int bbx_lacosmic(float *img, const uint8_t *inmask, uint8_t *crmask, int H, int W,

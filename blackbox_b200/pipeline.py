@@ -52,7 +52,7 @@ class FramePipeline:
 
     def __init__(self, tel, raw_shape, mbias=None, mflat=None, bpm=None, coeffs=None, niter=None,
                  xbin=1, ybin=1, device=None, exptime=60.0, count_objects=True, use_graphs=False,
-                 fill_edge=False, fuse_scan=False):
+                 fill_edge=False, fuse_scan=False, stats_in_apply=True):
         self.tel = tel
         self.device = device if device is not None else R._device()
         self.geom = Geometry.from_raw_shape(tuple(raw_shape), xbin=xbin, ybin=ybin, tel=tel)
@@ -90,6 +90,8 @@ class FramePipeline:
         # 560 MB less DRAM traffic per frame, but measured slower than the two tuned kernels apart
         # (0.63 ms against 0.34 + 0.25 ms, profiles/r02_fused_scan.txt) -- off unless asked for
         self.fuse_scan = bool(fuse_scan)
+        # middle road: only the background statistics move into the per-pixel pass (bbx_reduce_apply_stats)
+        self.stats_in_apply = bool(stats_in_apply)
         self.chan_med = torch.zeros(self.geom.nchans, dtype=torch.float32, device=dev)
         self._cm_work = (torch.empty(R.query('bbx_chanmed_work_bytes'), dtype=torch.uint8, device=dev)
                          if self.fill_edge else None)
@@ -237,8 +239,10 @@ class FramePipeline:
         # The usual case fuses the dense Laplacian scan of LACosmic's first iteration into the
         # per-pixel pass (the image is scanned while it is made); the rare repeats -- dense
         # morphology, LACosmic with the background level up front or densely -- take the passes apart.
-        fused = (self.fuse_scan and not dense_morph and lac_mode == R.LAC_LAZY and self.niter > 0
-                 and R.fusable(geom, raw_t, out_img, out_mask, self.mbias, self.mflat, self.bpm, self.crmask))
+        fusable = (not dense_morph and lac_mode == R.LAC_LAZY and self.niter > 0
+                   and R.fusable(geom, raw_t, out_img, out_mask, self.mbias, self.mflat, self.bpm, self.crmask))
+        fused = self.fuse_scan and fusable
+        stats = self.stats_in_apply and fusable and not fused
         lac_args = (get_par(set_bb.sigclip, tel), get_par(set_bb.sigfrac, tel), get_par(set_bb.objlim, tel))
         if fused:
             run('apply', lambda: R.apply_scan_enqueue(
@@ -248,6 +252,15 @@ class FramePipeline:
             run('mask_morph', lambda: R.mask_morph_enqueue(
                 out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=True, track=(out_img, self.lwork)))
             lac_mode = R.LAC_FUSED
+        elif stats:
+            # the per-pixel pass takes the statistics of LACosmic's background level on its way; the
+            # dense scan is then the Laplacian alone
+            run('apply', lambda: R.apply_stats_enqueue(
+                raw_t, geom, tel, self.st, self._gain_for(raw_t), self.mbias, self.mflat, self.bpm, out_img, out_mask,
+                self.mwork, self.niter, self.lwork))
+            run('mask_morph', lambda: R.mask_morph_enqueue(
+                out_mask, tel, self.mwork, count_objects=self.count_objects, sparse=True, track=(out_img, self.lwork)))
+            lac_mode = R.LAC_STATS
         else:
             run('apply', lambda: R.apply_enqueue(
                 raw_t, geom, tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias, mflat=self.mflat,
@@ -267,7 +280,7 @@ class FramePipeline:
 
             def lac_finish():
                 call('bbx_lacosmic_finish', R._ptr(self.crmask), R._ptr(out_mask), bit, RH, RW,
-                     int(R.LAC_LAZY if lac_mode == R.LAC_FUSED else lac_mode),
+                     int(R.LAC_LAZY if lac_mode in (R.LAC_FUSED, R.LAC_STATS) else lac_mode),
                      R._ptr(self.lwork.buf), R._ptr(self.mwork.labels), R._ptr(self.ncosmic), R._stream())
 
             run('lacosmic', lac)

@@ -345,6 +345,20 @@ def apply_scan_enqueue(raw_t, geom, tel_, st, gain, mbias, mflat, bpm, out_img, 
     return out_img, out_mask
 
 
+def apply_stats_enqueue(raw_t, geom, tel_, st, gain, mbias, mflat, bpm, out_img, out_mask, mwork, niter, lwork):
+    """Enqueue the fused per-pixel pass with the statistics of detect_cosmics' background level taken
+    on the way (include/bbx.h: bbx_reduce_apply_stats).  To be followed by ``mask_morph_enqueue(...,
+    track=(out_img, lwork))`` and ``lacosmic_enqueue(..., mode=LAC_STATS)`` with the same work buffer."""
+    g = geom.as_struct()
+    bits = _bits(tel_)
+    gain_h = _harr([float(x) for x in gain], C.c_float) if gain is not None else None
+    call('bbx_reduce_apply_stats', _ptr(raw_t), _raw_type(raw_t), C.byref(g), gain_h, _ptr(st.vos_fit), _ptr(st.oscan),
+         _ptr(mbias), _ptr(mflat), _ptr(bpm), _ptr(st.satlevel), C.byref(bits), _ptr(out_img), _ptr(out_mask),
+         _ptr(mwork.seeds), _ptr(mwork.seed_count), int(mwork.seed_cap), int(niter), _ptr(lwork.buf), _ptr(lwork.info),
+         _stream())
+    return out_img, out_mask
+
+
 def os_corr(data, header, imgtype, xbin=1, ybin=1, data_limit=2000, tel=None, strict=True,
             return_state=False):
     """Overscan correction; returns the cropped float32 frame and fills the header keywords
@@ -613,7 +627,7 @@ class LacosmicWork:
         self.info = info if info is not None else torch.zeros(4 + max(niter, 1), dtype=torch.int64, device=device)
 
 
-LAC_LAZY, LAC_DENSE, LAC_LAZY_BG, LAC_FUSED = 0, 1, 2, 3      # LAC_FUSED: after apply_scan_enqueue
+LAC_LAZY, LAC_DENSE, LAC_LAZY_BG, LAC_FUSED, LAC_STATS = 0, 1, 2, 3, 4   # LAC_FUSED / LAC_STATS: after apply_scan_enqueue / apply_stats_enqueue
 LAC_STATUS_OVERFLOW, LAC_STATUS_NEED_BG = 1, 2
 
 

@@ -164,6 +164,19 @@ int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_geom *g, cons
                           const double *readnoise_dev, int niter, void *lac_work, long long *lac_info,
                           void *stream);
 
+/* bbx_reduce_apply that also takes the statistics of detect_cosmics' background level (count of
+ * unmasked pixels, of those below a bracket, histogram inside it) while the values are in
+ * registers, so that LACosmic's dense scan is the Laplacian alone (no mask read, no key
+ * arithmetic).  Does what bbx_lacosmic_begin does.  Afterwards: bbx_mask_morph_sparse_track (corrects
+ * the statistics for the pixels it masks), bbx_lacosmic_iteration(..., mode 4), bbx_lacosmic_finish
+ * (mode 0).  Bit-identical to the separate calls.  Needs the 4-pixel-aligned layout. */
+int bbx_reduce_apply_stats(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
+                           const double *vos_fit, const double *oscan, const float *mbias,
+                           const float *mflat, const uint8_t *bpm, const double *satlevel,
+                           const bbx_maskbits *bits, float *out_img, uint8_t *out_mask,
+                           unsigned int *seeds, unsigned int *seed_count, unsigned int seed_cap,
+                           int niter, void *lac_work, long long *lac_info, void *stream);
+
 /* satlevel[i] = sat_e_h[i] - biasm[i] on the device (blackbox.py:4448-4454) */
 int bbx_satlevels(const double *sat_e_h, const double *biasm, double *out_satlevel,
                   void *stream);
@@ -295,6 +308,8 @@ int bbx_stack_clipped_median(const float *const *frames_h, const float *scale_h,
  *            pixels) computed up front by three extra passes over image + mask
  *        3 = lazy, the dense pass already done by bbx_reduce_apply_scan (bbx_lacosmic_iteration
  *            only; bbx_lacosmic_begin is a no-op)
+ *        4 = lazy, the background statistics already taken by bbx_reduce_apply_stats: the dense
+ *            pass is the Laplacian alone (bbx_lacosmic_begin is a no-op)
  * out_info int64 [4 + niter] device: [0] iterations run, [1] internal, [2] status bits
  * (BBX_LAC_OVERFLOW: a work list overflowed -> result incomplete, repeat with mode 1;
  * BBX_LAC_NEED_BG (mode 0 only): a cosmic-ray pixel without any usable neighbour in its 5x5

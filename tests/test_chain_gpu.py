@@ -335,11 +335,16 @@ def test_fused_scan_equals_separate_passes_with_rings_next_to_cosmic_rays(tel, s
     data_o, mask_o, hdr_o, hm_o = R.reduce_frame(raw, tel, mbias, mflat, bpm, coeffs, niter=4)
     cr = (mask_o & 2) != 0
     fused = FramePipeline(tel, raw.shape, fuse_scan=True, **kw)
-    plain = FramePipeline(tel, raw.shape, fuse_scan=False, **kw)
-    rf, rp = fused.reduce(raw), plain.reduce(raw)
-    assert rf.redo == rp.redo
+    plain = FramePipeline(tel, raw.shape, fuse_scan=False, stats_in_apply=False, **kw)
+    stats = FramePipeline(tel, raw.shape, fuse_scan=False, stats_in_apply=True, **kw)
+    rf, rp, rs = fused.reduce(raw), plain.reduce(raw), stats.reduce(raw)
+    assert rf.redo == rp.redo == rs.redo
     assert torch.equal(rf.mask, rp.mask) and torch.equal(rf.img, rp.img)
+    assert torch.equal(rs.mask, rp.mask) and torch.equal(rs.img, rp.img)
     assert rf.header == rp.header and rf.header_mask == rp.header_mask
+    assert rs.header == rp.header and rs.header_mask == rp.header_mask
+    rs2 = stats.reduce(raw)
+    assert torch.equal(rs2.mask, rp.mask) and torch.equal(rs2.img, rp.img)
     assert np.array_equal(rf.mask.cpu().numpy(), mask_o)
     img = rf.img.cpu().numpy()
     assert np.mean(img == data_o) > 0.999

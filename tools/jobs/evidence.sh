@@ -7,14 +7,8 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --batch 4 --no-e2e --no-cpu-baseline --no-masters --no-strong > gpurun_out/${R}_launches_bench.log 2>&1; echo "launch list rc $?"
 python tools/launch_summary.py gpurun_out/${R}_launches_bench.csv 60 > gpurun_out/${R}_launches_bench.summary.txt 2>&1
 # one frame under ncu --set full: skip the first frame's launches (warm-up), take the second frame's
-N=$(python - <<'PY'
-import csv
-rows=[l for l in open('gpurun_out/r02_launches_bench.csv') if l.startswith('"')]
-print(len(rows))
-PY
-)
-timeout 1200 ncu --set full --clock-control none --import-source on -s 64 -c 72 -o gpurun_out/${R}_frame -f python tools/one_frame.py --frames 2 > gpurun_out/${R}_ncu_frame.log 2>&1; echo "ncu full rc $?"
-python tools/ncu_summary.py gpurun_out/${R}_frame.ncu-rep gpurun_out/${R}_ncu_full_summary.txt gpurun_out/${R}_ncu_traffic.json "round 2" > /dev/null 2>&1
+timeout 1200 ncu --set full --clock-control none -s 64 -c 72 -o /tmp/${R}_frame -f python tools/one_frame.py --frames 2 > gpurun_out/${R}_ncu_frame.log 2>&1; echo "ncu full rc $?"
+python tools/ncu_summary.py /tmp/${R}_frame.ncu-rep gpurun_out/${R}_ncu_full_summary.txt gpurun_out/${R}_ncu_traffic.json "round 2" > /dev/null 2>&1
 timeout 300 python tools/kbench.py > gpurun_out/${R}_kbench.txt 2>&1
 timeout 300 python tools/rice_bench.py > gpurun_out/${R}_rice_bench.txt 2>&1
 timeout 200 python tools/xt_bench.py > gpurun_out/${R}_xt_bench.txt 2>&1
