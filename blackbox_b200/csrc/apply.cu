@@ -122,6 +122,11 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
 {
     const int RW = g.nx * g.xsize_chan, RH = g.ny * g.ysize_chan;
     const int x = (blockIdx.x * APPLY_THREADS + threadIdx.x) * 4;
+    __shared__ unsigned int s_stat[2];
+    if (STATS) {
+        if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+        __syncthreads();
+    }
     if (x >= RW) return;
     const int c = x / g.xsize_chan, lx = x - c * g.xsize_chan;
     const int ya = blockIdx.y * APPLY_ROWS, yb = min(ya + APPLY_ROWS, RH);
@@ -243,9 +248,19 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
         finish_row(y, in0);
     }
     if (STATS) {
-        // (threads beyond the frame have left: the counters go out one atomic per thread that has any)
-        if (n_valid) atomicAdd(&bg->n_valid, (unsigned long long)n_valid);
-        if (n_below) atomicAdd(&bg->n_below, (unsigned long long)n_below);
+        // per warp (the lanes beyond the frame have left), per CTA in shared memory, then two atomics
+        // per CTA: one atomic per thread on the same two words cost 3 ms per frame
+        const unsigned int m = __activemask();
+        const unsigned int tv = __reduce_add_sync(m, n_valid), tb = __reduce_add_sync(m, n_below);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+            if (tv) atomicAdd(&s_stat[0], tv);
+            if (tb) atomicAdd(&s_stat[1], tb);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                       // (thread 0 of a CTA is always inside the frame)
+            if (s_stat[0]) atomicAdd(&bg->n_valid, (unsigned long long)s_stat[0]);
+            if (s_stat[1]) atomicAdd(&bg->n_below, (unsigned long long)s_stat[1]);
+        }
     }
 }
 
