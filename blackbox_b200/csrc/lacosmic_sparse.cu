@@ -1022,6 +1022,23 @@ __global__ void sp_init_kernel(long long *info, int n, SparseCounters *cnt, unsi
     }
 }
 
+// The flag bytes of this iteration go back to zero, list by list (every flag sits on a pixel of
+// list A -- which holds B and C0 --, of list C1 or of list Q), so that the 2-bit iteration stamp can
+// wrap without the 111 MB memset it used to cost every third iteration.  Runs before sp_control_kernel
+// resets the counters.
+__global__ void __launch_bounds__(256)
+sp_flags_cleanup_kernel(SparseWork w, int it, const long long *__restrict__ info)
+{
+    if (!info[INFO_ACTIVE]) return;
+    const unsigned int nA = list_len(&w.cnt->nA[it & 1], w.capA), nC1 = list_len(&w.cnt->nC1, w.capC);
+    const unsigned int nQ = list_len(&w.cnt->nQ, w.capB);
+    const unsigned int total = nA + nC1 + nQ;
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned int p = t < nA ? w.listA[it & 1][t] : t < nA + nC1 ? w.listC1[t - nA] : w.listB[t - nA - nC1];
+        w.flags[p] = 0;
+    }
+}
+
 // after grow2: stop flag for the iterations that follow, reset of the per-iteration lists
 __global__ void sp_control_kernel(long long *info, int iter, SparseCounters *cnt)
 {
@@ -1147,7 +1164,6 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     // grid would mostly launch and retire idle CTAs
     const int list_blocks = it == 0 ? BBX_SM_COUNT * 8 : BBX_SM_COUNT * 2;
     const int warp_blocks = it == 0 ? BBX_SM_COUNT * 16 : BBX_SM_COUNT * 4;
-    if (it > 0 && it % STAMP_PERIOD == 0) BBX_CUDA(cudaMemsetAsync(w.flags, 0, n, st));      // stamps wrap
     if (it == 0 && prescanned) {
         // bbx_reduce_apply_scan has made list A, the statistics and the cleared byte maps; the mask
         // morphology has corrected the statistics for the pixels it masked since
@@ -1170,6 +1186,7 @@ static int sparse_iteration(float *img, const uint8_t *inmask, uint8_t *crmask, 
     sp_grow1_kernel<<<list_blocks, 128, 0, st>>>(H, W, w, stamp, info);
     sp_grow2a_kernel<<<list_blocks, 128, 0, st>>>(inmask, crmask, H, W, prm, w, stamp, it, info);
     sp_grow2b_kernel<<<warp_blocks, 128, 0, st>>>(img, crmask, H, W, prm, w, stamp, it, info);
+    sp_flags_cleanup_kernel<<<list_blocks, 256, 0, st>>>(w, it, info);
     sp_control_kernel<<<1, 1, 0, st>>>(info, it, w.cnt);
     if (it == 0) sp_clean_kernel<true><<<warp_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
     else sp_clean_kernel<false><<<warp_blocks, 128, 0, st>>>(img, crmask, inmask, H, W, w, info);
