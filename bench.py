@@ -334,20 +334,24 @@ def run_gpu(args, rank, world, local_rank):
         p.enable_stage_timing(False)
 
     # ---- end to end: pinned host raw in, pinned host image + mask out -----------------------
-    e2e = e2e_plain = None
+    e2e = e2e_plain = e2e_f32 = None
     if not args.no_e2e:
-        def e2e_entry(packed, steps):
-            ms, h2d, d2h = measure_e2e(args, batch, raws, red_shape, barrier, packed=packed, steps=steps)
+        def e2e_entry(mode, steps):
+            ms, h2d, d2h = measure_e2e(args, batch, raws, red_shape, barrier, mode=mode, steps=steps)
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return {'value': world * B * steps / (float(t.item()) * 1e-3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': int(world * B * h2d), 'd2h_bytes_per_step': int(world * B * d2h),
                     'steps': steps}
-        e2e = e2e_entry(True, args.steps)
-        e2e['io'] = ('in: fpacked raw frame (Rice-coded heap + tile descriptors, pinned host memory), decoded on '
-                     'the device; out: float32 image + Rice-coded uint8 mask (the reference\'s fpack -D -Y product)')
-        e2e_plain = e2e_entry(False, max(1, min(args.steps, 3)))
+        e2e = e2e_entry('fz', args.steps)
+        e2e['io'] = ('the files of the reference on both sides -- in: fpacked raw frame (Rice-coded heap + tile '
+                     'descriptors, pinned host memory), decoded on the device; out: the reduced image as `fpack -q 16 '
+                     '-D -Y` writes it (blackbox.py:836: rows quantised at 1/16 of their noise with subtractive '
+                     'dither, Rice-coded: bbx_fpack_f32) + the mask as `fpack -D -Y` (losslessly Rice-coded uint8)')
+        e2e_f32 = e2e_entry('f32', max(1, min(args.steps, 3)))
+        e2e_f32['io'] = 'in: fpacked raw frame; out: float32 image as it is + Rice-coded uint8 mask'
+        e2e_plain = e2e_entry('plain', max(1, min(args.steps, 3)))
         e2e_plain['io'] = 'in: uint16 raw frame; out: float32 image + plain uint8 mask (round 1\'s e2e)'
 
     # ---- strong scaling: the night batch as one job of B frames in total -----------------------
@@ -376,7 +380,8 @@ def run_gpu(args, rank, world, local_rank):
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args), 'roofline': roof, 'roofline_stages': stages, 'cpu_baseline': cpu,
-            'clocks': clocks, 'e2e': e2e, 'e2e_uncompressed': e2e_plain, 'gpu_launches': launches,
+            'clocks': clocks, 'e2e': e2e, 'e2e_f32_image': e2e_f32, 'e2e_uncompressed': e2e_plain,
+            'gpu_launches': launches,
             'chain_hbm_frac': (ALGO_BYTES_CHAIN_4IT * frames / world / (ms_total * 1e-3)) / (peak_hbm()[0] * 1e9),
             'frames_redone': redo, 'host_spline_columns': spline_cols[0],
             'graph_replays': sum(p.graph_replays for p in batch.pipes),
@@ -648,22 +653,28 @@ def stage_rooflines(pipes):
     return roof, stages
 
 
-def measure_e2e(args, batch, raws, red_shape, barrier, packed=True, steps=None):
+def measure_e2e(args, batch, raws, red_shape, barrier, mode='fz', steps=None):
     """Public API with host buffers (BatchReducer.run_host), H2D / D2H copies, the chain and the
     codecs overlapping on their own streams, `--depth` frames in flight.
-    packed (the headline): every raw frame arrives as the telescope delivers it -- an fpacked
+    mode 'fz' (the headline): every raw frame arrives as the telescope delivers it -- an fpacked
     .fits.fz, i.e. a pinned host buffer with its Rice-coded heap (~1/3 of the frame) plus tile
-    descriptors, decoded on the device -- and the mask leaves as the reference's own product, the
-    losslessly Rice-coded uint8 image (`fpack -D -Y`); the float32 image leaves as it is.
-    not packed: pinned uint16 raw frames in, float32 image + plain uint8 mask out (round 1's e2e).
-    -> (ms, h2d bytes per frame, d2h bytes per frame)"""
+    descriptors, decoded on the device -- and both products leave as the reference writes them to
+    disk: the image as `fpack -q 16 -D -Y` (quantised + Rice-coded on the device, bbx_fpack_f32),
+    the mask as `fpack -D -Y` (losslessly Rice-coded uint8).
+    mode 'f32': as 'fz', but the float32 image leaves as it is (446 MB per frame).
+    mode 'plain': pinned uint16 raw frames in, float32 image + plain uint8 mask out (round 1's e2e).
+    -> (ms, h2d bytes per frame, d2h bytes per frame: counted from the copies made)"""
     import torch
     from blackbox_b200 import fitsio, reduce as R
     B = args.batch
     steps = args.steps if steps is None else steps
     nring = min(B, 8)              # 8 distinct pinned raw frames, cycled through the batch
     nout = min(max(2, args.depth), B) if B > 1 else 1
-    host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nout)]
+    packed = mode in ('fz', 'f32')
+    if mode == 'fz':
+        host_img = [torch.empty(batch.img_fz_bytes(), dtype=torch.uint8).pin_memory() for _ in range(nout)]
+    else:
+        host_img = [torch.empty(red_shape, dtype=torch.float32).pin_memory() for _ in range(nout)]
     if packed:
         ring = []
         for k in range(nring):     # set-up, outside the timed region: fpack the synthetic frames
@@ -675,8 +686,7 @@ def measure_e2e(args, batch, raws, red_shape, barrier, packed=True, steps=None):
         h2d = sum(c.heap.numel() + c.descriptors().numel() for c in ring) / len(ring)
         nbytes = batch.mask_fz_bytes()
         host_mask = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(nout)]
-        d2h = red_shape[0] * red_shape[1] * 4 + nbytes
-        kw = dict(mask_fz=True)
+        kw = dict(mask_fz=True, img_fz=(mode == 'fz'))
     else:
         ring = [torch.empty(raws[0].shape, dtype=torch.uint16).pin_memory() for _ in range(nring)]
         for k in range(nring):
@@ -687,18 +697,22 @@ def measure_e2e(args, batch, raws, red_shape, barrier, packed=True, steps=None):
                 a[...] = be.view(np.int16)
         h2d = raws[0].numel() * 2
         host_mask = [torch.empty(red_shape, dtype=torch.uint8).pin_memory() for _ in range(nout)]
-        d2h = red_shape[0] * red_shape[1] * 5
         kw = dict(fits=bool(args.fits))
     host_raw = [ring[k % nring] for k in range(B)]
+
+    copied = [0, 0]
 
     def run(nsteps):
         redo = 0
         for _ in range(nsteps):
             for res in batch.run_host(host_raw, host_img, host_mask, fill_header=True, **kw):
                 redo += res.redo
+            copied[0] += batch.d2h_bytes
+            copied[1] += B
         return redo
 
     run(1)
+    copied[:] = [0, 0]
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -709,7 +723,8 @@ def measure_e2e(args, batch, raws, red_shape, barrier, packed=True, steps=None):
     t1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    return max(t0.elapsed_time(t1), wall_ms), h2d, d2h
+    del host_img, host_mask
+    return max(t0.elapsed_time(t1), wall_ms), h2d, copied[0] / max(copied[1], 1)
 
 
 def main():

@@ -83,13 +83,18 @@ _SIGNATURES = {
     'bbx_rice_encode_work_bytes': [I, I, I],
     'bbx_rice_encode_out_bytes': [I, I, I],
     'bbx_rice_encode': [P, I, I, I, P, SZ, P, SZ, P],
+    'bbx_fpack_f32_work_bytes': [I, I],
+    'bbx_fpack_f32_out_bytes': [I, I],
+    'bbx_fpack_f32_heap_offset': [I],
+    'bbx_fpack_f32': [P, I, I, F, I, P, P, SZ, P, SZ, P],
     'bbx_chanmed_work_bytes': [],
     'bbx_channel_medians': [P, I, I, I, I, I, P, P, P],
     'bbx_fill_edge': [P, P, I, I, I, I, I, P, P],
 }
 _RESTYPES = {'bbx_fill_holes_work_bytes': SZ, 'bbx_lacosmic_work_bytes': SZ,
              'bbx_select_work_bytes': SZ, 'bbx_chanmed_work_bytes': SZ,
-             'bbx_rice_encode_work_bytes': SZ, 'bbx_rice_encode_out_bytes': SZ}
+             'bbx_rice_encode_work_bytes': SZ, 'bbx_rice_encode_out_bytes': SZ,
+             'bbx_fpack_f32_work_bytes': SZ, 'bbx_fpack_f32_out_bytes': SZ, 'bbx_fpack_f32_heap_offset': SZ}
 
 EXPORTS = tuple(sorted(list(_SIGNATURES) + ['bbx_last_error']))
 

@@ -164,6 +164,7 @@ rice_decode_kernel(const uint8_t *__restrict__ heap, size_t heap_bytes, const lo
     r.ring = &ring[0][threadIdx.x];
     const long long o = offs[tile];
     const int n = lens[tile];
+    if (n == 0) return;                     // stored in the table's fall-back column: the host fills the row
     if (o < 0 || n < BP + 1 || (unsigned long long)o + (unsigned long long)n > heap_bytes) {
         atomicOr(status, 2);
         return;
@@ -375,39 +376,84 @@ template <int BP> __device__ __forceinline__ int rice_signed(typename RiceP<BP>:
     return BP == 1 ? (int)(int8_t)v : BP == 2 ? (int)(int16_t)v : (int)v;
 }
 
+// Where the encoder's pixels come from.  PlainSrc: an integer image.  QuantSrc: a float32 image
+// quantised on the fly as fits_quantize_float does (SUBTRACTIVE_DITHER_1; zscale[tile] == 0 marks
+// a row that is not quantised: it gets no Rice-coded bytes) -- the int32 image never exists.
+template <int BP> struct PlainSrc {
+    const typename RiceP<BP>::T *img;
+    int nx;
+    const typename RiceP<BP>::T *row;
+    __device__ __forceinline__ bool open(int tile, int) { row = img + (size_t)tile * nx; return true; }
+    __device__ __forceinline__ int px(int x) { return rice_signed<BP>(row[x]); }
+};
+
+struct QuantSrc {
+    const float *img;
+    const double *zscale, *zzero;
+    const float *rnd;
+    int nx, zdither0;
+    const float *row;
+    double scale, zero;
+    int seed, nextrand, base;               // position in the random sequence: R[nextrand + (x - base)]
+    __device__ __forceinline__ bool open(int tile, int)
+    {
+        scale = zscale[tile];
+        if (scale == 0.0) return false;
+        zero = zzero[tile];
+        row = img + (size_t)tile * nx;
+        seed = (int)(((long long)tile + zdither0 - 1) % RICE_NRANDOM);
+        if (seed < 0) seed += RICE_NRANDOM;
+        nextrand = (int)(rnd[seed] * 500.0f);
+        base = 0;
+        return true;
+    }
+    // x never decreases from call to call (per lane)
+    __device__ __forceinline__ int px(int x)
+    {
+        while (x - base >= RICE_NRANDOM - nextrand) {
+            base += RICE_NRANDOM - nextrand;
+            seed = seed + 1 == RICE_NRANDOM ? 0 : seed + 1;
+            nextrand = (int)(rnd[seed] * 500.0f);
+        }
+        const double v = ((double)row[x] - zero) / scale + (double)rnd[nextrand + (x - base)] - 0.5;
+        return (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+    }
+};
+
 // One warp per tile (grid-stride), a lane per pixel of the block.  scratch: ntiles rows of
 // `stride` bytes (16-byte multiples); out_lens[t] = compressed bytes of tile t.
-template <int BP>
+template <int BP, typename SRC>
 __global__ void __launch_bounds__(RENC_WARPS * 32)
-rice_encode_kernel(const typename RiceP<BP>::T *__restrict__ img, int ntiles, int nx, uint8_t *__restrict__ scratch,
-                   size_t stride, int *__restrict__ out_lens)
+rice_encode_kernel(SRC src, int ntiles, int nx, uint8_t *__restrict__ scratch, size_t stride, int *__restrict__ out_lens)
 {
     typedef RiceP<BP> P;
-    typedef typename P::T T;
     __shared__ uint32_t sbuf[RENC_WARPS][RENC_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *buf = sbuf[warp];
     const unsigned FULL = 0xffffffffu;
     for (int tile = blockIdx.x * RENC_WARPS + warp; tile < ntiles; tile += gridDim.x * RENC_WARPS) {
-        const T *row = img + (size_t)tile * nx;
+        if (!src.open(tile, lane)) {
+            if (lane == 0) out_lens[tile] = 0;
+            continue;
+        }
         uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (size_t)tile * stride);
         int wpos = 0;                       // whole 32-bit words already written for this tile
         uint32_t carry;                     // the partly filled word (its top cbits bits are valid)
         int cbits;
-        const T first = row[0];
+        int cur = (lane < nx) ? src.px(lane) : 0;
+        const int first = __shfl_sync(FULL, cur, 0);
         if (BP == 4) {
             if (lane == 0) dst[0] = __byte_perm((uint32_t)first, 0, 0x0123);
             wpos = 1; carry = 0; cbits = 0;
         } else {
             carry = (uint32_t)first << (32 - P::BBITS); cbits = P::BBITS;
         }
-        int lastpix = rice_signed<BP>(first);
-        int cur = (lane < nx) ? rice_signed<BP>(row[lane]) : 0;
+        int lastpix = first;
         for (int i = 0; i < nx; i += RICE_BLOCK) {
             const int nthis = min(RICE_BLOCK, nx - i);
             // the next block's pixel is requested before this block is coded
             const int inext = i + RICE_BLOCK + lane;
-            const int nxt = (inext < nx) ? rice_signed<BP>(row[inext]) : 0;
+            const int nxt = (inext < nx) ? src.px(inext) : 0;
             int prev = __shfl_up_sync(FULL, cur, 1);
             if (lane == 0) prev = lastpix;
             // difference in the pixel's own width (it wraps), zig-zag mapped
@@ -483,7 +529,7 @@ struct RiceOutHdr { long long total; int ntiles; int status; };
 
 __global__ void __launch_bounds__(1024)
 rice_scan_kernel(const int *__restrict__ lens, int ntiles, long long *__restrict__ offs, RiceOutHdr *hdr,
-                 long long heap_cap)
+                 long long heap_cap, const int *__restrict__ nskipped)
 {
     __shared__ long long part[1024];
     const int t = threadIdx.x;
@@ -504,7 +550,7 @@ rice_scan_kernel(const int *__restrict__ lens, int ntiles, long long *__restrict
     if (t == 1023) {
         hdr->total = part[1023];
         hdr->ntiles = ntiles;
-        hdr->status = part[1023] > heap_cap ? 1 : 0;
+        hdr->status = (part[1023] > heap_cap ? 1 : 0) | (nskipped ? (*nskipped << 8) : 0);
     }
 }
 
@@ -588,11 +634,269 @@ extern "C" int bbx_rice_encode(const void *img, int ntiles, int nx, int bytepix,
     const long long heap_cap = (long long)(out_bytes - rice_heap_offset(ntiles));
     const int want = (ntiles + RENC_WARPS - 1) / RENC_WARPS;
     const int blocks = want < BBX_SM_COUNT * 16 ? want : BBX_SM_COUNT * 16;
-    if (bytepix == 1) rice_encode_kernel<1><<<blocks, RENC_WARPS * 32, 0, st>>>((const uint8_t *)img, ntiles, nx, scratch, stride, lens);
-    else if (bytepix == 2) rice_encode_kernel<2><<<blocks, RENC_WARPS * 32, 0, st>>>((const uint16_t *)img, ntiles, nx, scratch, stride, lens);
-    else rice_encode_kernel<4><<<blocks, RENC_WARPS * 32, 0, st>>>((const uint32_t *)img, ntiles, nx, scratch, stride, lens);
+    if (bytepix == 1) {
+        PlainSrc<1> src = {(const uint8_t *)img, nx, nullptr};
+        rice_encode_kernel<1><<<blocks, RENC_WARPS * 32, 0, st>>>(src, ntiles, nx, scratch, stride, lens);
+    } else if (bytepix == 2) {
+        PlainSrc<2> src = {(const uint16_t *)img, nx, nullptr};
+        rice_encode_kernel<2><<<blocks, RENC_WARPS * 32, 0, st>>>(src, ntiles, nx, scratch, stride, lens);
+    } else {
+        PlainSrc<4> src = {(const uint32_t *)img, nx, nullptr};
+        rice_encode_kernel<4><<<blocks, RENC_WARPS * 32, 0, st>>>(src, ntiles, nx, scratch, stride, lens);
+    }
     BBX_CHECK_LAUNCH("rice_encode_kernel");
-    rice_scan_kernel<<<1, 1024, 0, st>>>(lens, ntiles, offs, hdr, heap_cap);
+    rice_scan_kernel<<<1, 1024, 0, st>>>(lens, ntiles, offs, hdr, heap_cap, nullptr);
+    BBX_CHECK_LAUNCH("rice_scan_kernel");
+    const int cblocks = (ntiles + 7) / 8 < BBX_SM_COUNT * 8 ? (ntiles + 7) / 8 : BBX_SM_COUNT * 8;
+    rice_compact_kernel<<<cblocks, 256, 0, st>>>(scratch, stride, lens, offs, ntiles, heap, heap_cap);
+    BBX_CHECK_LAUNCH("rice_compact_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// `fpack -q <q>` of a float32 image on the device (blackbox.py:826-836: every reduced image is
+// written as `fpack -q 16 -D -Y`: quantised with subtractive dither, Rice-coded) -- so that the
+// compressed product, a fifth of the float32 image, is what crosses PCIe on the way out.
+//
+// Per row tile (fits_quantize_float + FnNoise5_float of CFITSIO's quantize.c, restated in
+// oracle/rice.py: fn_noise5_row / fpack_quantize_row):
+//   c = 4 .. nx-5, v1..v9 = row[c-4 .. c+4], float32 arithmetic left to right
+//     d2 = |v5 - v7|                       unless v5 == v6 == v7
+//     d3 = |2 v5 - v3 - v7|                unless v3 == v4 == v5 == v6 == v7
+//     d5 = |6 v5 - 4 v3 - 4 v7 + v1 + v9|  (as d3)
+//   med = element (m - 1) / 2 of the m = count(d3) sorted values (d2: over m entries of a
+//   zero-filled array holding count(d2) <= m values, and only if count(d2) > 1, or == 1 when m == 1)
+//   sigma = 0.6052697 med3, replaced by 1.0483579 med2 / 0.1772048 med5 where non-zero and smaller
+//   ZSCALE = sigma / q, ZZERO = trunc(min / ZSCALE + 0.5) ZSCALE  (mid-range if the span needs > 31 bits)
+//   ZSCALE = 0 marks a row that is not quantised: sigma == 0, span > 32 bits, or a non-finite value.
+// fq_row_stats_kernel: one CTA per row, the row in shared memory; the three medians by exact
+// radix select on the float bits (non-negative: the bits order like the values), 11 + 11 + 9
+// bits, three histogram passes for all three at once, the differences recomputed each pass.
+// The quantised values are made inside the Rice encoder (QuantSrc).
+// ---------------------------------------------------------------------------------------------
+#define FQ_THREADS 256
+#define FQ_BINS 2048
+#define FQ_MAX_NX 16384
+
+struct FqSel { unsigned int prefix; unsigned int rank; int use; };
+
+__global__ void __launch_bounds__(FQ_THREADS)
+fq_row_stats_kernel(const float *__restrict__ img, int ntiles, int nx, float qlevel, double *__restrict__ zscale,
+                    double *__restrict__ zzero, int *__restrict__ nskipped)
+{
+    extern __shared__ __align__(16) unsigned char fq_smem[];
+    unsigned int (*hist)[FQ_BINS] = reinterpret_cast<unsigned int (*)[FQ_BINS]>(fq_smem);
+    float *srow = reinterpret_cast<float *>(fq_smem + 3 * FQ_BINS * sizeof(unsigned int));
+    __shared__ float s_lo[FQ_THREADS / 32], s_hi[FQ_THREADS / 32];
+    __shared__ unsigned int s_cnt[3][FQ_THREADS / 32];
+    __shared__ unsigned int s_scan[FQ_THREADS / 32];
+    __shared__ FqSel sel[3];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const float *row = img + (size_t)tile * nx;
+        // ---- the row, its range, non-finite values
+        float lo = INFINITY, hi = -INFINITY;
+        int bad = 0;
+        if (tid == 0) s_bad = 0;
+        if ((nx & 3) == 0 && ((uintptr_t)row & 15) == 0) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(row);
+            for (int i = tid; i < nx / 4; i += FQ_THREADS) {
+                const float4 v = __ldcs(r4 + i);
+                reinterpret_cast<float4 *>(srow)[i] = v;
+                lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
+                hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+                bad |= !isfinite(v.x) | !isfinite(v.y) | !isfinite(v.z) | !isfinite(v.w);
+            }
+        } else {
+            for (int i = tid; i < nx; i += FQ_THREADS) {
+                const float v = row[i];
+                srow[i] = v;
+                lo = fminf(lo, v); hi = fmaxf(hi, v);
+                bad |= !isfinite(v);
+            }
+        }
+        for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(FULL, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
+        }
+        __syncthreads();                                   // s_bad = 0, histograms cleared, row stored
+        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+        if (bad) s_bad = 1;
+        __syncthreads();
+        lo = s_lo[0]; hi = s_hi[0];
+#pragma unroll
+        for (int w = 1; w < FQ_THREADS / 32; w++) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        const bool unusable = s_bad != 0 || nx < 9;
+        // ---- three passes: histogram of the next key bits of the values still in the running
+        for (int level = 0; level < 3 && !unusable; level++) {
+            const int shift = level == 0 ? 20 : level == 1 ? 9 : 0;
+            const int pshift = level == 1 ? 20 : 9;        // bits fixed so far = key >> pshift
+            const unsigned int mask = level == 2 ? 0x1ffu : 0x7ffu;
+            unsigned int n2 = 0, n3 = 0;
+            unsigned int p2 = 0, p3 = 0, p5 = 0;
+            if (level > 0) { p2 = sel[0].prefix; p3 = sel[1].prefix; p5 = sel[2].prefix; }
+            for (int c = 4 + tid; c < nx - 4; c += FQ_THREADS) {
+                const float v1 = srow[c - 4], v3 = srow[c - 2], v4 = srow[c - 1], v5 = srow[c], v6 = srow[c + 1],
+                            v7 = srow[c + 2], v9 = srow[c + 4];
+                const bool e567 = (v5 == v6) && (v6 == v7);
+                const bool keep3 = !((v3 == v4) && (v4 == v5) && e567);
+                if (!e567) {
+                    const unsigned int k = __float_as_uint(fabsf(v5 - v7));
+                    n2++;
+                    if (level == 0 || (k >> pshift) == p2) atomicAdd(&hist[0][(k >> shift) & mask], 1u);
+                }
+                if (keep3) {
+                    float a = 2.0f * v5;
+                    a = a - v3;
+                    a = a - v7;
+                    float b = 6.0f * v5;
+                    b = b - 4.0f * v3;
+                    b = b - 4.0f * v7;
+                    b = b + v1;
+                    b = b + v9;
+                    const unsigned int k3 = __float_as_uint(fabsf(a)), k5 = __float_as_uint(fabsf(b));
+                    n3++;
+                    if (level == 0 || (k3 >> pshift) == p3) atomicAdd(&hist[1][(k3 >> shift) & mask], 1u);
+                    if (level == 0 || (k5 >> pshift) == p5) atomicAdd(&hist[2][(k5 >> shift) & mask], 1u);
+                }
+            }
+            if (level == 0) {
+                // the ranks asked for: m = count(d3); d2 sits in a zero-filled array of m entries
+                n2 = __reduce_add_sync(FULL, n2);
+                n3 = __reduce_add_sync(FULL, n3);
+                if (lane == 0) { s_cnt[0][warp] = n2; s_cnt[1][warp] = n3; }
+            }
+            __syncthreads();
+            if (level == 0 && tid == 0) {
+                unsigned int m2 = 0, m = 0;
+                for (int w = 0; w < FQ_THREADS / 32; w++) { m2 += s_cnt[0][w]; m += s_cnt[1][w]; }
+                const unsigned int r = m ? (m - 1) / 2 : 0, nz = m - m2;
+                sel[1].prefix = 0; sel[1].rank = r; sel[1].use = m > 0;
+                sel[2].prefix = 0; sel[2].rank = r; sel[2].use = m > 0;
+                sel[0].prefix = 0;
+                sel[0].use = (m == 1 ? m2 == 1 : m2 > 1) && r >= nz;
+                sel[0].rank = r >= nz ? r - nz : 0;
+            }
+            __syncthreads();
+            // find, per array, the bin that holds the rank; move the rank into the bin
+            for (int a = 0; a < 3; a++) {
+                const int per = FQ_BINS / FQ_THREADS;
+                unsigned int mine = 0;
+#pragma unroll
+                for (int i = 0; i < per; i++) mine += hist[a][tid * per + i];
+                unsigned int inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) s_scan[warp] = inc;
+                __syncthreads();
+                unsigned int before = inc - mine;
+                for (int w = 0; w < warp; w++) before += s_scan[w];
+                const unsigned int k = sel[a].rank;
+                __syncthreads();                            // everybody has read the rank
+                if (sel[a].use && k >= before && k < before + mine) {
+                    unsigned int acc = before;
+                    int b = tid * per;
+                    for (; b < tid * per + per - 1; b++) { if (acc + hist[a][b] > k) break; acc += hist[a][b]; }
+                    sel[a].prefix = (sel[a].prefix << (level == 2 ? 9 : 11)) | (unsigned int)b;
+                    sel[a].rank = k - acc;
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            double delta = 0.0, zero = 0.0;
+            if (!unusable && sel[1].use) {
+                const double n3v = 0.6052697 * (double)__uint_as_float(sel[1].prefix);
+                const double n5v = 0.1772048 * (double)__uint_as_float(sel[2].prefix);
+                const double n2v = sel[0].use ? 1.0483579 * (double)__uint_as_float(sel[0].prefix) : 0.0;
+                double sigma = n3v;
+                if (n2v != 0.0 && n2v < sigma) sigma = n2v;
+                if (n5v != 0.0 && n5v < sigma) sigma = n5v;
+                delta = sigma / (double)qlevel;
+                if (delta != 0.0) {
+                    const double span = ((double)hi - (double)lo) / delta;
+                    if (!(span <= 2.0 * 2147483647.0 - 10.0)) delta = 0.0;       // (also a NaN / infinite sigma)
+                    else if (span < 2147483647.0 - 10.0) zero = trunc((double)lo / delta + 0.5) * delta;
+                    else zero = ((double)lo + (double)hi) / 2.0;
+                }
+            }
+            zscale[tile] = delta;
+            zzero[tile] = zero;
+            if (delta == 0.0) atomicAdd(nskipped, 1);
+        }
+        __syncthreads();
+    }
+}
+
+static size_t fq_lens_bytes(int ntiles) { return ((size_t)ntiles * 4 + 15) / 16 * 16; }
+static size_t fq_col_bytes(int ntiles) { return ((size_t)ntiles * 8 + 15) / 16 * 16; }
+static size_t fq_heap_offset(int ntiles) { return 16 + fq_lens_bytes(ntiles) + 2 * fq_col_bytes(ntiles); }
+
+// bbx_fpack_f32: img (device float32, ntiles rows of nx pixels) -> out (device):
+//     [0:8)  int64 total heap bytes    [8:12) int32 ntiles
+//     [12:16) int32 status: bit 0 the heap did not fit into out_bytes; bits 8.. = number of rows NOT
+//             quantised (ZSCALE 0, no Rice-coded bytes: the caller stores them losslessly)
+//     int32 compressed bytes per tile (padded to 16 B), float64 ZSCALE per tile (padded to 16 B),
+//     float64 ZZERO per tile (padded to 16 B), then the heap (bbx_fpack_f32_heap_offset).
+// qlevel: fpack's -q (16 for the reduced images); zdither0: the ZDITHER0 keyword to write (1..10000;
+// fpack takes it from the clock); rand10000: the FITS standard's random table on the device.
+extern "C" size_t bbx_fpack_f32_work_bytes(int ntiles, int nx) { return bbx_rice_encode_work_bytes(ntiles, nx, 4); }
+
+extern "C" size_t bbx_fpack_f32_heap_offset(int ntiles) { return ntiles > 0 ? fq_heap_offset(ntiles) : 0; }
+
+extern "C" size_t bbx_fpack_f32_out_bytes(int ntiles, int nx)
+{
+    if (ntiles <= 0 || nx <= 0) return 0;
+    return fq_heap_offset(ntiles) + (size_t)ntiles * rice_stride(nx, 4);
+}
+
+extern "C" int bbx_fpack_f32(const float *img, int ntiles, int nx, float qlevel, int zdither0, const float *rand10000,
+                             void *work, size_t work_bytes, void *out, size_t out_bytes, void *stream)
+{
+    BBX_REQUIRE(img && work && out && rand10000, "bbx_fpack_f32: null argument");
+    BBX_REQUIRE(ntiles > 0 && nx > 0 && nx <= FQ_MAX_NX, "bbx_fpack_f32: %d tiles of %d pixels (rows of up to %d)", ntiles, nx, FQ_MAX_NX);
+    BBX_REQUIRE(qlevel > 0.f, "bbx_fpack_f32: quantisation level %g", (double)qlevel);
+    BBX_REQUIRE(zdither0 >= 1 && zdither0 <= RICE_NRANDOM, "bbx_fpack_f32: ZDITHER0 %d", zdither0);
+    BBX_REQUIRE(work_bytes >= bbx_fpack_f32_work_bytes(ntiles, nx), "bbx_fpack_f32: work buffer too small");
+    BBX_REQUIRE(out_bytes >= fq_heap_offset(ntiles), "bbx_fpack_f32: output buffer too small for the table columns");
+    BBX_REQUIRE(((uintptr_t)work % 16) == 0 && ((uintptr_t)out % 16) == 0, "bbx_fpack_f32: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t stride = rice_stride(nx, 4);
+    uint8_t *scratch = (uint8_t *)work;
+    long long *offs = reinterpret_cast<long long *>(scratch + ((size_t)ntiles * stride + 15) / 16 * 16);
+    RiceOutHdr *hdr = (RiceOutHdr *)out;
+    int *lens = reinterpret_cast<int *>((uint8_t *)out + 16);
+    double *zscale = reinterpret_cast<double *>((uint8_t *)out + 16 + fq_lens_bytes(ntiles));
+    double *zzero = reinterpret_cast<double *>((uint8_t *)zscale + fq_col_bytes(ntiles));
+    uint8_t *heap = (uint8_t *)out + fq_heap_offset(ntiles);
+    const long long heap_cap = (long long)(out_bytes - fq_heap_offset(ntiles));
+    int *nskipped = reinterpret_cast<int *>(offs + ntiles);               // the work buffer's last 16 bytes
+    BBX_CUDA(cudaMemsetAsync(nskipped, 0, sizeof(int), st));
+    const size_t smem = 3 * FQ_BINS * sizeof(unsigned int) + ((size_t)nx * 4 + 15) / 16 * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BBX_CUDA(cudaFuncSetAttribute(fq_row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FQ_BINS * 4 + FQ_MAX_NX * 4));
+        attr_set = true;
+    }
+    const int sblocks = ntiles < BBX_SM_COUNT * 3 ? ntiles : BBX_SM_COUNT * 3;
+    fq_row_stats_kernel<<<sblocks, FQ_THREADS, smem, st>>>(img, ntiles, nx, qlevel, zscale, zzero, nskipped);
+    BBX_CHECK_LAUNCH("fq_row_stats_kernel");
+    const int want = (ntiles + RENC_WARPS - 1) / RENC_WARPS;
+    const int blocks = want < BBX_SM_COUNT * 16 ? want : BBX_SM_COUNT * 16;
+    QuantSrc src = {img, zscale, zzero, rand10000, nx, zdither0, nullptr, 0.0, 0.0, 0, 0, 0};
+    rice_encode_kernel<4><<<blocks, RENC_WARPS * 32, 0, st>>>(src, ntiles, nx, scratch, stride, lens);
+    BBX_CHECK_LAUNCH("rice_encode_kernel(quantised)");
+    rice_scan_kernel<<<1, 1024, 0, st>>>(lens, ntiles, offs, hdr, heap_cap, nskipped);
     BBX_CHECK_LAUNCH("rice_scan_kernel");
     const int cblocks = (ntiles + 7) / 8 < BBX_SM_COUNT * 8 ? (ntiles + 7) / 8 : BBX_SM_COUNT * 8;
     rice_compact_kernel<<<cblocks, 256, 0, st>>>(scratch, stride, lens, offs, ntiles, heap, heap_cap);

@@ -183,9 +183,12 @@ class CompressedImage:
     tile, ``info`` (see ``read_compressed``), ``header``; for float images ``zscale`` / ``zzero``
     (float64 per tile)."""
 
-    def __init__(self, header, heap, offsets, lengths, info, zscale=None, zzero=None):
+    def __init__(self, header, heap, offsets, lengths, info, zscale=None, zzero=None, fallback=None):
         self.header, self.heap, self.offsets, self.lengths, self.info = header, heap, offsets, lengths, info
         self.zscale, self.zzero = zscale, zzero
+        # rows that are not Rice-coded (length 0): {row: pixel values}, unpacked on the host from the
+        # GZIP_COMPRESSED_DATA column (CFITSIO stores a float row there when it cannot be quantised)
+        self.fallback = fallback or {}
         self._desc = None
 
     def __iter__(self):                 # (header, heap, offsets, lengths, info) = read_compressed(...)
@@ -267,9 +270,19 @@ def read_compressed(path, pinned=False):
         else:
             desc = rows[:, found[0]:found[0] + 16].copy().view('>i8').astype(np.int64)
         lengths, offsets = desc[:, 0], desc[:, 1]
+        gz_rows = {}
         if (lengths <= 0).any():
-            raise FitsError('{}: {} tile(s) without Rice-coded bytes (stored in a fall-back column)'.format(
-                path, int((lengths <= 0).sum())))
+            gz = cols.get('GZIP_COMPRESSED_DATA')
+            if gz is None or gz[1] not in ('P', 'Q') or (lengths < 0).any():
+                raise FitsError('{}: {} tile(s) without Rice-coded bytes and no fall-back column'.format(
+                    path, int((lengths <= 0).sum())))
+            w = 8 if gz[1] == 'P' else 16
+            gdesc = rows[:, gz[0]:gz[0] + w].copy().view('>i4' if gz[1] == 'P' else '>i8').astype(np.int64)
+            for r in np.nonzero(lengths == 0)[0]:
+                if gdesc[r, 0] <= 0:
+                    raise FitsError('{}: tile {} has no data in either column'.format(path, int(r)))
+                gz_rows[int(r)] = (int(gdesc[r, 1]), int(gdesc[r, 0]))
+            offsets = np.where(lengths == 0, 0, offsets)
         zscale = zzero = None
         quantize, zdither0, zblank = None, 0, None
         if zbitpix == -32:
@@ -299,6 +312,21 @@ def read_compressed(path, pinned=False):
             raise FitsError('{}: tile descriptors point outside the heap'.format(path))
         if os.path.getsize(path) < heap_start + heap_bytes:
             raise FitsError('{}: truncated heap'.format(path))
+        fallback = {}
+        if gz_rows:
+            import zlib
+            dt = {8: 'u1', 16: '>i2', 32: '>i4', -32: '>f4'}[zbitpix]
+            for r, (o, n) in gz_rows.items():
+                if o < 0 or o + n > heap_bytes:
+                    raise FitsError('{}: tile descriptors point outside the heap'.format(path))
+                fh.seek(heap_start + o)
+                try:
+                    vals = np.frombuffer(zlib.decompress(fh.read(n), 47), dtype=dt)
+                except zlib.error as exc:
+                    raise FitsError('{}: gzipped tile {}: {}'.format(path, r, exc))
+                if vals.size != shape[1]:
+                    raise FitsError('{}: gzipped tile {} holds {} pixels'.format(path, r, vals.size))
+                fallback[r] = vals.astype(vals.dtype.newbyteorder('='))
         if pinned:
             import torch
             heap = torch.empty(heap_bytes, dtype=torch.uint8).pin_memory()
@@ -316,7 +344,8 @@ def read_compressed(path, pinned=False):
     info = dict(bitpix=zbitpix, shape=shape, bzero=float(get('BZERO', 0.0)), bscale=float(get('BSCALE', 1.0)),
                 blocksize=blocksize, bytepix=bytepix, tile_shape=tile, quantize=quantize, zdither0=zdither0,
                 zblank=zblank)
-    return CompressedImage(merged, heap, offsets.astype(np.int64), lengths.astype(np.int32), info, zscale, zzero)
+    return CompressedImage(merged, heap, offsets.astype(np.int64), lengths.astype(np.int32), info, zscale, zzero,
+                           fallback)
 
 
 _dither_table = None
@@ -340,13 +369,17 @@ def dither_random_table():
     return _dither_table
 
 
-def write_compressed(path, heap, lengths, shape, zbitpix, header=None):
-    """Write a tile-compressed image the way fpack lays it out (empty primary HDU; BINTABLE with one
+def write_compressed(path, heap, lengths, shape, zbitpix, header=None, zscale=None, zzero=None, zdither0=None,
+                     lossless_rows=None):
+    """Write a tile-compressed image the way fpack lays it out (empty primary HDU; BINTABLE with a
     COMPRESSED_DATA column of row tiles, RICE_1, BLOCKSIZE 32) from Rice-coded tiles that already
     exist -- ``heap``: the tiles back to back (numpy uint8 / pinned torch tensor), ``lengths``:
-    bytes per tile, as ``bbx_rice_encode`` leaves them.  ``zbitpix`` 8 (the mask: what the reference
-    gets from ``fpack -D -Y``, blackbox.py:826-827), 16 or 32."""
-    if zbitpix not in (8, 16, 32):
+    bytes per tile, as ``bbx_rice_encode`` / ``bbx_fpack_f32`` leave them.  ``zbitpix`` 8 (the mask:
+    what the reference gets from ``fpack -D -Y``, blackbox.py:826-827), 16, 32, or -32: a float image
+    quantised by ``bbx_fpack_f32`` (``fpack -q 16``, blackbox.py:836) with its per-row ``zscale`` /
+    ``zzero`` columns and the ``zdither0`` it was dithered with; ``lossless_rows``: {row: float32
+    values} of the rows that were not quantised (length 0), gzipped into GZIP_COMPRESSED_DATA."""
+    if zbitpix not in (8, 16, 32, -32):
         raise FitsError('write_compressed: ZBITPIX {}'.format(zbitpix))
     H, W = shape
     lens = np.asarray(lengths, dtype=np.int64)
@@ -358,18 +391,59 @@ def write_compressed(path, heap, lengths, shape, zbitpix, header=None):
     if raw.size < total:
         raise FitsError('write_compressed: heap holds {} bytes, the tiles need {}'.format(raw.size, total))
     offs = np.concatenate(([0], np.cumsum(lens)[:-1]))
-    pointer = 'P' if total < 2 ** 31 else 'Q'
-    desc = np.stack([lens, offs], axis=1).astype('>i4' if pointer == 'P' else '>i8')
-    width = desc.dtype.itemsize * 2
+    gz, glens, goffs = [], np.zeros(H, dtype=np.int64), np.zeros(H, dtype=np.int64)
+    if zbitpix == -32:
+        if zscale is None or zzero is None or zdither0 is None:
+            raise FitsError('write_compressed: a float image needs zscale, zzero and zdither0')
+        zs, zz = np.asarray(zscale, dtype=np.float64), np.asarray(zzero, dtype=np.float64)
+        if zs.shape != (H,) or zz.shape != (H,):
+            raise FitsError('write_compressed: {} / {} scale factors for {} rows'.format(zs.size, zz.size, H))
+        missing = set(np.nonzero(lens == 0)[0].tolist()) - set(lossless_rows or {})
+        if missing:
+            raise FitsError('write_compressed: rows {} are neither Rice-coded nor given losslessly'.format(sorted(missing)[:8]))
+        import zlib
+        pos = total
+        for r in sorted(lossless_rows or {}):
+            if lens[r] != 0:
+                continue
+            vals = np.asarray(lossless_rows[r], dtype=np.float32)
+            if vals.shape != (W,):
+                raise FitsError('write_compressed: lossless row {} has shape {}'.format(r, vals.shape))
+            co = zlib.compressobj(6, zlib.DEFLATED, 31)
+            blob = co.compress(vals.astype('>f4').tobytes()) + co.flush()
+            gz.append(blob)
+            glens[r], goffs[r] = len(blob), pos
+            pos += len(blob)
+        offs = np.where(lens == 0, 0, offs)
+    elif (lens <= 0).any():
+        raise FitsError('write_compressed: empty tiles in an integer image')
+    pcount = total + int(glens.sum())
+    pointer = 'P' if pcount < 2 ** 31 else 'Q'
+    ptype = '>i4' if pointer == 'P' else '>i8'
+    pw = 8 if pointer == 'P' else 16
+    columns = [np.stack([lens, offs], axis=1).astype(ptype).view(np.uint8).reshape(H, pw)]
+    fields = [('COMPRESSED_DATA', '1{}B({})'.format(pointer, int(lens.max())))]
+    if zbitpix == -32:
+        if gz:
+            columns.append(np.stack([glens, goffs], axis=1).astype(ptype).view(np.uint8).reshape(H, pw))
+            fields.append(('GZIP_COMPRESSED_DATA', '1{}B({})'.format(pointer, int(glens.max()))))
+        for name, vals in (('ZSCALE', zs), ('ZZERO', zz)):
+            columns.append(np.ascontiguousarray(vals.astype('>f8')).view(np.uint8).reshape(H, 8))
+            fields.append((name, '1D'))
+    table = np.ascontiguousarray(np.concatenate(columns, axis=1))
+    width = table.shape[1]
     primary = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0),
                _card('EXTEND', True), 'END'.ljust(80)]
     ext = ["XTENSION= 'BINTABLE'".ljust(80), _card('BITPIX', 8), _card('NAXIS', 2), _card('NAXIS1', width),
-           _card('NAXIS2', H), _card('PCOUNT', total), _card('GCOUNT', 1), _card('TFIELDS', 1),
-           _card('TTYPE1', 'COMPRESSED_DATA'), _card('TFORM1', '1{}B({})'.format(pointer, int(lens.max()))),
-           _card('ZIMAGE', True), _card('ZSIMPLE', True), _card('ZBITPIX', zbitpix), _card('ZNAXIS', 2),
-           _card('ZNAXIS1', W), _card('ZNAXIS2', H), _card('ZTILE1', W), _card('ZTILE2', 1),
-           _card('ZCMPTYPE', 'RICE_1'), _card('ZNAME1', 'BLOCKSIZE'), _card('ZVAL1', 32),
-           _card('ZNAME2', 'BYTEPIX'), _card('ZVAL2', zbitpix // 8)]
+           _card('NAXIS2', H), _card('PCOUNT', pcount), _card('GCOUNT', 1), _card('TFIELDS', len(fields))]
+    for n, (name, form) in enumerate(fields, 1):
+        ext += [_card('TTYPE{}'.format(n), name), _card('TFORM{}'.format(n), form)]
+    ext += [_card('ZIMAGE', True), _card('ZSIMPLE', True), _card('ZBITPIX', zbitpix), _card('ZNAXIS', 2),
+            _card('ZNAXIS1', W), _card('ZNAXIS2', H), _card('ZTILE1', W), _card('ZTILE2', 1),
+            _card('ZCMPTYPE', 'RICE_1'), _card('ZNAME1', 'BLOCKSIZE'), _card('ZVAL1', 32),
+            _card('ZNAME2', 'BYTEPIX'), _card('ZVAL2', abs(zbitpix) // 8)]
+    if zbitpix == -32:
+        ext += [_card('ZQUANTIZ', 'SUBTRACTIVE_DITHER_1'), _card('ZDITHER0', int(zdither0))]
     skip = {'SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'END', 'EXTEND', 'XTENSION', 'PCOUNT', 'GCOUNT', 'TFIELDS'}
     for key, val in (header.items() if header is not None else ()):
         if str(key).upper() in skip or str(key).upper() in ('COMMENT', 'HISTORY'):
@@ -383,9 +457,11 @@ def write_compressed(path, heap, lengths, shape, zbitpix, header=None):
         for cards in (primary, ext):
             text = ''.join(cards)
             fh.write((text + ' ' * (-len(text) % BLOCK)).encode('ascii', 'replace'))
-        fh.write(desc.tobytes())
+        fh.write(table.tobytes())
         fh.write(memoryview(np.ascontiguousarray(raw[:total])))
-        fh.write(b'\0' * (-(desc.nbytes + total) % BLOCK))
+        for blob in gz:
+            fh.write(blob)
+        fh.write(b'\0' * (-(table.nbytes + pcount) % BLOCK))
     os.replace(tmp, path)
     return path
 

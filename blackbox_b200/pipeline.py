@@ -33,6 +33,8 @@ class FrameResult:
         self.spline_columns = spline_columns   # overscan columns taken from the host spline
         self.redo = redo                       # hole filling needed extra rounds -> chain redone
         self.mask_fz = None                    # (heap, lengths) of the Rice-coded mask (run_host(mask_fz=True))
+        self.img_fz = None                     # the `fpack -q 16` image (run_host(img_fz=True)): keyword
+                                               # arguments of fitsio.write_compressed(..., zbitpix=-32)
 
 
 class FramePipeline:
@@ -97,6 +99,9 @@ class FramePipeline:
                          if self.fill_edge else None)
         # optional: the mask also leaves stage B Rice-coded (BatchReducer.run_host(mask_fz=True))
         self.mask_encoder = None
+        # optional: the image leaves stage B as `fpack -q 16` would write it (run_host(img_fz=True))
+        self.img_encoder = None
+        self._zdither0 = 1
         self._ev_a = torch.cuda.Event()
         self._ev_b = torch.cuda.Event()
         self._raw = None
@@ -129,6 +134,16 @@ class FramePipeline:
         if FramePipeline._cap_stream is None:
             FramePipeline._cap_stream = torch.cuda.Stream()
         return FramePipeline._cap_stream
+
+    def _timed(self, name, fn):
+        """Run ``fn`` eagerly on the current stream (between a pair of events with stage timing on)."""
+        if self.stage_events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.stage_events.setdefault(name, []).append((e0, e1))
 
     def _run(self, name, key, fn):
         """Run one stage on the current stream: eagerly, or (``use_graphs``) as a CUDA graph
@@ -312,14 +327,21 @@ class FramePipeline:
             # the reference's mask product is the losslessly fpacked uint8 image (blackbox.py:826-827)
             enc = self.mask_encoder
             run('mask_fz', lambda: enc.enqueue(out_mask), extra=(enc.out.data_ptr(), enc.work.data_ptr()))
+        if self.img_encoder is not None:
+            # the reference's image product is `fpack -q 16 -D -Y` of the float32 image
+            # (blackbox.py:836).  Not a graph: ZDITHER0 changes from frame to frame, as fpack's does.
+            enc, seed = self.img_encoder, self._zdither0
+            self._timed('img_fz', lambda: enc.enqueue(out_img, seed))
         run('status', status)
 
-    def stage_b_enqueue(self, raw_t, out_img, out_mask, exptime=None):
+    def stage_b_enqueue(self, raw_t, out_img, out_mask, exptime=None, zdither0=None):
         """Stage B on the current stream (which must be ordered after stage A and the spline
         patch): everything from the fused per-pixel pass to the crosstalk correction, then the
         header block into pinned memory.  ``exptime``: the frame's EXPTIME [s] (NCOSMICS is a rate,
         blackbox.py:4354-4361); default: the pipeline's constructor value."""
         self._check_frame(raw_t, out_img, out_mask)
+        if zdither0 is not None:
+            self._zdither0 = 1 + (int(zdither0) - 1) % 10000
         self._rest(raw_t, out_img, out_mask)
         self._ev_b.record()
         self._raw, self._out = raw_t, (out_img, out_mask)
@@ -470,8 +492,16 @@ class BatchReducer:
         RH, RW = self.pipes[0].geom.red_shape
         return 16 + (4 * RH + 15) // 16 * 16 + int(heap_bytes)
 
+    def img_fz_bytes(self, bytes_per_pixel=1.25):
+        """Size of a pinned host buffer that receives a frame's `fpack -q 16` image (``run_host(...,
+        img_fz=True)``): the table columns plus ``bytes_per_pixel`` of heap per pixel.  A sky image
+        quantised at a sixteenth of its noise codes to ~0.85 bytes per pixel; one that does not fit
+        is fetched in full by ``run_host`` (rare, slow)."""
+        RH, RW = self.pipes[0].geom.red_shape
+        return int(R.query('bbx_fpack_f32_heap_offset', RH)) + int(RH * RW * float(bytes_per_pixel)) // 16 * 16
+
     def run_host(self, host_raws, host_imgs, host_masks, fill_header=True, fits=False, exptimes=None,
-                 mask_fz=False):
+                 mask_fz=False, img_fz=False, zdither0=None):
         """The same batch with HOST buffers on both sides: ``host_raws`` pinned uint16 (or
         float32) raw frames, ``host_imgs`` / ``host_masks`` pinned float32 / uint8 outputs (rings:
         frame k goes to index k % len; a ring slot must have been consumed by the caller before
@@ -494,7 +524,17 @@ class BatchReducer:
         reference writes (``fpack -D -Y``, blackbox.py:826-827, 1990); ``host_masks`` are then pinned
         uint8 buffers of ``mask_fz_bytes()`` bytes and every FrameResult carries ``mask_fz = (heap,
         lengths)`` (views into its ring slot) for ``fitsio.write_compressed(path, heap, lengths, shape,
-        8, header_mask)``."""
+        8, header_mask)``.
+
+        ``img_fz``: the image leaves the device as the reference writes it to disk, ``fpack -q 16 -D
+        -Y`` (blackbox.py:826-836, 7677-7679): quantised per row with subtractive dither and
+        Rice-coded by ``bbx_fpack_f32`` -- a fifth of the float32 image's bytes cross PCIe.
+        ``host_imgs`` are then pinned uint8 buffers of ``img_fz_bytes()`` bytes and every FrameResult
+        carries ``img_fz``: the keyword arguments of ``fitsio.write_compressed(path, shape=...,
+        zbitpix=-32, header=..., **res.img_fz)`` (views into its ring slot).  Only as many bytes as
+        the previous frame's heap took (+5 %) are copied; a frame that needs more gets the rest in a
+        second copy.  ``zdither0``: ZDITHER0 of frame k (list; default 1 + k mod 10000 -- fpack
+        draws it from the clock).  ``self.d2h_bytes`` counts the bytes copied to the host."""
         n, d = len(host_raws), self.depth
         if n == 0:
             return []
@@ -541,8 +581,24 @@ class BatchReducer:
                 if m.dtype != torch.uint8 or m.numel() != want or want < self.mask_fz_bytes(0) + 16:
                     raise ValueError('mask_fz: host mask buffers must be equal-sized pinned uint8 buffers of at '
                                      'least mask_fz_bytes(0) + 16 bytes')
+        if img_fz:
+            if fits:
+                raise ValueError('img_fz: the image leaves as a compressed table, fits=True does not apply')
+            want_i = host_imgs[0].numel()
+            if getattr(self, '_fz_img', None) is None or self._fz_img[0].out_bytes != want_i:
+                self._fz_img = [R.FpackEncoder((RH, RW), dev, 16.0, out_bytes=want_i) for _ in range(d)]
+                self._fz_img_guess = want_i
+            for m in host_imgs:
+                if m.dtype != torch.uint8 or m.numel() != want_i or want_i < self.img_fz_bytes(0) + 16:
+                    raise ValueError('img_fz: host image buffers must be equal-sized pinned uint8 buffers of at '
+                                     'least img_fz_bytes(0) + 16 bytes')
+            if zdither0 is not None and len(zdither0) != n:
+                raise ValueError('{} dither seeds for {} frames'.format(len(zdither0), n))
+        copied = [0] * n
+        self.d2h_bytes = 0
         for j, p in enumerate(self.pipes):
             p.mask_encoder = self._fz_out[j] if mask_fz else None
+            p.img_encoder = self._fz_img[j] if img_fz else None
         results = [None] * n
         caller = torch.cuda.current_stream()
         for s in set(self.streams + self.hi_streams) | {self._s_in, self._s_out}:
@@ -556,11 +612,17 @@ class BatchReducer:
                 if fits:
                     img = self._hbuf[j][1]
                     call('bbx_fits_encode', R._ptr(img), -32, 0, img.numel(), R._ptr(img), R._stream())
-                host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
+                if img_fz:
+                    nb = copied[k] = min(host_imgs[0].numel(), self._fz_img_guess)
+                    host_imgs[k % ni][:nb].copy_(self._fz_img[j].out[:nb], non_blocking=True)
+                else:
+                    nb = self._hbuf[j][1].numel() * 4
+                    host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
                 if mask_fz:
                     host_masks[k % nm].copy_(self._fz_out[j].out, non_blocking=True)     # coded at the end of stage B
                 else:
                     host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
+                self.d2h_bytes += nb + host_masks[k % nm].numel()
                 self._ev_out[j].record()
 
         def retire(k):
@@ -571,7 +633,7 @@ class BatchReducer:
                     self._ev_done[j].record()
             if results[k].redo:
                 copy_out(k)
-            if packed[k] or mask_fz:
+            if packed[k] or mask_fz or img_fz:
                 self._ev_out[j].synchronize()
             if packed[k] and int(self._fz_in[j]['status_host'][0]) != 0:
                 raise ValueError('frame {}: corrupt Rice-coded tile(s) in the compressed raw frame (status {})'.format(
@@ -585,6 +647,31 @@ class BatchReducer:
                         host = big.enqueue(self._hbuf[j][2]).cpu()
                     total, lens, heap, _ = big.parse(host)
                 results[k].mask_fz = (heap, lens)
+            if img_fz:
+                enc, host = self._fz_img[j], host_imgs[k % ni]
+                view = host[:copied[k]]
+                got = enc.parse(view)
+                if not got['fits']:
+                    need = enc.heap_offset + got['total']
+                    with torch.cuda.stream(self._s_out):
+                        if need <= host.numel():         # the guess was short: the rest of the heap
+                            host[copied[k]:need].copy_(enc.out[copied[k]:need], non_blocking=True)
+                            self.d2h_bytes += need - copied[k]
+                            view = host[:need]
+                        else:                            # rare: an image that hardly compresses
+                            enc = R.FpackEncoder((RH, RW), dev, 16.0)
+                            view = enc.enqueue(self._hbuf[j][1], self.pipes[j]._zdither0).cpu()
+                            self.d2h_bytes += view.numel()
+                    self._s_out.synchronize()
+                    got = enc.parse(view)
+                self._fz_img_guess = min(host_imgs[0].numel(),
+                                         (enc.heap_offset + int(got['total'] * 1.05) + (1 << 20)) // 4096 * 4096)
+                rows = {}
+                if got['skipped']:
+                    for r in np.nonzero(got['lengths'] == 0)[0]:
+                        rows[int(r)] = self._hbuf[j][1][int(r)].cpu().numpy()
+                results[k].img_fz = dict(heap=got['heap'], lengths=got['lengths'], zscale=got['zscale'],
+                                         zzero=got['zzero'], zdither0=self.pipes[j]._zdither0, lossless_rows=rows)
 
         def stage_a(k):
             j = k % d
@@ -627,7 +714,8 @@ class BatchReducer:
             with torch.cuda.stream(self.streams[j]):
                 self.streams[j].wait_stream(self.hi_streams[j])
                 self.streams[j].wait_event(self._ev_out[j])          # outputs of frame k-d copied out
-                self.pipes[j].stage_b_enqueue(*self._hbuf[j], exptime=None if exptimes is None else exptimes[k])
+                self.pipes[j].stage_b_enqueue(*self._hbuf[j], exptime=None if exptimes is None else exptimes[k],
+                                              zdither0=(1 + k % 10000) if zdither0 is None else zdither0[k])
                 self._ev_done[j].record()
             copy_out(k)
         for k in range(max(n - d, 0), n):

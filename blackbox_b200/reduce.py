@@ -827,7 +827,7 @@ def read_fits_image(path, dtype=None):
         ci = fitsio.read_compressed(path, pinned=True)
         hdr = ci.header
         t = rice_decode(ci.heap.to(_device(), non_blocking=True), ci.offsets, ci.lengths, ci.info,
-                        zscale=ci.zscale, zzero=ci.zzero)
+                        zscale=ci.zscale, zzero=ci.zzero, fallback=ci.fallback)
     else:
         hdr, buf, info = fitsio.read_primary(path, pinned=True)
         if info['bitpix'] == 8:
@@ -868,14 +868,15 @@ def fits_decode(be, info, out=None):
 _RICE_DTYPES = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
 
 
-def rice_decode(heap, offsets, lengths, info, out=None, check=True, zscale=None, zzero=None):
+def rice_decode(heap, offsets, lengths, info, out=None, check=True, zscale=None, zzero=None, fallback=None):
     """Tile-compressed image (``fitsio.read_compressed``: heap bytes + per-tile descriptors) ->
     native CUDA tensor of shape ``info['shape']``: uint16 counts for BITPIX 16 / BZERO 32768 (what
     read_hdulist returns for an fpacked raw frame, blackbox.py:1451), int16 / uint8 / int32 for the
     other integer images, float32 for quantised float images (``zscale`` / ``zzero``: the table's
     per-tile columns).  The heap crosses PCIe compressed; ``bbx_rice_decode`` unpacks it.
     ``check``: synchronise and raise on a corrupt tile (pass False inside a pipeline and test the
-    returned status later)."""
+    returned status later).  ``fallback``: {row: values} of the tiles that are not Rice-coded
+    (``CompressedImage.fallback``; their length is 0 and the decoder leaves the rows alone)."""
     shape = tuple(info['shape'])
     bitpix, bytepix = info.get('bitpix'), info.get('bytepix', 2)
     if (bitpix, bytepix) not in ((8, 1), (16, 2), (32, 4), (-32, 4)):
@@ -908,6 +909,11 @@ def rice_decode(heap, offsets, lengths, info, out=None, check=True, zscale=None,
         call('bbx_unquantize', _ptr(ints), shape[0], shape[1], _ptr(zs), _ptr(zz), _ptr(rnd), method,
              int(info.get('zdither0', 1) or 1), int(zblank if zblank is not None else 0), int(zblank is not None),
              _ptr(res), _stream())
+    empty = (np.asarray(lengths.cpu() if isinstance(lengths, torch.Tensor) else lengths) == 0).nonzero()[0]
+    if set(int(r) for r in empty) - set(fallback or {}):
+        raise ValueError('rice_decode: {} tile(s) without bytes and without fall-back values'.format(len(empty)))
+    for r, vals in (fallback or {}).items():
+        res[int(r)].copy_(torch.from_numpy(np.ascontiguousarray(vals)).to(res.dtype))
     if check:
         code = int(status.item())
         if code:
@@ -948,6 +954,63 @@ class RiceEncoder:
         lens = raw[16:16 + 4 * H].view(np.int32)
         fits = status == 0 and self.heap_offset + total <= raw.size
         return total, lens, raw[self.heap_offset:self.heap_offset + min(total, raw.size - self.heap_offset)], fits
+
+
+class FpackEncoder:
+    """Scratch and output buffers of ``bbx_fpack_f32`` for float32 images of one shape: what the
+    reference's ``fpack -q 16 -D -Y`` makes of a reduced image (blackbox.py:826-836), made on the
+    device.  ``out_bytes``: size of the output buffer (table columns + heap); None = always fits."""
+
+    def __init__(self, shape, device, q=16.0, out_bytes=None):
+        self.shape, self.q = tuple(shape), float(q)
+        H, W = self.shape
+        self.work = torch.empty(query('bbx_fpack_f32_work_bytes', H, W), dtype=torch.uint8, device=device)
+        self.heap_offset = int(query('bbx_fpack_f32_heap_offset', H))
+        full = query('bbx_fpack_f32_out_bytes', H, W)
+        self.out_bytes = int(full if out_bytes is None else max(int(out_bytes), self.heap_offset + 16))
+        self.out = torch.empty(self.out_bytes, dtype=torch.uint8, device=device)
+        self.rand = _to_dev(fitsio.dither_random_table())
+
+    def enqueue(self, img_t, zdither0=1):
+        H, W = self.shape
+        if tuple(img_t.shape) != self.shape or img_t.dtype != torch.float32 or not img_t.is_contiguous():
+            raise ValueError('fpack_f32: expected a contiguous float32 image of shape {}'.format(self.shape))
+        call('bbx_fpack_f32', _ptr(img_t), H, W, self.q, int(zdither0), _ptr(self.rand), _ptr(self.work),
+             self.work.numel(), _ptr(self.out), self.out.numel(), _stream())
+        return self.out
+
+    def parse(self, host_buf):
+        """-> dict(total, lengths int32 [H], zscale / zzero float64 [H], heap view, fits, skipped)
+        of an output buffer (or its leading part) copied to the host.  ``fits`` False: the buffer
+        does not hold the whole heap; ``skipped``: rows that were not quantised (length 0, ZSCALE 0)."""
+        raw = host_buf.numpy() if hasattr(host_buf, 'numpy') else np.asarray(host_buf)
+        total = int(raw[0:8].view(np.int64)[0])
+        status = int(raw[12:16].view(np.int32)[0])
+        H = self.shape[0]
+        o1 = 16 + (4 * H + 15) // 16 * 16
+        o2 = o1 + (8 * H + 15) // 16 * 16
+        lens = raw[16:16 + 4 * H].view(np.int32)
+        fits = (status & 1) == 0 and self.heap_offset + total <= raw.size
+        return dict(total=total, lengths=lens, zscale=raw[o1:o1 + 8 * H].view(np.float64),
+                    zzero=raw[o2:o2 + 8 * H].view(np.float64), fits=fits, skipped=status >> 8,
+                    heap=raw[self.heap_offset:self.heap_offset + min(total, raw.size - self.heap_offset)])
+
+
+def fpack_f32(data, q=16.0, zdither0=1):
+    """float32 image (numpy or CUDA tensor) -> dict(heap, lengths, zscale, zzero, zdither0,
+    lossless_rows) -- the keyword arguments ``fitsio.write_compressed(path, shape=..., zbitpix=-32,
+    **packed)`` wants: the image as ``fpack -q <q> -D -Y`` stores it (blackbox.py:836).  Synchronises."""
+    t = _to_dev(data)
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise NotImplementedError('fpack_f32: dtype {} / {} dimensions'.format(t.dtype, t.dim()))
+    t = t.contiguous()
+    enc = FpackEncoder(tuple(t.shape), t.device, q)
+    got = enc.parse(enc.enqueue(t, zdither0).cpu().numpy())
+    if not got['fits']:
+        raise RuntimeError('fpack_f32: output buffer too small')
+    rows = {int(r): t[int(r)].cpu().numpy() for r in np.nonzero(got['lengths'] == 0)[0]}
+    return dict(heap=got['heap'].copy(), lengths=got['lengths'].copy(), zscale=got['zscale'].copy(),
+                zzero=got['zzero'].copy(), zdither0=int(zdither0), lossless_rows=rows)
 
 
 def rice_encode(data):

@@ -440,6 +440,27 @@ size_t bbx_rice_encode_out_bytes(int ntiles, int nx, int bytepix);
 int bbx_rice_encode(const void *img, int ntiles, int nx, int bytepix, void *work, size_t work_bytes,
                     void *out, size_t out_bytes, void *stream);
 
+/* The reduced image itself leaves the reference as `fpack -q 16 -D -Y` (blackbox.py:826-836, the
+ * float branch of fpack(), called from write_fits, blackbox.py:7677-7679): every row quantised to
+ * integers of ZSCALE = (row noise) / q with subtractive dither, then Rice-coded (BYTEPIX 4).  This
+ * does the same on the device -- CFITSIO's fits_quantize_float / FnNoise5_float restated in
+ * oracle/rice.py (fpack_quantize_row) -- so that the compressed product is what crosses PCIe:
+ * img (device float32, ntiles rows of nx <= 16384 pixels) -> out (device):
+ *     [0:8)   int64 total heap bytes            [8:12) int32 ntiles
+ *     [12:16) int32 status: bit 0 = the heap did not fit into out_bytes (sizes still valid);
+ *             bits 8.. = number of rows NOT quantised (ZSCALE 0 and no Rice-coded bytes: zero noise,
+ *             a span beyond 32 bits or a non-finite value; the caller stores those rows losslessly,
+ *             fitsio.write_compressed gzips them into GZIP_COMPRESSED_DATA as CFITSIO would)
+ *     int32 [ntiles] compressed bytes per tile, float64 [ntiles] ZSCALE, float64 [ntiles] ZZERO,
+ *     each padded to a multiple of 16 bytes; then, at bbx_fpack_f32_heap_offset(ntiles), the heap.
+ * qlevel: fpack's -q; zdither0: the ZDITHER0 keyword that goes with the file (1..10000; fpack
+ * draws it from the clock); rand10000: as for bbx_unquantize.  work >= bbx_fpack_f32_work_bytes. */
+size_t bbx_fpack_f32_work_bytes(int ntiles, int nx);
+size_t bbx_fpack_f32_out_bytes(int ntiles, int nx);
+size_t bbx_fpack_f32_heap_offset(int ntiles);
+int bbx_fpack_f32(const float *img, int ntiles, int nx, float qlevel, int zdither0, const float *rand10000,
+                  void *work, size_t work_bytes, void *out, size_t out_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * small elementwise helpers for the drop-in functions used one step at a time
  * ------------------------------------------------------------------------------------- */

@@ -265,18 +265,29 @@ def unquantize_tile(q, tile_index, scale, zero, dither=1, zdither0=1, zblank=NUL
     return out
 
 
-def _fz_file(path, tiles, shape, zbitpix, bytepix, header, pointer, lead_column, extra_cols=None, extra_cards=()):
+def _fz_file(path, tiles, shape, zbitpix, bytepix, header, pointer, lead_column, extra_cols=None, extra_cards=(),
+             gzip_tiles=None):
     """Lay out primary HDU + BINTABLE + heap the way fpack does.  ``extra_cols``: list of
     (name, float64 array per tile) stored as 1D columns behind COMPRESSED_DATA."""
     from blackbox_b200 import fitsio
     H, W = shape
-    lens = np.array([len(t) for t in tiles], dtype=np.int64)
-    offs = np.concatenate(([0], np.cumsum(lens)[:-1]))
-    heap = b''.join(tiles)
-    desc = np.stack([lens, offs], axis=1).astype('>i4' if pointer == 'P' else '>i8')
+    gzip_tiles = gzip_tiles or {}
+    stored = [gzip_tiles.get(r, t) for r, t in enumerate(tiles)]       # heap order: row by row
+    slens = np.array([len(t) for t in stored], dtype=np.int64)
+    offs = np.concatenate(([0], np.cumsum(slens)[:-1]))
+    heap = b''.join(stored)
+    isgz = np.array([r in gzip_tiles for r in range(H)])
+    ptype = '>i4' if pointer == 'P' else '>i8'
+    desc = np.stack([np.where(isgz, 0, slens), np.where(isgz, 0, offs)], axis=1).astype(ptype)
+    lens = np.where(isgz, 0, slens)
     rows = [desc.view(np.uint8).reshape(H, -1)]
     names = ['COMPRESSED_DATA']
     forms = ['1{}B({})'.format(pointer, int(lens.max()))]
+    if gzip_tiles:
+        gdesc = np.stack([np.where(isgz, slens, 0), np.where(isgz, offs, 0)], axis=1).astype(ptype)
+        rows.append(gdesc.view(np.uint8).reshape(H, -1))
+        names.append('GZIP_COMPRESSED_DATA')
+        forms.append('1{}B({})'.format(pointer, int(np.where(isgz, slens, 0).max())))
     if lead_column:
         rows.insert(0, np.zeros_like(rows[0]))
         names.insert(0, 'GZIP_COMPRESSED_DATA')
@@ -330,30 +341,138 @@ def write_fz_u8(path, img, header=None, pointer='P'):
     return _fz_file(path, tiles, img.shape, 8, 1, header, pointer, False)
 
 
+# -------------------------------------------------------------------------------------------
+# `fpack -q <q>` of a float image (blackbox.py:826-836 runs `fpack -q 16 -D -Y` on every reduced
+# image): CFITSIO's fits_quantize_float with the noise estimate of FnNoise5_float (quantize.c of
+# CFITSIO 4.x; not in /root/reference -- restated from the published source, PARITY UNPINNED:
+# neither CFITSIO nor astropy is in this image.  fpack seeds the dither from the clock by
+# default, so no two runs of the reference itself agree bit for bit; what a reader needs is in
+# the file: ZSCALE / ZZERO per row and ZDITHER0).
+#   row of n >= 9 pixels, c = 4 .. n-5, v1..v9 = row[c-4 .. c+4]:
+#     d2 = |v5 - v7|                          unless v5 == v6 == v7
+#     d3 = |2 v5 - v3 - v7|                   unless v3 == v4 == v5 == v6 == v7
+#     d5 = |6 v5 - 4 v3 - 4 v7 + v1 + v9|     (same condition as d3)
+#   (float32 arithmetic, left to right); median = element (m - 1) / 2 of the m = count(d3)
+#   sorted values -- for d2 ALSO over m entries of its zero-initialised array (it holds
+#   count(d2) <= m values: the rest are zeros), and only if count(d2) > 1;
+#   noise2 = 1.0483579 med2, noise3 = 0.6052697 med3, noise5 = 0.1772048 med5;
+#   sigma = noise3, replaced by noise2 / noise5 where those are non-zero and smaller.
+#   delta = sigma / q; zero = trunc(min / delta + 0.5) * delta;
+#   value = NINT((v - zero) / delta + R - 0.5), NINT(x) = trunc(x + 0.5) / trunc(x - 0.5) for x >= 0 / < 0.
+# A row is NOT quantised (-> None; the writer stores it losslessly in GZIP_COMPRESSED_DATA) if
+# delta == 0 or the quantised range would not fit 32 bits -- and, here, if it holds a non-finite
+# value (CFITSIO would code NaN as ZBLANK; the reduced image has none: they were zeroed and masked).
+# -------------------------------------------------------------------------------------------
+N_RESERVED_VALUES = 10
+
+
+def _lower_median(vals, m):
+    """Element (m - 1) // 2 of the m sorted entries of a zero-initialised array holding ``vals``."""
+    nz = m - vals.size
+    r = (m - 1) // 2
+    if r < nz:
+        return np.float32(0.0)
+    return np.partition(vals, r - nz)[r - nz]
+
+
+def fn_noise5_row(row):
+    """-> (min, max, noise2, noise3, noise5) of one row (float32 in, float64 noise out)."""
+    v = np.asarray(row, dtype=np.float32)
+    n = v.size
+    lo, hi = v.min(), v.max()
+    if n < 9:
+        return lo, hi, 0.0, 0.0, 0.0
+    f = np.float32
+    v1, v3, v4, v5, v6, v7, v9 = v[0:n - 8], v[2:n - 6], v[3:n - 5], v[4:n - 4], v[5:n - 3], v[6:n - 2], v[8:n]
+    keep2 = ~((v5 == v6) & (v6 == v7))
+    keep3 = ~((v3 == v4) & (v4 == v5) & (v5 == v6) & (v6 == v7))
+    d2 = np.abs(v5 - v7)[keep2]
+    d3 = np.abs((f(2) * v5 - v3) - v7)[keep3]
+    d5 = np.abs((((f(6) * v5 - f(4) * v3) - f(4) * v7) + v1) + v9)[keep3]
+    m = d3.size
+    if m == 0:
+        return lo, hi, 0.0, 0.0, 0.0
+    med3, med5 = _lower_median(d3, m), _lower_median(d5, m)
+    if m == 1:
+        med2 = d2[0] if d2.size == 1 else f(0)
+    else:
+        med2 = _lower_median(d2, m) if d2.size > 1 else f(0)
+    return lo, hi, 1.0483579 * float(med2), 0.6052697 * float(med3), 0.1772048 * float(med5)
+
+
+def _nint(x):
+    return np.where(x >= 0, np.trunc(x + 0.5), np.trunc(x - 0.5))
+
+
+def fpack_quantize_row(values, tile_index, q=16.0, zdither0=1):
+    """-> (int32 row, ZSCALE, ZZERO) as `fpack -q <q>` (SUBTRACTIVE_DITHER_1) stores the row, or
+    (None, 0.0, 0.0) for a row it cannot quantise."""
+    v = np.asarray(values, dtype=np.float32)
+    if v.size <= 1 or not np.isfinite(v).all():
+        return None, 0.0, 0.0
+    lo, hi, n2, n3, n5 = fn_noise5_row(v)
+    sigma = n3
+    if n2 != 0.0 and n2 < sigma:
+        sigma = n2
+    if n5 != 0.0 and n5 < sigma:
+        sigma = n5
+    delta = sigma / float(np.float32(q))
+    if delta == 0.0:
+        return None, 0.0, 0.0
+    lo, hi = float(lo), float(hi)
+    if (hi - lo) / delta > 2.0 * 2147483647.0 - N_RESERVED_VALUES:
+        return None, 0.0, 0.0
+    if (hi - lo) / delta < 2147483647.0 - N_RESERVED_VALUES:
+        zero = float(np.trunc(lo / delta + 0.5)) * delta
+    else:
+        zero = (lo + hi) / 2.0
+    r = _dither_sequence(tile_index, zdither0, v.size).astype(np.float64)
+    x = (v.astype(np.float64) - zero) / delta + r - 0.5
+    return _nint(x).astype(np.int64).astype(np.int32), delta, zero
+
+
 def write_fz_f32(path, img, header=None, q=16.0, dither=1, zdither0=1, pointer='P'):
-    """float32 image as `fpack -q` stores it: every row scaled to integers (ZSCALE = a noise
-    estimate / q, ZZERO = the row minimum -- the decoder does not care how they were chosen),
-    subtractive dithering, RICE_1 with BYTEPIX 4.  Returns (path, what a reader must get back)."""
+    """float32 image as `fpack -q <q>` stores it (``fpack_quantize_row``; ``dither`` 0 / 2: the
+    same scaling without dither / with exact zeros kept): RICE_1 with BYTEPIX 4, ZSCALE / ZZERO
+    columns; rows that cannot be quantised go gzipped into GZIP_COMPRESSED_DATA.  Returns (path,
+    what a reader must get back)."""
+    import zlib
     from blackbox_b200 import fitsio
     img = np.asarray(img, dtype=np.float32)
     H, W = img.shape
-    tiles, scales, zeros, back = [], [], [], np.empty_like(img)
+    tiles, scales, zeros, back, gz = [], [], [], np.empty_like(img), {}
     for r in range(H):
-        row = img[r].astype(np.float64)
-        good = row[np.isfinite(row)]
-        noise = 1.4826 * np.median(np.abs(np.diff(good))) / np.sqrt(2) if good.size > 2 else 1.0
-        scale = float(noise / q) if noise > 0 else 1.0
-        zero = float(good.min()) if good.size else 0.0
-        qrow = quantize_tile(img[r], r, scale, zero, dither, zdither0)
-        tiles.append(encode_tile(qrow, 4))
+        finite = np.isfinite(img[r])
+        if not finite.all() and finite.sum() > 2:
+            # CFITSIO codes NaN as ZBLANK; scale and zero point from the finite pixels (their choice
+            # does not matter to a reader; bbx_fpack_f32 stores such a row losslessly instead)
+            good = img[r][finite].astype(np.float64)
+            noise = 1.4826 * np.median(np.abs(np.diff(good))) / np.sqrt(2)
+            scale, zero = (float(noise / q) if noise > 0 else 1.0), float(good.min())
+            qrow = quantize_tile(img[r], r, scale, zero, dither, zdither0)
+            tiles.append(encode_tile(qrow, 4))
+            back[r] = unquantize_tile(qrow, r, scale, zero, dither, zdither0)
+            scales.append(scale)
+            zeros.append(zero)
+            continue
+        qrow, scale, zero = fpack_quantize_row(img[r], r, q, zdither0)
+        if qrow is None:
+            co = zlib.compressobj(6, zlib.DEFLATED, 31)
+            gz[r] = co.compress(img[r].astype('>f4').tobytes()) + co.flush()
+            tiles.append(b'')
+            back[r] = img[r]
+        else:
+            if dither != 1:
+                qrow = quantize_tile(img[r], r, scale, zero, dither, zdither0)
+            tiles.append(encode_tile(qrow, 4))
+            back[r] = unquantize_tile(qrow, r, scale, zero, dither, zdither0)
         scales.append(scale)
         zeros.append(zero)
-        back[r] = unquantize_tile(qrow, r, scale, zero, dither, zdither0)
     card = fitsio._card
     method = {0: 'NO_DITHER', 1: 'SUBTRACTIVE_DITHER_1', 2: 'SUBTRACTIVE_DITHER_2'}[dither]
     extra = [card('ZQUANTIZ', method), card('ZBLANK', NULL_VALUE)]
     if dither:
         extra.append(card('ZDITHER0', zdither0))
     _fz_file(path, tiles, img.shape, -32, 4, header, pointer, False,
-             extra_cols=[('ZSCALE', scales), ('ZZERO', zeros)], extra_cards=extra)
+             extra_cols=[('ZSCALE', scales), ('ZZERO', zeros)], extra_cards=extra, gzip_tiles=gz)
     return path, back

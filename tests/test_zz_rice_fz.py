@@ -372,3 +372,183 @@ def test_c_copy_of_the_codec_equals_the_python_statement(bytepix):
                                   rice.decode_tile(slow, nx, bytepix, fast=False))
     with pytest.raises(ValueError):
         rice.decode_tile(rice.encode_tile(np.arange(300) * 7, bytepix)[:-20], 300, bytepix, fast=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# `fpack -q 16` of the reduced image (blackbox.py:826-836)
+# ---------------------------------------------------------------------------------------------
+def _float_rows(seed, nx, nrows=24):
+    """Rows with different noise levels and the special cases of the noise estimate: constant rows
+    (not quantised), runs of equal values (d2 / d3 skip their entries), a negative background, a
+    step, a row shorter on noise than on signal."""
+    rng = np.random.default_rng(seed)
+    img = np.empty((nrows, nx), dtype=np.float32)
+    for r in range(nrows):
+        img[r] = rng.normal(rng.uniform(-50, 900), rng.uniform(0.5, 60), nx)
+    img[1] = 7.25                                         # constant: no noise, stored losslessly
+    img[2, : nx // 2] = 0.0                               # half the row constant
+    img[3] = np.round(img[3])                             # integers: equal neighbours now and then
+    img[4] = np.round(rng.normal(0, 0.6, nx))             # mostly runs of equal values
+    img[5] = np.where(np.arange(nx) < nx // 3, 100.0, 5000.0) + rng.normal(0, 3, nx)
+    img[6] = 0.0
+    img[6, 1] = 3.0                                       # differs only where no difference looks: no noise either
+    img[8] = 0.0
+    img[8, nx // 2] = 3.0                                 # five differences, three of them non-zero
+    img[7] = rng.normal(-400, 9, nx)                      # negative zero point
+    return img
+
+
+def test_fpack_quantisation_statement(tmp_path):
+    """The oracle's restatement of fits_quantize_float: ZSCALE = noise / q with the noise of a
+    Gaussian row recovered to a few per cent by all three estimators, the zero point a whole
+    number of steps, errors below half a step, unquantisable rows losslessly in the fall-back
+    column -- and the file reads back through blackbox_b200.fitsio."""
+    from blackbox_b200 import fitsio
+    from oracle import rice
+    rng = np.random.default_rng(12)
+    row = rng.normal(300, 12, 10560).astype(np.float32)
+    lo, hi, n2, n3, n5 = rice.fn_noise5_row(row)
+    assert lo == row.min() and hi == row.max()
+    for n in (n2, n3, n5):
+        assert abs(n / 12.0 - 1.0) < 0.05
+    q, scale, zero = rice.fpack_quantize_row(row, 3, 16.0, 77)
+    assert scale == min(n2, n3, n5) / 16.0 and abs(zero / scale - round(zero / scale)) < 1e-9
+    assert np.abs(rice.unquantize_tile(q, 3, scale, zero, 1, 77) - row).max() <= 0.5 * scale * (1 + 1e-6)
+    assert rice.fpack_quantize_row(np.full(100, 3.5, np.float32), 0)[0] is None
+    assert rice.fpack_quantize_row(np.array([1, 2, np.inf] * 10, np.float32), 0)[0] is None
+    # differences of rows shorter than 9 pixels do not exist: no noise, not quantised
+    assert rice.fpack_quantize_row(np.arange(8, dtype=np.float32), 0)[0] is None
+    # d2's median is taken over count(d3) entries of a zero-filled array
+    v = np.zeros(40, np.float32)
+    v[10:30] = rng.normal(0, 1, 20)
+    assert rice.fn_noise5_row(v)[2] <= 1.0483579 * np.median(np.abs(v[12:30] - v[10:28])) + 1e-6
+    img = _float_rows(5, 333)
+    path, back = rice.write_fz_f32(str(tmp_path / 'red.fits.fz'), img, {'S-BKG': 12.5}, zdither0=4321)
+    ci = fitsio.read_compressed(path)
+    assert sorted(ci.fallback) == [1, 6] and np.array_equal(ci.fallback[1], img[1]) and ci.info['zdither0'] == 4321
+    assert (ci.lengths[[1, 6]] == 0).all() and (np.delete(ci.lengths, [1, 6]) > 0).all()
+    heap = np.asarray(ci.heap)
+    for r in range(img.shape[0]):
+        if r in ci.fallback:
+            continue
+        qrow = rice.decode_tile(heap[ci.offsets[r]:ci.offsets[r] + ci.lengths[r]].tobytes(), img.shape[1], 4)
+        qrow = np.asarray(qrow).astype(np.int64).astype(np.int32)
+        assert np.array_equal(rice.unquantize_tile(qrow, r, ci.zscale[r], ci.zzero[r], 1, 4321), back[r])
+        assert np.abs(back[r] - img[r]).max() <= 0.5 * ci.zscale[r] * (1 + 1e-6) + 1e-4
+
+
+def test_write_compressed_float_layout_on_the_host(tmp_path):
+    """fitsio.write_compressed(zbitpix=-32): Rice tiles + ZSCALE / ZZERO columns + gzipped rows,
+    read back by read_compressed and decoded by the oracle."""
+    from blackbox_b200 import fitsio
+    from oracle import rice
+    img = _float_rows(9, 200, nrows=10)
+    tiles, zs, zz, lossless = [], [], [], {}
+    for r in range(img.shape[0]):
+        q, s, z = rice.fpack_quantize_row(img[r], r, 16.0, 55)
+        tiles.append(b'' if q is None else rice.encode_tile(q, 4))
+        zs.append(s)
+        zz.append(z)
+        if q is None:
+            lossless[r] = img[r]
+    with pytest.raises(fitsio.FitsError):
+        fitsio.write_compressed(str(tmp_path / 'bad.fits.fz'), np.frombuffer(b''.join(tiles), np.uint8),
+                                [len(t) for t in tiles], img.shape, -32, zscale=zs, zzero=zz, zdither0=55)
+    path = fitsio.write_compressed(str(tmp_path / 'red.fits.fz'), np.frombuffer(b''.join(tiles), np.uint8),
+                                   [len(t) for t in tiles], img.shape, -32, {'AIRMASS': 1.25}, zscale=zs, zzero=zz,
+                                   zdither0=55, lossless_rows=lossless)
+    ci = fitsio.read_compressed(path)
+    assert ci.info['bitpix'] == -32 and ci.info['quantize'] == 'SUBTRACTIVE_DITHER_1' and ci.info['zdither0'] == 55
+    assert ci.header['AIRMASS'][0] == 1.25 and sorted(ci.fallback) == sorted(lossless)
+    heap = np.asarray(ci.heap)
+    for r in range(img.shape[0]):
+        if r in lossless:
+            assert np.array_equal(ci.fallback[r], img[r])
+            continue
+        qrow = rice.decode_tile(heap[ci.offsets[r]:ci.offsets[r] + ci.lengths[r]].tobytes(), img.shape[1], 4)
+        qrow = np.asarray(qrow).astype(np.int64).astype(np.int32)
+        assert np.abs(rice.unquantize_tile(qrow, r, ci.zscale[r], ci.zzero[r], 1, 55) - img[r]).max() <= 0.5 * zs[r] * (1 + 1e-6) + 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nx,zdither0', [(333, 1), (1000, 9999), (10560, 4242), (9, 17), (8, 3)])
+def test_gpu_fpack_f32_equals_the_oracle(tmp_path, nx, zdither0):
+    """bbx_fpack_f32: ZSCALE / ZZERO bit for bit what the oracle's fits_quantize_float restatement
+    gives, the heap byte for byte the Rice code of its integers; unquantisable rows (constant, a
+    non-finite pixel, fewer than 9 pixels) are left to the lossless column; the file that comes out
+    reads back (on the GPU) to within half a quantisation step."""
+    import torch
+    from blackbox_b200 import fitsio, reduce as bbr
+    from oracle import rice
+    img = _float_rows(31 + nx, nx, nrows=24 if nx < 5000 else 12)
+    if nx > 20:
+        img[9, 5] = np.inf
+        img[10, nx - 1] = np.nan
+    packed = bbr.fpack_f32(torch.from_numpy(img).cuda(), 16.0, zdither0)
+    offs = np.concatenate(([0], np.cumsum(packed['lengths'])[:-1]))
+    for r in range(img.shape[0]):
+        q, s, z = rice.fpack_quantize_row(img[r], r, 16.0, zdither0)
+        assert packed['zscale'][r] == s and packed['zzero'][r] == z, r
+        if q is None:
+            assert packed['lengths'][r] == 0 and np.array_equal(packed['lossless_rows'][r], img[r], equal_nan=True)
+            continue
+        assert packed['heap'][offs[r]:offs[r] + packed['lengths'][r]].tobytes() == rice.encode_tile(q, 4), r
+    assert len(packed['lossless_rows']) >= (2 if nx >= 9 else img.shape[0])
+    path = fitsio.write_compressed(str(tmp_path / 'red.fits.fz'), shape=img.shape, zbitpix=-32,
+                                   header={'RDNOISE': 9.5}, **packed)
+    hdr, back = bbr.read_fits_image(path)
+    back = back.cpu().numpy()
+    assert hdr['RDNOISE'] == 9.5
+    for r in range(img.shape[0]):
+        if r in packed['lossless_rows']:
+            assert np.array_equal(back[r], img[r], equal_nan=True)
+        else:
+            assert np.abs(back[r] - img[r]).max() <= 0.5 * packed['zscale'][r] * (1 + 1e-6) + 1e-4
+
+
+@pytest.mark.gpu
+def test_run_host_writes_the_image_as_fpack_q16(tmp_path, small_bb):
+    """BatchReducer.run_host(img_fz=True): what leaves the device is the reference's disk product
+    (`fpack -q 16 -D -Y`, blackbox.py:836).  Its rows equal the oracle's quantisation of the float32
+    image of the plain path bit for bit, the file reads back to within half a step of a sixteenth of
+    the row noise, and the guessed copy size is topped up when it was short."""
+    import torch
+    from blackbox_b200 import fitsio, reduce as bbr, set_bb, synth
+    from blackbox_b200.pipeline import BatchReducer
+    from oracle import rice
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    shape = (2 * ysc, 8 * set_bb.xsize_chan)
+    mbias, mflat, bpm = synth.make_masters(tel, 53, shape)
+    coeffs = synth.make_xtalk(54)[3]
+    raws = [synth.make_raw(tel, seed, nstars=100, ncosmics=60)[0] for seed in (52, 53, 54, 55, 56, 57)]
+    batch = BatchReducer(tel, raws[0].shape, depth=3, mbias=mbias, mflat=mflat, bpm=bpm, coeffs=coeffs, niter=3)
+    plain_in = [torch.from_numpy(r.view(np.int16)).view(torch.uint16).pin_memory() for r in raws]
+    imgs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in raws]
+    masks = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in raws]
+    want = batch.run_host(plain_in, imgs, masks)
+    nbytes = batch.img_fz_bytes(2.0)
+    fz = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in raws]
+    seeds = [9998 + k for k in range(len(raws))]
+    for rep in range(2):
+        if rep == 1:
+            batch._fz_img_guess = batch.img_fz_bytes(0) + 4096          # far too short: every frame is topped up
+        got = batch.run_host(plain_in, fz, masks, img_fz=True, zdither0=seeds)
+        assert batch.d2h_bytes - sum(m.numel() for m in masks) < sum(i.numel() * 4 for i in imgs) // 2
+        for k in range(len(raws)):
+            p = got[k].img_fz
+            assert p['zdither0'] == 1 + (seeds[k] - 1) % 10000 and got[k].header == want[k].header
+            offs = np.concatenate(([0], np.cumsum(p['lengths'], dtype=np.int64)[:-1]))
+            ref = imgs[k].numpy()
+            for row in (0, 5, shape[0] // 2, shape[0] - 1):
+                q, s, z = rice.fpack_quantize_row(ref[row], row, 16.0, p['zdither0'])
+                assert p['zscale'][row] == s and p['zzero'][row] == z, (rep, k, row)
+                assert p['heap'][offs[row]:offs[row] + p['lengths'][row]].tobytes() == rice.encode_tile(q, 4), (rep, k, row)
+    p = got[3].img_fz
+    path = fitsio.write_compressed(str(tmp_path / 'red.fits.fz'), shape=shape, zbitpix=-32,
+                                   header={k: (v, '') for k, v in got[3].header.items()}, **p)
+    hdr, back = bbr.read_fits_image(path)
+    err = np.abs(back.cpu().numpy() - imgs[3].numpy())
+    assert (err <= 0.5 * p['zscale'][:, None] * (1 + 1e-6) + 1e-3).all()
+    assert os.path.getsize(path) < imgs[3].numel() * 4 // 3
+    assert hdr['NCOSMICS'] == want[3].header['NCOSMICS']

@@ -3,7 +3,8 @@
   * bbx_rice_decode, BYTEPIX 2: a whole fpacked raw frame (10600 tiles of 12000 pixels), the frame
     coded by bbx_rice_encode itself (the tests hold its bytes against the oracle's);
   * bbx_rice_encode, BYTEPIX 1: the 10560^2 mask of a reduced frame (three kernels: code, scan, compact);
-  * bbx_rice_encode, BYTEPIX 2: the raw frame.
+  * bbx_rice_encode, BYTEPIX 2: the raw frame;
+  * bbx_fpack_f32: the reduced float32 image as `fpack -q 16` (row noise, quantisation, Rice code).
 
     python tools/rice_bench.py [--reps 20]
 """
@@ -74,7 +75,24 @@ def main():
     med, mn = timeit(lambda: enc2.enqueue(stored), args.reps, flush)
     print('rice_encode BYTEPIX 2, raw frame: median {:.3f} ms, min {:.3f} ms, input {:.1f} GB/s'.format(
         med, mn, H * W * 2 / med / 1e6))
-    return 0 if ok else 1
+    del enc2, stored
+    # bbx_fpack_f32: the reduced image as `fpack -q 16` (row statistics + quantising Rice coder + scan + compact)
+    img = res.img
+    fenc = bbr.FpackEncoder(shape, img.device, 16.0)
+    got = fenc.parse(fenc.enqueue(img, 4242).cpu().numpy())
+    pinfo = dict(bitpix=-32, shape=shape, blocksize=32, bytepix=4, quantize='SUBTRACTIVE_DITHER_1', zdither0=4242, zblank=None)
+    poffs = np.concatenate(([0], np.cumsum(got['lengths'].astype(np.int64))[:-1]))
+    back = bbr.rice_decode(torch.from_numpy(got['heap'].copy()).cuda(), poffs, got['lengths'].copy(), pinfo,
+                           zscale=got['zscale'].copy(), zzero=got['zzero'].copy())
+    err = (back - img).abs() / torch.from_numpy(got['zscale'].copy()).cuda().float()[:, None]
+    ok2 = bool(got['fits']) and got['skipped'] == 0 and float(err.max()) <= 0.5 + 1e-2
+    print('fpack_f32: fits {}, rows not quantised {}, largest error {:.6f} steps'.format(got['fits'], got['skipped'], float(err.max())))
+    med, mn = timeit(lambda: fenc.enqueue(img, 4242), args.reps, flush)
+    print('fpack_f32 -q 16, image {}x{}: round trip within half a step {}, median {:.3f} ms, min {:.3f} ms; '
+          '{:.1f} MB of heap ({:.3f} bytes per pixel, 1/{:.1f} of the float32 image), median ZSCALE {:.4f}'.format(
+              shape[0], shape[1], ok2, med, mn, got['total'] / 1e6, got['total'] / (shape[0] * shape[1]),
+              4.0 * shape[0] * shape[1] / max(got['total'], 1), float(np.median(got['zscale']))))
+    return 0 if (ok and ok2) else 1
 
 
 if __name__ == '__main__':
