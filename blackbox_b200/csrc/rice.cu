@@ -29,10 +29,11 @@
 //     part, two shifts the FS low bits; "all zero" and "raw" blocks are selects on the same
 //     values; only a code longer than 32 bits (a rare outlier) takes a side path;
 //   * pixels are packed in registers and leave as one 16-byte store per 16 / 8 / 4 pixels.
-// ENCODER.  A warp per tile, a lane per pixel of the 32-pixel block: differences, block sum and FS
-// by shuffles, code lengths by a warp scan, the codes OR-ed into a shared-memory bit buffer,
-// whole words flushed to a fixed-stride scratch row; a scan over the tile sizes and a compaction
-// pass then pack the tiles back to back into the heap (what a FITS binary table wants).
+// ENCODER.  A warp per tile, 1024 pixels at a time, a lane per 32-pixel block: differences, block
+// sum, FS and code lengths in the lane's registers, the bit positions of the 32 blocks by a warp
+// scan, the codes OR-ed into a shared-memory bit buffer, whole words flushed to a fixed-stride
+// scratch row; a scan over the tile sizes and a compaction pass then pack the tiles back to back
+// into the heap (what a FITS binary table wants).
 #include "bbx_common.cuh"
 
 template <int BP> struct RiceP;
@@ -355,9 +356,11 @@ extern "C" int bbx_unquantize(const int32_t *q, int ntiles, int nx, const double
 // = 73 zeros; FS = 0 means S < 2n + n/2 + 1 = 81.  A coded block is therefore at most
 // FSBITS + 32 (FSMAX - 1 + 1) + 80 bits, a raw one FSBITS + 32 BBITS:
 //   BYTEPIX 1: 275 bits (35 B)   BYTEPIX 2: 532 bits (67 B)   BYTEPIX 4: 1029 bits (129 B)
-// plus at most 31 carried bits in front: 34 words.
+// The encoder's bit buffer holds 32 blocks and at most 31 carried bits in front: 1031 words (+ the
+// word put_bits may touch behind its last bit).
 #define RENC_WARPS 4
-#define RENC_WORDS 40
+#define RENC_CHUNK (32 * RICE_BLOCK)    // pixels a warp codes at a time: one block per lane
+#define RENC_WORDS 1034
 __host__ __device__ static inline int rice_block_bytes(int bp) { return bp == 1 ? 35 : bp == 2 ? 67 : 129; }
 
 // OR the `nbits` (1..32) low bits of `value` into a cleared MSB-first bit buffer at bit `pos`
@@ -380,6 +383,7 @@ template <int BP> __device__ __forceinline__ int rice_signed(typename RiceP<BP>:
 // quantised on the fly as fits_quantize_float does (SUBTRACTIVE_DITHER_1; zscale[tile] == 0 marks
 // a row that is not quantised: it gets no Rice-coded bytes) -- the int32 image never exists.
 template <int BP> struct PlainSrc {
+    static constexpr int AHEAD = 16;        // pixel loads of a lane in flight while a chunk is fetched
     const typename RiceP<BP>::T *img;
     int nx;
     const typename RiceP<BP>::T *row;
@@ -388,18 +392,24 @@ template <int BP> struct PlainSrc {
 };
 
 struct QuantSrc {
+    static constexpr int AHEAD = 8;
     const float *img;
     const double *zscale, *zzero;
     const float *rnd;
     int nx, zdither0;
     const float *row;
     double scale, zero;
+    float zero_f, inv_f, guard0;
     int seed, nextrand, base;               // position in the random sequence: R[nextrand + (x - base)]
     __device__ __forceinline__ bool open(int tile, int)
     {
         scale = zscale[tile];
         if (scale == 0.0) return false;
         zero = zzero[tile];
+        const double inv = 1.0 / scale;
+        zero_f = (float)zero;
+        inv_f = (float)inv;
+        guard0 = (float)((fabs(zero) * inv + 8.0) * 1.1920928955078125e-07);      // 2^-23
         row = img + (size_t)tile * nx;
         seed = (int)(((long long)tile + zdither0 - 1) % RICE_NRANDOM);
         if (seed < 0) seed += RICE_NRANDOM;
@@ -415,22 +425,44 @@ struct QuantSrc {
             seed = seed + 1 == RICE_NRANDOM ? 0 : seed + 1;
             nextrand = (int)(rnd[seed] * 500.0f);
         }
-        const double v = ((double)row[x] - zero) / scale + (double)rnd[nextrand + (x - base)] - 0.5;
-        return (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+        // NINT((v - zero) / scale + R - 0.5), evaluated in double by CFITSIO.  Here first in float32:
+        // with Z = |zero| / scale the float value is off by less than (Z + 5 |x| + 3) 2^-24, which can
+        // change the integer only if x sits that close to a half-integer -- the guard is twice that,
+        // and the few pixels inside it (one in some thousands) take the double-precision statement.
+        const float pix = row[x], rr = rnd[nextrand + (x - base)];
+        const float xf = (pix - zero_f) * inv_f + rr - 0.5f;
+        const float g = guard0 + fabsf(xf) * 9.5367431640625e-07f;               // 8 * 2^-23
+        const float yf = xf + 0.5f, ff = yf - floorf(yf);
+        if (ff < g || ff > 1.0f - g) {
+            const double v = ((double)pix - zero) / scale + (double)rr - 0.5;
+            return (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+        }
+        return (xf >= 0.f) ? (int)(xf + 0.5f) : (int)(xf - 0.5f);
     }
 };
 
-// One warp per tile (grid-stride), a lane per pixel of the block.  scratch: ntiles rows of
-// `stride` bytes (16-byte multiples); out_lens[t] = compressed bytes of tile t.
+// One warp per tile (grid-stride).  The warp codes 1024 pixels at a time: first, with the lanes
+// side by side along the row (coalesced loads; QuantSrc quantises here), the pixel values go into
+// shared memory, one 32-pixel block per row of a 33-word-pitch array; then every lane codes ONE
+// block on its own -- differences, block sum, FS and the code lengths in registers -- a warp scan
+// of the 32 block lengths gives every lane its bit position, and the lanes OR their codes into the
+// warp's (cleared) bit buffer; whole words are flushed to a fixed-stride scratch row.  Round 2's
+// first encoder gave a lane one PIXEL of a block: seven warp-wide steps (scan, shuffles, syncs)
+// per 32 pixels, ~170 instructions; this way it is ~30.
+// scratch: ntiles rows of `stride` bytes (16-byte multiples); out_lens[t] = compressed bytes of tile t.
 template <int BP, typename SRC>
-__global__ void __launch_bounds__(RENC_WARPS * 32)
+__global__ void __launch_bounds__(RENC_WARPS * 32, 6)
 rice_encode_kernel(SRC src, int ntiles, int nx, uint8_t *__restrict__ scratch, size_t stride, int *__restrict__ out_lens)
 {
     typedef RiceP<BP> P;
+    __shared__ int svals[RENC_WARPS][32 * 33];
     __shared__ uint32_t sbuf[RENC_WARPS][RENC_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *vals = svals[warp];
     uint32_t *buf = sbuf[warp];
     const unsigned FULL = 0xffffffffu;
+    for (int w = lane; w < RENC_WORDS; w += 32) buf[w] = 0u;       // kept clear from chunk to chunk
+    __syncwarp();
     for (int tile = blockIdx.x * RENC_WARPS + warp; tile < ntiles; tile += gridDim.x * RENC_WARPS) {
         if (!src.open(tile, lane)) {
             if (lane == 0) out_lens[tile] = 0;
@@ -438,88 +470,135 @@ rice_encode_kernel(SRC src, int ntiles, int nx, uint8_t *__restrict__ scratch, s
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (size_t)tile * stride);
         int wpos = 0;                       // whole 32-bit words already written for this tile
-        uint32_t carry;                     // the partly filled word (its top cbits bits are valid)
-        int cbits;
-        int cur = (lane < nx) ? src.px(lane) : 0;
-        const int first = __shfl_sync(FULL, cur, 0);
-        if (BP == 4) {
-            if (lane == 0) dst[0] = __byte_perm((uint32_t)first, 0, 0x0123);
-            wpos = 1; carry = 0; cbits = 0;
-        } else {
-            carry = (uint32_t)first << (32 - P::BBITS); cbits = P::BBITS;
-        }
-        int lastpix = first;
-        for (int i = 0; i < nx; i += RICE_BLOCK) {
-            const int nthis = min(RICE_BLOCK, nx - i);
-            // the next block's pixel is requested before this block is coded
-            const int inext = i + RICE_BLOCK + lane;
-            const int nxt = (inext < nx) ? src.px(inext) : 0;
-            int prev = __shfl_up_sync(FULL, cur, 1);
-            if (lane == 0) prev = lastpix;
-            // difference in the pixel's own width (it wraps), zig-zag mapped
-            int pd = (int)((unsigned)cur - (unsigned)prev);
-            if (BP == 1) pd = (int)(int8_t)pd;
-            if (BP == 2) pd = (int)(int16_t)pd;
-            uint32_t diff = (pd < 0) ? ~((uint32_t)pd << 1) : ((uint32_t)pd << 1);
-            if (lane >= nthis) diff = 0;
-            lastpix = __shfl_sync(FULL, cur, nthis - 1);
-            cur = nxt;
-            if (__ballot_sync(FULL, diff != 0) == 0) {
-                // all differences zero: the code 0 and nothing else
-                cbits += P::FSBITS;
-                if (cbits >= 32) {
-                    if (lane == 0) dst[wpos] = __byte_perm(carry, 0, 0x0123);
-                    wpos++; carry = 0; cbits -= 32;
+        int cbits = 0;                      // bits of the partly filled word, which sits in buf[0]
+        int lastpix = 0;
+        for (int i0 = 0; i0 < nx; i0 += RENC_CHUNK) {
+            // ---- the chunk's pixel values, block k in vals[33 k ..]
+            if (i0 == 0) lastpix = src.px(0);            // the first pixel: block 0 starts with difference 0
+            bool differs = false;
+#pragma unroll SRC::AHEAD
+            for (int k = 0; k < 32; k++) {
+                const int x = i0 + 32 * k + lane;
+                const int v = (x < nx) ? src.px(x) : lastpix;
+                differs |= v != lastpix;
+                vals[k * 33 + lane] = v;
+            }
+            if (i0 == 0) {
+                // the first pixel of the tile as it is
+                if (BP == 4) {
+                    if (lane == 0) dst[0] = __byte_perm((uint32_t)lastpix, 0, 0x0123);
+                    wpos = 1;
+                } else {
+                    if (lane == 0) buf[0] = (uint32_t)lastpix << (32 - P::BBITS);
+                    cbits = P::BBITS;
                 }
-                continue;
-            }
-            // block sum (exact: 32 values below 2^32), FS as fits_rcomp computes it in double
-            unsigned long long sum = diff;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-            double dpsum = ((double)sum - (double)(nthis / 2) - 1.0) / (double)nthis;
-            if (dpsum < 0) dpsum = 0.0;
-            const unsigned long long ip = (unsigned long long)dpsum;
-            uint32_t psum = (BP == 1 ? (uint32_t)(uint8_t)ip : BP == 2 ? (uint32_t)(uint16_t)ip : (uint32_t)ip) >> 1;
-            int fs = 0;
-            while (psum > 0) { psum >>= 1; fs++; }
-            const bool raw = fs >= P::FSMAX;
-            const uint32_t top = raw ? 0u : (diff >> fs);
-            const int len = (lane < nthis) ? (raw ? P::BBITS : (int)top + 1 + fs) : 0;
-            // bit position of this lane's code: carry + FS code + the codes of the lanes before it
-            int pos = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, pos, o);
-                if (lane >= o) pos += t;
-            }
-            const int total = cbits + P::FSBITS + __shfl_sync(FULL, pos, 31);
-            pos = cbits + P::FSBITS + pos - len;
-            buf[lane] = (lane == 0) ? carry : 0u;
-            if (lane + 32 < RENC_WORDS) buf[lane + 32] = 0u;
-            __syncwarp();
-            if (lane == 0) put_bits(buf, cbits, raw ? (uint32_t)(P::FSMAX + 1) : (uint32_t)(fs + 1), P::FSBITS);
-            if (lane < nthis) {
-                // what has to be written of a code: raw -> the BBITS bits of diff; else a one and
-                // the low FS bits, ending at pos + len (the zeros in front are the cleared buffer)
-                if (raw) put_bits(buf, pos, BP == 4 ? diff : (diff & ((1u << (P::BBITS & 31)) - 1u)), P::BBITS);
-                else put_bits(buf, pos + (int)top, (1u << fs) | (diff & ((1u << fs) - 1u)), fs + 1);
             }
             __syncwarp();
+            int total;
+            if (!__any_sync(FULL, differs)) {
+                // a chunk of one value (most of a mask): every block is the code 0, nothing to write
+                const int nblocks = min(32, (nx - i0 + RICE_BLOCK - 1) / RICE_BLOCK);
+                total = cbits + nblocks * P::FSBITS;
+            } else {
+                // ---- lane = block; the differences replace the values in shared memory
+                const int nthis = max(0, min(RICE_BLOCK, nx - (i0 + RICE_BLOCK * lane)));
+                int prev = (lane == 0) ? lastpix : vals[(lane - 1) * 33 + 31];
+                lastpix = vals[31 * 33 + 31];   // (of use only if another chunk follows: then the chunk was full)
+                __syncwarp();
+                int *mine = vals + lane * 33;
+                unsigned long long sum = 0;
+#pragma unroll
+                for (int j = 0; j < RICE_BLOCK; j++) {
+                    const int cur = mine[j];
+                    // difference in the pixel's own width (it wraps), zig-zag mapped
+                    int pd = (int)((unsigned)cur - (unsigned)prev);
+                    if (BP == 1) pd = (int)(int8_t)pd;
+                    if (BP == 2) pd = (int)(int16_t)pd;
+                    uint32_t d = (pd < 0) ? ~((uint32_t)pd << 1) : ((uint32_t)pd << 1);
+                    if (j >= nthis) d = 0;
+                    mine[j] = (int)d;
+                    sum += d;
+                    prev = cur;
+                }
+                int fs = 0, nbits = 0;
+                bool raw = false;
+                if (nthis > 0) {
+                    nbits = P::FSBITS;          // all differences zero: the code 0 and nothing else
+                    if (sum != 0) {
+                        // FS from the block sum, as fits_rcomp computes it in double
+                        // (a full block divides by 32: the same double, by a multiplication)
+                        double dpsum = (double)sum - (double)(nthis / 2) - 1.0;
+                        dpsum = nthis == RICE_BLOCK ? dpsum * (1.0 / RICE_BLOCK) : dpsum / (double)nthis;
+                        if (dpsum < 0) dpsum = 0.0;
+                        const unsigned long long ip = (unsigned long long)dpsum;
+                        const uint32_t psum = (BP == 1 ? (uint32_t)(uint8_t)ip : BP == 2 ? (uint32_t)(uint16_t)ip : (uint32_t)ip) >> 1;
+                        fs = 32 - __clz((int)psum);                  // number of bits of psum
+                        raw = fs >= P::FSMAX;
+                        if (raw) {
+                            nbits += nthis * P::BBITS;
+                        } else {
+                            uint32_t tops = 0;
+#pragma unroll
+                            for (int j = 0; j < RICE_BLOCK; j++) tops += (uint32_t)mine[j] >> fs;
+                            nbits += (int)tops + nthis * (fs + 1);
+                        }
+                    }
+                }
+                // ---- bit position of every block: the carried bits, then the blocks in order
+                int incl = nbits;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                total = cbits + __shfl_sync(FULL, incl, 31);
+                int pos = cbits + incl - nbits;
+                if (nthis > 0 && sum != 0) {
+                    put_bits(buf, pos, raw ? (uint32_t)(P::FSMAX + 1) : (uint32_t)(fs + 1), P::FSBITS);
+                    pos += P::FSBITS;
+                    if (raw) {
+#pragma unroll 8
+                        for (int j = 0; j < nthis; j++) {
+                            const uint32_t d = (uint32_t)mine[j];
+                            put_bits(buf, pos, BP == 4 ? d : (d & ((1u << (P::BBITS & 31)) - 1u)), P::BBITS);
+                            pos += P::BBITS;
+                        }
+                    } else {
+                        // a code = (diff >> FS) zeros (the cleared buffer), a one, the low FS bits
+                        const uint32_t low = (1u << fs) - 1u;
+#pragma unroll 8
+                        for (int j = 0; j < nthis; j++) {
+                            const uint32_t d = (uint32_t)mine[j];
+                            const int top = (int)(d >> fs);
+                            put_bits(buf, pos + top, (1u << fs) | (d & low), fs + 1);
+                            pos += top + fs + 1;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- whole words out, the rest stays in front of the next chunk
             const int nfull = total >> 5;
             for (int w = lane; w < nfull; w += 32) dst[wpos + w] = __byte_perm(buf[w], 0, 0x0123);
+            const uint32_t carry = buf[nfull];
+            __syncwarp();
+            for (int w = lane; w <= nfull + 1; w += 32) buf[w] = 0u;
+            __syncwarp();
+            if (lane == 0) buf[0] = carry;
             wpos += nfull;
-            carry = buf[nfull];
             cbits = total & 31;
             __syncwarp();
         }
         // flush the partly filled word: the stream ends on a byte boundary, zero padded
         const int tail_bytes = (cbits + 7) >> 3;
         if (lane == 0) {
+            const uint32_t carry = buf[0];
             uint8_t *tb = reinterpret_cast<uint8_t *>(dst + wpos);
             for (int b = 0; b < tail_bytes; b++) tb[b] = (uint8_t)(carry >> (24 - 8 * b));
             out_lens[tile] = 4 * wpos + tail_bytes;
+            buf[0] = 0u;
         }
+        __syncwarp();
     }
 }
 
@@ -669,16 +748,80 @@ extern "C" int bbx_rice_encode(const void *img, int ntiles, int nx, int bytepix,
 //   sigma = 0.6052697 med3, replaced by 1.0483579 med2 / 0.1772048 med5 where non-zero and smaller
 //   ZSCALE = sigma / q, ZZERO = trunc(min / ZSCALE + 0.5) ZSCALE  (mid-range if the span needs > 31 bits)
 //   ZSCALE = 0 marks a row that is not quantised: sigma == 0, span > 32 bits, or a non-finite value.
-// fq_row_stats_kernel: one CTA per row, the row in shared memory; the three medians by exact
-// radix select on the float bits (non-negative: the bits order like the values), 11 + 11 + 9
-// bits, three histogram passes for all three at once, the differences recomputed each pass.
+// fq_row_stats_kernel: one CTA per row, the row in shared memory, the differences recomputed in
+// every pass.  The three medians are exact selections: a linear histogram scaled by a 32-value
+// sample finds the bin of the wanted rank, the handful of values in it are ranked directly;
+// rows where that does not work (hundreds of tied values, a misleading sample) take a radix
+// select on the float bits (non-negative: the bits order like the values), 11 + 11 + 9 bits.
 // The quantised values are made inside the Rice encoder (QuantSrc).
 // ---------------------------------------------------------------------------------------------
 #define FQ_THREADS 256
 #define FQ_BINS 2048
 #define FQ_MAX_NX 16384
+#define FQ_CAND 128                     // candidates per array the fast path ranks directly
 
-struct FqSel { unsigned int prefix; unsigned int rank; int use; };
+struct FqSel { unsigned int prefix; unsigned int rank; int use; int bin; unsigned int in_bin; float scale; };
+
+// the three differences around pixel c (v1..v9 = row[c-4 .. c+4]) and whether they count
+__device__ __forceinline__ void fq_diffs(const float *srow, int c, bool &keep2, bool &keep3, float &d2, float &d3, float &d5)
+{
+    const float v1 = srow[c - 4], v3 = srow[c - 2], v4 = srow[c - 1], v5 = srow[c], v6 = srow[c + 1], v7 = srow[c + 2],
+                v9 = srow[c + 4];
+    const bool e567 = (v5 == v6) && (v6 == v7);
+    keep2 = !e567;
+    keep3 = !((v3 == v4) && (v4 == v5) && e567);
+    d2 = fabsf(v5 - v7);
+    float a = 2.0f * v5;
+    a = a - v3;
+    a = a - v7;
+    float b = 6.0f * v5;
+    b = b - 4.0f * v3;
+    b = b - 4.0f * v7;
+    b = b + v1;
+    b = b + v9;
+    d3 = fabsf(a);
+    d5 = fabsf(b);
+}
+
+// monotone in d (d >= 0 or NaN): the bin of the linear histogram
+__device__ __forceinline__ int fq_linear_bin(float d, float scale)
+{
+    const float x = d * scale;
+    return x < (float)(FQ_BINS - 1) ? (int)x : FQ_BINS - 1;       // NaN -> last bin
+}
+
+// Block-wide: the bin of hist[0..FQ_BINS) that holds rank s.rank (if s.use); s.bin = that bin,
+// s.in_bin = its count, s.rank becomes the rank inside the bin.
+__device__ __forceinline__ void fq_find_bin(const unsigned int *hist, FqSel &s, unsigned int *s_scan)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = FQ_BINS / FQ_THREADS;
+    unsigned int mine = 0;
+#pragma unroll
+    for (int i = 0; i < per; i++) mine += hist[tid * per + i];
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    unsigned int before = inc - mine;
+    for (int w = 0; w < warp; w++) before += s_scan[w];
+    const unsigned int k = s.rank;
+    const int use = s.use;
+    __syncthreads();                                    // everybody has read the rank
+    if (use && k >= before && k < before + mine) {
+        unsigned int acc = before;
+        int b = tid * per;
+        for (; b < tid * per + per - 1; b++) { if (acc + hist[b] > k) break; acc += hist[b]; }
+        s.bin = b;
+        s.in_bin = hist[b];
+        s.rank = k - acc;
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(FQ_THREADS)
 fq_row_stats_kernel(const float *__restrict__ img, int ntiles, int nx, float qlevel, double *__restrict__ zscale,
@@ -688,19 +831,23 @@ fq_row_stats_kernel(const float *__restrict__ img, int ntiles, int nx, float qle
     unsigned int (*hist)[FQ_BINS] = reinterpret_cast<unsigned int (*)[FQ_BINS]>(fq_smem);
     float *srow = reinterpret_cast<float *>(fq_smem + 3 * FQ_BINS * sizeof(unsigned int));
     __shared__ float s_lo[FQ_THREADS / 32], s_hi[FQ_THREADS / 32];
-    __shared__ unsigned int s_cnt[3][FQ_THREADS / 32];
+    __shared__ unsigned int s_cnt[2][FQ_THREADS / 32];
     __shared__ unsigned int s_scan[FQ_THREADS / 32];
     __shared__ FqSel sel[3];
-    __shared__ int s_bad;
+    __shared__ unsigned int cand[3][FQ_CAND];
+    __shared__ unsigned int ncand[3];
+    __shared__ int s_bad, s_slow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
 
+    for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const float *row = img + (size_t)tile * nx;
         // ---- the row, its range, non-finite values
         float lo = INFINITY, hi = -INFINITY;
         int bad = 0;
-        if (tid == 0) s_bad = 0;
+        if (tid == 0) { s_bad = 0; s_slow = 0; }
+        if (tid < 3) ncand[tid] = 0;
         if ((nx & 3) == 0 && ((uintptr_t)row & 15) == 0) {
             const float4 *r4 = reinterpret_cast<const float4 *>(row);
             for (int i = tid; i < nx / 4; i += FQ_THREADS) {
@@ -718,13 +865,12 @@ fq_row_stats_kernel(const float *__restrict__ img, int ntiles, int nx, float qle
                 bad |= !isfinite(v);
             }
         }
-        for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = fminf(lo, __shfl_xor_sync(FULL, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
         }
-        __syncthreads();                                   // s_bad = 0, histograms cleared, row stored
+        __syncthreads();                                   // flags reset, row stored
         if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
         if (bad) s_bad = 1;
         __syncthreads();
@@ -732,86 +878,123 @@ fq_row_stats_kernel(const float *__restrict__ img, int ntiles, int nx, float qle
 #pragma unroll
         for (int w = 1; w < FQ_THREADS / 32; w++) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
         const bool unusable = s_bad != 0 || nx < 9;
-        // ---- three passes: histogram of the next key bits of the values still in the running
-        for (int level = 0; level < 3 && !unusable; level++) {
-            const int shift = level == 0 ? 20 : level == 1 ? 9 : 0;
-            const int pshift = level == 1 ? 20 : 9;        // bits fixed so far = key >> pshift
-            const unsigned int mask = level == 2 ? 0x1ffu : 0x7ffu;
-            unsigned int n2 = 0, n3 = 0;
-            unsigned int p2 = 0, p3 = 0, p5 = 0;
-            if (level > 0) { p2 = sel[0].prefix; p3 = sel[1].prefix; p5 = sel[2].prefix; }
-            for (int c = 4 + tid; c < nx - 4; c += FQ_THREADS) {
-                const float v1 = srow[c - 4], v3 = srow[c - 2], v4 = srow[c - 1], v5 = srow[c], v6 = srow[c + 1],
-                            v7 = srow[c + 2], v9 = srow[c + 4];
-                const bool e567 = (v5 == v6) && (v6 == v7);
-                const bool keep3 = !((v3 == v4) && (v4 == v5) && e567);
-                if (!e567) {
-                    const unsigned int k = __float_as_uint(fabsf(v5 - v7));
-                    n2++;
-                    if (level == 0 || (k >> pshift) == p2) atomicAdd(&hist[0][(k >> shift) & mask], 1u);
+        const int nd = nx - 8;                             // centres c = 4 .. nx - 5
+
+        if (!unusable) {
+            // ---- a first look: 32 differences spread over the row give the scale of a LINEAR
+            // histogram (its bins hold a handful of values each; the float bits of a noise-like
+            // quantity would pile thousands of values onto a few exponent bins and the
+            // shared-memory atomics would queue up behind each other)
+            if (warp == 0) {
+                const int c = 4 + (int)(((long long)(2 * lane + 1) * nd) / 64);
+                bool k2, k3;
+                float d[3];
+                fq_diffs(srow, c, k2, k3, d[0], d[1], d[2]);
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    int rank = 0;
+                    for (int j = 0; j < 32; j++) {
+                        const float o = __shfl_sync(FULL, d[a], j);
+                        rank += (o < d[a]) || (o == d[a] && j < lane);
+                    }
+                    const unsigned int who = __ballot_sync(FULL, rank == 16);
+                    const float med = __shfl_sync(FULL, d[a], who ? __ffs(who) - 1 : 0);
+                    // four sample medians span the histogram; no usable sample -> the slow path
+                    const float sc = (float)(FQ_BINS - 1) / (4.0f * med);
+                    if (lane == 0) sel[a].scale = (who && med > 0.f && isfinite(sc)) ? sc : 0.f;
                 }
-                if (keep3) {
-                    float a = 2.0f * v5;
-                    a = a - v3;
-                    a = a - v7;
-                    float b = 6.0f * v5;
-                    b = b - 4.0f * v3;
-                    b = b - 4.0f * v7;
-                    b = b + v1;
-                    b = b + v9;
-                    const unsigned int k3 = __float_as_uint(fabsf(a)), k5 = __float_as_uint(fabsf(b));
-                    n3++;
-                    if (level == 0 || (k3 >> pshift) == p3) atomicAdd(&hist[1][(k3 >> shift) & mask], 1u);
-                    if (level == 0 || (k5 >> pshift) == p5) atomicAdd(&hist[2][(k5 >> shift) & mask], 1u);
-                }
-            }
-            if (level == 0) {
-                // the ranks asked for: m = count(d3); d2 sits in a zero-filled array of m entries
-                n2 = __reduce_add_sync(FULL, n2);
-                n3 = __reduce_add_sync(FULL, n3);
-                if (lane == 0) { s_cnt[0][warp] = n2; s_cnt[1][warp] = n3; }
             }
             __syncthreads();
-            if (level == 0 && tid == 0) {
+            const float sc2 = sel[0].scale, sc3 = sel[1].scale, sc5 = sel[2].scale;
+            unsigned int n2 = 0, n3 = 0;
+            for (int c = 4 + tid; c < nx - 4; c += FQ_THREADS) {
+                bool k2, k3;
+                float d2, d3, d5;
+                fq_diffs(srow, c, k2, k3, d2, d3, d5);
+                if (k2) { n2++; atomicAdd(&hist[0][fq_linear_bin(d2, sc2)], 1u); }
+                if (k3) {
+                    n3++;
+                    atomicAdd(&hist[1][fq_linear_bin(d3, sc3)], 1u);
+                    atomicAdd(&hist[2][fq_linear_bin(d5, sc5)], 1u);
+                }
+            }
+            n2 = __reduce_add_sync(FULL, n2);
+            n3 = __reduce_add_sync(FULL, n3);
+            if (lane == 0) { s_cnt[0][warp] = n2; s_cnt[1][warp] = n3; }
+            __syncthreads();
+            if (tid == 0) {
+                // the ranks asked for: m = count(d3); d2 sits in a zero-filled array of m entries
                 unsigned int m2 = 0, m = 0;
                 for (int w = 0; w < FQ_THREADS / 32; w++) { m2 += s_cnt[0][w]; m += s_cnt[1][w]; }
                 const unsigned int r = m ? (m - 1) / 2 : 0, nz = m - m2;
-                sel[1].prefix = 0; sel[1].rank = r; sel[1].use = m > 0;
-                sel[2].prefix = 0; sel[2].rank = r; sel[2].use = m > 0;
-                sel[0].prefix = 0;
+                sel[1].rank = r; sel[1].use = m > 0;
+                sel[2].rank = r; sel[2].use = m > 0;
                 sel[0].use = (m == 1 ? m2 == 1 : m2 > 1) && r >= nz;
                 sel[0].rank = r >= nz ? r - nz : 0;
+                s_cnt[0][0] = sel[0].rank; s_cnt[0][1] = r;          // kept for the slow path
             }
             __syncthreads();
-            // find, per array, the bin that holds the rank; move the rank into the bin
-            for (int a = 0; a < 3; a++) {
-                const int per = FQ_BINS / FQ_THREADS;
-                unsigned int mine = 0;
-#pragma unroll
-                for (int i = 0; i < per; i++) mine += hist[a][tid * per + i];
-                unsigned int inc = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(FULL, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                if (lane == 31) s_scan[warp] = inc;
-                __syncthreads();
-                unsigned int before = inc - mine;
-                for (int w = 0; w < warp; w++) before += s_scan[w];
-                const unsigned int k = sel[a].rank;
-                __syncthreads();                            // everybody has read the rank
-                if (sel[a].use && k >= before && k < before + mine) {
-                    unsigned int acc = before;
-                    int b = tid * per;
-                    for (; b < tid * per + per - 1; b++) { if (acc + hist[a][b] > k) break; acc += hist[a][b]; }
-                    sel[a].prefix = (sel[a].prefix << (level == 2 ? 9 : 11)) | (unsigned int)b;
-                    sel[a].rank = k - acc;
-                }
-                __syncthreads();
-            }
+            for (int a = 0; a < 3; a++) fq_find_bin(hist[a], sel[a], s_scan);
             for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
+            if (tid < 3 && sel[tid].use &&
+                (sel[tid].scale == 0.f || sel[tid].bin == FQ_BINS - 1 || sel[tid].in_bin > FQ_CAND)) s_slow = 1;
             __syncthreads();
+            if (!s_slow) {
+                // ---- the few values of the three bins, ranked directly
+                const int b2 = sel[0].use ? sel[0].bin : -1, b3 = sel[1].use ? sel[1].bin : -1,
+                          b5 = sel[2].use ? sel[2].bin : -1;
+                for (int c = 4 + tid; c < nx - 4; c += FQ_THREADS) {
+                    bool k2, k3;
+                    float d2, d3, d5;
+                    fq_diffs(srow, c, k2, k3, d2, d3, d5);
+                    if (k2 && fq_linear_bin(d2, sc2) == b2) cand[0][atomicAdd(&ncand[0], 1u)] = __float_as_uint(d2);
+                    if (k3 && fq_linear_bin(d3, sc3) == b3) cand[1][atomicAdd(&ncand[1], 1u)] = __float_as_uint(d3);
+                    if (k3 && fq_linear_bin(d5, sc5) == b5) cand[2][atomicAdd(&ncand[2], 1u)] = __float_as_uint(d5);
+                }
+                __syncthreads();
+                for (int a = 0; a < 3; a++) {
+                    const unsigned int n = ncand[a];
+                    if (!sel[a].use || (unsigned int)tid >= n) continue;
+                    const unsigned int mine = cand[a][tid];
+                    unsigned int rank = 0;
+                    for (unsigned int j = 0; j < n; j++) {
+                        const unsigned int o = cand[a][j];
+                        rank += (o < mine) || (o == mine && j < (unsigned int)tid);
+                    }
+                    if (rank == sel[a].rank) sel[a].prefix = mine;
+                }
+                __syncthreads();
+            } else {
+                // ---- the slow path (ties by the hundred, or a sample that misled): exact radix
+                // select on the float bits, 11 + 11 + 9 bits, the differences recomputed each pass
+                if (tid == 0) {
+                    sel[0].rank = s_cnt[0][0]; sel[1].rank = s_cnt[0][1]; sel[2].rank = s_cnt[0][1];
+                    sel[0].prefix = sel[1].prefix = sel[2].prefix = 0;
+                }
+                __syncthreads();
+                for (int level = 0; level < 3; level++) {
+                    const int shift = level == 0 ? 20 : level == 1 ? 9 : 0;
+                    const int pshift = level == 1 ? 20 : 9;        // bits fixed so far = key >> pshift
+                    const unsigned int mask = level == 2 ? 0x1ffu : 0x7ffu;
+                    const unsigned int p2 = sel[0].prefix, p3 = sel[1].prefix, p5 = sel[2].prefix;
+                    for (int c = 4 + tid; c < nx - 4; c += FQ_THREADS) {
+                        bool k2, k3;
+                        float d2, d3, d5;
+                        fq_diffs(srow, c, k2, k3, d2, d3, d5);
+                        const unsigned int q2 = __float_as_uint(d2), q3 = __float_as_uint(d3), q5 = __float_as_uint(d5);
+                        if (k2 && (level == 0 || (q2 >> pshift) == p2)) atomicAdd(&hist[0][(q2 >> shift) & mask], 1u);
+                        if (k3 && (level == 0 || (q3 >> pshift) == p3)) atomicAdd(&hist[1][(q3 >> shift) & mask], 1u);
+                        if (k3 && (level == 0 || (q5 >> pshift) == p5)) atomicAdd(&hist[2][(q5 >> shift) & mask], 1u);
+                    }
+                    __syncthreads();
+                    for (int a = 0; a < 3; a++) {
+                        fq_find_bin(hist[a], sel[a], s_scan);
+                        if (tid == 0 && sel[a].use) sel[a].prefix = (sel[a].prefix << (level == 2 ? 9 : 11)) | (unsigned int)sel[a].bin;
+                    }
+                    for (int i = tid; i < 3 * FQ_BINS; i += FQ_THREADS) (&hist[0][0])[i] = 0u;
+                    __syncthreads();
+                }
+            }
         }
         if (tid == 0) {
             double delta = 0.0, zero = 0.0;
@@ -893,7 +1076,7 @@ extern "C" int bbx_fpack_f32(const float *img, int ntiles, int nx, float qlevel,
     BBX_CHECK_LAUNCH("fq_row_stats_kernel");
     const int want = (ntiles + RENC_WARPS - 1) / RENC_WARPS;
     const int blocks = want < BBX_SM_COUNT * 16 ? want : BBX_SM_COUNT * 16;
-    QuantSrc src = {img, zscale, zzero, rand10000, nx, zdither0, nullptr, 0.0, 0.0, 0, 0, 0};
+    QuantSrc src = {img, zscale, zzero, rand10000, nx, zdither0, nullptr, 0.0, 0.0, 0.f, 0.f, 0.f, 0, 0, 0};
     rice_encode_kernel<4><<<blocks, RENC_WARPS * 32, 0, st>>>(src, ntiles, nx, scratch, stride, lens);
     BBX_CHECK_LAUNCH("rice_encode_kernel(quantised)");
     rice_scan_kernel<<<1, 1024, 0, st>>>(lens, ntiles, offs, hdr, heap_cap, nskipped);

@@ -572,11 +572,13 @@ class BatchReducer:
             self._fz_in = [dict(heap=torch.empty(cap, dtype=torch.uint8, device=dev),
                                 desc=torch.empty(12 * geom.H, dtype=torch.uint8, device=dev),
                                 status=torch.zeros(1, dtype=torch.int32, device=dev),
-                                status_host=torch.zeros(1, dtype=torch.int32).pin_memory()) for _ in range(d)]
+                                status_host=torch.zeros(1, dtype=torch.int32).pin_memory(),
+                                decoded=torch.cuda.Event()) for _ in range(d)]
         if mask_fz:
             want = host_masks[0].numel()
             if self._fz_out is None or self._fz_out[0].out_bytes != want:
                 self._fz_out = [R.RiceEncoder((RH, RW), 1, dev, out_bytes=want) for _ in range(d)]
+                self._fz_mask_guess = want
             for m in host_masks:
                 if m.dtype != torch.uint8 or m.numel() != want or want < self.mask_fz_bytes(0) + 16:
                     raise ValueError('mask_fz: host mask buffers must be equal-sized pinned uint8 buffers of at '
@@ -594,7 +596,7 @@ class BatchReducer:
                                      'least img_fz_bytes(0) + 16 bytes')
             if zdither0 is not None and len(zdither0) != n:
                 raise ValueError('{} dither seeds for {} frames'.format(len(zdither0), n))
-        copied = [0] * n
+        copied, copied_m = [0] * n, [0] * n
         self.d2h_bytes = 0
         for j, p in enumerate(self.pipes):
             p.mask_encoder = self._fz_out[j] if mask_fz else None
@@ -618,11 +620,13 @@ class BatchReducer:
                 else:
                     nb = self._hbuf[j][1].numel() * 4
                     host_imgs[k % ni].copy_(self._hbuf[j][1], non_blocking=True)
-                if mask_fz:
-                    host_masks[k % nm].copy_(self._fz_out[j].out, non_blocking=True)     # coded at the end of stage B
+                if mask_fz:                              # coded at the end of stage B; sized like the image's copy
+                    nmb = copied_m[k] = min(host_masks[0].numel(), self._fz_mask_guess)
+                    host_masks[k % nm][:nmb].copy_(self._fz_out[j].out[:nmb], non_blocking=True)
                 else:
+                    nmb = host_masks[k % nm].numel()
                     host_masks[k % nm].copy_(self._hbuf[j][2], non_blocking=True)
-                self.d2h_bytes += nb + host_masks[k % nm].numel()
+                self.d2h_bytes += nb + nmb
                 self._ev_out[j].record()
 
         def retire(k):
@@ -639,13 +643,22 @@ class BatchReducer:
                 raise ValueError('frame {}: corrupt Rice-coded tile(s) in the compressed raw frame (status {})'.format(
                     k, int(self._fz_in[j]['status_host'][0])))
             if mask_fz:
-                enc = self._fz_out[j]
-                total, lens, heap, fits_in = enc.parse(host_masks[k % nm])
-                if not fits_in:                          # rare: a mask that hardly compresses
+                enc, host = self._fz_out[j], host_masks[k % nm]
+                total, lens, heap, fits_in = enc.parse(host[:copied_m[k]])
+                if not fits_in:
+                    need = enc.heap_offset + total
                     with torch.cuda.stream(self._s_out):
-                        big = R.RiceEncoder((RH, RW), 1, dev)
-                        host = big.enqueue(self._hbuf[j][2]).cpu()
-                    total, lens, heap, _ = big.parse(host)
+                        if need <= host.numel():         # the guess was short: the rest of the heap
+                            host[copied_m[k]:need].copy_(enc.out[copied_m[k]:need], non_blocking=True)
+                            self.d2h_bytes += need - copied_m[k]
+                            view = host[:need]
+                        else:                            # rare: a mask that hardly compresses
+                            enc = R.RiceEncoder((RH, RW), 1, dev)
+                            view = enc.enqueue(self._hbuf[j][2]).cpu()
+                            self.d2h_bytes += view.numel()
+                    self._s_out.synchronize()
+                    total, lens, heap, _ = enc.parse(view)
+                self._fz_mask_guess = min(host.numel(), (enc.heap_offset + int(total * 1.25) + (1 << 18)) // 4096 * 4096)
                 results[k].mask_fz = (heap, lens)
             if img_fz:
                 enc, host = self._fz_img[j], host_imgs[k % ni]
@@ -677,26 +690,37 @@ class BatchReducer:
             j = k % d
             if k >= d:
                 retire(k - d)
-            with torch.cuda.stream(self._s_in):
-                src = host_raws[k]
-                if packed[k]:
-                    fz = self._fz_in[j]
-                    nheap = src.heap.numel()
-                    if nheap > fz['heap'].numel():
-                        raise ValueError('frame {}: compressed heap of {} bytes is larger than the frame'.format(k, nheap))
+            src = host_raws[k]
+            if packed[k]:
+                # the copy stream only copies (frame after frame); the decoder runs on the slot's own
+                # stage-A stream, next to the copies and decoders of the other frames
+                fz = self._fz_in[j]
+                nheap = src.heap.numel()
+                if nheap > fz['heap'].numel():
+                    raise ValueError('frame {}: compressed heap of {} bytes is larger than the frame'.format(k, nheap))
+                if src.fallback:
+                    raise ValueError('frame {}: {} tile(s) of the raw frame are not Rice-coded'.format(k, len(src.fallback)))
+                with torch.cuda.stream(self._s_in):
+                    self._s_in.wait_event(fz['decoded'])      # the decoder of frame k-d has read the heap buffer
                     fz['heap'][:nheap].copy_(src.heap, non_blocking=True)
                     fz['desc'].copy_(src.descriptors(), non_blocking=True)
-                    self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
+                    self._ev_in[j].record()
+                with torch.cuda.stream(self.hi_streams[j]):
+                    self.hi_streams[j].wait_event(self._ev_in[j])
+                    self.hi_streams[j].wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
                     call('bbx_rice_decode', R._ptr(fz['heap']), nheap, R._ptr(fz['desc']),
                          R._ptr(fz['desc'][8 * geom.H:]), geom.H, geom.W, int(src.info.get('blocksize', 32)), 2, 1,
                          R._ptr(self._hbuf[j][0]), R._ptr(fz['status']), R._stream())
+                    fz['decoded'].record()
                     fz['status_host'].copy_(fz['status'], non_blocking=True)
-                else:
-                    self._s_in.wait_stream(self.streams[j])   # stage B of frame k-d has read the raw buffer
-                    self._hbuf[j][0].copy_(src if src.dtype == raw_dt else src.view(raw_dt), non_blocking=True)
-                    if fits:
-                        raw = self._hbuf[j][0]
-                        call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
+                    self.pipes[j].stage_a_enqueue(self._hbuf[j][0])
+                return
+            with torch.cuda.stream(self._s_in):
+                self._s_in.wait_stream(self.streams[j])       # stage B of frame k-d has read the raw buffer
+                self._hbuf[j][0].copy_(src if src.dtype == raw_dt else src.view(raw_dt), non_blocking=True)
+                if fits:
+                    raw = self._hbuf[j][0]
+                    call('bbx_fits_decode', R._ptr(raw), 16, 1, raw.numel(), R._ptr(raw), R._stream())
                 self._ev_in[j].record()
             with torch.cuda.stream(self.hi_streams[j]):
                 self.hi_streams[j].wait_event(self._ev_in[j])

@@ -48,6 +48,20 @@ def analyse(path, frames):
         depth += d
         last = t
     streams = sorted(set(e['args'].get('stream') for e in kern))
+    kp = sorted([(e['ts'], 1) for e in kern if e.get('cat') == 'kernel'] +
+                [(e['ts'] + e['dur'], -1) for e in kern if e.get('cat') == 'kernel'])
+    kbusy, depth_k, last_k = 0.0, 0, kp[0][0]
+    for t, d in kp:
+        if depth_k >= 1:
+            kbusy += t - last_k
+        depth_k += d
+        last_k = t
+    print('kernels alone (copies left out): busy %.3f ms (%.1f%% of the wall time)' % (kbusy / 1e3, 100 * kbusy / (t1 - t0)))
+    for cat, what in (('gpu_memcpy', 'copies'),):
+        cp = [e for e in kern if e.get('cat') == cat]
+        for kind in sorted(set(e['name'] for e in cp)):
+            sel = [e for e in cp if e['name'] == kind]
+            print('   %-28s %4d, %.3f ms per frame' % (kind, len(sel), sum(e['dur'] for e in sel) / 1e3 / frames))
     print('frames %d  wall %.3f ms (%.3f ms/frame)  busy %.3f ms (%.1f%%)  >=2 kernels resident %.3f ms (%.1f%%)' % (
         frames, (t1 - t0) / 1e3, (t1 - t0) / 1e3 / frames, busy / 1e3, 100 * busy / (t1 - t0), over / 1e3,
         100 * over / (t1 - t0)))
@@ -71,7 +85,7 @@ def analyse(path, frames):
         tot[name] = tot.get(name, 0.0) + e['dur']
         alone[name] = alone.get(name, 0.0) + sum(bounds[i + 1] - bounds[i] for i in range(a, b) if cover[i] == 1)
     print('%-46s %10s %10s   (us per frame)' % ('kernel', 'device', 'alone'))
-    for name in sorted(tot, key=lambda n: -alone[n])[:28]:
+    for name in sorted(tot, key=lambda n: -alone[n])[:34]:
         print('%-46s %10.1f %10.1f' % (name, tot[name] / frames, alone[name] / frames))
     print('%-46s %10.1f %10.1f' % ('TOTAL', sum(tot.values()) / frames, sum(alone.values()) / frames))
     if rt:
@@ -83,6 +97,36 @@ def analyse(path, frames):
             (h1 - h0) / 1e3, len(launch), sum(e['dur'] for e in launch) / 1e3, len(sync), sum(e['dur'] for e in sync) / 1e3))
 
 
+def main_host(args):
+    import numpy as np
+    from blackbox_b200 import fitsio
+    tel = args.tel
+    raws = [R._to_dev(synth.make_raw(tel, 4001 + k)[0]) for k in range(4)]
+    red = (2 * set_bb.ysize_chan, 8 * set_bb.xsize_chan)
+    mbias, mflat, bpm = synth.make_masters(tel, 9, red)
+    batch = BatchReducer(tel, tuple(raws[0].shape), depth=args.depth, ahead=args.ahead, mbias=mbias, mflat=mflat, bpm=bpm,
+                         coeffs=synth.make_xtalk(3)[3], niter=4, use_graphs=bool(args.graphs))
+    ring = []
+    for r in raws:
+        heap, lens = R.rice_encode(r)
+        offs = np.concatenate(([0], np.cumsum(lens.astype(np.int64))[:-1]))
+        info = dict(shape=tuple(r.shape), bitpix=16, bytepix=2, bzero=32768.0, bscale=1.0, blocksize=32)
+        ring.append(fitsio.CompressedImage({}, torch.from_numpy(heap).pin_memory(), offs, lens.astype(np.int32), info))
+        ring[-1].descriptors()
+    host_img = [torch.empty(batch.img_fz_bytes(), dtype=torch.uint8).pin_memory() for _ in range(args.depth)]
+    host_mask = [torch.empty(batch.mask_fz_bytes(), dtype=torch.uint8).pin_memory() for _ in range(args.depth)]
+    host_raw = [ring[k % len(ring)] for k in range(args.frames)]
+    for _ in range(2):
+        batch.run_host(host_raw, host_img, host_mask, mask_fz=True, img_fz=True)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        batch.run_host(host_raw, host_img, host_mask, mask_fz=True, img_fz=True)
+        torch.cuda.synchronize()
+    os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
+    prof.export_chrome_trace(args.out)
+    analyse(args.out, args.frames)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=8)
@@ -92,7 +136,11 @@ def main():
     ap.add_argument('--graphs', type=int, default=0)
     ap.add_argument('--split-priority', type=int, default=1)
     ap.add_argument('--out', default='gpurun_out/trace.json')
+    ap.add_argument('--host', type=int, default=0,
+                    help='1: run_host with fpacked raw frames in, fpack -q 16 image + Rice-coded mask out')
     args = ap.parse_args()
+    if args.host:
+        return main_host(args)
     tel = args.tel
     raw = synth.make_raw(tel, 4001)[0]
     red = (2 * set_bb.ysize_chan, 8 * set_bb.xsize_chan)
