@@ -8,18 +8,21 @@ A step = one pass of the full chain (gain + overscan + master bias + mask_init +
 LACosmic with 4 iterations + crosstalk; blackbox.py:1479-1902) over a night batch of synthetic
 10600x12000 uint16 raw BlackGEM frames: `--batch` (64, BASELINE.json config 4) frames per GPU,
 resident in HBM (16.3 GB).  Weak scaling: frames are independent, frame k -> GPU k mod N, no
-collective on the data path.  Per GPU `--depth` (4) frames are in flight, the overscan stage
-`--ahead` (2) frames in front on a high-priority stream, stages replayed as CUDA graphs.
+collective on the data path.  Per GPU `--depth` (12) frames are in flight, the overscan stage
+`--ahead` (4) frames in front on a high-priority stream, stages replayed as CUDA graphs.
 `--impl reference`: the CPU arm (the oracle port of the reference path on all host cores, bounded
 sample per step) as a run of its own, rank 0 only.
 
 Printed JSON (rank 0, one line):
   value      frames/s over all GPUs, raw frames already resident in HBM
   e2e        frames/s through the public API (BatchReducer.run_host) with HOST buffers on both
-             sides, H2D / D2H copies inside the timed region: the fpacked raw frame in (as the
-             telescope delivers it; Rice-decoded on the device), the float32 image and the Rice-coded
-             mask (the reference's fpack -D -Y product) out.  e2e_uncompressed: plain uint16 frame in,
-             image + plain mask out (round 1's definition), fewer steps
+             sides, H2D / D2H copies inside the timed region, the reference's own files on both
+             sides: the fpacked raw frame in (as the telescope delivers it; Rice-decoded on the
+             device); out the reduced image as `fpack -q 16 -D -Y` writes it (blackbox.py:836:
+             quantised + Rice-coded on the device, bbx_fpack_f32) and the mask as `fpack -D -Y`.
+             e2e_f32_image: the same with the float32 image leaving as it is (446 MB per frame);
+             e2e_uncompressed: plain uint16 frame in, image + plain mask out (round 1's definition);
+             both over fewer steps
   roofline   the dominant single kernel of the chain (largest mean device time among the
              one-kernel stages, CUDA events on the launching stream INSIDE the timed region) against
              the measured HBM peak; roofline_stages lists every stage the same way
@@ -64,9 +67,9 @@ STAGES = {
     'overscan': ('vos_rowstats, vos_fit, hos_satcount, hos_stats, vos_std, hos_fit, satlevels (S1)', 60e6, False),
     'apply': ('reduce_apply_strip_kernel<uint16> (S2: raw u16 + mbias + mflat + bpm -> img f32 + mask u8)', 1815.6e6, True),
     'mask_morph': ('ms_* / hole_* / ccl kernels (S3)', 223e6, False),
-    'lacosmic': ('sp_scan + sparse candidate / grow / clean kernels, %d iterations (S4)' % NITER, NITER * 1115.1e6, False),
+    'lacosmic': ('sp_scan (Laplacian of iteration 1) + sparse candidate / grow / clean kernels on work lists, %d iterations (S4)' % NITER, NITER * 1115.1e6, False),
     'lacosmic_finish': ('cosmic-ray bit + NCOSMICS from the CR list', None, False),
-    'xtalk': ('xtalk_tile_kernel + mask_counts_kernel (S5: img r+w + mask r; M-*NUM counts: mask r)', 1003.6e6 + 111.5e6, False),
+    'xtalk': ('xtalk_tile_kernel, the M-*NUM counts of the mask taken on the way + xtalk_count_sum (S5: img r+w + mask r)', 1003.6e6, False),
     'edge_fill': ('cs_hist x3 + cs_find x3 + cs_fill_edge (3 x img r + mask r)', 3 * 446.1e6 + 111.5e6, False),
 }
 
@@ -79,8 +82,8 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=64,
                     help='frames per GPU per step (BASELINE.json config 4: a night batch of 64 frames)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--depth', type=int, default=4, help='frames in flight per GPU')
-    ap.add_argument('--ahead', type=int, default=2, help='frames the overscan stage runs ahead')
+    ap.add_argument('--depth', type=int, default=12, help='frames in flight per GPU')
+    ap.add_argument('--ahead', type=int, default=4, help='frames the overscan stage runs ahead')
     ap.add_argument('--split-priority', type=int, default=1,
                     help='1: overscan stage on a high-priority stream of its own')
     ap.add_argument('--graphs', type=int, default=1, help='1: replay the stages as CUDA graphs')
@@ -328,8 +331,10 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- roofline: one LACosmic iteration, timed with CUDA events on the launching stream ---
     roof = stages = None
+    alone = measure_kernel_alone(batch, raws, out_imgs, out_masks) if rank == 0 else None
+    barrier()
     if rank == 0:
-        roof, stages = stage_rooflines(batch.pipes)
+        roof, stages = stage_rooflines(batch.pipes, alone)
     for p in batch.pipes:
         p.enable_stage_timing(False)
 
@@ -585,11 +590,36 @@ def measure_link(dev):
 
 def pipe_launches(tel, niter):
     """Kernels of libbbx.so launched per frame by FramePipeline (memsets and copies not counted;
-    cross-checked against the ncu launch list under profiles/): overscan 6 (+1 BlackGEM
-    saturated-column count) + header means 1, fused apply 1, sparse mask morphology 11, LACosmic
-    2 (begin) + 9 (first iteration) + 8 per further iteration, cosmic-ray bit + object count 3,
-    crosstalk 1, per-bit mask counts 1."""
-    return 6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 11 + 2 + 9 + 8 * max(niter - 1, 0) + 3 + 1 + 1
+    equal to the ncu launch list profiles/r02_launches_bench.csv, 66 per BlackGEM frame at niter 4):
+    overscan 6 (+1 BlackGEM saturated-column count) + header means 1, fused per-pixel pass 1,
+    LACosmic set-up 3 (init, background gather + sample), sparse mask morphology 12, Laplacian scan +
+    background rank 2, per iteration 7 (two candidate, three growth kernels, flag clean-up, control)
+    + 1 cleaning pass, + 1 rescan per further iteration, cosmic-ray bit + object count 3, crosstalk
+    with the per-bit mask counts 2."""
+    return (6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 3 + 12 + 2 + 8 * niter + max(niter - 1, 0) + 3 + 2) if niter > 0 \
+        else (6 + (0 if tel.startswith('ML') else 1) + 1 + 1 + 12 + 2)
+
+
+def measure_kernel_alone(batch, raws, out_imgs, out_masks):
+    """The fused per-pixel kernel on its own: one launch per frame of the resident batch, back to
+    back on one stream with nothing else on the GPU, every launch between its own pair of CUDA
+    events on that stream.  Inputs larger than L2 (each launch reads another 254 MB frame and the
+    1 GB of masters).  -> (mean ms, min ms, launches)"""
+    import torch
+    p = batch.pipes[0]
+    torch.cuda.synchronize()
+    evs = []
+    for rep in range(2):
+        evs = []
+        for k, raw in enumerate(raws):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            p.apply_only(raw, out_imgs[k % len(out_imgs)], out_masks[k % len(out_masks)])
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
+    return sum(ts) / len(ts), min(ts), len(ts)
 
 
 def peak_hbm():
@@ -615,7 +645,7 @@ def ncu_traffic():
     return out
 
 
-def stage_rooflines(pipes):
+def stage_rooflines(pipes, alone=None):
     """Mean device time of every stage of the chain over the frames of the timed region (CUDA
     events recorded on the launching streams by FramePipeline), each against the measured HBM
     peak with SURVEY.md 8(d)'s algorithmic bytes.  -> (roofline of the dominant single kernel,
@@ -644,12 +674,25 @@ def stage_rooflines(pipes):
     if best is None:
         return None, stages
     kname = best['kernels'].split(' ')[0].split('<')[0]
-    roof = {'bound': 'hbm', 'kernel': best['kernels'], 'achieved': best['achieved'], 'peak': peak,
-            'unit': 'GB/s', 'frac': best['frac'], 'traffic': traffic.get(kname),
-            'ms_per_launch': best['ms_per_frame'], 'launches_timed': best['frames'],
-            'algorithmic_bytes': best['algorithmic_bytes'], 'peak_source': how,
-            'note': 'dominant single kernel by mean device time inside the timed region (several frames in '
-                    'flight: other streams\' kernels share the GPU during the launch)'}
+    in_pipe = {'ms_per_launch': best['ms_per_frame'], 'launches_timed': best['frames'], 'achieved': best['achieved'],
+               'frac': best['frac'],
+               'note': 'the same kernel between CUDA events INSIDE the timed region: a dozen frames are in flight and '
+                       'other streams\' kernels share the SMs and the HBM during the launch, so this is a share of a '
+                       'busy GPU, not the kernel\'s own speed'}
+    if alone is None or best['stage'] != 'apply':
+        roof = dict(in_pipe, bound='hbm', kernel=best['kernels'], peak=peak, unit='GB/s', traffic=traffic.get(kname),
+                    algorithmic_bytes=best['algorithmic_bytes'], peak_source=how)
+        return roof, stages
+    ms, ms_min, n = alone
+    ach = best['algorithmic_bytes'] / (ms * 1e-3) / 1e9
+    roof = {'bound': 'hbm', 'kernel': best['kernels'], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'frac': ach / peak, 'traffic': traffic.get(kname), 'ms_per_launch': ms, 'ms_min': ms_min,
+            'launches_timed': n, 'algorithmic_bytes': best['algorithmic_bytes'], 'peak_source': how,
+            'note': 'dominant single kernel of the chain (largest device time among the one-kernel stages), timed '
+                    'ALONE in bench.py: one launch per frame of the resident batch back to back on one stream, each '
+                    'between its own CUDA events, inputs larger than L2 (another 254 MB frame per launch); peak = the '
+                    'measured copy bandwidth (burst)',
+            'in_pipeline': in_pipe}
     return roof, stages
 
 

@@ -25,7 +25,7 @@ def main(rep, out_txt, out_json, note=''):
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(c) for c in COLS]
     ik = hdr.index('Kernel Name')
-    lines = ['ncu --set full --clock-control none, tools/one_frame.py (second frame), B200. ' + note, '',
+    lines = ['ncu --set full --clock-control none, B200. ' + note, '',
              '%-32s %9s %10s %10s %7s %7s %7s %7s %7s %5s %7s %6s %6s' % (
                  'kernel', 'time us', 'dram rd MB', 'dram wr MB', 'dram%', 'sm%', 'issue%', 'fp64%', 'warps%', 'regs',
                  'grid', 'block', 'L2hit%')]
