@@ -1278,7 +1278,7 @@ extern "C" int bbx_reduce_apply_stats(const void *raw, int raw_type, const bbx_g
                                       unsigned int seed_cap, int niter, void *lac_work, long long *lac_info, void *stream)
 {
     BBX_REQUIRE(g && raw && out_img && out_mask && bits && lac_work && lac_info, "bbx_reduce_apply_stats: null argument");
-    BBX_REQUIRE(niter > 0, "bbx_reduce_apply_stats: niter %d", niter);
+    BBX_REQUIRE(niter != 0, "bbx_reduce_apply_stats: niter %d", niter);
     const long long RW = (long long)g->nx * g->xsize_chan, RH = (long long)g->ny * g->ysize_chan;
     BBX_REQUIRE(RH * RW < 2147483647LL, "bbx_reduce_apply_stats: frame too large for 31-bit pixel indices");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1287,6 +1287,9 @@ extern "C" int bbx_reduce_apply_stats(const void *raw, int raw_type, const bbx_g
     ApplyArgs a = {vos_fit, oscan, mbias, mflat, bpm, satlevel, out_img, out_mask, bits->bad, bits->saturated,
                    seeds, seed_count, seed_cap, (unsigned int)(bits->saturated | bits->satcon)};
     SparseWork w = carve_sparse(lac_work, (size_t)(RH * RW));
+    if (niter < 0)              // the per-pixel kernel alone, with the bracket of an earlier call (for timing it)
+        return apply_launch(raw, raw_type, g, gain_h, vos_fit, oscan, mbias, mflat, bpm, satlevel, bits, out_img, out_mask,
+                            seeds, seed_count, seed_cap, w.bg, w.bghist, stream);
     BBX_CUDA(cudaMemsetAsync(w.bghist, 0, 4ull * BG_BINS, st));
     static bool attr_set = false;
     if (!attr_set) {

@@ -373,6 +373,34 @@ __device__ __forceinline__ void put_bits(uint32_t *buf, int pos, uint32_t value,
     if (lo) atomicOr(&buf[w + 1], lo);
 }
 
+// Bit writer of one lane: codes are appended MSB first to a 64-bit window; whole 32-bit words go
+// to the warp's cleared bit buffer by atomicOr (the first and the last word of a block are shared
+// with the neighbouring lanes' blocks).
+struct BitOut {
+    uint32_t *buf;
+    int w, n;                               // word index; n (< 32 between calls) pending bits at the top of acc
+    unsigned long long acc;
+    __device__ __forceinline__ void open(uint32_t *b, int pos) { buf = b; w = pos >> 5; n = pos & 31; acc = 0; }
+    __device__ __forceinline__ void flush_word()
+    {
+        const uint32_t hi = (uint32_t)(acc >> 32);
+        if (hi) atomicOr(&buf[w], hi);
+        w++; acc <<= 32; n -= 32;
+    }
+    __device__ __forceinline__ void put(uint32_t value, int nbits)             // 1 <= nbits <= 32
+    {
+        acc |= (unsigned long long)value << (64 - n - nbits);
+        n += nbits;
+        if (n >= 32) flush_word();
+    }
+    __device__ __forceinline__ void zeros(int nbits)
+    {
+        n += nbits;
+        while (n >= 32) flush_word();
+    }
+    __device__ __forceinline__ void close() { if (n > 0) { n += 32; flush_word(); } }
+};
+
 template <int BP> __device__ __forceinline__ int rice_signed(typename RiceP<BP>::T v)
 {
     // fits_rcomp_byte / _short / fits_rcomp see the pixels as signed char / short / int
@@ -383,16 +411,28 @@ template <int BP> __device__ __forceinline__ int rice_signed(typename RiceP<BP>:
 // quantised on the fly as fits_quantize_float does (SUBTRACTIVE_DITHER_1; zscale[tile] == 0 marks
 // a row that is not quantised: it gets no Rice-coded bytes) -- the int32 image never exists.
 template <int BP> struct PlainSrc {
-    static constexpr int AHEAD = 16;        // pixel loads of a lane in flight while a chunk is fetched
     const typename RiceP<BP>::T *img;
     int nx;
     const typename RiceP<BP>::T *row;
     __device__ __forceinline__ bool open(int tile, int) { row = img + (size_t)tile * nx; return true; }
     __device__ __forceinline__ int px(int x) { return rice_signed<BP>(row[x]); }
+    // the 1024 pixels from i0 on into vals (block k at vals[33 k]); pixels beyond the row repeat
+    // `lastpix`.  -> does any of them differ from lastpix?
+    __device__ __forceinline__ bool fill(int *vals, int i0, int lane, int lastpix)
+    {
+        bool differs = false;
+#pragma unroll 16
+        for (int k = 0; k < 32; k++) {
+            const int x = i0 + 32 * k + lane;
+            const int v = (x < nx) ? px(x) : lastpix;
+            differs |= v != lastpix;
+            vals[k * 33 + lane] = v;
+        }
+        return differs;
+    }
 };
 
 struct QuantSrc {
-    static constexpr int AHEAD = 8;
     const float *img;
     const double *zscale, *zzero;
     const float *rnd;
@@ -418,26 +458,79 @@ struct QuantSrc {
         return true;
     }
     // x never decreases from call to call (per lane)
-    __device__ __forceinline__ int px(int x)
+    __device__ __forceinline__ void advance(int x)
     {
         while (x - base >= RICE_NRANDOM - nextrand) {
             base += RICE_NRANDOM - nextrand;
             seed = seed + 1 == RICE_NRANDOM ? 0 : seed + 1;
             nextrand = (int)(rnd[seed] * 500.0f);
         }
-        // NINT((v - zero) / scale + R - 0.5), evaluated in double by CFITSIO.  Here first in float32:
-        // with Z = |zero| / scale the float value is off by less than (Z + 5 |x| + 3) 2^-24, which can
-        // change the integer only if x sits that close to a half-integer -- the guard is twice that,
-        // and the few pixels inside it (one in some thousands) take the double-precision statement.
-        const float pix = row[x], rr = rnd[nextrand + (x - base)];
+    }
+    // NINT((v - zero) / scale + R - 0.5) as CFITSIO evaluates it, in double
+    __device__ __forceinline__ int exact(float pix, float rr) const
+    {
+        const double v = ((double)pix - zero) / scale + (double)rr - 0.5;
+        return (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+    }
+    // The same in float32 first: with Z = |zero| / scale the float value is off by less than
+    // (Z + 5 |x| + 3) 2^-24, which can change the integer only if x sits that close to a
+    // half-integer -- the guard is twice that, and the few pixels inside it (one in some thousands)
+    // take the double-precision statement (`unsure`).
+    __device__ __forceinline__ int quick(float pix, float rr, bool &unsure) const
+    {
         const float xf = (pix - zero_f) * inv_f + rr - 0.5f;
         const float g = guard0 + fabsf(xf) * 9.5367431640625e-07f;               // 8 * 2^-23
         const float yf = xf + 0.5f, ff = yf - floorf(yf);
-        if (ff < g || ff > 1.0f - g) {
-            const double v = ((double)pix - zero) / scale + (double)rr - 0.5;
-            return (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+        unsure = ff < g || ff > 1.0f - g;
+        return (int)(xf + copysignf(0.5f, xf));
+    }
+    __device__ __forceinline__ int px(int x)
+    {
+        advance(x);
+        const float pix = row[x], rr = rnd[nextrand + (x - base)];
+        bool unsure;
+        const int v = quick(pix, rr, unsure);
+        return unsure ? exact(pix, rr) : v;
+    }
+    __device__ __forceinline__ bool fill(int *vals, int i0, int lane, int lastpix)
+    {
+        bool differs = false;
+        const int x0 = i0 + lane;
+        bool straight = i0 + RENC_CHUNK <= nx;
+        if (straight) {
+            advance(x0);
+            straight = (x0 + 31 * 32 - base) < RICE_NRANDOM - nextrand;          // no restart of the sequence inside
         }
-        return (xf >= 0.f) ? (int)(xf + 0.5f) : (int)(xf - 0.5f);
+        if (__all_sync(0xffffffffu, straight)) {
+            // a full chunk, one run of the random sequence: straight-line code, the unsure pixels afterwards
+            const float *rp = rnd + (nextrand - base);
+            unsigned int redo = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const int x = x0 + 32 * k;
+                bool unsure;
+                const int v = quick(row[x], rp[x], unsure);
+                redo |= (unsigned int)unsure << k;
+                differs |= v != lastpix;
+                vals[k * 33 + lane] = v;
+            }
+            while (redo) {
+                const int k = __ffs(redo) - 1, x = x0 + 32 * k;
+                redo &= redo - 1;
+                const int v = exact(row[x], rp[x]);
+                differs |= v != lastpix;
+                vals[k * 33 + lane] = v;
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < 32; k++) {
+                const int x = x0 + 32 * k;
+                const int v = (x < nx) ? px(x) : lastpix;
+                differs |= v != lastpix;
+                vals[k * 33 + lane] = v;
+            }
+        }
+        return differs;
     }
 };
 
@@ -475,14 +568,7 @@ rice_encode_kernel(SRC src, int ntiles, int nx, uint8_t *__restrict__ scratch, s
         for (int i0 = 0; i0 < nx; i0 += RENC_CHUNK) {
             // ---- the chunk's pixel values, block k in vals[33 k ..]
             if (i0 == 0) lastpix = src.px(0);            // the first pixel: block 0 starts with difference 0
-            bool differs = false;
-#pragma unroll SRC::AHEAD
-            for (int k = 0; k < 32; k++) {
-                const int x = i0 + 32 * k + lane;
-                const int v = (x < nx) ? src.px(x) : lastpix;
-                differs |= v != lastpix;
-                vals[k * 33 + lane] = v;
-            }
+            const bool differs = src.fill(vals, i0, lane, lastpix);
             if (i0 == 0) {
                 // the first pixel of the tile as it is
                 if (BP == 4) {
@@ -554,26 +640,26 @@ rice_encode_kernel(SRC src, int ntiles, int nx, uint8_t *__restrict__ scratch, s
                 total = cbits + __shfl_sync(FULL, incl, 31);
                 int pos = cbits + incl - nbits;
                 if (nthis > 0 && sum != 0) {
-                    put_bits(buf, pos, raw ? (uint32_t)(P::FSMAX + 1) : (uint32_t)(fs + 1), P::FSBITS);
-                    pos += P::FSBITS;
+                    BitOut out;
+                    out.open(buf, pos);
+                    out.put(raw ? (uint32_t)(P::FSMAX + 1) : (uint32_t)(fs + 1), P::FSBITS);
                     if (raw) {
 #pragma unroll 8
                         for (int j = 0; j < nthis; j++) {
                             const uint32_t d = (uint32_t)mine[j];
-                            put_bits(buf, pos, BP == 4 ? d : (d & ((1u << (P::BBITS & 31)) - 1u)), P::BBITS);
-                            pos += P::BBITS;
+                            out.put(BP == 4 ? d : (d & ((1u << (P::BBITS & 31)) - 1u)), P::BBITS);
                         }
                     } else {
-                        // a code = (diff >> FS) zeros (the cleared buffer), a one, the low FS bits
+                        // a code = (diff >> FS) zeros, a one, the low FS bits
                         const uint32_t low = (1u << fs) - 1u;
 #pragma unroll 8
                         for (int j = 0; j < nthis; j++) {
                             const uint32_t d = (uint32_t)mine[j];
-                            const int top = (int)(d >> fs);
-                            put_bits(buf, pos + top, (1u << fs) | (d & low), fs + 1);
-                            pos += top + fs + 1;
+                            out.zeros((int)(d >> fs));
+                            out.put((1u << fs) | (d & low), fs + 1);
                         }
                     }
+                    out.close();
                 }
                 __syncwarp();
             }

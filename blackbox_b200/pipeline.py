@@ -335,14 +335,16 @@ class FramePipeline:
         run('status', status)
 
     def apply_only(self, raw_t, out_img, out_mask):
-        """Enqueue ONLY the fused per-pixel pass (gain, overscan, master bias, mask seed, master flat;
-        with the background statistics if the pipeline takes them there) with the overscan state of
-        the last frame this pipeline saw: for timing the kernel on its own (bench.py's roofline)."""
+        """Enqueue ONLY the kernel of the fused per-pixel pass (gain, overscan, master bias, mask seed,
+        master flat; with the background statistics if the pipeline takes them there) with the
+        overscan state and the statistics bracket of the last frame this pipeline saw: for timing the
+        kernel on its own (bench.py's roofline).  The outputs are those of a frame; the statistics
+        in the work buffer are not (they keep accumulating)."""
         self._check_frame(raw_t, out_img, out_mask)
         if self.stats_in_apply and self.niter > 0 and R.fusable(self.geom, raw_t, out_img, out_mask, self.mbias,
                                                                 self.mflat, self.bpm, self.crmask):
             R.apply_stats_enqueue(raw_t, self.geom, self.tel, self.st, self._gain_for(raw_t), self.mbias, self.mflat,
-                                  self.bpm, out_img, out_mask, self.mwork, self.niter, self.lwork)
+                                  self.bpm, out_img, out_mask, self.mwork, -1, self.lwork)
         else:
             R.apply_enqueue(raw_t, self.geom, self.tel, st=self.st, gain=self._gain_for(raw_t), mbias=self.mbias,
                             mflat=self.mflat, bpm=self.bpm, want_mask=True, out_img=out_img, out_mask=out_mask,

@@ -169,7 +169,9 @@ int bbx_reduce_apply_scan(const void *raw, int raw_type, const bbx_geom *g, cons
  * registers, so that LACosmic's dense scan is the Laplacian alone (no mask read, no key
  * arithmetic).  Does what bbx_lacosmic_begin does.  Afterwards: bbx_mask_morph_sparse_track (corrects
  * the statistics for the pixels it masks), bbx_lacosmic_iteration(..., mode 4), bbx_lacosmic_finish
- * (mode 0).  Bit-identical to the separate calls.  Needs the 4-pixel-aligned layout. */
+ * (mode 0).  Bit-identical to the separate calls.  Needs the 4-pixel-aligned layout.
+ * niter < 0: ONLY the per-pixel kernel, with the bracket an earlier call left in lac_work (no
+ * set-up kernels; the statistics keep accumulating) -- for timing that kernel on its own. */
 int bbx_reduce_apply_stats(const void *raw, int raw_type, const bbx_geom *g, const float *gain_h,
                            const double *vos_fit, const double *oscan, const float *mbias,
                            const float *mflat, const uint8_t *bpm, const double *satlevel,
