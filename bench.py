@@ -370,7 +370,19 @@ def run_gpu(args, rank, world, local_rank):
         del raws[2:]                       # the stacks need the room of the resident night batch
         torch.cuda.empty_cache()
         masters = measure_master_sharded(args, rank, world, dev, barrier)
-    link = measure_link(dev) if (rank == 0 and not args.no_e2e) else None
+    # the link ceiling of the end-to-end number: every rank copies at the same time (at N > 1 the
+    # ranks share the host's memory system), rank 0 reports its own figures and the sum over ranks
+    link = None
+    if not args.no_e2e:
+        barrier()
+        link = measure_link(dev)
+        if world > 1:
+            both = torch.tensor([link['both_each_GBs']], dtype=torch.float64, device=dev)
+            lo = both.clone()
+            dist.all_reduce(both, op=dist.ReduceOp.SUM)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            link['all_ranks_concurrently'] = {'ranks': world, 'both_each_GBs_sum': float(both.item()),
+                                              'both_each_GBs_min': float(lo.item())}
 
     if rank == 0:
         cpu = None
