@@ -444,9 +444,14 @@ def write_compressed(path, heap, lengths, shape, zbitpix, header=None, zscale=No
             _card('ZNAME2', 'BYTEPIX'), _card('ZVAL2', abs(zbitpix) // 8)]
     if zbitpix == -32:
         ext += [_card('ZQUANTIZ', 'SUBTRACTIVE_DITHER_1'), _card('ZDITHER0', int(zdither0))]
-    skip = {'SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'END', 'EXTEND', 'XTENSION', 'PCOUNT', 'GCOUNT', 'TFIELDS'}
+    # keywords that describe the layout of whatever file the header came from (a raw frame's
+    # BZERO 32768 on a float image would be applied by every reader) stay behind
+    skip = {'SIMPLE', 'BITPIX', 'NAXIS', 'NAXIS1', 'NAXIS2', 'END', 'EXTEND', 'XTENSION', 'PCOUNT', 'GCOUNT', 'TFIELDS',
+            'BSCALE', 'BZERO', 'THEAP', 'CHECKSUM', 'DATASUM', 'ZHECKSUM', 'ZDATASUM'}
     for key, val in (header.items() if header is not None else ()):
-        if str(key).upper() in skip or str(key).upper() in ('COMMENT', 'HISTORY'):
+        ku = str(key).upper()
+        if ku in skip or ku in ('COMMENT', 'HISTORY') or ku.startswith(('TTYPE', 'TFORM', 'ZNAME', 'ZVAL', 'ZTILE', 'ZNAXIS')) \
+                or ku in ('ZIMAGE', 'ZSIMPLE', 'ZEXTEND', 'ZBITPIX', 'ZCMPTYPE', 'ZQUANTIZ', 'ZDITHER0', 'ZBLANK', 'ZSCALE', 'ZZERO'):
             continue
         value, comment = (val if isinstance(val, tuple) and len(val) == 2 else (val, ''))
         ext.append(_card(key, value, comment))

@@ -534,7 +534,8 @@ class BatchReducer:
         big-endian 16-bit data unit of a raw frame (BZERO 32768; ``fitsio.read_primary(...,
         pinned=True)`` reshaped to the frame, any 2-byte dtype), ``host_imgs`` receives the
         big-endian float32 data unit of the reduced image (``fitsio.write_primary(..., be_bytes=True)``).
-        The byte swaps run on the device, in place, next to the copies.
+        The byte swaps run on the device, in place, next to the copies.  (With ``img_fz`` only the
+        input side applies.)
 
         ``mask_fz``: the mask leaves the device Rice-coded -- the losslessly fpacked uint8 image the
         reference writes (``fpack -D -Y``, blackbox.py:826-827, 1990); ``host_masks`` are then pinned
@@ -600,8 +601,6 @@ class BatchReducer:
                     raise ValueError('mask_fz: host mask buffers must be equal-sized pinned uint8 buffers of at '
                                      'least mask_fz_bytes(0) + 16 bytes')
         if img_fz:
-            if fits:
-                raise ValueError('img_fz: the image leaves as a compressed table, fits=True does not apply')
             want_i = host_imgs[0].numel()
             if getattr(self, '_fz_img', None) is None or self._fz_img[0].out_bytes != want_i:
                 self._fz_img = [R.FpackEncoder((RH, RW), dev, 16.0, out_bytes=want_i) for _ in range(d)]
@@ -627,7 +626,7 @@ class BatchReducer:
             j = k % d
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(self._ev_done[j])
-                if fits:
+                if fits and not img_fz:
                     img = self._hbuf[j][1]
                     call('bbx_fits_encode', R._ptr(img), -32, 0, img.numel(), R._ptr(img), R._stream())
                 if img_fz:

@@ -552,3 +552,48 @@ def test_run_host_writes_the_image_as_fpack_q16(tmp_path, small_bb):
     assert (err <= 0.5 * p['zscale'][:, None] * (1 + 1e-6) + 1e-3).all()
     assert os.path.getsize(path) < imgs[3].numel() * 4 // 3
     assert hdr['NCOSMICS'] == want[3].header['NCOSMICS']
+
+
+@pytest.mark.gpu
+def test_reduce_night_tool_with_fpacked_files_on_both_sides(small_bb, tmp_path):
+    """tools/reduce_night.py --fpack on a directory of .fits.fz raw frames with fpacked masters:
+    _red.fits.fz / _mask.fits.fz come out; the mask equals the oracle's chain, the image is the
+    oracle's image to within half a quantisation step (a sixteenth of the row noise), the header
+    keywords of the reduction steps are in the files and the raw frame's BZERO is not."""
+    import importlib.util
+    from blackbox_b200 import fitsio, reduce as bbr, set_bb, synth
+    from oracle import reduce as R, rice
+    tel, ysc = 'BG3', 120
+    small_bb(ysc)
+    shape = (2 * ysc, 8 * set_bb.xsize_chan)
+    raw_dir, out_dir = tmp_path / 'raw', tmp_path / 'red'
+    raw_dir.mkdir()
+    raws = [synth.make_raw(tel, 4800 + k, nstars=100, ncosmics=60)[0] for k in range(5)]
+    mbias, mflat, bpm = synth.make_masters(tel, 4800, shape)
+    victim, source, corr, coeffs = synth.make_xtalk(4802)
+    for k, r in enumerate(raws):
+        rice.write_fz(str(raw_dir / 'BG3_2026_{:02d}.fits.fz'.format(k)), r, {'EXPTIME': 45.0 + k, 'FILTER': 'q'})
+    fitsio.write_primary(str(tmp_path / 'mbias.fits'), mbias)
+    fitsio.write_primary(str(tmp_path / 'mflat.fits'), mflat)
+    rice.write_fz_u8(str(tmp_path / 'bpm.fits.fz'), bpm)
+    synth.write_xtalk_file(str(tmp_path / 'xtalk.txt'), victim, source, corr)
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('reduce_night', os.path.join(here, 'tools', 'reduce_night.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    n = tool.main([str(raw_dir), str(out_dir), '--tel', tel, '--mbias', str(tmp_path / 'mbias.fits'),
+                   '--mflat', str(tmp_path / 'mflat.fits'), '--bpm', str(tmp_path / 'bpm.fits.fz'),
+                   '--xtalk', str(tmp_path / 'xtalk.txt'), '--niter', '2', '--fpack', '--chunk', '2'])
+    assert n == 5
+    for k, r in enumerate(raws):
+        data_o, mask_o, hdr_o, _ = R.reduce_frame(r, tel, mbias, mflat, bpm, coeffs, niter=2)
+        red = str(out_dir / 'BG3_2026_{:02d}_red.fits.fz'.format(k))
+        ci = fitsio.read_compressed(red)
+        assert ci.info['bitpix'] == -32 and ci.info['zdither0'] == 1 + k and ci.info['bzero'] == 0.0
+        h, img = bbr.read_fits_image(red)
+        _, m = bbr.read_fits_image(str(out_dir / 'BG3_2026_{:02d}_mask.fits.fz'.format(k)))
+        assert np.mean(m.cpu().numpy() != mask_o) <= 1e-5
+        err = np.abs(img.cpu().numpy() - data_o)
+        assert np.mean(err <= 0.5 * ci.zscale[:, None] * (1 + 1e-6) + 1e-3) > 0.999
+        assert h['FILTER'] == 'q' and h['REDFILE'].endswith('_red') and h['EXPTIME'] == 45.0 + k
+        assert h['BIASMEAN'] == pytest.approx(hdr_o['BIASMEAN'], rel=1e-9) and h['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
