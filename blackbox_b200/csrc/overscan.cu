@@ -610,7 +610,7 @@ template <> __device__ __forceinline__ float raw_to_f32_alu<float>(float v) { re
 // the sample is unrepresentative) the evaluation is "band moments + the listed values inside
 // the bounds"; otherwise, or if a list overflows, it walks the strip again.
 template <typename T>
-__global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS, 1)
+__global__ void __cluster_dims__(VSTD_CLUSTER, 1, 1) __launch_bounds__(VSTD_THREADS, 2)
 vos_std_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain,
                const double *__restrict__ vos_fit, const double *__restrict__ dlevel_arr,
                double *__restrict__ out_std)
