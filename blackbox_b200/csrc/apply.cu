@@ -115,7 +115,10 @@ reduce_apply_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyAr
 // those below the bracket, the histogram inside it: lacosmic_sparse.cu) while the values are in
 // registers -- against the seed mask; the mask morphology that follows corrects them for the pixels
 // it masks (bg_track.cuh).  The dense Laplacian scan then reads neither the mask nor computes keys.
-template <typename T, bool STATS>
+// FULL: every optional input and output is there (overscan vectors, master bias and flat, bad-pixel
+// mask, saturation levels, mask and seed list: the pipeline's case) -- a compile-time fact, so the
+// per-pixel code carries no tests of pointers (a tenth of the generic kernel's instructions).
+template <typename T, bool STATS, bool FULL>
 __global__ void __launch_bounds__(APPLY_THREADS, 8)
 reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, ApplyArgs a, BgState *bg,
                           unsigned int *__restrict__ bghist)
@@ -130,8 +133,10 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
     if (x >= RW) return;
     const int c = x / g.xsize_chan, lx = x - c * g.xsize_chan;
     const int ya = blockIdx.y * APPLY_ROWS, yb = min(ya + APPLY_ROWS, RH);
-    const bool have_mask = a.out_mask != nullptr;
-    const bool has_bias = a.mbias != nullptr, has_flat = a.mflat != nullptr;
+    const bool have_mask = FULL || a.out_mask != nullptr;
+    const bool has_bias = FULL || a.mbias != nullptr, has_flat = FULL || a.mflat != nullptr;
+    const bool has_bpm = FULL || a.bpm != nullptr, has_fit = FULL || a.vos_fit != nullptr;
+    const bool has_osc = FULL || a.oscan != nullptr, has_seeds = FULL || a.seeds != nullptr;
     int r_cur = -1;
     double osc[4] = {0.0, 0.0, 0.0, 0.0};
     float gn = 1.0f, satl = 0.0f;
@@ -155,8 +160,8 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
         in.mm = 0;
         if (has_bias) in.mb = __ldcs(reinterpret_cast<const float4 *>(a.mbias + oo));
         if (has_flat) in.mf = __ldcs(reinterpret_cast<const float4 *>(a.mflat + oo));
-        if (a.bpm) in.mm = __ldcs(reinterpret_cast<const unsigned int *>(a.bpm + oo));
-        in.fitv = a.vos_fit ? a.vos_fit[(size_t)(r * g.nx + c) * g.dy + (rr - r * g.dy)] : 0.0;
+        if (has_bpm) in.mm = __ldcs(reinterpret_cast<const unsigned int *>(a.bpm + oo));
+        in.fitv = has_fit ? a.vos_fit[(size_t)(r * g.nx + c) * g.dy + (rr - r * g.dy)] : 0.0;
     };
     auto finish_row = [&](int y, const RowIn &in) {
         const int r = (y >= g.ysize_chan) ? 1 : 0;
@@ -164,11 +169,11 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
             r_cur = r;
             const int ch = r * g.nx + c;
             gn = gain.v[ch];
-            if (a.oscan) {
+            if (has_osc) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) osc[k] = a.oscan[(size_t)ch * g.xsize_chan + lx + k];
             }
-            has_sat = have_mask && a.satlevel != nullptr;
+            has_sat = have_mask && (FULL || a.satlevel != nullptr);
             if (has_sat) {
                 const double lv = a.satlevel[ch];
                 if (lv != lv) has_sat = false;     // NaN level: the comparison is never true
@@ -196,7 +201,7 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
             v[k] = w;
             mout |= m << (8 * k);
         }
-        if (a.seeds && any_seed) {
+        if (has_seeds && any_seed) {
             // pixels found saturated (type 0) and pixels whose bad-pixel mask already carries a
             // saturated / saturated-connected bit (type 1, bit 31) seed the sparse morphology
 #pragma unroll
@@ -338,11 +343,17 @@ int apply_launch(const void *raw, int raw_type, const bbx_geom *g, const float *
         BgState *bg = (BgState *)bg_state;
         if (bg) {
             BBX_REQUIRE(out_mask != nullptr && bghist != nullptr, "bbx_reduce_apply: statistics need the mask output");
-            if (raw_type == BBX_RAW_U16) reduce_apply_strip_kernel<uint16_t, true><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, bg, bghist);
-            else reduce_apply_strip_kernel<float, true><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, bg, bghist);
+            const bool full = vos_fit && oscan && mbias && mflat && bpm && satlevel && seeds;
+            if (raw_type == BBX_RAW_U16) {
+                if (full) reduce_apply_strip_kernel<uint16_t, true, true><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, bg, bghist);
+                else reduce_apply_strip_kernel<uint16_t, true, false><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, bg, bghist);
+            } else reduce_apply_strip_kernel<float, true, false><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, bg, bghist);
         } else {
-            if (raw_type == BBX_RAW_U16) reduce_apply_strip_kernel<uint16_t, false><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, nullptr, nullptr);
-            else reduce_apply_strip_kernel<float, false><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, nullptr, nullptr);
+            const bool full = vos_fit && oscan && mbias && mflat && bpm && satlevel && seeds && out_mask;
+            if (raw_type == BBX_RAW_U16) {
+                if (full) reduce_apply_strip_kernel<uint16_t, false, true><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, nullptr, nullptr);
+                else reduce_apply_strip_kernel<uint16_t, false, false><<<grid, APPLY_THREADS, 0, s>>>((const uint16_t *)raw, *g, gn, a, nullptr, nullptr);
+            } else reduce_apply_strip_kernel<float, false, false><<<grid, APPLY_THREADS, 0, s>>>((const float *)raw, *g, gn, a, nullptr, nullptr);
         }
         BBX_CHECK_LAUNCH("bbx_reduce_apply");
         return 0;
