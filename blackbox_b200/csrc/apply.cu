@@ -195,12 +195,13 @@ reduce_apply_strip_kernel(const T *__restrict__ raw, bbx_geom g, ChanF32 gain, A
             if (have_mask) {
                 if (!isfinite(w)) { w = 0.f; if (m == 0) m |= (uint32_t)a.bit_bad; }
                 if (has_sat && w >= satl) m |= (uint32_t)(a.bit_sat | BBX_TMP_SAT);
-                any_seed |= (m & (BBX_TMP_SAT | a.seed_bits)) != 0;
             }
             if (has_flat) w = w / mf[k];
             v[k] = w;
             mout |= m << (8 * k);
         }
+        // (one test for the four mask bytes of the row)
+        any_seed = have_mask && (mout & (((uint32_t)(BBX_TMP_SAT | a.seed_bits) & 0xffu) * 0x01010101u)) != 0;
         if (has_seeds && any_seed) {
             // pixels found saturated (type 0) and pixels whose bad-pixel mask already carries a
             // saturated / saturated-connected bit (type 1, bit 31) seed the sparse morphology
