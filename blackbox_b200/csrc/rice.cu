@@ -357,21 +357,11 @@ extern "C" int bbx_unquantize(const int32_t *q, int ntiles, int nx, const double
 // FSBITS + 32 (FSMAX - 1 + 1) + 80 bits, a raw one FSBITS + 32 BBITS:
 //   BYTEPIX 1: 275 bits (35 B)   BYTEPIX 2: 532 bits (67 B)   BYTEPIX 4: 1029 bits (129 B)
 // The encoder's bit buffer holds 32 blocks and at most 31 carried bits in front: 1031 words (+ the
-// word put_bits may touch behind its last bit).
+// word the last lane's window may flush behind its last bit).
 #define RENC_WARPS 4
 #define RENC_CHUNK (32 * RICE_BLOCK)    // pixels a warp codes at a time: one block per lane
 #define RENC_WORDS 1034
 __host__ __device__ static inline int rice_block_bytes(int bp) { return bp == 1 ? 35 : bp == 2 ? 67 : 129; }
-
-// OR the `nbits` (1..32) low bits of `value` into a cleared MSB-first bit buffer at bit `pos`
-__device__ __forceinline__ void put_bits(uint32_t *buf, int pos, uint32_t value, int nbits)
-{
-    const int w = pos >> 5, off = pos & 31;
-    const unsigned long long v = (unsigned long long)value << (64 - off - nbits);       // off + nbits <= 63
-    atomicOr(&buf[w], (uint32_t)(v >> 32));
-    const uint32_t lo = (uint32_t)v;
-    if (lo) atomicOr(&buf[w + 1], lo);
-}
 
 // Bit writer of one lane: codes are appended MSB first to a 64-bit window; whole 32-bit words go
 // to the warp's cleared bit buffer by atomicOr (the first and the last word of a block are shared

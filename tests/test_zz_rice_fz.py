@@ -597,3 +597,18 @@ def test_reduce_night_tool_with_fpacked_files_on_both_sides(small_bb, tmp_path):
         assert np.mean(err <= 0.5 * ci.zscale[:, None] * (1 + 1e-6) + 1e-3) > 0.999
         assert h['FILTER'] == 'q' and h['REDFILE'].endswith('_red') and h['EXPTIME'] == 45.0 + k
         assert h['BIASMEAN'] == pytest.approx(hdr_o['BIASMEAN'], rel=1e-9) and h['NOBJ-SAT'] == hdr_o['NOBJ-SAT']
+
+
+def test_fpack_output_layout_is_what_the_host_side_parses():
+    """The size / offset entry points of bbx_fpack_f32 are host code (no GPU): the table columns sit
+    where reduce.FpackEncoder.parse looks for them, the always-fitting output size is columns +
+    one fixed-stride row per tile, and the scratch is the Rice encoder's for BYTEPIX 4."""
+    from blackbox_b200._lib import query
+    for H, W in ((1, 1), (7, 33), (240, 10560), (10560, 10560)):
+        off = query('bbx_fpack_f32_heap_offset', H)
+        assert off == 16 + (4 * H + 15) // 16 * 16 + 2 * ((8 * H + 15) // 16 * 16) and off % 16 == 0
+        nblocks = (W + 31) // 32
+        stride = (4 + nblocks * 129 + 8 + 15) // 16 * 16
+        assert query('bbx_fpack_f32_out_bytes', H, W) == off + H * stride
+        assert query('bbx_fpack_f32_work_bytes', H, W) == query('bbx_rice_encode_work_bytes', H, W, 4) >= H * stride
+    assert query('bbx_fpack_f32_out_bytes', 0, 5) == 0 and query('bbx_fpack_f32_heap_offset', 0) == 0
