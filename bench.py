@@ -396,7 +396,12 @@ def run_gpu(args, rank, world, local_rank):
             'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args), 'roofline': roof, 'roofline_stages': stages, 'cpu_baseline': cpu,
+            'config': workload_config(args), 'roofline': roof, 'roofline_stages': stages,
+            'roofline_stages_note': 'ms_per_frame = device time between CUDA events around the stage INSIDE the timed '
+                                    'region, %d frames in flight: the stages of different frames share the GPU, so the '
+                                    'figures add up to several times the frame time (ms_per_step / frames); kernels '
+                                    'timed alone: profiles/r02_kbench.txt, r02_ncu_full_summary.txt' % args.depth,
+            'cpu_baseline': cpu,
             'clocks': clocks, 'e2e': e2e, 'e2e_f32_image': e2e_f32, 'e2e_uncompressed': e2e_plain,
             'gpu_launches': launches,
             'chain_hbm_frac': (ALGO_BYTES_CHAIN_4IT * frames / world / (ms_total * 1e-3)) / (peak_hbm()[0] * 1e9),
