@@ -180,6 +180,29 @@ def check_rice(report):
                     for r in range(mask.shape[0]))
         report.append(('CFITSIO Rice coder (fpack, 8 bit)', 'encoder writes fpack\'s bytes: {}'.format(same8), None))
         ok = ok and same8
+        # fpack -q 16 of a float image (blackbox.py:836): ZSCALE / ZZERO per row do not depend on the
+        # dither seed (fpack draws it from the clock), so they pin fits_quantize_float + FnNoise5_float
+        # exactly; the integers are compared with the oracle's for the ZDITHER0 fpack chose
+        rng = np.random.default_rng(77)
+        img = (rng.normal(300, 12, (48, 1056)) + np.linspace(0, 40, 1056)[None, :]).astype(np.float32)
+        img[5] = np.round(img[5])                      # ties: the differences' skip rules
+        img[6, 100:400] = 17.0                         # a constant run
+        fplain = os.path.join(d, 'red.fits')
+        fitsio.write_primary(fplain, img)
+        subprocess.check_call([fpack, '-q', '16', '-D', '-Y', fplain])
+        ci = fitsio.read_compressed(fplain + '.fz')
+        heap = np.asarray(ci.heap)
+        same_scale = same_ints = True
+        for r in range(img.shape[0]):
+            q, sc, ze = rice.fpack_quantize_row(img[r], r, 16.0, ci.info['zdither0'])
+            same_scale = same_scale and q is not None and sc == ci.zscale[r] and ze == ci.zzero[r]
+            if q is not None and r not in ci.fallback:
+                got = rice.decode_tile(heap[ci.offsets[r]:ci.offsets[r] + ci.lengths[r]].tobytes(), img.shape[1], 4)
+                same_ints = same_ints and np.array_equal(np.asarray(got).astype(np.int64).astype(np.int32), q)
+        report.append(('CFITSIO quantiser (fpack -q 16)', 'ZSCALE / ZZERO of every row equal: {}; quantised integers equal: {}'.format(
+            same_scale, same_ints), None if same_scale else 'oracle/rice.py: fn_noise5_row / fpack_quantize_row (float32 against double arithmetic of '
+                                                            'the differences, the d2 array length, the zero-point rule)'))
+        ok = ok and same_scale and same_ints
         if funpack:
             # our writer's file through funpack
             tiles = [rice.encode_tile(mask[r], 1) for r in range(mask.shape[0])]
@@ -190,6 +213,14 @@ def check_rice(report):
             good = np.array_equal(np.asarray(back), mask)
             report.append(('fitsio.write_compressed -> funpack', 'round trip: {}'.format(good), None))
             ok = ok and good
+            # and a float image as the oracle's writer lays it out (bbx_fpack_f32 writes the same table)
+            fours = os.path.join(d, 'ours_red.fits.fz')
+            _, back_want = rice.write_fz_f32(fours, img, zdither0=4321)
+            subprocess.check_call([funpack, fours])
+            _, fback, finfo = fitsio.read_primary(fours[:-3])
+            fgood = np.array_equal(fitsio.to_native(fback, finfo), back_want)
+            report.append(('float .fits.fz (ZSCALE / ZZERO / ZDITHER0) -> funpack', 'values as un-quantised here: {}'.format(fgood), None))
+            ok = ok and fgood
     return ok
 
 
